@@ -1,0 +1,240 @@
+/*
+ * vsr_b200.h — C-ABI of libvsr_sm100.so: the sm_100a kernels under the drop-in SR nets.
+ *
+ * The reference (yangsenwxy/VSR) has no FFI for this path: its nets call torch.nn modules
+ * (src/model/nets/drf_net.py:55-106,141-147), which dispatch to ATen/cuDNN.  Every entry
+ * point below states which reference call site(s) it replaces.  INTEGRATION.md shows the
+ * ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no torch / C++ types cross this boundary.
+ *  - every device buffer (including workspaces) is owned by the caller; the library allocates
+ *    nothing on the device and keeps only host-side caches (TMA descriptors).
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*), never
+ *    synchronises, and is CUDA-graph capturable.
+ *  - return value: 0 on success, a negative VsrStatus otherwise; vsr_last_error() gives text.
+ *    Nothing throws or exits across the ABI.
+ *
+ * Feature-map layout ("pixel-major"): dense [n][h][w][c], c contiguous.  A high-resolution map
+ * of upscale r is kept *phase-blocked*: the r*r sub-pixels of low-resolution pixel (y,x) are
+ * stored as r*r consecutive channel groups of that pixel, i.e. as a [n][h][w][r*r*C] map, so
+ * that nn.PixelShuffle (drf_net.py:142,146) is a reinterpretation, the transposed convolution
+ * (drf_net.py:81,93) is a dense GEMM into channel slices, and the strided convolution
+ * (drf_net.py:86,100) reads channel slices of neighbouring low-resolution pixels.
+ */
+#ifndef VSR_B200_H_
+#define VSR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VSR_ABI_VERSION 1
+#define VSR_MAX_SRCS 8
+
+typedef enum VsrStatus {
+  VSR_OK = 0,
+  VSR_ERR_BAD_ARG = -1,
+  VSR_ERR_UNSUPPORTED = -2,
+  VSR_ERR_CUDA = -3,
+  VSR_ERR_DRIVER = -4
+} VsrStatus;
+
+typedef enum VsrDType { VSR_F32 = 0, VSR_BF16 = 1 } VsrDType;
+
+/* epilogue flags of the tap-GEMM (applied in this order) */
+enum {
+  VSR_EPI_BIAS = 1,       /* v += bias[o]                                              */
+  VSR_EPI_RES_PRE = 2,    /* v += residual[pix][o]        (before the activation)      */
+  VSR_EPI_PRELU = 4,      /* v = v > 0 ? v : a*v          (nn.PReLU, scalar a)         */
+  VSR_EPI_RELU = 8,       /* v = max(v, 0)                                             */
+  VSR_EPI_PRELU_BWD = 16, /* y=aux_y: v = y>0 ? v : a*v ; slope grad += v_in * y/a     */
+  VSR_EPI_RELU_BWD = 32,  /* y=aux_y: v = y>0 ? v : 0                                  */
+  VSR_EPI_OUT2 = 64,      /* out2[pix][o] = v + res2[pix][o]   (after the activation)  */
+  VSR_EPI_SCALE = 128     /* v *= out_scale   (after bias, before the residual)        */
+};
+
+typedef struct VsrTensor4 {
+  void* ptr;        /* device pointer, 16-byte aligned */
+  int32_t n, h, w, c;
+} VsrTensor4;
+
+/*
+ * Tap-GEMM: for every output pixel (n,y,x) of `out` and every group g
+ *   out[n,y,x, o0_g + j] = epi( sum_{t in taps(g)} sum_{k<kc}
+ *                               srcs[t.src][n, y+t.dy, x+t.dx, t.c0 + k] * w[t][j][k] ),  j < nt
+ * with zero for out-of-range source pixels.  All srcs and out share n,h,w.
+ * Replaces, with the right tap tables: nn.Conv2d 1x1 on torch.cat (drf_net.py:57,65,90,97,105,
+ * 119-131: the cat is never materialised, each cat operand is one tap), nn.Conv2d 3x3
+ * (drf_net.py:141,144,147), nn.ConvTranspose2d k,s=r,p=2 (drf_net.py:81,93), nn.Conv2d k,s=r,p=2
+ * (drf_net.py:86,100), and the data-gradient of each of them.
+ *
+ * group_tab: int32[n_groups][4] = {o0, tap_begin, n_taps, reserved}
+ * tap_tab:   int32[n_taps_total][4] = {src, dy, dx, c0}
+ * w:         n_taps_total slabs of [nt][kc]; VSR_F32: plain row-major fp32;
+ *            VSR_BF16: bf16, each slab in the 128-byte-swizzled K-major shared-memory image
+ *            (16-byte chunk q of row j stored at chunk q ^ (j & 7)); see vsr_slab_index().
+ */
+typedef struct VsrTapGemmDesc {
+  int32_t dtype; /* VsrDType of srcs / out / residual / aux / w */
+  int32_t kc;    /* channels per tap                (BF16: 64) */
+  int32_t nt;    /* output channels per group       (BF16: multiple of 16, <= 256) */
+  int32_t n_srcs;
+  VsrTensor4 srcs[VSR_MAX_SRCS];
+  VsrTensor4 out;
+  int32_t n_groups;
+  int32_t n_taps_total;
+  const int32_t* group_tab; /* device */
+  const int32_t* tap_tab;   /* device */
+  const void* w;            /* device */
+  const float* bias;        /* device, [out.c] fp32, or NULL */
+  int32_t epi;              /* VSR_EPI_* flags */
+  float out_scale;
+  const float* slope;    /* device scalar (PRELU / PRELU_BWD) */
+  const void* residual;  /* [n,h,w,out.c] dtype (RES_PRE) */
+  const void* aux_y;     /* [n,h,w,out.c] dtype (PRELU_BWD / RELU_BWD) */
+  void* out2;            /* [n,h,w,out.c] dtype (OUT2) */
+  const void* res2;      /* [n,h,w,out.c] dtype (OUT2) */
+  float* slope_partials; /* device, >= vsr_partials_len() floats: per-CTA partial slope grads */
+} VsrTapGemmDesc;
+
+int vsr_abi_version(void);
+const char* vsr_last_error(void);
+/* number of floats a slope_partials row must hold (upper bound of any grid) */
+int vsr_partials_len(void);
+
+/* forward / data-gradient tap-GEMM (see above) */
+int vsr_tapgemm(const VsrTapGemmDesc* d, void* stream);
+
+/*
+ * Weight-gradient of a tap-GEMM: dw[t][j][k] (+)= sum_{n,y,x} dz[n,y,x,o0_g+j] *
+ *   srcs[t.src][n,y+t.dy,x+t.dx,t.c0+k]; dw is fp32 [n_taps_total][nt][kc] plain row-major
+ * (never swizzled).  `d->out.ptr` is dz; d->w, bias, epilogue fields are ignored.
+ * workspace: >= vsr_tapgemm_wgrad_workspace(d) bytes.  accumulate!=0 adds to dw.
+ * Replaces the weight half of aten.convolution_backward for the call sites listed above;
+ * the summation order is fixed (deterministic, main.py:32 cudnn.deterministic).
+ */
+size_t vsr_tapgemm_wgrad_workspace(const VsrTapGemmDesc* d);
+int vsr_tapgemm_wgrad(const VsrTapGemmDesc* d, float* dw, int accumulate, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
+/* colsum: db[c] (+)= sum over pixels x[pix][c]  (bias gradient; fixed order).
+ * workspace >= vsr_colsum_workspace(rows, c) bytes. */
+size_t vsr_colsum_workspace(int64_t rows, int32_t c);
+int vsr_colsum(const void* x, int32_t dtype, int64_t rows, int32_t c, float* db, int accumulate,
+               void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * First layer (in_block.conv1, drf_net.py:55-56): 3x3 pad-1 convolution of a Cin-channel image
+ * (NCHW fp32, Cin small) to `cout` channels + bias + PReLU, written pixel-major in `dtype`.
+ * w: fp32 [cout][cin][3][3] (reference layout, used as is).
+ */
+int vsr_conv3x3_first(const float* x, int32_t n, int32_t cin, int32_t h, int32_t w_, const float* w,
+                      const float* bias, const float* slope, void* y, int32_t dtype, int32_t cout,
+                      void* stream);
+/* its backward: dz is [n,h,w,cout] (already multiplied by PReLU'); produces dw (fp32
+ * [cout][cin][3][3]) and db; dx is not needed (network input).  deterministic two-pass. */
+size_t vsr_conv3x3_first_bwd_workspace(int32_t n, int32_t cin, int32_t h, int32_t w_, int32_t cout);
+int vsr_conv3x3_first_bwd(const float* x, int32_t n, int32_t cin, int32_t h, int32_t w_,
+                          const void* dz, int32_t dtype, int32_t cout, float* dw, float* db,
+                          int accumulate, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Last layer (out_block.conv{k}, drf_net.py:144,147): 3x3 pad-1 convolution from C channels to
+ * cout (small) on a phase-blocked high-resolution map x [n,h,w,r*r*C] (phase order given by
+ * `phase_yx`, a HOST int32[r*r][2] = (py,px) of each phase slot), producing NCHW fp32 [n,cout,r*h,r*w].
+ * w: fp32 [cout][C][3][3]; bias fp32 [cout].
+ */
+int vsr_conv3x3_last(const void* x, int32_t dtype, int32_t n, int32_t h, int32_t w_, int32_t r,
+                     int32_t c, const int32_t* phase_yx, const float* w, const float* bias,
+                     float* y, int32_t cout, void* stream);
+/* backward: dy NCHW fp32 [n,cout,rh,rw] -> dx phase-blocked [n,h,w,r*r*c] in dtype, and dw/db. */
+size_t vsr_conv3x3_last_bwd_workspace(int32_t n, int32_t h, int32_t w_, int32_t r, int32_t c,
+                                      int32_t cout);
+int vsr_conv3x3_last_bwd(const void* x, int32_t dtype, int32_t n, int32_t h, int32_t w_, int32_t r,
+                         int32_t c, const int32_t* phase_yx, const float* w, const float* dy,
+                         int32_t cout, void* dx, float* dw, float* db, int accumulate,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* elementwise PReLU / ReLU backward on a pixel-major map: dz = y>0 ? dy : a*dy, partial slope
+ * grads to slope_partials (nn.PReLU backward, drf_net.py:56-106). a == NULL means ReLU. */
+int vsr_act_bwd(const void* dy, const void* y, void* dz, int32_t dtype, int64_t numel,
+                const float* slope, float* slope_partials, void* stream);
+
+/* out[i] = a[i] + b[i] (pixel-major maps, dtype) — global skip drf_net.py:46 when not fused */
+int vsr_add(const void* a, const void* b, void* out, int32_t dtype, int64_t numel, void* stream);
+
+/* dst[row_dst[r]] += sum(partials[r][0..len))  for r < rows; fixed order. */
+int vsr_reduce_partials(const float* partials, int32_t rows, int32_t len, const int32_t* row_dst,
+                        float* dst, void* stream);
+
+/* gather: dst[i] = idx[i] >= 0 ? cast(src[idx[i]]) : 0, i < n.  Packs reference-layout fp32
+ * parameters into tap slabs (dst dtype) and un-packs slab gradients (fp32 -> fp32). */
+int vsr_gather(const float* src, const int32_t* idx, void* dst, int32_t dst_dtype, int64_t n,
+               void* stream);
+/* dst[i] += src[idx[i]] for idx[i] >= 0 (fp32) */
+int vsr_gather_add(const float* src, const int32_t* idx, float* dst, int64_t n, void* stream);
+
+/* index of element (row j, k) inside a bf16 [nt][64] slab in the swizzled image */
+int64_t vsr_slab_index(int32_t j, int32_t k);
+
+/*
+ * Fused loss forward+backward over one frame (torch.nn.L1Loss / MSELoss via main.py:60-63,
+ * CharbonnierLoss losses.py:23-34, HuberLoss losses.py:5-20), mean reduction:
+ *   partial sums -> loss_partials[vsr_partials_len()], grad[i] = dloss/dout[i] * grad_scale.
+ * kind: 0 L1, 1 MSE, 2 Charbonnier(param=epsilon), 3 Huber(param=delta). grad may be NULL.
+ */
+int vsr_loss_fwd_bwd(const float* out, const float* target, int64_t numel, int32_t kind, float param,
+                     float grad_scale, float* loss_partials, float* grad, void* stream);
+
+/*
+ * Fused denormalize + PSNR (src/utils.py:1-20 + metrics.py:20-36): per sample
+ * mse over (x*std+mean).round().clamp(0,255) of both inputs, psnr = 10 log10(max^2/(mse+1e-10)).
+ * psnr_out: [n] fp32.  std<=0 disables the denormalisation (inputs used as they are).
+ * workspace (both metrics): >= vsr_metric_workspace(n, per_sample) bytes; partial sums, fixed-order reduce.
+ */
+size_t vsr_metric_workspace(int32_t n, int64_t per_sample);
+int vsr_psnr(const float* out, const float* target, int32_t n, int64_t per_sample, float mean,
+             float std, float max_value, float* psnr_out, void* workspace, size_t workspace_bytes,
+             void* stream);
+
+/*
+ * Fused denormalize + SSIM (metrics.py:51-113, dim=2, channels=1): separable 11-tap window
+ * (weights given by the caller, fp32[11]; the reference's window is exp(-((i-5)/(2 sigma))^2)
+ * normalised, metrics.py:74-77), valid convolution, per-sample mean of the SSIM map.
+ * ssim_out: [n] fp32.  imgs are [n][h][w] fp32.
+ */
+int vsr_ssim(const float* out, const float* target, int32_t n, int32_t h, int32_t w_,
+             const float* win11, float mean, float std, float c1, float c2, float* ssim_out,
+             void* workspace, size_t workspace_bytes, void* stream);
+
+/* nn.PixelShuffle / its inverse on NCHW fp32 (standalone, for the kernel sweep; the nets never
+ * launch it).  x [n, c*r*r, h, w] -> y [n, c, h*r, w*r]  (drf_net.py:142). */
+int vsr_pixel_shuffle(const float* x, float* y, int32_t n, int32_t c, int32_t h, int32_t w_,
+                      int32_t r, int inverse, void* stream);
+
+/* F.interpolate(mode='bilinear'|'trilinear') forward on NCHW / NCDHW fp32 (srfb_net.py:47;
+ * trilinear has no reference call site, torch is the oracle).  d==1 -> bilinear. */
+int vsr_upsample_linear(const float* x, float* y, int32_t nc, int32_t d, int32_t h, int32_t w_,
+                        int32_t od, int32_t oh, int32_t ow, int align_corners, void* stream);
+int vsr_upsample_linear_bwd(const float* dy, float* dx, int32_t nc, int32_t d, int32_t h,
+                            int32_t w_, int32_t od, int32_t oh, int32_t ow, int align_corners,
+                            void* stream);
+
+/* Fused Adam over a flat fp32 parameter bucket (torch.optim.Adam semantics, main.py:73-74):
+ * grads are multiplied by grad_scale first (1/world_size after the NCCL sum). */
+int vsr_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
+                  void* stream);
+
+/* cast fp32 <-> bf16 / layout helpers */
+int vsr_cast(const void* src, int32_t src_dtype, void* dst, int32_t dst_dtype, int64_t n,
+             void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VSR_B200_H_ */

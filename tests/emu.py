@@ -1,0 +1,330 @@
+"""TEST INFRASTRUCTURE — a plain-torch emulation of every op of vsr_b200.ops.CudaOps.
+
+It exists so that (a) the host logic (tap tables, weight packing, forward/backward schedule) can
+be verified on a CPU-only box against the oracle, and (b) each CUDA kernel can be checked against
+an independent implementation on the GPU box.  Nothing in the product imports this file.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+from vsr_b200 import _lib
+from vsr_b200.ops import slab_index
+
+E = _lib
+
+
+def _shift(x, dy, dx):
+    """y[n, i, j] = x[n, i+dy, j+dx], zero outside."""
+    n, h, w, c = x.shape
+    out = torch.zeros_like(x)
+    ys0, ys1 = max(0, dy), min(h, h + dy)
+    xs0, xs1 = max(0, dx), min(w, w + dx)
+    if ys1 <= ys0 or xs1 <= xs0:
+        return out
+    out[:, ys0 - dy:ys1 - dy, xs0 - dx:xs1 - dx] = x[:, ys0:ys1, xs0:xs1]
+    return out
+
+
+def unswizzle_slabs(w, n_taps, nt):
+    """bf16 swizzled slab image -> plain [n_taps, nt, 64]."""
+    w = w.reshape(n_taps, nt * 64)
+    j = torch.arange(nt).view(nt, 1)
+    k = torch.arange(64).view(1, 64)
+    idx = (j * 64 + (((k >> 3) ^ (j & 7)) << 3) + (k & 7)).reshape(-1).to(w.device)
+    return w[:, idx].reshape(n_taps, nt, 64)
+
+
+def swizzle_slabs(w_plain):
+    """plain [n_taps, nt, 64] -> swizzled image (flat)."""
+    n_taps, nt, kc = w_plain.shape
+    assert kc == 64
+    j = torch.arange(nt).view(nt, 1)
+    k = torch.arange(64).view(1, 64)
+    idx = (j * 64 + (((k >> 3) ^ (j & 7)) << 3) + (k & 7)).reshape(-1).to(w_plain.device)
+    out = torch.empty(n_taps, nt * 64, dtype=w_plain.dtype, device=w_plain.device)
+    out[:, idx] = w_plain.reshape(n_taps, nt * 64)
+    return out.reshape(-1)
+
+
+class EmuOps:
+    """Same interface as CudaOps; computes in fp32 (or fp64 if the tensors are fp64) with torch ops.
+    `swizzled` says whether bf16 weight slabs are in the swizzled image (as the product packs them).
+    """
+    name = "emu"
+
+    def __init__(self, partials_len=1024, swizzled_bf16=True):
+        self.partials_len = partials_len
+        self.swizzled_bf16 = swizzled_bf16
+        self.launches = 0
+
+    # ---- tap-GEMM ----------------------------------------------------------------------
+    def _slabs(self, tab, w):
+        if w.dtype == torch.bfloat16 and self.swizzled_bf16 and tab.kc == 64:
+            return unswizzle_slabs(w, tab.n_taps_total, tab.nt)
+        return w.reshape(tab.n_taps_total, tab.nt, tab.kc)
+
+    def tapgemm(self, tab, srcs, out, w, bias=None, epi=0, out_scale=1.0, slope=None, residual=None,
+                aux_y=None, out2=None, res2=None, slope_partials=None, force_simt=False):
+        ct = torch.float64 if out.dtype == torch.float64 else torch.float32
+        slabs = self._slabs(tab, w).to(ct)
+        ti = 0
+        for o0, taps in tab.groups:
+            acc = torch.zeros(*out.shape[:3], tab.nt, dtype=ct, device=out.device)
+            for (s, dy, dx, c0) in taps:
+                x = _shift(srcs[s][..., c0:c0 + tab.kc].to(ct), dy, dx)
+                acc += x @ slabs[ti].t()
+                ti += 1
+            sl = slice(o0, o0 + tab.nt)
+            v = acc
+            if epi & E.EPI_BIAS:
+                v = v + bias[sl].to(ct)
+            if epi & E.EPI_SCALE:
+                v = v * out_scale
+            if epi & E.EPI_RES_PRE:
+                v = v + residual[..., sl].to(ct)
+            if epi & E.EPI_PRELU:
+                a = slope.to(ct).reshape(())
+                v = torch.where(v > 0, v, a * v)
+            if epi & E.EPI_RELU:
+                v = v.clamp_min(0)
+            if epi & E.EPI_PRELU_BWD:
+                a = slope.to(ct).reshape(())
+                y = aux_y[..., sl].to(ct)
+                pos = y > 0
+                inv = 1.0 / a if float(a) != 0.0 else torch.zeros_like(a)
+                contrib = torch.where(pos, torch.zeros_like(v), v * (y * inv)).sum()
+                slope_partials.view(-1)[0] += contrib.to(slope_partials.dtype)
+                v = torch.where(pos, v, a * v)
+            elif epi & E.EPI_RELU_BWD:
+                y = aux_y[..., sl].to(ct)
+                v = torch.where(y > 0, v, torch.zeros_like(v))
+            out[..., sl] = v.to(out.dtype)
+            if epi & E.EPI_OUT2:
+                # the kernels add in fp32 from the unrounded value
+                out2[..., sl] = (v + res2[..., sl].to(ct)).to(out2.dtype)
+        self.launches += 1
+
+    def tapgemm_wgrad_workspace(self, tab, srcs, dz):
+        return 16
+
+    def tapgemm_wgrad(self, tab, srcs, dz, dw, accumulate, workspace):
+        ct = torch.float64 if dw.dtype == torch.float64 else torch.float32
+        res = torch.empty(tab.n_taps_total, tab.nt, tab.kc, dtype=ct, device=dz.device)
+        ti = 0
+        for o0, taps in tab.groups:
+            g = dz[..., o0:o0 + tab.nt].to(ct).reshape(-1, tab.nt)
+            for (s, dy, dx, c0) in taps:
+                x = _shift(srcs[s][..., c0:c0 + tab.kc].to(ct), dy, dx).reshape(-1, tab.kc)
+                res[ti] = g.t() @ x
+                ti += 1
+        flat = dw.view(-1)[:res.numel()]
+        if accumulate:
+            flat += res.reshape(-1).to(dw.dtype)
+        else:
+            flat.copy_(res.reshape(-1).to(dw.dtype))
+        self.launches += 2
+
+    # ---- small kernels -----------------------------------------------------------------
+    def colsum_workspace(self, rows, c):
+        return 16
+
+    def colsum(self, x, rows, c, db, accumulate, workspace):
+        s = x.reshape(rows, c).to(db.dtype).sum(0)
+        if accumulate:
+            db += s
+        else:
+            db.copy_(s)
+        self.launches += 2
+
+    def conv3x3_first(self, x, w, bias, slope, y):
+        ct = x.dtype
+        z = F.conv2d(x, w.to(ct), bias.to(ct) if bias is not None else None, padding=1)
+        if slope is not None:
+            z = torch.where(z > 0, z, slope.to(ct).reshape(()) * z)
+        y.copy_(z.permute(0, 2, 3, 1).to(y.dtype))
+        self.launches += 1
+
+    def conv3x3_first_bwd_workspace(self, x, cout):
+        return 16
+
+    def conv3x3_first_bwd(self, x, dz, dw, db, accumulate, workspace):
+        ct = dw.dtype
+        g = dz.to(ct).permute(0, 3, 1, 2)
+        gw = torch.nn.grad.conv2d_weight(x.to(ct), (dz.shape[-1], x.shape[1], 3, 3), g, padding=1)
+        gb = g.sum((0, 2, 3))
+        if accumulate:
+            dw += gw
+            db += gb
+        else:
+            dw.copy_(gw)
+            db.copy_(gb)
+        self.launches += 2
+
+    @staticmethod
+    def _unblock(x, r, c, phase_yx):
+        """phase-blocked [n,h,w,r*r*c] -> NCHW [n,c,rh,rw]."""
+        n, h, w, _ = x.shape
+        xv = x.reshape(n, h, w, r * r, c)
+        out = torch.empty(n, c, h * r, w * r, dtype=x.dtype, device=x.device)
+        for s, (py, px) in enumerate(phase_yx):
+            out[:, :, py::r, px::r] = xv[:, :, :, s].permute(0, 3, 1, 2)
+        return out
+
+    @staticmethod
+    def _block(x, r, phase_yx):
+        """NCHW [n,c,rh,rw] -> phase-blocked [n,h,w,r*r*c]."""
+        n, c, H, W = x.shape
+        h, w = H // r, W // r
+        out = torch.empty(n, h, w, r * r, c, dtype=x.dtype, device=x.device)
+        for s, (py, px) in enumerate(phase_yx):
+            out[:, :, :, s] = x[:, :, py::r, px::r].permute(0, 2, 3, 1)
+        return out.reshape(n, h, w, r * r * c)
+
+    def conv3x3_last(self, x, r, c, phase_yx, w, bias, y):
+        ct = y.dtype
+        xi = self._unblock(x.to(ct), r, c, phase_yx)
+        y.copy_(F.conv2d(xi, w.to(ct), bias.to(ct) if bias is not None else None, padding=1))
+        self.launches += 1
+
+    def conv3x3_last_bwd_workspace(self, x, r, c, cout):
+        return 16
+
+    def conv3x3_last_bwd(self, x, r, c, phase_yx, w, dy, dx, dw, db, accumulate, workspace):
+        ct = dw.dtype
+        xi = self._unblock(x.to(ct), r, c, phase_yx)
+        gx = torch.nn.grad.conv2d_input(xi.shape, w.to(ct), dy.to(ct), padding=1)
+        gw = torch.nn.grad.conv2d_weight(xi, w.shape, dy.to(ct), padding=1)
+        gb = dy.to(ct).sum((0, 2, 3))
+        dx.copy_(self._block(gx, r, phase_yx).to(dx.dtype))
+        if accumulate:
+            dw += gw
+            db += gb
+        else:
+            dw.copy_(gw)
+            db.copy_(gb)
+        self.launches += 2
+
+    def act_bwd(self, dy, y, dz, slope=None, slope_partials=None):
+        ct = torch.float64 if dy.dtype == torch.float64 else torch.float32
+        g, v = dy.to(ct), y.to(ct)
+        pos = v > 0
+        if slope is not None:
+            a = slope.to(ct).reshape(())
+            inv = 1.0 / a if float(a) != 0.0 else torch.zeros_like(a)
+            slope_partials.view(-1)[0] += torch.where(pos, torch.zeros_like(g), g * (v * inv)).sum().to(
+                slope_partials.dtype)
+            dz.copy_(torch.where(pos, g, a * g).to(dz.dtype))
+        else:
+            dz.copy_(torch.where(pos, g, torch.zeros_like(g)).to(dz.dtype))
+        self.launches += 1
+
+    def add(self, a, b, out):
+        ct = torch.float64 if a.dtype == torch.float64 else torch.float32
+        out.copy_((a.to(ct) + b.to(ct)).to(out.dtype))
+        self.launches += 1
+
+    def reduce_partials(self, partials, rows, row_dst, dst):
+        sums = partials.reshape(-1, partials.shape[-1])[:rows].sum(1)
+        for r in range(rows):
+            dst[int(row_dst[r])] += sums[r].to(dst.dtype)
+        self.launches += 1
+
+    def gather(self, src, idx, dst):
+        li = idx.long()
+        vals = torch.where(li >= 0, src[li.clamp_min(0)], torch.zeros((), dtype=src.dtype, device=src.device))
+        dst.view(-1)[:li.numel()].copy_(vals.to(dst.dtype))
+        self.launches += 1
+
+    def gather_add(self, src, idx, dst):
+        li = idx.long()
+        vals = torch.where(li >= 0, src[li.clamp_min(0)], torch.zeros((), dtype=src.dtype, device=src.device))
+        dst.view(-1)[:li.numel()] += vals.to(dst.dtype)
+        self.launches += 1
+
+    def cast(self, src, dst):
+        dst.copy_(src.to(dst.dtype))
+        self.launches += 1
+
+    def zero_(self, t):
+        t.zero_()
+
+    # ---- loss / metrics ----------------------------------------------------------------
+    def loss_fwd_bwd(self, out, target, kind, param, grad_scale, partials, grad):
+        d = out - target
+        if kind == 0:
+            val, g = d.abs().sum(), torch.sign(d)
+        elif kind == 1:
+            val, g = (d * d).sum(), 2 * d
+        elif kind == 2:
+            s = torch.sqrt(d * d + param)
+            val, g = s.sum(), d / s
+        else:
+            ad = d.abs()
+            q = ad.clamp_max(param)
+            val = (0.5 * q * q + param * (ad - q)).sum()
+            g = torch.where(ad < param, d, param * torch.sign(d))
+        partials.view(-1)[0] += val.to(partials.dtype)
+        if grad is not None:
+            grad.copy_((g * grad_scale).to(grad.dtype))
+        self.launches += 1
+
+    def metric_workspace(self, n, per_sample):
+        return 16
+
+    @staticmethod
+    def _denorm(x, mean, std):
+        if std <= 0:
+            return x
+        return (x * std + mean).round().clamp(0, 255)
+
+    def psnr(self, out, target, mean, std, max_value, psnr_out, workspace):
+        a, b = self._denorm(out, mean, std), self._denorm(target, mean, std)
+        n = out.shape[0]
+        mse = ((a - b) ** 2).reshape(n, -1).mean(1)
+        psnr_out.copy_(10 * torch.log10(max_value ** 2 / (mse + 1e-10)))
+        self.launches += 2
+
+    def ssim(self, out, target, win11, mean, std, c1, c2, ssim_out, workspace):
+        a, b = self._denorm(out, mean, std), self._denorm(target, mean, std)
+        n = out.shape[0]
+        a = a.reshape(n, 1, *out.shape[-2:])
+        b = b.reshape(n, 1, *out.shape[-2:])
+        k2 = torch.outer(win11, win11).reshape(1, 1, 11, 11).to(a.dtype)
+        conv = lambda t: F.conv2d(t, k2)
+        mu1, mu2 = conv(a), conv(b)
+        s11 = conv(a * a) - mu1 ** 2
+        s22 = conv(b * b) - mu2 ** 2
+        s12 = conv(a * b) - mu1 * mu2
+        m = ((2 * mu1 * mu2 + c1) * (2 * s12 + c2)) / ((mu1 ** 2 + mu2 ** 2 + c1) * (s11 + s22 + c2))
+        ssim_out.copy_(m.reshape(n, -1).mean(1))
+        self.launches += 2
+
+    # ---- standalone --------------------------------------------------------------------
+    def pixel_shuffle(self, x, y, r, inverse=False):
+        y.copy_(F.pixel_unshuffle(x, r) if inverse else F.pixel_shuffle(x, r))
+        self.launches += 1
+
+    def upsample_linear(self, x, y, align_corners):
+        mode = "bilinear" if x.dim() == 4 else "trilinear"
+        y.copy_(F.interpolate(x, size=y.shape[2:], mode=mode, align_corners=bool(align_corners)))
+        self.launches += 1
+
+    def upsample_linear_bwd(self, dy, dx, align_corners):
+        mode = "bilinear" if dx.dim() == 4 else "trilinear"
+        x = torch.zeros_like(dx, requires_grad=True)
+        y = F.interpolate(x, size=dy.shape[2:], mode=mode, align_corners=bool(align_corners))
+        dx.copy_(torch.autograd.grad(y, x, dy)[0])
+        self.launches += 1
+
+    def adam_flat(self, p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
+        gi = g * grad_scale
+        if weight_decay != 0:
+            gi = gi + weight_decay * p
+        m.mul_(beta1).add_(gi, alpha=1 - beta1)
+        v.mul_(beta2).addcmul_(gi, gi, value=1 - beta2)
+        bc1, bc2 = 1 - beta1 ** step, 1 - beta2 ** step
+        denom = v.sqrt() / math.sqrt(bc2) + eps
+        p.addcdiv_(m, denom, value=-lr / bc1)
+        self.launches += 1

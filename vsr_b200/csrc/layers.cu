@@ -1,0 +1,460 @@
+// layers.cu — the two bandwidth-bound boundary convolutions of the nets:
+//   first: NCHW fp32 image (Cin small) -> pixel-major features   (drf_net.py:55-56)
+//   last : phase-blocked features -> NCHW fp32 image (Cout small) (drf_net.py:144,147)
+// and their backward passes.  K=9*Cin resp. N=Cout are far too thin for tensor cores
+// (4 FLOP/B); these are coalesced CUDA-core kernels bound by HBM.
+#include "common.cuh"
+
+namespace vsr {
+namespace {
+
+constexpr int kMaxCin = 4;
+constexpr int kMaxCoutLast = 4;
+
+// ------------------------------------------------------------------------------------------
+// first conv: one thread = one pixel x 8 output channels; a warp covers 256 consecutive channels
+// of one pixel (coalesced 16-byte stores).
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void conv_first_kernel(const float* __restrict__ x, int n, int cin, int h, int w,
+                                  const float* __restrict__ wt, const float* __restrict__ bias,
+                                  const float* __restrict__ slope_p, T* __restrict__ y, int cout) {
+  extern __shared__ float sw[];  // [cin*9][cout] transposed weights, then bias[cout]
+  float* sb = sw + cin * 9 * cout;
+  for (int i = threadIdx.x; i < cin * 9 * cout; i += blockDim.x) {
+    const int co = i / (cin * 9), r = i % (cin * 9);
+    sw[r * cout + co] = wt[i];
+  }
+  for (int i = threadIdx.x; i < cout; i += blockDim.x) sb[i] = bias ? bias[i] : 0.f;
+  __syncthreads();
+  const float a = slope_p ? __ldg(slope_p) : 1.f;
+  const int groups = cout / 8;
+  const long total = (long)n * h * w * groups;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int gq = (int)(i % groups);
+    const long pix = i / groups;
+    const int px = (int)(pix % w);
+    const long q = pix / w;
+    const int py = (int)(q % h);
+    const int ni = (int)(q / h);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = sb[gq * 8 + j];
+    for (int ci = 0; ci < cin; ++ci) {
+      const float* xp = x + ((size_t)ni * cin + ci) * h * w;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int yy = py + ky - 1;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int xx = px + kx - 1;
+          float v = 0.f;
+          if (yy >= 0 && yy < h && xx >= 0 && xx < w) v = __ldg(xp + (size_t)yy * w + xx);
+          const float* wp = sw + ((ci * 3 + ky) * 3 + kx) * cout + gq * 8;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wp[j], acc[j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = acc[j] > 0.f ? acc[j] : a * acc[j];
+    T* yp = y + pix * cout + gq * 8;
+    if constexpr (sizeof(T) == 2) {
+      uint4 o;
+      o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
+      o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
+      *reinterpret_cast<uint4*>(yp) = o;
+    } else {
+      reinterpret_cast<float4*>(yp)[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      reinterpret_cast<float4*>(yp)[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+  }
+}
+
+// first conv backward: block b covers a pixel range, thread = output channel; partial
+// dw[co][cin*9] and db[co] in registers -> ws[b][cout][cin*9+1]; fixed-order final reduce.
+template <typename T>
+__global__ void conv_first_bwd_kernel(const float* __restrict__ x, int n, int cin, int h, int w,
+                                      const T* __restrict__ dz, int cout, long pix_per_block,
+                                      float* __restrict__ ws) {
+  const long total = (long)n * h * w;
+  const long p0 = blockIdx.x * pix_per_block;
+  long p1 = p0 + pix_per_block;
+  if (p1 > total) p1 = total;
+  const int stride = cin * 9 + 1;
+  for (int co = threadIdx.x; co < cout; co += blockDim.x) {
+    float acc[kMaxCin * 9 + 1];
+#pragma unroll
+    for (int i = 0; i < kMaxCin * 9 + 1; ++i) acc[i] = 0.f;
+    for (long p = p0; p < p1; ++p) {
+      const int px = (int)(p % w);
+      const long q = p / w;
+      const int py = (int)(q % h);
+      const int ni = (int)(q / h);
+      const float g = Elem<T>::ld(dz + p * cout + co);
+      acc[kMaxCin * 9] += g;
+#pragma unroll
+      for (int ci = 0; ci < kMaxCin; ++ci) {
+        if (ci < cin) {
+          const float* xp = x + ((size_t)ni * cin + ci) * h * w;
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) {
+            const int yy = py + ky - 1;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+              const int xx = px + kx - 1;
+              float v = 0.f;
+              if (yy >= 0 && yy < h && xx >= 0 && xx < w) v = __ldg(xp + (size_t)yy * w + xx);
+              acc[(ci * 3 + ky) * 3 + kx] = fmaf(g, v, acc[(ci * 3 + ky) * 3 + kx]);
+            }
+          }
+        }
+      }
+    }
+    float* o = ws + ((size_t)blockIdx.x * cout + co) * stride;
+    for (int i = 0; i < cin * 9; ++i) o[i] = acc[i];
+    o[cin * 9] = acc[kMaxCin * 9];
+  }
+}
+
+__global__ void conv_first_bwd_final_kernel(const float* __restrict__ ws, int blocks, int cout, int cin,
+                                            float* __restrict__ dw, float* __restrict__ db, int accumulate) {
+  const int stride = cin * 9 + 1;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cout * stride) return;
+  const int co = i / stride, r = i % stride;
+  float s = 0.f;
+  for (int b = 0; b < blocks; ++b) s += ws[((size_t)b * cout + co) * stride + r];
+  float* dst = (r == cin * 9) ? (db + co) : (dw + (size_t)co * cin * 9 + r);
+  *dst = accumulate ? *dst + s : s;
+}
+
+// ------------------------------------------------------------------------------------------
+// last conv: one warp = one high-resolution output pixel; lanes stride the C channels.
+// x is phase-blocked [n][h][w][r*r][C]; slot_of[py*r+px] gives the phase slot.
+// ------------------------------------------------------------------------------------------
+struct LastGeom {
+  int n, h, w, r, c, cout;
+  int slot_of[64];  // r*r <= 64
+};
+
+template <typename T>
+__device__ __forceinline__ const T* hr_ptr(const T* x, const LastGeom& g, int ni, int Y, int X) {
+  const int y = Y / g.r, py = Y % g.r, xx = X / g.r, px = X % g.r;
+  const int slot = g.slot_of[py * g.r + px];
+  return x + ((((size_t)ni * g.h + y) * g.w + xx) * (g.r * g.r) + slot) * g.c;
+}
+
+template <typename T>
+__global__ void conv_last_kernel(const T* __restrict__ x, const __grid_constant__ LastGeom g,
+                                 const float* __restrict__ wt, const float* __restrict__ bias,
+                                 float* __restrict__ y) {
+  extern __shared__ float sw[];  // [cout][9][C]
+  for (int i = threadIdx.x; i < g.cout * g.c * 9; i += blockDim.x) {
+    const int co = i / (g.c * 9), rem = i % (g.c * 9), ci = rem / 9, tap = rem % 9;
+    sw[(co * 9 + tap) * g.c + ci] = wt[i];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int H = g.h * g.r, W = g.w * g.r;
+  const long total = (long)g.n * H * W;
+  const long warp0 = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+  const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+  for (long p = warp0; p < total; p += nwarps) {
+    const int X = (int)(p % W);
+    const long q = p / W;
+    const int Y = (int)(q % H);
+    const int ni = (int)(q / H);
+    float acc[kMaxCoutLast];
+#pragma unroll
+    for (int co = 0; co < kMaxCoutLast; ++co) acc[co] = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int yy = Y + ky - 1;
+      if (yy < 0 || yy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int xx = X + kx - 1;
+        if (xx < 0 || xx >= W) continue;
+        const T* xp = hr_ptr(x, g, ni, yy, xx);
+        for (int ci = lane; ci < g.c; ci += 32) {
+          const float v = Elem<T>::ld(xp + ci);
+#pragma unroll
+          for (int co = 0; co < kMaxCoutLast; ++co)
+            if (co < g.cout) acc[co] = fmaf(v, sw[(co * 9 + ky * 3 + kx) * g.c + ci], acc[co]);
+        }
+      }
+    }
+#pragma unroll
+    for (int co = 0; co < kMaxCoutLast; ++co) {
+      if (co < g.cout) {
+        const float s = warp_sum(acc[co]);
+        if (lane == 0) y[(((size_t)ni * g.cout + co) * H + Y) * W + X] = s + (bias ? __ldg(bias + co) : 0.f);
+      }
+    }
+  }
+}
+
+// last conv backward: per HR pixel P (one warp): dx(P,c) = sum_{co,tap} dy(co, P - off(tap)) * w[co][c][tap]
+// and dw[co][c][tap] += dy(co,P) * x(P + off(tap), c); db[co] += dy(co,P).
+// dw/db partials: per-warp registers -> per-block smem (fixed warp order) -> ws[block][...] -> final.
+template <typename T>
+__global__ void conv_last_bwd_kernel(const T* __restrict__ x, const __grid_constant__ LastGeom g,
+                                     const float* __restrict__ wt, const float* __restrict__ dy,
+                                     T* __restrict__ dx, float* __restrict__ ws, int ch_per_lane) {
+  // smem: weights [cout][9][C] then block partial [nwarps][cout*9*C + cout]
+  extern __shared__ float sm[];
+  float* sw = sm;
+  const int wsz = g.cout * 9 * g.c;
+  for (int i = threadIdx.x; i < g.cout * g.c * 9; i += blockDim.x) {
+    const int co = i / (g.c * 9), rem = i % (g.c * 9), ci = rem / 9, tap = rem % 9;
+    sw[(co * 9 + tap) * g.c + ci] = wt[i];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int H = g.h * g.r, W = g.w * g.r;
+  const long total = (long)g.n * H * W;
+  const long warp0 = (long)blockIdx.x * nw + warp;
+  const long nwarps = (long)gridDim.x * nw;
+  // per-lane dw accumulators: channels ci = lane + 32*k, k < ch_per_lane (<=4), cout==1..kMaxCoutLast
+  // restricted to cout*ch_per_lane <= 4 groups of 9 to bound registers.
+  float dwacc[4][9];
+  float dbacc[kMaxCoutLast];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) dwacc[i][t] = 0.f;
+#pragma unroll
+  for (int co = 0; co < kMaxCoutLast; ++co) dbacc[co] = 0.f;
+
+  for (long p = warp0; p < total; p += nwarps) {
+    const int X = (int)(p % W);
+    const long q = p / W;
+    const int Y = (int)(q % H);
+    const int ni = (int)(q / H);
+    // ---- dx ----
+    float dxa[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int co = 0; co < g.cout; ++co) {
+      const float* dyp = dy + ((size_t)ni * g.cout + co) * H * W;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int yy = Y - (ky - 1);
+        if (yy < 0 || yy >= H) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int xx = X - (kx - 1);
+          if (xx < 0 || xx >= W) continue;
+          const float gval = __ldg(dyp + (size_t)yy * W + xx);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int ci = lane + 32 * k;
+            if (k < ch_per_lane && ci < g.c) dxa[k] = fmaf(gval, sw[(co * 9 + ky * 3 + kx) * g.c + ci], dxa[k]);
+          }
+        }
+      }
+    }
+    T* dxp = const_cast<T*>(hr_ptr(dx, g, ni, Y, X));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int ci = lane + 32 * k;
+      if (k < ch_per_lane && ci < g.c) Elem<T>::st(dxp + ci, dxa[k]);
+    }
+    // ---- dw / db (cout * ch_per_lane <= 4) ----
+    for (int co = 0; co < g.cout; ++co) {
+      const float gval = __ldg(dy + (((size_t)ni * g.cout + co) * H + Y) * W + X);
+      dbacc[co] += gval;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int yy = Y + ky - 1;
+        if (yy < 0 || yy >= H) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int xx = X + kx - 1;
+          if (xx < 0 || xx >= W) continue;
+          const T* xp = hr_ptr(x, g, ni, yy, xx);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int ci = lane + 32 * k;
+            const int slot = co * ch_per_lane + k;
+            if (k < ch_per_lane && ci < g.c && slot < 4)
+              dwacc[slot][ky * 3 + kx] = fmaf(gval, Elem<T>::ld(xp + ci), dwacc[slot][ky * 3 + kx]);
+          }
+        }
+      }
+    }
+  }
+  // block reduce in fixed warp order
+  float* part = sm + wsz;  // [nw][wsz + cout]
+  const int psz = wsz + g.cout;
+  for (int co = 0; co < g.cout; ++co) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int ci = lane + 32 * k;
+      const int slot = co * ch_per_lane + k;
+      if (k < ch_per_lane && ci < g.c && slot < 4)
+#pragma unroll
+        for (int t = 0; t < 9; ++t) part[(size_t)warp * psz + (co * 9 + t) * g.c + ci] = dwacc[slot][t];
+    }
+    if (lane == 0) part[(size_t)warp * psz + wsz + co] = dbacc[co];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < psz; i += blockDim.x) {
+    float s = 0.f;
+    for (int wv = 0; wv < nw; ++wv) s += part[(size_t)wv * psz + i];
+    ws[(size_t)blockIdx.x * psz + i] = s;
+  }
+}
+
+__global__ void conv_last_bwd_final_kernel(const float* __restrict__ ws, int blocks, int cout, int c,
+                                           float* __restrict__ dw, float* __restrict__ db, int accumulate) {
+  const int wsz = cout * 9 * c, psz = wsz + cout;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= psz) return;
+  float s = 0.f;
+  for (int b = 0; b < blocks; ++b) s += ws[(size_t)b * psz + i];
+  float* dst;
+  if (i < wsz) {
+    const int co = i / (9 * c), rem = i % (9 * c), tap = rem / c, ci = rem % c;
+    dst = dw + ((size_t)co * c + ci) * 9 + tap;
+  } else {
+    dst = db + (i - wsz);
+  }
+  *dst = accumulate ? *dst + s : s;
+}
+
+int first_bwd_blocks(long pixels) {
+  long b = (pixels + 31) / 32;
+  const long cap = (long)num_sms() * 4;
+  if (b > cap) b = cap;
+  return (int)(b < 1 ? 1 : b);
+}
+
+constexpr int kLastBwdThreads = 256;
+int last_bwd_blocks() { return num_sms() * 2; }
+
+int fill_geom(LastGeom* g, int n, int h, int w, int r, int c, int cout, const int32_t* phase_yx_host) {
+  g->n = n; g->h = h; g->w = w; g->r = r; g->c = c; g->cout = cout;
+  for (int i = 0; i < 64; ++i) g->slot_of[i] = 0;
+  for (int s = 0; s < r * r; ++s) {
+    const int py = phase_yx_host[2 * s], px = phase_yx_host[2 * s + 1];
+    if (py < 0 || py >= r || px < 0 || px >= r) return -1;
+    g->slot_of[py * r + px] = s;
+  }
+  return 0;
+}
+
+}  // namespace
+}  // namespace vsr
+
+using namespace vsr;
+
+extern "C" int vsr_conv3x3_first(const float* x, int32_t n, int32_t cin, int32_t h, int32_t w_, const float* w,
+                                 const float* bias, const float* slope, void* y, int32_t dtype, int32_t cout,
+                                 void* stream) {
+  VSR_CHECK_ARG(x && w && y && n > 0 && h > 0 && w_ > 0, "vsr_conv3x3_first: bad arguments");
+  VSR_CHECK_SUPPORTED(cin >= 1 && cin <= kMaxCin, "vsr_conv3x3_first: cin must be in [1,%d]", kMaxCin);
+  VSR_CHECK_SUPPORTED(cout % 8 == 0 && cout > 0, "vsr_conv3x3_first: cout must be a multiple of 8");
+  const size_t smem = ((size_t)cin * 9 * cout + cout) * sizeof(float);
+  VSR_CHECK_SUPPORTED(smem <= 48 * 1024, "vsr_conv3x3_first: cin*cout too large for shared memory");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const long total = (long)n * h * w_ * (cout / 8);
+  const int grid = grid_for(total, 256, 4);
+  if (dtype == VSR_F32)
+    conv_first_kernel<float><<<grid, 256, smem, s>>>(x, n, cin, h, w_, w, bias, slope, (float*)y, cout);
+  else if (dtype == VSR_BF16)
+    conv_first_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>(x, n, cin, h, w_, w, bias, slope, (__nv_bfloat16*)y, cout);
+  else
+    VSR_CHECK_ARG(false, "vsr_conv3x3_first: bad dtype %d", dtype);
+  VSR_CHECK_LAUNCH("vsr_conv3x3_first");
+  return VSR_OK;
+}
+
+extern "C" size_t vsr_conv3x3_first_bwd_workspace(int32_t n, int32_t cin, int32_t h, int32_t w_, int32_t cout) {
+  return (size_t)first_bwd_blocks((long)n * h * w_) * cout * (cin * 9 + 1) * sizeof(float);
+}
+
+extern "C" int vsr_conv3x3_first_bwd(const float* x, int32_t n, int32_t cin, int32_t h, int32_t w_,
+                                     const void* dz, int32_t dtype, int32_t cout, float* dw, float* db,
+                                     int accumulate, void* workspace, size_t workspace_bytes, void* stream) {
+  VSR_CHECK_ARG(x && dz && dw && db && n > 0 && h > 0 && w_ > 0 && cout > 0, "vsr_conv3x3_first_bwd: bad arguments");
+  VSR_CHECK_SUPPORTED(cin >= 1 && cin <= kMaxCin, "vsr_conv3x3_first_bwd: cin must be in [1,%d]", kMaxCin);
+  VSR_CHECK_ARG(workspace && workspace_bytes >= vsr_conv3x3_first_bwd_workspace(n, cin, h, w_, cout),
+                "vsr_conv3x3_first_bwd: workspace too small");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const long pixels = (long)n * h * w_;
+  const int blocks = first_bwd_blocks(pixels);
+  const long ppb = (pixels + blocks - 1) / blocks;
+  const int threads = cout >= 256 ? 256 : ((cout + 31) / 32) * 32;
+  float* ws = static_cast<float*>(workspace);
+  if (dtype == VSR_F32)
+    conv_first_bwd_kernel<float><<<blocks, threads, 0, s>>>(x, n, cin, h, w_, (const float*)dz, cout, ppb, ws);
+  else if (dtype == VSR_BF16)
+    conv_first_bwd_kernel<__nv_bfloat16><<<blocks, threads, 0, s>>>(x, n, cin, h, w_, (const __nv_bfloat16*)dz, cout, ppb, ws);
+  else
+    VSR_CHECK_ARG(false, "vsr_conv3x3_first_bwd: bad dtype %d", dtype);
+  VSR_CHECK_LAUNCH("vsr_conv3x3_first_bwd");
+  const int tot = cout * (cin * 9 + 1);
+  conv_first_bwd_final_kernel<<<(tot + 127) / 128, 128, 0, s>>>(ws, blocks, cout, cin, dw, db, accumulate);
+  VSR_CHECK_LAUNCH("vsr_conv3x3_first_bwd_final");
+  return VSR_OK;
+}
+
+extern "C" int vsr_conv3x3_last(const void* x, int32_t dtype, int32_t n, int32_t h, int32_t w_, int32_t r,
+                                int32_t c, const int32_t* phase_yx, const float* w, const float* bias,
+                                float* y, int32_t cout, void* stream) {
+  VSR_CHECK_ARG(x && w && y && phase_yx && n > 0 && h > 0 && w_ > 0, "vsr_conv3x3_last: bad arguments");
+  VSR_CHECK_SUPPORTED(r >= 1 && r <= 8, "vsr_conv3x3_last: r must be in [1,8]");
+  VSR_CHECK_SUPPORTED(cout >= 1 && cout <= kMaxCoutLast, "vsr_conv3x3_last: cout must be in [1,%d]", kMaxCoutLast);
+  LastGeom g;
+  VSR_CHECK_ARG(fill_geom(&g, n, h, w_, r, c, cout, phase_yx) == 0, "vsr_conv3x3_last: bad phase table");
+  const size_t smem = (size_t)cout * 9 * c * sizeof(float);
+  VSR_CHECK_SUPPORTED(smem <= 48 * 1024, "vsr_conv3x3_last: cout*c too large");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const long total = (long)n * h * r * w_ * r;
+  const int grid = grid_for(total, 8, 8);
+  if (dtype == VSR_F32)
+    conv_last_kernel<float><<<grid, 256, smem, s>>>((const float*)x, g, w, bias, y);
+  else if (dtype == VSR_BF16)
+    conv_last_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>((const __nv_bfloat16*)x, g, w, bias, y);
+  else
+    VSR_CHECK_ARG(false, "vsr_conv3x3_last: bad dtype %d", dtype);
+  VSR_CHECK_LAUNCH("vsr_conv3x3_last");
+  return VSR_OK;
+}
+
+extern "C" size_t vsr_conv3x3_last_bwd_workspace(int32_t n, int32_t h, int32_t w_, int32_t r, int32_t c,
+                                                 int32_t cout) {
+  (void)n; (void)h; (void)w_; (void)r;
+  return (size_t)last_bwd_blocks() * ((size_t)cout * 9 * c + cout) * sizeof(float);
+}
+
+extern "C" int vsr_conv3x3_last_bwd(const void* x, int32_t dtype, int32_t n, int32_t h, int32_t w_, int32_t r,
+                                    int32_t c, const int32_t* phase_yx, const float* w, const float* dy,
+                                    int32_t cout, void* dx, float* dw, float* db, int accumulate,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
+  VSR_CHECK_ARG(x && w && dy && dx && dw && db && phase_yx, "vsr_conv3x3_last_bwd: bad arguments");
+  VSR_CHECK_SUPPORTED(r >= 1 && r <= 8, "vsr_conv3x3_last_bwd: r must be in [1,8]");
+  const int cpl = (c + 31) / 32;
+  VSR_CHECK_SUPPORTED(cout >= 1 && cout * cpl <= 4, "vsr_conv3x3_last_bwd: cout*ceil(c/32) must be <= 4 (got %d*%d)", cout, cpl);
+  VSR_CHECK_ARG(workspace && workspace_bytes >= vsr_conv3x3_last_bwd_workspace(n, h, w_, r, c, cout),
+                "vsr_conv3x3_last_bwd: workspace too small");
+  LastGeom g;
+  VSR_CHECK_ARG(fill_geom(&g, n, h, w_, r, c, cout, phase_yx) == 0, "vsr_conv3x3_last_bwd: bad phase table");
+  const int nw = kLastBwdThreads / 32;
+  const size_t psz = (size_t)cout * 9 * c + cout;
+  const size_t smem = ((size_t)cout * 9 * c + nw * psz) * sizeof(float);
+  VSR_CHECK_SUPPORTED(smem <= 48 * 1024, "vsr_conv3x3_last_bwd: shared memory need too large");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int blocks = last_bwd_blocks();
+  float* ws = static_cast<float*>(workspace);
+  if (dtype == VSR_F32)
+    conv_last_bwd_kernel<float><<<blocks, kLastBwdThreads, smem, s>>>((const float*)x, g, w, dy, (float*)dx, ws, cpl);
+  else if (dtype == VSR_BF16)
+    conv_last_bwd_kernel<__nv_bfloat16><<<blocks, kLastBwdThreads, smem, s>>>((const __nv_bfloat16*)x, g, w, dy, (__nv_bfloat16*)dx, ws, cpl);
+  else
+    VSR_CHECK_ARG(false, "vsr_conv3x3_last_bwd: bad dtype %d", dtype);
+  VSR_CHECK_LAUNCH("vsr_conv3x3_last_bwd");
+  conv_last_bwd_final_kernel<<<((int)psz + 127) / 128, 128, 0, s>>>(ws, blocks, cout, c, dw, db, accumulate);
+  VSR_CHECK_LAUNCH("vsr_conv3x3_last_bwd_final");
+  return VSR_OK;
+}

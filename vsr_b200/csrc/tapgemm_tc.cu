@@ -1,0 +1,447 @@
+// tapgemm_tc.cu — bf16 tap-GEMM on tcgen05 tensor cores (sm_100a).
+//
+// One persistent CTA per SM.  A work tile is 128 output pixels (a bw x bh box of one image)
+// times the `nt` output channels of one group.  Per tap the producer thread issues one 4-D TMA
+// box load of the (shifted) source pixels [128 x 64 ch] (out-of-image pixels are zero-filled by
+// the TMA unit, which is the convolution padding) and one bulk copy of the tap's pre-swizzled
+// weight slab [nt x 64]; a single thread issues 4 tcgen05.mma (128 x nt x 16) per tap into a
+// TMEM accumulator; four epilogue warps drain the other TMEM accumulator of the previous tile
+// (bias / residual / PReLU / PReLU-backward / second output) while the next tile's MMAs run.
+//
+// Replaces aten.convolution / convolution_backward(data) under drf_net.py:55-106,141-147.
+#include <cuda.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+#include "ptx_sm100.cuh"
+
+namespace vsr {
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kKc = 64;                       // bf16 channels per tap = one 128-byte row
+constexpr int kATileBytes = kBlockM * 128;    // 16 KiB
+constexpr int kMaxStages = 8;
+constexpr int kSmemBudget = 227 * 1024;
+constexpr int kCtrlBytes = 1024;              // barriers + tmem pointer + reduction scratch
+constexpr int kTmemCols = 512;
+constexpr int kThreads = 192;                 // warp0 TMA, warp1 MMA, warps2-5 epilogue
+
+struct TcArgs {
+  CUtensorMap maps[VSR_MAX_SRCS];
+  const int4* tap_tab;
+  const int4* group_tab;
+  const uint8_t* w;
+  const float* bias;
+  const float* slope;
+  const __nv_bfloat16* residual;
+  const __nv_bfloat16* aux_y;
+  __nv_bfloat16* out;
+  __nv_bfloat16* out2;
+  const __nv_bfloat16* res2;
+  float* slope_partials;
+  float out_scale;
+  int epi;
+  int nt, n_groups;
+  int N, H, W, Cout;
+  int bw, bh, tiles_x, tiles_y;
+  int num_tiles;
+  int stages;
+};
+
+struct TileCoord {
+  int g, n, y0, x0;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const TcArgs& a, int tile) {
+  TileCoord t;
+  t.g = tile % a.n_groups;
+  int mt = tile / a.n_groups;
+  const int tx = mt % a.tiles_x;
+  mt /= a.tiles_x;
+  const int ty = mt % a.tiles_y;
+  t.n = mt / a.tiles_y;
+  t.x0 = tx * a.bw;
+  t.y0 = ty * a.bh;
+  return t;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& q, float* f) {
+  f[0] = bf16_lo(q.x); f[1] = bf16_hi(q.x);
+  f[2] = bf16_lo(q.y); f[3] = bf16_hi(q.y);
+  f[4] = bf16_lo(q.z); f[5] = bf16_hi(q.z);
+  f[6] = bf16_lo(q.w); f[7] = bf16_hi(q.w);
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 q;
+  q.x = pack_bf16x2(f[0], f[1]);
+  q.y = pack_bf16x2(f[2], f[3]);
+  q.z = pack_bf16x2(f[4], f[5]);
+  q.w = pack_bf16x2(f[6], f[7]);
+  return q;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) tapgemm_tc_kernel(const __grid_constant__ TcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+
+  // control block
+  const uint32_t full_bar = smem_base;                     // kMaxStages x 8 B
+  const uint32_t empty_bar = smem_base + 64;               // kMaxStages x 8 B
+  const uint32_t tfull_bar = smem_base + 128;              // 2 x 8 B
+  const uint32_t tempty_bar = smem_base + 144;             // 2 x 8 B
+  const uint32_t tmem_slot = smem_base + 160;              // u32
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + 160);
+  float* red = reinterpret_cast<float*>(smem_gen + 192);   // 4 floats
+  const uint32_t stage_base = smem_base + kCtrlBytes;
+  const uint32_t b_bytes = static_cast<uint32_t>(a.nt) * 128u;
+  const uint32_t stage_bytes = kATileBytes + b_bytes;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < a.stages; ++s) {
+      ptx::mbar_init(full_bar + 8 * s, 1);
+      ptx::mbar_init(empty_bar + 8 * s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(tfull_bar + 8 * b, 1);
+      ptx::mbar_init(tempty_bar + 8 * b, 128);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(a, tile);
+        const int4 grp = __ldg(a.group_tab + tc.g);
+        for (int t = 0; t < grp.z; ++t) {
+          const int4 tap = __ldg(a.tap_tab + grp.y + t);
+          ptx::mbar_wait(empty_bar + 8 * stage, phase ^ 1u);
+          const uint32_t fb = full_bar + 8 * stage;
+          ptx::mbar_arrive_expect_tx(fb, stage_bytes);
+          const uint32_t sa = stage_base + stage * stage_bytes;
+          ptx::tma_load_4d(sa, &a.maps[tap.x], fb, tap.w, tc.x0 + tap.z, tc.y0 + tap.y, tc.n);
+          ptx::bulk_load(sa + kATileBytes, a.w + static_cast<size_t>(grp.y + t) * b_bytes, b_bytes,
+                         fb);
+          if (++stage == a.stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      const uint32_t idesc = ptx::make_idesc_bf16(kBlockM, a.nt, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
+        const TileCoord tc = decode_tile(a, tile);
+        const int4 grp = __ldg(a.group_tab + tc.g);
+        const int buf = it & 1;
+        const uint32_t bphase = (it >> 1) & 1;
+        ptx::mbar_wait(tempty_bar + 8 * buf, bphase ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * a.nt);
+        for (int t = 0; t < grp.z; ++t) {
+          ptx::mbar_wait(full_bar + 8 * stage, phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = stage_base + stage * stage_bytes;
+          const uint64_t adesc = ptx::make_sw128_desc(sa, 16, 1024);
+          const uint64_t bdesc = ptx::make_sw128_desc(sa + kATileBytes, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < kKc / 16; ++k) {
+            // advancing K by 16 bf16 = 32 bytes = 2 descriptor address units
+            ptx::mma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (t | k) != 0);
+          }
+          ptx::mma_commit(empty_bar + 8 * stage);
+          if (++stage == a.stages) { stage = 0; phase ^= 1u; }
+        }
+        ptx::mma_commit(tfull_bar + 8 * buf);
+      }
+    }
+  } else {
+    // ===================== epilogue (4 warps, one TMEM lane quarter each) =====================
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int ry = row / a.bw, rx = row % a.bw;
+    const float slope = (a.epi & (VSR_EPI_PRELU | VSR_EPI_PRELU_BWD)) ? __ldg(a.slope) : 0.f;
+    const float inv_slope = slope != 0.f ? 1.f / slope : 0.f;
+    float slope_acc = 0.f;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
+      const TileCoord tc = decode_tile(a, tile);
+      const int4 grp = __ldg(a.group_tab + tc.g);
+      const int buf = it & 1;
+      const uint32_t bphase = (it >> 1) & 1;
+      const int y = tc.y0 + ry, x = tc.x0 + rx;
+      const bool valid = (y < a.H) && (x < a.W);
+      const size_t rowoff =
+          ((static_cast<size_t>(tc.n) * a.H + y) * a.W + x) * static_cast<size_t>(a.Cout) + grp.x;
+      ptx::mbar_wait(tfull_bar + 8 * buf, bphase);
+      ptx::tc_fence_after();
+      const uint32_t taddr =
+          tmem_base + static_cast<uint32_t>(buf * a.nt) + (static_cast<uint32_t>(quarter * 32) << 16);
+      for (int c = 0; c < a.nt; c += 16) {
+        uint32_t r[16];
+        ptx::tmem_ld16(taddr + c, r);
+        ptx::tmem_ld_wait();
+        if (valid) {
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+          if (a.epi & VSR_EPI_BIAS) {
+            const float4* bp = reinterpret_cast<const float4*>(a.bias + grp.x + c);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 b = __ldg(bp + i);
+              v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+            }
+          }
+          if (a.epi & VSR_EPI_SCALE) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] *= a.out_scale;
+          }
+          if (a.epi & VSR_EPI_RES_PRE) {
+            const uint4* rp = reinterpret_cast<const uint4*>(a.residual + rowoff + c);
+            float f[16];
+            unpack8(__ldg(rp), f);
+            unpack8(__ldg(rp + 1), f + 8);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += f[i];
+          }
+          if (a.epi & VSR_EPI_PRELU) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.f ? v[i] : slope * v[i];
+          }
+          if (a.epi & VSR_EPI_RELU) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
+          if (a.epi & (VSR_EPI_PRELU_BWD | VSR_EPI_RELU_BWD)) {
+            const uint4* yp = reinterpret_cast<const uint4*>(a.aux_y + rowoff + c);
+            float f[16];
+            unpack8(__ldg(yp), f);
+            unpack8(__ldg(yp + 1), f + 8);
+            if (a.epi & VSR_EPI_PRELU_BWD) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const bool pos = f[i] > 0.f;
+                slope_acc += pos ? 0.f : v[i] * (f[i] * inv_slope);
+                v[i] = pos ? v[i] : slope * v[i];
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = f[i] > 0.f ? v[i] : 0.f;
+            }
+          }
+          uint4* op = reinterpret_cast<uint4*>(a.out + rowoff + c);
+          op[0] = pack8(v);
+          op[1] = pack8(v + 8);
+          if (a.epi & VSR_EPI_OUT2) {
+            const uint4* rp = reinterpret_cast<const uint4*>(a.res2 + rowoff + c);
+            float f[16];
+            unpack8(__ldg(rp), f);
+            unpack8(__ldg(rp + 1), f + 8);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] += v[i];
+            uint4* o2 = reinterpret_cast<uint4*>(a.out2 + rowoff + c);
+            o2[0] = pack8(f);
+            o2[1] = pack8(f + 8);
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(tempty_bar + 8 * buf);
+    }
+    if (a.epi & VSR_EPI_PRELU_BWD) {
+      slope_acc = warp_sum(slope_acc);
+      if (lane == 0) red[quarter] = slope_acc;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (warp == 2 && lane == 0) a.slope_partials[blockIdx.x] = (red[0] + red[1]) + (red[2] + red[3]);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr;
+  int n, h, w, c, bw, bh;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && n == o.n && h == o.h && w == o.w && c == o.c && bw == o.bw && bh == o.bh;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    auto mix = [&h](size_t v) { h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
+    mix(k.n); mix(k.h); mix(k.w); mix(k.c); mix(k.bw); mix(k.bh);
+    return h;
+  }
+};
+
+std::mutex g_map_mu;
+std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_map_cache;
+
+// 4-D bf16 map over a dense [n][h][w][c] map; box = 64 channels x bw x bh x 1, 128B swizzle.
+int get_src_map(const VsrTensor4& t, int bw, int bh, CUtensorMap* out) {
+  MapKey key{t.ptr, t.n, t.h, t.w, t.c, bw, bh};
+  {
+    std::lock_guard<std::mutex> lk(g_map_mu);
+    auto it = g_map_cache.find(key);
+    if (it != g_map_cache.end()) {
+      *out = it->second;
+      return VSR_OK;
+    }
+  }
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return VSR_ERR_DRIVER;
+  }
+  cuuint64_t dims[4] = {(cuuint64_t)t.c, (cuuint64_t)t.w, (cuuint64_t)t.h, (cuuint64_t)t.n};
+  cuuint64_t strides[3] = {(cuuint64_t)t.c * 2, (cuuint64_t)t.w * t.c * 2,
+                           (cuuint64_t)t.h * t.w * t.c * 2};
+  cuuint32_t box[4] = {(cuuint32_t)kKc, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, t.ptr, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) for [%d,%d,%d,%d] box %dx%d", (int)r, t.n, t.h,
+              t.w, t.c, bw, bh);
+    return VSR_ERR_DRIVER;
+  }
+  {
+    std::lock_guard<std::mutex> lk(g_map_mu);
+    if (g_map_cache.size() > 16384) g_map_cache.clear();
+    g_map_cache.emplace(key, m);
+  }
+  *out = m;
+  return VSR_OK;
+}
+
+// pick the pixel box (bw x bh = 128) that wastes the fewest MMA rows
+void pick_box(int h, int w, int* bw_out, int* bh_out) {
+  long best = -1;
+  int best_bw = 128;
+  for (int bw = 128; bw >= 1; bw >>= 1) {
+    const int bh = kBlockM / bw;
+    if (bh > 256) break;
+    const long tx = (w + bw - 1) / bw, ty = (h + bh - 1) / bh;
+    const long cost = tx * ty;
+    if (best < 0 || cost < best) {
+      best = cost;
+      best_bw = bw;
+    }
+  }
+  *bw_out = best_bw;
+  *bh_out = kBlockM / best_bw;
+}
+
+}  // namespace
+
+int tapgemm_tc_launch(const VsrTapGemmDesc* d, cudaStream_t stream) {
+  VSR_CHECK_SUPPORTED(d->kc == kKc, "tapgemm(bf16): kc must be 64, got %d", d->kc);
+  VSR_CHECK_SUPPORTED(d->nt >= 16 && d->nt <= 256 && d->nt % 16 == 0,
+                      "tapgemm(bf16): nt must be a multiple of 16 in [16,256], got %d", d->nt);
+  VSR_CHECK_ARG(d->out.c % 8 == 0, "tapgemm(bf16): out.c must be a multiple of 8");
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(smem) failed: %s", cudaGetErrorString(e));
+      return VSR_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  TcArgs a;
+  memset(&a, 0, sizeof(a));
+  int bw, bh;
+  pick_box(d->out.h, d->out.w, &bw, &bh);
+  for (int s = 0; s < d->n_srcs; ++s) {
+    VSR_CHECK_ARG(d->srcs[s].c % 8 == 0, "tapgemm(bf16): src channels must be a multiple of 8");
+    int rc = get_src_map(d->srcs[s], bw, bh, &a.maps[s]);
+    if (rc != VSR_OK) return rc;
+  }
+  a.tap_tab = reinterpret_cast<const int4*>(d->tap_tab);
+  a.group_tab = reinterpret_cast<const int4*>(d->group_tab);
+  a.w = static_cast<const uint8_t*>(d->w);
+  a.bias = d->bias;
+  a.slope = d->slope;
+  a.residual = static_cast<const __nv_bfloat16*>(d->residual);
+  a.aux_y = static_cast<const __nv_bfloat16*>(d->aux_y);
+  a.out = static_cast<__nv_bfloat16*>(d->out.ptr);
+  a.out2 = static_cast<__nv_bfloat16*>(d->out2);
+  a.res2 = static_cast<const __nv_bfloat16*>(d->res2);
+  a.slope_partials = d->slope_partials;
+  a.out_scale = d->out_scale;
+  a.epi = d->epi;
+  a.nt = d->nt;
+  a.n_groups = d->n_groups;
+  a.N = d->out.n; a.H = d->out.h; a.W = d->out.w; a.Cout = d->out.c;
+  a.bw = bw; a.bh = bh;
+  a.tiles_x = (a.W + bw - 1) / bw;
+  a.tiles_y = (a.H + bh - 1) / bh;
+  const long tiles = (long)a.n_groups * a.N * a.tiles_x * a.tiles_y;
+  VSR_CHECK_SUPPORTED(tiles < (1l << 30), "tapgemm(bf16): too many tiles");
+  a.num_tiles = (int)tiles;
+  const int stage_bytes = kATileBytes + d->nt * 128;
+  int stages = (kSmemBudget - kCtrlBytes - 1024) / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  a.stages = stages;
+  const int smem = kCtrlBytes + 1024 + stages * stage_bytes;
+  int grid = num_sms();
+  if (grid > a.num_tiles) grid = a.num_tiles;
+  if (grid > kPartialsLen) grid = kPartialsLen;
+  tapgemm_tc_kernel<<<grid, kThreads, smem, stream>>>(a);
+  VSR_CHECK_LAUNCH("tapgemm_tc");
+  return VSR_OK;
+}
+
+}  // namespace vsr

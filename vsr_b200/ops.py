@@ -1,0 +1,295 @@
+"""Tensor-level wrappers over the C-ABI (include/vsr_b200.h).  PyTorch is used here only for
+device memory and streams; every function launches hand-written sm_100a kernels and raises
+VsrError if the shared library is missing or a call fails.  No CPU path exists.
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import (EPI_BIAS, EPI_OUT2, EPI_PRELU, EPI_PRELU_BWD, EPI_RELU, EPI_RELU_BWD,  # noqa: F401
+                   EPI_RES_PRE, EPI_SCALE, VSR_BF16, VSR_F32, VsrTapGemmDesc, VsrTensor4, check)
+
+_DT = {torch.float32: VSR_F32, torch.bfloat16: VSR_BF16}
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t: Optional[torch.Tensor]):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.VsrError("vsr_b200 ops need CUDA tensors (there is no CPU fallback)")
+        if t is not None and not t.is_contiguous():
+            raise _lib.VsrError("vsr_b200 ops need contiguous tensors")
+
+
+@dataclass
+class TapTable:
+    """Host description of a tap-GEMM: groups of (o0, [(src, dy, dx, c0), ...])."""
+    kc: int
+    nt: int
+    groups: List[Tuple[int, List[Tuple[int, int, int, int]]]]
+    _dev: dict = field(default_factory=dict, repr=False)
+
+    @property
+    def n_groups(self):
+        return len(self.groups)
+
+    @property
+    def n_taps_total(self):
+        return sum(len(t) for _, t in self.groups)
+
+    def flat_taps(self):
+        return [t for _, taps in self.groups for t in taps]
+
+    def device_tabs(self, device):
+        key = str(device)
+        if key not in self._dev:
+            g_rows, t_rows, begin = [], [], 0
+            for o0, taps in self.groups:
+                g_rows.append([o0, begin, len(taps), 0])
+                begin += len(taps)
+                t_rows.extend([list(t) for t in taps])
+            self._dev[key] = (torch.tensor(g_rows, dtype=torch.int32, device=device),
+                              torch.tensor(t_rows, dtype=torch.int32, device=device))
+        return self._dev[key]
+
+
+def _tensor4(t: torch.Tensor) -> VsrTensor4:
+    n, h, w, c = t.shape
+    return VsrTensor4(t.data_ptr(), n, h, w, c)
+
+
+def _make_desc(tab: TapTable, srcs: Sequence[torch.Tensor], out: torch.Tensor):
+    if len(srcs) > _lib.VSR_MAX_SRCS:
+        raise _lib.VsrError(f"tap-GEMM takes at most {_lib.VSR_MAX_SRCS} sources")
+    _need_cuda(out, *srcs)
+    d = VsrTapGemmDesc()
+    d.dtype = _DT[out.dtype]
+    d.kc, d.nt, d.n_srcs = tab.kc, tab.nt, len(srcs)
+    for i, s in enumerate(srcs):
+        if s.dtype != out.dtype:
+            raise _lib.VsrError("tap-GEMM sources and output must share a dtype")
+        d.srcs[i] = _tensor4(s)
+    d.out = _tensor4(out)
+    gt, tt = tab.device_tabs(out.device)
+    d.n_groups, d.n_taps_total = tab.n_groups, tab.n_taps_total
+    d.group_tab, d.tap_tab = gt.data_ptr(), tt.data_ptr()
+    return d
+
+
+class CudaOps:
+    """The product backend: every method is one or two kernel launches on the current stream."""
+    name = "cuda"
+
+    def __init__(self):
+        self.lib = _lib.lib()
+        self.partials_len = self.lib.vsr_partials_len()
+        self.launches = 0
+
+    # ---- tap-GEMM ----------------------------------------------------------------------
+    def tapgemm(self, tab, srcs, out, w, bias=None, epi=0, out_scale=1.0, slope=None, residual=None,
+                aux_y=None, out2=None, res2=None, slope_partials=None, force_simt=False):
+        d = _make_desc(tab, srcs, out)
+        _need_cuda(w, bias, slope, residual, aux_y, out2, res2, slope_partials)
+        d.w, d.bias = w.data_ptr(), (bias.data_ptr() if bias is not None else None)
+        d.epi, d.out_scale = epi, out_scale
+        d.slope = slope.data_ptr() if slope is not None else None
+        d.residual = residual.data_ptr() if residual is not None else None
+        d.aux_y = aux_y.data_ptr() if aux_y is not None else None
+        d.out2 = out2.data_ptr() if out2 is not None else None
+        d.res2 = res2.data_ptr() if res2 is not None else None
+        d.slope_partials = slope_partials.data_ptr() if slope_partials is not None else None
+        fn = self.lib.vsr_tapgemm_simt_bf16 if force_simt else self.lib.vsr_tapgemm
+        check(fn(C.byref(d), _stream()), "vsr_tapgemm")
+        self.launches += 1
+
+    def tapgemm_wgrad_workspace(self, tab, srcs, dz):
+        return self.lib.vsr_tapgemm_wgrad_workspace(C.byref(_make_desc(tab, srcs, dz)))
+
+    def tapgemm_wgrad(self, tab, srcs, dz, dw, accumulate, workspace):
+        d = _make_desc(tab, srcs, dz)
+        _need_cuda(dw, workspace)
+        check(self.lib.vsr_tapgemm_wgrad(C.byref(d), _p(dw), int(accumulate), _p(workspace),
+                                         workspace.numel() * workspace.element_size(), _stream()),
+              "vsr_tapgemm_wgrad")
+        self.launches += 2
+
+    # ---- small kernels -----------------------------------------------------------------
+    def colsum_workspace(self, rows, c):
+        return self.lib.vsr_colsum_workspace(rows, c)
+
+    def colsum(self, x, rows, c, db, accumulate, workspace):
+        _need_cuda(x, db, workspace)
+        check(self.lib.vsr_colsum(_p(x), _DT[x.dtype], rows, c, _p(db), int(accumulate), _p(workspace),
+                                  workspace.numel() * workspace.element_size(), _stream()), "vsr_colsum")
+        self.launches += 2
+
+    def conv3x3_first(self, x, w, bias, slope, y):
+        _need_cuda(x, w, bias, slope, y)
+        n, cin, h, w_ = x.shape
+        check(self.lib.vsr_conv3x3_first(_p(x), n, cin, h, w_, _p(w), _p(bias), _p(slope), _p(y),
+                                         _DT[y.dtype], y.shape[-1], _stream()), "vsr_conv3x3_first")
+        self.launches += 1
+
+    def conv3x3_first_bwd_workspace(self, x, cout):
+        n, cin, h, w_ = x.shape
+        return self.lib.vsr_conv3x3_first_bwd_workspace(n, cin, h, w_, cout)
+
+    def conv3x3_first_bwd(self, x, dz, dw, db, accumulate, workspace):
+        _need_cuda(x, dz, dw, db, workspace)
+        n, cin, h, w_ = x.shape
+        check(self.lib.vsr_conv3x3_first_bwd(_p(x), n, cin, h, w_, _p(dz), _DT[dz.dtype], dz.shape[-1],
+                                             _p(dw), _p(db), int(accumulate), _p(workspace),
+                                             workspace.numel() * workspace.element_size(), _stream()),
+              "vsr_conv3x3_first_bwd")
+        self.launches += 2
+
+    @staticmethod
+    def _phase_arr(phase_yx):
+        flat = [v for yx in phase_yx for v in yx]
+        return (C.c_int32 * len(flat))(*flat)
+
+    def conv3x3_last(self, x, r, c, phase_yx, w, bias, y):
+        _need_cuda(x, w, bias, y)
+        n, h, w_, _ = x.shape
+        check(self.lib.vsr_conv3x3_last(_p(x), _DT[x.dtype], n, h, w_, r, c, self._phase_arr(phase_yx),
+                                        _p(w), _p(bias), _p(y), y.shape[1], _stream()), "vsr_conv3x3_last")
+        self.launches += 1
+
+    def conv3x3_last_bwd_workspace(self, x, r, c, cout):
+        n, h, w_, _ = x.shape
+        return self.lib.vsr_conv3x3_last_bwd_workspace(n, h, w_, r, c, cout)
+
+    def conv3x3_last_bwd(self, x, r, c, phase_yx, w, dy, dx, dw, db, accumulate, workspace):
+        _need_cuda(x, w, dy, dx, dw, db, workspace)
+        n, h, w_, _ = x.shape
+        check(self.lib.vsr_conv3x3_last_bwd(_p(x), _DT[x.dtype], n, h, w_, r, c, self._phase_arr(phase_yx),
+                                            _p(w), _p(dy), dy.shape[1], _p(dx), _p(dw), _p(db),
+                                            int(accumulate), _p(workspace),
+                                            workspace.numel() * workspace.element_size(), _stream()),
+              "vsr_conv3x3_last_bwd")
+        self.launches += 2
+
+    def act_bwd(self, dy, y, dz, slope=None, slope_partials=None):
+        _need_cuda(dy, y, dz, slope, slope_partials)
+        check(self.lib.vsr_act_bwd(_p(dy), _p(y), _p(dz), _DT[dy.dtype], dy.numel(), _p(slope),
+                                   _p(slope_partials), _stream()), "vsr_act_bwd")
+        self.launches += 1
+
+    def add(self, a, b, out):
+        _need_cuda(a, b, out)
+        check(self.lib.vsr_add(_p(a), _p(b), _p(out), _DT[a.dtype], a.numel(), _stream()), "vsr_add")
+        self.launches += 1
+
+    def reduce_partials(self, partials, rows, row_dst, dst):
+        _need_cuda(partials, row_dst, dst)
+        check(self.lib.vsr_reduce_partials(_p(partials), rows, partials.shape[-1], _p(row_dst), _p(dst),
+                                           _stream()), "vsr_reduce_partials")
+        self.launches += 1
+
+    def gather(self, src, idx, dst):
+        _need_cuda(src, idx, dst)
+        check(self.lib.vsr_gather(_p(src), _p(idx), _p(dst), _DT[dst.dtype], idx.numel(), _stream()),
+              "vsr_gather")
+        self.launches += 1
+
+    def gather_add(self, src, idx, dst):
+        _need_cuda(src, idx, dst)
+        check(self.lib.vsr_gather_add(_p(src), _p(idx), _p(dst), idx.numel(), _stream()), "vsr_gather_add")
+        self.launches += 1
+
+    def cast(self, src, dst):
+        _need_cuda(src, dst)
+        check(self.lib.vsr_cast(_p(src), _DT[src.dtype], _p(dst), _DT[dst.dtype], src.numel(), _stream()),
+              "vsr_cast")
+        self.launches += 1
+
+    def zero_(self, t):
+        t.zero_()  # cudaMemsetAsync on the current stream
+
+    # ---- loss / metrics ----------------------------------------------------------------
+    def loss_fwd_bwd(self, out, target, kind, param, grad_scale, partials, grad):
+        _need_cuda(out, target, partials, grad)
+        check(self.lib.vsr_loss_fwd_bwd(_p(out), _p(target), out.numel(), kind, param, grad_scale,
+                                        _p(partials), _p(grad), _stream()), "vsr_loss_fwd_bwd")
+        self.launches += 1
+
+    def metric_workspace(self, n, per_sample):
+        return self.lib.vsr_metric_workspace(n, per_sample)
+
+    def psnr(self, out, target, mean, std, max_value, psnr_out, workspace):
+        _need_cuda(out, target, psnr_out, workspace)
+        n = out.shape[0]
+        check(self.lib.vsr_psnr(_p(out), _p(target), n, out.numel() // n, mean, std, max_value,
+                                _p(psnr_out), _p(workspace), workspace.numel() * workspace.element_size(),
+                                _stream()), "vsr_psnr")
+        self.launches += 2
+
+    def ssim(self, out, target, win11, mean, std, c1, c2, ssim_out, workspace):
+        _need_cuda(out, target, win11, ssim_out, workspace)
+        n, h, w_ = out.shape[0], out.shape[-2], out.shape[-1]
+        check(self.lib.vsr_ssim(_p(out), _p(target), n, h, w_, _p(win11), mean, std, c1, c2, _p(ssim_out),
+                                _p(workspace), workspace.numel() * workspace.element_size(), _stream()),
+              "vsr_ssim")
+        self.launches += 2
+
+    # ---- standalone resampling / optimiser ------------------------------------------------
+    def pixel_shuffle(self, x, y, r, inverse=False):
+        _need_cuda(x, y)
+        if not inverse:
+            n, cr2, h, w_ = x.shape
+            c = cr2 // (r * r)
+        else:
+            n, c, hh, ww = x.shape
+            h, w_ = hh // r, ww // r
+        check(self.lib.vsr_pixel_shuffle(_p(x), _p(y), n, c, h, w_, r, int(inverse), _stream()),
+              "vsr_pixel_shuffle")
+        self.launches += 1
+
+    def upsample_linear(self, x, y, align_corners):
+        _need_cuda(x, y)
+        d, h, w_ = (1, *x.shape[-2:]) if x.dim() == 4 else x.shape[-3:]
+        od, oh, ow = (1, *y.shape[-2:]) if y.dim() == 4 else y.shape[-3:]
+        nc = x.shape[0] * x.shape[1]
+        check(self.lib.vsr_upsample_linear(_p(x), _p(y), nc, d, h, w_, od, oh, ow, int(align_corners),
+                                           _stream()), "vsr_upsample_linear")
+        self.launches += 1
+
+    def upsample_linear_bwd(self, dy, dx, align_corners):
+        _need_cuda(dy, dx)
+        d, h, w_ = (1, *dx.shape[-2:]) if dx.dim() == 4 else dx.shape[-3:]
+        od, oh, ow = (1, *dy.shape[-2:]) if dy.dim() == 4 else dy.shape[-3:]
+        nc = dx.shape[0] * dx.shape[1]
+        check(self.lib.vsr_upsample_linear_bwd(_p(dy), _p(dx), nc, d, h, w_, od, oh, ow,
+                                               int(align_corners), _stream()), "vsr_upsample_linear_bwd")
+        self.launches += 1
+
+    def adam_flat(self, p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
+        _need_cuda(p, g, m, v)
+        check(self.lib.vsr_adam_flat(_p(p), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps,
+                                     weight_decay, step, grad_scale, _stream()), "vsr_adam_flat")
+        self.launches += 1
+
+
+_OPS = None
+
+
+def cuda_ops() -> CudaOps:
+    global _OPS
+    if _OPS is None:
+        _OPS = CudaOps()
+    return _OPS
+
+
+def slab_index(j, k):
+    """Element offset of (row j, k) in the swizzled bf16 [nt][64] slab image (vsr_slab_index)."""
+    return j * 64 + (((k >> 3) ^ (j & 7)) << 3) + (k & 7)
