@@ -1,0 +1,177 @@
+"""TEST INFRASTRUCTURE — plain-torch CPU restatement of the reference's SR hot path.
+
+Functional (no nn.Module): every function takes the reference's own state_dict (same keys,
+shapes, layouts) and follows the cited reference lines.  All arithmetic is torch CPU ops in the
+dtype of the inputs (fp32, or fp64 for the high-precision oracle).  The algorithmic content of
+`torch.nn.Conv2d / ConvTranspose2d / PReLU / PixelShuffle` lives in PyTorch (pinned by the
+reference to pytorch=1.1.0, env.yml:150; torch 2.11 here — semantics unchanged for these ops).
+
+Pinned against golden vectors produced by the real reference (oracle/make_golden.py ->
+tests/golden/, checked in tests/test_oracle.py).
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+# (kernel, stride, padding) of the projection pair per upscale factor — drf_net.py:70-77
+PROJ = {2: (6, 2, 2), 3: (7, 3, 2), 4: (8, 4, 2), 8: (12, 8, 2)}
+
+
+def _prelu(x, sd, key):
+    # nn.PReLU(num_parameters=1) — drf_net.py:56,58,66,...
+    return F.prelu(x, sd[key + ".weight"])
+
+
+def _conv(x, sd, key, **kw):
+    return F.conv2d(x, sd[key + ".weight"], sd[key + ".bias"], **kw)
+
+
+def _deconv(x, sd, key, **kw):
+    return F.conv_transpose2d(x, sd[key + ".weight"], sd[key + ".bias"], **kw)
+
+
+def num_groups_of(sd):
+    g = 0
+    while f"f_block.down_blocks.{g}.prelu.weight" in sd or f"f_block.down_blocks.{g}.prelu2.weight" in sd:
+        g += 1
+    return g
+
+
+def in_block(x, sd, p="in_block"):
+    # _InBlock — drf_net.py:52-58: conv3x3(p=1) + PReLU, conv1x1 + PReLU
+    x = _prelu(_conv(x, sd, f"{p}.conv1", padding=1), sd, f"{p}.prelu1")
+    return _prelu(_conv(x, sd, f"{p}.conv2"), sd, f"{p}.prelu2")
+
+
+def f_block(x, hidden, sd, upscale, p="f_block"):
+    # _FBlock.forward — drf_net.py:118-133
+    k, s, pad = PROJ[upscale]
+    G = num_groups_of(sd) if p == "f_block" else None
+    feats = torch.cat([x, hidden], dim=1)                                            # :119
+    lr = _prelu(_conv(feats, sd, f"{p}.in_block.conv"), sd, f"{p}.in_block.prelu")   # :120
+    lr_list, hr_list = [lr], []
+    g = 0
+    while True:
+        if f"{p}.up_blocks.{g}.deconv.weight" in sd:                                 # i == 0, :79-88
+            hr = _prelu(_deconv(torch.cat(lr_list, 1), sd, f"{p}.up_blocks.{g}.deconv", stride=s, padding=pad),
+                        sd, f"{p}.up_blocks.{g}.prelu")
+            hr_list.append(hr)
+            lr = _prelu(_conv(torch.cat(hr_list, 1), sd, f"{p}.down_blocks.{g}.conv", stride=s, padding=pad),
+                        sd, f"{p}.down_blocks.{g}.prelu")
+        elif f"{p}.up_blocks.{g}.conv1.weight" in sd:                                # i > 0, :89-102
+            t = _prelu(_conv(torch.cat(lr_list, 1), sd, f"{p}.up_blocks.{g}.conv1"), sd, f"{p}.up_blocks.{g}.prelu1")
+            hr = _prelu(_deconv(t, sd, f"{p}.up_blocks.{g}.deconv2", stride=s, padding=pad),
+                        sd, f"{p}.up_blocks.{g}.prelu2")
+            hr_list.append(hr)
+            t = _prelu(_conv(torch.cat(hr_list, 1), sd, f"{p}.down_blocks.{g}.conv1"), sd, f"{p}.down_blocks.{g}.prelu1")
+            lr = _prelu(_conv(t, sd, f"{p}.down_blocks.{g}.conv2", stride=s, padding=pad),
+                        sd, f"{p}.down_blocks.{g}.prelu2")
+        else:
+            break
+        lr_list.append(lr)
+        g += 1
+    del G
+    feats = torch.cat(lr_list[1:], dim=1)                                            # :131
+    return _prelu(_conv(feats, sd, f"{p}.out_block.conv"), sd, f"{p}.out_block.prelu")  # :132
+
+
+def out_block(x, sd, upscale, p="out_block"):
+    # _OutBlock — drf_net.py:136-147
+    if math.log(upscale, 2) % 1 == 0:
+        n = int(math.log(upscale, 2))
+        for i in range(n):
+            x = F.pixel_shuffle(_conv(x, sd, f"{p}.conv{i + 1}", padding=1), 2)      # :141-142
+        return _conv(x, sd, f"{p}.conv{n + 1}", padding=1)                           # :144
+    x = F.pixel_shuffle(_conv(x, sd, f"{p}.conv1", padding=1), 3)                    # :145-146
+    return _conv(x, sd, f"{p}.conv2", padding=1)                                     # :147
+
+
+def drfnet_forward(inputs, sd, upscale):
+    """DRFNet.forward — drf_net.py:38-49. inputs: list of T tensors [N,C,h,w]."""
+    outputs, hidden = [], None
+    for i, x in enumerate(inputs):
+        feats = in_block(x, sd)                     # :41
+        if i == 0:
+            hidden = feats                          # :42-43
+        f = f_block(feats, hidden, sd, upscale)     # :44
+        hidden = f                                  # :45
+        outputs.append(out_block(feats + f, sd, upscale))  # :46-48
+    return outputs
+
+
+# ---- losses -----------------------------------------------------------------------------
+def l1_loss(o, t):          # torch.nn.L1Loss resolved by name, main.py:60-63
+    return (o - t).abs().mean()
+
+
+def mse_loss(o, t):         # torch.nn.MSELoss
+    return ((o - t) ** 2).mean()
+
+
+def charbonnier_loss(o, t, epsilon):   # losses.py:23-34
+    return torch.sqrt((o - t) ** 2 + epsilon).mean()
+
+
+def huber_loss(o, t, delta):           # losses.py:5-20
+    abs_error = (o - t).abs()
+    quadratic = torch.clamp(abs_error, max=delta)
+    linear = abs_error - quadratic
+    return (0.5 * quadratic ** 2 + delta * linear).mean()
+
+
+LOSSES = {"L1Loss": (0, l1_loss), "MSELoss": (1, mse_loss),
+          "CharbonnierLoss": (2, charbonnier_loss), "HuberLoss": (3, huber_loss)}
+
+
+def vsr_loss(outputs, targets, fn):
+    # AcdcVSRTrainer._compute_losses — acdc_vsr_trainer.py:74-88: mean over frames of per-frame loss
+    return torch.stack([fn(o, t) for o, t in zip(outputs, targets)]).mean()
+
+
+# ---- metrics ----------------------------------------------------------------------------
+DATASET_STATS = {"acdc": (54.089, 48.084), "dsb15": (51.193, 52.671)}   # utils.py:13-16
+
+
+def denormalize(x, dataset):   # utils.py:1-20
+    mean, std = DATASET_STATS[dataset]
+    return (x.clone() * std + mean).round().clamp(0, 255)
+
+
+def psnr(o, t, max_value=255, size_average=True):   # metrics.py:20-36
+    dims = list(range(1, o.dim()))
+    mse = ((o - t) ** 2).mean(dims)
+    val = 10 * torch.log10(max_value ** 2 / (mse + 1e-10))
+    return val.mean() if size_average else val
+
+
+def ssim_window_1d(dtype=torch.float32):
+    """Per-axis factor of the reference window (metrics.py:68-77): exp(-((i-5)/(2*1.5))^2); the
+    2-D kernel is the outer product, normalised to sum 1 — the 1-D factor normalised to sum 1
+    gives the same outer product."""
+    i = torch.arange(11, dtype=torch.float32)
+    g = 1 / (1.5 * math.sqrt(2 * math.pi)) * torch.exp(-((i - 5) / (2 * 1.5)) ** 2)
+    return (g / g.sum()).to(dtype)
+
+
+def ssim(o, t, value_range=255, size_average=True):   # metrics.py:51-113, dim=2, channels=1
+    c1, c2 = (0.01 * value_range) ** 2, (0.03 * value_range) ** 2
+    grids = torch.meshgrid([torch.arange(11, dtype=torch.float32)] * 2, indexing="ij")
+    k = 1
+    for g in grids:
+        k = k * (1 / (1.5 * math.sqrt(2 * math.pi)) * torch.exp(-((g - 5) / (2 * 1.5)) ** 2))
+    k = (k / k.sum()).to(o.dtype).view(1, 1, 11, 11)
+    mu1, mu2 = F.conv2d(o, k), F.conv2d(t, k)
+    s11 = F.conv2d(o * o, k) - mu1.pow(2)
+    s22 = F.conv2d(t * t, k) - mu2.pow(2)
+    s12 = F.conv2d(o * t, k) - mu1 * mu2
+    m = ((2 * mu1 * mu2 + c1) * (2.0 * s12 + c2)) / ((mu1.pow(2) + mu2.pow(2) + c1) * (s11 + s22 + c2))
+    return m.mean() if size_average else m.mean(dim=list(range(1, o.dim())))
+
+
+def vsr_metrics(outputs, targets, dataset="acdc"):
+    # AcdcVSRTrainer._compute_metrics — acdc_vsr_trainer.py:90-107
+    o = [denormalize(x, dataset) for x in outputs]
+    t = [denormalize(x, dataset) for x in targets]
+    return (torch.stack([psnr(a, b) for a, b in zip(o, t)]).mean(),
+            torch.stack([ssim(a, b) for a, b in zip(o, t)]).mean())
