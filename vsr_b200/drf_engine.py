@@ -1,0 +1,280 @@
+"""Forward / backward schedule of DRFNet on the kernel set (reference: drf_net.py:38-49,118-133).
+
+The engine owns the whole backward pass (it is one autograd node): data-gradients of the feature
+lists are single tap-GEMMs over the *virtual concat of the consumers' gradients*, the PReLU
+derivative and the scalar-slope gradient are fused into the epilogue of the kernel that produces
+each gradient map, and weight gradients of all T frames accumulate into one packed fp32 buffer
+that is un-packed into the flat gradient bucket once per step.
+
+`ops` is vsr_b200.ops.CudaOps in the product (tests substitute the torch emulation to check this
+schedule on a CPU-only box).
+"""
+import torch
+
+from ._lib import EPI_BIAS, EPI_OUT2, EPI_PRELU, EPI_PRELU_BWD, EPI_RES_PRE
+from .drf_plan import DrfPlan
+
+
+class _Frame:
+    __slots__ = ("x", "a1", "inn", "hidden", "lr", "u", "hr", "d", "f", "feat", "s", "y")
+
+
+class DrfEngine:
+    def __init__(self, plan: DrfPlan, ops, device, act_dtype, param_dtype=torch.float32):
+        self.plan, self.ops, self.device = plan, ops, device
+        self.act_dtype, self.param_dtype = act_dtype, param_dtype
+        dev = device
+        self.fwd_w = torch.empty(plan.fwd_w_numel, dtype=act_dtype, device=dev)
+        self.bwd_w = torch.empty(plan.bwd_w_numel, dtype=act_dtype, device=dev)
+        self.fwd_b = torch.empty(plan.fwd_b_numel, dtype=param_dtype, device=dev)
+        self.fwd_w_idx = torch.from_numpy(plan.fwd_w_idx).to(dev)
+        self.bwd_w_idx = torch.from_numpy(plan.bwd_w_idx).to(dev)
+        self.fwd_b_idx = torch.from_numpy(plan.fwd_b_idx).to(dev)
+        self.unpack = [(lo, torch.from_numpy(idx).to(dev)) for lo, idx in plan.unpack_passes]
+        b = plan.bias_unpack_idx
+        nz = (b >= 0).nonzero()[0]
+        self.bias_unpack = (int(nz.min()), torch.from_numpy(b[nz.min():nz.max() + 1].copy()).to(dev))
+        self._ws = {}
+        self.flat = None
+
+    # ---- buffers ---------------------------------------------------------------------------
+    def _new(self, *shape, dtype=None):
+        return torch.empty(*shape, dtype=dtype or self.act_dtype, device=self.device)
+
+    def _workspace(self, key, nbytes):
+        nbytes = max(int(nbytes), 16)
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() * 4 < nbytes:
+            ws = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=self.device)
+            self._ws[key] = ws
+        return ws
+
+    def _pview(self, flat, name):
+        p = self.plan.params[name]
+        n = 1
+        for d in p.shape:
+            n *= d
+        return flat[p.offset:p.offset + n].view(p.shape)
+
+    def _slope(self, pref):
+        return self.flat[pref.offset:pref.offset + 1]
+
+    # ---- weights ---------------------------------------------------------------------------
+    def pack(self, flat, need_bwd):
+        """flat fp32 parameter bucket -> packed slabs (one gather kernel per buffer)."""
+        self.flat = flat
+        self.ops.gather(flat, self.fwd_w_idx, self.fwd_w)
+        self.ops.gather(flat, self.fwd_b_idx, self.fwd_b)
+        if need_bwd:
+            self.ops.gather(flat, self.bwd_w_idx, self.bwd_w)
+
+    def _fw(self, L):
+        return self.fwd_w[L.w_off:L.w_off + L.w_numel]
+
+    def _bw(self, L):
+        return self.bwd_w[L.w_off:L.w_off + L.w_numel]
+
+    def _fwd(self, lname, srcs, out, extra=0, **kw):
+        L = self.plan.fwd[lname]
+        epi = EPI_BIAS | extra
+        slope = None
+        if L.slope is not None:
+            epi |= EPI_PRELU
+            slope = self._slope(L.slope)
+        self.ops.tapgemm(L.table, srcs, out, self._fw(L), bias=self.fwd_b[L.b_off:L.b_off + L.out_c],
+                         epi=epi, slope=slope, **kw)
+
+    # ---- forward ---------------------------------------------------------------------------
+    def forward(self, frames, save):
+        """frames: list of T contiguous [N,Cin,h,w] tensors. Returns (outputs, saved frames)."""
+        P, ops = self.plan, self.ops
+        F, G, r = P.F, P.G, P.r
+        r2 = r * r
+        saved, outs, prev_f = [], [], None
+        for t, x in enumerate(frames):
+            N, _, h, w = x.shape
+            S = _Frame()
+            S.x = x
+            S.a1 = self._new(N, h, w, 4 * F)
+            ops.conv3x3_first(x, self._pview(self.flat, "in_block.conv1.weight"),
+                              self._pview(self.flat, "in_block.conv1.bias"),
+                              self._slope(P.params["in_block.prelu1.weight"]), S.a1)
+            S.inn = self._new(N, h, w, F)
+            self._fwd("in2", [S.a1], S.inn)
+            S.hidden = S.inn if t == 0 else prev_f                      # drf_net.py:42-43
+            S.lr, S.hr, S.u, S.d = [self._new(N, h, w, F)], [], [None], [None]
+            self._fwd("fin", [S.inn, S.hidden], S.lr[0])
+            hv = lambda z: z.view(N, h, w * r2, F)
+            for g in range(G):
+                if g == 0:
+                    src = S.lr[0]
+                else:
+                    S.u.append(self._new(N, h, w, F))
+                    self._fwd(f"up{g}_c1", S.lr[:g + 1], S.u[g])
+                    src = S.u[g]
+                S.hr.append(self._new(N, h, w, r2 * F))
+                self._fwd(f"up{g}_dc", [src], S.hr[g])
+                if g == 0:
+                    src = S.hr[0]
+                else:
+                    S.d.append(self._new(N, h, w, r2 * F))
+                    self._fwd(f"dn{g}_c1", [hv(z) for z in S.hr[:g + 1]], hv(S.d[g]))
+                    src = S.d[g]
+                S.lr.append(self._new(N, h, w, F))
+                self._fwd(f"dn{g}_sc", [src], S.lr[g + 1])
+            S.f, S.feat = self._new(N, h, w, F), self._new(N, h, w, F)
+            self._fwd("fout", S.lr[1:], S.f, extra=EPI_OUT2, out2=S.feat, res2=S.inn)   # :46 global skip
+            S.s = [S.feat]
+            for lv in range(P.out_levels):
+                L = P.fwd[f"out{lv + 1}"]
+                nxt = self._new(N, h, w, L.out_c)
+                self._fwd(L.name, [S.s[-1]], nxt)
+                S.s.append(nxt)
+            y = self._new(N, P.cout, h * r, w * r, dtype=self.param_dtype)
+            ops.conv3x3_last(S.s[-1], r, F, P.phases, self._pview(self.flat, P.last_name + ".weight"),
+                             self._pview(self.flat, P.last_name + ".bias"), y)
+            outs.append(y)
+            prev_f = S.f
+            if save:
+                saved.append(S)
+            else:
+                S = None
+        return outs, saved
+
+    # ---- backward --------------------------------------------------------------------------
+    def backward(self, saved, d_outs):
+        """d_outs: list of T [N,Cout,rh,rw] gradients (None = zero). Returns the flat gradient."""
+        P, ops = self.plan, self.ops
+        F, G, r = P.F, P.G, P.r
+        r2 = r * r
+        dev, pd = self.device, self.param_dtype
+        gflat = torch.zeros(P.n_params, dtype=pd, device=dev)
+        dw_packed = torch.zeros(P.fwd_w_numel, dtype=pd, device=dev)
+        db_packed = torch.zeros(P.fwd_b_numel, dtype=pd, device=dev)
+        T = len(saved)
+        n_rows = T * (4 * G + 4)
+        partials = torch.zeros(n_rows, ops.partials_len, dtype=pd, device=dev)
+        row_dst, row = [], [0]
+
+        def prow(pref):
+            i = row[0]
+            row[0] += 1
+            row_dst.append(pref.offset)
+            return partials[i]
+
+        def wgrad(lname, srcs, dz):
+            L = P.fwd[lname]
+            ws = self._workspace("wgrad", ops.tapgemm_wgrad_workspace(L.table, srcs, dz))
+            ops.tapgemm_wgrad(L.table, srcs, dz, dw_packed[L.w_off:L.w_off + L.w_numel], True, ws)
+            rows = dz.numel() // L.bias_c
+            wsb = self._workspace("colsum", ops.colsum_workspace(rows, L.bias_c))
+            ops.colsum(dz, rows, L.bias_c, db_packed[L.b_off:L.b_off + L.bias_c], True, wsb)
+
+        def dgrad(lname, srcs, out, aux=None, slope_ref=None, residual=None):
+            L = P.bwd[lname]
+            epi, kw = 0, {}
+            if residual is not None:
+                epi |= EPI_RES_PRE
+                kw["residual"] = residual
+            if aux is not None:
+                epi |= EPI_PRELU_BWD
+                kw.update(aux_y=aux, slope=self._slope(slope_ref), slope_partials=prow(slope_ref))
+            ops.tapgemm(L.table, srcs, out, self._bw(L), epi=epi, **kw)
+
+        def act_bwd(dy, y, dz, slope_ref):
+            ops.act_bwd(dy, y, dz, slope=self._slope(slope_ref), slope_partials=prow(slope_ref))
+
+        next_dz_lr0 = None
+        for t in reversed(range(T)):
+            S = saved[t]
+            N, _, h, w = S.x.shape
+            hv = lambda z: z.view(N, h, w * r2, F)
+            new = lambda c=F: self._new(N, h, w, c)
+            d_out = d_outs[t]
+            if d_out is None:
+                d_out = torch.zeros(N, P.cout, h * r, w * r, dtype=pd, device=dev)
+            # ---- output block ----
+            d_s = new(S.s[-1].shape[-1])
+            ws = self._workspace("last", ops.conv3x3_last_bwd_workspace(S.s[-1], r, F, P.cout))
+            ops.conv3x3_last_bwd(S.s[-1], r, F, P.phases, self._pview(self.flat, P.last_name + ".weight"),
+                                 d_out.contiguous(), d_s, self._pview(gflat, P.last_name + ".weight"),
+                                 self._pview(gflat, P.last_name + ".bias"), True, ws)
+            for lv in reversed(range(P.out_levels)):
+                lname = f"out{lv + 1}"
+                wgrad(lname, [S.s[lv]], d_s)
+                d_prev = new(S.s[lv].shape[-1])
+                dgrad(lname, [d_s], d_prev)
+                d_s = d_prev
+            d_feat = d_s
+            # ---- feedback block output (+ hidden-state gradient of frame t+1: BPTT) ----
+            dz_f = new()
+            fout = P.fwd["fout"]
+            if next_dz_lr0 is not None:
+                dgrad("fin_hid", [next_dz_lr0], dz_f, aux=S.f, slope_ref=fout.slope, residual=d_feat)
+            else:
+                act_bwd(d_feat, S.f, dz_f, fout.slope)
+            wgrad("fout", S.lr[1:], dz_f)
+            dz_u, dz_d, p_hr0, p_lr0 = {}, {}, None, None
+            for g in reversed(range(G)):
+                j = g + 1
+                srcs = [dz_f] + [dz_u[gg] for gg in range(max(j, 1), G)]
+                dz_lr = new()
+                dgrad(f"lr{j}", srcs, dz_lr, aux=S.lr[j], slope_ref=P.fwd[f"dn{g}_sc"].slope)
+                # down-projection group g
+                wgrad(f"dn{g}_sc", [S.hr[0] if g == 0 else S.d[g]], dz_lr)
+                if g >= 1:
+                    dz_d[g] = new(r2 * F)
+                    dgrad(f"dn{g}_sc", [dz_lr], dz_d[g], aux=S.d[g], slope_ref=P.fwd[f"dn{g}_c1"].slope)
+                    wgrad(f"dn{g}_c1", [hv(z) for z in S.hr[:g + 1]], hv(dz_d[g]))
+                else:
+                    p_hr0 = new(r2 * F)
+                    dgrad("dn0_sc", [dz_lr], p_hr0)
+                # gradient of hr_g
+                cons = [dz_d[gg] for gg in range(max(g, 1), G)]
+                dz_hr = new(r2 * F)
+                up_slope = P.fwd[f"up{g}_dc"].slope
+                if cons:
+                    dgrad(f"hr{g}", [hv(c) for c in cons], hv(dz_hr), aux=hv(S.hr[g]), slope_ref=up_slope,
+                          residual=hv(p_hr0) if g == 0 else None)
+                else:
+                    act_bwd(p_hr0, S.hr[g], dz_hr, up_slope)
+                # up-projection group g
+                wgrad(f"up{g}_dc", [S.lr[0] if g == 0 else S.u[g]], dz_hr)
+                if g >= 1:
+                    dz_u[g] = new()
+                    dgrad(f"up{g}_dc", [dz_hr], dz_u[g], aux=S.u[g], slope_ref=P.fwd[f"up{g}_c1"].slope)
+                    wgrad(f"up{g}_c1", S.lr[:g + 1], dz_u[g])
+                else:
+                    p_lr0 = new()
+                    dgrad("up0_dc", [dz_hr], p_lr0)
+            # ---- feedback block input ----
+            dz_lr0 = new()
+            cons = [dz_u[gg] for gg in range(1, G)]
+            fin = P.fwd["fin"]
+            if cons:
+                dgrad("lr0", cons, dz_lr0, aux=S.lr[0], slope_ref=fin.slope, residual=p_lr0)
+            else:
+                act_bwd(p_lr0, S.lr[0], dz_lr0, fin.slope)
+            wgrad("fin", [S.inn, S.hidden], dz_lr0)
+            dz_in = new()
+            in2 = P.fwd["in2"]
+            if t == 0:   # hidden == in_features at the first frame (drf_net.py:42-43)
+                dgrad("fin_in0", [dz_lr0, dz_lr0], dz_in, aux=S.inn, slope_ref=in2.slope, residual=d_feat)
+            else:
+                dgrad("fin_in", [dz_lr0], dz_in, aux=S.inn, slope_ref=in2.slope, residual=d_feat)
+            # ---- input block ----
+            wgrad("in2", [S.a1], dz_in)
+            dz_a1 = new(4 * F)
+            dgrad("in2", [dz_in], dz_a1, aux=S.a1, slope_ref=P.params["in_block.prelu1.weight"])
+            ws = self._workspace("first", ops.conv3x3_first_bwd_workspace(S.x, 4 * F))
+            ops.conv3x3_first_bwd(S.x, dz_a1, self._pview(gflat, "in_block.conv1.weight"),
+                                  self._pview(gflat, "in_block.conv1.bias"), True, ws)
+            next_dz_lr0 = dz_lr0
+        # ---- un-pack: weights, biases, PReLU slopes ----
+        for lo, idx in self.unpack:
+            ops.gather_add(dw_packed, idx, gflat[lo:lo + idx.numel()])
+        lo, idx = self.bias_unpack
+        ops.gather_add(db_packed, idx, gflat[lo:lo + idx.numel()])
+        rd = torch.tensor(row_dst, dtype=torch.int32, device=dev)
+        ops.reduce_partials(partials, row[0], rd, gflat)
+        return gflat

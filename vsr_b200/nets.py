@@ -1,0 +1,224 @@
+"""Drop-in SR nets: same class names, constructor kwargs, forward I/O and state_dict layout as the
+reference (src/model/nets/drf_net.py:8-49, drf_sisr_net.py:8-50, base_net.py:5-13), executed by
+hand-written sm_100a kernels through libvsr_sm100.so.
+
+The sub-modules below (`in_block`, `f_block`, `out_block`) only *hold parameters* — they give the
+reference's state_dict keys, shapes, dtypes and default initialisation (same construction order,
+hence the same values under the same torch seed).  They are never called: forward and backward
+run in vsr_b200.drf_engine.  All parameters are views into one flat fp32 bucket (`net.flat`), and
+all gradients of a step are views into one flat bucket (`net.flat_grad`) — the unit the
+data-parallel trainer all-reduces.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from .drf_engine import DrfEngine
+from .drf_plan import PROJ, DrfPlan
+
+_PRECISIONS = {"fp32": torch.float32, "bf16": torch.bfloat16}
+
+
+class BaseNet(nn.Module):
+    """The base class for all nets (reference: base_net.py:5-13)."""
+
+    def __init__(self):
+        super().__init__()
+
+    def __repr__(self):
+        n = sum(p.numel() for p in self.parameters() if p.requires_grad)
+        return super().__repr__() + f"\nTrainable parameters: {n / 1e6} M\nMemory usage: {(n * 4) / (1 << 20)} MB"
+
+
+def _seq(**mods):
+    s = nn.Sequential()
+    for k, m in mods.items():
+        s.add_module(k, m)
+    return s
+
+
+def _prelu():
+    return nn.PReLU(num_parameters=1, init=0.2)
+
+
+class _FBlockParams(nn.Module):
+    """Parameter container with the reference's _FBlock naming (drf_net.py:61-116)."""
+
+    def __init__(self, F, G, r):
+        super().__init__()
+        k, s, p = PROJ[r]
+        self.in_block = _seq(conv=nn.Conv2d(2 * F, F, 1), prelu=_prelu())
+        self.up_blocks, self.down_blocks = nn.ModuleList(), nn.ModuleList()
+        for g in range(G):
+            if g == 0:
+                self.up_blocks.append(_seq(deconv=nn.ConvTranspose2d(F, F, k, s, p), prelu=_prelu()))
+                self.down_blocks.append(_seq(conv=nn.Conv2d(F, F, k, s, p), prelu=_prelu()))
+            else:
+                self.up_blocks.append(_seq(conv1=nn.Conv2d(F * (g + 1), F, 1), prelu1=_prelu(),
+                                           deconv2=nn.ConvTranspose2d(F, F, k, s, p), prelu2=_prelu()))
+                self.down_blocks.append(_seq(conv1=nn.Conv2d(F * (g + 1), F, 1), prelu1=_prelu(),
+                                             conv2=nn.Conv2d(F, F, k, s, p), prelu2=_prelu()))
+        self.out_block = _seq(conv=nn.Conv2d(F * G, F, 1), prelu=_prelu())
+        self._hidden_state = None
+
+    @property
+    def hidden_state(self):
+        return self._hidden_state
+
+    @hidden_state.setter
+    def hidden_state(self, state):
+        self._hidden_state = state
+
+
+def _out_block(F, cout, r):
+    s = nn.Sequential()
+    if math.log(r, 2) % 1 == 0:
+        n = int(math.log(r, 2))
+        for i in range(n):
+            s.add_module(f"conv{i + 1}", nn.Conv2d(F, 4 * F, 3, padding=1))
+            s.add_module(f"pixelshuffle{i + 1}", nn.PixelShuffle(2))
+        s.add_module(f"conv{n + 1}", nn.Conv2d(F, cout, 3, padding=1))
+    else:
+        s.add_module("conv1", nn.Conv2d(F, 9 * F, 3, padding=1))
+        s.add_module("pixelshuffle1", nn.PixelShuffle(3))
+        s.add_module("conv2", nn.Conv2d(F, cout, 3, padding=1))
+    return s
+
+
+class _DRFFunction(torch.autograd.Function):
+    """One autograd node for the whole T-frame forward; backward is the engine's own schedule."""
+
+    @staticmethod
+    def forward(ctx, net, T, *args):
+        eng = net._engine
+        eng.pack(net.flat, need_bwd=True)
+        outs, saved = eng.forward([f.contiguous() for f in args[:T]], save=True)
+        ctx.net, ctx.saved, ctx.T = net, saved, T
+        ctx.set_materialize_grads(False)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        net = ctx.net
+        gflat = net._engine.backward(ctx.saved, list(grads))
+        ctx.saved = None
+        net.flat_grad = gflat
+        pg = []
+        for p in net._plan.params.values():
+            n = 1
+            for d in p.shape:
+                n *= d
+            pg.append(gflat[p.offset:p.offset + n].view(p.shape))
+        return (None, None) + (None,) * ctx.T + tuple(pg)
+
+
+class _DRFBase(BaseNet):
+    def _setup(self, in_channels, out_channels, num_features, num_groups, upscale_factor, precision):
+        if upscale_factor not in [2, 3, 4, 8]:
+            raise ValueError(f"The upscale factor should be 2, 3, 4 or 8. Got {upscale_factor}.")
+        if precision not in _PRECISIONS:
+            raise ValueError(f"precision should be one of {sorted(_PRECISIONS)}. Got {precision!r}.")
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.num_features, self.num_groups = num_features, num_groups
+        self.upscale_factor, self.precision = upscale_factor, precision
+        F = num_features
+        self.in_block = _seq(conv1=nn.Conv2d(in_channels, 4 * F, 3, padding=1), prelu1=_prelu(),
+                             conv2=nn.Conv2d(4 * F, F, 1), prelu2=_prelu())
+        self.f_block = _FBlockParams(F, num_groups, upscale_factor)
+        self.out_block = _out_block(F, out_channels, upscale_factor)
+        self._plan = DrfPlan(in_channels, out_channels, F, num_groups, upscale_factor,
+                             bf16=(precision == "bf16"))
+        names = [n for n, _ in self.named_parameters()]
+        assert names == list(self._plan.params), "parameter order differs from the plan"
+        self._engine = None
+        self._ops = None          # tests may set an emulated backend here; product uses CudaOps
+        self.flat = None
+        self.flat_grad = None
+        self._flatten()
+
+    # ---- flat parameter bucket -------------------------------------------------------------
+    def _flatten(self):
+        params = list(self.parameters())
+        dev, dt = params[0].device, params[0].dtype
+        flat = torch.empty(self._plan.n_params, dtype=dt, device=dev)
+        for p, ref in zip(params, self._plan.params.values()):
+            n = p.numel()
+            flat[ref.offset:ref.offset + n].copy_(p.data.reshape(-1))
+            p.data = flat[ref.offset:ref.offset + n].view(ref.shape)
+        self.flat = flat
+        if self._engine is not None and (self._engine.device != dev or self._engine.param_dtype != dt):
+            self._engine = None
+
+    def _is_flat(self):
+        base = self.flat.data_ptr()
+        es = self.flat.element_size()
+        for p, ref in zip(self.parameters(), self._plan.params.values()):
+            if p.data_ptr() != base + ref.offset * es or p.device != self.flat.device:
+                return False
+        return True
+
+    def _apply(self, fn, *a, **kw):
+        out = super()._apply(fn, *a, **kw)     # .to(device) / .double(): params moved in place
+        self._flatten()
+        return out
+
+    def _backend(self):
+        if self._ops is not None:
+            return self._ops
+        if self.flat.device.type != "cuda":
+            raise RuntimeError("vsr_b200 nets run on CUDA only (there is no CPU fallback); call .to('cuda')")
+        from .ops import cuda_ops
+        return cuda_ops()
+
+    def _run(self, frames):
+        if not self._is_flat():
+            self._flatten()
+        ops = self._backend()
+        if self._engine is None or self._engine.ops is not ops:
+            act = _PRECISIONS[self.precision]
+            if self.flat.dtype == torch.float64:     # emulated high-precision oracle runs (tests)
+                act = torch.float64
+            self._engine = DrfEngine(self._plan, ops, self.flat.device, act, self.flat.dtype)
+        frames = list(frames)
+        for f in frames:
+            if f.dim() != 4 or f.shape[1] != self.in_channels:
+                raise ValueError(f"expected frames of shape [N,{self.in_channels},h,w], got {tuple(f.shape)}")
+        needs_grad = torch.is_grad_enabled() and (
+            any(p.requires_grad for p in self.parameters()) or any(f.requires_grad for f in frames))
+        if needs_grad:
+            outs = _DRFFunction.apply(self, len(frames), *frames, *self.parameters())
+        else:
+            self._engine.pack(self.flat, need_bwd=False)
+            outs, _ = self._engine.forward([f.contiguous() for f in frames], save=False)
+        return list(outs)
+
+
+class DRFNet(_DRFBase):
+    """Deep Recurrent Feedback Network for video SR (reference: drf_net.py:8-49).
+
+    Args: in_channels, out_channels, num_features, num_groups, upscale_factor (2, 3, 4 or 8) — as the
+    reference; precision ('fp32' = CUDA-core strict mode, 'bf16' = tcgen05 tensor-core mode).
+    forward(list of T tensors [N,C,h,w]) -> list of T tensors [N,C,r*h,r*w].
+    """
+
+    def __init__(self, in_channels, out_channels, num_features, num_groups, upscale_factor, precision="fp32"):
+        super().__init__()
+        self._setup(in_channels, out_channels, num_features, num_groups, upscale_factor, precision)
+
+    def forward(self, inputs):
+        return self._run(inputs)
+
+
+class DRFSISRNet(_DRFBase):
+    """DRFN for single-image SR (reference: drf_sisr_net.py:8-50): the same blocks iterated
+    `num_steps` times on one image; returns the list of the per-step outputs."""
+
+    def __init__(self, in_channels, out_channels, num_steps, num_features, num_groups, upscale_factor,
+                 precision="fp32"):
+        super().__init__()
+        self.num_steps = num_steps
+        self._setup(in_channels, out_channels, num_features, num_groups, upscale_factor, precision)
+
+    def forward(self, input):
+        return self._run([input] * self.num_steps)
