@@ -1,0 +1,101 @@
+"""GPU parity of the drop-in nets (through the C-ABI) against the real reference's goldens."""
+import glob
+import os
+
+import pytest
+import torch
+
+from oracle import restated
+from tests.test_oracle import _state
+from vsr_b200.nets import DRFNet
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+CASES = sorted(glob.glob(os.path.join(GOLDEN, "drfnet_*.pt")))
+
+
+def _net(fx, precision):
+    net = DRFNet(precision=precision, **fx["kwargs"])
+    net.load_state_dict(_state(fx))
+    return net.to("cuda")
+
+
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[:-3] for p in CASES])
+def test_fp32_mode_matches_reference_golden(path):
+    """north_star fp32 bar: tensor-normalised max error <= 1e-4 (outputs and gradients)."""
+    fx = torch.load(path)
+    net = _net(fx, "fp32")
+    x = [t.cuda() for t in fx["inputs"]]
+    y = [t.cuda() for t in fx["targets"]]
+    outs = net(x)
+    for o, ref in zip(outs, fx["outputs"]):
+        assert (o.cpu() - ref).abs().max() <= 1e-4 * ref.abs().max()
+    loss = torch.stack([torch.nn.L1Loss()(o, t) for o, t in zip(outs, y)]).mean()
+    assert abs(loss.item() - float(fx["loss_l1"])) <= 1e-5 * abs(float(fx["loss_l1"]))
+    loss.backward()
+    got = {k: p.grad.cpu() for k, p in net.named_parameters()}
+    if fx["grads"] is not None:
+        gmax = max(float(g.abs().max()) for g in fx["grads"].values())
+        num = sum(float(((got[k] - g) ** 2).sum()) for k, g in fx["grads"].items()) ** 0.5
+        den = sum(float((g ** 2).sum()) for g in fx["grads"].values()) ** 0.5
+        assert num / den <= 1e-4
+        for k, g in fx["grads"].items():
+            assert (got[k] - g).abs().max() <= 1e-4 * gmax, k
+    else:
+        for k, dg in fx["grad_digest"].items():
+            assert abs(float(got[k].norm()) - float(dg["norm"])) <= 2e-4 * float(dg["norm"]) + 1e-6, k
+
+
+def test_bf16_mode_psnr_and_gradients():
+    """north_star bf16 bar: PSNR within 0.05 dB of the reference output's PSNR; gradients within a
+    stated global relative L2 tolerance (5e-2 at random weights)."""
+    fx = torch.load(os.path.join(GOLDEN, "drfnet_f64_g2_x4.pt"))
+    sd = _state(fx)
+    net = _net(fx, "bf16")
+    x = [t.cuda() for t in fx["inputs"]]
+    y = [t.cuda() for t in fx["targets"]]
+    outs = net(x)
+    psnr_ref, _ = restated.vsr_metrics(fx["outputs"], fx["targets"])
+    psnr_got, _ = restated.vsr_metrics([o.detach().cpu() for o in outs], fx["targets"])
+    assert abs(float(psnr_got) - float(psnr_ref)) <= 0.05
+    for o, ref in zip(outs, fx["outputs"]):
+        assert (o.cpu() - ref).abs().max() <= 5e-2 * ref.abs().max()
+    loss = torch.stack([((o - t) ** 2).mean() for o, t in zip(outs, y)]).mean()
+    loss.backward()
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    ref_outs = restated.drfnet_forward(fx["inputs"], sdg, 4)
+    torch.stack([((o - t) ** 2).mean() for o, t in zip(ref_outs, fx["targets"])]).mean().backward()
+    num = sum(float(((p.grad.cpu() - sdg[k].grad) ** 2).sum()) for k, p in net.named_parameters()) ** 0.5
+    den = sum(float((v.grad ** 2).sum()) for v in sdg.values()) ** 0.5
+    print("bf16 global grad rel L2 error:", num / den)
+    assert num / den <= 5e-2
+
+
+def test_eval_mode_no_grad_matches_training_forward():
+    fx = torch.load(os.path.join(GOLDEN, "drfnet_f8_g3_x4.pt"))
+    net = _net(fx, "fp32")
+    x = [t.cuda() for t in fx["inputs"]]
+    a = net(x)
+    with torch.no_grad():
+        b = net.eval()(x)
+    for p, q in zip(a, b):
+        assert torch.equal(p.detach(), q)
+
+
+def test_training_step_is_deterministic():
+    """the reference asserts bit-identical reruns (test/runner/test_trainer.py:133)."""
+    fx = torch.load(os.path.join(GOLDEN, "drfnet_f64_g2_x4.pt"))
+    res = []
+    for _ in range(2):
+        net = _net(fx, "bf16")
+        opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+        x = [t.cuda() for t in fx["inputs"]]
+        y = [t.cuda() for t in fx["targets"]]
+        for _ in range(2):
+            outs = net(x)
+            loss = torch.stack([torch.nn.L1Loss()(o, t) for o, t in zip(outs, y)]).mean()
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+        res.append(net.flat.clone())
+    assert torch.equal(res[0], res[1])

@@ -1,0 +1,174 @@
+"""Synthetic ACDC / DSB15-shaped cine data with pinned host staging (north_star item (d)).
+
+The real datasets are NIfTI files read with nibabel (src/data/datasets/acdc_vsr_dataset.py:51-88);
+here the same *contract* is produced from a seeded generator:
+    {'lr_imgs': list of T tensors [1,h,w], 'hr_imgs': list of T tensors [1,r*h,r*w], 'index': i}
+values are uint8-range intensities normalised with the dataset constants (transforms.py:154-168),
+float32; LR = the reference's `Downscale` (k-space truncation + bicubic resize + round + clip,
+acdc_preprocess.py:102-180) restated with numpy / cv2; training windows of `num_frames` frames with
+temporal wrap-around (acdc_vsr_dataset.py:59-78); LR/HR-consistent random crop and flips
+(transforms.py:321-450).
+"""
+import numpy as np
+import torch
+from torch.utils.data import DataLoader, Dataset
+
+from .utils import DATASET_STATS
+
+SHAPES = {"acdc": dict(hr=(128, 128), slices=10, frames=20), "dsb15": dict(hr=(256, 256), slices=12, frames=30)}
+
+
+def synth_cine(h, w, frames, rng):
+    """HR cine [frames,h,w]: moving anisotropic Gaussian blobs + smooth noise, periodic in time,
+    rounded to integers in [0,255] (as the preprocessed data, acdc_preprocess.py:39-40)."""
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    img = np.zeros((frames, h, w), np.float32)
+    for _ in range(8):
+        cy, cx = rng.uniform(0.2, 0.8) * h, rng.uniform(0.2, 0.8) * w
+        sy, sx = rng.uniform(0.04, 0.2) * h, rng.uniform(0.04, 0.2) * w
+        amp, ph, mv = rng.uniform(40, 160), rng.uniform(0, 2 * np.pi), rng.uniform(0.0, 0.06)
+        for t in range(frames):
+            c = np.cos(2 * np.pi * t / frames + ph)
+            s = 1.0 + 0.25 * c
+            img[t] += amp * np.exp(-(((yy - cy - mv * h * c) / (sy * s)) ** 2 + ((xx - cx) / (sx * s)) ** 2) / 2)
+    noise = rng.standard_normal((h // 4 + 1, w // 4 + 1)).astype(np.float32)
+    noise = np.kron(noise, np.ones((4, 4), np.float32))[:h, :w] * 6.0
+    return np.clip(np.round(img + noise[None]), 0, 255)
+
+
+def downscale(img, r):
+    """reference Downscale (acdc_preprocess.py:111-180) for one [h,w] image."""
+    import cv2
+    from numpy.fft import fftn, fftshift, ifftn, ifftshift
+    k = fftshift(fftn(ifftshift(img), norm="ortho"))
+    rect = np.zeros_like(k)
+    kx, ky = k.shape[0] // 2, k.shape[1] // 2
+    lx, ly = k.shape[0] // r, k.shape[1] // r
+    rect[kx - lx // 2:kx + (lx - lx // 2), ky - ly // 2:ky + (ly - ly // 2)] = 1
+    out = np.around(np.abs(fftshift(ifftn(ifftshift(rect * k), norm="ortho")))).astype(np.float32)
+    out = cv2.resize(out, (img.shape[1] // r, img.shape[0] // r), interpolation=cv2.INTER_CUBIC)
+    return np.clip(out.round(), 0, 255)
+
+
+class SyntheticCineDataset(Dataset):
+    """Args mirror AcdcVSRDataset (acdc_vsr_dataset.py:22): downscale_factor, num_frames,
+    temporal_order, type ('train' | 'valid'); plus dataset ('acdc' | 'dsb15'), num_sequences,
+    patch_size (LR crop for training, RandomCropPatch.size) and seed."""
+
+    def __init__(self, downscale_factor, num_frames=5, temporal_order="last", type="train", dataset="acdc",
+                 num_sequences=16, patch_size=(32, 32), seed=0):
+        if downscale_factor not in [2, 3, 4]:
+            raise ValueError(f"The downscale factor should be 2, 3, 4. Got {downscale_factor}.")
+        if temporal_order not in ["last", "middle"]:
+            raise ValueError(f"The temporal order should be 'last' or 'middle'. Got {temporal_order}.")
+        self.r, self.num_frames, self.temporal_order, self.type = downscale_factor, num_frames, temporal_order, type
+        self.patch = tuple(patch_size) if patch_size else None
+        self.mean, self.std = DATASET_STATS[dataset]
+        shape = SHAPES[dataset]
+        rng = np.random.default_rng(seed)
+        h, w = shape["hr"]
+        h, w = h - h % self.r, w - w % self.r
+        self.hr, self.lr = [], []
+        for _ in range(num_sequences):
+            cine = synth_cine(h, w, shape["frames"], rng)
+            self.hr.append(cine)
+            self.lr.append(np.stack([downscale(f, self.r) for f in cine]))
+        self.T = shape["frames"]
+        self.rng = np.random.default_rng(seed + 1)
+        self.data = [(s, t) for s in range(num_sequences) for t in range(self.T)] if type == "train" \
+            else [(s, None) for s in range(num_sequences)]
+
+    def __len__(self):
+        return len(self.data)
+
+    def _window(self, t):
+        n, T = self.num_frames, self.T
+        if self.temporal_order == "last":
+            start, end = t - n + 1, t + 1
+        else:
+            start, end = t - (n - 1) // 2, t + ((n - 1) - (n - 1) // 2) + 1
+        return [i % T for i in range(start, end)]
+
+    def __getitem__(self, index):
+        s, t = self.data[index]
+        idx = self._window(t) if self.type == "train" else list(range(self.T))
+        lr, hr = self.lr[s][idx], self.hr[s][idx]
+        if self.type == "train":
+            if self.rng.random() < 0.5:
+                lr, hr = lr[:, :, ::-1], hr[:, :, ::-1]
+            if self.rng.random() < 0.5:
+                lr, hr = lr[:, ::-1], hr[:, ::-1]
+            if self.patch:
+                ph, pw = self.patch
+                y0 = int(self.rng.integers(0, lr.shape[1] - ph + 1))
+                x0 = int(self.rng.integers(0, lr.shape[2] - pw + 1))
+                lr = lr[:, y0:y0 + ph, x0:x0 + pw]
+                hr = hr[:, y0 * self.r:(y0 + ph) * self.r, x0 * self.r:(x0 + pw) * self.r]
+        norm = lambda a: torch.from_numpy(((np.ascontiguousarray(a) - self.mean) / self.std).astype(np.float32))
+        lr, hr = norm(lr), norm(hr)
+        return {"lr_imgs": [f.unsqueeze(0) for f in lr], "hr_imgs": [f.unsqueeze(0) for f in hr], "index": index}
+
+
+class Dataloader(DataLoader):
+    """Same constructor keywords as the reference Dataloader (src/data/dataloader.py:6-53), with
+    pinned host memory on by default so H2D copies can be asynchronous."""
+
+    def __init__(self, dataset, batch_size=1, shuffle=False, sampler=None, batch_sampler=None, num_workers=0,
+                 collate_fn=None, pin_memory=True, drop_last=False, timeout=0, worker_init_fn=None):
+        if worker_init_fn is None:
+            worker_init_fn = self._default_worker_init_fn
+        kw = dict(dataset=dataset, batch_size=batch_size, shuffle=shuffle, sampler=sampler,
+                  batch_sampler=batch_sampler, num_workers=num_workers,
+                  pin_memory=pin_memory and torch.cuda.is_available(), drop_last=drop_last, timeout=timeout,
+                  worker_init_fn=worker_init_fn)
+        if collate_fn is not None:
+            kw["collate_fn"] = collate_fn
+        super().__init__(**kw)
+
+    @staticmethod
+    def _default_worker_init_fn(worker_id):
+        np.random.seed((np.random.get_state()[1][0] + worker_id) % (2 ** 32))
+
+
+class DeviceStager:
+    """Wraps a batch iterator: copies each batch from pinned host memory to the device on a side
+    stream one step ahead of the consumer (replaces the blocking, pageable `tensor.to(device)` of
+    base_trainer.py:146-161)."""
+
+    def __init__(self, loader, device):
+        self.loader, self.device = loader, torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+
+    def _move(self, obj):
+        if isinstance(obj, torch.Tensor):
+            src = obj if obj.is_pinned() else obj.pin_memory()
+            return src.to(self.device, non_blocking=True)
+        if isinstance(obj, dict):
+            return {k: self._move(v) for k, v in obj.items()}
+        if isinstance(obj, (list, tuple)):
+            return type(obj)(self._move(v) for v in obj)
+        return obj
+
+    def __len__(self):
+        return len(self.loader)
+
+    def __iter__(self):
+        it = iter(self.loader)
+
+        def fetch():
+            try:
+                host = next(it)
+            except StopIteration:
+                return None
+            with torch.cuda.stream(self.stream):
+                dev = self._move(host)
+                ev = torch.cuda.Event()
+                ev.record(self.stream)
+            return dev, ev
+
+        nxt = fetch()
+        while nxt is not None:
+            dev, ev = nxt
+            nxt = fetch()
+            torch.cuda.current_stream(self.device).wait_event(ev)
+            yield dev
