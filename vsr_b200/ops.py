@@ -94,6 +94,7 @@ class CudaOps:
         self.lib = _lib.lib()
         self.partials_len = self.lib.vsr_partials_len()
         self.launches = 0
+        self.timing = None      # set to a list to record (kind, flops, start_event, end_event)
 
     # ---- tap-GEMM ----------------------------------------------------------------------
     def tapgemm(self, tab, srcs, out, w, bias=None, epi=0, out_scale=1.0, slope=None, residual=None,
@@ -109,7 +110,15 @@ class CudaOps:
         d.res2 = res2.data_ptr() if res2 is not None else None
         d.slope_partials = slope_partials.data_ptr() if slope_partials is not None else None
         fn = self.lib.vsr_tapgemm_simt_bf16 if force_simt else self.lib.vsr_tapgemm
-        check(fn(C.byref(d), _stream()), "vsr_tapgemm")
+        if self.timing is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            check(fn(C.byref(d), _stream()), "vsr_tapgemm")
+            e1.record()
+            pix = out.shape[0] * out.shape[1] * out.shape[2]
+            self.timing.append(("tapgemm", 2.0 * pix * tab.n_taps_total * tab.nt * tab.kc, e0, e1))
+        else:
+            check(fn(C.byref(d), _stream()), "vsr_tapgemm")
         self.launches += 1
 
     def tapgemm_wgrad_workspace(self, tab, srcs, dz):
@@ -118,9 +127,16 @@ class CudaOps:
     def tapgemm_wgrad(self, tab, srcs, dz, dw, accumulate, workspace):
         d = _make_desc(tab, srcs, dz)
         _need_cuda(dw, workspace)
+        if self.timing is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         check(self.lib.vsr_tapgemm_wgrad(C.byref(d), _p(dw), int(accumulate), _p(workspace),
                                          workspace.numel() * workspace.element_size(), _stream()),
               "vsr_tapgemm_wgrad")
+        if self.timing is not None:
+            e1.record()
+            pix = dz.shape[0] * dz.shape[1] * dz.shape[2]
+            self.timing.append(("wgrad", 2.0 * pix * tab.n_taps_total * tab.nt * tab.kc, e0, e1))
         self.launches += 2
 
     # ---- small kernels -----------------------------------------------------------------

@@ -40,7 +40,6 @@ class FlatAdam(torch.optim.Optimizer):
 
     @torch.no_grad()
     def step(self, closure=None, flat_grad=None):
-        from .ops import cuda_ops
         loss = closure() if closure is not None else None
         flat = self._ensure_state()
         g = flat_grad if flat_grad is not None else self._net.flat_grad
@@ -48,7 +47,7 @@ class FlatAdam(torch.optim.Optimizer):
             raise RuntimeError("FlatAdam.step: no flat gradient (run backward first)")
         grp = self.param_groups[0]
         self._step += 1
-        cuda_ops().adam_flat(flat, g, self._m, self._v, float(grp["lr"]), grp["betas"][0], grp["betas"][1],
+        self._net._backend().adam_flat(flat, g, self._m, self._v, float(grp["lr"]), grp["betas"][0], grp["betas"][1],
                              grp["eps"], grp["weight_decay"], self._step, self.grad_scale)
         return loss
 
