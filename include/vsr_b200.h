@@ -87,6 +87,7 @@ typedef struct VsrTapGemmDesc {
   VsrTensor4 out;
   int32_t n_groups;
   int32_t n_taps_total;
+  int32_t max_group_taps;   /* host copy of max over groups of n_taps (needed by vsr_tapgemm_wgrad) */
   const int32_t* group_tab; /* device */
   const int32_t* tap_tab;   /* device */
   const void* w;            /* device */

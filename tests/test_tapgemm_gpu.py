@@ -163,3 +163,48 @@ def test_wgrad(dtype):
     ops.tapgemm_wgrad(tab, [src], dz, dw2, True, ws)
     torch.cuda.synchronize()
     assert torch.equal(dw2, res[0])
+
+
+def _wgrad_case(tab, n, h, w, src_c, out_c, n_srcs=1, seed=11):
+    ops, emu = _ops(), EmuOps()
+    gen = torch.Generator(device="cuda").manual_seed(seed)
+    srcs = [_rand((n, h, w, src_c), torch.bfloat16, gen) for _ in range(n_srcs)]
+    dz = _rand((n, h, w, out_c), torch.bfloat16, gen)
+    res = []
+    for o in (ops, emu):
+        dw = torch.ones(tab.n_taps_total * tab.nt * tab.kc, device="cuda")
+        ws = torch.empty(max(16, o.tapgemm_wgrad_workspace(tab, srcs, dz)) // 4 + 4, device="cuda")
+        o.tapgemm_wgrad(tab, srcs, dz, dw, True, ws)
+        res.append(dw)
+    torch.cuda.synchronize()
+    err = (res[0] - res[1]).abs().max().item() / res[1].abs().max().item()
+    assert err <= 1e-3, err
+    dw2 = torch.ones_like(res[0])
+    ws = torch.empty(max(16, ops.tapgemm_wgrad_workspace(tab, srcs, dz)) // 4 + 4, device="cuda")
+    ops.tapgemm_wgrad(tab, srcs, dz, dw2, True, ws)
+    torch.cuda.synchronize()
+    assert torch.equal(dw2, res[0])
+
+
+def test_wgrad_tc_single_tap_single_tile():
+    _wgrad_case(multi_src_table(64, 64, 1), n=1, h=4, w=32, src_c=64, out_c=64)
+
+
+def test_wgrad_tc_1x1_multi_src_many_tiles():
+    _wgrad_case(multi_src_table(64, 64, 5), n=4, h=32, w=64, src_c=64, out_c=64, n_srcs=5)
+
+
+def test_wgrad_tc_conv3x3_n256_ragged():
+    _wgrad_case(conv3x3_table(64, 256), n=3, h=19, w=21, src_c=64, out_c=256)
+
+
+def test_wgrad_tc_strided_64taps():
+    taps = [(0, (t // 8) % 3 - 1, (t % 8) % 3 - 1, (t % 16) * 64) for t in range(64)]
+    _wgrad_case(TapTable(kc=64, nt=64, groups=[(0, taps)]), n=4, h=16, w=16, src_c=1024, out_c=64)
+
+
+def test_wgrad_tc_grouped_nt128_nonuniform_groups():
+    g0 = [(0, dy, dx, 0) for dy in (0, 1) for dx in (0, 1)]
+    g1 = [(0, dy, dx, 64) for dy in (-1, 0, 1) for dx in (-1, 0, 1)]
+    tab = TapTable(kc=64, nt=128, groups=[(0, g0), (128, g1)])
+    _wgrad_case(tab, n=2, h=12, w=20, src_c=128, out_c=256)

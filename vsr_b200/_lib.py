@@ -23,7 +23,7 @@ class VsrTapGemmDesc(C.Structure):
     _fields_ = [
         ("dtype", C.c_int32), ("kc", C.c_int32), ("nt", C.c_int32), ("n_srcs", C.c_int32),
         ("srcs", VsrTensor4 * VSR_MAX_SRCS), ("out", VsrTensor4),
-        ("n_groups", C.c_int32), ("n_taps_total", C.c_int32),
+        ("n_groups", C.c_int32), ("n_taps_total", C.c_int32), ("max_group_taps", C.c_int32),
         ("group_tab", C.c_void_p), ("tap_tab", C.c_void_p), ("w", C.c_void_p), ("bias", C.c_void_p),
         ("epi", C.c_int32), ("out_scale", C.c_float),
         ("slope", C.c_void_p), ("residual", C.c_void_p), ("aux_y", C.c_void_p),

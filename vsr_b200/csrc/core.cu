@@ -94,10 +94,47 @@ __global__ void act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y
   }
 }
 
-// column sums, pass 1: block b sums rows [b*rpb, (b+1)*rpb) for all c columns -> ws[b][c]
+// column sums, pass 1: block b sums rows [b*rpb, (b+1)*rpb); 16-byte vector loads, each thread owns
+// VEC consecutive columns of every (blockDim/TPR)-th row; fixed-order shared-memory fold.
 template <typename T>
-__global__ void colsum_kernel(const T* __restrict__ x, long rows, int c, long rows_per_block,
-                              float* __restrict__ ws) {
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, long rows, int c, long rows_per_block,
+                                                    float* __restrict__ ws) {
+  constexpr int VEC = 16 / sizeof(T);
+  extern __shared__ float sm[];           // [rpp][c]
+  const int tpr = c / VEC;                // threads per row
+  const int rpp = blockDim.x / tpr;       // rows per pass
+  const int cg = threadIdx.x % tpr, ro = threadIdx.x / tpr;
+  const long r0 = blockIdx.x * rows_per_block;
+  long r1 = r0 + rows_per_block;
+  if (r1 > rows) r1 = rows;
+  float acc[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+  if (ro < rpp) {
+    for (long r = r0 + ro; r < r1; r += rpp) {
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(x + r * c + cg * VEC));
+      if constexpr (sizeof(T) == 2) {
+        acc[0] += bf16_lo(q.x); acc[1] += bf16_hi(q.x); acc[2] += bf16_lo(q.y); acc[3] += bf16_hi(q.y);
+        acc[4] += bf16_lo(q.z); acc[5] += bf16_hi(q.z); acc[6] += bf16_lo(q.w); acc[7] += bf16_hi(q.w);
+      } else {
+        acc[0] += __uint_as_float(q.x); acc[1] += __uint_as_float(q.y);
+        acc[2] += __uint_as_float(q.z); acc[3] += __uint_as_float(q.w);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) sm[ro * c + cg * VEC + i] = acc[i];
+  }
+  __syncthreads();
+  for (int col = threadIdx.x; col < c; col += blockDim.x) {
+    float s = 0.f;
+    for (int r = 0; r < rpp; ++r) s += sm[r * c + col];
+    ws[(size_t)blockIdx.x * c + col] = s;
+  }
+}
+// generic (any c, scalar loads)
+template <typename T>
+__global__ void colsum_scalar_kernel(const T* __restrict__ x, long rows, int c, long rows_per_block,
+                                     float* __restrict__ ws) {
   const long r0 = blockIdx.x * rows_per_block;
   long r1 = r0 + rows_per_block;
   if (r1 > rows) r1 = rows;
@@ -107,13 +144,26 @@ __global__ void colsum_kernel(const T* __restrict__ x, long rows, int c, long ro
     ws[(size_t)blockIdx.x * c + col] = s;
   }
 }
-__global__ void colsum_final_kernel(const float* __restrict__ ws, int blocks, int c,
-                                    float* __restrict__ db, int accumulate) {
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
-  if (col >= c) return;
-  float s = accumulate ? db[col] : 0.f;
-  for (int b = 0; b < blocks; ++b) s += ws[(size_t)b * c + col];
-  db[col] = s;
+// pass 2: one block; thread (part, col) sums every parts-th partial row, then a fixed-order fold
+__global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ ws, int blocks, int c,
+                                                          float* __restrict__ db, int accumulate) {
+  extern __shared__ float sm[];           // [parts][cw]
+  const int cw = c < 256 ? c : 256;       // columns per pass
+  const int parts = 256 / cw;
+  for (int c0 = 0; c0 < c; c0 += cw) {
+    const int col = c0 + threadIdx.x % cw, part = threadIdx.x / cw;
+    float s = 0.f;
+    if (col < c && part < parts)
+      for (int b = part; b < blocks; b += parts) s += ws[(size_t)b * c + col];
+    __syncthreads();
+    if (part < parts) sm[part * cw + threadIdx.x % cw] = s;
+    __syncthreads();
+    if (threadIdx.x < cw && c0 + threadIdx.x < c) {
+      float t = accumulate ? db[c0 + threadIdx.x] : 0.f;
+      for (int q = 0; q < parts; ++q) t += sm[q * cw + threadIdx.x];
+      db[c0 + threadIdx.x] = t;
+    }
+  }
 }
 
 __global__ void reduce_partials_kernel(const float* __restrict__ partials, int rows, int len,
@@ -245,7 +295,7 @@ extern "C" int vsr_act_bwd(const void* dy, const void* y, void* dz, int32_t dtyp
 }
 
 static int colsum_blocks(int64_t rows) {
-  int64_t b = (rows + 63) / 64;
+  int64_t b = (rows + 255) / 256;
   const int64_t cap = (int64_t)num_sms() * 4;
   if (b > cap) b = cap;
   if (b < 1) b = 1;
@@ -256,6 +306,22 @@ extern "C" size_t vsr_colsum_workspace(int64_t rows, int32_t c) {
   return (size_t)colsum_blocks(rows) * (size_t)c * sizeof(float);
 }
 
+template <typename T>
+static int colsum_launch(const T* x, int64_t rows, int32_t c, float* ws, int blocks, long rpb, cudaStream_t s) {
+  constexpr int VEC = 16 / sizeof(T);
+  const int tpr = c / VEC;
+  if (c % VEC == 0 && tpr >= 1 && tpr <= 256) {
+    const int rpp = 256 / tpr;
+    const size_t smem = (size_t)rpp * c * sizeof(float);
+    if (smem <= 48 * 1024) {
+      colsum_kernel<T><<<blocks, 256, smem, s>>>(x, rows, c, rpb, ws);
+      return 0;
+    }
+  }
+  colsum_scalar_kernel<T><<<blocks, 256, 0, s>>>(x, rows, c, rpb, ws);
+  return 0;
+}
+
 extern "C" int vsr_colsum(const void* x, int32_t dtype, int64_t rows, int32_t c, float* db, int accumulate,
                           void* workspace, size_t workspace_bytes, void* stream) {
   VSR_CHECK_ARG(x && db && rows > 0 && c > 0, "vsr_colsum: bad arguments");
@@ -263,16 +329,15 @@ extern "C" int vsr_colsum(const void* x, int32_t dtype, int64_t rows, int32_t c,
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int blocks = colsum_blocks(rows);
   const long rpb = (rows + blocks - 1) / blocks;
-  const int threads = c >= 256 ? 256 : ((c + 31) / 32) * 32;
   float* ws = static_cast<float*>(workspace);
   if (dtype == VSR_F32)
-    colsum_kernel<float><<<blocks, threads, 0, s>>>((const float*)x, rows, c, rpb, ws);
+    colsum_launch<float>((const float*)x, rows, c, ws, blocks, rpb, s);
   else if (dtype == VSR_BF16)
-    colsum_kernel<__nv_bfloat16><<<blocks, threads, 0, s>>>((const __nv_bfloat16*)x, rows, c, rpb, ws);
+    colsum_launch<__nv_bfloat16>((const __nv_bfloat16*)x, rows, c, ws, blocks, rpb, s);
   else
     VSR_CHECK_ARG(false, "vsr_colsum: bad dtype %d", dtype);
   VSR_CHECK_LAUNCH("vsr_colsum");
-  colsum_final_kernel<<<(c + 127) / 128, 128, 0, s>>>(ws, blocks, c, db, accumulate);
+  colsum_final_kernel<<<1, 256, 256 * sizeof(float), s>>>(ws, blocks, c, db, accumulate);
   VSR_CHECK_LAUNCH("vsr_colsum_final");
   return VSR_OK;
 }

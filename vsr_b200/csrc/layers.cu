@@ -322,6 +322,290 @@ __global__ void conv_last_bwd_final_kernel(const float* __restrict__ ws, int blo
   *dst = accumulate ? *dst + s : s;
 }
 
+// ------------------------------------------------------------------------------------------
+// last conv, v2 (cout == 1, C in {32, 64, 128}): one warp = one SB x SB sub-block of HR pixels
+// (SB = 4, or r for r < 4) with its 1-pixel halo held in registers; every lane owns CPL channels
+// of every halo pixel (coalesced 64/128-byte loads), accumulates the SB*SB partial dot products
+// and the warp folds them with a 16-shuffle transpose-reduce.
+// ------------------------------------------------------------------------------------------
+constexpr int kSBMax = 4;
+constexpr int kHalo = (kSBMax + 2) * (kSBMax + 2);   // 36
+
+struct LastGeom2 {
+  int n, h, w, r, c, sb, nsb;       // nsb = sub-blocks per LR block side (r / sb)
+  int slot_of[64];
+};
+
+template <typename T, int CPL>
+__device__ __forceinline__ void load_cpl(const T* p, float* f) {
+  if constexpr (sizeof(T) == 2) {
+    if constexpr (CPL == 2) {
+      const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(p));
+      f[0] = bf16_lo(u); f[1] = bf16_hi(u);
+    } else {
+      f[0] = __bfloat162float(p[0]);
+    }
+  } else {
+    if constexpr (CPL == 2) {
+      const float2 v = __ldg(reinterpret_cast<const float2*>(p));
+      f[0] = v.x; f[1] = v.y;
+    } else {
+      f[0] = __ldg(p);
+    }
+  }
+}
+template <typename T, int CPL>
+__device__ __forceinline__ void store_cpl(T* p, const float* f) {
+  if constexpr (sizeof(T) == 2) {
+    if constexpr (CPL == 2) *reinterpret_cast<uint32_t*>(p) = pack_bf16x2(f[0], f[1]);
+    else p[0] = __float2bfloat16_rn(f[0]);
+  } else {
+    if constexpr (CPL == 2) *reinterpret_cast<float2*>(p) = make_float2(f[0], f[1]);
+    else p[0] = f[0];
+  }
+}
+
+// fold 16 per-lane values over the 32 lanes: afterwards lanes 2q and 2q+1 hold the sum of value q
+__device__ __forceinline__ float transpose_reduce16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const bool up = lane & 16;
+    const float send = up ? v[i] : v[i + 8];
+    const float keep = up ? v[i + 8] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const bool up = lane & 8;
+    const float send = up ? v[i] : v[i + 4];
+    const float keep = up ? v[i + 4] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const bool up = lane & 4;
+    const float send = up ? v[i] : v[i + 2];
+    const float keep = up ? v[i + 2] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  {
+    const bool up = lane & 2;
+    const float send = up ? v[0] : v[1];
+    const float keep = up ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+struct SubBlock {
+  int ni, Y0, X0;   // top-left HR pixel of the sub-block
+};
+__device__ __forceinline__ SubBlock decode_sb(const LastGeom2& g, long item) {
+  SubBlock b;
+  const int sx = (int)(item % g.nsb); item /= g.nsb;
+  const int sy = (int)(item % g.nsb); item /= g.nsb;
+  const int x = (int)(item % g.w); item /= g.w;
+  const int y = (int)(item % g.h);
+  b.ni = (int)(item / g.h);
+  b.Y0 = y * g.r + sy * g.sb;
+  b.X0 = x * g.r + sx * g.sb;
+  return b;
+}
+template <typename T>
+__device__ __forceinline__ const T* hr_ptr2(const T* x, const LastGeom2& g, int ni, int Y, int X) {
+  const int y = Y / g.r, py = Y - y * g.r, xx = X / g.r, px = X - xx * g.r;
+  return x + ((((size_t)ni * g.h + y) * g.w + xx) * (g.r * g.r) + g.slot_of[py * g.r + px]) * g.c;
+}
+
+template <typename T, int CPL>
+__global__ void __launch_bounds__(256) conv_last2_kernel(const T* __restrict__ x, const __grid_constant__ LastGeom2 g,
+                                                        const float* __restrict__ wt, const float* __restrict__ bias,
+                                                        float* __restrict__ y) {
+  extern __shared__ float sw[];    // [9][C]
+  for (int i = threadIdx.x; i < g.c * 9; i += blockDim.x) sw[(i % 9) * g.c + i / 9] = wt[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int H = g.h * g.r, W = g.w * g.r, HT = g.sb + 2;
+  const long total = (long)g.n * g.h * g.w * g.nsb * g.nsb;
+  const long warp0 = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+  const float b0 = bias ? __ldg(bias) : 0.f;
+  for (long item = warp0; item < total; item += nwarps) {
+    const SubBlock sbk = decode_sb(g, item);
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+    for (int cb = 0; cb < g.c; cb += 32 * CPL) {
+      const int c0 = cb + lane * CPL;
+      float wr[9][CPL];
+#pragma unroll
+      for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int q = 0; q < CPL; ++q) wr[t][q] = sw[t * g.c + c0 + q];
+      float xv[kHalo][CPL];
+#pragma unroll
+      for (int i = 0; i < kSBMax + 2; ++i)
+#pragma unroll
+        for (int j = 0; j < kSBMax + 2; ++j) {
+          const int Y = sbk.Y0 + i - 1, X = sbk.X0 + j - 1;
+          float f[CPL];
+#pragma unroll
+          for (int q = 0; q < CPL; ++q) f[q] = 0.f;
+          if (i < HT && j < HT && Y >= 0 && Y < H && X >= 0 && X < W) load_cpl<T, CPL>(hr_ptr2(x, g, sbk.ni, Y, X) + c0, f);
+#pragma unroll
+          for (int q = 0; q < CPL; ++q) xv[i * (kSBMax + 2) + j][q] = f[q];
+        }
+#pragma unroll
+      for (int oy = 0; oy < kSBMax; ++oy)
+#pragma unroll
+        for (int ox = 0; ox < kSBMax; ++ox) {
+          float s = acc[oy * kSBMax + ox];
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+              for (int q = 0; q < CPL; ++q) s = fmaf(xv[(oy + ky) * (kSBMax + 2) + ox + kx][q], wr[ky * 3 + kx][q], s);
+          acc[oy * kSBMax + ox] = s;
+        }
+    }
+    const float tot = transpose_reduce16(acc, lane);
+    const int q = lane >> 1, oy = q / kSBMax, ox = q % kSBMax;
+    if ((lane & 1) == 0 && oy < g.sb && ox < g.sb)
+      y[((size_t)sbk.ni * H + sbk.Y0 + oy) * W + sbk.X0 + ox] = tot + b0;
+  }
+}
+
+// backward v2 (cout == 1): per sub-block the warp loads the x halo and the dy halo once;
+//   dx(P,c)   = sum_tap dy(P - off(tap)) * w[c][tap]           (stored, CPL channels per lane)
+//   dw[c][tap] += dy(P) * x(P + off(tap), c),  db += dy(P)       (registers -> block -> ws -> final)
+template <typename T, int CPL>
+__global__ void __launch_bounds__(256) conv_last2_bwd_kernel(const T* __restrict__ x, const __grid_constant__ LastGeom2 g,
+                                                            const float* __restrict__ wt, const float* __restrict__ dy,
+                                                            T* __restrict__ dx, float* __restrict__ ws) {
+  extern __shared__ float sm[];    // weights [9][C], then block partial [nw][9*C + 1]
+  float* sw = sm;
+  for (int i = threadIdx.x; i < g.c * 9; i += blockDim.x) sw[(i % 9) * g.c + i / 9] = wt[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int H = g.h * g.r, W = g.w * g.r, HT = g.sb + 2;
+  const long total = (long)g.n * g.h * g.w * g.nsb * g.nsb;
+  const long warp0 = (long)blockIdx.x * nw + warp;
+  const long nwarps = (long)gridDim.x * nw;
+  constexpr int NCB = 4 / CPL;            // channel blocks of 32*CPL (C <= 128)
+  float dwacc[NCB][9][CPL];
+#pragma unroll
+  for (int b = 0; b < NCB; ++b)
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int q = 0; q < CPL; ++q) dwacc[b][t][q] = 0.f;
+  float dbacc = 0.f;
+  for (long item = warp0; item < total; item += nwarps) {
+    const SubBlock sbk = decode_sb(g, item);
+    float gy[kHalo];
+#pragma unroll
+    for (int i = 0; i < kSBMax + 2; ++i)
+#pragma unroll
+      for (int j = 0; j < kSBMax + 2; ++j) {
+        const int Y = sbk.Y0 + i - 1, X = sbk.X0 + j - 1;
+        // dy outside the sub-block's own pixels is needed for dx only; outside the image it is 0
+        gy[i * (kSBMax + 2) + j] =
+            (i < HT && j < HT && Y >= 0 && Y < H && X >= 0 && X < W) ? __ldg(dy + ((size_t)sbk.ni * H + Y) * W + X) : 0.f;
+      }
+#pragma unroll
+    for (int oy = 0; oy < kSBMax; ++oy)
+#pragma unroll
+      for (int ox = 0; ox < kSBMax; ++ox)
+        if (oy < g.sb && ox < g.sb) dbacc += gy[(oy + 1) * (kSBMax + 2) + ox + 1];
+#pragma unroll
+    for (int b = 0; b < NCB; ++b) {
+      const int cb = b * 32 * CPL;
+      if (cb < g.c) {
+        const int c0 = cb + lane * CPL;
+        float wr[9][CPL];
+#pragma unroll
+        for (int t = 0; t < 9; ++t)
+#pragma unroll
+          for (int q = 0; q < CPL; ++q) wr[t][q] = sw[t * g.c + c0 + q];
+        float xv[kHalo][CPL];
+#pragma unroll
+        for (int i = 0; i < kSBMax + 2; ++i)
+#pragma unroll
+          for (int j = 0; j < kSBMax + 2; ++j) {
+            const int Y = sbk.Y0 + i - 1, X = sbk.X0 + j - 1;
+            float f[CPL];
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) f[q] = 0.f;
+            if (i < HT && j < HT && Y >= 0 && Y < H && X >= 0 && X < W) load_cpl<T, CPL>(hr_ptr2(x, g, sbk.ni, Y, X) + c0, f);
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) xv[i * (kSBMax + 2) + j][q] = f[q];
+          }
+#pragma unroll
+        for (int oy = 0; oy < kSBMax; ++oy)
+#pragma unroll
+          for (int ox = 0; ox < kSBMax; ++ox) {
+            if (oy < g.sb && ox < g.sb) {
+              float d[CPL];
+#pragma unroll
+              for (int q = 0; q < CPL; ++q) d[q] = 0.f;
+              const float gc = gy[(oy + 1) * (kSBMax + 2) + ox + 1];
+#pragma unroll
+              for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                  // dx(P) uses dy at P - (ky-1, kx-1): halo index (oy + 1 - (ky-1), ox + 1 - (kx-1))
+                  const float gn = gy[(oy + 2 - ky) * (kSBMax + 2) + ox + 2 - kx];
+#pragma unroll
+                  for (int q = 0; q < CPL; ++q) {
+                    d[q] = fmaf(gn, wr[ky * 3 + kx][q], d[q]);
+                    dwacc[b][ky * 3 + kx][q] = fmaf(gc, xv[(oy + ky) * (kSBMax + 2) + ox + kx][q], dwacc[b][ky * 3 + kx][q]);
+                  }
+                }
+              store_cpl<T, CPL>(const_cast<T*>(hr_ptr2(dx, g, sbk.ni, sbk.Y0 + oy, sbk.X0 + ox)) + c0, d);
+            }
+          }
+      }
+    }
+  }
+  // block fold in fixed warp order
+  const int wsz = 9 * g.c, psz = wsz + 1;
+  float* part = sm + wsz;
+#pragma unroll
+  for (int b = 0; b < NCB; ++b) {
+    const int cb = b * 32 * CPL;
+    if (cb < g.c)
+#pragma unroll
+      for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int q = 0; q < CPL; ++q) part[(size_t)warp * psz + t * g.c + cb + lane * CPL + q] = dwacc[b][t][q];
+  }
+  // every lane accumulated the same db (broadcast dy loads)
+  if (lane == 0) part[(size_t)warp * psz + wsz] = dbacc;
+  __syncthreads();
+  for (int i = threadIdx.x; i < psz; i += blockDim.x) {
+    float s2 = 0.f;
+    for (int wv = 0; wv < nw; ++wv) s2 += part[(size_t)wv * psz + i];
+    ws[(size_t)blockIdx.x * psz + i] = s2;
+  }
+}
+
+bool last2_supported(int r, int c, int cout) { return cout == 1 && (c == 32 || c == 64 || c == 128) && r >= 2 && r <= 8; }
+
+int fill_geom2(LastGeom2* g, int n, int h, int w, int r, int c, const int32_t* phase_yx_host) {
+  g->n = n; g->h = h; g->w = w; g->r = r; g->c = c;
+  g->sb = (r % 4 == 0) ? 4 : r;
+  if (g->sb > kSBMax) return -1;
+  g->nsb = r / g->sb;
+  for (int i = 0; i < 64; ++i) g->slot_of[i] = 0;
+  for (int s = 0; s < r * r; ++s) {
+    const int py = phase_yx_host[2 * s], px = phase_yx_host[2 * s + 1];
+    if (py < 0 || py >= r || px < 0 || px >= r) return -1;
+    g->slot_of[py * r + px] = s;
+  }
+  return 0;
+}
+
 int first_bwd_blocks(long pixels) {
   long b = (pixels + 31) / 32;
   const long cap = (long)num_sms() * 4;
@@ -405,11 +689,27 @@ extern "C" int vsr_conv3x3_last(const void* x, int32_t dtype, int32_t n, int32_t
   VSR_CHECK_ARG(x && w && y && phase_yx && n > 0 && h > 0 && w_ > 0, "vsr_conv3x3_last: bad arguments");
   VSR_CHECK_SUPPORTED(r >= 1 && r <= 8, "vsr_conv3x3_last: r must be in [1,8]");
   VSR_CHECK_SUPPORTED(cout >= 1 && cout <= kMaxCoutLast, "vsr_conv3x3_last: cout must be in [1,%d]", kMaxCoutLast);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (last2_supported(r, c, cout) && (dtype == VSR_F32 || dtype == VSR_BF16)) {
+    LastGeom2 g2;
+    VSR_CHECK_ARG(fill_geom2(&g2, n, h, w_, r, c, phase_yx) == 0, "vsr_conv3x3_last: bad phase table");
+    const long items = (long)n * h * w_ * g2.nsb * g2.nsb;
+    const int grid2 = grid_for(items, 8, 8);
+    const size_t smem2 = (size_t)9 * c * sizeof(float);
+    if (dtype == VSR_BF16) {
+      if (c % 64 == 0) conv_last2_kernel<__nv_bfloat16, 2><<<grid2, 256, smem2, s>>>((const __nv_bfloat16*)x, g2, w, bias, y);
+      else conv_last2_kernel<__nv_bfloat16, 1><<<grid2, 256, smem2, s>>>((const __nv_bfloat16*)x, g2, w, bias, y);
+    } else {
+      if (c % 64 == 0) conv_last2_kernel<float, 2><<<grid2, 256, smem2, s>>>((const float*)x, g2, w, bias, y);
+      else conv_last2_kernel<float, 1><<<grid2, 256, smem2, s>>>((const float*)x, g2, w, bias, y);
+    }
+    VSR_CHECK_LAUNCH("vsr_conv3x3_last(v2)");
+    return VSR_OK;
+  }
   LastGeom g;
   VSR_CHECK_ARG(fill_geom(&g, n, h, w_, r, c, cout, phase_yx) == 0, "vsr_conv3x3_last: bad phase table");
   const size_t smem = (size_t)cout * 9 * c * sizeof(float);
   VSR_CHECK_SUPPORTED(smem <= 48 * 1024, "vsr_conv3x3_last: cout*c too large");
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
   const long total = (long)n * h * r * w_ * r;
   const int grid = grid_for(total, 8, 8);
   if (dtype == VSR_F32)
@@ -434,6 +734,29 @@ extern "C" int vsr_conv3x3_last_bwd(const void* x, int32_t dtype, int32_t n, int
                                     void* workspace, size_t workspace_bytes, void* stream) {
   VSR_CHECK_ARG(x && w && dy && dx && dw && db && phase_yx, "vsr_conv3x3_last_bwd: bad arguments");
   VSR_CHECK_SUPPORTED(r >= 1 && r <= 8, "vsr_conv3x3_last_bwd: r must be in [1,8]");
+  if (last2_supported(r, c, cout) && (dtype == VSR_F32 || dtype == VSR_BF16)) {
+    VSR_CHECK_ARG(workspace && workspace_bytes >= vsr_conv3x3_last_bwd_workspace(n, h, w_, r, c, cout),
+                  "vsr_conv3x3_last_bwd: workspace too small");
+    LastGeom2 g2;
+    VSR_CHECK_ARG(fill_geom2(&g2, n, h, w_, r, c, phase_yx) == 0, "vsr_conv3x3_last_bwd: bad phase table");
+    cudaStream_t s2 = static_cast<cudaStream_t>(stream);
+    const int blocks2 = last_bwd_blocks();
+    const int nw2 = kLastBwdThreads / 32;
+    const size_t psz2 = (size_t)9 * c + 1;
+    const size_t smem2 = ((size_t)9 * c + nw2 * psz2) * sizeof(float);
+    float* ws2 = static_cast<float*>(workspace);
+    if (dtype == VSR_BF16) {
+      if (c % 64 == 0) conv_last2_bwd_kernel<__nv_bfloat16, 2><<<blocks2, kLastBwdThreads, smem2, s2>>>((const __nv_bfloat16*)x, g2, w, dy, (__nv_bfloat16*)dx, ws2);
+      else conv_last2_bwd_kernel<__nv_bfloat16, 1><<<blocks2, kLastBwdThreads, smem2, s2>>>((const __nv_bfloat16*)x, g2, w, dy, (__nv_bfloat16*)dx, ws2);
+    } else {
+      if (c % 64 == 0) conv_last2_bwd_kernel<float, 2><<<blocks2, kLastBwdThreads, smem2, s2>>>((const float*)x, g2, w, dy, (float*)dx, ws2);
+      else conv_last2_bwd_kernel<float, 1><<<blocks2, kLastBwdThreads, smem2, s2>>>((const float*)x, g2, w, dy, (float*)dx, ws2);
+    }
+    VSR_CHECK_LAUNCH("vsr_conv3x3_last_bwd(v2)");
+    conv_last_bwd_final_kernel<<<((int)psz2 + 127) / 128, 128, 0, s2>>>(ws2, blocks2, 1, c, dw, db, accumulate);
+    VSR_CHECK_LAUNCH("vsr_conv3x3_last_bwd_final");
+    return VSR_OK;
+  }
   const int cpl = (c + 31) / 32;
   VSR_CHECK_SUPPORTED(cout >= 1 && cout * cpl <= 4, "vsr_conv3x3_last_bwd: cout*ceil(c/32) must be <= 4 (got %d*%d)", cout, cpl);
   VSR_CHECK_ARG(workspace && workspace_bytes >= vsr_conv3x3_last_bwd_workspace(n, h, w_, r, c, cout),

@@ -362,6 +362,9 @@ int launch_wgrad(const VsrTapGemmDesc* d, float* dw, int accumulate, void* works
 }  // namespace
 
 int tapgemm_tc_launch(const VsrTapGemmDesc* d, cudaStream_t stream);  // tapgemm_tc.cu
+bool wgrad_tc_supported(const VsrTapGemmDesc* d);                       // wgrad_tc.cu
+size_t wgrad_tc_workspace(const VsrTapGemmDesc* d);
+int wgrad_tc_launch(const VsrTapGemmDesc* d, float* dw, int accumulate, void* workspace, cudaStream_t stream);
 
 int validate_desc(const VsrTapGemmDesc* d, const char* who) {
   VSR_CHECK_ARG(d != nullptr, "%s: null descriptor", who);
@@ -410,6 +413,7 @@ extern "C" int vsr_tapgemm_simt_bf16(const VsrTapGemmDesc* d, void* stream) {
 
 extern "C" size_t vsr_tapgemm_wgrad_workspace(const VsrTapGemmDesc* d) {
   if (!d) return 0;
+  if (vsr::wgrad_tc_supported(d)) return vsr::wgrad_tc_workspace(d);
   return (size_t)vsr::wgrad_splits(d) * d->n_taps_total * d->nt * d->kc * sizeof(float);
 }
 
@@ -422,6 +426,23 @@ extern "C" int vsr_tapgemm_wgrad(const VsrTapGemmDesc* d, float* dw, int accumul
   VSR_CHECK_ARG(workspace && workspace_bytes >= vsr_tapgemm_wgrad_workspace(d),
                 "vsr_tapgemm_wgrad: workspace too small (%zu < %zu)", workspace_bytes,
                 vsr_tapgemm_wgrad_workspace(d));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (wgrad_tc_supported(d)) return wgrad_tc_launch(d, dw, accumulate, workspace, s);
+  if (d->dtype == VSR_BF16) return launch_wgrad<__nv_bfloat16>(d, dw, accumulate, workspace, s);
+  return launch_wgrad<float>(d, dw, accumulate, workspace, s);
+}
+
+// test hook: the CUDA-core weight gradient on bf16 storage (cross-check for the tcgen05 path)
+extern "C" size_t vsr_tapgemm_wgrad_simt_workspace(const VsrTapGemmDesc* d) {
+  if (!d) return 0;
+  return (size_t)vsr::wgrad_splits(d) * d->n_taps_total * d->nt * d->kc * sizeof(float);
+}
+extern "C" int vsr_tapgemm_wgrad_simt(const VsrTapGemmDesc* d, float* dw, int accumulate, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
+  using namespace vsr;
+  int rc = validate_desc(d, "vsr_tapgemm_wgrad_simt");
+  if (rc != VSR_OK) return rc;
+  VSR_CHECK_ARG(workspace && workspace_bytes >= vsr_tapgemm_wgrad_simt_workspace(d), "vsr_tapgemm_wgrad_simt: workspace too small");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (d->dtype == VSR_BF16) return launch_wgrad<__nv_bfloat16>(d, dw, accumulate, workspace, s);
   return launch_wgrad<float>(d, dw, accumulate, workspace, s);

@@ -25,7 +25,8 @@ constexpr int kKc = 64;                       // bf16 channels per tap = one 128
 constexpr int kATileBytes = kBlockM * 128;    // 16 KiB
 constexpr int kMaxStages = 8;
 constexpr int kSmemBudget = 227 * 1024;
-constexpr int kCtrlBytes = 1024;              // barriers + tmem pointer + reduction scratch
+constexpr int kStageTileBytes = 4096;         // per epilogue warp: 32 rows x 128 B staging tile
+constexpr int kCtrlBytes = 1024 + 4 * kStageTileBytes;   // barriers, tmem pointer, scratch + staging
 constexpr int kTmemCols = 512;
 constexpr int kThreads = 192;                 // warp0 TMA, warp1 MMA, warps2-5 epilogue
 
@@ -83,6 +84,49 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
   return q;
 }
 
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+// staging tile: row r (0..31), 16-byte chunk q (0..7) lives at r*128 + ((q ^ (r & 7)) << 4)
+__device__ __forceinline__ uint32_t stg_addr(uint32_t base, int r, int q) {
+  return base + r * 128 + ((q ^ (r & 7)) << 4);
+}
+// coalesced read of this warp's [32 rows x 64 ch] bf16 block of a pixel-major map into f[64] of
+// the row-owning thread (lane = row): 4 rows x 128 B per load instruction, via the staging tile.
+__device__ __forceinline__ void load_rows64(const __nv_bfloat16* __restrict__ src, const size_t (&rowoff)[8],
+                                            uint32_t valid_mask, int col0, uint32_t stg, int lane, float* f) {
+  const int q = lane & 7;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if ((valid_mask >> it) & 1u) v = __ldg(reinterpret_cast<const uint4*>(src + rowoff[it] + col0) + q);
+    st_shared_v4(stg_addr(stg, it * 4 + (lane >> 3), q), v);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int c = 0; c < 8; ++c) unpack8(ld_shared_v4(stg_addr(stg, lane, c)), f + 8 * c);
+  __syncwarp();
+}
+// the reverse: v[64] of the row-owning thread -> bf16 -> coalesced store
+__device__ __forceinline__ void store_rows64(__nv_bfloat16* __restrict__ dst, const size_t (&rowoff)[8],
+                                             uint32_t valid_mask, int col0, uint32_t stg, int lane, const float* v) {
+  const int q = lane & 7;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) st_shared_v4(stg_addr(stg, lane, c), pack8(v + 8 * c));
+  __syncwarp();
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const uint4 o = ld_shared_v4(stg_addr(stg, it * 4 + (lane >> 3), q));
+    if ((valid_mask >> it) & 1u) *(reinterpret_cast<uint4*>(dst + rowoff[it] + col0) + q) = o;
+  }
+  __syncwarp();
+}
+
 __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc_kernel(const __grid_constant__ TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -96,6 +140,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc_kernel(const __grid_co
   const uint32_t tmem_slot = smem_base + 160;              // u32
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + 160);
   float* red = reinterpret_cast<float*>(smem_gen + 192);   // 4 floats
+  const uint32_t stg_base = smem_base + 1024;              // 4 x 4 KiB epilogue staging tiles
   const uint32_t stage_base = smem_base + kCtrlBytes;
   const uint32_t b_bytes = static_cast<uint32_t>(a.nt) * 128u;
   const uint32_t stage_bytes = kATileBytes + b_bytes;
@@ -198,6 +243,82 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc_kernel(const __grid_co
       ptx::tc_fence_after();
       const uint32_t taddr =
           tmem_base + static_cast<uint32_t>(buf * a.nt) + (static_cast<uint32_t>(quarter * 32) << 16);
+      if ((a.nt & 63) == 0) {
+        // ---- v2: 64 columns at a time, coalesced global traffic through the staging tile ----
+        const uint32_t stg = stg_base + (warp - 2) * kStageTileBytes;
+        size_t ro[8];
+        uint32_t vmask = 0;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int rr = quarter * 32 + it * 4 + (lane >> 3);
+          const int yy = tc.y0 + rr / a.bw, xx = tc.x0 + rr % a.bw;
+          const bool ok = (yy < a.H) && (xx < a.W);
+          vmask |= (ok ? 1u : 0u) << it;
+          ro[it] = ((static_cast<size_t>(tc.n) * a.H + yy) * a.W + xx) * static_cast<size_t>(a.Cout) + grp.x;
+        }
+        for (int c = 0; c < a.nt; c += 64) {
+          float v[64];
+          {
+            uint32_t r[16];
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              ptx::tmem_ld16(taddr + c + 16 * q4, r);
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[16 * q4 + i] = __uint_as_float(r[i]);
+            }
+          }
+          if (a.epi & VSR_EPI_BIAS) {
+            const float4* bp = reinterpret_cast<const float4*>(a.bias + grp.x + c);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float4 b = __ldg(bp + i);
+              v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+            }
+          }
+          if (a.epi & VSR_EPI_SCALE) {
+#pragma unroll
+            for (int i = 0; i < 64; ++i) v[i] *= a.out_scale;
+          }
+          if (a.epi & VSR_EPI_RES_PRE) {
+            float f[64];
+            load_rows64(a.residual, ro, vmask, c, stg, lane, f);
+#pragma unroll
+            for (int i = 0; i < 64; ++i) v[i] += f[i];
+          }
+          if (a.epi & VSR_EPI_PRELU) {
+#pragma unroll
+            for (int i = 0; i < 64; ++i) v[i] = v[i] > 0.f ? v[i] : slope * v[i];
+          }
+          if (a.epi & VSR_EPI_RELU) {
+#pragma unroll
+            for (int i = 0; i < 64; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
+          if (a.epi & (VSR_EPI_PRELU_BWD | VSR_EPI_RELU_BWD)) {
+            float f[64];
+            load_rows64(a.aux_y, ro, vmask, c, stg, lane, f);
+            if (a.epi & VSR_EPI_PRELU_BWD) {
+#pragma unroll
+              for (int i = 0; i < 64; ++i) {
+                const bool pos = f[i] > 0.f;
+                if (valid) slope_acc += pos ? 0.f : v[i] * (f[i] * inv_slope);
+                v[i] = pos ? v[i] : slope * v[i];
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 64; ++i) v[i] = f[i] > 0.f ? v[i] : 0.f;
+            }
+          }
+          store_rows64(a.out, ro, vmask, c, stg, lane, v);
+          if (a.epi & VSR_EPI_OUT2) {
+            float f[64];
+            load_rows64(a.res2, ro, vmask, c, stg, lane, f);
+#pragma unroll
+            for (int i = 0; i < 64; ++i) f[i] += v[i];
+            store_rows64(a.out2, ro, vmask, c, stg, lane, f);
+          }
+        }
+      } else
       for (int c = 0; c < a.nt; c += 16) {
         uint32_t r[16];
         ptx::tmem_ld16(taddr + c, r);
@@ -385,6 +506,9 @@ void pick_box(int h, int w, int* bw_out, int* bh_out) {
 
 }  // namespace
 
+int get_src_map_pub(const VsrTensor4& t, int bw, int bh, CUtensorMap* out) { return get_src_map(t, bw, bh, out); }
+void pick_box_pub(int h, int w, int* bw, int* bh) { pick_box(h, w, bw, bh); }
+
 int tapgemm_tc_launch(const VsrTapGemmDesc* d, cudaStream_t stream) {
   VSR_CHECK_SUPPORTED(d->kc == kKc, "tapgemm(bf16): kc must be 64, got %d", d->kc);
   VSR_CHECK_SUPPORTED(d->nt >= 16 && d->nt <= 256 && d->nt % 16 == 0,
@@ -433,6 +557,7 @@ int tapgemm_tc_launch(const VsrTapGemmDesc* d, cudaStream_t stream) {
   a.num_tiles = (int)tiles;
   const int stage_bytes = kATileBytes + d->nt * 128;
   int stages = (kSmemBudget - kCtrlBytes - 1024) / stage_bytes;
+  if (stages < 2) stages = 2;
   if (stages > kMaxStages) stages = kMaxStages;
   a.stages = stages;
   const int smem = kCtrlBytes + 1024 + stages * stage_bytes;

@@ -1,0 +1,293 @@
+// wgrad_tc.cu — bf16 weight-gradient of the tap-GEMM on tcgen05 tensor cores (sm_100a).
+//
+//   dw[t][j][k] = sum_pix dz[pix][o0+j] * src_t[pix + off_t][c0_t + k]
+//
+// The reduction runs over pixels, so both operands are "MN-major" for the tensor core: a TMA box
+// [128 pixels x 64 channels] (128-byte rows, 128B swizzle) is a K=128 x MN=64 operand tile.
+// A work item is (group, N-slice of <=128 output channels, chunk of <=8 taps, pixel split):
+// per 128-pixel tile the producer loads the dz tile once (B operand, N = 64 or 128) and streams
+// tap *pairs* (A operand, M = 128 = 2 taps x 64 channels); the MMA thread accumulates every pair
+// into its own TMEM accumulator [128 x N] over all pixel tiles of the split; the epilogue writes
+// fp32 partials to the workspace, and a fixed-order kernel reduces the splits (deterministic).
+//
+// Replaces the weight half of aten.convolution_backward under drf_net.py:55-106,141-147.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "ptx_sm100.cuh"
+
+namespace vsr {
+
+// from tapgemm_tc.cu
+int get_src_map_pub(const VsrTensor4& t, int bw, int bh, CUtensorMap* out);
+void pick_box_pub(int h, int w, int* bw, int* bh);
+
+namespace {
+
+constexpr int kTile = 128;
+constexpr int kTileBytes = kTile * 128;   // one [128 px x 64 ch] bf16 box
+constexpr int kAStages = 4;               // ring of tap pairs (2 boxes each)
+constexpr int kMaxChunk = 8;              // taps per work item
+constexpr int kCtrl = 1024;
+constexpr int kThreads = 192;
+constexpr int kTmemCols = 512;
+
+struct WgArgs {
+  CUtensorMap src_maps[VSR_MAX_SRCS];
+  CUtensorMap dz_map;
+  const int4* tap_tab;
+  const int4* group_tab;
+  float* ws;              // [splits][n_taps_total][nt][64]
+  int n_items, splits, chunks;   // item = (group, N-slice, chunk of <= kMaxChunk taps)
+  int nt, ncta;           // group width, per-item N (64 or 128)
+  int n_taps_total;
+  int N, H, W;
+  int bw, bh, tiles_x, tiles_y, num_ptiles;
+};
+
+__device__ __forceinline__ void tile_coord(const WgArgs& a, int pt, int* n, int* y0, int* x0) {
+  const int tx = pt % a.tiles_x;
+  pt /= a.tiles_x;
+  const int ty = pt % a.tiles_y;
+  *n = pt / a.tiles_y;
+  *x0 = tx * a.bw;
+  *y0 = ty * a.bh;
+}
+
+// MN-major 128B-swizzled operand: 64-element MN atoms are `lbo` bytes apart, 8-row K groups 1024 B.
+__device__ __forceinline__ uint64_t mn_desc(uint32_t addr, uint32_t lbo) {
+  return ptx::make_sw128_desc(addr, lbo, 1024);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_constant__ WgArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - ptx::smem_u32(smem_raw));
+  const uint32_t a_full = base, a_empty = base + 64, b_full = base + 128, b_empty = base + 144;
+  const uint32_t done_bar = base + 160, tmem_slot = base + 168;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(gen + 168);
+  const int nb = a.ncta / 64;                                // dz boxes per tile
+  const uint32_t b_bytes = nb * kTileBytes;
+  const uint32_t b_base = base + kCtrl;                      // 2 buffers
+  const uint32_t a_base = b_base + 2 * b_bytes;              // kAStages x 2 boxes
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item_i = blockIdx.x % a.n_items, split = blockIdx.x / a.n_items;
+  const int halves = a.nt / a.ncta;
+  const int chunk = item_i % a.chunks;
+  const int4 grp = __ldg(a.group_tab + (item_i / a.chunks) / halves);
+  int4 item;                                   // {-, n0, first tap (global), taps in this chunk}
+  item.x = 0;
+  item.y = ((item_i / a.chunks) % halves) * a.ncta;
+  item.z = grp.y + chunk * kMaxChunk;
+  item.w = max(0, min(kMaxChunk, grp.z - chunk * kMaxChunk));
+  const int n_pairs = (item.w + 1) >> 1;
+  const int per = (a.num_ptiles + a.splits - 1) / a.splits;
+  const int pt0 = split * per;
+  const int pt1 = min(pt0 + per, a.num_ptiles);
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < kAStages; ++s) {
+      ptx::mbar_init(a_full + 8 * s, 1);
+      ptx::mbar_init(a_empty + 8 * s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(b_full + 8 * b, 1);
+      ptx::mbar_init(b_empty + 8 * b, 1);
+    }
+    ptx::mbar_init(done_bar, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int pt = pt0; pt < pt1; ++pt, ++it) {
+        int n, y0, x0;
+        tile_coord(a, pt, &n, &y0, &x0);
+        const int bb = it & 1;
+        ptx::mbar_wait(b_empty + 8 * bb, ((it >> 1) & 1) ^ 1u);
+        ptx::mbar_arrive_expect_tx(b_full + 8 * bb, b_bytes);
+        for (int i = 0; i < nb; ++i)
+          ptx::tma_load_4d(b_base + bb * b_bytes + i * kTileBytes, &a.dz_map, b_full + 8 * bb,
+                           grp.x + item.y + i * 64, x0, y0, n);
+        for (int p = 0; p < n_pairs; ++p) {
+          ptx::mbar_wait(a_empty + 8 * stage, phase ^ 1u);
+          ptx::mbar_arrive_expect_tx(a_full + 8 * stage, 2 * kTileBytes);
+          const uint32_t sa = a_base + stage * 2 * kTileBytes;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            int ti = item.z + 2 * p + h;
+            if (2 * p + h >= item.w) ti = item.z + 2 * p;      // odd count: duplicate (rows ignored)
+            const int4 tap = __ldg(a.tap_tab + ti);
+            ptx::tma_load_4d(sa + h * kTileBytes, &a.src_maps[tap.x], a_full + 8 * stage, tap.w, x0 + tap.z,
+                             y0 + tap.y, n);
+          }
+          if (++stage == kAStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = ptx::make_idesc_bf16(128, a.ncta, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int pt = pt0; pt < pt1; ++pt, ++it) {
+        const int bb = it & 1;
+        ptx::mbar_wait(b_full + 8 * bb, (it >> 1) & 1);
+        ptx::tc_fence_after();
+        const uint32_t sb = b_base + bb * b_bytes;
+        for (int p = 0; p < n_pairs; ++p) {
+          ptx::mbar_wait(a_full + 8 * stage, phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = a_base + stage * 2 * kTileBytes;
+#pragma unroll
+          for (int k = 0; k < kTile / 16; ++k) {
+            // 16 pixels = two 8-row K groups = 2048 bytes
+            const uint64_t ad = mn_desc(sa + k * 2048, kTileBytes);
+            const uint64_t bd = mn_desc(sb + k * 2048, kTileBytes);
+            ptx::mma_bf16_ss(tmem_base + p * a.ncta, ad, bd, idesc, (it | k) != 0);
+          }
+          ptx::mma_commit(a_empty + 8 * stage);
+          if (++stage == kAStages) { stage = 0; phase ^= 1u; }
+        }
+        ptx::mma_commit(b_empty + 8 * bb);
+      }
+      ptx::mma_commit(done_bar);
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;       // (tap half, k)
+    const int half = row >> 6, k = row & 63;
+    if (pt1 > pt0) {
+      ptx::mbar_wait(done_bar, 0);
+      ptx::tc_fence_after();
+    }
+    float* wsp = a.ws + (size_t)split * a.n_taps_total * a.nt * 64;
+    for (int p = 0; p < n_pairs; ++p) {
+      const int tl = 2 * p + half;
+      const bool live = tl < item.w;
+      const int ti = item.z + tl;
+      const uint32_t taddr = tmem_base + p * a.ncta + (static_cast<uint32_t>(quarter * 32) << 16);
+      for (int c = 0; c < a.ncta; c += 16) {
+        uint32_t r[16];
+        if (pt1 > pt0) {
+          ptx::tmem_ld16(taddr + c, r);
+          ptx::tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) r[i] = 0u;      // empty split: contributes zeros
+        }
+        if (live) {
+          float* o = wsp + ((size_t)ti * a.nt + item.y + c) * 64 + k;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) o[(size_t)i * 64] = __uint_as_float(r[i]);
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+__global__ void wg_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, long n, int splits,
+                                 int accumulate) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    float s = accumulate ? dw[i] : 0.f;
+    for (int k = 0; k < splits; ++k) s += ws[(size_t)k * n + i];
+    dw[i] = s;
+  }
+}
+
+struct WgPlan {
+  int ncta, n_items, splits, chunks, bw, bh, num_ptiles;
+};
+
+WgPlan make_plan(const VsrTapGemmDesc* d) {
+  WgPlan p;
+  p.ncta = d->nt % 128 == 0 ? 128 : 64;
+  pick_box_pub(d->out.h, d->out.w, &p.bw, &p.bh);
+  const int tx = (d->out.w + p.bw - 1) / p.bw, ty = (d->out.h + p.bh - 1) / p.bh;
+  p.num_ptiles = d->out.n * tx * ty;
+  const int mg = d->max_group_taps > 0 ? d->max_group_taps : (d->n_taps_total + d->n_groups - 1) / d->n_groups;
+  p.chunks = (mg + kMaxChunk - 1) / kMaxChunk;
+  p.n_items = d->n_groups * (d->nt / p.ncta) * p.chunks;
+  int s = (2 * num_sms() + p.n_items - 1) / p.n_items;
+  if (s > p.num_ptiles) s = p.num_ptiles;
+  if (s < 1) s = 1;
+  p.splits = s;
+  return p;
+}
+
+}  // namespace
+
+bool wgrad_tc_supported(const VsrTapGemmDesc* d) {
+  return d->dtype == VSR_BF16 && d->kc == 64 && d->nt % 64 == 0 && d->nt <= 256 && d->out.c % 8 == 0 &&
+         (d->max_group_taps > 0 || d->n_taps_total % d->n_groups == 0);
+}
+
+size_t wgrad_tc_workspace(const VsrTapGemmDesc* d) {
+  const WgPlan p = make_plan(d);
+  return (size_t)p.splits * d->n_taps_total * d->nt * 64 * sizeof(float);
+}
+
+int wgrad_tc_launch(const VsrTapGemmDesc* d, float* dw, int accumulate, void* workspace, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(wgrad smem) failed: %s", cudaGetErrorString(e));
+      return VSR_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  const WgPlan p = make_plan(d);
+  WgArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int s = 0; s < d->n_srcs; ++s) {
+    int rc = get_src_map_pub(d->srcs[s], p.bw, p.bh, &a.src_maps[s]);
+    if (rc != VSR_OK) return rc;
+  }
+  int rc = get_src_map_pub(d->out, p.bw, p.bh, &a.dz_map);
+  if (rc != VSR_OK) return rc;
+  a.tap_tab = reinterpret_cast<const int4*>(d->tap_tab);
+  a.group_tab = reinterpret_cast<const int4*>(d->group_tab);
+  a.ws = static_cast<float*>(workspace);
+  a.n_items = p.n_items;
+  a.splits = p.splits;
+  a.chunks = p.chunks;
+  a.nt = d->nt;
+  a.ncta = p.ncta;
+  a.n_taps_total = d->n_taps_total;
+  a.N = d->out.n; a.H = d->out.h; a.W = d->out.w;
+  a.bw = p.bw; a.bh = p.bh;
+  a.tiles_x = (a.W + p.bw - 1) / p.bw;
+  a.tiles_y = (a.H + p.bh - 1) / p.bh;
+  a.num_ptiles = p.num_ptiles;
+  const int nb = p.ncta / 64;
+  const int smem = kCtrl + 1024 + 2 * nb * kTileBytes + kAStages * 2 * kTileBytes;
+  wgrad_tc_kernel<<<p.n_items * p.splits, kThreads, smem, stream>>>(a);
+  VSR_CHECK_LAUNCH("wgrad_tc");
+  const long n = (long)d->n_taps_total * d->nt * 64;
+  wg_reduce_kernel<<<grid_for(n, 256), 256, 0, stream>>>(a.ws, dw, n, p.splits, accumulate);
+  VSR_CHECK_LAUNCH("wgrad_tc_reduce");
+  return VSR_OK;
+}
+
+}  // namespace vsr

@@ -82,6 +82,7 @@ def _make_desc(tab: TapTable, srcs: Sequence[torch.Tensor], out: torch.Tensor):
     d.out = _tensor4(out)
     gt, tt = tab.device_tabs(out.device)
     d.n_groups, d.n_taps_total = tab.n_groups, tab.n_taps_total
+    d.max_group_taps = max(len(t) for _, t in tab.groups)
     d.group_tab, d.tap_tab = gt.data_ptr(), tt.data_ptr()
     return d
 
