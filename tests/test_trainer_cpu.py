@@ -102,7 +102,7 @@ def _dp_worker(rank, world, port, path, q):
     for _ in range(2):
         step.train_step(xs, ys)
     if rank == 0:
-        q.put(net.flat.clone())
+        q.put(net.flat.detach().numpy().copy())   # by value (a tensor would be passed by fd)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -119,7 +119,7 @@ def test_two_rank_data_parallel_equals_single_rank():
     procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, path, q)) for r in range(2)]
     for p in procs:
         p.start()
-    flat = q.get(timeout=180)
+    flat = torch.from_numpy(q.get(timeout=180))
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
