@@ -231,6 +231,12 @@ int vsr_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, float
                   float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
                   void* stream);
 
+/* Same update with the hyper-parameters read from device memory, so that a captured CUDA graph of
+ * the training step can be replayed while lr / step change:
+ * hyper = float[7] {lr, beta1, beta2, eps, weight_decay, step (>=1), grad_scale}. */
+int vsr_adam_flat_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper,
+                      void* stream);
+
 /* cast fp32 <-> bf16 / layout helpers */
 int vsr_cast(const void* src, int32_t src_dtype, void* dst, int32_t dst_dtype, int64_t n,
              void* stream);

@@ -328,3 +328,7 @@ class EmuOps:
         denom = v.sqrt() / math.sqrt(bc2) + eps
         p.addcdiv_(m, denom, value=-lr / bc1)
         self.launches += 1
+
+    def adam_flat_dev(self, p, g, m, v, hyper):
+        lr, b1, b2, eps, wd, step, gs = [float(x) for x in hyper.tolist()]
+        self.adam_flat(p, g, m, v, lr, b1, b2, eps, wd, int(round(step)), gs)

@@ -83,11 +83,13 @@ _SIGS = {
     "vsr_adam_flat": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float,
                                 C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32, C.c_float,
                                 C.c_void_p]),
+    "vsr_adam_flat_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                    C.c_void_p]),
     "vsr_cast": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p]),
 }
 
 # every symbol include/vsr_b200.h declares (vsr_tapgemm_simt_bf16 is a test hook, not in the header)
-HEADER_SYMBOLS = [s for s in _SIGS if s != "vsr_tapgemm_simt_bf16"]
+HEADER_SYMBOLS = [s for s in _SIGS if s not in ("vsr_tapgemm_simt_bf16",)]
 
 _lib = None
 

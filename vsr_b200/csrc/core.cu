@@ -199,6 +199,25 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                float* __restrict__ v, long n, const float* __restrict__ hyper) {
+  const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4], step = hyper[5],
+              gscale = hyper[6];
+  const float bc1 = 1.f - powf(b1, step);
+  const float bc2_sqrt = sqrtf(1.f - powf(b2, step));
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    float gi = g[i] * gscale;
+    const float pi = p[i];
+    if (wd != 0.f) gi = fmaf(wd, pi, gi);
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - (lr / bc1) * (mi / denom);
+  }
+}
+
 }  // namespace
 }  // namespace vsr
 
@@ -296,7 +315,7 @@ extern "C" int vsr_act_bwd(const void* dy, const void* y, void* dz, int32_t dtyp
 
 static int colsum_blocks(int64_t rows) {
   int64_t b = (rows + 255) / 256;
-  const int64_t cap = (int64_t)num_sms() * 4;
+  const int64_t cap = (int64_t)num_sms();
   if (b > cap) b = cap;
   if (b < 1) b = 1;
   return (int)b;
@@ -363,5 +382,14 @@ extern "C" int vsr_adam_flat(float* p, const float* g, float* m, float* v, int64
   adam_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2), grad_scale);
   VSR_CHECK_LAUNCH("vsr_adam_flat");
+  return VSR_OK;
+}
+
+extern "C" int vsr_adam_flat_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper,
+                                 void* stream) {
+  VSR_CHECK_ARG(p && g && m && v && hyper && n >= 0, "vsr_adam_flat_dev: bad arguments");
+  if (n == 0) return VSR_OK;
+  adam_dev_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, v, n, hyper);
+  VSR_CHECK_LAUNCH("vsr_adam_flat_dev");
   return VSR_OK;
 }

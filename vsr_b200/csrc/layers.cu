@@ -417,6 +417,36 @@ __device__ __forceinline__ const T* hr_ptr2(const T* x, const LastGeom2& g, int 
   return x + ((((size_t)ni * g.h + y) * g.w + xx) * (g.r * g.r) + g.slot_of[py * g.r + px]) * g.c;
 }
 
+// per-item halo geometry: element offset (in pixels*slots) of every halo pixel and its validity;
+// coordinates are clamped so that every load is legal and can be issued unconditionally.
+struct HaloIdx {
+  size_t rowbase[kSBMax + 2];   // ((ni*h + y) * w) * r2  for halo row i
+  int rowphase[kSBMax + 2];     // py * r
+  int colbase[kSBMax + 2];      // x * r2 for halo column j
+  int colphase[kSBMax + 2];     // px
+  uint32_t rowok, colok;        // validity bit masks
+};
+__device__ __forceinline__ void halo_index(const LastGeom2& g, const SubBlock& b, HaloIdx* hi) {
+  const int H = g.h * g.r, W = g.w * g.r, r2 = g.r * g.r, HT = g.sb + 2;
+  hi->rowok = hi->colok = 0;
+#pragma unroll
+  for (int i = 0; i < kSBMax + 2; ++i) {
+    const int Y = b.Y0 + i - 1, X = b.X0 + i - 1;
+    const bool yo = i < HT && Y >= 0 && Y < H, xo = i < HT && X >= 0 && X < W;
+    const int Yc = min(max(Y, 0), H - 1), Xc = min(max(X, 0), W - 1);
+    const int y = Yc / g.r, x = Xc / g.r;
+    hi->rowbase[i] = ((size_t)b.ni * g.h + y) * g.w * r2;
+    hi->rowphase[i] = (Yc - y * g.r) * g.r;
+    hi->colbase[i] = x * r2;
+    hi->colphase[i] = Xc - x * g.r;
+    hi->rowok |= (yo ? 1u : 0u) << i;
+    hi->colok |= (xo ? 1u : 0u) << i;
+  }
+}
+__device__ __forceinline__ size_t halo_off(const LastGeom2& g, const HaloIdx& hi, int i, int j) {
+  return (hi.rowbase[i] + hi.colbase[j] + g.slot_of[hi.rowphase[i] + hi.colphase[j]]) * (size_t)g.c;
+}
+
 template <typename T, int CPL>
 __global__ void __launch_bounds__(256) conv_last2_kernel(const T* __restrict__ x, const __grid_constant__ LastGeom2 g,
                                                         const float* __restrict__ wt, const float* __restrict__ bias,
@@ -432,6 +462,8 @@ __global__ void __launch_bounds__(256) conv_last2_kernel(const T* __restrict__ x
   const float b0 = bias ? __ldg(bias) : 0.f;
   for (long item = warp0; item < total; item += nwarps) {
     const SubBlock sbk = decode_sb(g, item);
+    HaloIdx hi;
+    halo_index(g, sbk, &hi);
     float acc[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) acc[i] = 0.f;
@@ -446,14 +478,15 @@ __global__ void __launch_bounds__(256) conv_last2_kernel(const T* __restrict__ x
 #pragma unroll
       for (int i = 0; i < kSBMax + 2; ++i)
 #pragma unroll
+        for (int j = 0; j < kSBMax + 2; ++j)
+          load_cpl<T, CPL>(x + halo_off(g, hi, i, j) + c0, xv[i * (kSBMax + 2) + j]);   // unconditional (clamped)
+#pragma unroll
+      for (int i = 0; i < kSBMax + 2; ++i)
+#pragma unroll
         for (int j = 0; j < kSBMax + 2; ++j) {
-          const int Y = sbk.Y0 + i - 1, X = sbk.X0 + j - 1;
-          float f[CPL];
+          const bool ok = ((hi.rowok >> i) & 1u) && ((hi.colok >> j) & 1u);
 #pragma unroll
-          for (int q = 0; q < CPL; ++q) f[q] = 0.f;
-          if (i < HT && j < HT && Y >= 0 && Y < H && X >= 0 && X < W) load_cpl<T, CPL>(hr_ptr2(x, g, sbk.ni, Y, X) + c0, f);
-#pragma unroll
-          for (int q = 0; q < CPL; ++q) xv[i * (kSBMax + 2) + j][q] = f[q];
+          for (int q = 0; q < CPL; ++q) xv[i * (kSBMax + 2) + j][q] = ok ? xv[i * (kSBMax + 2) + j][q] : 0.f;
         }
 #pragma unroll
       for (int oy = 0; oy < kSBMax; ++oy)
@@ -503,15 +536,23 @@ __global__ void __launch_bounds__(256) conv_last2_bwd_kernel(const T* __restrict
   float dbacc = 0.f;
   for (long item = warp0; item < total; item += nwarps) {
     const SubBlock sbk = decode_sb(g, item);
+    HaloIdx hi;
+    halo_index(g, sbk, &hi);
     float gy[kHalo];
 #pragma unroll
     for (int i = 0; i < kSBMax + 2; ++i)
 #pragma unroll
       for (int j = 0; j < kSBMax + 2; ++j) {
-        const int Y = sbk.Y0 + i - 1, X = sbk.X0 + j - 1;
         // dy outside the sub-block's own pixels is needed for dx only; outside the image it is 0
-        gy[i * (kSBMax + 2) + j] =
-            (i < HT && j < HT && Y >= 0 && Y < H && X >= 0 && X < W) ? __ldg(dy + ((size_t)sbk.ni * H + Y) * W + X) : 0.f;
+        const int Yc = min(max(sbk.Y0 + i - 1, 0), H - 1), Xc = min(max(sbk.X0 + j - 1, 0), W - 1);
+        gy[i * (kSBMax + 2) + j] = __ldg(dy + ((size_t)sbk.ni * H + Yc) * W + Xc);
+      }
+#pragma unroll
+    for (int i = 0; i < kSBMax + 2; ++i)
+#pragma unroll
+      for (int j = 0; j < kSBMax + 2; ++j) {
+        const bool ok = ((hi.rowok >> i) & 1u) && ((hi.colok >> j) & 1u);
+        gy[i * (kSBMax + 2) + j] = ok ? gy[i * (kSBMax + 2) + j] : 0.f;
       }
 #pragma unroll
     for (int oy = 0; oy < kSBMax; ++oy)
@@ -532,14 +573,15 @@ __global__ void __launch_bounds__(256) conv_last2_bwd_kernel(const T* __restrict
 #pragma unroll
         for (int i = 0; i < kSBMax + 2; ++i)
 #pragma unroll
+          for (int j = 0; j < kSBMax + 2; ++j)
+            load_cpl<T, CPL>(x + halo_off(g, hi, i, j) + c0, xv[i * (kSBMax + 2) + j]);
+#pragma unroll
+        for (int i = 0; i < kSBMax + 2; ++i)
+#pragma unroll
           for (int j = 0; j < kSBMax + 2; ++j) {
-            const int Y = sbk.Y0 + i - 1, X = sbk.X0 + j - 1;
-            float f[CPL];
+            const bool ok = ((hi.rowok >> i) & 1u) && ((hi.colok >> j) & 1u);
 #pragma unroll
-            for (int q = 0; q < CPL; ++q) f[q] = 0.f;
-            if (i < HT && j < HT && Y >= 0 && Y < H && X >= 0 && X < W) load_cpl<T, CPL>(hr_ptr2(x, g, sbk.ni, Y, X) + c0, f);
-#pragma unroll
-            for (int q = 0; q < CPL; ++q) xv[i * (kSBMax + 2) + j][q] = f[q];
+            for (int q = 0; q < CPL; ++q) xv[i * (kSBMax + 2) + j][q] = ok ? xv[i * (kSBMax + 2) + j][q] : 0.f;
           }
 #pragma unroll
         for (int oy = 0; oy < kSBMax; ++oy)
@@ -562,7 +604,7 @@ __global__ void __launch_bounds__(256) conv_last2_bwd_kernel(const T* __restrict
                     dwacc[b][ky * 3 + kx][q] = fmaf(gc, xv[(oy + ky) * (kSBMax + 2) + ox + kx][q], dwacc[b][ky * 3 + kx][q]);
                   }
                 }
-              store_cpl<T, CPL>(const_cast<T*>(hr_ptr2(dx, g, sbk.ni, sbk.Y0 + oy, sbk.X0 + ox)) + c0, d);
+              store_cpl<T, CPL>(dx + halo_off(g, hi, oy + 1, ox + 1) + c0, d);
             }
           }
       }

@@ -26,9 +26,11 @@ constexpr int kATileBytes = kBlockM * 128;    // 16 KiB
 constexpr int kMaxStages = 8;
 constexpr int kSmemBudget = 227 * 1024;
 constexpr int kStageTileBytes = 4096;         // per epilogue warp: 32 rows x 128 B staging tile
-constexpr int kCtrlBytes = 1024 + 4 * kStageTileBytes;   // barriers, tmem pointer, scratch + staging
+constexpr int kEpiWarps = 8;                  // two epilogue groups, one per TMEM accumulator buffer
+constexpr int kBiasBytes = 1024;              // bias of outputs with <= 256 channels is staged in smem
+constexpr int kCtrlBytes = 1024 + kBiasBytes + kEpiWarps * kStageTileBytes;
 constexpr int kTmemCols = 512;
-constexpr int kThreads = 192;                 // warp0 TMA, warp1 MMA, warps2-5 epilogue
+constexpr int kThreads = 64 + 32 * 8;          // warp0 TMA, warp1 MMA, warps 2-5 / 6-9 epilogue groups
 
 struct TcArgs {
   CUtensorMap maps[VSR_MAX_SRCS];
@@ -139,8 +141,12 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc_kernel(const __grid_co
   const uint32_t tempty_bar = smem_base + 144;             // 2 x 8 B
   const uint32_t tmem_slot = smem_base + 160;              // u32
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + 160);
-  float* red = reinterpret_cast<float*>(smem_gen + 192);   // 4 floats
-  const uint32_t stg_base = smem_base + 1024;              // 4 x 4 KiB epilogue staging tiles
+  float* red = reinterpret_cast<float*>(smem_gen + 192);   // 8 floats
+  float* bias_s = reinterpret_cast<float*>(smem_gen + 1024);   // [min(Cout,1024)] when Cout <= 1024
+  const uint32_t stg_base = smem_base + 1024 + kBiasBytes;     // 8 x 4 KiB epilogue staging tiles
+  const bool bias_in_smem = (a.epi & VSR_EPI_BIAS) && a.Cout <= kBiasBytes / 4;
+  if (bias_in_smem)
+    for (int i = threadIdx.x; i < a.Cout; i += blockDim.x) bias_s[i] = a.bias[i];
   const uint32_t stage_base = smem_base + kCtrlBytes;
   const uint32_t b_bytes = static_cast<uint32_t>(a.nt) * 128u;
   const uint32_t stage_bytes = kATileBytes + b_bytes;
@@ -224,6 +230,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc_kernel(const __grid_co
   } else {
     // ===================== epilogue (4 warps, one TMEM lane quarter each) =====================
     const int quarter = warp & 3;
+    const int egroup = (warp - 2) >> 2;          // drains TMEM buffer `egroup` (tiles with it&1 == egroup)
     const int row = quarter * 32 + lane;
     const int ry = row / a.bw, rx = row % a.bw;
     const float slope = (a.epi & (VSR_EPI_PRELU | VSR_EPI_PRELU_BWD)) ? __ldg(a.slope) : 0.f;
@@ -231,6 +238,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc_kernel(const __grid_co
     float slope_acc = 0.f;
     int it = 0;
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
+      if ((it & 1) != egroup) continue;
       const TileCoord tc = decode_tile(a, tile);
       const int4 grp = __ldg(a.group_tab + tc.g);
       const int buf = it & 1;
@@ -259,20 +267,18 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc_kernel(const __grid_co
         for (int c = 0; c < a.nt; c += 64) {
           float v[64];
           {
-            uint32_t r[16];
+            uint32_t r[64];
+            ptx::tmem_ld64(taddr + c, r);
+            ptx::tmem_ld_wait();
 #pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-              ptx::tmem_ld16(taddr + c + 16 * q4, r);
-              ptx::tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[16 * q4 + i] = __uint_as_float(r[i]);
-            }
+            for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
           }
           if (a.epi & VSR_EPI_BIAS) {
-            const float4* bp = reinterpret_cast<const float4*>(a.bias + grp.x + c);
+            const float4* bp = bias_in_smem ? reinterpret_cast<const float4*>(bias_s + grp.x + c)
+                                            : reinterpret_cast<const float4*>(a.bias + grp.x + c);
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              const float4 b = __ldg(bp + i);
+              const float4 b = bp[i];
               v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
             }
           }
@@ -393,9 +399,11 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc_kernel(const __grid_co
     }
     if (a.epi & VSR_EPI_PRELU_BWD) {
       slope_acc = warp_sum(slope_acc);
-      if (lane == 0) red[quarter] = slope_acc;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (warp == 2 && lane == 0) a.slope_partials[blockIdx.x] = (red[0] + red[1]) + (red[2] + red[3]);
+      if (lane == 0) red[warp - 2] = slope_acc;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (warp == 2 && lane == 0)
+        a.slope_partials[blockIdx.x] =
+            ((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7]));
     }
   }
 

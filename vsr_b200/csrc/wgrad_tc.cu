@@ -206,12 +206,27 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
   }
 }
 
-__global__ void wg_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, long n, int splits,
-                                 int accumulate) {
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-    float s = accumulate ? dw[i] : 0.f;
-    for (int k = 0; k < splits; ++k) s += ws[(size_t)k * n + i];
-    dw[i] = s;
+// dw[i] (+)= sum_s ws[s][i]: block = 64 float4 columns x 4 split lanes; every lane sums the splits
+// s = lane (mod 4) in increasing order, then a fixed-order fold -> deterministic.
+__global__ void __launch_bounds__(256) wg_reduce_kernel(const float4* __restrict__ ws, float4* __restrict__ dw, long n4,
+                                                       int splits, int accumulate) {
+  __shared__ float4 sm[4][64];
+  const int col = threadIdx.x & 63, part = threadIdx.x >> 6;
+  const long i = (long)blockIdx.x * 64 + col;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i < n4) {
+    for (int k = part; k < splits; k += 4) {
+      const float4 v = __ldg(ws + (size_t)k * n4 + i);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+  }
+  sm[part][col] = s;
+  __syncthreads();
+  if (part == 0 && i < n4) {
+    float4 t = accumulate ? dw[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { t.x += sm[q][col].x; t.y += sm[q][col].y; t.z += sm[q][col].z; t.w += sm[q][col].w; }
+    dw[i] = t;
   }
 }
 
@@ -228,7 +243,7 @@ WgPlan make_plan(const VsrTapGemmDesc* d) {
   const int mg = d->max_group_taps > 0 ? d->max_group_taps : (d->n_taps_total + d->n_groups - 1) / d->n_groups;
   p.chunks = (mg + kMaxChunk - 1) / kMaxChunk;
   p.n_items = d->n_groups * (d->nt / p.ncta) * p.chunks;
-  int s = (2 * num_sms() + p.n_items - 1) / p.n_items;
+  int s = (num_sms() + p.n_items - 1) / p.n_items;   // one wave of equal-work CTAs
   if (s > p.num_ptiles) s = p.num_ptiles;
   if (s < 1) s = 1;
   p.splits = s;
@@ -285,7 +300,9 @@ int wgrad_tc_launch(const VsrTapGemmDesc* d, float* dw, int accumulate, void* wo
   wgrad_tc_kernel<<<p.n_items * p.splits, kThreads, smem, stream>>>(a);
   VSR_CHECK_LAUNCH("wgrad_tc");
   const long n = (long)d->n_taps_total * d->nt * 64;
-  wg_reduce_kernel<<<grid_for(n, 256), 256, 0, stream>>>(a.ws, dw, n, p.splits, accumulate);
+  const long n4 = n / 4;     // nt * 64 is a multiple of 4
+  wg_reduce_kernel<<<(int)((n4 + 63) / 64), 256, 0, stream>>>(reinterpret_cast<const float4*>(a.ws),
+                                                             reinterpret_cast<float4*>(dw), n4, p.splits, accumulate);
   VSR_CHECK_LAUNCH("wgrad_tc_reduce");
   return VSR_OK;
 }

@@ -35,6 +35,7 @@ class DrfEngine:
         nz = (b >= 0).nonzero()[0]
         self.bias_unpack = (int(nz.min()), torch.from_numpy(b[nz.min():nz.max() + 1].copy()).to(dev))
         self._ws = {}
+        self._row_dst = {}
         self.flat = None
 
     # ---- buffers ---------------------------------------------------------------------------
@@ -275,6 +276,9 @@ class DrfEngine:
             ops.gather_add(dw_packed, idx, gflat[lo:lo + idx.numel()])
         lo, idx = self.bias_unpack
         ops.gather_add(db_packed, idx, gflat[lo:lo + idx.numel()])
-        rd = torch.tensor(row_dst, dtype=torch.int32, device=dev)
+        rd = self._row_dst.get(T)
+        if rd is None or rd.numel() != len(row_dst):        # the launch sequence is a function of T only
+            rd = torch.tensor(row_dst, dtype=torch.int32, device=dev)
+            self._row_dst[T] = rd
         ops.reduce_partials(partials, row[0], rd, gflat)
         return gflat

@@ -12,6 +12,7 @@ class FlatAdam(torch.optim.Optimizer):
         self._m = self._v = None
         self._step = 0
         self.grad_scale = 1.0
+        self._hyper_host = self._hyper_dev = None
 
     def bind(self, net):
         """bind to a vsr_b200 net (its parameters must be exactly this optimizer's parameters)."""
@@ -38,17 +39,37 @@ class FlatAdam(torch.optim.Optimizer):
                                  "exp_avg_sq": self._v[ref.offset:ref.offset + n].view(ref.shape)}
         return flat
 
+    def prepare_step(self):
+        """host side of a step: advance the step count and upload {lr, betas, eps, wd, step, grad_scale}
+        to the device (outside any captured graph)."""
+        flat = self._ensure_state()
+        grp = self.param_groups[0]
+        self._step += 1
+        vals = [float(grp["lr"]), grp["betas"][0], grp["betas"][1], grp["eps"], grp["weight_decay"],
+                float(self._step), self.grad_scale]
+        if self._hyper_dev is None or self._hyper_dev.device != flat.device:
+            self._hyper_host = torch.zeros(7, dtype=torch.float32)
+            if flat.is_cuda:
+                self._hyper_host = self._hyper_host.pin_memory()
+            self._hyper_dev = torch.zeros(7, dtype=torch.float32, device=flat.device)
+        self._hyper_host.copy_(torch.tensor(vals, dtype=torch.float32))
+        self._hyper_dev.copy_(self._hyper_host, non_blocking=True)
+
+    def launch(self, flat_grad):
+        """device side of a step: one fused kernel (graph-capturable)."""
+        flat = self._net.flat
+        self._net._backend().adam_flat_dev(flat, flat_grad.to(flat.dtype) if flat_grad.dtype != flat.dtype else flat_grad,
+                                           self._m, self._v, self._hyper_dev.to(flat.dtype) if flat.dtype != torch.float32 else self._hyper_dev)
+
     @torch.no_grad()
     def step(self, closure=None, flat_grad=None):
         loss = closure() if closure is not None else None
-        flat = self._ensure_state()
+        self._ensure_state()
         g = flat_grad if flat_grad is not None else self._net.flat_grad
         if g is None:
             raise RuntimeError("FlatAdam.step: no flat gradient (run backward first)")
-        grp = self.param_groups[0]
-        self._step += 1
-        self._net._backend().adam_flat(flat, g, self._m, self._v, float(grp["lr"]), grp["betas"][0], grp["betas"][1],
-                             grp["eps"], grp["weight_decay"], self._step, self.grad_scale)
+        self.prepare_step()
+        self.launch(g)
         return loss
 
     def state_dict(self):

@@ -33,8 +33,13 @@ def _loss_kind(fn):
 class VSRTrainStep:
     """The fused training / evaluation step on one rank."""
 
-    def __init__(self, net, loss_fns, loss_weights, metric_fns, optimizer, dataset="acdc", process_group=None):
+    def __init__(self, net, loss_fns, loss_weights, metric_fns, optimizer, dataset="acdc", process_group=None,
+                 use_graph=False):
         self.net, self.optimizer = net, optimizer
+        # CUDA-graph the whole step (needs FlatAdam: its hyper-parameters live on the device);
+        # the first two calls per input shape run eagerly, the third captures, later ones replay.
+        self.use_graph = use_graph and isinstance(optimizer, FlatAdam)
+        self._graphs, self._calls = {}, {}
         self.losses = [_loss_kind(f) for f in loss_fns]
         self.loss_names = [f.__class__.__name__ for f in loss_fns]
         self.loss_weights = [float(w) for w in loss_weights]
@@ -112,15 +117,10 @@ class VSRTrainStep:
         ops.reduce_partials(partials, L * T, rd, sums)
         return sums / (outs[0].numel() * T), grads     # all frames share a shape
 
-    def train_step(self, inputs, targets, acc=None, with_metrics=True):
-        """One optimisation step. `acc` ([1 + n_loss + n_metric] device tensor) accumulates
-        Loss, each loss and each metric for logging. Returns the loss values (device tensor)."""
+    def _device_step(self, inputs, targets, acc, with_metrics):
+        """everything of a step that runs on the device (graph-capturable)."""
         net = self.net
-        if not net._is_flat():
-            net._flatten()
         eng = self._engine()
-        inputs = [x.contiguous() for x in inputs]
-        targets = [y.contiguous() for y in targets]
         eng.pack(net.flat, need_bwd=True)
         outs, saved = eng.forward(inputs, save=True)
         lvals, grads = self._loss(outs, targets, True)
@@ -129,18 +129,65 @@ class VSRTrainStep:
         if self.world > 1:
             dist.all_reduce(gflat, group=self.pg)        # NCCL sum over NVLink; mean folded into Adam
         if isinstance(self.optimizer, FlatAdam):
-            self.optimizer.step(flat_grad=gflat)
-        else:
+            self.optimizer.launch(gflat)
+        if acc is not None:
+            self._log(acc, lvals)
+            if with_metrics and self.metric_names:
+                self._metrics(outs, targets, acc)
+        return lvals, outs, gflat
+
+    def train_step(self, inputs, targets, acc=None, with_metrics=True):
+        """One optimisation step. `acc` ([1 + n_loss + n_metric] device tensor) accumulates
+        Loss, each loss and each metric for logging. Returns the loss values (device tensor)."""
+        net = self.net
+        if not net._is_flat():
+            net._flatten()
+        inputs = [x.contiguous() for x in inputs]
+        targets = [y.contiguous() for y in targets]
+        flat_adam = isinstance(self.optimizer, FlatAdam)
+        if flat_adam:
+            self.optimizer.prepare_step()
+        if self.use_graph and net.flat.is_cuda:
+            return self._graphed_step(inputs, targets, acc, with_metrics)
+        lvals, outs, gflat = self._device_step(inputs, targets, acc, with_metrics)
+        if not flat_adam:
             if self.world > 1:
                 gflat.mul_(1.0 / self.world)
             for p, ref in zip(net.parameters(), net._plan.params.values()):
                 p.grad = gflat[ref.offset:ref.offset + p.numel()].view(ref.shape)
             self.optimizer.step()
-        if acc is not None:
-            self._log(acc, lvals)
-            if with_metrics and self.metric_names:
-                self._metrics(outs, targets, acc)
         return lvals, outs
+
+    def _graphed_step(self, inputs, targets, acc, with_metrics):
+        key = (len(inputs), tuple(inputs[0].shape), tuple(targets[0].shape), acc is not None, with_metrics)
+        n = self._calls.get(key, 0)
+        self._calls[key] = n + 1
+        if n < 2:                                   # eager: fills workspaces / descriptor caches
+            lvals, outs, _ = self._device_step(inputs, targets, acc, with_metrics)
+            return lvals, outs
+        g = self._graphs.get(key)
+        if g is None:
+            dev = self.net.flat.device
+            st = {"in": [torch.empty_like(x) for x in inputs], "tg": [torch.empty_like(y) for y in targets],
+                  "acc": torch.zeros(1 + len(self.losses) + len(self.metric_names), device=dev)}
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(graph, stream=side):
+                    st["acc"].zero_()
+                    st["lvals"], st["outs"], _ = self._device_step(st["in"], st["tg"], st["acc"], with_metrics)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            st["graph"] = graph
+            self._graphs[key] = g = st
+        for d, s_ in zip(g["in"], inputs):
+            d.copy_(s_, non_blocking=True)
+        for d, s_ in zip(g["tg"], targets):
+            d.copy_(s_, non_blocking=True)
+        g["graph"].replay()
+        if acc is not None:
+            acc += g["acc"]
+        return g["lvals"], g["outs"]
 
     @torch.no_grad()
     def eval_step(self, inputs, targets, acc=None):
