@@ -294,18 +294,27 @@ def main():
     if rank == 0:
         pk = peaks()
         # dominant kernel family: the tcgen05 tap-GEMM (all forward / data-gradient convolutions)
-        agg = {}
-        for kind, flops, a, b in timing:
+        agg, detail = {}, {}
+        for kind, flops, a, b, sig, nbytes in timing:
+            t_ms = a.elapsed_time(b)
             d = agg.setdefault(kind, [0.0, 0.0, 0])
             d[0] += flops
-            d[1] += a.elapsed_time(b)
+            d[1] += t_ms
             d[2] += 1
+            q = detail.setdefault(f"{kind}:{sig}", [0.0, 0.0, 0, 0.0])
+            q[0] += flops
+            q[1] += t_ms
+            q[2] += 1
+            q[3] += nbytes
         dom = max(agg, key=lambda k: agg[k][1])
         flops, kms, cnt = agg[dom]
         achieved = flops / (kms * 1e-3) / 1e12
         peak = pk["bf16_tflops_sustained"]
         kernel_share = {k: {"ms_per_step": v[1] / prof_steps, "launches_per_step": v[2] / prof_steps,
                             "tflops": v[0] / (v[1] * 1e-3) / 1e12} for k, v in agg.items()}
+        top = sorted(detail.items(), key=lambda kv: -kv[1][1])[:14]
+        kernel_detail = {k: {"ms_per_step": v[1] / prof_steps, "n_per_step": v[2] / prof_steps,
+                             "tflops": v[0] / (v[1] * 1e-3) / 1e12, "gbs": v[3] / (v[1] * 1e-3) / 1e9} for k, v in top}
         step_flops = 3.0 * FWD_FLOPS_PER_LR_PIXEL * args.batch * T * LR * LR
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -321,7 +330,7 @@ def main():
             "roofline": {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak, "traffic": None,
                          "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk['source']})",
-                         "launches": cnt, "kernels": kernel_share,
+                         "launches": cnt, "kernels": kernel_share, "kernel_detail": kernel_detail,
                          "timing_pass": f"{prof_steps} extra steps of the same workload, CUDA events around each launch",
                          "step_tflops_algorithmic": step_flops / (ms * 1e-3) / 1e12 * world},
         }

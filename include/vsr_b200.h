@@ -122,6 +122,12 @@ size_t vsr_tapgemm_wgrad_workspace(const VsrTapGemmDesc* d);
 int vsr_tapgemm_wgrad(const VsrTapGemmDesc* d, float* dw, int accumulate, void* workspace,
                       size_t workspace_bytes, void* stream);
 
+/* Weight gradient with the bias gradient fused where the kernel supports it:
+ * db[q] (+)= sum over pixels and channels c = q (mod db_period) of dz.  Returns 1 if db was produced,
+ * 0 if only dw was (the caller then runs vsr_colsum), negative on error. */
+int vsr_tapgemm_wgrad_bias(const VsrTapGemmDesc* d, float* dw, float* db, int32_t db_period, int accumulate,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
 /* colsum: db[c] (+)= sum over pixels x[pix][c]  (bias gradient; fixed order).
  * workspace >= vsr_colsum_workspace(rows, c) bytes. */
 size_t vsr_colsum_workspace(int64_t rows, int32_t c);

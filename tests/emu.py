@@ -109,8 +109,14 @@ class EmuOps:
     def tapgemm_wgrad_workspace(self, tab, srcs, dz):
         return 16
 
-    def tapgemm_wgrad(self, tab, srcs, dz, dw, accumulate, workspace):
+    def tapgemm_wgrad(self, tab, srcs, dz, dw, accumulate, workspace, db=None, db_period=0):
         ct = torch.float64 if dw.dtype == torch.float64 else torch.float32
+        if db is not None:
+            s = dz.to(ct).reshape(-1, dz.shape[-1] // db_period, db_period).sum((0, 1))
+            if accumulate:
+                db += s.to(db.dtype)
+            else:
+                db.copy_(s.to(db.dtype))
         res = torch.empty(tab.n_taps_total, tab.nt, tab.kc, dtype=ct, device=dz.device)
         ti = 0
         for o0, taps in tab.groups:
@@ -125,6 +131,7 @@ class EmuOps:
         else:
             flat.copy_(res.reshape(-1).to(dw.dtype))
         self.launches += 2
+        return db is not None
 
     # ---- small kernels -----------------------------------------------------------------
     def colsum_workspace(self, rows, c):

@@ -39,14 +39,20 @@ def timed(fn, iters, flush):
     return ts[len(ts) // 2]
 
 
+CASES = None
+EPI = 1 | 4
+
+
 def tapgemm_case(name, tab, n, h, w, src_cs, out_c, dtype, iters, flush, results):
+    if CASES and name not in CASES:
+        return
     ops = cuda_ops()
     srcs = [torch.randn(n, h, w, c, device="cuda").to(dtype) for c in src_cs]
     out = torch.empty(n, h, w, out_c, device="cuda", dtype=dtype)
     wts = (torch.randn(tab.n_taps_total * tab.nt * tab.kc, device="cuda") * 0.05).to(dtype)
     bias = torch.zeros(out_c, device="cuda")
     slope = torch.tensor([0.2], device="cuda")
-    fn = lambda: ops.tapgemm(tab, srcs, out, wts, bias=bias, epi=1 | 4, slope=slope)
+    fn = lambda: ops.tapgemm(tab, srcs, out, wts, bias=bias, epi=EPI, slope=slope)
     ms = timed(fn, iters, flush)
     pix = n * h * w
     flops = 2.0 * pix * tab.n_taps_total * tab.nt * tab.kc
@@ -64,7 +70,12 @@ def main():
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--json", default=None)
     ap.add_argument("--fp32", action="store_true", help="also time the CUDA-core fp32 kernels")
+    ap.add_argument("--cases", default=None, help="comma-separated kernel names")
+    ap.add_argument("--epi", type=int, default=5, help="epilogue flags (default bias+PReLU)")
     args = ap.parse_args()
+    global CASES, EPI
+    CASES = set(args.cases.split(",")) if args.cases else None
+    EPI = args.epi
     flush = torch.zeros(64 * 1024 * 1024, device="cuda")  # 256 MB
     results = []
     N, h, w, F = 32, 32, 32, 64

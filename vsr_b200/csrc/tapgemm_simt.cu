@@ -364,7 +364,8 @@ int launch_wgrad(const VsrTapGemmDesc* d, float* dw, int accumulate, void* works
 int tapgemm_tc_launch(const VsrTapGemmDesc* d, cudaStream_t stream);  // tapgemm_tc.cu
 bool wgrad_tc_supported(const VsrTapGemmDesc* d);                       // wgrad_tc.cu
 size_t wgrad_tc_workspace(const VsrTapGemmDesc* d);
-int wgrad_tc_launch(const VsrTapGemmDesc* d, float* dw, int accumulate, void* workspace, cudaStream_t stream);
+int wgrad_tc_launch(const VsrTapGemmDesc* d, float* dw, float* db, int db_period, int accumulate, void* workspace,
+                    cudaStream_t stream);
 
 int validate_desc(const VsrTapGemmDesc* d, const char* who) {
   VSR_CHECK_ARG(d != nullptr, "%s: null descriptor", who);
@@ -427,7 +428,7 @@ extern "C" int vsr_tapgemm_wgrad(const VsrTapGemmDesc* d, float* dw, int accumul
                 "vsr_tapgemm_wgrad: workspace too small (%zu < %zu)", workspace_bytes,
                 vsr_tapgemm_wgrad_workspace(d));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (wgrad_tc_supported(d)) return wgrad_tc_launch(d, dw, accumulate, workspace, s);
+  if (wgrad_tc_supported(d)) return wgrad_tc_launch(d, dw, nullptr, 0, accumulate, workspace, s);
   if (d->dtype == VSR_BF16) return launch_wgrad<__nv_bfloat16>(d, dw, accumulate, workspace, s);
   return launch_wgrad<float>(d, dw, accumulate, workspace, s);
 }
@@ -446,4 +447,24 @@ extern "C" int vsr_tapgemm_wgrad_simt(const VsrTapGemmDesc* d, float* dw, int ac
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (d->dtype == VSR_BF16) return launch_wgrad<__nv_bfloat16>(d, dw, accumulate, workspace, s);
   return launch_wgrad<float>(d, dw, accumulate, workspace, s);
+}
+
+// weight gradient + bias gradient (db[q] (+)= sum over pixels and channels c = q mod period of dz).
+// Returns 1 if the bias gradient was fused, 0 if the caller still has to run vsr_colsum.
+extern "C" int vsr_tapgemm_wgrad_bias(const VsrTapGemmDesc* d, float* dw, float* db, int32_t db_period,
+                                      int accumulate, void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace vsr;
+  int rc = validate_desc(d, "vsr_tapgemm_wgrad_bias");
+  if (rc != VSR_OK) return rc;
+  VSR_CHECK_ARG(dw != nullptr && db != nullptr && db_period > 0, "vsr_tapgemm_wgrad_bias: bad arguments");
+  VSR_CHECK_ARG(workspace && workspace_bytes >= vsr_tapgemm_wgrad_workspace(d),
+                "vsr_tapgemm_wgrad_bias: workspace too small (%zu < %zu)", workspace_bytes,
+                vsr_tapgemm_wgrad_workspace(d));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (wgrad_tc_supported(d) && d->out.c <= 1024 && d->out.c % db_period == 0) {
+    rc = wgrad_tc_launch(d, dw, db, db_period, accumulate, workspace, s);
+    return rc == VSR_OK ? 1 : rc;
+  }
+  rc = vsr_tapgemm_wgrad(d, dw, accumulate, workspace, workspace_bytes, stream);
+  return rc;
 }

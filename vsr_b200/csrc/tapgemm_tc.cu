@@ -28,7 +28,10 @@ constexpr int kSmemBudget = 227 * 1024;
 constexpr int kStageTileBytes = 4096;         // per epilogue warp: 32 rows x 128 B staging tile
 constexpr int kEpiWarps = 8;                  // two epilogue groups, one per TMEM accumulator buffer
 constexpr int kBiasBytes = 1024;              // bias of outputs with <= 256 channels is staged in smem
-constexpr int kCtrlBytes = 1024 + kBiasBytes + kEpiWarps * kStageTileBytes;
+constexpr int kMaxSmemGroups = 48;            // group table rows cached in smem (16 B each, ctrl[256..1024))
+constexpr int kMaxSmemTaps = 256;             // packed tap entries cached in smem (4 B each)
+constexpr int kTapBytes = kMaxSmemTaps * 4;
+constexpr int kCtrlBytes = 1024 + kTapBytes + kBiasBytes + kEpiWarps * kStageTileBytes;
 constexpr int kTmemCols = 512;
 constexpr int kThreads = 64 + 32 * 8;          // warp0 TMA, warp1 MMA, warps 2-5 / 6-9 epilogue groups
 
@@ -50,9 +53,19 @@ struct TcArgs {
   int nt, n_groups;
   int N, H, W, Cout;
   int bw, bh, tiles_x, tiles_y;
+  int bw_shift;            // bw is a power of two
   int num_tiles;
   int stages;
+  int n_taps_total;
 };
+
+// tap entry packed into 32 bits: src[0:4) | dy+8 [4:8) | dx+8 [8:12) | c0/8 [12:32)
+__device__ __forceinline__ uint32_t pack_tap(const int4& t) {
+  return (uint32_t)t.x | ((uint32_t)(t.y + 8) << 4) | ((uint32_t)(t.z + 8) << 8) | ((uint32_t)(t.w >> 3) << 12);
+}
+__device__ __forceinline__ int4 unpack_tap(uint32_t p) {
+  return make_int4((int)(p & 15u), (int)((p >> 4) & 15u) - 8, (int)((p >> 8) & 15u) - 8, (int)(p >> 12) << 3);
+}
 
 struct TileCoord {
   int g, n, y0, x0;
@@ -130,9 +143,10 @@ __device__ __forceinline__ void store_rows64(__nv_bfloat16* __restrict__ dst, co
 }
 
 __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc_kernel(const __grid_constant__ TcArgs a) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = ptx::smem_u32(smem_raw);
+  uint8_t* smem_gen = smem_raw;
+  if (smem_base & 1023u) __trap();             // the swizzled tiles need a 1024-byte aligned window
 
   // control block
   const uint32_t full_bar = smem_base;                     // kMaxStages x 8 B
@@ -142,8 +156,16 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc_kernel(const __grid_co
   const uint32_t tmem_slot = smem_base + 160;              // u32
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + 160);
   float* red = reinterpret_cast<float*>(smem_gen + 192);   // 8 floats
-  float* bias_s = reinterpret_cast<float*>(smem_gen + 1024);   // [min(Cout,1024)] when Cout <= 1024
-  const uint32_t stg_base = smem_base + 1024 + kBiasBytes;     // 8 x 4 KiB epilogue staging tiles
+  int4* grp_s = reinterpret_cast<int4*>(smem_gen + 256);        // group table (<= 48 rows)
+  uint32_t* tap_s = reinterpret_cast<uint32_t*>(smem_gen + 1024);   // packed tap table (<= 256 entries)
+  float* bias_s = reinterpret_cast<float*>(smem_gen + 1024 + kTapBytes);   // bias when Cout <= 256
+  const uint32_t stg_base = smem_base + 1024 + kTapBytes + kBiasBytes;     // 8 x 4 KiB staging tiles
+  const bool grp_in_smem = a.n_groups <= kMaxSmemGroups;
+  const bool taps_in_smem = a.n_taps_total <= kMaxSmemTaps;
+  if (grp_in_smem)
+    for (int i = threadIdx.x; i < a.n_groups; i += blockDim.x) grp_s[i] = __ldg(a.group_tab + i);
+  if (taps_in_smem)
+    for (int i = threadIdx.x; i < a.n_taps_total; i += blockDim.x) tap_s[i] = pack_tap(__ldg(a.tap_tab + i));
   const bool bias_in_smem = (a.epi & VSR_EPI_BIAS) && a.Cout <= kBiasBytes / 4;
   if (bias_in_smem)
     for (int i = threadIdx.x; i < a.Cout; i += blockDim.x) bias_s[i] = a.bias[i];
@@ -181,9 +203,9 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc_kernel(const __grid_co
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(a, tile);
-        const int4 grp = __ldg(a.group_tab + tc.g);
+        const int4 grp = grp_in_smem ? grp_s[tc.g] : __ldg(a.group_tab + tc.g);
         for (int t = 0; t < grp.z; ++t) {
-          const int4 tap = __ldg(a.tap_tab + grp.y + t);
+          const int4 tap = taps_in_smem ? unpack_tap(tap_s[grp.y + t]) : __ldg(a.tap_tab + grp.y + t);
           ptx::mbar_wait(empty_bar + 8 * stage, phase ^ 1u);
           const uint32_t fb = full_bar + 8 * stage;
           ptx::mbar_arrive_expect_tx(fb, stage_bytes);
@@ -204,7 +226,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc_kernel(const __grid_co
       int it = 0;
       for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
         const TileCoord tc = decode_tile(a, tile);
-        const int4 grp = __ldg(a.group_tab + tc.g);
+        const int4 grp = grp_in_smem ? grp_s[tc.g] : __ldg(a.group_tab + tc.g);
         const int buf = it & 1;
         const uint32_t bphase = (it >> 1) & 1;
         ptx::mbar_wait(tempty_bar + 8 * buf, bphase ^ 1u);
@@ -232,7 +254,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc_kernel(const __grid_co
     const int quarter = warp & 3;
     const int egroup = (warp - 2) >> 2;          // drains TMEM buffer `egroup` (tiles with it&1 == egroup)
     const int row = quarter * 32 + lane;
-    const int ry = row / a.bw, rx = row % a.bw;
+    const int ry = row >> a.bw_shift, rx = row & (a.bw - 1);
     const float slope = (a.epi & (VSR_EPI_PRELU | VSR_EPI_PRELU_BWD)) ? __ldg(a.slope) : 0.f;
     const float inv_slope = slope != 0.f ? 1.f / slope : 0.f;
     float slope_acc = 0.f;
@@ -240,7 +262,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc_kernel(const __grid_co
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
       if ((it & 1) != egroup) continue;
       const TileCoord tc = decode_tile(a, tile);
-      const int4 grp = __ldg(a.group_tab + tc.g);
+      const int4 grp = grp_in_smem ? grp_s[tc.g] : __ldg(a.group_tab + tc.g);
       const int buf = it & 1;
       const uint32_t bphase = (it >> 1) & 1;
       const int y = tc.y0 + ry, x = tc.x0 + rx;
@@ -259,7 +281,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc_kernel(const __grid_co
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int rr = quarter * 32 + it * 4 + (lane >> 3);
-          const int yy = tc.y0 + rr / a.bw, xx = tc.x0 + rr % a.bw;
+          const int yy = tc.y0 + (rr >> a.bw_shift), xx = tc.x0 + (rr & (a.bw - 1));
           const bool ok = (yy < a.H) && (xx < a.W);
           vmask |= (ok ? 1u : 0u) << it;
           ro[it] = ((static_cast<size_t>(tc.n) * a.H + yy) * a.W + xx) * static_cast<size_t>(a.Cout) + grp.x;
@@ -558,17 +580,20 @@ int tapgemm_tc_launch(const VsrTapGemmDesc* d, cudaStream_t stream) {
   a.n_groups = d->n_groups;
   a.N = d->out.n; a.H = d->out.h; a.W = d->out.w; a.Cout = d->out.c;
   a.bw = bw; a.bh = bh;
+  a.bw_shift = 0;
+  while ((1 << a.bw_shift) < bw) ++a.bw_shift;
   a.tiles_x = (a.W + bw - 1) / bw;
   a.tiles_y = (a.H + bh - 1) / bh;
   const long tiles = (long)a.n_groups * a.N * a.tiles_x * a.tiles_y;
   VSR_CHECK_SUPPORTED(tiles < (1l << 30), "tapgemm(bf16): too many tiles");
   a.num_tiles = (int)tiles;
+  a.n_taps_total = d->n_taps_total;
   const int stage_bytes = kATileBytes + d->nt * 128;
-  int stages = (kSmemBudget - kCtrlBytes - 1024) / stage_bytes;
+  int stages = (kSmemBudget - kCtrlBytes) / stage_bytes;
   if (stages < 2) stages = 2;
   if (stages > kMaxStages) stages = kMaxStages;
   a.stages = stages;
-  const int smem = kCtrlBytes + 1024 + stages * stage_bytes;
+  const int smem = kCtrlBytes + stages * stage_bytes;
   int grid = num_sms();
   if (grid > a.num_tiles) grid = a.num_tiles;
   if (grid > kPartialsLen) grid = kPartialsLen;

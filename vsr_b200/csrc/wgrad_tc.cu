@@ -38,6 +38,8 @@ struct WgArgs {
   const int4* tap_tab;
   const int4* group_tab;
   float* ws;              // [splits][n_taps_total][nt][64]
+  float* bias_ws;         // [splits][cout] column sums of dz (bias gradient), or NULL
+  int cout;
   int n_items, splits, chunks;   // item = (group, N-slice, chunk of <= kMaxChunk taps)
   int nt, ncta;           // group width, per-item N (64 or 128)
   int n_taps_total;
@@ -85,7 +87,10 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
   const int per = (a.num_ptiles + a.splits - 1) / a.splits;
   const int pt0 = split * per;
   const int pt1 = min(pt0 + per, a.num_ptiles);
+  // the first chunk of every (group, N-slice) also sums the columns of its dz tiles (bias gradient)
+  const bool do_cs = a.bias_ws != nullptr && chunk == 0;
 
+  float cs0_out = 0.f, cs1_out = 0.f;
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < kAStages; ++s) {
       ptx::mbar_init(a_full + 8 * s, 1);
@@ -93,7 +98,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
     }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(b_full + 8 * b, 1);
-      ptx::mbar_init(b_empty + 8 * b, 1);
+      ptx::mbar_init(b_empty + 8 * b, do_cs ? 5 : 1);   // MMA commit (+ the 4 column-sum warps)
     }
     ptx::mbar_init(done_bar, 1);
     ptx::fence_mbar_init();
@@ -112,6 +117,9 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      int4 taps[kMaxChunk];                     // the chunk's taps, fetched once (independent loads)
+#pragma unroll
+      for (int i = 0; i < kMaxChunk; ++i) taps[i] = __ldg(a.tap_tab + item.z + (i < item.w ? i : 0));
       for (int pt = pt0; pt < pt1; ++pt, ++it) {
         int n, y0, x0;
         tile_coord(a, pt, &n, &y0, &x0);
@@ -127,9 +135,11 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
           const uint32_t sa = a_base + stage * 2 * kTileBytes;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            int ti = item.z + 2 * p + h;
-            if (2 * p + h >= item.w) ti = item.z + 2 * p;      // odd count: duplicate (rows ignored)
-            const int4 tap = __ldg(a.tap_tab + ti);
+            int tl = 2 * p + h;
+            if (tl >= item.w) tl = 2 * p;                      // odd count: duplicate (rows ignored)
+            int4 tap = taps[0];
+#pragma unroll
+            for (int i = 1; i < kMaxChunk; ++i) tap = (i == tl) ? taps[i] : tap;
             ptx::tma_load_4d(sa + h * kTileBytes, &a.src_maps[tap.x], a_full + 8 * stage, tap.w, x0 + tap.z,
                              y0 + tap.y, n);
           }
@@ -170,6 +180,29 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;       // (tap half, k)
     const int half = row >> 6, k = row & 63;
+    float cs0 = 0.f, cs1 = 0.f;
+    const int cpairs = a.ncta >> 1;            // column pairs of the dz tile (32 or 64)
+    const int cp = row % cpairs, part = row / cpairs;
+    if (do_cs) {
+      const int rows_per = kTile / (kTile / cpairs);
+      const int c = 2 * cp, cc = c & 63;
+      int it = 0;
+      for (int pt = pt0; pt < pt1; ++pt, ++it) {
+        const int bb = it & 1;
+        ptx::mbar_wait(b_full + 8 * bb, (it >> 1) & 1);
+        const uint32_t tb = b_base + bb * b_bytes + (c >> 6) * kTileBytes;
+#pragma unroll 8
+        for (int r = part * rows_per; r < (part + 1) * rows_per; ++r) {
+          uint32_t u;
+          const uint32_t addr = tb + r * 128 + ((((cc >> 3) ^ (r & 7))) << 4) + (cc & 7) * 2;
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u) : "r"(addr) : "memory");
+          cs0 += bf16_lo(u);
+          cs1 += bf16_hi(u);
+        }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(b_empty + 8 * bb);
+      }
+    }
     if (pt1 > pt0) {
       ptx::mbar_wait(done_bar, 0);
       ptx::tc_fence_after();
@@ -196,6 +229,23 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
         }
       }
     }
+    cs0_out = cs0;
+    cs1_out = cs1;
+  }
+  if (do_cs && warp >= 2) {
+    // fold the row parts in fixed order through smem (all MMAs / TMA loads of this CTA are done)
+    const int quarter = warp & 3, row = quarter * 32 + lane;
+    float2* scr = reinterpret_cast<float2*>(gen + kCtrl);
+    const int cpairs = a.ncta >> 1, cp = row % cpairs, part = row / cpairs, parts = kTile / cpairs;
+    scr[row] = make_float2(cs0_out, cs1_out);
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (part == 0) {
+      float s0 = 0.f, s1 = 0.f;
+      for (int q = 0; q < parts; ++q) { s0 += scr[q * cpairs + cp].x; s1 += scr[q * cpairs + cp].y; }
+      float* o = a.bias_ws + (size_t)split * a.cout + grp.x + item.y + 2 * cp;
+      o[0] = s0;
+      o[1] = s1;
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -208,9 +258,26 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
 
 // dw[i] (+)= sum_s ws[s][i]: block = 64 float4 columns x 4 split lanes; every lane sums the splits
 // s = lane (mod 4) in increasing order, then a fixed-order fold -> deterministic.
+// The last block (if bias_ws) reduces the bias partials: db[q] (+)= sum_s sum_{c = q mod period} bias_ws[s][c].
 __global__ void __launch_bounds__(256) wg_reduce_kernel(const float4* __restrict__ ws, float4* __restrict__ dw, long n4,
-                                                       int splits, int accumulate) {
+                                                       int splits, int accumulate, const float* __restrict__ bias_ws,
+                                                       int cout, int period, float* __restrict__ db) {
   __shared__ float4 sm[4][64];
+  if (bias_ws != nullptr && blockIdx.x == gridDim.x - 1) {
+    float* colsum = reinterpret_cast<float*>(sm);          // [cout <= 1024]
+    for (int c = threadIdx.x; c < cout; c += blockDim.x) {
+      float s = 0.f;
+      for (int k = 0; k < splits; ++k) s += bias_ws[(size_t)k * cout + c];
+      colsum[c] = s;
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < period; q += blockDim.x) {
+      float s = accumulate ? db[q] : 0.f;
+      for (int c = q; c < cout; c += period) s += colsum[c];
+      db[q] = s;
+    }
+    return;
+  }
   const int col = threadIdx.x & 63, part = threadIdx.x >> 6;
   const long i = (long)blockIdx.x * 64 + col;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -259,10 +326,11 @@ bool wgrad_tc_supported(const VsrTapGemmDesc* d) {
 
 size_t wgrad_tc_workspace(const VsrTapGemmDesc* d) {
   const WgPlan p = make_plan(d);
-  return (size_t)p.splits * d->n_taps_total * d->nt * 64 * sizeof(float);
+  return (size_t)p.splits * ((size_t)d->n_taps_total * d->nt * 64 + d->out.c) * sizeof(float);
 }
 
-int wgrad_tc_launch(const VsrTapGemmDesc* d, float* dw, int accumulate, void* workspace, cudaStream_t stream) {
+int wgrad_tc_launch(const VsrTapGemmDesc* d, float* dw, float* db, int db_period, int accumulate, void* workspace,
+                    cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -284,6 +352,9 @@ int wgrad_tc_launch(const VsrTapGemmDesc* d, float* dw, int accumulate, void* wo
   a.tap_tab = reinterpret_cast<const int4*>(d->tap_tab);
   a.group_tab = reinterpret_cast<const int4*>(d->group_tab);
   a.ws = static_cast<float*>(workspace);
+  const bool with_bias = db != nullptr && d->out.c <= 1024 && db_period > 0 && d->out.c % db_period == 0;
+  a.bias_ws = with_bias ? a.ws + (size_t)p.splits * d->n_taps_total * d->nt * 64 : nullptr;
+  a.cout = d->out.c;
   a.n_items = p.n_items;
   a.splits = p.splits;
   a.chunks = p.chunks;
@@ -301,8 +372,9 @@ int wgrad_tc_launch(const VsrTapGemmDesc* d, float* dw, int accumulate, void* wo
   VSR_CHECK_LAUNCH("wgrad_tc");
   const long n = (long)d->n_taps_total * d->nt * 64;
   const long n4 = n / 4;     // nt * 64 is a multiple of 4
-  wg_reduce_kernel<<<(int)((n4 + 63) / 64), 256, 0, stream>>>(reinterpret_cast<const float4*>(a.ws),
-                                                             reinterpret_cast<float4*>(dw), n4, p.splits, accumulate);
+  wg_reduce_kernel<<<(int)((n4 + 63) / 64) + (with_bias ? 1 : 0), 256, 0, stream>>>(
+      reinterpret_cast<const float4*>(a.ws), reinterpret_cast<float4*>(dw), n4, p.splits, accumulate, a.bias_ws,
+      d->out.c, db_period, db);
   VSR_CHECK_LAUNCH("wgrad_tc_reduce");
   return VSR_OK;
 }

@@ -166,10 +166,13 @@ class DrfEngine:
         def wgrad(lname, srcs, dz):
             L = P.fwd[lname]
             ws = self._workspace("wgrad", ops.tapgemm_wgrad_workspace(L.table, srcs, dz))
-            ops.tapgemm_wgrad(L.table, srcs, dz, dw_packed[L.w_off:L.w_off + L.w_numel], True, ws)
-            rows = dz.numel() // L.bias_c
-            wsb = self._workspace("colsum", ops.colsum_workspace(rows, L.bias_c))
-            ops.colsum(dz, rows, L.bias_c, db_packed[L.b_off:L.b_off + L.bias_c], True, wsb)
+            db = db_packed[L.b_off:L.b_off + L.bias_c]
+            fused = ops.tapgemm_wgrad(L.table, srcs, dz, dw_packed[L.w_off:L.w_off + L.w_numel], True, ws,
+                                      db=db, db_period=L.bias_c)
+            if not fused:      # CUDA-core path / unsupported shape: separate column-sum kernels
+                rows = dz.numel() // L.bias_c
+                wsb = self._workspace("colsum", ops.colsum_workspace(rows, L.bias_c))
+                ops.colsum(dz, rows, L.bias_c, db, True, wsb)
 
         def dgrad(lname, srcs, out, aux=None, slope_ref=None, residual=None):
             L = P.bwd[lname]

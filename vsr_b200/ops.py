@@ -117,7 +117,10 @@ class CudaOps:
             check(fn(C.byref(d), _stream()), "vsr_tapgemm")
             e1.record()
             pix = out.shape[0] * out.shape[1] * out.shape[2]
-            self.timing.append(("tapgemm", 2.0 * pix * tab.n_taps_total * tab.nt * tab.kc, e0, e1))
+            sig = f"taps{tab.n_taps_total}_nt{tab.nt}_g{tab.n_groups}_px{pix}_epi{epi}"
+            es = out.element_size()
+            nbytes = es * (sum(pix * s.shape[-1] for s in srcs) + pix * out.shape[-1])
+            self.timing.append(("tapgemm", 2.0 * pix * tab.n_taps_total * tab.nt * tab.kc, e0, e1, sig, nbytes))
         else:
             check(fn(C.byref(d), _stream()), "vsr_tapgemm")
         self.launches += 1
@@ -125,20 +128,33 @@ class CudaOps:
     def tapgemm_wgrad_workspace(self, tab, srcs, dz):
         return self.lib.vsr_tapgemm_wgrad_workspace(C.byref(_make_desc(tab, srcs, dz)))
 
-    def tapgemm_wgrad(self, tab, srcs, dz, dw, accumulate, workspace):
+    def tapgemm_wgrad(self, tab, srcs, dz, dw, accumulate, workspace, db=None, db_period=0):
+        """weight gradient; with db, also tries to fuse the bias gradient — returns True if db was produced."""
         d = _make_desc(tab, srcs, dz)
-        _need_cuda(dw, workspace)
+        _need_cuda(dw, workspace, db)
         if self.timing is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        check(self.lib.vsr_tapgemm_wgrad(C.byref(d), _p(dw), int(accumulate), _p(workspace),
-                                         workspace.numel() * workspace.element_size(), _stream()),
-              "vsr_tapgemm_wgrad")
+        fused = False
+        nbytes_ws = workspace.numel() * workspace.element_size()
+        if db is not None:
+            rc = self.lib.vsr_tapgemm_wgrad_bias(C.byref(d), _p(dw), _p(db), db_period, int(accumulate),
+                                                 _p(workspace), nbytes_ws, _stream())
+            if rc < 0:
+                check(rc, "vsr_tapgemm_wgrad_bias")
+            fused = rc == 1
+        else:
+            check(self.lib.vsr_tapgemm_wgrad(C.byref(d), _p(dw), int(accumulate), _p(workspace), nbytes_ws,
+                                             _stream()), "vsr_tapgemm_wgrad")
         if self.timing is not None:
             e1.record()
             pix = dz.shape[0] * dz.shape[1] * dz.shape[2]
-            self.timing.append(("wgrad", 2.0 * pix * tab.n_taps_total * tab.nt * tab.kc, e0, e1))
+            sig = f"taps{tab.n_taps_total}_nt{tab.nt}_g{tab.n_groups}_px{pix}"
+            es = dz.element_size()
+            nbytes = es * (sum(pix * s.shape[-1] for s in srcs) + pix * dz.shape[-1])
+            self.timing.append(("wgrad", 2.0 * pix * tab.n_taps_total * tab.nt * tab.kc, e0, e1, sig, nbytes))
         self.launches += 2
+        return fused
 
     # ---- small kernels -----------------------------------------------------------------
     def colsum_workspace(self, rows, c):
