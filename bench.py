@@ -337,9 +337,14 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line), flush=True)
+    # hang-proof exit: synchronise, then leave without tearing NCCL / CUDA graphs down
+    torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 if __name__ == "__main__":

@@ -57,6 +57,9 @@ struct TcArgs {
   int num_tiles;
   int stages;
   int n_taps_total;
+  int resident;            // 1: the current group's weight slabs stay in smem across tiles
+  int res_bytes;           // size of the resident weight region
+  int m_tiles;             // pixel tiles per group
 };
 
 // tap entry packed into 32 bits: src[0:4) | dy+8 [4:8) | dx+8 [8:12) | c0/8 [12:32)
@@ -71,10 +74,18 @@ struct TileCoord {
   int g, n, y0, x0;
 };
 
+// non-resident: groups vary fastest (concurrent CTAs share A tiles in L2);
+// resident: group-major, every CTA walks a contiguous tile range (the group rarely changes).
 __device__ __forceinline__ TileCoord decode_tile(const TcArgs& a, int tile) {
   TileCoord t;
-  t.g = tile % a.n_groups;
-  int mt = tile / a.n_groups;
+  int mt;
+  if (a.resident) {
+    t.g = tile / a.m_tiles;
+    mt = tile - t.g * a.m_tiles;
+  } else {
+    t.g = tile % a.n_groups;
+    mt = tile / a.n_groups;
+  }
   const int tx = mt % a.tiles_x;
   mt /= a.tiles_x;
   const int ty = mt % a.tiles_y;
@@ -154,6 +165,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc_kernel(const __grid_co
   const uint32_t tfull_bar = smem_base + 128;              // 2 x 8 B
   const uint32_t tempty_bar = smem_base + 144;             // 2 x 8 B
   const uint32_t tmem_slot = smem_base + 160;              // u32
+  const uint32_t bres_full = smem_base + 168, bres_empty = smem_base + 176;
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + 160);
   float* red = reinterpret_cast<float*>(smem_gen + 192);   // 8 floats
   int4* grp_s = reinterpret_cast<int4*>(smem_gen + 256);        // group table (<= 48 rows)
@@ -169,9 +181,14 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc_kernel(const __grid_co
   const bool bias_in_smem = (a.epi & VSR_EPI_BIAS) && a.Cout <= kBiasBytes / 4;
   if (bias_in_smem)
     for (int i = threadIdx.x; i < a.Cout; i += blockDim.x) bias_s[i] = a.bias[i];
-  const uint32_t stage_base = smem_base + kCtrlBytes;
+  const uint32_t res_base = smem_base + kCtrlBytes;        // resident weight slabs (resident mode)
+  const uint32_t stage_base = res_base + a.res_bytes;
   const uint32_t b_bytes = static_cast<uint32_t>(a.nt) * 128u;
-  const uint32_t stage_bytes = kATileBytes + b_bytes;
+  const uint32_t stage_bytes = a.resident ? kATileBytes : kATileBytes + b_bytes;
+  // tile walk of this CTA
+  const int tile_begin = a.resident ? (int)((long)a.num_tiles * blockIdx.x / gridDim.x) : (int)blockIdx.x;
+  const int tile_end = a.resident ? (int)((long)a.num_tiles * (blockIdx.x + 1) / gridDim.x) : a.num_tiles;
+  const int tile_step = a.resident ? 1 : (int)gridDim.x;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -185,6 +202,8 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc_kernel(const __grid_co
       ptx::mbar_init(tfull_bar + 8 * b, 1);
       ptx::mbar_init(tempty_bar + 8 * b, 128);
     }
+    ptx::mbar_init(bres_full, 1);
+    ptx::mbar_init(bres_empty, 1);
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
@@ -201,9 +220,20 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc_kernel(const __grid_co
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+      int cur_g = -1;
+      uint32_t gcount = 0;
+      for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
         const TileCoord tc = decode_tile(a, tile);
         const int4 grp = grp_in_smem ? grp_s[tc.g] : __ldg(a.group_tab + tc.g);
+        if (a.resident && tc.g != cur_g) {
+          // (re)load this group's weight slabs once all MMAs of the previous group are done
+          ptx::mbar_wait(bres_empty, (gcount & 1u) ^ 1u);
+          ptx::mbar_arrive_expect_tx(bres_full, static_cast<uint32_t>(grp.z) * b_bytes);
+          for (int t = 0; t < grp.z; ++t)
+            ptx::bulk_load(res_base + t * b_bytes, a.w + static_cast<size_t>(grp.y + t) * b_bytes, b_bytes, bres_full);
+          cur_g = tc.g;
+          ++gcount;
+        }
         for (int t = 0; t < grp.z; ++t) {
           const int4 tap = taps_in_smem ? unpack_tap(tap_s[grp.y + t]) : __ldg(a.tap_tab + grp.y + t);
           ptx::mbar_wait(empty_bar + 8 * stage, phase ^ 1u);
@@ -211,8 +241,8 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc_kernel(const __grid_co
           ptx::mbar_arrive_expect_tx(fb, stage_bytes);
           const uint32_t sa = stage_base + stage * stage_bytes;
           ptx::tma_load_4d(sa, &a.maps[tap.x], fb, tap.w, tc.x0 + tap.z, tc.y0 + tap.y, tc.n);
-          ptx::bulk_load(sa + kATileBytes, a.w + static_cast<size_t>(grp.y + t) * b_bytes, b_bytes,
-                         fb);
+          if (!a.resident)
+            ptx::bulk_load(sa + kATileBytes, a.w + static_cast<size_t>(grp.y + t) * b_bytes, b_bytes, fb);
           if (++stage == a.stages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -224,9 +254,16 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc_kernel(const __grid_co
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
+      int cur_g = -1;
+      uint32_t gcount = 0;
+      for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++it) {
         const TileCoord tc = decode_tile(a, tile);
         const int4 grp = grp_in_smem ? grp_s[tc.g] : __ldg(a.group_tab + tc.g);
+        if (a.resident && tc.g != cur_g) {
+          ptx::mbar_wait(bres_full, gcount & 1u);
+          cur_g = tc.g;
+          ++gcount;
+        }
         const int buf = it & 1;
         const uint32_t bphase = (it >> 1) & 1;
         ptx::mbar_wait(tempty_bar + 8 * buf, bphase ^ 1u);
@@ -237,7 +274,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc_kernel(const __grid_co
           ptx::tc_fence_after();
           const uint32_t sa = stage_base + stage * stage_bytes;
           const uint64_t adesc = ptx::make_sw128_desc(sa, 16, 1024);
-          const uint64_t bdesc = ptx::make_sw128_desc(sa + kATileBytes, 16, 1024);
+          const uint64_t bdesc = ptx::make_sw128_desc(a.resident ? res_base + t * b_bytes : sa + kATileBytes, 16, 1024);
 #pragma unroll
           for (int k = 0; k < kKc / 16; ++k) {
             // advancing K by 16 bf16 = 32 bytes = 2 descriptor address units
@@ -247,6 +284,10 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc_kernel(const __grid_co
           if (++stage == a.stages) { stage = 0; phase ^= 1u; }
         }
         ptx::mma_commit(tfull_bar + 8 * buf);
+        if (a.resident) {
+          const int next = tile + tile_step;
+          if (next >= tile_end || decode_tile(a, next).g != cur_g) ptx::mma_commit(bres_empty);
+        }
       }
     }
   } else {
@@ -259,7 +300,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc_kernel(const __grid_co
     const float inv_slope = slope != 0.f ? 1.f / slope : 0.f;
     float slope_acc = 0.f;
     int it = 0;
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++it) {
       if ((it & 1) != egroup) continue;
       const TileCoord tc = decode_tile(a, tile);
       const int4 grp = grp_in_smem ? grp_s[tc.g] : __ldg(a.group_tab + tc.g);
@@ -588,12 +629,17 @@ int tapgemm_tc_launch(const VsrTapGemmDesc* d, cudaStream_t stream) {
   VSR_CHECK_SUPPORTED(tiles < (1l << 30), "tapgemm(bf16): too many tiles");
   a.num_tiles = (int)tiles;
   a.n_taps_total = d->n_taps_total;
-  const int stage_bytes = kATileBytes + d->nt * 128;
-  int stages = (kSmemBudget - kCtrlBytes) / stage_bytes;
-  if (stages < 2) stages = 2;
+  a.m_tiles = a.N * a.tiles_x * a.tiles_y;
+  const int b_bytes = d->nt * 128;
+  const long res_need = (long)d->max_group_taps * b_bytes;
+  a.resident = d->max_group_taps > 0 && res_need <= kSmemBudget - kCtrlBytes - 4 * kATileBytes;
+  a.res_bytes = a.resident ? (int)res_need : 0;
+  const int stage_bytes = a.resident ? kATileBytes : kATileBytes + b_bytes;
+  int stages = (kSmemBudget - kCtrlBytes - a.res_bytes) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) stages = 2;
   a.stages = stages;
-  const int smem = kCtrlBytes + stages * stage_bytes;
+  const int smem = kCtrlBytes + a.res_bytes + stages * stage_bytes;
   int grid = num_sms();
   if (grid > a.num_tiles) grid = a.num_tiles;
   if (grid > kPartialsLen) grid = kPartialsLen;

@@ -117,8 +117,8 @@ class VSRTrainStep:
         ops.reduce_partials(partials, L * T, rd, sums)
         return sums / (outs[0].numel() * T), grads     # all frames share a shape
 
-    def _device_step(self, inputs, targets, acc, with_metrics):
-        """everything of a step that runs on the device (graph-capturable)."""
+    def _device_fwd_bwd(self, inputs, targets):
+        """pack + forward + fused loss + backward: everything before the gradient exchange."""
         net = self.net
         eng = self._engine()
         eng.pack(net.flat, need_bwd=True)
@@ -126,14 +126,23 @@ class VSRTrainStep:
         lvals, grads = self._loss(outs, targets, True)
         gflat = eng.backward(saved, grads)
         net.flat_grad = gflat
+        return lvals, outs, gflat
+
+    def _device_update(self, lvals, outs, targets, gflat, acc, with_metrics):
+        """gradient all-reduce (NCCL over NVLink) + fused Adam + logging / metrics."""
         if self.world > 1:
-            dist.all_reduce(gflat, group=self.pg)        # NCCL sum over NVLink; mean folded into Adam
+            dist.all_reduce(gflat, group=self.pg)        # sum; the 1/world mean is folded into Adam
         if isinstance(self.optimizer, FlatAdam):
             self.optimizer.launch(gflat)
         if acc is not None:
             self._log(acc, lvals)
             if with_metrics and self.metric_names:
                 self._metrics(outs, targets, acc)
+
+    def _device_step(self, inputs, targets, acc, with_metrics):
+        """everything of a step that runs on the device."""
+        lvals, outs, gflat = self._device_fwd_bwd(inputs, targets)
+        self._device_update(lvals, outs, targets, gflat, acc, with_metrics)
         return lvals, outs, gflat
 
     def train_step(self, inputs, targets, acc=None, with_metrics=True):
@@ -166,6 +175,7 @@ class VSRTrainStep:
             lvals, outs, _ = self._device_step(inputs, targets, acc, with_metrics)
             return lvals, outs
         g = self._graphs.get(key)
+        single = self.world == 1
         if g is None:
             dev = self.net.flat.device
             st = {"in": [torch.empty_like(x) for x in inputs], "tg": [torch.empty_like(y) for y in targets],
@@ -174,9 +184,13 @@ class VSRTrainStep:
             side.wait_stream(torch.cuda.current_stream(dev))
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.stream(side):
-                with torch.cuda.graph(graph, stream=side):
-                    st["acc"].zero_()
-                    st["lvals"], st["outs"], _ = self._device_step(st["in"], st["tg"], st["acc"], with_metrics)
+                # one rank: the whole step is one graph.  Several ranks: the graph ends before the
+                # NCCL all-reduce, which (with Adam and the metrics, ~30 launches) is issued eagerly.
+                with torch.cuda.graph(graph, stream=side, capture_error_mode="thread_local"):
+                    st["lvals"], st["outs"], st["gflat"] = self._device_fwd_bwd(st["in"], st["tg"])
+                    if single:
+                        st["acc"].zero_()
+                        self._device_update(st["lvals"], st["outs"], st["tg"], st["gflat"], st["acc"], with_metrics)
             torch.cuda.current_stream(dev).wait_stream(side)
             st["graph"] = graph
             self._graphs[key] = g = st
@@ -185,8 +199,12 @@ class VSRTrainStep:
         for d, s_ in zip(g["tg"], targets):
             d.copy_(s_, non_blocking=True)
         g["graph"].replay()
-        if acc is not None:
-            acc += g["acc"]
+        self.net.flat_grad = g["gflat"]
+        if single:
+            if acc is not None:
+                acc += g["acc"]
+        else:
+            self._device_update(g["lvals"], g["outs"], g["tg"], g["gflat"], acc, with_metrics)
         return g["lvals"], g["outs"]
 
     @torch.no_grad()
