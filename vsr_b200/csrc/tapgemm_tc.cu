@@ -10,6 +10,7 @@
 //
 // Replaces aten.convolution / convolution_backward(data) under drf_net.py:55-106,141-147.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include <mutex>
 #include <unordered_map>
@@ -633,14 +634,20 @@ int tapgemm_tc_launch(const VsrTapGemmDesc* d, cudaStream_t stream) {
   const int b_bytes = d->nt * 128;
   const long res_need = (long)d->max_group_taps * b_bytes;
   a.resident = d->max_group_taps > 0 && res_need <= kSmemBudget - kCtrlBytes - 4 * kATileBytes;
+  static const char* env_res = getenv("VSR_TC_RESIDENT");      // tuning overrides (not part of the ABI)
+  static const char* env_stg = getenv("VSR_TC_STAGES");
+  static const char* env_grid = getenv("VSR_TC_GRID");
+  if (!(env_res && env_res[0] == '1')) a.resident = 0;   // opt-in: measured no gain (profiles/README.md)
   a.res_bytes = a.resident ? (int)res_need : 0;
   const int stage_bytes = a.resident ? kATileBytes : kATileBytes + b_bytes;
   int stages = (kSmemBudget - kCtrlBytes - a.res_bytes) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
-  if (stages < 2) stages = 2;
+  if (env_stg && atoi(env_stg) >= 1 && atoi(env_stg) < stages) stages = atoi(env_stg);
+  if (stages < 1) stages = 1;
   a.stages = stages;
   const int smem = kCtrlBytes + a.res_bytes + stages * stage_bytes;
   int grid = num_sms();
+  if (env_grid && atoi(env_grid) >= 1) grid = atoi(env_grid);
   if (grid > a.num_tiles) grid = a.num_tiles;
   if (grid > kPartialsLen) grid = kPartialsLen;
   tapgemm_tc_kernel<<<grid, kThreads, smem, stream>>>(a);
