@@ -114,6 +114,7 @@ def run_reference(args):
         return
     from oracle import restated
     from vsr_b200.nets import DRFNet
+    torch.set_num_threads(os.cpu_count() or 1)      # torchrun pins OMP_NUM_THREADS=1: use every host core
     torch.manual_seed(0)
     sample = 2
     net = DRFNet(**MODEL)            # parameter container only (same init as the reference class)
@@ -153,6 +154,7 @@ def cpu_baseline(budget_s=20.0):
     """oracle port timed on this box's host cores on a bounded sample (rank 0, N=1 only)."""
     from oracle import restated
     from vsr_b200.nets import DRFNet
+    torch.set_num_threads(os.cpu_count() or 1)
     torch.manual_seed(0)
     sample = 2
     net = DRFNet(**MODEL)

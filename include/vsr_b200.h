@@ -174,6 +174,10 @@ int vsr_act_bwd(const void* dy, const void* y, void* dz, int32_t dtype, int64_t 
 /* out[i] = a[i] + b[i] (pixel-major maps, dtype) — global skip drf_net.py:46 when not fused */
 int vsr_add(const void* a, const void* b, void* out, int32_t dtype, int64_t numel, void* stream);
 
+/* x[i] *= alpha (fp32) — res_scale of the EDSR residual blocks applied to packed gradients
+ * (edsr_net.py:50-52). */
+int vsr_scale(float* x, int64_t n, float alpha, void* stream);
+
 /* dst[row_dst[r]] += sum(partials[r][0..len))  for r < rows; fixed order. */
 int vsr_reduce_partials(const float* partials, int32_t rows, int32_t len, const int32_t* row_dst,
                         float* dst, void* stream);

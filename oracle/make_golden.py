@@ -97,6 +97,39 @@ def main():
         torch.save(fx, path)
         print(name, os.path.getsize(path) // 1024, "KiB", "loss", float(loss), "psnr", float(psnr), "ssim", float(ssim))
 
+    # the secondary nets on the same kernels: SRFBNet (srfb_net.py) and EDSRNet (edsr_net.py)
+    for name, cls, kw, n, h, w in [
+        ("srfbnet_f8_g2_x4", "SRFBNet", dict(in_channels=1, out_channels=1, num_steps=3, num_features=8, num_groups=2, upscale_factor=4), 2, 10, 12),
+        ("srfbnet_f8_g2_x2", "SRFBNet", dict(in_channels=1, out_channels=1, num_steps=2, num_features=8, num_groups=2, upscale_factor=2), 1, 12, 9),
+        ("edsrnet_f8_b3_x4", "EDSRNet", dict(in_channels=1, out_channels=1, num_resblocks=3, num_features=8, upscale_factor=4), 2, 10, 12),
+        ("edsrnet_f8_b2_x3", "EDSRNet", dict(in_channels=1, out_channels=1, num_resblocks=2, num_features=8, upscale_factor=3), 1, 11, 9),
+        ("srfbnet_f64_g2_x4", "SRFBNet", dict(in_channels=1, out_channels=1, num_steps=2, num_features=64, num_groups=2, upscale_factor=4), 1, 12, 12),
+        ("edsrnet_f64_b2_x4", "EDSRNet", dict(in_channels=1, out_channels=1, num_resblocks=2, num_features=64, upscale_factor=4), 1, 12, 12),
+    ]:
+        torch.manual_seed(len(name))
+        net = getattr(ref, cls)(**kw)
+        big = kw["num_features"] >= 32
+        if big:
+            net.load_state_dict(seeded_fill(net.state_dict(), seed=2000 + len(name)))
+        r = kw["upscale_factor"]
+        lr, hr = synth(n, 1, h, w, r, seed=300 + len(name))
+        x, y = lr[0], hr[0]
+        out = net(x)
+        outs = out if isinstance(out, list) else [out]
+        loss = torch.stack([torch.nn.L1Loss()(o, y) for o in outs]).mean()
+        net.zero_grad()
+        loss.backward()
+        fx = {"cls": cls, "kwargs": kw, "input": x, "target": y,
+              "state_dict": None if big else {k: v.detach().clone() for k, v in net.state_dict().items()},
+              "state_seed": 2000 + len(name) if big else None,
+              "state_shapes": {k: tuple(v.shape) for k, v in net.state_dict().items()},
+              "outputs": [o.detach().clone() for o in outs], "loss_l1": loss.detach().clone(),
+              "grads": None if big else {k: p.grad.detach().clone() for k, p in net.named_parameters()},
+              "grad_digest": {k: grad_digest(p.grad.detach()) for k, p in net.named_parameters()} if big else None}
+        path = os.path.join(OUT, name + ".pt")
+        torch.save(fx, path)
+        print(name, os.path.getsize(path) // 1024, "KiB", "loss", float(loss))
+
     # losses / metrics known-answer vectors from the reference classes
     g = torch.Generator().manual_seed(7)
     a = torch.randn(3, 1, 40, 36, generator=g)

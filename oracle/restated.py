@@ -100,6 +100,23 @@ def drfnet_forward(inputs, sd, upscale):
     return outputs
 
 
+def srfbnet_forward(x, sd, upscale, num_steps):
+    """SRFBNet.forward — srfb_net.py:38-50 (lrf_block = _InBlock layout, _RBlock :137-151)."""
+    k, s, pad = PROJ[upscale]
+    outputs, hidden = [], None
+    for i in range(num_steps):
+        feats = in_block(x, sd, p="lrf_block")                                       # :41
+        if i == 0:
+            hidden = feats                                                           # :42-43
+        feats = f_block(feats, hidden, sd, upscale)                                  # :44
+        hidden = feats                                                               # :45
+        r = _prelu(_deconv(feats, sd, "r_block.deconv1", stride=s, padding=pad), sd, "r_block.prelu1")
+        r = _conv(r, sd, "r_block.conv2", padding=1)                                 # :46
+        up = F.interpolate(x, scale_factor=upscale, mode="bilinear", align_corners=False)   # :47
+        outputs.append(up + r)                                                       # :48
+    return outputs
+
+
 # ---- losses -----------------------------------------------------------------------------
 def l1_loss(o, t):          # torch.nn.L1Loss resolved by name, main.py:60-63
     return (o - t).abs().mean()
@@ -175,3 +192,19 @@ def vsr_metrics(outputs, targets, dataset="acdc"):
     t = [denormalize(x, dataset) for x in targets]
     return (torch.stack([psnr(a, b) for a, b in zip(o, t)]).mean(),
             torch.stack([ssim(a, b) for a, b in zip(o, t)]).mean())
+
+
+def edsrnet_forward(x, sd, upscale, res_scale=0.1):
+    """EDSRNet.forward — edsr_net.py:34-38 with _ResBlock :41-53 and _UpBlock :56-67."""
+    head = _conv(x, sd, "head.0", padding=1)                                        # :35
+    y, b = head, 0
+    while f"body.{b}.body.conv1.weight" in sd:
+        t = _conv(torch.relu(_conv(y, sd, f"body.{b}.body.conv1", padding=1)), sd, f"body.{b}.body.conv2", padding=1)
+        y = t * res_scale + y                                                        # :50-52
+        b += 1
+    y = _conv(y, sd, "body.conv", padding=1) + head                                 # :36
+    i = 1
+    while f"tail.0.conv{i}.weight" in sd:
+        y = F.pixel_shuffle(_conv(y, sd, f"tail.0.conv{i}", padding=1), 3 if upscale == 3 else 2)   # :60-65
+        i += 1
+    return _conv(y, sd, "tail.conv", padding=1)                                     # :32,37

@@ -339,3 +339,7 @@ class EmuOps:
     def adam_flat_dev(self, p, g, m, v, hyper):
         lr, b1, b2, eps, wd, step, gs = [float(x) for x in hyper.tolist()]
         self.adam_flat(p, g, m, v, lr, b1, b2, eps, wd, int(round(step)), gs)
+
+    def scale_(self, x, alpha):
+        x.mul_(alpha)
+        self.launches += 1

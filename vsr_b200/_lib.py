@@ -87,6 +87,7 @@ _SIGS = {
                                 C.c_void_p]),
     "vsr_adam_flat_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                     C.c_void_p]),
+    "vsr_scale": (C.c_int, [C.c_void_p, C.c_int64, C.c_float, C.c_void_p]),
     "vsr_cast": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p]),
 }
 

@@ -199,6 +199,10 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+__global__ void scale_kernel(float* __restrict__ x, long n, float alpha) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) x[i] *= alpha;
+}
+
 __global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                 float* __restrict__ v, long n, const float* __restrict__ hyper) {
   const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4], step = hyper[5],
@@ -391,5 +395,13 @@ extern "C" int vsr_adam_flat_dev(float* p, const float* g, float* m, float* v, i
   if (n == 0) return VSR_OK;
   adam_dev_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, v, n, hyper);
   VSR_CHECK_LAUNCH("vsr_adam_flat_dev");
+  return VSR_OK;
+}
+
+extern "C" int vsr_scale(float* x, int64_t n, float alpha, void* stream) {
+  VSR_CHECK_ARG(x && n >= 0, "vsr_scale: bad arguments");
+  if (n == 0) return VSR_OK;
+  scale_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n, alpha);
+  VSR_CHECK_LAUNCH("vsr_scale");
   return VSR_OK;
 }

@@ -97,9 +97,9 @@ class DrfEngine:
             S = _Frame()
             S.x = x
             S.a1 = self._new(N, h, w, 4 * F)
-            ops.conv3x3_first(x, self._pview(self.flat, "in_block.conv1.weight"),
-                              self._pview(self.flat, "in_block.conv1.bias"),
-                              self._slope(P.params["in_block.prelu1.weight"]), S.a1)
+            ops.conv3x3_first(x, self._pview(self.flat, f"{P.in_name}.conv1.weight"),
+                              self._pview(self.flat, f"{P.in_name}.conv1.bias"),
+                              self._slope(P.params[f"{P.in_name}.prelu1.weight"]), S.a1)
             S.inn = self._new(N, h, w, F)
             self._fwd("in2", [S.a1], S.inn)
             S.hidden = S.inn if t == 0 else prev_f                      # drf_net.py:42-43
@@ -123,17 +123,33 @@ class DrfEngine:
                     src = S.d[g]
                 S.lr.append(self._new(N, h, w, F))
                 self._fwd(f"dn{g}_sc", [src], S.lr[g + 1])
-            S.f, S.feat = self._new(N, h, w, F), self._new(N, h, w, F)
-            self._fwd("fout", S.lr[1:], S.f, extra=EPI_OUT2, out2=S.feat, res2=S.inn)   # :46 global skip
-            S.s = [S.feat]
-            for lv in range(P.out_levels):
-                L = P.fwd[f"out{lv + 1}"]
-                nxt = self._new(N, h, w, L.out_c)
-                self._fwd(L.name, [S.s[-1]], nxt)
-                S.s.append(nxt)
-            y = self._new(N, P.cout, h * r, w * r, dtype=self.param_dtype)
-            ops.conv3x3_last(S.s[-1], r, F, P.phases, self._pview(self.flat, P.last_name + ".weight"),
-                             self._pview(self.flat, P.last_name + ".bias"), y)
+            if P.variant == "srfb":
+                # srfb_net.py:44-48: residual = r_block(f);  output = bilinear(input) + residual
+                S.f = self._new(N, h, w, F)
+                S.feat = None
+                self._fwd("fout", S.lr[1:], S.f)
+                hr_out = self._new(N, h, w, r2 * F)
+                self._fwd("rdc", [S.f], hr_out)
+                S.s = [hr_out]
+                res = self._new(N, P.cout, h * r, w * r, dtype=self.param_dtype)
+                ops.conv3x3_last(hr_out, r, F, P.phases, self._pview(self.flat, P.last_name + ".weight"),
+                                 self._pview(self.flat, P.last_name + ".bias"), res)
+                up = self._new(N, P.cin, h * r, w * r, dtype=self.param_dtype)
+                ops.upsample_linear(x, up, False)
+                y = self._new(N, P.cout, h * r, w * r, dtype=self.param_dtype)
+                ops.add(up, res, y)
+            else:
+                S.f, S.feat = self._new(N, h, w, F), self._new(N, h, w, F)
+                self._fwd("fout", S.lr[1:], S.f, extra=EPI_OUT2, out2=S.feat, res2=S.inn)   # :46 global skip
+                S.s = [S.feat]
+                for lv in range(P.out_levels):
+                    L = P.fwd[f"out{lv + 1}"]
+                    nxt = self._new(N, h, w, L.out_c)
+                    self._fwd(L.name, [S.s[-1]], nxt)
+                    S.s.append(nxt)
+                y = self._new(N, P.cout, h * r, w * r, dtype=self.param_dtype)
+                ops.conv3x3_last(S.s[-1], r, F, P.phases, self._pview(self.flat, P.last_name + ".weight"),
+                                 self._pview(self.flat, P.last_name + ".bias"), y)
             outs.append(y)
             prev_f = S.f
             if save:
@@ -209,6 +225,12 @@ class DrfEngine:
                 d_prev = new(S.s[lv].shape[-1])
                 dgrad(lname, [d_s], d_prev)
                 d_s = d_prev
+            if P.variant == "srfb":
+                dz_r = new(r2 * F)
+                act_bwd(d_s, S.s[0], dz_r, P.fwd["rdc"].slope)       # r_block.prelu1
+                wgrad("rdc", [S.f], dz_r)
+                d_s = new()
+                dgrad("rdc", [dz_r], d_s)
             d_feat = d_s
             # ---- feedback block output (+ hidden-state gradient of frame t+1: BPTT) ----
             dz_f = new()
@@ -262,17 +284,18 @@ class DrfEngine:
             wgrad("fin", [S.inn, S.hidden], dz_lr0)
             dz_in = new()
             in2 = P.fwd["in2"]
+            skip = d_feat if P.variant == "drf" else None      # the feature skip exists in DRFNet only
             if t == 0:   # hidden == in_features at the first frame (drf_net.py:42-43)
-                dgrad("fin_in0", [dz_lr0, dz_lr0], dz_in, aux=S.inn, slope_ref=in2.slope, residual=d_feat)
+                dgrad("fin_in0", [dz_lr0, dz_lr0], dz_in, aux=S.inn, slope_ref=in2.slope, residual=skip)
             else:
-                dgrad("fin_in", [dz_lr0], dz_in, aux=S.inn, slope_ref=in2.slope, residual=d_feat)
+                dgrad("fin_in", [dz_lr0], dz_in, aux=S.inn, slope_ref=in2.slope, residual=skip)
             # ---- input block ----
             wgrad("in2", [S.a1], dz_in)
             dz_a1 = new(4 * F)
-            dgrad("in2", [dz_in], dz_a1, aux=S.a1, slope_ref=P.params["in_block.prelu1.weight"])
+            dgrad("in2", [dz_in], dz_a1, aux=S.a1, slope_ref=P.params[f"{P.in_name}.prelu1.weight"])
             ws = self._workspace("first", ops.conv3x3_first_bwd_workspace(S.x, 4 * F))
-            ops.conv3x3_first_bwd(S.x, dz_a1, self._pview(gflat, "in_block.conv1.weight"),
-                                  self._pview(gflat, "in_block.conv1.bias"), True, ws)
+            ops.conv3x3_first_bwd(S.x, dz_a1, self._pview(gflat, f"{P.in_name}.conv1.weight"),
+                                  self._pview(gflat, f"{P.in_name}.conv1.bias"), True, ws)
             next_dz_lr0 = dz_lr0
         # ---- un-pack: weights, biases, PReLU slopes ----
         for lo, idx in self.unpack:

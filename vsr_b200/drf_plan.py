@@ -86,7 +86,13 @@ def _split_nt(total: int) -> List[Tuple[int, int]]:
 
 
 class DrfPlan:
-    def __init__(self, in_channels, out_channels, F, G, r, bf16):
+    """variant 'drf': DRFNet / DRFSISRNet (drf_net.py); 'srfb': SRFBNet (srfb_net.py:38-50,137-151) — the
+    same feedback block, input block named `lrf_block`, reconstruction block `r_block` = transposed
+    conv + PReLU + 3x3 conv, no feature skip (the global skip is the bilinear up-sampled input)."""
+
+    def __init__(self, in_channels, out_channels, F, G, r, bf16, variant="drf"):
+        self.variant = variant
+        self.in_name = "in_block" if variant == "drf" else "lrf_block"
         if r not in PROJ:
             raise ValueError(f"The upscale factor should be 2, 3, 4 or 8. Got {r}.")
         if G + 1 > 8:
@@ -115,8 +121,8 @@ class DrfPlan:
         conv = lambda p, o, i, ks: (self._add_param(p + ".weight", (o, i, ks, ks)), self._add_param(p + ".bias", (o,)))
         dconv = conv  # ConvTranspose2d weight is [Cin, Cout, k, k] — same rank, roles swapped
         prelu = lambda p: self._add_param(p + ".weight", (1,))
-        conv("in_block.conv1", 4 * F, self.cin, 3); prelu("in_block.prelu1")
-        conv("in_block.conv2", F, 4 * F, 1); prelu("in_block.prelu2")
+        conv(f"{self.in_name}.conv1", 4 * F, self.cin, 3); prelu(f"{self.in_name}.prelu1")
+        conv(f"{self.in_name}.conv2", F, 4 * F, 1); prelu(f"{self.in_name}.prelu2")
         conv("f_block.in_block.conv", F, 2 * F, 1); prelu("f_block.in_block.prelu")
         for g in range(G):                      # nn.ModuleList up_blocks first (drf_net.py:68,79-95)
             if g == 0:
@@ -131,7 +137,11 @@ class DrfPlan:
                 conv(f"f_block.down_blocks.{g}.conv1", F, F * (g + 1), 1); prelu(f"f_block.down_blocks.{g}.prelu1")
                 conv(f"f_block.down_blocks.{g}.conv2", F, F, k); prelu(f"f_block.down_blocks.{g}.prelu2")
         conv("f_block.out_block.conv", F, F * G, 1); prelu("f_block.out_block.prelu")
-        if self.r == 3:
+        if self.variant == "srfb":
+            dconv("r_block.deconv1", F, F, k); prelu("r_block.prelu1")
+            conv("r_block.conv2", self.cout, F, 3)
+            self.out_levels, self.last_name = 0, "r_block.conv2"
+        elif self.r == 3:
             conv("out_block.conv1", 9 * F, F, 3); conv("out_block.conv2", self.cout, F, 3)
             self.out_levels, self.last_name = 1, "out_block.conv2"
         else:
@@ -315,8 +325,8 @@ class DrfPlan:
     def _build_layers(self):
         F, G, P = self.F, self.G, self.params
         # in_block.conv1 is the dedicated first-layer kernel (K = 9*Cin).
-        self._conv1x1_cat("in2", "in_block.conv2", 1, src_c=4 * F, slope=P["in_block.prelu2.weight"])
-        self._dgrad1x1("in2", [("in_block.conv2", 0)], out_c=4 * F)   # dz_in -> d(a1)
+        self._conv1x1_cat("in2", f"{self.in_name}.conv2", 1, src_c=4 * F, slope=P[f"{self.in_name}.prelu2.weight"])
+        self._dgrad1x1("in2", [(f"{self.in_name}.conv2", 0)], out_c=4 * F)   # dz_in -> d(a1)
         self._conv1x1_cat("fin", "f_block.in_block.conv", 2, slope=P["f_block.in_block.prelu.weight"])
         # d(in) from the first concat operand (+ second operand at t == 0 where hidden == in)
         self._dgrad1x1("fin_in", [("f_block.in_block.conv", 0)])
@@ -355,7 +365,12 @@ class DrfPlan:
             cons = [(f"f_block.down_blocks.{g}.conv1", j * F) for g in range(max(j, 1), G)]
             if cons:
                 self._dgrad1x1(f"hr{j}", cons)
-        if self.r == 3:
+        if self.variant == "srfb":
+            WT = self._W("r_block.deconv1")
+            self._up_form("rdc", lambda a, b, ky, kx, WT=WT: WT.idx(a, b, ky, kx), self.fwd,
+                          slope=P["r_block.prelu1.weight"], bias_name="r_block.deconv1")
+            self._down_form("rdc", lambda a, b, ky, kx, WT=WT: WT.idx(a, b, ky, kx), self.bwd)
+        elif self.r == 3:
             self._out_level(0, "out_block.conv1")
         else:
             for lv in range(self.out_levels):

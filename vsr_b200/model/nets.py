@@ -1,1 +1,2 @@
-from ..nets import BaseNet, DRFNet, DRFSISRNet  # noqa: F401
+from ..nets import BaseNet, DRFNet, DRFSISRNet, SRFBNet  # noqa: F401
+from ..edsr import EDSRNet  # noqa: F401

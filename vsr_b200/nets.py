@@ -114,6 +114,8 @@ class _DRFFunction(torch.autograd.Function):
 
 
 class _DRFBase(BaseNet):
+    _variant = "drf"
+
     def _setup(self, in_channels, out_channels, num_features, num_groups, upscale_factor, precision):
         if upscale_factor not in [2, 3, 4, 8]:
             raise ValueError(f"The upscale factor should be 2, 3, 4 or 8. Got {upscale_factor}.")
@@ -123,12 +125,20 @@ class _DRFBase(BaseNet):
         self.num_features, self.num_groups = num_features, num_groups
         self.upscale_factor, self.precision = upscale_factor, precision
         F = num_features
-        self.in_block = _seq(conv1=nn.Conv2d(in_channels, 4 * F, 3, padding=1), prelu1=_prelu(),
-                             conv2=nn.Conv2d(4 * F, F, 1), prelu2=_prelu())
-        self.f_block = _FBlockParams(F, num_groups, upscale_factor)
-        self.out_block = _out_block(F, out_channels, upscale_factor)
+        first = _seq(conv1=nn.Conv2d(in_channels, 4 * F, 3, padding=1), prelu1=_prelu(),
+                     conv2=nn.Conv2d(4 * F, F, 1), prelu2=_prelu())
+        if self._variant == "drf":
+            self.in_block = first
+            self.f_block = _FBlockParams(F, num_groups, upscale_factor)
+            self.out_block = _out_block(F, out_channels, upscale_factor)
+        else:                       # SRFBNet naming (srfb_net.py:34-36,137-151)
+            k, s_, p_ = PROJ[upscale_factor]
+            self.lrf_block = first
+            self.f_block = _FBlockParams(F, num_groups, upscale_factor)
+            self.r_block = _seq(deconv1=nn.ConvTranspose2d(F, F, k, s_, p_), prelu1=_prelu(),
+                                conv2=nn.Conv2d(F, out_channels, 3, padding=1))
         self._plan = DrfPlan(in_channels, out_channels, F, num_groups, upscale_factor,
-                             bf16=(precision == "bf16"))
+                             bf16=(precision == "bf16"), variant=self._variant)
         names = [n for n, _ in self.named_parameters()]
         assert names == list(self._plan.params), "parameter order differs from the plan"
         self._engine = None
@@ -218,6 +228,24 @@ class DRFSISRNet(_DRFBase):
                  precision="fp32"):
         super().__init__()
         self.num_steps = num_steps
+        self._setup(in_channels, out_channels, num_features, num_groups, upscale_factor, precision)
+
+    def forward(self, input):
+        return self._run([input] * self.num_steps)
+
+
+class SRFBNet(_DRFBase):
+    """Super-Resolution FeedBack Network (reference: srfb_net.py:8-50): `num_steps` iterations of the
+    feedback block on one image; each step's output = bilinear(input) + r_block(features).
+    forward(tensor [N,C,h,w]) -> list of num_steps tensors [N,C,r*h,r*w]."""
+    _variant = "srfb"
+
+    def __init__(self, in_channels, out_channels, num_steps, num_features, num_groups, upscale_factor,
+                 precision="fp32"):
+        super().__init__()
+        self.num_steps = num_steps
+        if in_channels != out_channels:
+            raise ValueError("SRFBNet adds the up-sampled input to the output: in_channels must equal out_channels")
         self._setup(in_channels, out_channels, num_features, num_groups, upscale_factor, precision)
 
     def forward(self, input):

@@ -312,6 +312,11 @@ class CudaOps:
                                      weight_decay, step, grad_scale, _stream()), "vsr_adam_flat")
         self.launches += 1
 
+    def scale_(self, x, alpha):
+        _need_cuda(x)
+        check(self.lib.vsr_scale(_p(x), x.numel(), float(alpha), _stream()), "vsr_scale")
+        self.launches += 1
+
     def adam_flat_dev(self, p, g, m, v, hyper):
         _need_cuda(p, g, m, v, hyper)
         check(self.lib.vsr_adam_flat_dev(_p(p), _p(g), _p(m), _p(v), p.numel(), _p(hyper), _stream()),
