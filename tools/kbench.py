@@ -65,6 +65,79 @@ def tapgemm_case(name, tab, n, h, w, src_cs, out_c, dtype, iters, flush, results
     print(json.dumps(r), flush=True)
 
 
+def bw_case(name, fn, nbytes, iters, flush, results):
+    ms = timed(fn, iters, flush)
+    r = {"kernel": name, "ms": ms, "gbs": nbytes / ms / 1e6, "bytes": nbytes, "frac_hbm": nbytes / ms / 1e6 / PEAKS["hbm_gbs"]}
+    results.append(r)
+    print(json.dumps(r), flush=True)
+
+
+def bandwidth_cases(iters, flush, results):
+    """HBM-bound kernels at BASELINE config-2/3 sizes; bytes = algorithmic bytes."""
+    from vsr_b200.drf_plan import phase_table
+    ops = cuda_ops()
+    dev = "cuda"
+    n, H, W = 32 * 5, 128, 128                      # all T=5 frames of a config-2 batch in one call
+    a, b = torch.randn(n, 1, H, W, device=dev), torch.randn(n, 1, H, W, device=dev)
+    numel = a.numel()
+    part = torch.zeros(ops.partials_len, device=dev)
+    grad = torch.empty_like(a)
+    for kind, nm in ((0, "l1"), (1, "mse"), (2, "charbonnier"), (3, "huber")):
+        bw_case(f"loss_{nm}_fwd_bwd", lambda k=kind: ops.loss_fwd_bwd(a, b, k, 0.5, 1.0 / numel, part, grad), 12 * numel, iters, flush, results)
+    ws = torch.empty(ops.metric_workspace(n, H * W) // 4 + 4, device=dev)
+    out = torch.empty(n, device=dev)
+    bw_case("psnr_denorm", lambda: ops.psnr(a, b, 54.089, 48.084, 255.0, out, ws), 8 * numel, iters, flush, results)
+    win = torch.ones(11, device=dev) / 11
+    bw_case("ssim_denorm", lambda: ops.ssim(a.view(n, H, W), b.view(n, H, W), win, 54.089, 48.084, 6.5, 58.5, out, ws), 8 * numel, iters, flush, results)
+    # DSB15-shaped frame batch (config 3): 12 x 256 x 256
+    a3, b3 = torch.randn(12 * 30, 1, 256, 256, device=dev), torch.randn(12 * 30, 1, 256, 256, device=dev)
+    ws3 = torch.empty(ops.metric_workspace(360, 65536) // 4 + 4, device=dev)
+    out3 = torch.empty(360, device=dev)
+    bw_case("psnr_denorm_dsb15", lambda: ops.psnr(a3, b3, 51.193, 52.671, 255.0, out3, ws3), 8 * a3.numel(), iters, flush, results)
+    bw_case("ssim_denorm_dsb15", lambda: ops.ssim(a3.view(360, 256, 256), b3.view(360, 256, 256), win, 51.193, 52.671, 6.5, 58.5, out3, ws3), 8 * a3.numel(), iters, flush, results)
+    # pixel shuffle / upsample (standalone kernels of the sweep)
+    x = torch.randn(32, 256, 64, 64, device=dev)
+    y = torch.empty(32, 64, 128, 128, device=dev)
+    bw_case("pixel_shuffle_r2", lambda: ops.pixel_shuffle(x, y, 2), 8 * x.numel(), iters, flush, results)
+    bw_case("pixel_unshuffle_r2", lambda: ops.pixel_shuffle(y, x, 2, inverse=True), 8 * x.numel(), iters, flush, results)
+    xi = torch.randn(32, 64, 64, 64, device=dev)
+    yo = torch.empty(32, 64, 256, 256, device=dev)
+    bw_case("bilinear_x4", lambda: ops.upsample_linear(xi, yo, False), 4 * (xi.numel() + yo.numel()), iters, flush, results)
+    bw_case("bilinear_x4_bwd", lambda: ops.upsample_linear_bwd(yo, xi, False), 4 * (xi.numel() + yo.numel()), iters, flush, results)
+    x3 = torch.randn(4, 32, 16, 64, 64, device=dev)
+    y3 = torch.empty(4, 32, 32, 128, 128, device=dev)
+    bw_case("trilinear_x2", lambda: ops.upsample_linear(x3, y3, False), 4 * (x3.numel() + y3.numel()), iters, flush, results)
+    bw_case("trilinear_x2_bwd", lambda: ops.upsample_linear_bwd(y3, x3, False), 4 * (x3.numel() + y3.numel()), iters, flush, results)
+    # Adam over a DRFNet-L sized and a large bucket
+    for P in (3658907, 64 * 1024 * 1024):
+        p_, g_, m_, v_ = (torch.randn(P, device=dev) for _ in range(4))
+        v_.abs_()
+        bw_case(f"adam_flat_{P}", lambda: ops.adam_flat(p_, g_, m_, v_, 1e-4, 0.9, 0.999, 1e-8, 0.0, 3), 28 * P, iters, flush, results)
+    # boundary convolutions
+    xin = torch.randn(32, 1, 32, 32, device=dev)
+    w1, b1 = torch.randn(256, 1, 3, 3, device=dev), torch.randn(256, device=dev)
+    sl = torch.tensor([0.2], device=dev)
+    a1 = torch.empty(32, 32, 32, 256, device=dev, dtype=torch.bfloat16)
+    bw_case("conv3x3_first_bf16", lambda: ops.conv3x3_first(xin, w1, b1, sl, a1), 2 * a1.numel() + 4 * xin.numel(), iters, flush, results)
+    hr = torch.randn(32, 32, 32, 1024, device=dev).to(torch.bfloat16)
+    wl, bl = torch.randn(1, 64, 3, 3, device=dev) * 0.1, torch.randn(1, device=dev)
+    yl = torch.empty(32, 1, 128, 128, device=dev)
+    ph = phase_table(4)
+    bw_case("conv3x3_last_bf16", lambda: ops.conv3x3_last(hr, 4, 64, ph, wl, bl, yl), 2 * hr.numel() + 4 * yl.numel(), iters, flush, results)
+    dyl, dxl = torch.randn_like(yl), torch.empty_like(hr)
+    dwl, dbl = torch.zeros_like(wl), torch.zeros_like(bl)
+    wsl = torch.empty(ops.conv3x3_last_bwd_workspace(hr, 4, 64, 1) // 4 + 4, device=dev)
+    bw_case("conv3x3_last_bwd_bf16", lambda: ops.conv3x3_last_bwd(hr, 4, 64, ph, wl, dyl, dxl, dwl, dbl, False, wsl), 4 * hr.numel() + 4 * yl.numel(), iters, flush, results)
+    z = torch.randn(524288, 64, device=dev).to(torch.bfloat16)
+    dbz = torch.zeros(64, device=dev)
+    wsz = torch.empty(ops.colsum_workspace(524288, 64) // 4 + 4, device=dev)
+    bw_case("colsum_hr_bf16", lambda: ops.colsum(z, 524288, 64, dbz, False, wsz), 2 * z.numel(), iters, flush, results)
+    z2 = torch.empty_like(z)
+    pr = torch.zeros(ops.partials_len, device=dev)
+    bw_case("prelu_bwd_hr_bf16", lambda: ops.act_bwd(z, z, z2, sl, pr), 6 * z.numel(), iters, flush, results)
+    bw_case("add_hr_bf16", lambda: ops.add(z, z, z2), 6 * z.numel(), iters, flush, results)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=20)
@@ -107,6 +180,8 @@ def main():
         t33 = [(0, dy, dx, 0) for dy in (-1, 0, 1) for dx in (-1, 0, 1)]
         tapgemm_case("conv3x3_n256_lr", TapTable(64, 256, [(0, t33)]), N, h, w, [F], 4 * F, dt, args.iters, flush, results)
         tapgemm_case("conv3x3_n256_2x", TapTable(64, 256, [(0, t33)]), N, 2 * h, 2 * w, [F], 4 * F, dt, args.iters, flush, results)
+    if not args.cases or "bw" in args.cases:
+        bandwidth_cases(args.iters, flush, results)
     if args.json:
         with open(args.json, "w") as f:
             json.dump(results, f, indent=1)

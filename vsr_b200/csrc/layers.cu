@@ -130,6 +130,143 @@ __global__ void conv_first_bwd_final_kernel(const float* __restrict__ ws, int bl
 }
 
 // ------------------------------------------------------------------------------------------
+// first conv, v2 (cin == 1, cout <= 256): a lane owns 8 output channels and keeps their 72 weights
+// and 8 biases in registers; a warp = one pixel at a time (9 broadcast loads, one 16/32-byte
+// store per lane -> 512 contiguous bytes per warp).
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) conv_first2_kernel(const float* __restrict__ x, int n, int h, int w,
+                                                         const float* __restrict__ wt, const float* __restrict__ bias,
+                                                         const float* __restrict__ slope_p, T* __restrict__ y, int cout) {
+  __shared__ float sw2[256 * 9 + 256];
+  for (int i = threadIdx.x; i < cout * 9; i += blockDim.x) sw2[i] = wt[i];
+  for (int i = threadIdx.x; i < cout; i += blockDim.x) sw2[256 * 9 + i] = bias ? bias[i] : 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int groups = cout >> 3;
+  const bool live = lane < groups;
+  float wr[8][9], br[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    br[j] = live ? sw2[256 * 9 + lane * 8 + j] : 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wr[j][t] = live ? sw2[(lane * 8 + j) * 9 + t] : 0.f;
+  }
+  const float a = slope_p ? __ldg(slope_p) : 1.f;
+  const long total = (long)n * h * w;
+  const long warp0 = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+  for (long pix = warp0; pix < total; pix += nwarps) {
+    const int px = (int)(pix % w);
+    const long q = pix / w;
+    const int py = (int)(q % h);
+    const float* xp = x + (q / h) * (size_t)h * w;
+    float v[9];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int yy = py + ky - 1, xx = px + kx - 1;
+        const bool ok = yy >= 0 && yy < h && xx >= 0 && xx < w;
+        const float t = __ldg(xp + (size_t)min(max(yy, 0), h - 1) * w + min(max(xx, 0), w - 1));
+        v[ky * 3 + kx] = ok ? t : 0.f;
+      }
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float s = br[j];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) s = fmaf(v[t], wr[j][t], s);
+      acc[j] = s > 0.f ? s : a * s;
+    }
+    if (live) {
+      T* yp = y + pix * cout + lane * 8;
+      if constexpr (sizeof(T) == 2) {
+        uint4 o;
+        o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
+        o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
+        *reinterpret_cast<uint4*>(yp) = o;
+      } else {
+        reinterpret_cast<float4*>(yp)[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        reinterpret_cast<float4*>(yp)[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      }
+    }
+  }
+}
+
+// first conv backward, v2 (cin == 1): block = 64 pixels, 4 pixel-lanes x 256 channel threads
+// (1024 threads); thread accumulates dw[co][9], db[co] over its 16 pixels, fixed-order smem fold
+// over the 4 pixel-lanes -> ws[block][cout][10]; parallel fixed-order final reduce.
+constexpr int kF2Pix = 64;
+template <typename T>
+__global__ void __launch_bounds__(1024) conv_first2_bwd_kernel(const float* __restrict__ x, int n, int h, int w,
+                                                              const T* __restrict__ dz, int cout, float* __restrict__ ws) {
+  __shared__ float xs[kF2Pix][9];
+  __shared__ float part[4][256][10];
+  const long total = (long)n * h * w;
+  const long p0 = (long)blockIdx.x * kF2Pix;
+  for (int i = threadIdx.x; i < kF2Pix * 9; i += blockDim.x) {
+    const int pl = i / 9, t = i % 9;
+    const long p = p0 + pl;
+    float v = 0.f;
+    if (p < total) {
+      const int px = (int)(p % w);
+      const long q = p / w;
+      const int py = (int)(q % h);
+      const int yy = py + t / 3 - 1, xx = px + t % 3 - 1;
+      if (yy >= 0 && yy < h && xx >= 0 && xx < w) v = __ldg(x + (q / h) * (size_t)h * w + (size_t)yy * w + xx);
+    }
+    xs[pl][t] = v;
+  }
+  __syncthreads();
+  const int co = threadIdx.x & 255, pl4 = threadIdx.x >> 8;
+  float acc[10];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) acc[i] = 0.f;
+  if (co < cout) {
+    float g[kF2Pix / 4];
+#pragma unroll
+    for (int i = 0; i < kF2Pix / 4; ++i) {
+      const long p = p0 + pl4 * (kF2Pix / 4) + i;
+      g[i] = p < total ? Elem<T>::ld(dz + p * cout + co) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < kF2Pix / 4; ++i) {
+      const int pl = pl4 * (kF2Pix / 4) + i;
+      acc[9] += g[i];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) acc[t] = fmaf(g[i], xs[pl][t], acc[t]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 10; ++i) part[pl4][co][i] = acc[i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < cout * 10; i += blockDim.x) {
+    const int c = i / 10, r = i % 10;
+    ws[(size_t)blockIdx.x * cout * 10 + i] = ((part[0][c][r] + part[1][c][r]) + part[2][c][r]) + part[3][c][r];
+  }
+}
+// out[i] (+)= sum_b ws[b][i], i < n: 256-thread blocks, 64 outputs x 4 block-lanes, fixed order
+__global__ void __launch_bounds__(256) rows_reduce_kernel(const float* __restrict__ ws, int blocks, int n,
+                                                         float* __restrict__ dw, float* __restrict__ db, int cout,
+                                                         int accumulate) {
+  __shared__ float sm[4][64];
+  const int col = threadIdx.x & 63, part = threadIdx.x >> 6;
+  const int i = blockIdx.x * 64 + col;
+  float s = 0.f;
+  if (i < n)
+    for (int b = part; b < blocks; b += 4) s += ws[(size_t)b * n + i];
+  sm[part][col] = s;
+  __syncthreads();
+  if (part == 0 && i < n) {
+    const float t = ((sm[0][col] + sm[1][col]) + sm[2][col]) + sm[3][col];
+    const int c = i / 10, r = i % 10;
+    float* dst = (r == 9) ? (db + c) : (dw + (size_t)c * 9 + r);
+    *dst = accumulate ? *dst + t : t;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // last conv: one warp = one high-resolution output pixel; lanes stride the C channels.
 // x is phase-blocked [n][h][w][r*r][C]; slot_of[py*r+px] gives the phase slot.
 // ------------------------------------------------------------------------------------------
@@ -399,6 +536,7 @@ __device__ __forceinline__ float transpose_reduce16(float (&v)[16], int lane) {
 
 struct SubBlock {
   int ni, Y0, X0;   // top-left HR pixel of the sub-block
+  int by, bx;       // its LR block
 };
 __device__ __forceinline__ SubBlock decode_sb(const LastGeom2& g, long item) {
   SubBlock b;
@@ -409,6 +547,8 @@ __device__ __forceinline__ SubBlock decode_sb(const LastGeom2& g, long item) {
   b.ni = (int)(item / g.h);
   b.Y0 = y * g.r + sy * g.sb;
   b.X0 = x * g.r + sx * g.sb;
+  b.by = y;
+  b.bx = x;
   return b;
 }
 template <typename T>
@@ -427,18 +567,24 @@ struct HaloIdx {
   uint32_t rowok, colok;        // validity bit masks
 };
 __device__ __forceinline__ void halo_index(const LastGeom2& g, const SubBlock& b, HaloIdx* hi) {
+  // the sub-block lies inside one LR block: a halo coordinate is at most one block away, so the
+  // (block, phase) split needs comparisons only
   const int H = g.h * g.r, W = g.w * g.r, r2 = g.r * g.r, HT = g.sb + 2;
+  const int y = b.by, x = b.bx, ly0 = b.Y0 - b.by * g.r, lx0 = b.X0 - b.bx * g.r;
   hi->rowok = hi->colok = 0;
 #pragma unroll
   for (int i = 0; i < kSBMax + 2; ++i) {
     const int Y = b.Y0 + i - 1, X = b.X0 + i - 1;
     const bool yo = i < HT && Y >= 0 && Y < H, xo = i < HT && X >= 0 && X < W;
-    const int Yc = min(max(Y, 0), H - 1), Xc = min(max(X, 0), W - 1);
-    const int y = Yc / g.r, x = Xc / g.r;
-    hi->rowbase[i] = ((size_t)b.ni * g.h + y) * g.w * r2;
-    hi->rowphase[i] = (Yc - y * g.r) * g.r;
-    hi->colbase[i] = x * r2;
-    hi->colphase[i] = Xc - x * g.r;
+    int ly = ly0 + i - 1, yy = y, lx = lx0 + i - 1, xx = x;
+    if (ly < 0) { ly += g.r; --yy; } else if (ly >= g.r) { ly -= g.r; ++yy; }
+    if (lx < 0) { lx += g.r; --xx; } else if (lx >= g.r) { lx -= g.r; ++xx; }
+    yy = min(max(yy, 0), g.h - 1);
+    xx = min(max(xx, 0), g.w - 1);
+    hi->rowbase[i] = ((size_t)b.ni * g.h + yy) * g.w * r2;
+    hi->rowphase[i] = ly * g.r;
+    hi->colbase[i] = xx * r2;
+    hi->colphase[i] = lx;
     hi->rowok |= (yo ? 1u : 0u) << i;
     hi->colok |= (xo ? 1u : 0u) << i;
   }
@@ -447,15 +593,29 @@ __device__ __forceinline__ size_t halo_off(const LastGeom2& g, const HaloIdx& hi
   return (hi.rowbase[i] + hi.colbase[j] + g.slot_of[hi.rowphase[i] + hi.colphase[j]]) * (size_t)g.c;
 }
 
+// rolling 3-row window over the sub-block's halo: row i of the halo for channel block c0
 template <typename T, int CPL>
-__global__ void __launch_bounds__(256) conv_last2_kernel(const T* __restrict__ x, const __grid_constant__ LastGeom2 g,
-                                                        const float* __restrict__ wt, const float* __restrict__ bias,
-                                                        float* __restrict__ y) {
+__device__ __forceinline__ void load_halo_row(const T* __restrict__ x, const LastGeom2& g, const HaloIdx& hi, int i,
+                                              int c0, float (&row)[kSBMax + 2][CPL]) {
+#pragma unroll
+  for (int j = 0; j < kSBMax + 2; ++j) load_cpl<T, CPL>(x + halo_off(g, hi, i, j) + c0, row[j]);
+#pragma unroll
+  for (int j = 0; j < kSBMax + 2; ++j) {
+    const bool ok = ((hi.rowok >> i) & 1u) && ((hi.colok >> j) & 1u);
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) row[j][q] = ok ? row[j][q] : 0.f;
+  }
+}
+
+template <typename T, int CPL>
+__global__ void __launch_bounds__(256, 2) conv_last2_kernel(const T* __restrict__ x, const __grid_constant__ LastGeom2 g,
+                                                           const float* __restrict__ wt, const float* __restrict__ bias,
+                                                           float* __restrict__ y) {
   extern __shared__ float sw[];    // [9][C]
   for (int i = threadIdx.x; i < g.c * 9; i += blockDim.x) sw[(i % 9) * g.c + i / 9] = wt[i];
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  const int H = g.h * g.r, W = g.w * g.r, HT = g.sb + 2;
+  const int H = g.h * g.r, W = g.w * g.r;
   const long total = (long)g.n * g.h * g.w * g.nsb * g.nsb;
   const long warp0 = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
@@ -474,33 +634,24 @@ __global__ void __launch_bounds__(256) conv_last2_kernel(const T* __restrict__ x
       for (int t = 0; t < 9; ++t)
 #pragma unroll
         for (int q = 0; q < CPL; ++q) wr[t][q] = sw[t * g.c + c0 + q];
-      float xv[kHalo][CPL];
+      float rows[3][kSBMax + 2][CPL];
+      load_halo_row<T, CPL>(x, g, hi, 0, c0, rows[0]);
+      load_halo_row<T, CPL>(x, g, hi, 1, c0, rows[1]);
 #pragma unroll
-      for (int i = 0; i < kSBMax + 2; ++i)
-#pragma unroll
-        for (int j = 0; j < kSBMax + 2; ++j)
-          load_cpl<T, CPL>(x + halo_off(g, hi, i, j) + c0, xv[i * (kSBMax + 2) + j]);   // unconditional (clamped)
-#pragma unroll
-      for (int i = 0; i < kSBMax + 2; ++i)
-#pragma unroll
-        for (int j = 0; j < kSBMax + 2; ++j) {
-          const bool ok = ((hi.rowok >> i) & 1u) && ((hi.colok >> j) & 1u);
-#pragma unroll
-          for (int q = 0; q < CPL; ++q) xv[i * (kSBMax + 2) + j][q] = ok ? xv[i * (kSBMax + 2) + j][q] : 0.f;
-        }
-#pragma unroll
-      for (int oy = 0; oy < kSBMax; ++oy)
+      for (int oy = 0; oy < kSBMax; ++oy) {
+        load_halo_row<T, CPL>(x, g, hi, oy + 2, c0, rows[(oy + 2) % 3]);
 #pragma unroll
         for (int ox = 0; ox < kSBMax; ++ox) {
-          float s = acc[oy * kSBMax + ox];
+          float sacc = acc[oy * kSBMax + ox];
 #pragma unroll
           for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
-              for (int q = 0; q < CPL; ++q) s = fmaf(xv[(oy + ky) * (kSBMax + 2) + ox + kx][q], wr[ky * 3 + kx][q], s);
-          acc[oy * kSBMax + ox] = s;
+              for (int q = 0; q < CPL; ++q) sacc = fmaf(rows[(oy + ky) % 3][ox + kx][q], wr[ky * 3 + kx][q], sacc);
+          acc[oy * kSBMax + ox] = sacc;
         }
+      }
     }
     const float tot = transpose_reduce16(acc, lane);
     const int q = lane >> 1, oy = q / kSBMax, ox = q % kSBMax;
@@ -509,19 +660,71 @@ __global__ void __launch_bounds__(256) conv_last2_kernel(const T* __restrict__ x
   }
 }
 
-// backward v2 (cout == 1): per sub-block the warp loads the x halo and the dy halo once;
-//   dx(P,c)   = sum_tap dy(P - off(tap)) * w[c][tap]           (stored, CPL channels per lane)
-//   dw[c][tap] += dy(P) * x(P + off(tap), c),  db += dy(P)       (registers -> block -> ws -> final)
+// backward, part 1 (cout == 1): dx(P,c) = sum_tap dy(P - off(tap)) * w[c][tap]; one warp per sub-block,
+// the dy halo in registers (broadcast loads), CPL channels per lane, coalesced stores.
 template <typename T, int CPL>
-__global__ void __launch_bounds__(256) conv_last2_bwd_kernel(const T* __restrict__ x, const __grid_constant__ LastGeom2 g,
-                                                            const float* __restrict__ wt, const float* __restrict__ dy,
-                                                            T* __restrict__ dx, float* __restrict__ ws) {
-  extern __shared__ float sm[];    // weights [9][C], then block partial [nw][9*C + 1]
-  float* sw = sm;
+__global__ void __launch_bounds__(256, 2) conv_last2_dx_kernel(const __grid_constant__ LastGeom2 g,
+                                                              const float* __restrict__ wt, const float* __restrict__ dy,
+                                                              T* __restrict__ dx) {
+  extern __shared__ float sw[];    // [9][C]
   for (int i = threadIdx.x; i < g.c * 9; i += blockDim.x) sw[(i % 9) * g.c + i / 9] = wt[i];
   __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int H = g.h * g.r, W = g.w * g.r;
+  const long total = (long)g.n * g.h * g.w * g.nsb * g.nsb;
+  const long warp0 = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+  for (long item = warp0; item < total; item += nwarps) {
+    const SubBlock sbk = decode_sb(g, item);
+    HaloIdx hi;
+    halo_index(g, sbk, &hi);
+    float gy[kHalo];
+#pragma unroll
+    for (int i = 0; i < kSBMax + 2; ++i)
+#pragma unroll
+      for (int j = 0; j < kSBMax + 2; ++j) {
+        const int Yc = min(max(sbk.Y0 + i - 1, 0), H - 1), Xc = min(max(sbk.X0 + j - 1, 0), W - 1);
+        const float t = __ldg(dy + ((size_t)sbk.ni * H + Yc) * W + Xc);
+        gy[i * (kSBMax + 2) + j] = (((hi.rowok >> i) & 1u) && ((hi.colok >> j) & 1u)) ? t : 0.f;
+      }
+    for (int cb = 0; cb < g.c; cb += 32 * CPL) {
+      const int c0 = cb + lane * CPL;
+      float wr[9][CPL];
+#pragma unroll
+      for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int q = 0; q < CPL; ++q) wr[t][q] = sw[t * g.c + c0 + q];
+#pragma unroll
+      for (int oy = 0; oy < kSBMax; ++oy)
+#pragma unroll
+        for (int ox = 0; ox < kSBMax; ++ox) {
+          if (oy < g.sb && ox < g.sb) {
+            float d[CPL];
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) d[q] = 0.f;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+              for (int kx = 0; kx < 3; ++kx) {
+                const float gn = gy[(oy + 2 - ky) * (kSBMax + 2) + ox + 2 - kx];
+#pragma unroll
+                for (int q = 0; q < CPL; ++q) d[q] = fmaf(gn, wr[ky * 3 + kx][q], d[q]);
+              }
+            store_cpl<T, CPL>(dx + halo_off(g, hi, oy + 1, ox + 1) + c0, d);
+          }
+        }
+    }
+  }
+}
+
+// backward, part 2: dw[c][tap] += dy(P) * x(P + off(tap), c), db += dy(P): the forward's rolling x
+// window; per-lane accumulators -> block fold (fixed warp order) -> ws -> final reduce.
+template <typename T, int CPL>
+__global__ void __launch_bounds__(256, 2) conv_last2_dw_kernel(const T* __restrict__ x, const __grid_constant__ LastGeom2 g,
+                                                              const float* __restrict__ dy, float* __restrict__ ws) {
+  extern __shared__ float sm[];    // block partial [nw][9*C + 1]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  const int H = g.h * g.r, W = g.w * g.r, HT = g.sb + 2;
+  const int H = g.h * g.r, W = g.w * g.r;
   const long total = (long)g.n * g.h * g.w * g.nsb * g.nsb;
   const long warp0 = (long)blockIdx.x * nw + warp;
   const long nwarps = (long)gridDim.x * nw;
@@ -538,81 +741,44 @@ __global__ void __launch_bounds__(256) conv_last2_bwd_kernel(const T* __restrict
     const SubBlock sbk = decode_sb(g, item);
     HaloIdx hi;
     halo_index(g, sbk, &hi);
-    float gy[kHalo];
-#pragma unroll
-    for (int i = 0; i < kSBMax + 2; ++i)
-#pragma unroll
-      for (int j = 0; j < kSBMax + 2; ++j) {
-        // dy outside the sub-block's own pixels is needed for dx only; outside the image it is 0
-        const int Yc = min(max(sbk.Y0 + i - 1, 0), H - 1), Xc = min(max(sbk.X0 + j - 1, 0), W - 1);
-        gy[i * (kSBMax + 2) + j] = __ldg(dy + ((size_t)sbk.ni * H + Yc) * W + Xc);
-      }
-#pragma unroll
-    for (int i = 0; i < kSBMax + 2; ++i)
-#pragma unroll
-      for (int j = 0; j < kSBMax + 2; ++j) {
-        const bool ok = ((hi.rowok >> i) & 1u) && ((hi.colok >> j) & 1u);
-        gy[i * (kSBMax + 2) + j] = ok ? gy[i * (kSBMax + 2) + j] : 0.f;
-      }
+    float gc[16];
 #pragma unroll
     for (int oy = 0; oy < kSBMax; ++oy)
 #pragma unroll
-      for (int ox = 0; ox < kSBMax; ++ox)
-        if (oy < g.sb && ox < g.sb) dbacc += gy[(oy + 1) * (kSBMax + 2) + ox + 1];
+      for (int ox = 0; ox < kSBMax; ++ox) {
+        const bool ok = oy < g.sb && ox < g.sb;
+        const int Yc = min(sbk.Y0 + oy, H - 1), Xc = min(sbk.X0 + ox, W - 1);
+        const float t = __ldg(dy + ((size_t)sbk.ni * H + Yc) * W + Xc);
+        gc[oy * kSBMax + ox] = ok ? t : 0.f;
+        dbacc += ok ? t : 0.f;
+      }
 #pragma unroll
     for (int b = 0; b < NCB; ++b) {
       const int cb = b * 32 * CPL;
       if (cb < g.c) {
         const int c0 = cb + lane * CPL;
-        float wr[9][CPL];
+        float rows[3][kSBMax + 2][CPL];
+        load_halo_row<T, CPL>(x, g, hi, 0, c0, rows[0]);
+        load_halo_row<T, CPL>(x, g, hi, 1, c0, rows[1]);
 #pragma unroll
-        for (int t = 0; t < 9; ++t)
-#pragma unroll
-          for (int q = 0; q < CPL; ++q) wr[t][q] = sw[t * g.c + c0 + q];
-        float xv[kHalo][CPL];
-#pragma unroll
-        for (int i = 0; i < kSBMax + 2; ++i)
-#pragma unroll
-          for (int j = 0; j < kSBMax + 2; ++j)
-            load_cpl<T, CPL>(x + halo_off(g, hi, i, j) + c0, xv[i * (kSBMax + 2) + j]);
-#pragma unroll
-        for (int i = 0; i < kSBMax + 2; ++i)
-#pragma unroll
-          for (int j = 0; j < kSBMax + 2; ++j) {
-            const bool ok = ((hi.rowok >> i) & 1u) && ((hi.colok >> j) & 1u);
-#pragma unroll
-            for (int q = 0; q < CPL; ++q) xv[i * (kSBMax + 2) + j][q] = ok ? xv[i * (kSBMax + 2) + j][q] : 0.f;
-          }
-#pragma unroll
-        for (int oy = 0; oy < kSBMax; ++oy)
+        for (int oy = 0; oy < kSBMax; ++oy) {
+          load_halo_row<T, CPL>(x, g, hi, oy + 2, c0, rows[(oy + 2) % 3]);
 #pragma unroll
           for (int ox = 0; ox < kSBMax; ++ox) {
-            if (oy < g.sb && ox < g.sb) {
-              float d[CPL];
+            const float gv = gc[oy * kSBMax + ox];
 #pragma unroll
-              for (int q = 0; q < CPL; ++q) d[q] = 0.f;
-              const float gc = gy[(oy + 1) * (kSBMax + 2) + ox + 1];
+            for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-              for (int ky = 0; ky < 3; ++ky)
+              for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
-                for (int kx = 0; kx < 3; ++kx) {
-                  // dx(P) uses dy at P - (ky-1, kx-1): halo index (oy + 1 - (ky-1), ox + 1 - (kx-1))
-                  const float gn = gy[(oy + 2 - ky) * (kSBMax + 2) + ox + 2 - kx];
-#pragma unroll
-                  for (int q = 0; q < CPL; ++q) {
-                    d[q] = fmaf(gn, wr[ky * 3 + kx][q], d[q]);
-                    dwacc[b][ky * 3 + kx][q] = fmaf(gc, xv[(oy + ky) * (kSBMax + 2) + ox + kx][q], dwacc[b][ky * 3 + kx][q]);
-                  }
-                }
-              store_cpl<T, CPL>(dx + halo_off(g, hi, oy + 1, ox + 1) + c0, d);
-            }
+                for (int q = 0; q < CPL; ++q)
+                  dwacc[b][ky * 3 + kx][q] = fmaf(gv, rows[(oy + ky) % 3][ox + kx][q], dwacc[b][ky * 3 + kx][q]);
           }
+        }
       }
     }
   }
-  // block fold in fixed warp order
   const int wsz = 9 * g.c, psz = wsz + 1;
-  float* part = sm + wsz;
 #pragma unroll
   for (int b = 0; b < NCB; ++b) {
     const int cb = b * 32 * CPL;
@@ -620,14 +786,13 @@ __global__ void __launch_bounds__(256) conv_last2_bwd_kernel(const T* __restrict
 #pragma unroll
       for (int t = 0; t < 9; ++t)
 #pragma unroll
-        for (int q = 0; q < CPL; ++q) part[(size_t)warp * psz + t * g.c + cb + lane * CPL + q] = dwacc[b][t][q];
+        for (int q = 0; q < CPL; ++q) sm[(size_t)warp * psz + t * g.c + cb + lane * CPL + q] = dwacc[b][t][q];
   }
-  // every lane accumulated the same db (broadcast dy loads)
-  if (lane == 0) part[(size_t)warp * psz + wsz] = dbacc;
+  if (lane == 0) sm[(size_t)warp * psz + wsz] = dbacc;   // every lane accumulated the same db
   __syncthreads();
   for (int i = threadIdx.x; i < psz; i += blockDim.x) {
     float s2 = 0.f;
-    for (int wv = 0; wv < nw; ++wv) s2 += part[(size_t)wv * psz + i];
+    for (int wv = 0; wv < nw; ++wv) s2 += sm[(size_t)wv * psz + i];
     ws[(size_t)blockIdx.x * psz + i] = s2;
   }
 }
@@ -683,6 +848,13 @@ extern "C" int vsr_conv3x3_first(const float* x, int32_t n, int32_t cin, int32_t
   const size_t smem = ((size_t)cin * 9 * cout + cout) * sizeof(float);
   VSR_CHECK_SUPPORTED(smem <= 48 * 1024, "vsr_conv3x3_first: cin*cout too large for shared memory");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (cin == 1 && cout <= 256 && (dtype == VSR_F32 || dtype == VSR_BF16)) {
+    const int grid2 = grid_for((long)n * h * w_, 8 * 8, 2);      // >= 8 pixels per warp
+    if (dtype == VSR_F32) conv_first2_kernel<float><<<grid2, 256, 0, s>>>(x, n, h, w_, w, bias, slope, (float*)y, cout);
+    else conv_first2_kernel<__nv_bfloat16><<<grid2, 256, 0, s>>>(x, n, h, w_, w, bias, slope, (__nv_bfloat16*)y, cout);
+    VSR_CHECK_LAUNCH("vsr_conv3x3_first(v2)");
+    return VSR_OK;
+  }
   const long total = (long)n * h * w_ * (cout / 8);
   const int grid = grid_for(total, 256, 4);
   if (dtype == VSR_F32)
@@ -696,7 +868,10 @@ extern "C" int vsr_conv3x3_first(const float* x, int32_t n, int32_t cin, int32_t
 }
 
 extern "C" size_t vsr_conv3x3_first_bwd_workspace(int32_t n, int32_t cin, int32_t h, int32_t w_, int32_t cout) {
-  return (size_t)first_bwd_blocks((long)n * h * w_) * cout * (cin * 9 + 1) * sizeof(float);
+  const long pixels = (long)n * h * w_;
+  size_t v1 = (size_t)first_bwd_blocks(pixels) * cout * (cin * 9 + 1) * sizeof(float);
+  size_t v2 = (size_t)((pixels + kF2Pix - 1) / kF2Pix) * cout * 10 * sizeof(float);
+  return v1 > v2 ? v1 : v2;
 }
 
 extern "C" int vsr_conv3x3_first_bwd(const float* x, int32_t n, int32_t cin, int32_t h, int32_t w_,
@@ -708,6 +883,17 @@ extern "C" int vsr_conv3x3_first_bwd(const float* x, int32_t n, int32_t cin, int
                 "vsr_conv3x3_first_bwd: workspace too small");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const long pixels = (long)n * h * w_;
+  if (cin == 1 && cout <= 256 && (dtype == VSR_F32 || dtype == VSR_BF16)) {
+    const int blocks2 = (int)((pixels + kF2Pix - 1) / kF2Pix);
+    float* ws2 = static_cast<float*>(workspace);
+    if (dtype == VSR_F32) conv_first2_bwd_kernel<float><<<blocks2, 1024, 0, s>>>(x, n, h, w_, (const float*)dz, cout, ws2);
+    else conv_first2_bwd_kernel<__nv_bfloat16><<<blocks2, 1024, 0, s>>>(x, n, h, w_, (const __nv_bfloat16*)dz, cout, ws2);
+    VSR_CHECK_LAUNCH("vsr_conv3x3_first_bwd(v2)");
+    const int nout = cout * 10;
+    rows_reduce_kernel<<<(nout + 63) / 64, 256, 0, s>>>(ws2, blocks2, nout, dw, db, cout, accumulate);
+    VSR_CHECK_LAUNCH("vsr_conv3x3_first_bwd_final(v2)");
+    return VSR_OK;
+  }
   const int blocks = first_bwd_blocks(pixels);
   const long ppb = (pixels + blocks - 1) / blocks;
   const int threads = cout >= 256 ? 256 : ((cout + 31) / 32) * 32;
@@ -785,14 +971,28 @@ extern "C" int vsr_conv3x3_last_bwd(const void* x, int32_t dtype, int32_t n, int
     const int blocks2 = last_bwd_blocks();
     const int nw2 = kLastBwdThreads / 32;
     const size_t psz2 = (size_t)9 * c + 1;
-    const size_t smem2 = ((size_t)9 * c + nw2 * psz2) * sizeof(float);
+    const size_t smem_w = (size_t)9 * c * sizeof(float);
+    const size_t smem_p = (size_t)nw2 * psz2 * sizeof(float);
     float* ws2 = static_cast<float*>(workspace);
+    const long items = (long)n * h * w_ * g2.nsb * g2.nsb;
+    const int grid_dx = grid_for(items, 8, 8);
     if (dtype == VSR_BF16) {
-      if (c % 64 == 0) conv_last2_bwd_kernel<__nv_bfloat16, 2><<<blocks2, kLastBwdThreads, smem2, s2>>>((const __nv_bfloat16*)x, g2, w, dy, (__nv_bfloat16*)dx, ws2);
-      else conv_last2_bwd_kernel<__nv_bfloat16, 1><<<blocks2, kLastBwdThreads, smem2, s2>>>((const __nv_bfloat16*)x, g2, w, dy, (__nv_bfloat16*)dx, ws2);
+      using B = __nv_bfloat16;
+      if (c % 64 == 0) {
+        conv_last2_dx_kernel<B, 2><<<grid_dx, 256, smem_w, s2>>>(g2, w, dy, (B*)dx);
+        conv_last2_dw_kernel<B, 2><<<blocks2, kLastBwdThreads, smem_p, s2>>>((const B*)x, g2, dy, ws2);
+      } else {
+        conv_last2_dx_kernel<B, 1><<<grid_dx, 256, smem_w, s2>>>(g2, w, dy, (B*)dx);
+        conv_last2_dw_kernel<B, 1><<<blocks2, kLastBwdThreads, smem_p, s2>>>((const B*)x, g2, dy, ws2);
+      }
     } else {
-      if (c % 64 == 0) conv_last2_bwd_kernel<float, 2><<<blocks2, kLastBwdThreads, smem2, s2>>>((const float*)x, g2, w, dy, (float*)dx, ws2);
-      else conv_last2_bwd_kernel<float, 1><<<blocks2, kLastBwdThreads, smem2, s2>>>((const float*)x, g2, w, dy, (float*)dx, ws2);
+      if (c % 64 == 0) {
+        conv_last2_dx_kernel<float, 2><<<grid_dx, 256, smem_w, s2>>>(g2, w, dy, (float*)dx);
+        conv_last2_dw_kernel<float, 2><<<blocks2, kLastBwdThreads, smem_p, s2>>>((const float*)x, g2, dy, ws2);
+      } else {
+        conv_last2_dx_kernel<float, 1><<<grid_dx, 256, smem_w, s2>>>(g2, w, dy, (float*)dx);
+        conv_last2_dw_kernel<float, 1><<<blocks2, kLastBwdThreads, smem_p, s2>>>((const float*)x, g2, dy, ws2);
+      }
     }
     VSR_CHECK_LAUNCH("vsr_conv3x3_last_bwd(v2)");
     conv_last_bwd_final_kernel<<<((int)psz2 + 127) / 128, 128, 0, s2>>>(ws2, blocks2, 1, c, dw, db, accumulate);

@@ -60,17 +60,30 @@ __device__ __forceinline__ float denorm(float v, float mean, float std, bool on)
   return fminf(fmaxf(r, 0.f), 255.f);
 }
 
-// PSNR pass 1: grid (blocks_per_sample, n): partial sum of squared error
-__global__ void psnr_partial_kernel(const float* __restrict__ out, const float* __restrict__ tgt,
-                                    long per_sample, float mean, float std, int denorm_on,
-                                    float* __restrict__ ws) {
+// PSNR pass 1: grid (blocks_per_sample, n): partial sum of squared error (16-byte loads when aligned)
+__global__ void __launch_bounds__(256) psnr_partial_kernel(const float* __restrict__ out, const float* __restrict__ tgt,
+                                                          long per_sample, float mean, float std, int denorm_on,
+                                                          float* __restrict__ ws) {
   __shared__ float red[32];
   const float* o = out + (size_t)blockIdx.y * per_sample;
   const float* t = tgt + (size_t)blockIdx.y * per_sample;
   float acc = 0.f;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < per_sample; i += (long)gridDim.x * blockDim.x) {
-    const float d = denorm(__ldg(o + i), mean, std, denorm_on) - denorm(__ldg(t + i), mean, std, denorm_on);
-    acc = fmaf(d, d, acc);
+  if ((per_sample & 3) == 0) {
+    const float4* o4 = reinterpret_cast<const float4*>(o);
+    const float4* t4 = reinterpret_cast<const float4*>(t);
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < per_sample / 4; i += (long)gridDim.x * blockDim.x) {
+      const float4 a = __ldg(o4 + i), b = __ldg(t4 + i);
+      const float d0 = denorm(a.x, mean, std, denorm_on) - denorm(b.x, mean, std, denorm_on);
+      const float d1 = denorm(a.y, mean, std, denorm_on) - denorm(b.y, mean, std, denorm_on);
+      const float d2 = denorm(a.z, mean, std, denorm_on) - denorm(b.z, mean, std, denorm_on);
+      const float d3 = denorm(a.w, mean, std, denorm_on) - denorm(b.w, mean, std, denorm_on);
+      acc = fmaf(d0, d0, acc); acc = fmaf(d1, d1, acc); acc = fmaf(d2, d2, acc); acc = fmaf(d3, d3, acc);
+    }
+  } else {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < per_sample; i += (long)gridDim.x * blockDim.x) {
+      const float d = denorm(__ldg(o + i), mean, std, denorm_on) - denorm(__ldg(t + i), mean, std, denorm_on);
+      acc = fmaf(d, d, acc);
+    }
   }
   const float s = block_sum(acc, red);
   if (threadIdx.x == 0) ws[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = s;
@@ -85,71 +98,84 @@ __global__ void psnr_final_kernel(const float* __restrict__ ws, int n, int bps, 
   psnr[i] = 10.f * log10f(max_value * max_value / (mse + 1e-10f));
 }
 
-// SSIM: block = 16 x 32 output pixels of one image (valid 11x11 separable window).
-constexpr int kSH = 16, kSW = 32, kWin = 11;
-__global__ void __launch_bounds__(kSH * kSW) ssim_partial_kernel(
-    const float* __restrict__ out, const float* __restrict__ tgt, int h, int w,
-    const float* __restrict__ win, float mean, float std, int denorm_on, float c1, float c2,
-    int tiles_x, int tiles_y, float* __restrict__ ws) {
-  __shared__ float sx[kSH + kWin - 1][kSW + kWin - 1];
-  __shared__ float sy[kSH + kWin - 1][kSW + kWin - 1];
-  __shared__ float hs[5][kSH + kWin - 1][kSW];
-  __shared__ float g[kWin];
-  __shared__ float red[32];
-  const int tid = threadIdx.x;
-  const int tile = blockIdx.x;
-  const int tx = tile % tiles_x, ty = tile / tiles_x;
-  const int ni = blockIdx.y;
+// SSIM (valid 11x11 separable window): one warp = a strip of 32 output columns x kSRows output rows.
+// Per input row the lane forms the 5 horizontal sums (x, y, x^2, y^2, xy) of its column from a
+// per-warp shared-memory row buffer and pushes them into an 11-deep register window; the vertical
+// sum over the window gives one SSIM value per row.  The window is indexed statically (the row loop
+// is unrolled by 11).  Partials per (image, strip) -> fixed-order final reduce.
+constexpr int kWin = 11, kSRows = 32, kSWarps = 4;
+__global__ void __launch_bounds__(kSWarps * 32) ssim_partial_kernel(
+    const float* __restrict__ out, const float* __restrict__ tgt, int h, int w, const float* __restrict__ win,
+    float mean, float std, int denorm_on, float c1, float c2, int tiles_x, int tiles_y, float* __restrict__ ws) {
+  __shared__ float rowbuf[kSWarps][2][48];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tx = blockIdx.x * kSWarps + warp;             // column strip
+  const int ty = blockIdx.y;                               // row tile
+  const int ni = blockIdx.z;
   const int oh = h - (kWin - 1), ow = w - (kWin - 1);
-  const int y0 = ty * kSH, x0 = tx * kSW;
+  if (tx >= tiles_x) return;                               // (no block-level barriers below)
+  float g[kWin];
+#pragma unroll
+  for (int k = 0; k < kWin; ++k) g[k] = __ldg(win + k);
+  const int x0 = tx * 32, y0 = ty * kSRows;
+  const int rows_out = min(kSRows, oh - y0);
+  const int rows_in = rows_out + kWin - 1;
   const float* o = out + (size_t)ni * h * w;
   const float* t = tgt + (size_t)ni * h * w;
-  if (tid < kWin) g[tid] = win[tid];
-  for (int i = tid; i < (kSH + kWin - 1) * (kSW + kWin - 1); i += blockDim.x) {
-    const int r = i / (kSW + kWin - 1), c = i % (kSW + kWin - 1);
-    const int yy = y0 + r, xx = x0 + c;
-    float a = 0.f, b = 0.f;
-    if (yy < h && xx < w) {
-      a = denorm(__ldg(o + (size_t)yy * w + xx), mean, std, denorm_on);
-      b = denorm(__ldg(t + (size_t)yy * w + xx), mean, std, denorm_on);
-    }
-    sx[r][c] = a;
-    sy[r][c] = b;
-  }
-  __syncthreads();
-  for (int i = tid; i < (kSH + kWin - 1) * kSW; i += blockDim.x) {
-    const int r = i / kSW, c = i % kSW;
-    float m1 = 0.f, m2 = 0.f, s11 = 0.f, s22 = 0.f, s12 = 0.f;
+  float* bx = rowbuf[warp][0];
+  float* by = rowbuf[warp][1];
+  float wv[5][kWin];
 #pragma unroll
-    for (int k = 0; k < kWin; ++k) {
-      const float a = sx[r][c + k], b = sy[r][c + k], wk = g[k];
-      m1 = fmaf(wk, a, m1);
-      m2 = fmaf(wk, b, m2);
-      s11 = fmaf(wk, a * a, s11);
-      s22 = fmaf(wk, b * b, s22);
-      s12 = fmaf(wk, a * b, s12);
-    }
-    hs[0][r][c] = m1; hs[1][r][c] = m2; hs[2][r][c] = s11; hs[3][r][c] = s22; hs[4][r][c] = s12;
-  }
-  __syncthreads();
-  const int r = tid / kSW, c = tid % kSW;
-  float val = 0.f;
-  if (y0 + r < oh && x0 + c < ow) {
-    float m1 = 0.f, m2 = 0.f, s11 = 0.f, s22 = 0.f, s12 = 0.f;
+  for (int q = 0; q < 5; ++q)
 #pragma unroll
-    for (int k = 0; k < kWin; ++k) {
-      const float wk = g[k];
-      m1 = fmaf(wk, hs[0][r + k][c], m1);
-      m2 = fmaf(wk, hs[1][r + k][c], m2);
-      s11 = fmaf(wk, hs[2][r + k][c], s11);
-      s22 = fmaf(wk, hs[3][r + k][c], s22);
-      s12 = fmaf(wk, hs[4][r + k][c], s12);
+    for (int k = 0; k < kWin; ++k) wv[q][k] = 0.f;
+  float acc = 0.f;
+  const bool col_ok = (x0 + lane) < ow;
+  for (int base = 0; base < rows_in; base += kWin) {
+#pragma unroll
+    for (int j = 0; j < kWin; ++j) {
+      const int r = base + j;
+      if (r < rows_in) {                                   // warp-uniform
+        const int yy = y0 + r;
+        // stage the row segment [x0, x0 + 42) (denormalised) for this warp
+        const int xa = x0 + lane, xb = x0 + 32 + lane;
+        float a0 = 0.f, b0 = 0.f, a1 = 0.f, b1 = 0.f;
+        if (xa < w) { a0 = denorm(__ldg(o + (size_t)yy * w + xa), mean, std, denorm_on); b0 = denorm(__ldg(t + (size_t)yy * w + xa), mean, std, denorm_on); }
+        if (lane < kWin - 1 && xb < w) { a1 = denorm(__ldg(o + (size_t)yy * w + xb), mean, std, denorm_on); b1 = denorm(__ldg(t + (size_t)yy * w + xb), mean, std, denorm_on); }
+        __syncwarp();
+        bx[lane] = a0; by[lane] = b0;
+        if (lane < kWin - 1) { bx[32 + lane] = a1; by[32 + lane] = b1; }
+        __syncwarp();
+        float m1 = 0.f, m2 = 0.f, s11 = 0.f, s22 = 0.f, s12 = 0.f;
+#pragma unroll
+        for (int k = 0; k < kWin; ++k) {
+          const float a = bx[lane + k], b = by[lane + k], wk = g[k];
+          m1 = fmaf(wk, a, m1);
+          m2 = fmaf(wk, b, m2);
+          s11 = fmaf(wk, a * a, s11);
+          s22 = fmaf(wk, b * b, s22);
+          s12 = fmaf(wk, a * b, s12);
+        }
+        wv[0][j] = m1; wv[1][j] = m2; wv[2][j] = s11; wv[3][j] = s22; wv[4][j] = s12;
+        if (r >= kWin - 1) {
+          // window rows r-10 .. r live in slots (j+1) % 11 .. j; slot (j + 1 + k) % 11 has tap k
+          float v[5];
+#pragma unroll
+          for (int q = 0; q < 5; ++q) {
+            float sv = 0.f;
+#pragma unroll
+            for (int k = 0; k < kWin; ++k) sv = fmaf(g[k], wv[q][(j + 1 + k) % kWin], sv);
+            v[q] = sv;
+          }
+          const float var1 = v[2] - v[0] * v[0], var2 = v[3] - v[1] * v[1], cov = v[4] - v[0] * v[1];
+          const float val = ((2.f * v[0] * v[1] + c1) * (2.f * cov + c2)) / ((v[0] * v[0] + v[1] * v[1] + c1) * (var1 + var2 + c2));
+          acc += col_ok ? val : 0.f;
+        }
+      }
     }
-    const float v1 = s11 - m1 * m1, v2 = s22 - m2 * m2, cov = s12 - m1 * m2;
-    val = ((2.f * m1 * m2 + c1) * (2.f * cov + c2)) / ((m1 * m1 + m2 * m2 + c1) * (v1 + v2 + c2));
   }
-  const float s = block_sum(val, red);
-  if (tid == 0) ws[(size_t)ni * (tiles_x * tiles_y) + tile] = s;
+  acc = warp_sum(acc);
+  if (lane == 0) ws[((size_t)ni * tiles_y + ty) * tiles_x + tx] = acc;
 }
 __global__ void ssim_final_kernel(const float* __restrict__ ws, int n, int tiles, float inv_count,
                                   float* __restrict__ ssim) {
@@ -225,11 +251,12 @@ extern "C" int vsr_ssim(const float* out, const float* target, int32_t n, int32_
   VSR_CHECK_ARG(workspace && workspace_bytes >= vsr_metric_workspace(n, (int64_t)h * w_), "vsr_ssim: workspace too small");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int oh = h - 10, ow = w_ - 10;
-  const int tiles_x = (ow + kSW - 1) / kSW, tiles_y = (oh + kSH - 1) / kSH;
+  const int tiles_x = (ow + 31) / 32, tiles_y = (oh + kSRows - 1) / kSRows;
+  VSR_CHECK_SUPPORTED(tiles_y <= 65535 && n <= 65535, "vsr_ssim: image too tall or batch too large");
   VSR_CHECK_SUPPORTED((size_t)tiles_x * tiles_y <= (size_t)((int64_t)h * w_ / 256 + 64), "vsr_ssim: degenerate aspect ratio");
   float* ws = static_cast<float*>(workspace);
-  ssim_partial_kernel<<<dim3(tiles_x * tiles_y, n), kSH * kSW, 0, s>>>(out, target, h, w_, win11, mean, std,
-                                                                     std > 0.f, c1, c2, tiles_x, tiles_y, ws);
+  ssim_partial_kernel<<<dim3((tiles_x + kSWarps - 1) / kSWarps, tiles_y, n), kSWarps * 32, 0, s>>>(
+      out, target, h, w_, win11, mean, std, std > 0.f, c1, c2, tiles_x, tiles_y, ws);
   VSR_CHECK_LAUNCH("vsr_ssim");
   ssim_final_kernel<<<(n + 127) / 128, 128, 0, s>>>(ws, n, tiles_x * tiles_y, 1.f / ((float)oh * (float)ow), ssim_out);
   VSR_CHECK_LAUNCH("vsr_ssim_final");
