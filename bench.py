@@ -309,6 +309,12 @@ def main():
             q[2] += 1
             q[3] += nbytes
         dom = max(agg, key=lambda k: agg[k][1])
+        traffic = None
+        try:       # per-launch dram__bytes_read+write of the same step under ncu (tools/ncu_summary.py)
+            with open(os.path.join(ROOT, "profiles", "r01_dram_by_kernel.json")) as f:
+                traffic = json.load(f).get({"tapgemm": "tapgemm_tc_kernel", "wgrad": "wgrad_tc_kernel"}.get(dom, dom), {}).get("dram_bytes_per_launch")
+        except (OSError, ValueError):
+            pass
         flops, kms, cnt = agg[dom]
         achieved = flops / (kms * 1e-3) / 1e12
         peak = pk["bf16_tflops_sustained"]
@@ -330,7 +336,8 @@ def main():
                     "ms_per_step": ms_e2e, "last_loss": last_loss},
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak, "traffic": None,
+                         "frac": achieved / peak, "traffic": traffic,
+                         "algorithmic_bytes_per_launch": sum(v[3] for k, v in detail.items() if k.startswith(dom)) / max(cnt, 1),
                          "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk['source']})",
                          "launches": cnt, "kernels": kernel_share, "kernel_detail": kernel_detail,
                          "timing_pass": f"{prof_steps} extra steps of the same workload, CUDA events around each launch",
