@@ -128,6 +128,16 @@ int vsr_tapgemm_wgrad(const VsrTapGemmDesc* d, float* dw, int accumulate, void* 
 int vsr_tapgemm_wgrad_bias(const VsrTapGemmDesc* d, float* dw, float* db, int32_t db_period, int accumulate,
                            void* workspace, size_t workspace_bytes, void* stream);
 
+/* Deferred reduction of the weight / bias gradient of one layer over several calls with identical
+ * shapes (the T frames of a recurrent net): _partial leaves per-split partial sums in `workspace`
+ * (ws_accumulate != 0 adds to what an earlier call left there) and returns 1, or returns 0 if the
+ * shape is not supported by the tensor-core kernel (then use vsr_tapgemm_wgrad); _finish reduces the
+ * splits in a fixed order into dw / db.  `d->out` is dz as in vsr_tapgemm_wgrad. */
+int vsr_tapgemm_wgrad_partial(const VsrTapGemmDesc* d, int32_t db_period, int ws_accumulate, void* workspace,
+                              size_t workspace_bytes, void* stream);
+int vsr_tapgemm_wgrad_finish(const VsrTapGemmDesc* d, float* dw, float* db, int32_t db_period, int accumulate,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
 /* colsum: db[c] (+)= sum over pixels x[pix][c]  (bias gradient; fixed order).
  * workspace >= vsr_colsum_workspace(rows, c) bytes. */
 size_t vsr_colsum_workspace(int64_t rows, int32_t c);

@@ -40,6 +40,7 @@ struct WgArgs {
   float* ws;              // [splits][n_taps_total][nt][64]
   float* bias_ws;         // [splits][cout] column sums of dz (bias gradient), or NULL
   int cout;
+  int ws_accumulate;      // add to the partials already in ws (same layer, earlier frame)
   int n_items, splits, chunks;   // item = (group, N-slice, chunk of <= kMaxChunk taps)
   int nt, ncta;           // group width, per-item N (64 or 128)
   int n_taps_total;
@@ -225,7 +226,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
         if (live) {
           float* o = wsp + ((size_t)ti * a.nt + item.y + c) * 64 + k;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) o[(size_t)i * 64] = __uint_as_float(r[i]);
+          for (int i = 0; i < 16; ++i)
+            o[(size_t)i * 64] = (a.ws_accumulate ? o[(size_t)i * 64] : 0.f) + __uint_as_float(r[i]);
         }
       }
     }
@@ -243,8 +245,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
       float s0 = 0.f, s1 = 0.f;
       for (int q = 0; q < parts; ++q) { s0 += scr[q * cpairs + cp].x; s1 += scr[q * cpairs + cp].y; }
       float* o = a.bias_ws + (size_t)split * a.cout + grp.x + item.y + 2 * cp;
-      o[0] = s0;
-      o[1] = s1;
+      o[0] = (a.ws_accumulate ? o[0] : 0.f) + s0;
+      o[1] = (a.ws_accumulate ? o[1] : 0.f) + s1;
     }
   }
   ptx::tc_fence_before();
@@ -329,8 +331,8 @@ size_t wgrad_tc_workspace(const VsrTapGemmDesc* d) {
   return (size_t)p.splits * ((size_t)d->n_taps_total * d->nt * 64 + d->out.c) * sizeof(float);
 }
 
-int wgrad_tc_launch(const VsrTapGemmDesc* d, float* dw, float* db, int db_period, int accumulate, void* workspace,
-                    cudaStream_t stream) {
+// partial pass: leaves per-split partial sums (weights, and bias columns if want_bias) in workspace
+int wgrad_tc_partial(const VsrTapGemmDesc* d, int want_bias, int ws_accumulate, void* workspace, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -352,9 +354,9 @@ int wgrad_tc_launch(const VsrTapGemmDesc* d, float* dw, float* db, int db_period
   a.tap_tab = reinterpret_cast<const int4*>(d->tap_tab);
   a.group_tab = reinterpret_cast<const int4*>(d->group_tab);
   a.ws = static_cast<float*>(workspace);
-  const bool with_bias = db != nullptr && d->out.c <= 1024 && db_period > 0 && d->out.c % db_period == 0;
-  a.bias_ws = with_bias ? a.ws + (size_t)p.splits * d->n_taps_total * d->nt * 64 : nullptr;
+  a.bias_ws = want_bias ? a.ws + (size_t)p.splits * d->n_taps_total * d->nt * 64 : nullptr;
   a.cout = d->out.c;
+  a.ws_accumulate = ws_accumulate;
   a.n_items = p.n_items;
   a.splits = p.splits;
   a.chunks = p.chunks;
@@ -370,13 +372,35 @@ int wgrad_tc_launch(const VsrTapGemmDesc* d, float* dw, float* db, int db_period
   const int smem = kCtrl + 1024 + 2 * nb * kTileBytes + kAStages * 2 * kTileBytes;
   wgrad_tc_kernel<<<p.n_items * p.splits, kThreads, smem, stream>>>(a);
   VSR_CHECK_LAUNCH("wgrad_tc");
+  return VSR_OK;
+}
+
+// final pass: dw (+)= sum over splits, db[q] (+)= sum over splits and columns c = q (mod period)
+int wgrad_tc_finish(const VsrTapGemmDesc* d, float* dw, float* db, int db_period, int accumulate, void* workspace,
+                    cudaStream_t stream) {
+  const WgPlan p = make_plan(d);
+  const float* ws = static_cast<const float*>(workspace);
+  const bool with_bias = db != nullptr;
+  const float* bias_ws = with_bias ? ws + (size_t)p.splits * d->n_taps_total * d->nt * 64 : nullptr;
   const long n = (long)d->n_taps_total * d->nt * 64;
   const long n4 = n / 4;     // nt * 64 is a multiple of 4
   wg_reduce_kernel<<<(int)((n4 + 63) / 64) + (with_bias ? 1 : 0), 256, 0, stream>>>(
-      reinterpret_cast<const float4*>(a.ws), reinterpret_cast<float4*>(dw), n4, p.splits, accumulate, a.bias_ws,
+      reinterpret_cast<const float4*>(ws), reinterpret_cast<float4*>(dw), n4, p.splits, accumulate, bias_ws,
       d->out.c, db_period, db);
   VSR_CHECK_LAUNCH("wgrad_tc_reduce");
   return VSR_OK;
+}
+
+bool wgrad_tc_bias_ok(const VsrTapGemmDesc* d, int db_period) {
+  return d->out.c <= 1024 && db_period > 0 && d->out.c % db_period == 0;
+}
+
+int wgrad_tc_launch(const VsrTapGemmDesc* d, float* dw, float* db, int db_period, int accumulate, void* workspace,
+                    cudaStream_t stream) {
+  const bool with_bias = db != nullptr && wgrad_tc_bias_ok(d, db_period);
+  int rc = wgrad_tc_partial(d, with_bias, 0, workspace, stream);
+  if (rc != VSR_OK) return rc;
+  return wgrad_tc_finish(d, dw, with_bias ? db : nullptr, db_period, accumulate, workspace, stream);
 }
 
 }  // namespace vsr

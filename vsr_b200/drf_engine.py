@@ -179,8 +179,16 @@ class DrfEngine:
             row_dst.append(pref.offset)
             return partials[i]
 
+        pending = {}     # layer -> (srcs, dz, workspace): partial sums awaiting the once-per-step reduction
+
         def wgrad(lname, srcs, dz):
             L = P.fwd[lname]
+            if T > 1:
+                # same layer, same shapes every frame: accumulate split partials, reduce once (below)
+                wsl = self._workspace("wg:" + lname, ops.tapgemm_wgrad_workspace(L.table, srcs, dz))
+                if ops.tapgemm_wgrad_partial(L.table, srcs, dz, wsl, lname in pending, L.bias_c):
+                    pending[lname] = (srcs, dz, wsl)
+                    return
             ws = self._workspace("wgrad", ops.tapgemm_wgrad_workspace(L.table, srcs, dz))
             db = db_packed[L.b_off:L.b_off + L.bias_c]
             fused = ops.tapgemm_wgrad(L.table, srcs, dz, dw_packed[L.w_off:L.w_off + L.w_numel], True, ws,
@@ -297,6 +305,10 @@ class DrfEngine:
             ops.conv3x3_first_bwd(S.x, dz_a1, self._pview(gflat, f"{P.in_name}.conv1.weight"),
                                   self._pview(gflat, f"{P.in_name}.conv1.bias"), True, ws)
             next_dz_lr0 = dz_lr0
+        for lname, (srcs, dz, wsl) in pending.items():
+            L = P.fwd[lname]
+            ops.tapgemm_wgrad_finish(L.table, srcs, dz, dw_packed[L.w_off:L.w_off + L.w_numel],
+                                     db_packed[L.b_off:L.b_off + L.bias_c], L.bias_c, True, wsl)
         # ---- un-pack: weights, biases, PReLU slopes ----
         for lo, idx in self.unpack:
             ops.gather_add(dw_packed, idx, gflat[lo:lo + idx.numel()])

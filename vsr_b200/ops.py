@@ -156,6 +156,35 @@ class CudaOps:
         self.launches += 2
         return fused
 
+    def tapgemm_wgrad_partial(self, tab, srcs, dz, workspace, ws_accumulate, db_period):
+        """per-split partials of dw / db into `workspace` (deferred reduction); False if unsupported."""
+        d = _make_desc(tab, srcs, dz)
+        _need_cuda(workspace)
+        if self.timing is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        rc = self.lib.vsr_tapgemm_wgrad_partial(C.byref(d), db_period, int(ws_accumulate), _p(workspace),
+                                                workspace.numel() * workspace.element_size(), _stream())
+        if rc < 0:
+            check(rc, "vsr_tapgemm_wgrad_partial")
+        if rc == 1:
+            if self.timing is not None:
+                e1.record()
+                pix = dz.shape[0] * dz.shape[1] * dz.shape[2]
+                sig = f"taps{tab.n_taps_total}_nt{tab.nt}_g{tab.n_groups}_px{pix}"
+                nbytes = dz.element_size() * (sum(pix * s.shape[-1] for s in srcs) + pix * dz.shape[-1])
+                self.timing.append(("wgrad", 2.0 * pix * tab.n_taps_total * tab.nt * tab.kc, e0, e1, sig, nbytes))
+            self.launches += 1
+        return rc == 1
+
+    def tapgemm_wgrad_finish(self, tab, srcs, dz, dw, db, db_period, accumulate, workspace):
+        d = _make_desc(tab, srcs, dz)
+        _need_cuda(dw, db, workspace)
+        check(self.lib.vsr_tapgemm_wgrad_finish(C.byref(d), _p(dw), _p(db), db_period, int(accumulate), _p(workspace),
+                                                workspace.numel() * workspace.element_size(), _stream()),
+              "vsr_tapgemm_wgrad_finish")
+        self.launches += 1
+
     # ---- small kernels -----------------------------------------------------------------
     def colsum_workspace(self, rows, c):
         return self.lib.vsr_colsum_workspace(rows, c)
