@@ -129,14 +129,15 @@ int vsr_tapgemm_wgrad_bias(const VsrTapGemmDesc* d, float* dw, float* db, int32_
                            void* workspace, size_t workspace_bytes, void* stream);
 
 /* Deferred reduction of the weight / bias gradient of one layer over several calls with identical
- * shapes (the T frames of a recurrent net): _partial leaves per-split partial sums in `workspace`
- * (ws_accumulate != 0 adds to what an earlier call left there) and returns 1, or returns 0 if the
+ * shapes (the T frames of a recurrent net): call k writes its per-split partial sums into slice k of
+ * `workspace` (>= n_slices * vsr_tapgemm_wgrad_workspace(d) bytes) and returns 1, or returns 0 if the
  * shape is not supported by the tensor-core kernel (then use vsr_tapgemm_wgrad); _finish reduces the
- * splits in a fixed order into dw / db.  `d->out` is dz as in vsr_tapgemm_wgrad. */
-int vsr_tapgemm_wgrad_partial(const VsrTapGemmDesc* d, int32_t db_period, int ws_accumulate, void* workspace,
-                              size_t workspace_bytes, void* stream);
+ * first `used_slices` slices in a fixed order into dw / db.  `d->out` is dz as in vsr_tapgemm_wgrad. */
+int vsr_tapgemm_wgrad_partial(const VsrTapGemmDesc* d, int32_t db_period, int32_t slice, int32_t n_slices,
+                              void* workspace, size_t workspace_bytes, void* stream);
 int vsr_tapgemm_wgrad_finish(const VsrTapGemmDesc* d, float* dw, float* db, int32_t db_period, int accumulate,
-                             void* workspace, size_t workspace_bytes, void* stream);
+                             int32_t used_slices, int32_t n_slices, void* workspace, size_t workspace_bytes,
+                             void* stream);
 
 /* colsum: db[c] (+)= sum over pixels x[pix][c]  (bias gradient; fixed order).
  * workspace >= vsr_colsum_workspace(rows, c) bytes. */

@@ -345,21 +345,21 @@ class EmuOps:
         self.launches += 1
 
     # deferred wgrad reduction: the emulation keeps the running sums in a side table keyed by workspace
-    def tapgemm_wgrad_partial(self, tab, srcs, dz, workspace, ws_accumulate, db_period):
+    def tapgemm_wgrad_partial(self, tab, srcs, dz, workspace, slice_, n_slices, db_period):
         ct = torch.float64 if dz.dtype == torch.float64 else torch.float32
         dw = torch.zeros(tab.n_taps_total * tab.nt * tab.kc, dtype=ct, device=dz.device)
         db = torch.zeros(db_period, dtype=ct, device=dz.device)
         self.tapgemm_wgrad(tab, srcs, dz, dw, False, workspace, db=db, db_period=db_period)
         store = self.__dict__.setdefault("_wg_store", {})
         key = workspace.data_ptr()
-        if ws_accumulate and key in store:
+        if slice_ > 0 and key in store:
             store[key][0].add_(dw)
             store[key][1].add_(db)
         else:
             store[key] = [dw, db]
         return True
 
-    def tapgemm_wgrad_finish(self, tab, srcs, dz, dw, db, db_period, accumulate, workspace):
+    def tapgemm_wgrad_finish(self, tab, srcs, dz, dw, db, db_period, accumulate, used, n_slices, workspace):
         pdw, pdb = self._wg_store.pop(workspace.data_ptr())
         flat = dw.view(-1)[:pdw.numel()]
         if accumulate:

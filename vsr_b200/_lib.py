@@ -42,10 +42,10 @@ _SIGS = {
                                     C.c_size_t, C.c_void_p]),
     "vsr_tapgemm_wgrad_bias": (C.c_int, [C.POINTER(VsrTapGemmDesc), C.c_void_p, C.c_void_p, C.c_int32, C.c_int,
                                          C.c_void_p, C.c_size_t, C.c_void_p]),
-    "vsr_tapgemm_wgrad_partial": (C.c_int, [C.POINTER(VsrTapGemmDesc), C.c_int32, C.c_int, C.c_void_p, C.c_size_t,
-                                            C.c_void_p]),
+    "vsr_tapgemm_wgrad_partial": (C.c_int, [C.POINTER(VsrTapGemmDesc), C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                            C.c_size_t, C.c_void_p]),
     "vsr_tapgemm_wgrad_finish": (C.c_int, [C.POINTER(VsrTapGemmDesc), C.c_void_p, C.c_void_p, C.c_int32, C.c_int,
-                                           C.c_void_p, C.c_size_t, C.c_void_p]),
+                                           C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),
     "vsr_colsum_workspace": (C.c_size_t, [C.c_int64, C.c_int32]),
     "vsr_colsum": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_int,
                              C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -366,9 +366,9 @@ bool wgrad_tc_supported(const VsrTapGemmDesc* d);                       // wgrad
 size_t wgrad_tc_workspace(const VsrTapGemmDesc* d);
 int wgrad_tc_launch(const VsrTapGemmDesc* d, float* dw, float* db, int db_period, int accumulate, void* workspace,
                     cudaStream_t stream);
-int wgrad_tc_partial(const VsrTapGemmDesc* d, int want_bias, int ws_accumulate, void* workspace, cudaStream_t stream);
-int wgrad_tc_finish(const VsrTapGemmDesc* d, float* dw, float* db, int db_period, int accumulate, void* workspace,
-                    cudaStream_t stream);
+int wgrad_tc_partial(const VsrTapGemmDesc* d, int want_bias, int slice, int n_slices, void* workspace, cudaStream_t stream);
+int wgrad_tc_finish(const VsrTapGemmDesc* d, float* dw, float* db, int db_period, int accumulate, int used_slices,
+                    int n_slices, void* workspace, cudaStream_t stream);
 bool wgrad_tc_bias_ok(const VsrTapGemmDesc* d, int db_period);
 
 int validate_desc(const VsrTapGemmDesc* d, const char* who) {
@@ -473,27 +473,31 @@ extern "C" int vsr_tapgemm_wgrad_bias(const VsrTapGemmDesc* d, float* dw, float*
   return rc;
 }
 
-// Deferred reduction: the same layer is differentiated once per frame with identical shapes, so the
-// per-split partial sums can accumulate in a per-layer workspace over the T frames
-// (vsr_tapgemm_wgrad_partial, ws_accumulate = 0 for the first frame) and be reduced once per step
-// (vsr_tapgemm_wgrad_finish).  partial returns 1 if the tcgen05 kernel took it (bias included),
-// 0 if the shape is unsupported (use vsr_tapgemm_wgrad / vsr_colsum instead).
-extern "C" int vsr_tapgemm_wgrad_partial(const VsrTapGemmDesc* d, int32_t db_period, int ws_accumulate,
+// Deferred reduction: the same layer is differentiated once per frame with identical shapes, so every
+// frame writes its per-split partial sums into its own slice of a per-layer workspace
+// (vsr_tapgemm_wgrad_partial, slice < n_slices; workspace >= n_slices * vsr_tapgemm_wgrad_workspace)
+// and one fixed-order pass reduces all slices (vsr_tapgemm_wgrad_finish).  partial returns 1 if the
+// tcgen05 kernel took it (bias included), 0 if the shape is unsupported (use vsr_tapgemm_wgrad).
+extern "C" int vsr_tapgemm_wgrad_partial(const VsrTapGemmDesc* d, int32_t db_period, int32_t slice, int32_t n_slices,
                                          void* workspace, size_t workspace_bytes, void* stream) {
   using namespace vsr;
   int rc = validate_desc(d, "vsr_tapgemm_wgrad_partial");
   if (rc != VSR_OK) return rc;
   if (!(wgrad_tc_supported(d) && wgrad_tc_bias_ok(d, db_period))) return 0;
-  VSR_CHECK_ARG(workspace && workspace_bytes >= vsr_tapgemm_wgrad_workspace(d), "vsr_tapgemm_wgrad_partial: workspace too small");
-  rc = wgrad_tc_partial(d, 1, ws_accumulate, workspace, static_cast<cudaStream_t>(stream));
+  VSR_CHECK_ARG(slice >= 0 && slice < n_slices, "vsr_tapgemm_wgrad_partial: slice out of range");
+  VSR_CHECK_ARG(workspace && workspace_bytes >= (size_t)n_slices * vsr_tapgemm_wgrad_workspace(d),
+                "vsr_tapgemm_wgrad_partial: workspace too small");
+  rc = wgrad_tc_partial(d, 1, slice, n_slices, workspace, static_cast<cudaStream_t>(stream));
   return rc == VSR_OK ? 1 : rc;
 }
 
 extern "C" int vsr_tapgemm_wgrad_finish(const VsrTapGemmDesc* d, float* dw, float* db, int32_t db_period,
-                                        int accumulate, void* workspace, size_t workspace_bytes, void* stream) {
+                                        int accumulate, int32_t used_slices, int32_t n_slices, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
   using namespace vsr;
   VSR_CHECK_ARG(d && dw && db && workspace, "vsr_tapgemm_wgrad_finish: bad arguments");
   VSR_CHECK_ARG(wgrad_tc_supported(d) && wgrad_tc_bias_ok(d, db_period), "vsr_tapgemm_wgrad_finish: shape was not accepted by _partial");
-  VSR_CHECK_ARG(workspace_bytes >= vsr_tapgemm_wgrad_workspace(d), "vsr_tapgemm_wgrad_finish: workspace too small");
-  return wgrad_tc_finish(d, dw, db, db_period, accumulate, workspace, static_cast<cudaStream_t>(stream));
+  VSR_CHECK_ARG(used_slices >= 1 && used_slices <= n_slices, "vsr_tapgemm_wgrad_finish: bad slice count");
+  VSR_CHECK_ARG(workspace_bytes >= (size_t)n_slices * vsr_tapgemm_wgrad_workspace(d), "vsr_tapgemm_wgrad_finish: workspace too small");
+  return wgrad_tc_finish(d, dw, db, db_period, accumulate, used_slices, n_slices, workspace, static_cast<cudaStream_t>(stream));
 }

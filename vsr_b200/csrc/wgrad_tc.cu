@@ -40,7 +40,7 @@ struct WgArgs {
   float* ws;              // [splits][n_taps_total][nt][64]
   float* bias_ws;         // [splits][cout] column sums of dz (bias gradient), or NULL
   int cout;
-  int ws_accumulate;      // add to the partials already in ws (same layer, earlier frame)
+
   int n_items, splits, chunks;   // item = (group, N-slice, chunk of <= kMaxChunk taps)
   int nt, ncta;           // group width, per-item N (64 or 128)
   int n_taps_total;
@@ -226,8 +226,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
         if (live) {
           float* o = wsp + ((size_t)ti * a.nt + item.y + c) * 64 + k;
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            o[(size_t)i * 64] = (a.ws_accumulate ? o[(size_t)i * 64] : 0.f) + __uint_as_float(r[i]);
+          for (int i = 0; i < 16; ++i) o[(size_t)i * 64] = __uint_as_float(r[i]);
         }
       }
     }
@@ -245,8 +244,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
       float s0 = 0.f, s1 = 0.f;
       for (int q = 0; q < parts; ++q) { s0 += scr[q * cpairs + cp].x; s1 += scr[q * cpairs + cp].y; }
       float* o = a.bias_ws + (size_t)split * a.cout + grp.x + item.y + 2 * cp;
-      o[0] = (a.ws_accumulate ? o[0] : 0.f) + s0;
-      o[1] = (a.ws_accumulate ? o[1] : 0.f) + s1;
+      o[0] = s0;
+      o[1] = s1;
     }
   }
   ptx::tc_fence_before();
@@ -332,7 +331,8 @@ size_t wgrad_tc_workspace(const VsrTapGemmDesc* d) {
 }
 
 // partial pass: leaves per-split partial sums (weights, and bias columns if want_bias) in workspace
-int wgrad_tc_partial(const VsrTapGemmDesc* d, int want_bias, int ws_accumulate, void* workspace, cudaStream_t stream) {
+int wgrad_tc_partial(const VsrTapGemmDesc* d, int want_bias, int slice, int n_slices, void* workspace,
+                     cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -353,10 +353,12 @@ int wgrad_tc_partial(const VsrTapGemmDesc* d, int want_bias, int ws_accumulate, 
   if (rc != VSR_OK) return rc;
   a.tap_tab = reinterpret_cast<const int4*>(d->tap_tab);
   a.group_tab = reinterpret_cast<const int4*>(d->group_tab);
-  a.ws = static_cast<float*>(workspace);
-  a.bias_ws = want_bias ? a.ws + (size_t)p.splits * d->n_taps_total * d->nt * 64 : nullptr;
+  // workspace: [n_slices * splits][n] weight partials, then [n_slices * splits][cout] bias partials
+  const size_t n_w = (size_t)d->n_taps_total * d->nt * 64;
+  float* ws0 = static_cast<float*>(workspace);
+  a.ws = ws0 + (size_t)slice * p.splits * n_w;
+  a.bias_ws = want_bias ? ws0 + (size_t)n_slices * p.splits * n_w + (size_t)slice * p.splits * d->out.c : nullptr;
   a.cout = d->out.c;
-  a.ws_accumulate = ws_accumulate;
   a.n_items = p.n_items;
   a.splits = p.splits;
   a.chunks = p.chunks;
@@ -376,12 +378,13 @@ int wgrad_tc_partial(const VsrTapGemmDesc* d, int want_bias, int ws_accumulate, 
 }
 
 // final pass: dw (+)= sum over splits, db[q] (+)= sum over splits and columns c = q (mod period)
-int wgrad_tc_finish(const VsrTapGemmDesc* d, float* dw, float* db, int db_period, int accumulate, void* workspace,
-                    cudaStream_t stream) {
-  const WgPlan p = make_plan(d);
+int wgrad_tc_finish(const VsrTapGemmDesc* d, float* dw, float* db, int db_period, int accumulate, int used_slices,
+                    int n_slices, void* workspace, cudaStream_t stream) {
+  WgPlan p = make_plan(d);
   const float* ws = static_cast<const float*>(workspace);
   const bool with_bias = db != nullptr;
-  const float* bias_ws = with_bias ? ws + (size_t)p.splits * d->n_taps_total * d->nt * 64 : nullptr;
+  const float* bias_ws = with_bias ? ws + (size_t)n_slices * p.splits * d->n_taps_total * d->nt * 64 : nullptr;
+  p.splits *= used_slices;                       // slices 0..used-1 are contiguous rows
   const long n = (long)d->n_taps_total * d->nt * 64;
   const long n4 = n / 4;     // nt * 64 is a multiple of 4
   wg_reduce_kernel<<<(int)((n4 + 63) / 64) + (with_bias ? 1 : 0), 256, 0, stream>>>(
@@ -398,9 +401,9 @@ bool wgrad_tc_bias_ok(const VsrTapGemmDesc* d, int db_period) {
 int wgrad_tc_launch(const VsrTapGemmDesc* d, float* dw, float* db, int db_period, int accumulate, void* workspace,
                     cudaStream_t stream) {
   const bool with_bias = db != nullptr && wgrad_tc_bias_ok(d, db_period);
-  int rc = wgrad_tc_partial(d, with_bias, 0, workspace, stream);
+  int rc = wgrad_tc_partial(d, with_bias, 0, 1, workspace, stream);
   if (rc != VSR_OK) return rc;
-  return wgrad_tc_finish(d, dw, with_bias ? db : nullptr, db_period, accumulate, workspace, stream);
+  return wgrad_tc_finish(d, dw, with_bias ? db : nullptr, db_period, accumulate, 1, 1, workspace, stream);
 }
 
 }  // namespace vsr

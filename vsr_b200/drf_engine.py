@@ -179,15 +179,17 @@ class DrfEngine:
             row_dst.append(pref.offset)
             return partials[i]
 
-        pending = {}     # layer -> (srcs, dz, workspace): partial sums awaiting the once-per-step reduction
+        pending = {}     # layer -> [srcs, dz, workspace, slices used]: partials awaiting the per-step reduction
 
         def wgrad(lname, srcs, dz):
             L = P.fwd[lname]
             if T > 1:
                 # same layer, same shapes every frame: accumulate split partials, reduce once (below)
-                wsl = self._workspace("wg:" + lname, ops.tapgemm_wgrad_workspace(L.table, srcs, dz))
-                if ops.tapgemm_wgrad_partial(L.table, srcs, dz, wsl, lname in pending, L.bias_c):
-                    pending[lname] = (srcs, dz, wsl)
+                # every frame writes its own workspace slice; one reduction per layer per step (below)
+                wsl = self._workspace("wg:" + lname, T * ops.tapgemm_wgrad_workspace(L.table, srcs, dz))
+                used = pending[lname][3] if lname in pending else 0
+                if ops.tapgemm_wgrad_partial(L.table, srcs, dz, wsl, used, T, L.bias_c):
+                    pending[lname] = [srcs, dz, wsl, used + 1]
                     return
             ws = self._workspace("wgrad", ops.tapgemm_wgrad_workspace(L.table, srcs, dz))
             db = db_packed[L.b_off:L.b_off + L.bias_c]
@@ -305,10 +307,10 @@ class DrfEngine:
             ops.conv3x3_first_bwd(S.x, dz_a1, self._pview(gflat, f"{P.in_name}.conv1.weight"),
                                   self._pview(gflat, f"{P.in_name}.conv1.bias"), True, ws)
             next_dz_lr0 = dz_lr0
-        for lname, (srcs, dz, wsl) in pending.items():
+        for lname, (srcs, dz, wsl, used) in pending.items():
             L = P.fwd[lname]
             ops.tapgemm_wgrad_finish(L.table, srcs, dz, dw_packed[L.w_off:L.w_off + L.w_numel],
-                                     db_packed[L.b_off:L.b_off + L.bias_c], L.bias_c, True, wsl)
+                                     db_packed[L.b_off:L.b_off + L.bias_c], L.bias_c, True, used, T, wsl)
         # ---- un-pack: weights, biases, PReLU slopes ----
         for lo, idx in self.unpack:
             ops.gather_add(dw_packed, idx, gflat[lo:lo + idx.numel()])

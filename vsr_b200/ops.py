@@ -156,14 +156,14 @@ class CudaOps:
         self.launches += 2
         return fused
 
-    def tapgemm_wgrad_partial(self, tab, srcs, dz, workspace, ws_accumulate, db_period):
-        """per-split partials of dw / db into `workspace` (deferred reduction); False if unsupported."""
+    def tapgemm_wgrad_partial(self, tab, srcs, dz, workspace, slice_, n_slices, db_period):
+        """per-split partials of dw / db into slice `slice_` of `workspace`; False if unsupported."""
         d = _make_desc(tab, srcs, dz)
         _need_cuda(workspace)
         if self.timing is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        rc = self.lib.vsr_tapgemm_wgrad_partial(C.byref(d), db_period, int(ws_accumulate), _p(workspace),
+        rc = self.lib.vsr_tapgemm_wgrad_partial(C.byref(d), db_period, int(slice_), int(n_slices), _p(workspace),
                                                 workspace.numel() * workspace.element_size(), _stream())
         if rc < 0:
             check(rc, "vsr_tapgemm_wgrad_partial")
@@ -177,10 +177,11 @@ class CudaOps:
             self.launches += 1
         return rc == 1
 
-    def tapgemm_wgrad_finish(self, tab, srcs, dz, dw, db, db_period, accumulate, workspace):
+    def tapgemm_wgrad_finish(self, tab, srcs, dz, dw, db, db_period, accumulate, used, n_slices, workspace):
         d = _make_desc(tab, srcs, dz)
         _need_cuda(dw, db, workspace)
-        check(self.lib.vsr_tapgemm_wgrad_finish(C.byref(d), _p(dw), _p(db), db_period, int(accumulate), _p(workspace),
+        check(self.lib.vsr_tapgemm_wgrad_finish(C.byref(d), _p(dw), _p(db), db_period, int(accumulate), int(used),
+                                                int(n_slices), _p(workspace),
                                                 workspace.numel() * workspace.element_size(), _stream()),
               "vsr_tapgemm_wgrad_finish")
         self.launches += 1
