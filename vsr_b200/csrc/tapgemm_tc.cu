@@ -61,6 +61,7 @@ struct TcArgs {
   int resident;            // 1: the current group's weight slabs stay in smem across tiles
   int res_bytes;           // size of the resident weight region
   int m_tiles;             // pixel tiles per group
+  int debug;               // timing-attribution switches (VSR_TC_DEBUG), wrong results when non-zero
 };
 
 // tap entry packed into 32 bits: src[0:4) | dy+8 [4:8) | dx+8 [8:12) | c0/8 [12:32)
@@ -154,7 +155,11 @@ __device__ __forceinline__ void store_rows64(__nv_bfloat16* __restrict__ dst, co
   __syncwarp();
 }
 
+// FIXED_EPI >= 0: the epilogue flag set is a compile-time constant (dead variants are not emitted, the
+// hot loop stays small); FIXED_EPI < 0: flags are read from the arguments (any combination).
+template <int FIXED_EPI>
 __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc_kernel(const __grid_constant__ TcArgs a) {
+  const int epi = FIXED_EPI >= 0 ? FIXED_EPI : a.epi;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = ptx::smem_u32(smem_raw);
   uint8_t* smem_gen = smem_raw;
@@ -179,7 +184,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc_kernel(const __grid_co
     for (int i = threadIdx.x; i < a.n_groups; i += blockDim.x) grp_s[i] = __ldg(a.group_tab + i);
   if (taps_in_smem)
     for (int i = threadIdx.x; i < a.n_taps_total; i += blockDim.x) tap_s[i] = pack_tap(__ldg(a.tap_tab + i));
-  const bool bias_in_smem = (a.epi & VSR_EPI_BIAS) && a.Cout <= kBiasBytes / 4;
+  const bool bias_in_smem = (epi & VSR_EPI_BIAS) && a.Cout <= kBiasBytes / 4;
   if (bias_in_smem)
     for (int i = threadIdx.x; i < a.Cout; i += blockDim.x) bias_s[i] = a.bias[i];
   const uint32_t res_base = smem_base + kCtrlBytes;        // resident weight slabs (resident mode)
@@ -223,6 +228,8 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc_kernel(const __grid_co
       uint32_t phase = 0;
       int cur_g = -1;
       uint32_t gcount = 0;
+      const bool prof = (a.debug & 32) != 0;
+      long long p_wait = 0, p_issue = 0, p_n = 0, p_t0 = clock64();
       for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
         const TileCoord tc = decode_tile(a, tile);
         const int4 grp = grp_in_smem ? grp_s[tc.g] : __ldg(a.group_tab + tc.g);
@@ -237,16 +244,34 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc_kernel(const __grid_co
         }
         for (int t = 0; t < grp.z; ++t) {
           const int4 tap = taps_in_smem ? unpack_tap(tap_s[grp.y + t]) : __ldg(a.tap_tab + grp.y + t);
+          long long c0 = 0;
+          if (prof) c0 = clock64();
           ptx::mbar_wait(empty_bar + 8 * stage, phase ^ 1u);
+          if (prof) { const long long c1 = clock64(); p_wait += c1 - c0; ++p_n; }
           const uint32_t fb = full_bar + 8 * stage;
-          ptx::mbar_arrive_expect_tx(fb, stage_bytes);
           const uint32_t sa = stage_base + stage * stage_bytes;
+          if (a.debug & 6) {
+            // attribution runs: skip the A (2) and/or B (4) transfer, keep the barrier protocol
+            uint32_t tx = 0;
+            if (!(a.debug & 2)) tx += kATileBytes;
+            if (!(a.debug & 4) && !a.resident) tx += b_bytes;
+            if (tx == 0) { ptx::mbar_arrive(fb); } else { ptx::mbar_arrive_expect_tx(fb, tx); }
+            if (!(a.debug & 2)) ptx::tma_load_4d(sa, &a.maps[tap.x], fb, tap.w, tc.x0 + tap.z, tc.y0 + tap.y, tc.n);
+            if (!(a.debug & 4) && !a.resident)
+              ptx::bulk_load(sa + kATileBytes, a.w + static_cast<size_t>(grp.y + t) * b_bytes, b_bytes, fb);
+            if (++stage == a.stages) { stage = 0; phase ^= 1u; }
+            continue;
+          }
+          ptx::mbar_arrive_expect_tx(fb, stage_bytes);
           ptx::tma_load_4d(sa, &a.maps[tap.x], fb, tap.w, tc.x0 + tap.z, tc.y0 + tap.y, tc.n);
           if (!a.resident)
             ptx::bulk_load(sa + kATileBytes, a.w + static_cast<size_t>(grp.y + t) * b_bytes, b_bytes, fb);
           if (++stage == a.stages) { stage = 0; phase ^= 1u; }
         }
       }
+      if (prof && blockIdx.x == 0)
+        printf("tc-prof producer: total %lld cyc, %lld taps, wait(empty) %lld\n", clock64() - p_t0, p_n, p_wait);
+      (void)p_issue;
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
@@ -257,6 +282,8 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc_kernel(const __grid_co
       int it = 0;
       int cur_g = -1;
       uint32_t gcount = 0;
+      const bool prof = (a.debug & 32) != 0;
+      long long m_wfull = 0, m_wtmem = 0, m_issue = 0, m_commit = 0, m_n = 0, m_t0 = clock64();
       for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++it) {
         const TileCoord tc = decode_tile(a, tile);
         const int4 grp = grp_in_smem ? grp_s[tc.g] : __ldg(a.group_tab + tc.g);
@@ -267,21 +294,29 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc_kernel(const __grid_co
         }
         const int buf = it & 1;
         const uint32_t bphase = (it >> 1) & 1;
+        long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+        if (prof) c0 = clock64();
         ptx::mbar_wait(tempty_bar + 8 * buf, bphase ^ 1u);
         ptx::tc_fence_after();
+        if (prof) m_wtmem += clock64() - c0;
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * a.nt);
         for (int t = 0; t < grp.z; ++t) {
+          if (prof) c0 = clock64();
           ptx::mbar_wait(full_bar + 8 * stage, phase);
           ptx::tc_fence_after();
+          if (prof) c1 = clock64();
           const uint32_t sa = stage_base + stage * stage_bytes;
           const uint64_t adesc = ptx::make_sw128_desc(sa, 16, 1024);
           const uint64_t bdesc = ptx::make_sw128_desc(a.resident ? res_base + t * b_bytes : sa + kATileBytes, 16, 1024);
 #pragma unroll
           for (int k = 0; k < kKc / 16; ++k) {
+            if (a.debug & 8) break;
             // advancing K by 16 bf16 = 32 bytes = 2 descriptor address units
             ptx::mma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (t | k) != 0);
           }
+          if (prof) c2 = clock64();
           ptx::mma_commit(empty_bar + 8 * stage);
+          if (prof) { c3 = clock64(); m_wfull += c1 - c0; m_issue += c2 - c1; m_commit += c3 - c2; ++m_n; }
           if (++stage == a.stages) { stage = 0; phase ^= 1u; }
         }
         ptx::mma_commit(tfull_bar + 8 * buf);
@@ -290,6 +325,9 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc_kernel(const __grid_co
           if (next >= tile_end || decode_tile(a, next).g != cur_g) ptx::mma_commit(bres_empty);
         }
       }
+      if (prof && blockIdx.x == 0)
+        printf("tc-prof mma: total %lld cyc, %lld taps, %d tiles, wait(full) %lld, issue %lld, commit %lld, wait(tmem) %lld\n",
+               clock64() - m_t0, m_n, it, m_wfull, m_issue, m_commit, m_wtmem);
     }
   } else {
     // ===================== epilogue (4 warps, one TMEM lane quarter each) =====================
@@ -297,10 +335,12 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc_kernel(const __grid_co
     const int egroup = (warp - 2) >> 2;          // drains TMEM buffer `egroup` (tiles with it&1 == egroup)
     const int row = quarter * 32 + lane;
     const int ry = row >> a.bw_shift, rx = row & (a.bw - 1);
-    const float slope = (a.epi & (VSR_EPI_PRELU | VSR_EPI_PRELU_BWD)) ? __ldg(a.slope) : 0.f;
+    const float slope = (epi & (VSR_EPI_PRELU | VSR_EPI_PRELU_BWD)) ? __ldg(a.slope) : 0.f;
     const float inv_slope = slope != 0.f ? 1.f / slope : 0.f;
     float slope_acc = 0.f;
     int it = 0;
+    const bool prof = (a.debug & 32) != 0;
+    long long e_wait = 0, e_work = 0, e_t0 = clock64(), e_ld = 0, e_math = 0, e_st = 0;
     for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++it) {
       if ((it & 1) != egroup) continue;
       const TileCoord tc = decode_tile(a, tile);
@@ -311,11 +351,16 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc_kernel(const __grid_co
       const bool valid = (y < a.H) && (x < a.W);
       const size_t rowoff =
           ((static_cast<size_t>(tc.n) * a.H + y) * a.W + x) * static_cast<size_t>(a.Cout) + grp.x;
+      long long ec0 = 0, ec1 = 0;
+      if (prof) ec0 = clock64();
       ptx::mbar_wait(tfull_bar + 8 * buf, bphase);
       ptx::tc_fence_after();
+      if (prof) { ec1 = clock64(); e_wait += ec1 - ec0; }
       const uint32_t taddr =
           tmem_base + static_cast<uint32_t>(buf * a.nt) + (static_cast<uint32_t>(quarter * 32) << 16);
-      if ((a.nt & 63) == 0) {
+      if (a.debug & 1) {
+        // attribution run: no epilogue work
+      } else if ((a.nt & 63) == 0) {
         // ---- v2: 64 columns at a time, coalesced global traffic through the staging tile ----
         const uint32_t stg = stg_base + (warp - 2) * kStageTileBytes;
         size_t ro[8];
@@ -330,6 +375,8 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc_kernel(const __grid_co
         }
         for (int c = 0; c < a.nt; c += 64) {
           float v[64];
+          long long q0 = 0, q1 = 0, q2 = 0;
+          if (prof) q0 = clock64();
           {
             uint32_t r[64];
             ptx::tmem_ld64(taddr + c, r);
@@ -337,7 +384,8 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc_kernel(const __grid_co
 #pragma unroll
             for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
           }
-          if (a.epi & VSR_EPI_BIAS) {
+          if (prof) q1 = clock64();
+          if (epi & VSR_EPI_BIAS) {
             const float4* bp = bias_in_smem ? reinterpret_cast<const float4*>(bias_s + grp.x + c)
                                             : reinterpret_cast<const float4*>(a.bias + grp.x + c);
 #pragma unroll
@@ -346,28 +394,28 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc_kernel(const __grid_co
               v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
             }
           }
-          if (a.epi & VSR_EPI_SCALE) {
+          if (epi & VSR_EPI_SCALE) {
 #pragma unroll
             for (int i = 0; i < 64; ++i) v[i] *= a.out_scale;
           }
-          if (a.epi & VSR_EPI_RES_PRE) {
+          if (epi & VSR_EPI_RES_PRE) {
             float f[64];
             load_rows64(a.residual, ro, vmask, c, stg, lane, f);
 #pragma unroll
             for (int i = 0; i < 64; ++i) v[i] += f[i];
           }
-          if (a.epi & VSR_EPI_PRELU) {
+          if (epi & VSR_EPI_PRELU) {
 #pragma unroll
             for (int i = 0; i < 64; ++i) v[i] = v[i] > 0.f ? v[i] : slope * v[i];
           }
-          if (a.epi & VSR_EPI_RELU) {
+          if (epi & VSR_EPI_RELU) {
 #pragma unroll
             for (int i = 0; i < 64; ++i) v[i] = fmaxf(v[i], 0.f);
           }
-          if (a.epi & (VSR_EPI_PRELU_BWD | VSR_EPI_RELU_BWD)) {
+          if (epi & (VSR_EPI_PRELU_BWD | VSR_EPI_RELU_BWD)) {
             float f[64];
             load_rows64(a.aux_y, ro, vmask, c, stg, lane, f);
-            if (a.epi & VSR_EPI_PRELU_BWD) {
+            if (epi & VSR_EPI_PRELU_BWD) {
 #pragma unroll
               for (int i = 0; i < 64; ++i) {
                 const bool pos = f[i] > 0.f;
@@ -379,8 +427,10 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc_kernel(const __grid_co
               for (int i = 0; i < 64; ++i) v[i] = f[i] > 0.f ? v[i] : 0.f;
             }
           }
-          store_rows64(a.out, ro, vmask, c, stg, lane, v);
-          if (a.epi & VSR_EPI_OUT2) {
+          if (prof) q2 = clock64();
+          store_rows64(a.out, ro, (a.debug & 16) ? 0u : vmask, c, stg, lane, v);
+          if (prof) { e_ld += q1 - q0; e_math += q2 - q1; e_st += clock64() - q2; }
+          if (epi & VSR_EPI_OUT2) {
             float f[64];
             load_rows64(a.res2, ro, vmask, c, stg, lane, f);
 #pragma unroll
@@ -397,7 +447,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc_kernel(const __grid_co
           float v[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-          if (a.epi & VSR_EPI_BIAS) {
+          if (epi & VSR_EPI_BIAS) {
             const float4* bp = reinterpret_cast<const float4*>(a.bias + grp.x + c);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -405,11 +455,11 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc_kernel(const __grid_co
               v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
             }
           }
-          if (a.epi & VSR_EPI_SCALE) {
+          if (epi & VSR_EPI_SCALE) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] *= a.out_scale;
           }
-          if (a.epi & VSR_EPI_RES_PRE) {
+          if (epi & VSR_EPI_RES_PRE) {
             const uint4* rp = reinterpret_cast<const uint4*>(a.residual + rowoff + c);
             float f[16];
             unpack8(__ldg(rp), f);
@@ -417,20 +467,20 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc_kernel(const __grid_co
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] += f[i];
           }
-          if (a.epi & VSR_EPI_PRELU) {
+          if (epi & VSR_EPI_PRELU) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.f ? v[i] : slope * v[i];
           }
-          if (a.epi & VSR_EPI_RELU) {
+          if (epi & VSR_EPI_RELU) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
           }
-          if (a.epi & (VSR_EPI_PRELU_BWD | VSR_EPI_RELU_BWD)) {
+          if (epi & (VSR_EPI_PRELU_BWD | VSR_EPI_RELU_BWD)) {
             const uint4* yp = reinterpret_cast<const uint4*>(a.aux_y + rowoff + c);
             float f[16];
             unpack8(__ldg(yp), f);
             unpack8(__ldg(yp + 1), f + 8);
-            if (a.epi & VSR_EPI_PRELU_BWD) {
+            if (epi & VSR_EPI_PRELU_BWD) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
                 const bool pos = f[i] > 0.f;
@@ -445,7 +495,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc_kernel(const __grid_co
           uint4* op = reinterpret_cast<uint4*>(a.out + rowoff + c);
           op[0] = pack8(v);
           op[1] = pack8(v + 8);
-          if (a.epi & VSR_EPI_OUT2) {
+          if (epi & VSR_EPI_OUT2) {
             const uint4* rp = reinterpret_cast<const uint4*>(a.res2 + rowoff + c);
             float f[16];
             unpack8(__ldg(rp), f);
@@ -460,8 +510,11 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc_kernel(const __grid_co
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(tempty_bar + 8 * buf);
+      if (prof) e_work += clock64() - ec1;
     }
-    if (a.epi & VSR_EPI_PRELU_BWD) {
+    if (prof && blockIdx.x == 0 && lane == 0 && (warp == 2 || warp == 6))
+      printf("tc-prof epilogue warp %d: total %lld cyc, wait(tfull) %lld, work %lld (tmem-ld %lld, math %lld, store %lld)\n", warp, clock64() - e_t0, e_wait, e_work, e_ld, e_math, e_st);
+    if (epi & VSR_EPI_PRELU_BWD) {
       slope_acc = warp_sum(slope_acc);
       if (lane == 0) red[warp - 2] = slope_acc;
       asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -581,21 +634,44 @@ void pick_box(int h, int w, int* bw_out, int* bh_out) {
 int get_src_map_pub(const VsrTensor4& t, int bw, int bh, CUtensorMap* out) { return get_src_map(t, bw, bh, out); }
 void pick_box_pub(int h, int w, int* bw, int* bh) { pick_box(h, w, bw, bh); }
 
+int tapgemm_tc2_launch(const VsrTapGemmDesc* d, cudaStream_t stream);   // tapgemm_tc2.cu
+
 int tapgemm_tc_launch(const VsrTapGemmDesc* d, cudaStream_t stream) {
+  {
+    // second-generation kernel for every shape it covers; VSR_TC_V1=1 keeps this one (A/B timing)
+    const char* env_v1 = getenv("VSR_TC_V1");
+    if (!(env_v1 && env_v1[0] == '1') && d->kc == kKc && d->nt >= 64 && d->nt <= 256 && d->nt % 64 == 0 &&
+        d->out.c >= 64)
+      return tapgemm_tc2_launch(d, stream);
+  }
   VSR_CHECK_SUPPORTED(d->kc == kKc, "tapgemm(bf16): kc must be 64, got %d", d->kc);
   VSR_CHECK_SUPPORTED(d->nt >= 16 && d->nt <= 256 && d->nt % 16 == 0,
                       "tapgemm(bf16): nt must be a multiple of 16 in [16,256], got %d", d->nt);
   VSR_CHECK_ARG(d->out.c % 8 == 0, "tapgemm(bf16): out.c must be a multiple of 8");
+  typedef void (*KernelFn)(const TcArgs);
+  static const struct { int epi; KernelFn fn; } kVariants[] = {
+      {-1, tapgemm_tc_kernel<-1>},
+      {0, tapgemm_tc_kernel<0>},
+      {VSR_EPI_BIAS, tapgemm_tc_kernel<VSR_EPI_BIAS>},
+      {VSR_EPI_RES_PRE, tapgemm_tc_kernel<VSR_EPI_RES_PRE>},
+      {VSR_EPI_BIAS | VSR_EPI_PRELU, tapgemm_tc_kernel<VSR_EPI_BIAS | VSR_EPI_PRELU>},
+      {VSR_EPI_PRELU_BWD, tapgemm_tc_kernel<VSR_EPI_PRELU_BWD>},
+      {VSR_EPI_PRELU_BWD | VSR_EPI_RES_PRE, tapgemm_tc_kernel<VSR_EPI_PRELU_BWD | VSR_EPI_RES_PRE>},
+  };
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
-    if (e != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(smem) failed: %s", cudaGetErrorString(e));
-      return VSR_ERR_CUDA;
+    for (const auto& v : kVariants) {
+      cudaError_t e = cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+      if (e != cudaSuccess) {
+        set_error("cudaFuncSetAttribute(smem) failed: %s", cudaGetErrorString(e));
+        return VSR_ERR_CUDA;
+      }
     }
     attr_set = true;
   }
+  KernelFn kernel = kVariants[0].fn;
+  for (const auto& v : kVariants)
+    if (v.epi == d->epi) kernel = v.fn;
   TcArgs a;
   memset(&a, 0, sizeof(a));
   int bw, bh;
@@ -638,6 +714,13 @@ int tapgemm_tc_launch(const VsrTapGemmDesc* d, cudaStream_t stream) {
   static const char* env_stg = getenv("VSR_TC_STAGES");
   static const char* env_grid = getenv("VSR_TC_GRID");
   if (!(env_res && env_res[0] == '1')) a.resident = 0;   // opt-in: measured no gain (profiles/README.md)
+  {
+    const char* env_dbg = getenv("VSR_TC_DEBUG");            // re-read per launch: attribution sweeps flip it
+    a.debug = env_dbg ? atoi(env_dbg) : 0;
+    const char* env_res2 = getenv("VSR_TC_RESIDENT2");
+    if (env_res2 && env_res2[0] == '1' && d->max_group_taps > 0 &&
+        res_need <= kSmemBudget - kCtrlBytes - 4 * kATileBytes) a.resident = 1;
+  }
   a.res_bytes = a.resident ? (int)res_need : 0;
   const int stage_bytes = a.resident ? kATileBytes : kATileBytes + b_bytes;
   int stages = (kSmemBudget - kCtrlBytes - a.res_bytes) / stage_bytes;
@@ -650,7 +733,7 @@ int tapgemm_tc_launch(const VsrTapGemmDesc* d, cudaStream_t stream) {
   if (env_grid && atoi(env_grid) >= 1) grid = atoi(env_grid);
   if (grid > a.num_tiles) grid = a.num_tiles;
   if (grid > kPartialsLen) grid = kPartialsLen;
-  tapgemm_tc_kernel<<<grid, kThreads, smem, stream>>>(a);
+  kernel<<<grid, kThreads, smem, stream>>>(a);
   VSR_CHECK_LAUNCH("tapgemm_tc");
   return VSR_OK;
 }

@@ -1,0 +1,642 @@
+// tapgemm_tc2.cu — bf16 tap-GEMM on tcgen05 tensor cores (sm_100a), second generation.
+//
+// Same contract as tapgemm_tc.cu (include/vsr_b200.h, vsr_tapgemm) for nt % 64 == 0.  What changed
+// and why (profiles/r01_attrib_*.log): with ~227 KB of shared memory per CTA the L1 is gone, so every
+// local-memory access (spilled registers, address arrays) and every plain global load in the epilogue
+// was an L2 round trip; the epilogue, not the tensor pipe or HBM, bounded the kernel.  Here
+//   * the kernel is specialised on the epilogue flag set (no dead variants in the instruction stream),
+//   * four epilogue warps keep everything in registers (192 threads -> up to 255 registers each),
+//   * outputs leave through TMA stores from a 128B-swizzled staging tile (no address arithmetic, no
+//     predicates: the TMA unit clips partial tiles), epilogue operands (residual, saved activation,
+//     second residual) arrive through TMA loads that are issued one 64-channel chunk ahead,
+//   * the bias of up to 1024 output channels is staged in shared memory once per CTA.
+// Producer / MMA roles, the tap and group tables, the weight-slab format and the optional
+// weight-resident mode are those of the first kernel.
+//
+// Replaces aten.convolution / convolution_backward(data) under drf_net.py:55-106,141-147.
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "ptx_sm100.cuh"
+
+namespace vsr {
+
+int get_src_map_pub(const VsrTensor4& t, int bw, int bh, CUtensorMap* out);   // tapgemm_tc.cu
+void pick_box_pub(int h, int w, int* bw, int* bh);
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kKc = 64;                       // bf16 channels per tap = one 128-byte row
+constexpr int kATileBytes = kBlockM * 128;    // 16 KiB
+constexpr int kMaxStages = 8;
+constexpr int kSmemBudget = 227 * 1024;
+constexpr int kEpiWarps = 4;
+constexpr int kTileBytes = 4096;              // epilogue tile: 32 pixels x 64 channels bf16
+constexpr int kMaxSmemGroups = 48;            // group table rows cached in smem (16 B each, ctrl[256..1024))
+constexpr int kMaxSmemTaps = 256;             // packed tap entries cached in smem (4 B each)
+constexpr int kBiasFloats = 1024;
+constexpr int kCtrlBytes = 1024 + kMaxSmemTaps * 4 + kBiasFloats * 4;   // 6 KiB, keeps 1024-byte alignment
+constexpr int kTmemCols = 512;
+constexpr int kThreads = 64 + 32 * kEpiWarps;  // warp0 TMA, warp1 MMA, warps 2-5 epilogue
+
+constexpr int kEpiIn = VSR_EPI_RES_PRE | VSR_EPI_PRELU_BWD | VSR_EPI_RELU_BWD | VSR_EPI_OUT2;
+
+struct Tc2Args {
+  CUtensorMap maps[VSR_MAX_SRCS];
+  CUtensorMap out_map, res_map, aux_map, out2_map, res2_map;
+  const int4* tap_tab;
+  const int4* group_tab;
+  const uint8_t* w;
+  const float* bias;
+  const float* slope;
+  float* slope_partials;
+  float out_scale;
+  int epi;
+  int nt, n_groups;
+  int N, H, W, Cout;
+  int bw, bh, tiles_x, tiles_y;
+  int bw_shift;            // bw is a power of two
+  int num_tiles;
+  int stages;
+  int n_taps_total;
+  int resident;            // 1: the current group's weight slabs stay in smem across tiles
+  int res_bytes;           // size of the resident weight region
+  int epi_bytes;           // size of the epilogue tile region
+  int m_tiles;             // pixel tiles per group
+  int debug;               // timing-attribution switches (VSR_TC_DEBUG); results are wrong when non-zero
+};
+
+// tap entry packed into 32 bits: src[0:4) | dy+8 [4:8) | dx+8 [8:12) | c0/8 [12:32)
+__device__ __forceinline__ uint32_t pack_tap(const int4& t) {
+  return (uint32_t)t.x | ((uint32_t)(t.y + 8) << 4) | ((uint32_t)(t.z + 8) << 8) | ((uint32_t)(t.w >> 3) << 12);
+}
+__device__ __forceinline__ int4 unpack_tap(uint32_t p) {
+  return make_int4((int)(p & 15u), (int)((p >> 4) & 15u) - 8, (int)((p >> 8) & 15u) - 8, (int)(p >> 12) << 3);
+}
+
+struct TileCoord {
+  int g, n, y0, x0;
+};
+
+// non-resident: groups vary fastest (concurrent CTAs share A tiles in L2);
+// resident: group-major, every CTA walks a contiguous tile range (the group rarely changes).
+__device__ __forceinline__ TileCoord decode_tile(const Tc2Args& a, int tile) {
+  TileCoord t;
+  int mt;
+  if (a.resident) {
+    t.g = tile / a.m_tiles;
+    mt = tile - t.g * a.m_tiles;
+  } else {
+    t.g = tile % a.n_groups;
+    mt = tile / a.n_groups;
+  }
+  const int tx = mt % a.tiles_x;
+  mt /= a.tiles_x;
+  const int ty = mt % a.tiles_y;
+  t.n = mt / a.tiles_y;
+  t.x0 = tx * a.bw;
+  t.y0 = ty * a.bh;
+  return t;
+}
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+// 128B-swizzled [32 pixels x 64 channels] tile (the TMA SWIZZLE_128B image): 16-byte chunk q of row r
+__device__ __forceinline__ uint32_t tile_addr(uint32_t base, int r, int q) {
+  return base + r * 128 + ((q ^ (r & 7)) << 4);
+}
+__device__ __forceinline__ void tma_store_4d(const void* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::
+                   "l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// FIXED_EPI >= 0: the epilogue flag set is a compile-time constant; FIXED_EPI < 0: read from the arguments.
+template <int FIXED_EPI>
+__global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_constant__ Tc2Args a) {
+  const int epi = FIXED_EPI >= 0 ? FIXED_EPI : a.epi;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = ptx::smem_u32(smem_raw);
+  uint8_t* smem_gen = smem_raw;
+  if (smem_base & 1023u) __trap();             // the swizzled tiles need a 1024-byte aligned window
+
+  // control block
+  const uint32_t full_bar = smem_base;                     // kMaxStages x 8 B
+  const uint32_t empty_bar = smem_base + 64;               // kMaxStages x 8 B
+  const uint32_t tfull_bar = smem_base + 128;              // 2 x 8 B
+  const uint32_t tempty_bar = smem_base + 144;             // 2 x 8 B
+  const uint32_t tmem_slot = smem_base + 160;              // u32
+  const uint32_t bres_full = smem_base + 168, bres_empty = smem_base + 176;
+  const uint32_t in_bar0 = smem_base + 184;                // kEpiWarps x 8 B
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + 160);
+  float* red = reinterpret_cast<float*>(smem_gen + 224);   // kEpiWarps floats
+  int4* grp_s = reinterpret_cast<int4*>(smem_gen + 256);        // group table (<= 48 rows)
+  uint32_t* tap_s = reinterpret_cast<uint32_t*>(smem_gen + 1024);   // packed tap table (<= 256 entries)
+  float* bias_s = reinterpret_cast<float*>(smem_gen + 1024 + kMaxSmemTaps * 4);   // bias when Cout <= 1024
+  const uint32_t epi_base = smem_base + kCtrlBytes;        // epilogue tiles
+  const uint32_t res_base = epi_base + a.epi_bytes;        // resident weight slabs (resident mode)
+  const uint32_t stage_base = res_base + a.res_bytes;
+  const bool grp_in_smem = a.n_groups <= kMaxSmemGroups;
+  const bool taps_in_smem = a.n_taps_total <= kMaxSmemTaps;
+  if (grp_in_smem)
+    for (int i = threadIdx.x; i < a.n_groups; i += blockDim.x) grp_s[i] = __ldg(a.group_tab + i);
+  if (taps_in_smem)
+    for (int i = threadIdx.x; i < a.n_taps_total; i += blockDim.x) tap_s[i] = pack_tap(__ldg(a.tap_tab + i));
+  const bool bias_in_smem = (epi & VSR_EPI_BIAS) && a.Cout <= kBiasFloats;
+  if (bias_in_smem)
+    for (int i = threadIdx.x; i < a.Cout; i += blockDim.x) bias_s[i] = __ldg(a.bias + i);
+  const uint32_t b_bytes = static_cast<uint32_t>(a.nt) * 128u;
+  const uint32_t stage_bytes = a.resident ? kATileBytes : kATileBytes + b_bytes;
+  // tile walk of this CTA
+  const int tile_begin = a.resident ? (int)((long)a.num_tiles * blockIdx.x / gridDim.x) : (int)blockIdx.x;
+  const int tile_end = a.resident ? (int)((long)a.num_tiles * (blockIdx.x + 1) / gridDim.x) : a.num_tiles;
+  const int tile_step = a.resident ? 1 : (int)gridDim.x;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const bool prof = (a.debug & 32) != 0;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < a.stages; ++s) {
+      ptx::mbar_init(full_bar + 8 * s, 1);
+      ptx::mbar_init(empty_bar + 8 * s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(tfull_bar + 8 * b, 1);
+      ptx::mbar_init(tempty_bar + 8 * b, kEpiWarps);
+    }
+    ptx::mbar_init(bres_full, 1);
+    ptx::mbar_init(bres_empty, 1);
+    for (int w = 0; w < kEpiWarps; ++w) ptx::mbar_init(in_bar0 + 8 * w, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int cur_g = -1;
+      uint32_t gcount = 0;
+      long long p_wait = 0, p_n = 0, p_t0 = clock64();
+      for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
+        const TileCoord tc = decode_tile(a, tile);
+        const int4 grp = grp_in_smem ? grp_s[tc.g] : __ldg(a.group_tab + tc.g);
+        if (a.resident && tc.g != cur_g) {
+          // (re)load this group's weight slabs once all MMAs of the previous group are done
+          ptx::mbar_wait(bres_empty, (gcount & 1u) ^ 1u);
+          ptx::mbar_arrive_expect_tx(bres_full, static_cast<uint32_t>(grp.z) * b_bytes);
+          for (int t = 0; t < grp.z; ++t)
+            ptx::bulk_load(res_base + t * b_bytes, a.w + static_cast<size_t>(grp.y + t) * b_bytes, b_bytes, bres_full);
+          cur_g = tc.g;
+          ++gcount;
+        }
+        for (int t = 0; t < grp.z; ++t) {
+          const int4 tap = taps_in_smem ? unpack_tap(tap_s[grp.y + t]) : __ldg(a.tap_tab + grp.y + t);
+          long long c0 = 0;
+          if (prof) c0 = clock64();
+          ptx::mbar_wait(empty_bar + 8 * stage, phase ^ 1u);
+          if (prof) { p_wait += clock64() - c0; ++p_n; }
+          const uint32_t fb = full_bar + 8 * stage;
+          const uint32_t sa = stage_base + stage * stage_bytes;
+          if (a.debug & 6) {
+            // attribution runs: skip the A (2) and/or B (4) transfer, keep the barrier protocol
+            uint32_t tx = 0;
+            if (!(a.debug & 2)) tx += kATileBytes;
+            if (!(a.debug & 4) && !a.resident) tx += b_bytes;
+            if (tx == 0) { ptx::mbar_arrive(fb); } else { ptx::mbar_arrive_expect_tx(fb, tx); }
+            if (!(a.debug & 2)) ptx::tma_load_4d(sa, &a.maps[tap.x], fb, tap.w, tc.x0 + tap.z, tc.y0 + tap.y, tc.n);
+            if (!(a.debug & 4) && !a.resident)
+              ptx::bulk_load(sa + kATileBytes, a.w + static_cast<size_t>(grp.y + t) * b_bytes, b_bytes, fb);
+          } else {
+            ptx::mbar_arrive_expect_tx(fb, stage_bytes);
+            ptx::tma_load_4d(sa, &a.maps[tap.x], fb, tap.w, tc.x0 + tap.z, tc.y0 + tap.y, tc.n);
+            if (!a.resident)
+              ptx::bulk_load(sa + kATileBytes, a.w + static_cast<size_t>(grp.y + t) * b_bytes, b_bytes, fb);
+          }
+          if (++stage == a.stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+      if (prof && blockIdx.x == 0)
+        printf("tc2-prof producer: total %lld cyc, %lld taps, wait(empty) %lld\n", clock64() - p_t0, p_n, p_wait);
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      const uint32_t idesc = ptx::make_idesc_bf16(kBlockM, a.nt, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      int cur_g = -1;
+      uint32_t gcount = 0;
+      long long m_wfull = 0, m_wtmem = 0, m_issue = 0, m_n = 0, m_t0 = clock64();
+      for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++it) {
+        const TileCoord tc = decode_tile(a, tile);
+        const int4 grp = grp_in_smem ? grp_s[tc.g] : __ldg(a.group_tab + tc.g);
+        if (a.resident && tc.g != cur_g) {
+          ptx::mbar_wait(bres_full, gcount & 1u);
+          cur_g = tc.g;
+          ++gcount;
+        }
+        const int buf = it & 1;
+        const uint32_t bphase = (it >> 1) & 1;
+        long long c0 = 0, c1 = 0;
+        if (prof) c0 = clock64();
+        ptx::mbar_wait(tempty_bar + 8 * buf, bphase ^ 1u);
+        ptx::tc_fence_after();
+        if (prof) m_wtmem += clock64() - c0;
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * a.nt);
+        for (int t = 0; t < grp.z; ++t) {
+          if (prof) c0 = clock64();
+          ptx::mbar_wait(full_bar + 8 * stage, phase);
+          ptx::tc_fence_after();
+          if (prof) c1 = clock64();
+          const uint32_t sa = stage_base + stage * stage_bytes;
+          const uint64_t adesc = ptx::make_sw128_desc(sa, 16, 1024);
+          const uint64_t bdesc = ptx::make_sw128_desc(a.resident ? res_base + t * b_bytes : sa + kATileBytes, 16, 1024);
+          if (!(a.debug & 8)) {
+#pragma unroll
+            for (int k = 0; k < kKc / 16; ++k) {
+              // advancing K by 16 bf16 = 32 bytes = 2 descriptor address units
+              ptx::mma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (t | k) != 0);
+            }
+          }
+          ptx::mma_commit(empty_bar + 8 * stage);
+          if (prof) { m_wfull += c1 - c0; m_issue += clock64() - c1; ++m_n; }
+          if (++stage == a.stages) { stage = 0; phase ^= 1u; }
+        }
+        ptx::mma_commit(tfull_bar + 8 * buf);
+        if (a.resident) {
+          const int next = tile + tile_step;
+          if (next >= tile_end || decode_tile(a, next).g != cur_g) ptx::mma_commit(bres_empty);
+        }
+      }
+      if (prof && blockIdx.x == 0)
+        printf("tc2-prof mma: total %lld cyc, %lld taps, %d tiles, wait(full) %lld, issue+commit %lld, wait(tmem) %lld\n",
+               clock64() - m_t0, m_n, it, m_wfull, m_issue, m_wtmem);
+    }
+  } else {
+    // ===================== epilogue (4 warps, one TMEM lane quarter each) =====================
+    const int ew = warp - 2;
+    const int quarter = warp & 3;                 // TMEM lanes [32*quarter, 32*quarter+32) = tile pixels
+    // this warp's 32 pixels as a sub-box of the bw x bh tile (the epilogue maps have box ew x eh)
+    const int sub_x = (quarter * 32) & (a.bw - 1);
+    const int sub_y = (quarter * 32) >> a.bw_shift;
+    const bool skip = (a.debug & 1) != 0;
+    const bool has_in = (epi & kEpiIn) != 0 && !skip;
+    const int n_in = ((epi & VSR_EPI_RES_PRE) ? 1 : 0) + ((epi & (VSR_EPI_PRELU_BWD | VSR_EPI_RELU_BWD)) ? 1 : 0) +
+                     ((epi & VSR_EPI_OUT2) ? 1 : 0);
+    const uint32_t out_t = epi_base + ew * (1 + n_in) * kTileBytes;
+    uint32_t nxt = out_t + kTileBytes;
+    const uint32_t res_t = nxt;
+    if (epi & VSR_EPI_RES_PRE) nxt += kTileBytes;
+    const uint32_t aux_t = nxt;
+    if (epi & (VSR_EPI_PRELU_BWD | VSR_EPI_RELU_BWD)) nxt += kTileBytes;
+    const uint32_t res2_t = nxt;
+    const uint32_t in_bar = in_bar0 + 8 * ew;
+    uint32_t in_phase = 0;
+    const float slope = (epi & (VSR_EPI_PRELU | VSR_EPI_PRELU_BWD)) ? __ldg(a.slope) : 0.f;
+    const float inv_slope = slope != 0.f ? 1.f / slope : 0.f;
+    float slope_acc = 0.f;
+    long long e_wait = 0, e_in = 0, e_ld = 0, e_math = 0, e_st = 0, e_t0 = clock64();
+
+    // one elected lane fetches the epilogue operands of a 64-channel chunk through TMA
+    auto issue_in = [&](int n, int y0, int x0, int c0) {
+      ptx::mbar_arrive_expect_tx(in_bar, static_cast<uint32_t>(n_in) * kTileBytes);
+      if (epi & VSR_EPI_RES_PRE) ptx::tma_load_4d(res_t, &a.res_map, in_bar, c0, x0 + sub_x, y0 + sub_y, n);
+      if (epi & (VSR_EPI_PRELU_BWD | VSR_EPI_RELU_BWD))
+        ptx::tma_load_4d(aux_t, &a.aux_map, in_bar, c0, x0 + sub_x, y0 + sub_y, n);
+      if (epi & VSR_EPI_OUT2) ptx::tma_load_4d(res2_t, &a.res2_map, in_bar, c0, x0 + sub_x, y0 + sub_y, n);
+    };
+    auto issue_next_in = [&](int tile, int c, const TileCoord& tc, int o0) {
+      if (c + 64 < a.nt) {
+        issue_in(tc.n, tc.y0, tc.x0, o0 + c + 64);
+      } else if (tile + tile_step < tile_end) {
+        const TileCoord t2 = decode_tile(a, tile + tile_step);
+        const int4 g2 = grp_in_smem ? grp_s[t2.g] : __ldg(a.group_tab + t2.g);
+        issue_in(t2.n, t2.y0, t2.x0, g2.x);
+      }
+    };
+
+    if (has_in && lane == 0 && tile_begin < tile_end) {
+      const TileCoord t0 = decode_tile(a, tile_begin);
+      const int4 g0 = grp_in_smem ? grp_s[t0.g] : __ldg(a.group_tab + t0.g);
+      issue_in(t0.n, t0.y0, t0.x0, g0.x);
+    }
+    int it = 0;
+    for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++it) {
+      const TileCoord tc = decode_tile(a, tile);
+      const int4 grp = grp_in_smem ? grp_s[tc.g] : __ldg(a.group_tab + tc.g);
+      const int buf = it & 1;
+      const uint32_t bphase = (it >> 1) & 1;
+      long long q0 = 0, q1 = 0;
+      if (prof) q0 = clock64();
+      ptx::mbar_wait(tfull_bar + 8 * buf, bphase);
+      ptx::tc_fence_after();
+      if (prof) e_wait += clock64() - q0;
+      const uint32_t taddr =
+          tmem_base + static_cast<uint32_t>(buf * a.nt) + (static_cast<uint32_t>(quarter * 32) << 16);
+      if (!skip) {
+#pragma unroll 1
+        for (int c = 0; c < a.nt; c += 64) {
+          if (prof) q0 = clock64();
+          if (has_in) {
+            ptx::mbar_wait(in_bar, in_phase);
+            in_phase ^= 1u;
+          }
+          if (prof) { q1 = clock64(); e_in += q1 - q0; }
+          float v[64];
+          {
+            uint32_t r[64];
+            ptx::tmem_ld64(taddr + c, r);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
+          }
+          if (prof) { q0 = clock64(); e_ld += q0 - q1; }
+          if (epi & VSR_EPI_BIAS) {
+            if (bias_in_smem) {
+              const float4* bp = reinterpret_cast<const float4*>(bias_s + grp.x + c);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float4 b = bp[i];
+                v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+              }
+            } else {
+              const float4* bp = reinterpret_cast<const float4*>(a.bias + grp.x + c);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float4 b = __ldg(bp + i);
+                v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+              }
+            }
+          }
+          if (epi & VSR_EPI_SCALE) {
+#pragma unroll
+            for (int i = 0; i < 64; ++i) v[i] *= a.out_scale;
+          }
+          if (epi & VSR_EPI_RES_PRE) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint4 rq = ld_shared_v4(tile_addr(res_t, lane, j));
+              v[8 * j + 0] += bf16_lo(rq.x); v[8 * j + 1] += bf16_hi(rq.x);
+              v[8 * j + 2] += bf16_lo(rq.y); v[8 * j + 3] += bf16_hi(rq.y);
+              v[8 * j + 4] += bf16_lo(rq.z); v[8 * j + 5] += bf16_hi(rq.z);
+              v[8 * j + 6] += bf16_lo(rq.w); v[8 * j + 7] += bf16_hi(rq.w);
+            }
+          }
+          if (epi & VSR_EPI_PRELU) {
+#pragma unroll
+            for (int i = 0; i < 64; ++i) v[i] = v[i] > 0.f ? v[i] : slope * v[i];
+          }
+          if (epi & VSR_EPI_RELU) {
+#pragma unroll
+            for (int i = 0; i < 64; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
+          if (epi & (VSR_EPI_PRELU_BWD | VSR_EPI_RELU_BWD)) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint4 aq = ld_shared_v4(tile_addr(aux_t, lane, j));
+              const uint32_t w4[4] = {aq.x, aq.y, aq.z, aq.w};
+#pragma unroll
+              for (int h = 0; h < 4; ++h) {
+#pragma unroll
+                for (int p = 0; p < 2; ++p) {
+                  const float f = p ? bf16_hi(w4[h]) : bf16_lo(w4[h]);
+                  const int i = 8 * j + 2 * h + p;
+                  const bool pos = f > 0.f;
+                  if (epi & VSR_EPI_PRELU_BWD) {
+                    // out-of-image pixels read f = 0 from the TMA zero fill and contribute exactly 0
+                    slope_acc += pos ? 0.f : v[i] * (f * inv_slope);
+                    v[i] = pos ? v[i] : slope * v[i];
+                  } else {
+                    v[i] = pos ? v[i] : 0.f;
+                  }
+                }
+              }
+            }
+          }
+          if (has_in && !(epi & VSR_EPI_OUT2)) {
+            // the operand tiles have been consumed: fetch the next chunk's while this one is stored
+            __syncwarp();
+            if (lane == 0) issue_next_in(tile, c, tc, grp.x);
+          }
+          if (prof) { q1 = clock64(); e_math += q1 - q0; }
+          // the previous chunk's TMA store must have read the staging tile before it is rewritten
+          if (lane == 0) bulk_wait_read0();
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            uint4 o;
+            o.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+            o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+            o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+            o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+            st_shared_v4(tile_addr(out_t, lane, j), o);
+          }
+          if (epi & VSR_EPI_OUT2) {
+            // out2 = v + res2, staged in place of the res2 tile (every thread owns its row)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              uint4 o;
+              const uint4 sq = ld_shared_v4(tile_addr(res2_t, lane, j));
+              o.x = pack_bf16x2(v[8 * j + 0] + bf16_lo(sq.x), v[8 * j + 1] + bf16_hi(sq.x));
+              o.y = pack_bf16x2(v[8 * j + 2] + bf16_lo(sq.y), v[8 * j + 3] + bf16_hi(sq.y));
+              o.z = pack_bf16x2(v[8 * j + 4] + bf16_lo(sq.z), v[8 * j + 5] + bf16_hi(sq.z));
+              o.w = pack_bf16x2(v[8 * j + 6] + bf16_lo(sq.w), v[8 * j + 7] + bf16_hi(sq.w));
+              st_shared_v4(tile_addr(res2_t, lane, j), o);
+            }
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            if (!(a.debug & 16)) {
+              tma_store_4d(&a.out_map, out_t, grp.x + c, tc.x0 + sub_x, tc.y0 + sub_y, tc.n);
+              if (epi & VSR_EPI_OUT2)
+                tma_store_4d(&a.out2_map, res2_t, grp.x + c, tc.x0 + sub_x, tc.y0 + sub_y, tc.n);
+            }
+            bulk_commit();
+            if (epi & VSR_EPI_OUT2) {
+              // the res2 tile doubles as the out2 staging tile: refill it only after the store has read it
+              bulk_wait_read0();
+              issue_next_in(tile, c, tc, grp.x);
+            }
+          }
+          if (prof) e_st += clock64() - q1;
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(tempty_bar + 8 * buf);
+    }
+    if (lane == 0) bulk_wait0();                 // all output bytes are written before the CTA retires
+    if (prof && blockIdx.x == 0 && lane == 0 && ew < 2)
+      printf("tc2-prof epilogue warp %d: total %lld cyc, wait(tfull) %lld, operands %lld, tmem-ld %lld, math %lld, stage+store %lld\n",
+             warp, clock64() - e_t0, e_wait, e_in, e_ld, e_math, e_st);
+    if (epi & VSR_EPI_PRELU_BWD) {
+      slope_acc = warp_sum(slope_acc);
+      if (lane == 0) red[ew] = slope_acc;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (ew == 0 && lane == 0) a.slope_partials[blockIdx.x] = (red[0] + red[1]) + (red[2] + red[3]);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+template <int EPI>
+cudaError_t prepare() {
+  return cudaFuncSetAttribute(tapgemm_tc2_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+}
+
+}  // namespace
+
+int tapgemm_tc2_launch(const VsrTapGemmDesc* d, cudaStream_t stream) {
+  VSR_CHECK_SUPPORTED(d->kc == kKc, "tapgemm(bf16): kc must be 64, got %d", d->kc);
+  VSR_CHECK_SUPPORTED(d->nt >= 64 && d->nt <= 256 && d->nt % 64 == 0,
+                      "tapgemm(bf16, v2): nt must be a multiple of 64 in [64,256], got %d", d->nt);
+  VSR_CHECK_ARG(d->out.c % 8 == 0 && d->out.c >= 64, "tapgemm(bf16): out.c must be a multiple of 8 and >= 64");
+  typedef void (*KernelFn)(const Tc2Args);
+  static const struct { int epi; KernelFn fn; cudaError_t (*prep)(); } kVariants[] = {
+      {-1, tapgemm_tc2_kernel<-1>, prepare<-1>},
+      {0, tapgemm_tc2_kernel<0>, prepare<0>},
+      {VSR_EPI_BIAS, tapgemm_tc2_kernel<VSR_EPI_BIAS>, prepare<VSR_EPI_BIAS>},
+      {VSR_EPI_RES_PRE, tapgemm_tc2_kernel<VSR_EPI_RES_PRE>, prepare<VSR_EPI_RES_PRE>},
+      {VSR_EPI_BIAS | VSR_EPI_PRELU, tapgemm_tc2_kernel<VSR_EPI_BIAS | VSR_EPI_PRELU>, prepare<VSR_EPI_BIAS | VSR_EPI_PRELU>},
+      {VSR_EPI_BIAS | VSR_EPI_PRELU | VSR_EPI_OUT2, tapgemm_tc2_kernel<VSR_EPI_BIAS | VSR_EPI_PRELU | VSR_EPI_OUT2>,
+       prepare<VSR_EPI_BIAS | VSR_EPI_PRELU | VSR_EPI_OUT2>},
+      {VSR_EPI_PRELU_BWD, tapgemm_tc2_kernel<VSR_EPI_PRELU_BWD>, prepare<VSR_EPI_PRELU_BWD>},
+      {VSR_EPI_PRELU_BWD | VSR_EPI_RES_PRE, tapgemm_tc2_kernel<VSR_EPI_PRELU_BWD | VSR_EPI_RES_PRE>,
+       prepare<VSR_EPI_PRELU_BWD | VSR_EPI_RES_PRE>},
+  };
+  static bool attr_set = false;
+  if (!attr_set) {
+    for (const auto& v : kVariants) {
+      cudaError_t e = v.prep();
+      if (e != cudaSuccess) {
+        set_error("cudaFuncSetAttribute(smem) failed: %s", cudaGetErrorString(e));
+        return VSR_ERR_CUDA;
+      }
+    }
+    attr_set = true;
+  }
+  KernelFn kernel = kVariants[0].fn;
+  for (const auto& v : kVariants)
+    if (v.epi == d->epi) kernel = v.fn;
+
+  Tc2Args a;
+  memset(&a, 0, sizeof(a));
+  int bw, bh;
+  pick_box_pub(d->out.h, d->out.w, &bw, &bh);
+  for (int s = 0; s < d->n_srcs; ++s) {
+    VSR_CHECK_ARG(d->srcs[s].c % 8 == 0, "tapgemm(bf16): src channels must be a multiple of 8");
+    int rc = get_src_map_pub(d->srcs[s], bw, bh, &a.maps[s]);
+    if (rc != VSR_OK) return rc;
+  }
+  // epilogue tensors: one warp = 32 consecutive tile pixels = an ew x eh sub-box
+  const int ew = bw < 32 ? bw : 32, eh = 32 / ew;
+  {
+    int rc = get_src_map_pub(d->out, ew, eh, &a.out_map);
+    if (rc != VSR_OK) return rc;
+    VsrTensor4 t = d->out;
+    if (d->epi & VSR_EPI_RES_PRE) {
+      VSR_CHECK_ARG(d->residual != nullptr, "tapgemm: RES_PRE without residual");
+      t.ptr = const_cast<void*>(d->residual);
+      if ((rc = get_src_map_pub(t, ew, eh, &a.res_map)) != VSR_OK) return rc;
+    }
+    if (d->epi & (VSR_EPI_PRELU_BWD | VSR_EPI_RELU_BWD)) {
+      VSR_CHECK_ARG(d->aux_y != nullptr, "tapgemm: activation backward without aux_y");
+      t.ptr = const_cast<void*>(d->aux_y);
+      if ((rc = get_src_map_pub(t, ew, eh, &a.aux_map)) != VSR_OK) return rc;
+    }
+    if (d->epi & VSR_EPI_OUT2) {
+      VSR_CHECK_ARG(d->out2 != nullptr && d->res2 != nullptr, "tapgemm: OUT2 without out2/res2");
+      t.ptr = d->out2;
+      if ((rc = get_src_map_pub(t, ew, eh, &a.out2_map)) != VSR_OK) return rc;
+      t.ptr = const_cast<void*>(d->res2);
+      if ((rc = get_src_map_pub(t, ew, eh, &a.res2_map)) != VSR_OK) return rc;
+    }
+  }
+  a.tap_tab = reinterpret_cast<const int4*>(d->tap_tab);
+  a.group_tab = reinterpret_cast<const int4*>(d->group_tab);
+  a.w = static_cast<const uint8_t*>(d->w);
+  a.bias = d->bias;
+  a.slope = d->slope;
+  a.slope_partials = d->slope_partials;
+  a.out_scale = d->out_scale;
+  a.epi = d->epi;
+  a.nt = d->nt;
+  a.n_groups = d->n_groups;
+  a.N = d->out.n; a.H = d->out.h; a.W = d->out.w; a.Cout = d->out.c;
+  a.bw = bw; a.bh = bh;
+  a.bw_shift = 0;
+  while ((1 << a.bw_shift) < bw) ++a.bw_shift;
+  a.tiles_x = (a.W + bw - 1) / bw;
+  a.tiles_y = (a.H + bh - 1) / bh;
+  const long tiles = (long)a.n_groups * a.N * a.tiles_x * a.tiles_y;
+  VSR_CHECK_SUPPORTED(tiles < (1l << 30), "tapgemm(bf16): too many tiles");
+  a.num_tiles = (int)tiles;
+  a.n_taps_total = d->n_taps_total;
+  a.m_tiles = a.N * a.tiles_x * a.tiles_y;
+  const int n_in = ((d->epi & VSR_EPI_RES_PRE) ? 1 : 0) + ((d->epi & (VSR_EPI_PRELU_BWD | VSR_EPI_RELU_BWD)) ? 1 : 0) +
+                   ((d->epi & VSR_EPI_OUT2) ? 1 : 0);
+  a.epi_bytes = kEpiWarps * (1 + n_in) * kTileBytes;
+  const int b_bytes = d->nt * 128;
+  const long res_need = (long)d->max_group_taps * b_bytes;
+  const long avail = kSmemBudget - kCtrlBytes - a.epi_bytes;
+  // weight-resident mode: the group's slabs stay in smem and >= 3 A stages remain; worth it when the
+  // slabs are large next to the A tile (nt > 64) and every CTA sees few groups
+  a.resident = d->max_group_taps > 0 && d->nt > 64 && res_need <= avail - 3 * kATileBytes &&
+               tiles >= 2 * (long)num_sms();
+  {
+    const char* env_dbg = getenv("VSR_TC_DEBUG");            // re-read per launch: attribution sweeps flip it
+    a.debug = env_dbg ? atoi(env_dbg) : 0;
+    const char* env_res = getenv("VSR_TC_RESIDENT");
+    if (env_res && env_res[0] == '0') a.resident = 0;
+    if (env_res && env_res[0] == '1' && d->max_group_taps > 0 && res_need <= avail - 2 * kATileBytes) a.resident = 1;
+  }
+  a.res_bytes = a.resident ? (int)res_need : 0;
+  const int stage_bytes = a.resident ? kATileBytes : kATileBytes + b_bytes;
+  int stages = (int)((avail - a.res_bytes) / stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  const char* env_stg = getenv("VSR_TC_STAGES");
+  if (env_stg && atoi(env_stg) >= 1 && atoi(env_stg) < stages) stages = atoi(env_stg);
+  VSR_CHECK_SUPPORTED(stages >= 1, "tapgemm(bf16, v2): no room for a pipeline stage");
+  a.stages = stages;
+  const int smem = kCtrlBytes + a.epi_bytes + a.res_bytes + stages * stage_bytes;
+  int grid = num_sms();
+  const char* env_grid = getenv("VSR_TC_GRID");
+  if (env_grid && atoi(env_grid) >= 1) grid = atoi(env_grid);
+  if (grid > a.num_tiles) grid = a.num_tiles;
+  if (grid > kPartialsLen) grid = kPartialsLen;
+  kernel<<<grid, kThreads, smem, stream>>>(a);
+  VSR_CHECK_LAUNCH("tapgemm_tc2");
+  return VSR_OK;
+}
+
+}  // namespace vsr
