@@ -27,7 +27,7 @@ def main():
         for res in ("0", "1"):
             for mode in args.modes.split(","):
                 os.environ["VSR_TC_DEBUG"] = mode
-                os.environ["VSR_TC_RESIDENT2"] = res
+                os.environ["VSR_TC_RESIDENT"] = res
                 sys.argv = ["kbench", "--cases", case, "--iters", str(args.iters)]
                 results = []
                 kbench.CASES = {case}

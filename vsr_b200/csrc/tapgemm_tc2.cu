@@ -32,14 +32,17 @@ constexpr int kKc = 64;                       // bf16 channels per tap = one 128
 constexpr int kATileBytes = kBlockM * 128;    // 16 KiB
 constexpr int kMaxStages = 8;
 constexpr int kSmemBudget = 227 * 1024;
-constexpr int kEpiWarps = 4;
+constexpr int kEpiWarps = 8;                  // two per TMEM lane quarter: even / odd 64-channel chunks
 constexpr int kTileBytes = 4096;              // epilogue tile: 32 pixels x 64 channels bf16
-constexpr int kMaxSmemGroups = 48;            // group table rows cached in smem (16 B each, ctrl[256..1024))
+constexpr int kMaxSmemGroups = 46;            // group table rows cached in smem (16 B each, ctrl[288..1024))
 constexpr int kMaxSmemTaps = 256;             // packed tap entries cached in smem (4 B each)
 constexpr int kBiasFloats = 1024;
 constexpr int kCtrlBytes = 1024 + kMaxSmemTaps * 4 + kBiasFloats * 4;   // 6 KiB, keeps 1024-byte alignment
 constexpr int kTmemCols = 512;
-constexpr int kThreads = 64 + 32 * kEpiWarps;  // warp0 TMA, warp1 MMA, warps 2-5 epilogue
+constexpr int kProducers = 3;                 // TMA-issuing warps: tap t of the CTA's sequence belongs to warp t % 3
+constexpr int kMmaWarp = kProducers;
+constexpr int kEpiWarp0 = kProducers + 1;      // first epilogue warp (a multiple of 4: TMEM lane quarter = warp & 3)
+constexpr int kThreads = 32 * (kEpiWarp0 + kEpiWarps);
 
 constexpr int kEpiIn = VSR_EPI_RES_PRE | VSR_EPI_PRELU_BWD | VSR_EPI_RELU_BWD | VSR_EPI_OUT2;
 
@@ -139,10 +142,10 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
   const uint32_t tempty_bar = smem_base + 144;             // 2 x 8 B
   const uint32_t tmem_slot = smem_base + 160;              // u32
   const uint32_t bres_full = smem_base + 168, bres_empty = smem_base + 176;
-  const uint32_t in_bar0 = smem_base + 184;                // kEpiWarps x 8 B
+  const uint32_t in_bar0 = smem_base + 184;                // kEpiWarps x 8 B (..248)
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + 160);
-  float* red = reinterpret_cast<float*>(smem_gen + 224);   // kEpiWarps floats
-  int4* grp_s = reinterpret_cast<int4*>(smem_gen + 256);        // group table (<= 48 rows)
+  float* red = reinterpret_cast<float*>(smem_gen + 256);   // kEpiWarps floats
+  int4* grp_s = reinterpret_cast<int4*>(smem_gen + 288);        // group table (<= 46 rows)
   uint32_t* tap_s = reinterpret_cast<uint32_t*>(smem_gen + 1024);   // packed tap table (<= 256 entries)
   float* bias_s = reinterpret_cast<float*>(smem_gen + 1024 + kMaxSmemTaps * 4);   // bias when Cout <= 1024
   const uint32_t epi_base = smem_base + kCtrlBytes;        // epilogue tiles
@@ -182,7 +185,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
     for (int w = 0; w < kEpiWarps; ++w) ptx::mbar_init(in_bar0 + 8 * w, 1);
     ptx::fence_mbar_init();
   }
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     ptx::tmem_alloc(tmem_slot, kTmemCols);
     ptx::tmem_relinquish();
   }
@@ -191,59 +194,79 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
 
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+  if (warp < kProducers) {
+    // ===================== TMA producers =====================
+    // The whole warp walks the (uniform) loops; one elected lane issues.  Keeping the control flow and
+    // the operands warp-uniform lets the compiler stay on the uniform datapath (no per-lane loops).
+    {
+      const bool leader = ptx::elect_one();
       int stage = 0;
       uint32_t phase = 0;
       int cur_g = -1;
       uint32_t gcount = 0;
+      int turn = 0;                               // position in the tap sequence modulo kProducers
       long long p_wait = 0, p_n = 0, p_t0 = clock64();
       for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
         const TileCoord tc = decode_tile(a, tile);
-        const int4 grp = grp_in_smem ? grp_s[tc.g] : __ldg(a.group_tab + tc.g);
-        if (a.resident && tc.g != cur_g) {
+        int4 grp = grp_in_smem ? grp_s[tc.g] : __ldg(a.group_tab + tc.g);
+        grp.y = __shfl_sync(0xffffffffu, grp.y, 0);
+        grp.z = __shfl_sync(0xffffffffu, grp.z, 0);
+        if (a.resident && tc.g != cur_g && warp == 0) {
           // (re)load this group's weight slabs once all MMAs of the previous group are done
           ptx::mbar_wait(bres_empty, (gcount & 1u) ^ 1u);
-          ptx::mbar_arrive_expect_tx(bres_full, static_cast<uint32_t>(grp.z) * b_bytes);
-          for (int t = 0; t < grp.z; ++t)
-            ptx::bulk_load(res_base + t * b_bytes, a.w + static_cast<size_t>(grp.y + t) * b_bytes, b_bytes, bres_full);
+          if (leader) {
+            ptx::mbar_arrive_expect_tx(bres_full, static_cast<uint32_t>(grp.z) * b_bytes);
+            for (int t = 0; t < grp.z; ++t)
+              ptx::bulk_load(res_base + t * b_bytes, a.w + static_cast<size_t>(grp.y + t) * b_bytes, b_bytes, bres_full);
+          }
           cur_g = tc.g;
           ++gcount;
         }
         for (int t = 0; t < grp.z; ++t) {
-          const int4 tap = taps_in_smem ? unpack_tap(tap_s[grp.y + t]) : __ldg(a.tap_tab + grp.y + t);
+          const bool mine = turn == warp;
+          if (++turn == kProducers) turn = 0;
+          if (!mine) {
+            if (++stage == a.stages) { stage = 0; phase ^= 1u; }
+            continue;
+          }
+          uint32_t ptap = taps_in_smem ? tap_s[grp.y + t] : pack_tap(__ldg(a.tap_tab + grp.y + t));
+          ptap = __shfl_sync(0xffffffffu, ptap, 0);
+          const int4 tap = unpack_tap(ptap);
           long long c0 = 0;
           if (prof) c0 = clock64();
           ptx::mbar_wait(empty_bar + 8 * stage, phase ^ 1u);
           if (prof) { p_wait += clock64() - c0; ++p_n; }
           const uint32_t fb = full_bar + 8 * stage;
           const uint32_t sa = stage_base + stage * stage_bytes;
-          if (a.debug & 6) {
-            // attribution runs: skip the A (2) and/or B (4) transfer, keep the barrier protocol
-            uint32_t tx = 0;
-            if (!(a.debug & 2)) tx += kATileBytes;
-            if (!(a.debug & 4) && !a.resident) tx += b_bytes;
-            if (tx == 0) { ptx::mbar_arrive(fb); } else { ptx::mbar_arrive_expect_tx(fb, tx); }
-            if (!(a.debug & 2)) ptx::tma_load_4d(sa, &a.maps[tap.x], fb, tap.w, tc.x0 + tap.z, tc.y0 + tap.y, tc.n);
-            if (!(a.debug & 4) && !a.resident)
-              ptx::bulk_load(sa + kATileBytes, a.w + static_cast<size_t>(grp.y + t) * b_bytes, b_bytes, fb);
-          } else {
-            ptx::mbar_arrive_expect_tx(fb, stage_bytes);
-            ptx::tma_load_4d(sa, &a.maps[tap.x], fb, tap.w, tc.x0 + tap.z, tc.y0 + tap.y, tc.n);
-            if (!a.resident)
-              ptx::bulk_load(sa + kATileBytes, a.w + static_cast<size_t>(grp.y + t) * b_bytes, b_bytes, fb);
+          if (leader) {
+            if (a.debug & 6) {
+              // attribution runs: skip the A (2) and/or B (4) transfer, keep the barrier protocol
+              uint32_t tx = 0;
+              if (!(a.debug & 2)) tx += kATileBytes;
+              if (!(a.debug & 4) && !a.resident) tx += b_bytes;
+              if (tx == 0) { ptx::mbar_arrive(fb); } else { ptx::mbar_arrive_expect_tx(fb, tx); }
+              if (!(a.debug & 2)) ptx::tma_load_4d(sa, &a.maps[tap.x], fb, tap.w, tc.x0 + tap.z, tc.y0 + tap.y, tc.n);
+              if (!(a.debug & 4) && !a.resident)
+                ptx::bulk_load(sa + kATileBytes, a.w + static_cast<size_t>(grp.y + t) * b_bytes, b_bytes, fb);
+            } else {
+              ptx::mbar_arrive_expect_tx(fb, stage_bytes);
+              ptx::tma_load_4d(sa, &a.maps[tap.x], fb, tap.w, tc.x0 + tap.z, tc.y0 + tap.y, tc.n);
+              if (!a.resident)
+                ptx::bulk_load(sa + kATileBytes, a.w + static_cast<size_t>(grp.y + t) * b_bytes, b_bytes, fb);
+            }
           }
           if (++stage == a.stages) { stage = 0; phase ^= 1u; }
         }
       }
-      if (prof && blockIdx.x == 0)
+      if (prof && blockIdx.x == 0 && leader && warp == 0)
         printf("tc2-prof producer: total %lld cyc, %lld taps, wait(empty) %lld\n", clock64() - p_t0, p_n, p_wait);
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
+  } else if (warp == kMmaWarp) {
+    // ===================== MMA issuer (one elected lane, warp-uniform control flow) =====================
+    {
+      const bool leader = ptx::elect_one();
       const uint32_t idesc = ptx::make_idesc_bf16(kBlockM, a.nt, 0, 0);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -252,7 +275,8 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
       long long m_wfull = 0, m_wtmem = 0, m_issue = 0, m_n = 0, m_t0 = clock64();
       for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++it) {
         const TileCoord tc = decode_tile(a, tile);
-        const int4 grp = grp_in_smem ? grp_s[tc.g] : __ldg(a.group_tab + tc.g);
+        int4 grp = grp_in_smem ? grp_s[tc.g] : __ldg(a.group_tab + tc.g);
+        grp.z = __shfl_sync(0xffffffffu, grp.z, 0);
         if (a.resident && tc.g != cur_g) {
           ptx::mbar_wait(bres_full, gcount & 1u);
           cur_g = tc.g;
@@ -265,7 +289,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
         ptx::mbar_wait(tempty_bar + 8 * buf, bphase ^ 1u);
         ptx::tc_fence_after();
         if (prof) m_wtmem += clock64() - c0;
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * a.nt);
+        const uint32_t d_tmem = tmem_u + static_cast<uint32_t>(buf * a.nt);
         for (int t = 0; t < grp.z; ++t) {
           if (prof) c0 = clock64();
           ptx::mbar_wait(full_bar + 8 * stage, phase);
@@ -274,39 +298,45 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
           const uint32_t sa = stage_base + stage * stage_bytes;
           const uint64_t adesc = ptx::make_sw128_desc(sa, 16, 1024);
           const uint64_t bdesc = ptx::make_sw128_desc(a.resident ? res_base + t * b_bytes : sa + kATileBytes, 16, 1024);
-          if (!(a.debug & 8)) {
+          if (leader) {
+            if (!(a.debug & 8)) {
 #pragma unroll
-            for (int k = 0; k < kKc / 16; ++k) {
-              // advancing K by 16 bf16 = 32 bytes = 2 descriptor address units
-              ptx::mma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (t | k) != 0);
+              for (int k = 0; k < kKc / 16; ++k) {
+                // advancing K by 16 bf16 = 32 bytes = 2 descriptor address units
+                ptx::mma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (t | k) != 0);
+              }
             }
+            ptx::mma_commit(empty_bar + 8 * stage);
           }
-          ptx::mma_commit(empty_bar + 8 * stage);
           if (prof) { m_wfull += c1 - c0; m_issue += clock64() - c1; ++m_n; }
           if (++stage == a.stages) { stage = 0; phase ^= 1u; }
         }
-        ptx::mma_commit(tfull_bar + 8 * buf);
+        if (leader) ptx::mma_commit(tfull_bar + 8 * buf);
         if (a.resident) {
           const int next = tile + tile_step;
-          if (next >= tile_end || decode_tile(a, next).g != cur_g) ptx::mma_commit(bres_empty);
+          if ((next >= tile_end || decode_tile(a, next).g != cur_g) && leader) ptx::mma_commit(bres_empty);
         }
       }
-      if (prof && blockIdx.x == 0)
+      if (prof && blockIdx.x == 0 && leader)
         printf("tc2-prof mma: total %lld cyc, %lld taps, %d tiles, wait(full) %lld, issue+commit %lld, wait(tmem) %lld\n",
                clock64() - m_t0, m_n, it, m_wfull, m_issue, m_wtmem);
     }
   } else {
-    // ===================== epilogue (4 warps, one TMEM lane quarter each) =====================
-    const int ew = warp - 2;
+    // ===================== epilogue (8 warps: TMEM lane quarter x chunk parity) =====================
+    const int ew = warp - kEpiWarp0;
     const int quarter = warp & 3;                 // TMEM lanes [32*quarter, 32*quarter+32) = tile pixels
+    const int chalf = ew >> 2;                    // this warp drains the 64-channel chunks c = 64*chalf (mod 128)
+    const int c_first = 64 * chalf;
+    // warps without a chunk (nt == 64, chalf == 1) only take part in the barrier protocol
+    const int slot = a.nt > 64 ? ew : (ew & 3);   // staging tiles exist for active warps only
     // this warp's 32 pixels as a sub-box of the bw x bh tile (the epilogue maps have box ew x eh)
     const int sub_x = (quarter * 32) & (a.bw - 1);
     const int sub_y = (quarter * 32) >> a.bw_shift;
     const bool skip = (a.debug & 1) != 0;
-    const bool has_in = (epi & kEpiIn) != 0 && !skip;
+    const bool has_in = (epi & kEpiIn) != 0 && !skip && c_first < a.nt;
     const int n_in = ((epi & VSR_EPI_RES_PRE) ? 1 : 0) + ((epi & (VSR_EPI_PRELU_BWD | VSR_EPI_RELU_BWD)) ? 1 : 0) +
                      ((epi & VSR_EPI_OUT2) ? 1 : 0);
-    const uint32_t out_t = epi_base + ew * (1 + n_in) * kTileBytes;
+    const uint32_t out_t = epi_base + slot * (1 + n_in) * kTileBytes;
     uint32_t nxt = out_t + kTileBytes;
     const uint32_t res_t = nxt;
     if (epi & VSR_EPI_RES_PRE) nxt += kTileBytes;
@@ -318,7 +348,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
     const float slope = (epi & (VSR_EPI_PRELU | VSR_EPI_PRELU_BWD)) ? __ldg(a.slope) : 0.f;
     const float inv_slope = slope != 0.f ? 1.f / slope : 0.f;
     float slope_acc = 0.f;
-    long long e_wait = 0, e_in = 0, e_ld = 0, e_math = 0, e_st = 0, e_t0 = clock64();
+    long long e_wait = 0, e_in = 0, e_ld = 0, e_math = 0, e_st = 0, e_iss = 0, e_t0 = clock64();
 
     // one elected lane fetches the epilogue operands of a 64-channel chunk through TMA
     auto issue_in = [&](int n, int y0, int x0, int c0) {
@@ -329,19 +359,19 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
       if (epi & VSR_EPI_OUT2) ptx::tma_load_4d(res2_t, &a.res2_map, in_bar, c0, x0 + sub_x, y0 + sub_y, n);
     };
     auto issue_next_in = [&](int tile, int c, const TileCoord& tc, int o0) {
-      if (c + 64 < a.nt) {
-        issue_in(tc.n, tc.y0, tc.x0, o0 + c + 64);
+      if (c + 128 < a.nt) {
+        issue_in(tc.n, tc.y0, tc.x0, o0 + c + 128);
       } else if (tile + tile_step < tile_end) {
         const TileCoord t2 = decode_tile(a, tile + tile_step);
         const int4 g2 = grp_in_smem ? grp_s[t2.g] : __ldg(a.group_tab + t2.g);
-        issue_in(t2.n, t2.y0, t2.x0, g2.x);
+        issue_in(t2.n, t2.y0, t2.x0, g2.x + c_first);
       }
     };
 
     if (has_in && lane == 0 && tile_begin < tile_end) {
       const TileCoord t0 = decode_tile(a, tile_begin);
       const int4 g0 = grp_in_smem ? grp_s[t0.g] : __ldg(a.group_tab + t0.g);
-      issue_in(t0.n, t0.y0, t0.x0, g0.x);
+      issue_in(t0.n, t0.y0, t0.x0, g0.x + c_first);
     }
     int it = 0;
     for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++it) {
@@ -358,114 +388,120 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
           tmem_base + static_cast<uint32_t>(buf * a.nt) + (static_cast<uint32_t>(quarter * 32) << 16);
       if (!skip) {
 #pragma unroll 1
-        for (int c = 0; c < a.nt; c += 64) {
+        for (int c = c_first; c < a.nt; c += 128) {
           if (prof) q0 = clock64();
           if (has_in) {
             ptx::mbar_wait(in_bar, in_phase);
             in_phase ^= 1u;
           }
+          // the previous chunk's TMA store must have read the staging tile before it is rewritten
+          if (lane == 0) bulk_wait_read0();
+          __syncwarp();
           if (prof) { q1 = clock64(); e_in += q1 - q0; }
-          float v[64];
-          {
-            uint32_t r[64];
-            ptx::tmem_ld64(taddr + c, r);
-            ptx::tmem_ld_wait();
+#pragma unroll 1
+          for (int h = 0; h < 2; ++h) {               // two 32-channel halves keep the live set small
+            if (prof) q1 = clock64();
+            float v[32];
+            {
+              uint32_t r[32];
+              ptx::tmem_ld32(taddr + c + 32 * h, r);
+              ptx::tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
-          }
-          if (prof) { q0 = clock64(); e_ld += q0 - q1; }
-          if (epi & VSR_EPI_BIAS) {
-            if (bias_in_smem) {
-              const float4* bp = reinterpret_cast<const float4*>(bias_s + grp.x + c);
+              for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+            }
+            if (prof) { q0 = clock64(); e_ld += q0 - q1; }
+            if (epi & VSR_EPI_BIAS) {
+              if (bias_in_smem) {
+                const float4* bp = reinterpret_cast<const float4*>(bias_s + grp.x + c + 32 * h);
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const float4 b = bp[i];
-                v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
-              }
-            } else {
-              const float4* bp = reinterpret_cast<const float4*>(a.bias + grp.x + c);
+                for (int i = 0; i < 8; ++i) {
+                  const float4 b = bp[i];
+                  v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+                }
+              } else {
+                const float4* bp = reinterpret_cast<const float4*>(a.bias + grp.x + c + 32 * h);
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const float4 b = __ldg(bp + i);
-                v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+                for (int i = 0; i < 8; ++i) {
+                  const float4 b = __ldg(bp + i);
+                  v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+                }
               }
             }
-          }
-          if (epi & VSR_EPI_SCALE) {
+            if (epi & VSR_EPI_SCALE) {
 #pragma unroll
-            for (int i = 0; i < 64; ++i) v[i] *= a.out_scale;
-          }
-          if (epi & VSR_EPI_RES_PRE) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const uint4 rq = ld_shared_v4(tile_addr(res_t, lane, j));
-              v[8 * j + 0] += bf16_lo(rq.x); v[8 * j + 1] += bf16_hi(rq.x);
-              v[8 * j + 2] += bf16_lo(rq.y); v[8 * j + 3] += bf16_hi(rq.y);
-              v[8 * j + 4] += bf16_lo(rq.z); v[8 * j + 5] += bf16_hi(rq.z);
-              v[8 * j + 6] += bf16_lo(rq.w); v[8 * j + 7] += bf16_hi(rq.w);
+              for (int i = 0; i < 32; ++i) v[i] *= a.out_scale;
             }
-          }
-          if (epi & VSR_EPI_PRELU) {
+            if (epi & VSR_EPI_RES_PRE) {
 #pragma unroll
-            for (int i = 0; i < 64; ++i) v[i] = v[i] > 0.f ? v[i] : slope * v[i];
-          }
-          if (epi & VSR_EPI_RELU) {
+              for (int j = 0; j < 4; ++j) {
+                const uint4 rq = ld_shared_v4(tile_addr(res_t, lane, 4 * h + j));
+                v[8 * j + 0] += bf16_lo(rq.x); v[8 * j + 1] += bf16_hi(rq.x);
+                v[8 * j + 2] += bf16_lo(rq.y); v[8 * j + 3] += bf16_hi(rq.y);
+                v[8 * j + 4] += bf16_lo(rq.z); v[8 * j + 5] += bf16_hi(rq.z);
+                v[8 * j + 6] += bf16_lo(rq.w); v[8 * j + 7] += bf16_hi(rq.w);
+              }
+            }
+            if (epi & VSR_EPI_PRELU) {
 #pragma unroll
-            for (int i = 0; i < 64; ++i) v[i] = fmaxf(v[i], 0.f);
-          }
-          if (epi & (VSR_EPI_PRELU_BWD | VSR_EPI_RELU_BWD)) {
+              for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : slope * v[i];
+            }
+            if (epi & VSR_EPI_RELU) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const uint4 aq = ld_shared_v4(tile_addr(aux_t, lane, j));
-              const uint32_t w4[4] = {aq.x, aq.y, aq.z, aq.w};
+              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+            }
+            if (epi & (VSR_EPI_PRELU_BWD | VSR_EPI_RELU_BWD)) {
 #pragma unroll
-              for (int h = 0; h < 4; ++h) {
+              for (int j = 0; j < 4; ++j) {
+                const uint4 aq = ld_shared_v4(tile_addr(aux_t, lane, 4 * h + j));
+                const uint32_t w4[4] = {aq.x, aq.y, aq.z, aq.w};
 #pragma unroll
-                for (int p = 0; p < 2; ++p) {
-                  const float f = p ? bf16_hi(w4[h]) : bf16_lo(w4[h]);
-                  const int i = 8 * j + 2 * h + p;
-                  const bool pos = f > 0.f;
-                  if (epi & VSR_EPI_PRELU_BWD) {
-                    // out-of-image pixels read f = 0 from the TMA zero fill and contribute exactly 0
-                    slope_acc += pos ? 0.f : v[i] * (f * inv_slope);
-                    v[i] = pos ? v[i] : slope * v[i];
-                  } else {
-                    v[i] = pos ? v[i] : 0.f;
+                for (int q = 0; q < 4; ++q) {
+#pragma unroll
+                  for (int p = 0; p < 2; ++p) {
+                    const float f = p ? bf16_hi(w4[q]) : bf16_lo(w4[q]);
+                    const int i = 8 * j + 2 * q + p;
+                    const bool pos = f > 0.f;
+                    if (epi & VSR_EPI_PRELU_BWD) {
+                      // out-of-image pixels read f = 0 from the TMA zero fill and contribute exactly 0
+                      slope_acc += pos ? 0.f : v[i] * (f * inv_slope);
+                      v[i] = pos ? v[i] : slope * v[i];
+                    } else {
+                      v[i] = pos ? v[i] : 0.f;
+                    }
                   }
                 }
               }
             }
+            if (prof) { q1 = clock64(); e_math += q1 - q0; }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 o;
+              o.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+              o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+              o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+              o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+              st_shared_v4(tile_addr(out_t, lane, 4 * h + j), o);
+            }
+            if (epi & VSR_EPI_OUT2) {
+              // out2 = v + res2, staged in place of the res2 tile (every thread owns its row)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 o;
+                const uint4 sq = ld_shared_v4(tile_addr(res2_t, lane, 4 * h + j));
+                o.x = pack_bf16x2(v[8 * j + 0] + bf16_lo(sq.x), v[8 * j + 1] + bf16_hi(sq.x));
+                o.y = pack_bf16x2(v[8 * j + 2] + bf16_lo(sq.y), v[8 * j + 3] + bf16_hi(sq.y));
+                o.z = pack_bf16x2(v[8 * j + 4] + bf16_lo(sq.z), v[8 * j + 5] + bf16_hi(sq.z));
+                o.w = pack_bf16x2(v[8 * j + 6] + bf16_lo(sq.w), v[8 * j + 7] + bf16_hi(sq.w));
+                st_shared_v4(tile_addr(res2_t, lane, 4 * h + j), o);
+              }
+            }
+            if (prof) e_st += clock64() - q1;
           }
+          if (prof) q1 = clock64();
           if (has_in && !(epi & VSR_EPI_OUT2)) {
             // the operand tiles have been consumed: fetch the next chunk's while this one is stored
             __syncwarp();
             if (lane == 0) issue_next_in(tile, c, tc, grp.x);
-          }
-          if (prof) { q1 = clock64(); e_math += q1 - q0; }
-          // the previous chunk's TMA store must have read the staging tile before it is rewritten
-          if (lane == 0) bulk_wait_read0();
-          __syncwarp();
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            uint4 o;
-            o.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-            o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-            o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-            o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-            st_shared_v4(tile_addr(out_t, lane, j), o);
-          }
-          if (epi & VSR_EPI_OUT2) {
-            // out2 = v + res2, staged in place of the res2 tile (every thread owns its row)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              uint4 o;
-              const uint4 sq = ld_shared_v4(tile_addr(res2_t, lane, j));
-              o.x = pack_bf16x2(v[8 * j + 0] + bf16_lo(sq.x), v[8 * j + 1] + bf16_hi(sq.x));
-              o.y = pack_bf16x2(v[8 * j + 2] + bf16_lo(sq.y), v[8 * j + 3] + bf16_hi(sq.y));
-              o.z = pack_bf16x2(v[8 * j + 4] + bf16_lo(sq.z), v[8 * j + 5] + bf16_hi(sq.z));
-              o.w = pack_bf16x2(v[8 * j + 6] + bf16_lo(sq.w), v[8 * j + 7] + bf16_hi(sq.w));
-              st_shared_v4(tile_addr(res2_t, lane, j), o);
-            }
           }
           fence_proxy_async();
           __syncwarp();
@@ -482,7 +518,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
               issue_next_in(tile, c, tc, grp.x);
             }
           }
-          if (prof) e_st += clock64() - q1;
+          if (prof) e_iss += clock64() - q1;
         }
       }
       ptx::tc_fence_before();
@@ -490,20 +526,21 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
       if (lane == 0) ptx::mbar_arrive(tempty_bar + 8 * buf);
     }
     if (lane == 0) bulk_wait0();                 // all output bytes are written before the CTA retires
-    if (prof && blockIdx.x == 0 && lane == 0 && ew < 2)
-      printf("tc2-prof epilogue warp %d: total %lld cyc, wait(tfull) %lld, operands %lld, tmem-ld %lld, math %lld, stage+store %lld\n",
-             warp, clock64() - e_t0, e_wait, e_in, e_ld, e_math, e_st);
+    if (prof && blockIdx.x == 0 && lane == 0 && (ew & 3) == 0)
+      printf("tc2-prof epilogue warp %d: total %lld cyc, wait(tfull) %lld, operands %lld, tmem-ld %lld, math %lld, pack+sts %lld, fence+issue %lld\n",
+             warp, clock64() - e_t0, e_wait, e_in, e_ld, e_math, e_st, e_iss);
     if (epi & VSR_EPI_PRELU_BWD) {
       slope_acc = warp_sum(slope_acc);
       if (lane == 0) red[ew] = slope_acc;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (ew == 0 && lane == 0) a.slope_partials[blockIdx.x] = (red[0] + red[1]) + (red[2] + red[3]);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (ew == 0 && lane == 0)
+        a.slope_partials[blockIdx.x] = ((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7]));
     }
   }
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, kTmemCols);
   }
@@ -605,7 +642,7 @@ int tapgemm_tc2_launch(const VsrTapGemmDesc* d, cudaStream_t stream) {
   a.m_tiles = a.N * a.tiles_x * a.tiles_y;
   const int n_in = ((d->epi & VSR_EPI_RES_PRE) ? 1 : 0) + ((d->epi & (VSR_EPI_PRELU_BWD | VSR_EPI_RELU_BWD)) ? 1 : 0) +
                    ((d->epi & VSR_EPI_OUT2) ? 1 : 0);
-  a.epi_bytes = kEpiWarps * (1 + n_in) * kTileBytes;
+  a.epi_bytes = (d->nt > 64 ? kEpiWarps : 4) * (1 + n_in) * kTileBytes;
   const int b_bytes = d->nt * 128;
   const long res_need = (long)d->max_group_taps * b_bytes;
   const long avail = kSmemBudget - kCtrlBytes - a.epi_bytes;
