@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define VSR_ABI_VERSION 1
+#define VSR_ABI_VERSION 2
 #define VSR_MAX_SRCS 8
 
 typedef enum VsrStatus {
@@ -100,6 +100,8 @@ typedef struct VsrTapGemmDesc {
   void* out2;            /* [n,h,w,out.c] dtype (OUT2) */
   const void* res2;      /* [n,h,w,out.c] dtype (OUT2) */
   float* slope_partials; /* device, >= vsr_partials_len() floats: per-CTA partial slope grads */
+  const int32_t* tap_tab_host; /* optional HOST copy of tap_tab (or NULL): lets the bf16 kernels plan shared loads
+                                  for taps that differ only by a row shift; results do not depend on it */
 } VsrTapGemmDesc;
 
 int vsr_abi_version(void);

@@ -66,5 +66,48 @@ def main():
     print(f"graph of 100 tiny torch kernels: {a.elapsed_time(b) * 10:.2f} us per launch", flush=True)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and len(sys.argv) == 1:
     main()
+
+
+def alternating():
+    """Does alternating kernels with different shared-memory carve-outs cost extra per launch?"""
+    ops = cuda_ops()
+    dt = torch.bfloat16
+    F = 64
+    n = 1
+    tab = TapTable(64, 64, [(0, [(s, 0, 0, 0) for s in range(3)])])
+    srcs = [torch.randn(n, 32, 32, F, device="cuda").to(dt) for _ in range(3)]
+    out = torch.empty(n, 32, 32, F, device="cuda", dtype=dt)
+    wts = (torch.randn(3 * 64 * 64, device="cuda") * 0.05).to(dt)
+    bias = torch.zeros(F, device="cuda")
+    slope = torch.tensor([0.2], device="cuda")
+    z = torch.zeros(1024, device="cuda")
+    z1, z2, z3 = (torch.zeros(4096, device="cuda", dtype=dt) for _ in range(3))
+    fa = lambda: ops.tapgemm(tab, srcs, out, wts, bias=bias, epi=5, slope=slope)
+    variants = {"tapgemm only": [fa], "tapgemm + torch add_": [fa, lambda: z.add_(1.0)],
+                "tapgemm + vsr add": [fa, lambda: ops.add(z1, z2, z3)], "torch add_ only": [lambda: z.add_(1.0)],
+                "vsr add only": [lambda: ops.add(z1, z2, z3)]}
+    for name, fns in variants.items():
+        for f in fns:
+            f()
+        g = torch.cuda.CUDAGraph()
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g, stream=s):
+                for _ in range(100):
+                    for f in fns:
+                        f()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g.replay()
+        a.record()
+        g.replay()
+        b.record()
+        torch.cuda.synchronize()
+        print(f"{name}: {a.elapsed_time(b) * 10:.2f} us per round of {len(fns)} launches", flush=True)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "alt":
+    alternating()

@@ -17,6 +17,9 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#include <algorithm>
+#include <vector>
+
 #include "common.cuh"
 #include "ptx_sm100.cuh"
 
@@ -35,9 +38,10 @@ constexpr int kSmemBudget = 227 * 1024;
 constexpr int kEpiWarps = 8;                  // two per TMEM lane quarter: even / odd 64-channel chunks
 constexpr int kTileBytes = 4096;              // epilogue tile: 32 pixels x 64 channels bf16
 constexpr int kMaxSmemGroups = 46;            // group table rows cached in smem (16 B each, ctrl[288..1024))
-constexpr int kMaxSmemTaps = 256;             // packed tap entries cached in smem (4 B each)
+constexpr int kMaxSmemTaps = 256;             // column entries cached in smem (8 B each)
+constexpr int kMaxParamCols = 32;             // host-built columns travel in the kernel arguments
 constexpr int kBiasFloats = 1024;
-constexpr int kCtrlBytes = 1024 + kMaxSmemTaps * 4 + kBiasFloats * 4;   // 6 KiB, keeps 1024-byte alignment
+constexpr int kCtrlBytes = 1024 + kMaxSmemTaps * 8 + kBiasFloats * 4;   // 7 KiB, keeps 1024-byte alignment
 constexpr int kTmemCols = 512;
 constexpr int kProducers = 3;                 // TMA-issuing warps: tap t of the CTA's sequence belongs to warp t % 3
 constexpr int kMmaWarp = kProducers;
@@ -48,7 +52,9 @@ constexpr int kEpiIn = VSR_EPI_RES_PRE | VSR_EPI_PRELU_BWD | VSR_EPI_RELU_BWD | 
 
 struct Tc2Args {
   CUtensorMap maps[VSR_MAX_SRCS];
+  CUtensorMap tall_maps[VSR_MAX_SRCS];   // shared-load mode: box of mb*bh + ndy_max - 1 rows
   CUtensorMap out_map, res_map, aux_map, out2_map, res2_map;
+  uint2 cols[kMaxParamCols];             // shared-load mode: {packed tap (dy = first row shift), slab0 | stride<<12 | ndy<<24}
   const int4* tap_tab;
   const int4* group_tab;
   const uint8_t* w;
@@ -69,6 +75,12 @@ struct Tc2Args {
   int epi_bytes;           // size of the epilogue tile region
   int m_tiles;             // pixel tiles per group
   int debug;               // timing-attribution switches (VSR_TC_DEBUG); results are wrong when non-zero
+  int tall;                // 1: shared-load mode (columns from `cols`, one group)
+  int n_cols;              // columns in `cols`
+  int mb;                  // 128-pixel sub-tiles stacked in y per CTA tile (1 or 2)
+  int a_bytes;             // bytes of one A box
+  int row_bytes;           // bw * 128: bytes of one pixel row of the A box
+  int stage_bytes;         // A box + the weight slabs of one column (none in resident mode)
 };
 
 // tap entry packed into 32 bits: src[0:4) | dy+8 [4:8) | dx+8 [8:12) | c0/8 [12:32)
@@ -100,7 +112,7 @@ __device__ __forceinline__ TileCoord decode_tile(const Tc2Args& a, int tile) {
   const int ty = mt % a.tiles_y;
   t.n = mt / a.tiles_y;
   t.x0 = tx * a.bw;
-  t.y0 = ty * a.bh;
+  t.y0 = ty * a.bh * a.mb;
   return t;
 }
 
@@ -130,6 +142,7 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 template <int FIXED_EPI>
 __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_constant__ Tc2Args a) {
   const int epi = FIXED_EPI >= 0 ? FIXED_EPI : a.epi;
+  const uint64_t g_t0 = ptx::globaltimer_ns();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = ptx::smem_u32(smem_raw);
   uint8_t* smem_gen = smem_raw;
@@ -146,22 +159,36 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + 160);
   float* red = reinterpret_cast<float*>(smem_gen + 256);   // kEpiWarps floats
   int4* grp_s = reinterpret_cast<int4*>(smem_gen + 288);        // group table (<= 46 rows)
-  uint32_t* tap_s = reinterpret_cast<uint32_t*>(smem_gen + 1024);   // packed tap table (<= 256 entries)
-  float* bias_s = reinterpret_cast<float*>(smem_gen + 1024 + kMaxSmemTaps * 4);   // bias when Cout <= 1024
+  uint2* col_s = reinterpret_cast<uint2*>(smem_gen + 1024);     // column table (<= 256 entries)
+  float* bias_s = reinterpret_cast<float*>(smem_gen + 1024 + kMaxSmemTaps * 8);   // bias when Cout <= 1024
   const uint32_t epi_base = smem_base + kCtrlBytes;        // epilogue tiles
   const uint32_t res_base = epi_base + a.epi_bytes;        // resident weight slabs (resident mode)
   const uint32_t stage_base = res_base + a.res_bytes;
   const bool grp_in_smem = a.n_groups <= kMaxSmemGroups;
   const bool taps_in_smem = a.n_taps_total <= kMaxSmemTaps;
-  if (grp_in_smem)
-    for (int i = threadIdx.x; i < a.n_groups; i += blockDim.x) grp_s[i] = __ldg(a.group_tab + i);
-  if (taps_in_smem)
-    for (int i = threadIdx.x; i < a.n_taps_total; i += blockDim.x) tap_s[i] = pack_tap(__ldg(a.tap_tab + i));
+  // A "column" is one A load feeding ndy taps (weight slabs slab0 + j*stride) whose row shifts are
+  // dy0 + j; plain mode: every tap is a column of its own.
+  if (a.tall) {
+    if (threadIdx.x == 0) {
+      int4 g = __ldg(a.group_tab);
+      g.y = 0;
+      g.z = a.n_cols;
+      grp_s[0] = g;
+    }
+    for (int i = threadIdx.x; i < a.n_cols; i += blockDim.x) col_s[i] = a.cols[i];
+  } else {
+    if (grp_in_smem)
+      for (int i = threadIdx.x; i < a.n_groups; i += blockDim.x) grp_s[i] = __ldg(a.group_tab + i);
+    if (taps_in_smem)
+      for (int i = threadIdx.x; i < a.n_taps_total; i += blockDim.x)
+        col_s[i] = make_uint2(pack_tap(__ldg(a.tap_tab + i)), (uint32_t)i | (1u << 24));
+  }
   const bool bias_in_smem = (epi & VSR_EPI_BIAS) && a.Cout <= kBiasFloats;
   if (bias_in_smem)
     for (int i = threadIdx.x; i < a.Cout; i += blockDim.x) bias_s[i] = __ldg(a.bias + i);
   const uint32_t b_bytes = static_cast<uint32_t>(a.nt) * 128u;
-  const uint32_t stage_bytes = a.resident ? kATileBytes : kATileBytes + b_bytes;
+  const uint32_t a_bytes = static_cast<uint32_t>(a.a_bytes);
+  const uint32_t stage_bytes = static_cast<uint32_t>(a.stage_bytes);
   // tile walk of this CTA
   const int tile_begin = a.resident ? (int)((long)a.num_tiles * blockIdx.x / gridDim.x) : (int)blockIdx.x;
   const int tile_end = a.resident ? (int)((long)a.num_tiles * (blockIdx.x + 1) / gridDim.x) : a.num_tiles;
@@ -193,6 +220,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  const uint64_t g_t1 = ptx::globaltimer_ns();
 
   if (warp < kProducers) {
     // ===================== TMA producers =====================
@@ -229,31 +257,28 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
             if (++stage == a.stages) { stage = 0; phase ^= 1u; }
             continue;
           }
-          uint32_t ptap = taps_in_smem ? tap_s[grp.y + t] : pack_tap(__ldg(a.tap_tab + grp.y + t));
-          ptap = __shfl_sync(0xffffffffu, ptap, 0);
-          const int4 tap = unpack_tap(ptap);
+          uint2 col = taps_in_smem ? col_s[grp.y + t]
+                                   : make_uint2(pack_tap(__ldg(a.tap_tab + grp.y + t)), (uint32_t)(grp.y + t) | (1u << 24));
+          col.x = __shfl_sync(0xffffffffu, col.x, 0);
+          col.y = __shfl_sync(0xffffffffu, col.y, 0);
+          const int4 tap = unpack_tap(col.x);
+          const int slab0 = (int)(col.y & 0xfffu), sstride = (int)((col.y >> 12) & 0xfffu), ndy = (int)(col.y >> 24);
           long long c0 = 0;
           if (prof) c0 = clock64();
           ptx::mbar_wait(empty_bar + 8 * stage, phase ^ 1u);
           if (prof) { p_wait += clock64() - c0; ++p_n; }
           const uint32_t fb = full_bar + 8 * stage;
           const uint32_t sa = stage_base + stage * stage_bytes;
+          const CUtensorMap* map = (a.tall ? a.tall_maps : a.maps) + tap.x;
           if (leader) {
-            if (a.debug & 6) {
-              // attribution runs: skip the A (2) and/or B (4) transfer, keep the barrier protocol
-              uint32_t tx = 0;
-              if (!(a.debug & 2)) tx += kATileBytes;
-              if (!(a.debug & 4) && !a.resident) tx += b_bytes;
-              if (tx == 0) { ptx::mbar_arrive(fb); } else { ptx::mbar_arrive_expect_tx(fb, tx); }
-              if (!(a.debug & 2)) ptx::tma_load_4d(sa, &a.maps[tap.x], fb, tap.w, tc.x0 + tap.z, tc.y0 + tap.y, tc.n);
-              if (!(a.debug & 4) && !a.resident)
-                ptx::bulk_load(sa + kATileBytes, a.w + static_cast<size_t>(grp.y + t) * b_bytes, b_bytes, fb);
-            } else {
-              ptx::mbar_arrive_expect_tx(fb, stage_bytes);
-              ptx::tma_load_4d(sa, &a.maps[tap.x], fb, tap.w, tc.x0 + tap.z, tc.y0 + tap.y, tc.n);
-              if (!a.resident)
-                ptx::bulk_load(sa + kATileBytes, a.w + static_cast<size_t>(grp.y + t) * b_bytes, b_bytes, fb);
-            }
+            // attribution runs skip the A (debug & 2) and/or B (debug & 4) transfer, keeping the protocol
+            const bool do_a = !(a.debug & 2), do_b = !(a.debug & 4) && !a.resident;
+            const uint32_t tx = (do_a ? a_bytes : 0u) + (do_b ? static_cast<uint32_t>(ndy) * b_bytes : 0u);
+            if (tx == 0) { ptx::mbar_arrive(fb); } else { ptx::mbar_arrive_expect_tx(fb, tx); }
+            if (do_a) ptx::tma_load_4d(sa, map, fb, tap.w, tc.x0 + tap.z, tc.y0 + tap.y, tc.n);
+            if (do_b)
+              for (int j = 0; j < ndy; ++j)
+                ptx::bulk_load(sa + a_bytes + j * b_bytes, a.w + static_cast<size_t>(slab0 + j * sstride) * b_bytes, b_bytes, fb);
           }
           if (++stage == a.stages) { stage = 0; phase ^= 1u; }
         }
@@ -289,21 +314,31 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
         ptx::mbar_wait(tempty_bar + 8 * buf, bphase ^ 1u);
         ptx::tc_fence_after();
         if (prof) m_wtmem += clock64() - c0;
-        const uint32_t d_tmem = tmem_u + static_cast<uint32_t>(buf * a.nt);
+        const uint32_t d_tmem = tmem_u + static_cast<uint32_t>(buf * a.mb * a.nt);
         for (int t = 0; t < grp.z; ++t) {
+          uint2 col = taps_in_smem ? col_s[grp.y + t] : make_uint2(0u, (uint32_t)(grp.y + t) | (1u << 24));
+          col.y = __shfl_sync(0xffffffffu, col.y, 0);
+          const int slab0 = (int)(col.y & 0xfffu), sstride = (int)((col.y >> 12) & 0xfffu), ndy = (int)(col.y >> 24);
           if (prof) c0 = clock64();
           ptx::mbar_wait(full_bar + 8 * stage, phase);
           ptx::tc_fence_after();
           if (prof) c1 = clock64();
           const uint32_t sa = stage_base + stage * stage_bytes;
-          const uint64_t adesc = ptx::make_sw128_desc(sa, 16, 1024);
-          const uint64_t bdesc = ptx::make_sw128_desc(a.resident ? res_base + t * b_bytes : sa + kATileBytes, 16, 1024);
           if (leader) {
             if (!(a.debug & 8)) {
+              for (int j = 0; j < ndy; ++j) {
+                const uint64_t bdesc = ptx::make_sw128_desc(
+                    a.resident ? res_base + (slab0 + j * sstride - grp.y) * b_bytes : sa + a_bytes + j * b_bytes, 16, 1024);
+                for (int m = 0; m < a.mb; ++m) {
+                  // rows shifted by j (tap) and m*bh (sub-tile) inside the shared A box: whole pixel rows,
+                  // i.e. multiples of 1024 bytes, so the swizzle phase of the descriptor is unchanged
+                  const uint64_t adesc = ptx::make_sw128_desc(sa + (j + m * a.bh) * a.row_bytes, 16, 1024);
 #pragma unroll
-              for (int k = 0; k < kKc / 16; ++k) {
-                // advancing K by 16 bf16 = 32 bytes = 2 descriptor address units
-                ptx::mma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (t | k) != 0);
+                  for (int k = 0; k < kKc / 16; ++k) {
+                    // advancing K by 16 bf16 = 32 bytes = 2 descriptor address units
+                    ptx::mma_bf16_ss(d_tmem + m * a.nt, adesc + 2 * k, bdesc + 2 * k, idesc, (t | j | k) != 0);
+                  }
+                }
               }
             }
             ptx::mma_commit(empty_bar + 8 * stage);
@@ -358,9 +393,11 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
         ptx::tma_load_4d(aux_t, &a.aux_map, in_bar, c0, x0 + sub_x, y0 + sub_y, n);
       if (epi & VSR_EPI_OUT2) ptx::tma_load_4d(res2_t, &a.res2_map, in_bar, c0, x0 + sub_x, y0 + sub_y, n);
     };
-    auto issue_next_in = [&](int tile, int c, const TileCoord& tc, int o0) {
+    auto issue_next_in = [&](int tile, int m, int c, const TileCoord& tc, int o0) {
       if (c + 128 < a.nt) {
-        issue_in(tc.n, tc.y0, tc.x0, o0 + c + 128);
+        issue_in(tc.n, tc.y0 + m * a.bh, tc.x0, o0 + c + 128);
+      } else if (m + 1 < a.mb) {
+        issue_in(tc.n, tc.y0 + (m + 1) * a.bh, tc.x0, o0 + c_first);
       } else if (tile + tile_step < tile_end) {
         const TileCoord t2 = decode_tile(a, tile + tile_step);
         const int4 g2 = grp_in_smem ? grp_s[t2.g] : __ldg(a.group_tab + t2.g);
@@ -384,11 +421,14 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
       ptx::mbar_wait(tfull_bar + 8 * buf, bphase);
       ptx::tc_fence_after();
       if (prof) e_wait += clock64() - q0;
-      const uint32_t taddr =
-          tmem_base + static_cast<uint32_t>(buf * a.nt) + (static_cast<uint32_t>(quarter * 32) << 16);
       if (!skip) {
 #pragma unroll 1
+        for (int mc = 0; mc < a.mb; ++mc)
+#pragma unroll 1
         for (int c = c_first; c < a.nt; c += 128) {
+          const int m = mc;                       // 128-pixel sub-tile of the CTA tile
+          const uint32_t taddr = tmem_base + static_cast<uint32_t>((buf * a.mb + m) * a.nt) +
+                                 (static_cast<uint32_t>(quarter * 32) << 16);
           if (prof) q0 = clock64();
           if (has_in) {
             ptx::mbar_wait(in_bar, in_phase);
@@ -501,21 +541,21 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
           if (has_in && !(epi & VSR_EPI_OUT2)) {
             // the operand tiles have been consumed: fetch the next chunk's while this one is stored
             __syncwarp();
-            if (lane == 0) issue_next_in(tile, c, tc, grp.x);
+            if (lane == 0) issue_next_in(tile, m, c, tc, grp.x);
           }
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
             if (!(a.debug & 16)) {
-              tma_store_4d(&a.out_map, out_t, grp.x + c, tc.x0 + sub_x, tc.y0 + sub_y, tc.n);
+              tma_store_4d(&a.out_map, out_t, grp.x + c, tc.x0 + sub_x, tc.y0 + m * a.bh + sub_y, tc.n);
               if (epi & VSR_EPI_OUT2)
-                tma_store_4d(&a.out2_map, res2_t, grp.x + c, tc.x0 + sub_x, tc.y0 + sub_y, tc.n);
+                tma_store_4d(&a.out2_map, res2_t, grp.x + c, tc.x0 + sub_x, tc.y0 + m * a.bh + sub_y, tc.n);
             }
             bulk_commit();
             if (epi & VSR_EPI_OUT2) {
               // the res2 tile doubles as the out2 staging tile: refill it only after the store has read it
               bulk_wait_read0();
-              issue_next_in(tile, c, tc, grp.x);
+              issue_next_in(tile, m, c, tc, grp.x);
             }
           }
           if (prof) e_iss += clock64() - q1;
@@ -538,12 +578,56 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
     }
   }
 
+  const uint64_t g_t2 = ptx::globaltimer_ns();
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == kMmaWarp) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, kTmemCols);
   }
+  if (prof && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1))
+    printf("tc2-prof block %d: start %llu ns, setup %llu ns, role done (producer) +%llu ns, exit +%llu ns\n", (int)blockIdx.x,
+           (unsigned long long)g_t0, (unsigned long long)(g_t1 - g_t0), (unsigned long long)(g_t2 - g_t0),
+           (unsigned long long)(ptx::globaltimer_ns() - g_t0));
+}
+
+// Host: fold the taps of a (single-group) table into columns = taps with equal (src, c0, dx), consecutive dy
+// and evenly spaced slab indices.  Returns the longest column (0 if the table does not fit the argument array).
+int build_columns(const int32_t* taps, int n_taps, uint2* cols, int* n_cols) {
+  struct T { int src, dy, dx, c0, idx; };
+  std::vector<T> v(n_taps);
+  for (int i = 0; i < n_taps; ++i) v[i] = T{taps[4 * i], taps[4 * i + 1], taps[4 * i + 2], taps[4 * i + 3], i};
+  for (const T& t : v)
+    if (t.src < 0 || t.src > 15 || t.dy < -8 || t.dy > 7 || t.dx < -8 || t.dx > 7 || (t.c0 & 7)) return 0;
+  std::stable_sort(v.begin(), v.end(), [](const T& x, const T& y) {
+    if (x.src != y.src) return x.src < y.src;
+    if (x.c0 != y.c0) return x.c0 < y.c0;
+    if (x.dx != y.dx) return x.dx < y.dx;
+    return x.dy < y.dy;
+  });
+  int n = 0, longest = 0;
+  size_t i = 0;
+  while (i < v.size()) {
+    size_t j = i + 1;
+    int stride = 0;
+    while (j < v.size() && j - i < 3 && v[j].src == v[i].src && v[j].c0 == v[i].c0 && v[j].dx == v[i].dx &&
+           v[j].dy == v[j - 1].dy + 1) {
+      const int st = v[j].idx - v[j - 1].idx;
+      if (j == i + 1) stride = st;
+      if (st != stride || st <= 0 || st > 4095) break;
+      ++j;
+    }
+    const int ndy = (int)(j - i);
+    if (n >= kMaxParamCols) return 0;
+    const int4 first = make_int4(v[i].src, v[i].dy, v[i].dx, v[i].c0);
+    cols[n].x = (uint32_t)first.x | ((uint32_t)(first.y + 8) << 4) | ((uint32_t)(first.z + 8) << 8) | ((uint32_t)(first.w >> 3) << 12);
+    cols[n].y = (uint32_t)v[i].idx | ((uint32_t)(ndy > 1 ? stride : 0) << 12) | ((uint32_t)ndy << 24);
+    ++n;
+    if (ndy > longest) longest = ndy;
+    i = j;
+  }
+  *n_cols = n;
+  return longest;
 }
 
 template <int EPI>
@@ -633,39 +717,69 @@ int tapgemm_tc2_launch(const VsrTapGemmDesc* d, cudaStream_t stream) {
   a.bw = bw; a.bh = bh;
   a.bw_shift = 0;
   while ((1 << a.bw_shift) < bw) ++a.bw_shift;
-  a.tiles_x = (a.W + bw - 1) / bw;
-  a.tiles_y = (a.H + bh - 1) / bh;
-  const long tiles = (long)a.n_groups * a.N * a.tiles_x * a.tiles_y;
-  VSR_CHECK_SUPPORTED(tiles < (1l << 30), "tapgemm(bf16): too many tiles");
-  a.num_tiles = (int)tiles;
   a.n_taps_total = d->n_taps_total;
-  a.m_tiles = a.N * a.tiles_x * a.tiles_y;
+  a.row_bytes = bw * 128;
   const int n_in = ((d->epi & VSR_EPI_RES_PRE) ? 1 : 0) + ((d->epi & (VSR_EPI_PRELU_BWD | VSR_EPI_RELU_BWD)) ? 1 : 0) +
                    ((d->epi & VSR_EPI_OUT2) ? 1 : 0);
   a.epi_bytes = (d->nt > 64 ? kEpiWarps : 4) * (1 + n_in) * kTileBytes;
   const int b_bytes = d->nt * 128;
-  const long res_need = (long)d->max_group_taps * b_bytes;
   const long avail = kSmemBudget - kCtrlBytes - a.epi_bytes;
+  const char* env_dbg = getenv("VSR_TC_DEBUG");            // re-read per launch: attribution sweeps flip it
+  a.debug = env_dbg ? atoi(env_dbg) : 0;
+
+  // ---- shared-load mode: taps that differ only by a row shift read one A box; two pixel tiles stacked
+  // in y share every weight slab.  Needs the host copy of the tap table (d->tap_tab_host).
+  a.mb = 1;
+  a.a_bytes = kATileBytes;
+  int ndy_max = 1;
+  {
+    const char* env_tall = getenv("VSR_TC_TALL");
+    const bool want = !(env_tall && env_tall[0] == '0');
+    if (want && d->tap_tab_host != nullptr && d->n_groups == 1 && d->nt <= 128 && bw >= 8 && bw * bh == kBlockM &&
+        d->n_taps_total <= 4095)
+      ndy_max = build_columns(d->tap_tab_host, d->n_taps_total, a.cols, &a.n_cols);
+    if (ndy_max >= 2) {
+      const int mb = (a.H >= 2 * bh) ? 2 : 1;
+      const int rows = mb * bh + ndy_max - 1;
+      const long stage = (long)rows * a.row_bytes + (long)ndy_max * b_bytes;
+      if (rows <= 256 && 3 * stage <= avail) {
+        a.tall = 1;
+        a.mb = mb;
+        a.a_bytes = rows * a.row_bytes;
+        for (int s = 0; s < d->n_srcs; ++s) {
+          int rc = get_src_map_pub(d->srcs[s], bw, rows, &a.tall_maps[s]);
+          if (rc != VSR_OK) return rc;
+        }
+      }
+    }
+    if (!a.tall) ndy_max = 1;
+  }
+  a.tiles_x = (a.W + bw - 1) / bw;
+  a.tiles_y = (a.H + bh * a.mb - 1) / (bh * a.mb);
+  const long tiles = (long)a.n_groups * a.N * a.tiles_x * a.tiles_y;
+  VSR_CHECK_SUPPORTED(tiles < (1l << 30), "tapgemm(bf16): too many tiles");
+  a.num_tiles = (int)tiles;
+  a.m_tiles = a.N * a.tiles_x * a.tiles_y;
+  const long res_need = (long)d->max_group_taps * b_bytes;
   // weight-resident mode: the group's slabs stay in smem and >= 3 A stages remain; worth it when the
   // slabs are large next to the A tile (nt > 64) and every CTA sees few groups
-  a.resident = d->max_group_taps > 0 && d->nt > 64 && res_need <= avail - 3 * kATileBytes &&
+  a.resident = !a.tall && d->max_group_taps > 0 && d->nt > 64 && res_need <= avail - 3 * kATileBytes &&
                tiles >= 2 * (long)num_sms();
   {
-    const char* env_dbg = getenv("VSR_TC_DEBUG");            // re-read per launch: attribution sweeps flip it
-    a.debug = env_dbg ? atoi(env_dbg) : 0;
     const char* env_res = getenv("VSR_TC_RESIDENT");
     if (env_res && env_res[0] == '0') a.resident = 0;
-    if (env_res && env_res[0] == '1' && d->max_group_taps > 0 && res_need <= avail - 2 * kATileBytes) a.resident = 1;
+    if (env_res && env_res[0] == '1' && !a.tall && d->max_group_taps > 0 && res_need <= avail - 2 * kATileBytes)
+      a.resident = 1;
   }
   a.res_bytes = a.resident ? (int)res_need : 0;
-  const int stage_bytes = a.resident ? kATileBytes : kATileBytes + b_bytes;
-  int stages = (int)((avail - a.res_bytes) / stage_bytes);
+  a.stage_bytes = a.resident ? a.a_bytes : a.a_bytes + ndy_max * b_bytes;
+  int stages = (int)((avail - a.res_bytes) / a.stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   const char* env_stg = getenv("VSR_TC_STAGES");
   if (env_stg && atoi(env_stg) >= 1 && atoi(env_stg) < stages) stages = atoi(env_stg);
   VSR_CHECK_SUPPORTED(stages >= 1, "tapgemm(bf16, v2): no room for a pipeline stage");
   a.stages = stages;
-  const int smem = kCtrlBytes + a.epi_bytes + a.res_bytes + stages * stage_bytes;
+  const int smem = kCtrlBytes + a.epi_bytes + a.res_bytes + stages * a.stage_bytes;
   int grid = num_sms();
   const char* env_grid = getenv("VSR_TC_GRID");
   if (env_grid && atoi(env_grid) >= 1) grid = atoi(env_grid);

@@ -62,6 +62,12 @@ class TapTable:
                               torch.tensor(t_rows, dtype=torch.int32, device=device))
         return self._dev[key]
 
+    def host_taps(self):
+        """Host copy of the tap table (kept alive with the table): VsrTapGemmDesc.tap_tab_host."""
+        if "host" not in self._dev:
+            self._dev["host"] = torch.tensor([list(t) for t in self.flat_taps()], dtype=torch.int32).contiguous()
+        return self._dev["host"]
+
 
 def _tensor4(t: torch.Tensor) -> VsrTensor4:
     n, h, w, c = t.shape
@@ -84,6 +90,7 @@ def _make_desc(tab: TapTable, srcs: Sequence[torch.Tensor], out: torch.Tensor):
     d.n_groups, d.n_taps_total = tab.n_groups, tab.n_taps_total
     d.max_group_taps = max(len(t) for _, t in tab.groups)
     d.group_tab, d.tap_tab = gt.data_ptr(), tt.data_ptr()
+    d.tap_tab_host = tab.host_taps().data_ptr()
     return d
 
 
