@@ -324,6 +324,14 @@ def main():
         kernel_detail = {k: {"ms_per_step": v[1] / prof_steps, "n_per_step": v[2] / prof_steps,
                              "tflops": v[0] / (v[1] * 1e-3) / 1e12, "gbs": v[3] / (v[1] * 1e-3) / 1e9} for k, v in top}
         step_flops = 3.0 * FWD_FLOPS_PER_LR_PIXEL * args.batch * T * LR * LR
+        try:      # full per-shape table for the profile notes (scratch; the JSON line keeps the top 14)
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            with open(os.path.join(ROOT, "gpurun_out", "kernel_detail_full.json"), "w") as f:
+                json.dump({k: {"ms_per_step": v[1] / prof_steps, "n_per_step": v[2] / prof_steps,
+                               "tflops": v[0] / (v[1] * 1e-3) / 1e12, "gbs": v[3] / (v[1] * 1e-3) / 1e9}
+                           for k, v in sorted(detail.items(), key=lambda kv: -kv[1][1])}, f, indent=1)
+        except OSError:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",

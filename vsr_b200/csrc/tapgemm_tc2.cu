@@ -184,8 +184,6 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
         col_s[i] = make_uint2(pack_tap(__ldg(a.tap_tab + i)), (uint32_t)i | (1u << 24));
   }
   const bool bias_in_smem = (epi & VSR_EPI_BIAS) && a.Cout <= kBiasFloats;
-  if (bias_in_smem)
-    for (int i = threadIdx.x; i < a.Cout; i += blockDim.x) bias_s[i] = __ldg(a.bias + i);
   const uint32_t b_bytes = static_cast<uint32_t>(a.nt) * 128u;
   const uint32_t a_bytes = static_cast<uint32_t>(a.a_bytes);
   const uint32_t stage_bytes = static_cast<uint32_t>(a.stage_bytes);
@@ -216,9 +214,16 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
     ptx::tmem_alloc(tmem_slot, kTmemCols);
     ptx::tmem_relinquish();
   }
+  // Everything above reads only launch-time constants (tables uploaded when the layer plan was built,
+  // kernel arguments) and this CTA's own shared / tensor memory; tensors written by earlier kernels
+  // are touched only below this point.
+  ptx::pdl_wait();
+  if (bias_in_smem)
+    for (int i = threadIdx.x; i < a.Cout; i += blockDim.x) bias_s[i] = __ldg(a.bias + i);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
+  ptx::pdl_launch_dependents();
   const uint32_t tmem_base = *tmem_slot_gen;
   const uint64_t g_t1 = ptx::globaltimer_ns();
 
@@ -785,7 +790,27 @@ int tapgemm_tc2_launch(const VsrTapGemmDesc* d, cudaStream_t stream) {
   if (env_grid && atoi(env_grid) >= 1) grid = atoi(env_grid);
   if (grid > a.num_tiles) grid = a.num_tiles;
   if (grid > kPartialsLen) grid = kPartialsLen;
-  kernel<<<grid, kThreads, smem, stream>>>(a);
+  {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    const char* env_pdl = getenv("VSR_PDL");
+    if (!(env_pdl && env_pdl[0] == '0')) {
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+    }
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, a);
+    if (e != cudaSuccess) {
+      set_error("tapgemm_tc2: launch failed: %s", cudaGetErrorString(e));
+      return VSR_ERR_CUDA;
+    }
+  }
   VSR_CHECK_LAUNCH("tapgemm_tc2");
   return VSR_OK;
 }

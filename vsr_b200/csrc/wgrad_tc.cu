@@ -12,6 +12,8 @@
 //
 // Replaces the weight half of aten.convolution_backward under drf_net.py:55-106,141-147.
 #include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "ptx_sm100.cuh"
@@ -108,9 +110,11 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
     ptx::tmem_alloc(tmem_slot, kTmemCols);
     ptx::tmem_relinquish();
   }
+  ptx::pdl_wait();            // nothing above touches tensors written by earlier kernels
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
+  ptx::pdl_launch_dependents();
   const uint32_t tmem_base = *tmem_slot_gen;
 
   if (warp == 0) {
@@ -372,7 +376,27 @@ int wgrad_tc_partial(const VsrTapGemmDesc* d, int want_bias, int slice, int n_sl
   a.num_ptiles = p.num_ptiles;
   const int nb = p.ncta / 64;
   const int smem = kCtrl + 1024 + 2 * nb * kTileBytes + kAStages * 2 * kTileBytes;
-  wgrad_tc_kernel<<<p.n_items * p.splits, kThreads, smem, stream>>>(a);
+  {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(p.n_items * p.splits);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    const char* env_pdl = getenv("VSR_PDL");
+    if (!(env_pdl && env_pdl[0] == '0')) {
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+    }
+    cudaError_t e = cudaLaunchKernelEx(&cfg, wgrad_tc_kernel, a);
+    if (e != cudaSuccess) {
+      set_error("wgrad_tc: launch failed: %s", cudaGetErrorString(e));
+      return VSR_ERR_CUDA;
+    }
+  }
   VSR_CHECK_LAUNCH("wgrad_tc");
   return VSR_OK;
 }
