@@ -235,6 +235,16 @@ int vsr_ssim(const float* out, const float* target, int32_t n, int32_t h, int32_
              const float* win11, float mean, float std, float c1, float c2, float* ssim_out,
              void* workspace, size_t workspace_bytes, void* stream);
 
+/*
+ * The same for volumes (metrics.py:51-113 with dim=3: F.conv3d with the 11x11x11 product window): three
+ * separable passes over the five moment maps, valid convolution, per-sample mean.  vols are [n][d][h][w].
+ * workspace >= vsr_ssim3d_workspace(n, d, h, w) bytes.
+ */
+size_t vsr_ssim3d_workspace(int32_t n, int32_t d, int32_t h, int32_t w_);
+int vsr_ssim3d(const float* out, const float* target, int32_t n, int32_t d, int32_t h, int32_t w_,
+               const float* win11, float mean, float std, float c1, float c2, float* ssim_out,
+               void* workspace, size_t workspace_bytes, void* stream);
+
 /* nn.PixelShuffle / its inverse on NCHW fp32 (standalone, for the kernel sweep; the nets never
  * launch it).  x [n, c*r*r, h, w] -> y [n, c, h*r, w*r]  (drf_net.py:142). */
 int vsr_pixel_shuffle(const float* x, float* y, int32_t n, int32_t c, int32_t h, int32_t w_,

@@ -55,5 +55,6 @@ def load():
     utils = _load("src.utils", "src/utils.py")
     ns.HuberLoss, ns.CharbonnierLoss = losses.HuberLoss, losses.CharbonnierLoss
     ns.PSNR, ns.SSIM = metrics.PSNR, metrics.SSIM
+    ns.CardiacPSNR, ns.CardiacSSIM = metrics.CardiacPSNR, metrics.CardiacSSIM
     ns.denormalize = utils.denormalize
     return ns

@@ -146,5 +146,36 @@ def main():
     print("losses_metrics", {k: float(v) for k, v in fx.items() if v.dim() == 0})
 
 
+def metrics3d():
+    """SSIM(dim=3) and the Cardiac* wrappers (metrics.py:51-165) of the real reference on a seeded volume."""
+    import pickle
+    import tempfile
+    ref = load_reference.load()
+    g = torch.Generator().manual_seed(11)
+    a = torch.randn(2, 1, 13, 20, 18, generator=g)
+    b = a + 0.3 * torch.randn(2, 1, 13, 20, 18, generator=g)
+    da, db = ref.denormalize(a, "acdc"), ref.denormalize(b, "acdc")
+    box = {"patient007": (3, 31, 2, 30)}
+    with tempfile.NamedTemporaryFile(suffix=".pkl", delete=False) as f:
+        pickle.dump(box, f)
+    a2, b2 = da[:, :, 0].repeat(1, 1, 2, 2), db[:, :, 0].repeat(1, 1, 2, 2)       # [2,1,40,36] images
+    fx = {
+        "a": a, "b": b,
+        "ssim3_mean": ref.SSIM(dim=3)(da, db), "ssim3_per": ref.SSIM(dim=3, size_average=False)(da, db),
+        "ssim3_window": ref.SSIM(dim=3).weight.detach().clone(),
+        "box": box, "img_a": a2, "img_b": b2,
+        "cardiac_psnr": ref.CardiacPSNR(f.name)(a2, b2, "patient007"),
+        "cardiac_ssim": ref.CardiacSSIM(f.name)(a2, b2, "patient007"),
+    }
+    os.unlink(f.name)
+    torch.save(fx, os.path.join(OUT, "metrics3d.pt"))
+    print("metrics3d", {k: float(v) for k, v in fx.items() if torch.is_tensor(v) and v.dim() == 0})
+
+
 if __name__ == "__main__":
-    main()
+    import sys
+    if len(sys.argv) > 1 and sys.argv[1] == "metrics3d":      # added later: leaves the other fixtures untouched
+        metrics3d()
+    else:
+        main()
+        metrics3d()

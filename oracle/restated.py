@@ -171,19 +171,25 @@ def ssim_window_1d(dtype=torch.float32):
     return (g / g.sum()).to(dtype)
 
 
-def ssim(o, t, value_range=255, size_average=True):   # metrics.py:51-113, dim=2, channels=1
+def ssim(o, t, value_range=255, size_average=True, dim=2):   # metrics.py:51-113, channels=1
     c1, c2 = (0.01 * value_range) ** 2, (0.03 * value_range) ** 2
-    grids = torch.meshgrid([torch.arange(11, dtype=torch.float32)] * 2, indexing="ij")
+    grids = torch.meshgrid([torch.arange(11, dtype=torch.float32)] * dim, indexing="ij")
     k = 1
     for g in grids:
         k = k * (1 / (1.5 * math.sqrt(2 * math.pi)) * torch.exp(-((g - 5) / (2 * 1.5)) ** 2))
-    k = (k / k.sum()).to(o.dtype).view(1, 1, 11, 11)
-    mu1, mu2 = F.conv2d(o, k), F.conv2d(t, k)
-    s11 = F.conv2d(o * o, k) - mu1.pow(2)
-    s22 = F.conv2d(t * t, k) - mu2.pow(2)
-    s12 = F.conv2d(o * t, k) - mu1 * mu2
+    k = (k / k.sum()).to(o.dtype).view(1, 1, *[11] * dim)
+    conv = F.conv2d if dim == 2 else F.conv3d            # metrics.py:60-63
+    mu1, mu2 = conv(o, k), conv(t, k)
+    s11 = conv(o * o, k) - mu1.pow(2)
+    s22 = conv(t * t, k) - mu2.pow(2)
+    s12 = conv(o * t, k) - mu1 * mu2
     m = ((2 * mu1 * mu2 + c1) * (2.0 * s12 + c2)) / ((mu1.pow(2) + mu2.pow(2) + c1) * (s11 + s22 + c2))
     return m.mean() if size_average else m.mean(dim=list(range(1, o.dim())))
+
+
+def cardiac(metric, o, t, box):   # CardiacPSNR / CardiacSSIM.forward — metrics.py:131-139,157-165
+    h0, hn, w0, wn = box
+    return metric(o[..., h0:hn, w0:wn], t[..., h0:hn, w0:wn])
 
 
 def vsr_metrics(outputs, targets, dataset="acdc"):

@@ -121,6 +121,27 @@ def test_psnr_ssim_match_reference_known_answers():
     assert torch.allclose(out.cpu(), want, atol=2e-5)
 
 
+def test_ssim3d_and_cardiac_metrics_match_reference_golden(tmp_path):
+    """SSIM(dim=3) (metrics.py:51-113) and CardiacPSNR / CardiacSSIM (:116-165) through the drop-in classes."""
+    import pickle
+    from vsr_b200.metrics import SSIM, CardiacPSNR, CardiacSSIM
+    fx = torch.load(os.path.join(GOLDEN, "metrics3d.pt"))
+    a, b = fx["a"].cuda(), fx["b"].cuda()
+    m = SSIM(dim=3, dataset="acdc").cuda()                      # fused denormalize
+    assert abs(float(m(a, b)) - float(fx["ssim3_mean"])) <= 2e-5
+    per = SSIM(dim=3, size_average=False, dataset="acdc").cuda()(a, b)
+    assert torch.allclose(per.cpu(), fx["ssim3_per"], atol=2e-5)
+    assert torch.allclose(m.weight.cpu(), fx["ssim3_window"], atol=1e-9)
+    with pytest.raises(ValueError):
+        SSIM(dim=3).cuda()(a[:, :, 0], b[:, :, 0])
+    path = tmp_path / "coords.pkl"
+    with open(path, "wb") as f:
+        pickle.dump(fx["box"], f)
+    ia, ib = fx["img_a"].cuda(), fx["img_b"].cuda()
+    assert abs(float(CardiacPSNR(str(path)).cuda()(ia, ib, "patient007")) - float(fx["cardiac_psnr"])) <= 1e-3
+    assert abs(float(CardiacSSIM(str(path)).cuda()(ia, ib, "patient007")) - float(fx["cardiac_ssim"])) <= 2e-5
+
+
 def test_small_helpers():
     ops, emu, g = _ops(), EmuOps(), _g(4)
     src = torch.randn(1000, device="cuda", generator=g)

@@ -106,6 +106,19 @@ def test_losses_metrics_known_answers():
     assert torch.allclose(restated.ssim(da, db, size_average=False), fx["ssim_per"], atol=1e-5)
 
 
+def test_ssim3d_and_cardiac_match_reference_golden():
+    # metrics.py:51-113 with dim=3 and the Cardiac* wrappers (:116-165), values from the real reference
+    fx = torch.load(os.path.join(GOLDEN, "metrics3d.pt"))
+    da, db = restated.denormalize(fx["a"], "acdc"), restated.denormalize(fx["b"], "acdc")
+    assert abs(float(restated.ssim(da, db, dim=3)) - float(fx["ssim3_mean"])) <= 1e-5
+    assert torch.allclose(restated.ssim(da, db, dim=3, size_average=False), fx["ssim3_per"], atol=1e-5)
+    w1 = restated.ssim_window_1d()
+    assert torch.allclose(torch.einsum("i,j,k->ijk", w1, w1, w1), fx["ssim3_window"][0, 0], atol=1e-9)
+    box = fx["box"]["patient007"]
+    assert abs(float(restated.cardiac(restated.psnr, fx["img_a"], fx["img_b"], box)) - float(fx["cardiac_psnr"])) <= 1e-4
+    assert abs(float(restated.cardiac(restated.ssim, fx["img_a"], fx["img_b"], box)) - float(fx["cardiac_ssim"])) <= 1e-5
+
+
 def test_ssim_window_is_the_reference_quirk():
     # metrics.py:74: exp(-((i-5)/(2 sigma))^2) — effective sigma = 1.5*sqrt(2), not 1.5
     fx = torch.load(os.path.join(GOLDEN, "drfnet_f8_g2_x2.pt"))

@@ -81,6 +81,10 @@ _SIGS = {
     "vsr_ssim": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                            C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p,
                            C.c_size_t, C.c_void_p]),
+    "vsr_ssim3d_workspace": (C.c_size_t, [C.c_int32] * 4),
+    "vsr_ssim3d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                             C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p,
+                             C.c_size_t, C.c_void_p]),
     "vsr_pixel_shuffle": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                     C.c_int32, C.c_int32, C.c_int, C.c_void_p]),
     "vsr_upsample_linear": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 7 + [C.c_int,

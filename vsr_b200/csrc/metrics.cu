@@ -186,6 +186,77 @@ __global__ void ssim_final_kernel(const float* __restrict__ ws, int n, int tiles
   ssim[i] = s * inv_count;
 }
 
+// ---- SSIM over volumes (dim = 3): the 11^3 window is separable; three passes over the five moment
+// maps (x, y, x^2, y^2, xy): along w (from the images, denormalised on load), along h, along d (fused
+// with the SSIM formula and a per-block partial sum).  Maps are stored [5][n][d][h'][w'].
+__global__ void __launch_bounds__(256) ssim3_w_kernel(const float* __restrict__ out, const float* __restrict__ tgt,
+                                                     long rows, int w, const float* __restrict__ win, float mean,
+                                                     float std, int denorm_on, float* __restrict__ m) {
+  const int ow = w - (kWin - 1);
+  const long total = rows * ow;
+  const long stride5 = total;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / ow;
+    const int x = (int)(i - r * ow);
+    const float* o = out + r * w + x;
+    const float* t = tgt + r * w + x;
+    float m1 = 0.f, m2 = 0.f, s11 = 0.f, s22 = 0.f, s12 = 0.f;
+#pragma unroll
+    for (int k = 0; k < kWin; ++k) {
+      const float a = denorm(__ldg(o + k), mean, std, denorm_on), b = denorm(__ldg(t + k), mean, std, denorm_on);
+      const float wk = __ldg(win + k);
+      m1 = fmaf(wk, a, m1); m2 = fmaf(wk, b, m2);
+      s11 = fmaf(wk, a * a, s11); s22 = fmaf(wk, b * b, s22); s12 = fmaf(wk, a * b, s12);
+    }
+    m[i] = m1; m[stride5 + i] = m2; m[2 * stride5 + i] = s11; m[3 * stride5 + i] = s22; m[4 * stride5 + i] = s12;
+  }
+}
+// valid 11-tap sum along the middle axis of [planes][len][inner] -> [planes][len-10][inner]
+__global__ void __launch_bounds__(256) ssim3_axis_kernel(const float* __restrict__ src, long planes, int len, long inner,
+                                                        const float* __restrict__ win, float* __restrict__ dst) {
+  const int ol = len - (kWin - 1);
+  const long total = planes * ol * inner;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long x = i % inner;
+    const long q = i / inner;
+    const int y = (int)(q % ol);
+    const long pl = q / ol;
+    const float* sp = src + (pl * len + y) * inner + x;
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < kWin; ++k) acc = fmaf(__ldg(win + k), __ldg(sp + k * inner), acc);
+    dst[i] = acc;
+  }
+}
+// last axis (d) + SSIM formula; grid (blocks, n); src is [5][n][d][inner]; partial sums per (n, block)
+__global__ void __launch_bounds__(256) ssim3_d_kernel(const float* __restrict__ src, int n, int d, long inner,
+                                                     const float* __restrict__ win, float c1, float c2,
+                                                     float* __restrict__ ws) {
+  __shared__ float red[32];
+  const int od = d - (kWin - 1);
+  const long per = (long)od * inner;
+  const long stride5 = (long)n * d * inner;
+  const float* base = src + (size_t)blockIdx.y * d * inner;
+  float acc = 0.f;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < per; i += (long)gridDim.x * blockDim.x) {
+    const long x = i % inner;
+    const int z = (int)(i / inner);
+    float v[5];
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+      const float* sp = base + q * stride5 + (long)z * inner + x;
+      float sv = 0.f;
+#pragma unroll
+      for (int k = 0; k < kWin; ++k) sv = fmaf(__ldg(win + k), __ldg(sp + k * inner), sv);
+      v[q] = sv;
+    }
+    const float var1 = v[2] - v[0] * v[0], var2 = v[3] - v[1] * v[1], cov = v[4] - v[0] * v[1];
+    acc += ((2.f * v[0] * v[1] + c1) * (2.f * cov + c2)) / ((v[0] * v[0] + v[1] * v[1] + c1) * (var1 + var2 + c2));
+  }
+  const float sm = block_sum(acc, red);
+  if (threadIdx.x == 0) ws[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = sm;
+}
+
 int psnr_bps(long per_sample, int n) {
   long b = (per_sample + 4095) / 4096;
   long want = ((long)num_sms() * 4 + n - 1) / n;
@@ -260,5 +331,39 @@ extern "C" int vsr_ssim(const float* out, const float* target, int32_t n, int32_
   VSR_CHECK_LAUNCH("vsr_ssim");
   ssim_final_kernel<<<(n + 127) / 128, 128, 0, s>>>(ws, n, tiles_x * tiles_y, 1.f / ((float)oh * (float)ow), ssim_out);
   VSR_CHECK_LAUNCH("vsr_ssim_final");
+  return VSR_OK;
+}
+
+extern "C" size_t vsr_ssim3d_workspace(int32_t n, int32_t d, int32_t h, int32_t w_) {
+  const size_t m1 = (size_t)5 * n * d * h * (size_t)(w_ > 10 ? w_ - 10 : 0);
+  const size_t m2 = (size_t)5 * n * d * (size_t)(h > 10 ? h - 10 : 0) * (size_t)(w_ > 10 ? w_ - 10 : 0);
+  return (m1 + m2 + (size_t)n * 1024 + 64) * sizeof(float);
+}
+
+extern "C" int vsr_ssim3d(const float* out, const float* target, int32_t n, int32_t d, int32_t h, int32_t w_,
+                          const float* win11, float mean, float std, float c1, float c2, float* ssim_out,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+  VSR_CHECK_ARG(out && target && ssim_out && win11 && n > 0, "vsr_ssim3d: bad arguments");
+  VSR_CHECK_ARG(d >= 11 && h >= 11 && w_ >= 11, "vsr_ssim3d: volume smaller than the 11x11x11 window");
+  VSR_CHECK_ARG(workspace && workspace_bytes >= vsr_ssim3d_workspace(n, d, h, w_), "vsr_ssim3d: workspace too small");
+  VSR_CHECK_SUPPORTED(n <= 65535, "vsr_ssim3d: batch too large");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int od = d - 10, oh = h - 10, ow = w_ - 10;
+  float* m1 = static_cast<float*>(workspace);
+  float* m2 = m1 + (size_t)5 * n * d * h * ow;
+  float* part = m2 + (size_t)5 * n * d * oh * ow;
+  const long rows = (long)n * d * h;
+  ssim3_w_kernel<<<grid_for(rows * ow, 256, 8), 256, 0, s>>>(out, target, rows, w_, win11, mean, std, std > 0.f, m1);
+  VSR_CHECK_LAUNCH("vsr_ssim3d(w)");
+  ssim3_axis_kernel<<<grid_for((long)5 * n * d * oh * ow, 256, 8), 256, 0, s>>>(m1, (long)5 * n * d, h, ow, win11, m2);
+  VSR_CHECK_LAUNCH("vsr_ssim3d(h)");
+  const long per = (long)od * oh * ow;
+  int bps = (int)((per + 2047) / 2048);
+  if (bps > 1024) bps = 1024;
+  if (bps < 1) bps = 1;
+  ssim3_d_kernel<<<dim3(bps, n), 256, 0, s>>>(m2, n, d, (long)oh * ow, win11, c1, c2, part);
+  VSR_CHECK_LAUNCH("vsr_ssim3d(d)");
+  ssim_final_kernel<<<(n + 127) / 128, 128, 0, s>>>(part, n, bps, 1.f / (float)per, ssim_out);
+  VSR_CHECK_LAUNCH("vsr_ssim3d_final");
   return VSR_OK;
 }

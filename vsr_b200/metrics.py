@@ -41,15 +41,14 @@ class PSNR(nn.Module):
 
 
 class SSIM(nn.Module):
-    """The SSIM score (metrics.py:39-113), dim=2. The window reproduces the reference's
-    exp(-((i-5)/(2*sigma))^2), sigma=1.5, normalised (metrics.py:74-77), applied separably."""
+    """The SSIM score (metrics.py:39-113), dim=2 (images [N,C,H,W]) or dim=3 (volumes [N,C,D,H,W]). The window
+    reproduces the reference's exp(-((i-5)/(2*sigma))^2), sigma=1.5, normalised (metrics.py:74-77); the
+    product window is applied separably (one fused pass for dim=2, three passes for dim=3)."""
 
     def __init__(self, dim=2, channels=1, size_average=True, value_range=255, dataset=None):
         super().__init__()
         if dim not in (2, 3):
             raise ValueError(f"Only dim=2, 3 are supported. Received dim={dim}.")
-        if dim == 3:
-            raise NotImplementedError("SSIM(dim=3) is not implemented yet (SURVEY.md §8f rank 2)")
         self.dim, self.channels = dim, channels
         self.size_average, self.value_range = size_average, value_range
         self.c1, self.c2 = (0.01 * value_range) ** 2, (0.03 * value_range) ** 2
@@ -57,8 +56,8 @@ class SSIM(nn.Module):
         g = 1 / (1.5 * math.sqrt(2 * math.pi)) * torch.exp(-((i - 5) / (2 * 1.5)) ** 2)
         self.register_buffer("window", g / g.sum())
         # the reference registers the full 2-D kernel as `weight`; keep the buffer for state parity
-        k2 = torch.outer(g, g)
-        self.register_buffer("weight", (k2 / k2.sum()).view(1, 1, 11, 11).repeat(channels, 1, 1, 1))
+        k = torch.outer(g, g) if dim == 2 else torch.einsum("i,j,k->ijk", g, g, g)
+        self.register_buffer("weight", (k / k.sum()).view(1, 1, *k.shape).repeat(channels, *[1] * (dim + 1)))
         self.groups = channels
         self.mean, self.std = DATASET_STATS[dataset] if dataset else (0.0, -1.0)
 
@@ -68,6 +67,16 @@ class SSIM(nn.Module):
         _check(output, target)
         ops = cuda_ops()
         o, t = output.detach().float().contiguous(), target.detach().float().contiguous()
+        if o.dim() != self.dim + 2:
+            raise ValueError(f"SSIM(dim={self.dim}) expects a {self.dim + 2}-D tensor, got {o.dim()}-D")
+        if self.dim == 3:
+            n, c, d, h, w = o.shape
+            o, t = o.view(n * c, d, h, w), t.view(n * c, d, h, w)
+            ws = torch.empty(ops.ssim3d_workspace(n * c, d, h, w) // 4 + 4, dtype=torch.float32, device=o.device)
+            out = torch.empty(n * c, dtype=torch.float32, device=o.device)
+            ops.ssim3d(o, t, self.window, self.mean, self.std, self.c1, self.c2, out, ws)
+            out = out.view(n, c).mean(1)
+            return out.mean() if self.size_average else out
         n, c, h, w = o.shape
         # depthwise (groups == channels): every channel is an independent image
         o, t = o.view(n * c, h, w), t.view(n * c, h, w)
@@ -76,3 +85,30 @@ class SSIM(nn.Module):
         ops.ssim(o, t, self.window, self.mean, self.std, self.c1, self.c2, out, ws)
         out = out.view(n, c).mean(1)
         return out.mean() if self.size_average else out
+
+
+class _Cardiac(nn.Module):
+    """Metric restricted to the cardiac bounding box of a patient (metrics.py:116-165): the pickle at
+    `coordinates_path` maps patient name -> (h0, hn, w0, wn); forward(output, target, name)."""
+    metric_cls = None
+
+    def __init__(self, coordinates_path, **kwargs):
+        super().__init__()
+        import pickle
+        self.metric = self.metric_cls(**kwargs)
+        with open(coordinates_path, "rb") as f:
+            self.coordinates = pickle.load(f)
+
+    def forward(self, output, target, name):
+        h0, hn, w0, wn = self.coordinates[name]
+        return self.metric(output[..., h0:hn, w0:wn], target[..., h0:hn, w0:wn])
+
+
+class CardiacPSNR(_Cardiac):
+    """The cardiac PSNR score (metrics.py:116-139)."""
+    metric_cls = PSNR
+
+
+class CardiacSSIM(_Cardiac):
+    """The cardiac SSIM score (metrics.py:142-165)."""
+    metric_cls = SSIM

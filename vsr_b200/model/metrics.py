@@ -1,1 +1,1 @@
-from ..metrics import PSNR, SSIM  # noqa: F401
+from ..metrics import PSNR, SSIM, CardiacPSNR, CardiacSSIM  # noqa: F401

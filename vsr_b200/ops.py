@@ -312,6 +312,17 @@ class CudaOps:
               "vsr_ssim")
         self.launches += 2
 
+    def ssim3d_workspace(self, n, d, h, w_):
+        return self.lib.vsr_ssim3d_workspace(n, d, h, w_)
+
+    def ssim3d(self, out, target, win11, mean, std, c1, c2, ssim_out, workspace):
+        _need_cuda(out, target, win11, ssim_out, workspace)
+        n, d, h, w_ = out.shape
+        check(self.lib.vsr_ssim3d(_p(out), _p(target), n, d, h, w_, _p(win11), mean, std, c1, c2, _p(ssim_out),
+                                  _p(workspace), workspace.numel() * workspace.element_size(), _stream()),
+              "vsr_ssim3d")
+        self.launches += 4
+
     # ---- standalone resampling / optimiser ------------------------------------------------
     def pixel_shuffle(self, x, y, r, inverse=False):
         _need_cuda(x, y)
