@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
     }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(tfull_bar + 8 * b, 1);
-      ptx::mbar_init(tempty_bar + 8 * b, kEpiWarps);
+      ptx::mbar_init(tempty_bar + 8 * b, a.nt > 64 ? kEpiWarps : kEpiWarps / 2);
     }
     ptx::mbar_init(bres_full, 1);
     ptx::mbar_init(bres_empty, 1);
@@ -365,15 +365,20 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
     // ===================== epilogue (8 warps: TMEM lane quarter x chunk parity) =====================
     const int ew = warp - kEpiWarp0;
     const int quarter = warp & 3;                 // TMEM lanes [32*quarter, 32*quarter+32) = tile pixels
-    const int chalf = ew >> 2;                    // this warp drains the 64-channel chunks c = 64*chalf (mod 128)
-    const int c_first = 64 * chalf;
-    // warps without a chunk (nt == 64, chalf == 1) only take part in the barrier protocol
-    const int slot = a.nt > 64 ? ew : (ew & 3);   // staging tiles exist for active warps only
+    // nt > 64: the two warps of a lane quarter split every tile by chunk parity (c = 64*chalf mod 128);
+    // nt == 64 (one chunk per tile): they alternate tiles instead, i.e. warp set `chalf` owns TMEM
+    // buffer `chalf`, which doubles the time each warp has to hide its operand loads
+    const int chalf = ew >> 2;
+    const bool by_tile = a.nt <= 64;
+    const int c_first = by_tile ? 0 : 64 * chalf;
+    const int my_step = by_tile ? 2 * tile_step : tile_step;       // distance between this warp's tiles
+    const int my_begin = by_tile ? tile_begin + chalf * tile_step : tile_begin;
+    const int slot = ew;
     // this warp's 32 pixels as a sub-box of the bw x bh tile (the epilogue maps have box ew x eh)
     const int sub_x = (quarter * 32) & (a.bw - 1);
     const int sub_y = (quarter * 32) >> a.bw_shift;
     const bool skip = (a.debug & 1) != 0;
-    const bool has_in = (epi & kEpiIn) != 0 && !skip && c_first < a.nt;
+    const bool has_in = (epi & kEpiIn) != 0 && !skip;
     const int n_in = ((epi & VSR_EPI_RES_PRE) ? 1 : 0) + ((epi & (VSR_EPI_PRELU_BWD | VSR_EPI_RELU_BWD)) ? 1 : 0) +
                      ((epi & VSR_EPI_OUT2) ? 1 : 0);
     const uint32_t out_t = epi_base + slot * (1 + n_in) * kTileBytes;
@@ -403,20 +408,21 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
         issue_in(tc.n, tc.y0 + m * a.bh, tc.x0, o0 + c + 128);
       } else if (m + 1 < a.mb) {
         issue_in(tc.n, tc.y0 + (m + 1) * a.bh, tc.x0, o0 + c_first);
-      } else if (tile + tile_step < tile_end) {
-        const TileCoord t2 = decode_tile(a, tile + tile_step);
+      } else if (tile + my_step < tile_end) {
+        const TileCoord t2 = decode_tile(a, tile + my_step);
         const int4 g2 = grp_in_smem ? grp_s[t2.g] : __ldg(a.group_tab + t2.g);
         issue_in(t2.n, t2.y0, t2.x0, g2.x + c_first);
       }
     };
 
-    if (has_in && lane == 0 && tile_begin < tile_end) {
-      const TileCoord t0 = decode_tile(a, tile_begin);
+    if (has_in && lane == 0 && my_begin < tile_end) {
+      const TileCoord t0 = decode_tile(a, my_begin);
       const int4 g0 = grp_in_smem ? grp_s[t0.g] : __ldg(a.group_tab + t0.g);
       issue_in(t0.n, t0.y0, t0.x0, g0.x + c_first);
     }
     int it = 0;
     for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++it) {
+      if (by_tile && (it & 1) != chalf) continue;
       const TileCoord tc = decode_tile(a, tile);
       const int4 grp = grp_in_smem ? grp_s[tc.g] : __ldg(a.group_tab + tc.g);
       const int buf = it & 1;
@@ -726,7 +732,7 @@ int tapgemm_tc2_launch(const VsrTapGemmDesc* d, cudaStream_t stream) {
   a.row_bytes = bw * 128;
   const int n_in = ((d->epi & VSR_EPI_RES_PRE) ? 1 : 0) + ((d->epi & (VSR_EPI_PRELU_BWD | VSR_EPI_RELU_BWD)) ? 1 : 0) +
                    ((d->epi & VSR_EPI_OUT2) ? 1 : 0);
-  a.epi_bytes = (d->nt > 64 ? kEpiWarps : 4) * (1 + n_in) * kTileBytes;
+  a.epi_bytes = kEpiWarps * (1 + n_in) * kTileBytes;
   const int b_bytes = d->nt * 128;
   const long avail = kSmemBudget - kCtrlBytes - a.epi_bytes;
   const char* env_dbg = getenv("VSR_TC_DEBUG");            // re-read per launch: attribution sweeps flip it

@@ -12,6 +12,8 @@
 //
 // Replaces the weight half of aten.convolution_backward under drf_net.py:55-106,141-147.
 #include <cuda.h>
+
+#include <vector>
 #include <stdlib.h>
 #include <string.h>
 
@@ -28,15 +30,24 @@ namespace {
 
 constexpr int kTile = 128;
 constexpr int kTileBytes = kTile * 128;   // one [128 px x 64 ch] bf16 box
-constexpr int kAStages = 4;               // ring of tap pairs (2 boxes each)
+constexpr int kMaxAStages = 6;            // ring of tap pairs (2 boxes each); as many as shared memory holds
 constexpr int kMaxChunk = 8;              // taps per work item
 constexpr int kCtrl = 1024;
 constexpr int kThreads = 192;
 constexpr int kTmemCols = 512;
 
+constexpr int kMaxPerm = 256;             // taps whose pairing order can travel in the kernel arguments
+
 struct WgArgs {
   CUtensorMap src_maps[VSR_MAX_SRCS];
+  CUtensorMap tall_maps[VSR_MAX_SRCS];   // shared-pair mode: box of bh + 1 pixel rows
   CUtensorMap dz_map;
+  uint16_t perm[kMaxPerm];               // position in the pairing order -> tap index (identity if unused)
+  int use_perm;                          // perm[] is valid
+  int tall;                              // every pair (2p, 2p+1) is (tap, same tap one pixel row lower): one A load
+  int row_bytes;                         // bw * 128
+  int stages;                            // tap-pair ring depth
+  int debug;                             // VSR_WG_DEBUG: 32 = per-role cycle counts of block 0
   const int4* tap_tab;
   const int4* group_tab;
   float* ws;              // [splits][n_taps_total][nt][64]
@@ -74,7 +85,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
   const int nb = a.ncta / 64;                                // dz boxes per tile
   const uint32_t b_bytes = nb * kTileBytes;
   const uint32_t b_base = base + kCtrl;                      // 2 buffers
-  const uint32_t a_base = b_base + 2 * b_bytes;              // kAStages x 2 boxes
+  const uint32_t a_base = b_base + 2 * b_bytes;              // a.stages x 2 boxes
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int item_i = blockIdx.x % a.n_items, split = blockIdx.x / a.n_items;
@@ -95,7 +106,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
 
   float cs0_out = 0.f, cs1_out = 0.f;
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < kAStages; ++s) {
+    for (int s = 0; s < a.stages; ++s) {
       ptx::mbar_init(a_full + 8 * s, 1);
       ptx::mbar_init(a_empty + 8 * s, 1);
     }
@@ -118,68 +129,117 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
   const uint32_t tmem_base = *tmem_slot_gen;
 
   if (warp == 0) {
-    if (lane == 0) {
+    // The whole warp walks the (uniform) loops and one elected lane issues: the operands stay on the
+    // uniform datapath (see tapgemm_tc2.cu).
+    {
+      const bool leader = ptx::elect_one();
+      const bool prof = (a.debug & 32) != 0;
+      long long p_wb = 0, p_wa = 0, p_t0 = clock64(), c0 = 0;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
       int4 taps[kMaxChunk];                     // the chunk's taps, fetched once (independent loads)
 #pragma unroll
-      for (int i = 0; i < kMaxChunk; ++i) taps[i] = __ldg(a.tap_tab + item.z + (i < item.w ? i : 0));
+      for (int i = 0; i < kMaxChunk; ++i) {
+        const int pos = item.z + (i < item.w ? i : 0);
+        int4 t = __ldg(a.tap_tab + (a.use_perm ? (int)a.perm[pos] : pos));
+        t.x = __shfl_sync(0xffffffffu, t.x, 0);
+        t.y = __shfl_sync(0xffffffffu, t.y, 0);
+        t.z = __shfl_sync(0xffffffffu, t.z, 0);
+        t.w = __shfl_sync(0xffffffffu, t.w, 0);
+        taps[i] = t;
+      }
       for (int pt = pt0; pt < pt1; ++pt, ++it) {
         int n, y0, x0;
         tile_coord(a, pt, &n, &y0, &x0);
         const int bb = it & 1;
+        if (prof) c0 = clock64();
         ptx::mbar_wait(b_empty + 8 * bb, ((it >> 1) & 1) ^ 1u);
-        ptx::mbar_arrive_expect_tx(b_full + 8 * bb, b_bytes);
-        for (int i = 0; i < nb; ++i)
-          ptx::tma_load_4d(b_base + bb * b_bytes + i * kTileBytes, &a.dz_map, b_full + 8 * bb,
-                           grp.x + item.y + i * 64, x0, y0, n);
+        if (prof) p_wb += clock64() - c0;
+        if (leader) {
+          ptx::mbar_arrive_expect_tx(b_full + 8 * bb, b_bytes);
+          for (int i = 0; i < nb; ++i)
+            ptx::tma_load_4d(b_base + bb * b_bytes + i * kTileBytes, &a.dz_map, b_full + 8 * bb,
+                             grp.x + item.y + i * 64, x0, y0, n);
+        }
         for (int p = 0; p < n_pairs; ++p) {
+          if (prof) c0 = clock64();
           ptx::mbar_wait(a_empty + 8 * stage, phase ^ 1u);
-          ptx::mbar_arrive_expect_tx(a_full + 8 * stage, 2 * kTileBytes);
+          if (prof) p_wa += clock64() - c0;
           const uint32_t sa = a_base + stage * 2 * kTileBytes;
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            int tl = 2 * p + h;
-            if (tl >= item.w) tl = 2 * p;                      // odd count: duplicate (rows ignored)
+          if (a.tall) {
+            // the pair is (tap, tap shifted one pixel row down): one box of bh + 1 rows serves both
             int4 tap = taps[0];
 #pragma unroll
-            for (int i = 1; i < kMaxChunk; ++i) tap = (i == tl) ? taps[i] : tap;
-            ptx::tma_load_4d(sa + h * kTileBytes, &a.src_maps[tap.x], a_full + 8 * stage, tap.w, x0 + tap.z,
-                             y0 + tap.y, n);
+            for (int i = 1; i < kMaxChunk; ++i) tap = (i == 2 * p) ? taps[i] : tap;
+            if (leader) {
+              ptx::mbar_arrive_expect_tx(a_full + 8 * stage, kTileBytes + a.row_bytes);
+              ptx::tma_load_4d(sa, &a.tall_maps[tap.x], a_full + 8 * stage, tap.w, x0 + tap.z, y0 + tap.y, n);
+            }
+          } else {
+            if (leader) ptx::mbar_arrive_expect_tx(a_full + 8 * stage, 2 * kTileBytes);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              int tl = 2 * p + h;
+              if (tl >= item.w) tl = 2 * p;                      // odd count: duplicate (rows ignored)
+              int4 tap = taps[0];
+#pragma unroll
+              for (int i = 1; i < kMaxChunk; ++i) tap = (i == tl) ? taps[i] : tap;
+              if (leader)
+                ptx::tma_load_4d(sa + h * kTileBytes, &a.src_maps[tap.x], a_full + 8 * stage, tap.w, x0 + tap.z,
+                                 y0 + tap.y, n);
+            }
           }
-          if (++stage == kAStages) { stage = 0; phase ^= 1u; }
+          if (++stage == a.stages) { stage = 0; phase ^= 1u; }
         }
       }
+      if (prof && blockIdx.x == 0 && leader)
+        printf("wg-prof producer: total %lld cyc, %d tiles x %d pairs, wait(b_empty) %lld, wait(a_empty) %lld, tall %d\n",
+               clock64() - p_t0, it, n_pairs, p_wb, p_wa, a.tall);
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
+      const bool leader = ptx::elect_one();
       const uint32_t idesc = ptx::make_idesc_bf16(128, a.ncta, 1, 1);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t lbo = a.tall ? a.row_bytes : kTileBytes;
+      const bool prof = (a.debug & 32) != 0;
+      long long m_wb = 0, m_wa = 0, m_is = 0, m_t0 = clock64(), c0 = 0, c1 = 0;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
       for (int pt = pt0; pt < pt1; ++pt, ++it) {
         const int bb = it & 1;
+        if (prof) c0 = clock64();
         ptx::mbar_wait(b_full + 8 * bb, (it >> 1) & 1);
         ptx::tc_fence_after();
+        if (prof) m_wb += clock64() - c0;
         const uint32_t sb = b_base + bb * b_bytes;
         for (int p = 0; p < n_pairs; ++p) {
+          if (prof) c0 = clock64();
           ptx::mbar_wait(a_full + 8 * stage, phase);
           ptx::tc_fence_after();
+          if (prof) { c1 = clock64(); m_wa += c1 - c0; }
           const uint32_t sa = a_base + stage * 2 * kTileBytes;
+          if (leader) {
 #pragma unroll
-          for (int k = 0; k < kTile / 16; ++k) {
-            // 16 pixels = two 8-row K groups = 2048 bytes
-            const uint64_t ad = mn_desc(sa + k * 2048, kTileBytes);
-            const uint64_t bd = mn_desc(sb + k * 2048, kTileBytes);
-            ptx::mma_bf16_ss(tmem_base + p * a.ncta, ad, bd, idesc, (it | k) != 0);
+            for (int k = 0; k < kTile / 16; ++k) {
+              // 16 pixels = two 8-row K groups = 2048 bytes
+              const uint64_t ad = mn_desc(sa + k * 2048, lbo);
+              const uint64_t bd = mn_desc(sb + k * 2048, kTileBytes);
+              ptx::mma_bf16_ss(tmem_u + p * a.ncta, ad, bd, idesc, (it | k) != 0);
+            }
+            ptx::mma_commit(a_empty + 8 * stage);
           }
-          ptx::mma_commit(a_empty + 8 * stage);
-          if (++stage == kAStages) { stage = 0; phase ^= 1u; }
+          if (prof) m_is += clock64() - c1;
+          if (++stage == a.stages) { stage = 0; phase ^= 1u; }
         }
-        ptx::mma_commit(b_empty + 8 * bb);
+        if (leader) ptx::mma_commit(b_empty + 8 * bb);
       }
-      ptx::mma_commit(done_bar);
+      if (leader) ptx::mma_commit(done_bar);
+      if (prof && blockIdx.x == 0 && leader)
+        printf("wg-prof mma: total %lld cyc, wait(b_full) %lld, wait(a_full) %lld, issue %lld\n", clock64() - m_t0, m_wb,
+               m_wa, m_is);
     }
   } else {
     const int quarter = warp & 3;
@@ -208,15 +268,17 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
         if (lane == 0) ptx::mbar_arrive(b_empty + 8 * bb);
       }
     }
+    const long long e_t0 = clock64();
     if (pt1 > pt0) {
       ptx::mbar_wait(done_bar, 0);
       ptx::tc_fence_after();
     }
+    const long long e_t1 = clock64();
     float* wsp = a.ws + (size_t)split * a.n_taps_total * a.nt * 64;
     for (int p = 0; p < n_pairs; ++p) {
       const int tl = 2 * p + half;
       const bool live = tl < item.w;
-      const int ti = item.z + tl;
+      const int ti = a.use_perm ? (int)a.perm[item.z + (live ? tl : 0)] : item.z + tl;
       const uint32_t taddr = tmem_base + p * a.ncta + (static_cast<uint32_t>(quarter * 32) << 16);
       for (int c = 0; c < a.ncta; c += 16) {
         uint32_t r[16];
@@ -234,6 +296,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
         }
       }
     }
+    if ((a.debug & 32) && blockIdx.x == 0 && warp == 2 && lane == 0)
+      printf("wg-prof epilogue: wait(done) %lld cyc, drain %lld cyc\n", e_t1 - e_t0, clock64() - e_t1);
     cs0_out = cs0;
     cs1_out = cs1;
   }
@@ -302,6 +366,42 @@ __global__ void __launch_bounds__(256) wg_reduce_kernel(const float4* __restrict
   }
 }
 
+// Host: order the taps as pairs (t, t') with equal (src, c0, dx) and dy' = dy + 1.  False if some tap has no partner.
+bool pair_rows(const int32_t* taps, int n, uint16_t* perm) {
+  std::vector<char> used(n, 0);
+  int out = 0;
+  for (int i = 0; i < n; ++i) {
+    if (used[i]) continue;
+    // i must be the upper tap of its pair: find the partner one row lower; if i is itself a lower row of an
+    // unused tap, that tap comes first
+    int up = i;
+    for (int j = 0; j < n; ++j)
+      if (!used[j] && j != i && taps[4 * j] == taps[4 * i] && taps[4 * j + 3] == taps[4 * i + 3] &&
+          taps[4 * j + 2] == taps[4 * i + 2] && taps[4 * j + 1] == taps[4 * i + 1] - 1) {
+        // prefer pairing (j, i) only if i has no lower partner of its own
+        bool has_lower = false;
+        for (int k = 0; k < n; ++k)
+          if (!used[k] && taps[4 * k] == taps[4 * i] && taps[4 * k + 3] == taps[4 * i + 3] &&
+              taps[4 * k + 2] == taps[4 * i + 2] && taps[4 * k + 1] == taps[4 * i + 1] + 1)
+            has_lower = true;
+        if (!has_lower) up = j;
+        break;
+      }
+    int low = -1;
+    for (int k = 0; k < n; ++k)
+      if (!used[k] && k != up && taps[4 * k] == taps[4 * up] && taps[4 * k + 3] == taps[4 * up + 3] &&
+          taps[4 * k + 2] == taps[4 * up + 2] && taps[4 * k + 1] == taps[4 * up + 1] + 1) {
+        low = k;
+        break;
+      }
+    if (low < 0) return false;
+    used[up] = used[low] = 1;
+    perm[out++] = (uint16_t)up;
+    perm[out++] = (uint16_t)low;
+  }
+  return out == n;
+}
+
 struct WgPlan {
   int ncta, n_items, splits, chunks, bw, bh, num_ptiles;
 };
@@ -357,6 +457,28 @@ int wgrad_tc_partial(const VsrTapGemmDesc* d, int want_bias, int slice, int n_sl
   if (rc != VSR_OK) return rc;
   a.tap_tab = reinterpret_cast<const int4*>(d->tap_tab);
   a.group_tab = reinterpret_cast<const int4*>(d->group_tab);
+  a.row_bytes = p.bw * 128;
+  {
+    const char* env_dbg = getenv("VSR_WG_DEBUG");
+    a.debug = env_dbg ? atoi(env_dbg) : 0;
+  }
+  {
+    // (opt-in with VSR_WG_TALL=1: measured no gain, the kernel is bound by the N=64 MMA rate - profiles/README.md)
+    // shared-pair mode: reorder the taps of every group so that positions (2p, 2p+1) hold a tap and the tap
+    // with the same source, channel slice and dx one pixel row lower; all pairs of the launch must be such
+    const char* env_tall = getenv("VSR_WG_TALL");
+    const int4* gt = nullptr;
+    if (env_tall && env_tall[0] == '1' && d->tap_tab_host && d->n_taps_total <= kMaxPerm && d->n_groups == 1 &&
+        p.bw >= 8 && p.bw * p.bh == kTile && d->n_taps_total % 2 == 0 && pair_rows(d->tap_tab_host, d->n_taps_total, a.perm)) {
+      a.use_perm = 1;
+      a.tall = 1;
+      for (int s = 0; s < d->n_srcs; ++s) {
+        int rc = get_src_map_pub(d->srcs[s], p.bw, p.bh + 1, &a.tall_maps[s]);
+        if (rc != VSR_OK) return rc;
+      }
+    }
+    (void)gt;
+  }
   // workspace: [n_slices * splits][n] weight partials, then [n_slices * splits][cout] bias partials
   const size_t n_w = (size_t)d->n_taps_total * d->nt * 64;
   float* ws0 = static_cast<float*>(workspace);
@@ -375,7 +497,9 @@ int wgrad_tc_partial(const VsrTapGemmDesc* d, int want_bias, int slice, int n_sl
   a.tiles_y = (a.H + p.bh - 1) / p.bh;
   a.num_ptiles = p.num_ptiles;
   const int nb = p.ncta / 64;
-  const int smem = kCtrl + 1024 + 2 * nb * kTileBytes + kAStages * 2 * kTileBytes;
+  a.stages = (227 * 1024 - kCtrl - 1024 - 2 * nb * kTileBytes) / (2 * kTileBytes);
+  if (a.stages > kMaxAStages) a.stages = kMaxAStages;
+  const int smem = kCtrl + 1024 + 2 * nb * kTileBytes + a.stages * 2 * kTileBytes;
   {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
