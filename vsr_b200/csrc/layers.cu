@@ -566,7 +566,31 @@ struct HaloIdx {
   int colphase[kSBMax + 2];     // px
   uint32_t rowok, colok;        // validity bit masks
 };
+// slot of phase (py, px) in the nested (Z-order) layout of a 4x up-scaled map (drf_plan.phase_table(4))
+__host__ __device__ constexpr int zslot4(int py, int px) {
+  return ((py >> 1) << 3) | ((px >> 1) << 2) | ((py & 1) << 1) | (px & 1);
+}
+// ZR4: r == 4, Z-order slots, sub-block == LR block: every phase below is a compile-time constant, the
+// halo rows / columns 1..4 share the centre block and the address arithmetic folds to 9 block bases.
+template <bool ZR4>
 __device__ __forceinline__ void halo_index(const LastGeom2& g, const SubBlock& b, HaloIdx* hi) {
+  if constexpr (ZR4) {
+    const int H = g.h * 4, W = g.w * 4;
+    hi->rowok = hi->colok = 0;
+#pragma unroll
+    for (int i = 0; i < kSBMax + 2; ++i) {
+      const int Y = b.Y0 + i - 1, X = b.X0 + i - 1;
+      const int yy = min(max(b.by + (i == 0 ? -1 : (i == 5 ? 1 : 0)), 0), g.h - 1);
+      const int xx = min(max(b.bx + (i == 0 ? -1 : (i == 5 ? 1 : 0)), 0), g.w - 1);
+      hi->rowbase[i] = ((size_t)b.ni * g.h + yy) * g.w * 16;
+      hi->colbase[i] = xx * 16;
+      hi->rowphase[i] = 0;
+      hi->colphase[i] = 0;
+      hi->rowok |= ((Y >= 0 && Y < H) ? 1u : 0u) << i;
+      hi->colok |= ((X >= 0 && X < W) ? 1u : 0u) << i;
+    }
+    return;
+  }
   // the sub-block lies inside one LR block: a halo coordinate is at most one block away, so the
   // (block, phase) split needs comparisons only
   const int H = g.h * g.r, W = g.w * g.r, r2 = g.r * g.r, HT = g.sb + 2;
@@ -589,16 +613,18 @@ __device__ __forceinline__ void halo_index(const LastGeom2& g, const SubBlock& b
     hi->colok |= (xo ? 1u : 0u) << i;
   }
 }
+template <bool ZR4>
 __device__ __forceinline__ size_t halo_off(const LastGeom2& g, const HaloIdx& hi, int i, int j) {
+  if constexpr (ZR4) return (hi.rowbase[i] + hi.colbase[j] + zslot4((i + 3) & 3, (j + 3) & 3)) * (size_t)g.c;
   return (hi.rowbase[i] + hi.colbase[j] + g.slot_of[hi.rowphase[i] + hi.colphase[j]]) * (size_t)g.c;
 }
 
 // rolling 3-row window over the sub-block's halo: row i of the halo for channel block c0
-template <typename T, int CPL>
+template <typename T, int CPL, bool ZR4>
 __device__ __forceinline__ void load_halo_row(const T* __restrict__ x, const LastGeom2& g, const HaloIdx& hi, int i,
                                               int c0, float (&row)[kSBMax + 2][CPL]) {
 #pragma unroll
-  for (int j = 0; j < kSBMax + 2; ++j) load_cpl<T, CPL>(x + halo_off(g, hi, i, j) + c0, row[j]);
+  for (int j = 0; j < kSBMax + 2; ++j) load_cpl<T, CPL>(x + halo_off<ZR4>(g, hi, i, j) + c0, row[j]);
 #pragma unroll
   for (int j = 0; j < kSBMax + 2; ++j) {
     const bool ok = ((hi.rowok >> i) & 1u) && ((hi.colok >> j) & 1u);
@@ -607,7 +633,7 @@ __device__ __forceinline__ void load_halo_row(const T* __restrict__ x, const Las
   }
 }
 
-template <typename T, int CPL>
+template <typename T, int CPL, bool ZR4 = false>
 __global__ void __launch_bounds__(256, 2) conv_last2_kernel(const T* __restrict__ x, const __grid_constant__ LastGeom2 g,
                                                            const float* __restrict__ wt, const float* __restrict__ bias,
                                                            float* __restrict__ y) {
@@ -623,7 +649,7 @@ __global__ void __launch_bounds__(256, 2) conv_last2_kernel(const T* __restrict_
   for (long item = warp0; item < total; item += nwarps) {
     const SubBlock sbk = decode_sb(g, item);
     HaloIdx hi;
-    halo_index(g, sbk, &hi);
+    halo_index<ZR4>(g, sbk, &hi);
     float acc[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) acc[i] = 0.f;
@@ -635,11 +661,11 @@ __global__ void __launch_bounds__(256, 2) conv_last2_kernel(const T* __restrict_
 #pragma unroll
         for (int q = 0; q < CPL; ++q) wr[t][q] = sw[t * g.c + c0 + q];
       float rows[3][kSBMax + 2][CPL];
-      load_halo_row<T, CPL>(x, g, hi, 0, c0, rows[0]);
-      load_halo_row<T, CPL>(x, g, hi, 1, c0, rows[1]);
+      load_halo_row<T, CPL, ZR4>(x, g, hi, 0, c0, rows[0]);
+      load_halo_row<T, CPL, ZR4>(x, g, hi, 1, c0, rows[1]);
 #pragma unroll
       for (int oy = 0; oy < kSBMax; ++oy) {
-        load_halo_row<T, CPL>(x, g, hi, oy + 2, c0, rows[(oy + 2) % 3]);
+        load_halo_row<T, CPL, ZR4>(x, g, hi, oy + 2, c0, rows[(oy + 2) % 3]);
 #pragma unroll
         for (int ox = 0; ox < kSBMax; ++ox) {
           float sacc = acc[oy * kSBMax + ox];
@@ -662,7 +688,7 @@ __global__ void __launch_bounds__(256, 2) conv_last2_kernel(const T* __restrict_
 
 // backward, part 1 (cout == 1): dx(P,c) = sum_tap dy(P - off(tap)) * w[c][tap]; one warp per sub-block,
 // the dy halo in registers (broadcast loads), CPL channels per lane, coalesced stores.
-template <typename T, int CPL>
+template <typename T, int CPL, bool ZR4 = false>
 __global__ void __launch_bounds__(256, 2) conv_last2_dx_kernel(const __grid_constant__ LastGeom2 g,
                                                               const float* __restrict__ wt, const float* __restrict__ dy,
                                                               T* __restrict__ dx) {
@@ -677,7 +703,7 @@ __global__ void __launch_bounds__(256, 2) conv_last2_dx_kernel(const __grid_cons
   for (long item = warp0; item < total; item += nwarps) {
     const SubBlock sbk = decode_sb(g, item);
     HaloIdx hi;
-    halo_index(g, sbk, &hi);
+    halo_index<ZR4>(g, sbk, &hi);
     float gy[kHalo];
 #pragma unroll
     for (int i = 0; i < kSBMax + 2; ++i)
@@ -710,7 +736,7 @@ __global__ void __launch_bounds__(256, 2) conv_last2_dx_kernel(const __grid_cons
 #pragma unroll
                 for (int q = 0; q < CPL; ++q) d[q] = fmaf(gn, wr[ky * 3 + kx][q], d[q]);
               }
-            store_cpl<T, CPL>(dx + halo_off(g, hi, oy + 1, ox + 1) + c0, d);
+            store_cpl<T, CPL>(dx + halo_off<ZR4>(g, hi, oy + 1, ox + 1) + c0, d);
           }
         }
     }
@@ -719,7 +745,7 @@ __global__ void __launch_bounds__(256, 2) conv_last2_dx_kernel(const __grid_cons
 
 // backward, part 2: dw[c][tap] += dy(P) * x(P + off(tap), c), db += dy(P): the forward's rolling x
 // window; per-lane accumulators -> block fold (fixed warp order) -> ws -> final reduce.
-template <typename T, int CPL>
+template <typename T, int CPL, bool ZR4 = false>
 __global__ void __launch_bounds__(256, 2) conv_last2_dw_kernel(const T* __restrict__ x, const __grid_constant__ LastGeom2 g,
                                                               const float* __restrict__ dy, float* __restrict__ ws) {
   extern __shared__ float sm[];    // block partial [nw][9*C + 1]
@@ -740,7 +766,7 @@ __global__ void __launch_bounds__(256, 2) conv_last2_dw_kernel(const T* __restri
   for (long item = warp0; item < total; item += nwarps) {
     const SubBlock sbk = decode_sb(g, item);
     HaloIdx hi;
-    halo_index(g, sbk, &hi);
+    halo_index<ZR4>(g, sbk, &hi);
     float gc[16];
 #pragma unroll
     for (int oy = 0; oy < kSBMax; ++oy)
@@ -758,11 +784,11 @@ __global__ void __launch_bounds__(256, 2) conv_last2_dw_kernel(const T* __restri
       if (cb < g.c) {
         const int c0 = cb + lane * CPL;
         float rows[3][kSBMax + 2][CPL];
-        load_halo_row<T, CPL>(x, g, hi, 0, c0, rows[0]);
-        load_halo_row<T, CPL>(x, g, hi, 1, c0, rows[1]);
+        load_halo_row<T, CPL, ZR4>(x, g, hi, 0, c0, rows[0]);
+        load_halo_row<T, CPL, ZR4>(x, g, hi, 1, c0, rows[1]);
 #pragma unroll
         for (int oy = 0; oy < kSBMax; ++oy) {
-          load_halo_row<T, CPL>(x, g, hi, oy + 2, c0, rows[(oy + 2) % 3]);
+          load_halo_row<T, CPL, ZR4>(x, g, hi, oy + 2, c0, rows[(oy + 2) % 3]);
 #pragma unroll
           for (int ox = 0; ox < kSBMax; ++ox) {
             const float gv = gc[oy * kSBMax + ox];
@@ -811,6 +837,14 @@ int fill_geom2(LastGeom2* g, int n, int h, int w, int r, int c, const int32_t* p
     g->slot_of[py * r + px] = s;
   }
   return 0;
+}
+
+bool geom_is_zr4(const LastGeom2& g) {
+  if (g.r != 4 || g.sb != 4) return false;
+  for (int py = 0; py < 4; ++py)
+    for (int px = 0; px < 4; ++px)
+      if (g.slot_of[py * 4 + px] != zslot4(py, px)) return false;
+  return true;
 }
 
 int first_bwd_blocks(long pixels) {
@@ -925,6 +959,8 @@ extern "C" int vsr_conv3x3_last(const void* x, int32_t dtype, int32_t n, int32_t
     const int grid2 = grid_for(items, 8, 8);
     const size_t smem2 = (size_t)9 * c * sizeof(float);
     if (dtype == VSR_BF16) {
+      // (the compile-time-phase variant <.., true> spills under the 128-register cap here and measured slower;
+      //  the backward kernels use it)
       if (c % 64 == 0) conv_last2_kernel<__nv_bfloat16, 2><<<grid2, 256, smem2, s>>>((const __nv_bfloat16*)x, g2, w, bias, y);
       else conv_last2_kernel<__nv_bfloat16, 1><<<grid2, 256, smem2, s>>>((const __nv_bfloat16*)x, g2, w, bias, y);
     } else {
@@ -978,7 +1014,10 @@ extern "C" int vsr_conv3x3_last_bwd(const void* x, int32_t dtype, int32_t n, int
     const int grid_dx = grid_for(items, 8, 8);
     if (dtype == VSR_BF16) {
       using B = __nv_bfloat16;
-      if (c % 64 == 0) {
+      if (c % 64 == 0 && geom_is_zr4(g2)) {
+        conv_last2_dx_kernel<B, 2, true><<<grid_dx, 256, smem_w, s2>>>(g2, w, dy, (B*)dx);
+        conv_last2_dw_kernel<B, 2, true><<<blocks2, kLastBwdThreads, smem_p, s2>>>((const B*)x, g2, dy, ws2);
+      } else if (c % 64 == 0) {
         conv_last2_dx_kernel<B, 2><<<grid_dx, 256, smem_w, s2>>>(g2, w, dy, (B*)dx);
         conv_last2_dw_kernel<B, 2><<<blocks2, kLastBwdThreads, smem_p, s2>>>((const B*)x, g2, dy, ws2);
       } else {

@@ -33,11 +33,11 @@ namespace {
 constexpr int kBlockM = 128;
 constexpr int kKc = 64;                       // bf16 channels per tap = one 128-byte row
 constexpr int kATileBytes = kBlockM * 128;    // 16 KiB
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 12;
 constexpr int kSmemBudget = 227 * 1024;
 constexpr int kEpiWarps = 8;                  // two per TMEM lane quarter: even / odd 64-channel chunks
 constexpr int kTileBytes = 4096;              // epilogue tile: 32 pixels x 64 channels bf16
-constexpr int kMaxSmemGroups = 46;            // group table rows cached in smem (16 B each, ctrl[288..1024))
+constexpr int kMaxSmemGroups = 36;            // group table rows cached in smem (16 B each, ctrl[448..1024))
 constexpr int kMaxSmemTaps = 256;             // column entries cached in smem (8 B each)
 constexpr int kMaxParamCols = 32;             // host-built columns travel in the kernel arguments
 constexpr int kBiasFloats = 1024;
@@ -149,16 +149,16 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
   if (smem_base & 1023u) __trap();             // the swizzled tiles need a 1024-byte aligned window
 
   // control block
-  const uint32_t full_bar = smem_base;                     // kMaxStages x 8 B
-  const uint32_t empty_bar = smem_base + 64;               // kMaxStages x 8 B
-  const uint32_t tfull_bar = smem_base + 128;              // 2 x 8 B
-  const uint32_t tempty_bar = smem_base + 144;             // 2 x 8 B
-  const uint32_t tmem_slot = smem_base + 160;              // u32
-  const uint32_t bres_full = smem_base + 168, bres_empty = smem_base + 176;
-  const uint32_t in_bar0 = smem_base + 184;                // kEpiWarps x 8 B (..248)
-  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + 160);
-  float* red = reinterpret_cast<float*>(smem_gen + 256);   // kEpiWarps floats
-  int4* grp_s = reinterpret_cast<int4*>(smem_gen + 288);        // group table (<= 46 rows)
+  const uint32_t full_bar = smem_base;                     // kMaxStages x 8 B (room for 16)
+  const uint32_t empty_bar = smem_base + 128;              // kMaxStages x 8 B (room for 16)
+  const uint32_t tfull_bar = smem_base + 256;              // 2 x 8 B
+  const uint32_t tempty_bar = smem_base + 272;             // 2 x 8 B
+  const uint32_t tmem_slot = smem_base + 288;              // u32
+  const uint32_t bres_full = smem_base + 296, bres_empty = smem_base + 304;
+  const uint32_t in_bar0 = smem_base + 312;                // kEpiWarps x 8 B (..376)
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + 288);
+  float* red = reinterpret_cast<float*>(smem_gen + 384);   // kEpiWarps floats
+  int4* grp_s = reinterpret_cast<int4*>(smem_gen + 448);        // group table (<= 36 rows)
   uint2* col_s = reinterpret_cast<uint2*>(smem_gen + 1024);     // column table (<= 256 entries)
   float* bias_s = reinterpret_cast<float*>(smem_gen + 1024 + kMaxSmemTaps * 8);   // bias when Cout <= 1024
   const uint32_t epi_base = smem_base + kCtrlBytes;        // epilogue tiles
@@ -774,6 +774,8 @@ int tapgemm_tc2_launch(const VsrTapGemmDesc* d, cudaStream_t stream) {
   const long res_need = (long)d->max_group_taps * b_bytes;
   // weight-resident mode: the group's slabs stay in smem and >= 3 A stages remain; worth it when the
   // slabs are large next to the A tile (nt > 64) and every CTA sees few groups
+  // (short nt=64 tables - the 1x1 convolutions on concatenations - were measured 5-10% slower resident:
+  // tools/hr_sweep.py, so they stream their 8 KB slabs with the A tiles)
   a.resident = !a.tall && d->max_group_taps > 0 && d->nt > 64 && res_need <= avail - 3 * kATileBytes &&
                tiles >= 2 * (long)num_sms();
   {

@@ -351,7 +351,16 @@ __global__ void __launch_bounds__(256) wg_reduce_kernel(const float4* __restrict
   const long i = (long)blockIdx.x * 64 + col;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
   if (i < n4) {
-    for (int k = part; k < splits; k += 4) {
+    // eight independent 16-byte loads in flight per thread; the additions keep the order k = part, part+4, ...
+    int k = part;
+    for (; k + 28 < splits; k += 32) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldg(ws + (size_t)(k + 4 * u) * n4 + i);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
+    }
+    for (; k < splits; k += 4) {
       const float4 v = __ldg(ws + (size_t)k * n4 + i);
       s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }
