@@ -20,6 +20,8 @@ import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"      # no version banner on stdout: rank 0 prints exactly one JSON line
 
 MODEL = dict(in_channels=1, out_channels=1, num_features=64, num_groups=6, upscale_factor=4)
 BATCH, T, LR = 32, 5, 32

@@ -208,3 +208,53 @@ def test_wgrad_tc_grouped_nt128_nonuniform_groups():
     g1 = [(0, dy, dx, 64) for dy in (-1, 0, 1) for dx in (-1, 0, 1)]
     tab = TapTable(kc=64, nt=128, groups=[(0, g0), (128, g1)])
     _wgrad_case(tab, n=2, h=12, w=20, src_c=128, out_c=256)
+
+
+def strided_conv_table(r=4, k=8, p=2, F=64):
+    """nn.Conv2d(k, stride=r, pad=p) on a phase-blocked r-times map (row-major slots): k*k taps in one group."""
+    taps = []
+    for ky in range(k):
+        for kx in range(k):
+            dy, py = divmod(ky - p, r)
+            dx, px = divmod(kx - p, r)
+            taps.append((0, dy, dx, (py * r + px) * F))
+    return TapTable(kc=F, nt=F, groups=[(0, taps)])
+
+
+@pytest.mark.parametrize("h,w", [(32, 32), (19, 32), (12, 12)])
+@pytest.mark.parametrize("epi", [L.EPI_BIAS | L.EPI_PRELU, L.EPI_PRELU_BWD, L.EPI_RES_PRE | L.EPI_PRELU_BWD])
+def test_tc_bf16_strided_conv_shared_loads(h, w, epi, monkeypatch):
+    """taps that differ by a row shift share one A box and two stacked pixel tiles share the slabs
+    (tapgemm_tc2.cu shared-load mode); the same launch with the mode off must agree with the emulation too."""
+    tab = strided_conv_table()
+    _run_case(tab, n=3, h=h, w=w, src_c=1024, out_c=64, dtype=torch.bfloat16, epi=epi, seed=21)
+    monkeypatch.setenv("VSR_TC_TALL", "0")
+    _run_case(tab, n=3, h=h, w=w, src_c=1024, out_c=64, dtype=torch.bfloat16, epi=epi, seed=21)
+
+
+def test_tc_bf16_strided_conv_r2_three_row_columns():
+    # 6x6 stride 2 pad 2: every (slot, dx) column has three row shifts
+    _run_case(strided_conv_table(r=2, k=6), n=2, h=24, w=16, src_c=256, out_c=64, dtype=torch.bfloat16,
+              epi=L.EPI_BIAS | L.EPI_PRELU, seed=22)
+
+
+def test_tc_bf16_resident_and_streamed_weights_agree(monkeypatch):
+    # deconv shape: 4 groups x 4 taps, nt 256; enough tiles for the weight-resident mode
+    tab = grouped_table(64, 256, 4, 1)
+    for mode in ("1", "0"):
+        monkeypatch.setenv("VSR_TC_RESIDENT", mode)
+        _run_case(tab, n=20, h=32, w=32, src_c=64, out_c=1024, dtype=torch.bfloat16, epi=L.EPI_BIAS | L.EPI_PRELU, seed=23)
+
+
+def test_tc_bf16_no_pdl_and_first_generation_kernel(monkeypatch):
+    tab = conv3x3_table(64, 64)
+    monkeypatch.setenv("VSR_PDL", "0")
+    _run_case(tab, n=2, h=20, w=32, src_c=64, out_c=64, dtype=torch.bfloat16, epi=L.EPI_BIAS | L.EPI_PRELU, seed=24)
+    monkeypatch.setenv("VSR_TC_V1", "1")
+    _run_case(tab, n=2, h=20, w=32, src_c=64, out_c=64, dtype=torch.bfloat16, epi=L.EPI_BIAS | L.EPI_PRELU, seed=24)
+
+
+def test_wgrad_tc_shared_pair_loads(monkeypatch):
+    monkeypatch.setenv("VSR_WG_TALL", "1")
+    _wgrad_case(strided_conv_table(), n=4, h=16, w=32, src_c=1024, out_c=64, seed=25)
+    _wgrad_case(strided_conv_table(), n=2, h=19, w=32, src_c=1024, out_c=64, seed=26)
