@@ -92,43 +92,57 @@ class DrfEngine:
         F, G, r = P.F, P.G, P.r
         r2 = r * r
         saved, outs, prev_f = [], [], None
+        T = len(frames)
+        # Saved activations of a layer live in ONE [T, N, h, w, c] buffer (frame t = slice t), so that the
+        # weight gradient of the layer is a single launch over all T frames (backward()).
+        stacked = save and T > 1 and all(f.shape == frames[0].shape for f in frames)
+        bufs = {}
+
+        def alloc(key, t, *shape):
+            if not stacked:
+                return self._new(*shape)
+            b = bufs.get(key)
+            if b is None:
+                b = bufs[key] = self._new(T, *shape)
+            return b[t]
+
         for t, x in enumerate(frames):
             N, _, h, w = x.shape
             S = _Frame()
             S.x = x
-            S.a1 = self._new(N, h, w, 4 * F)
+            S.a1 = alloc("a1", t, N, h, w, 4 * F)
             ops.conv3x3_first(x, self._pview(self.flat, f"{P.in_name}.conv1.weight"),
                               self._pview(self.flat, f"{P.in_name}.conv1.bias"),
                               self._slope(P.params[f"{P.in_name}.prelu1.weight"]), S.a1)
-            S.inn = self._new(N, h, w, F)
+            S.inn = alloc("inn", t, N, h, w, F)
             self._fwd("in2", [S.a1], S.inn)
             S.hidden = S.inn if t == 0 else prev_f                      # drf_net.py:42-43
-            S.lr, S.hr, S.u, S.d = [self._new(N, h, w, F)], [], [None], [None]
+            S.lr, S.hr, S.u, S.d = [alloc("lr0", t, N, h, w, F)], [], [None], [None]
             self._fwd("fin", [S.inn, S.hidden], S.lr[0])
             hv = lambda z: z.view(N, h, w * r2, F)
             for g in range(G):
                 if g == 0:
                     src = S.lr[0]
                 else:
-                    S.u.append(self._new(N, h, w, F))
+                    S.u.append(alloc(f"u{g}", t, N, h, w, F))
                     self._fwd(f"up{g}_c1", S.lr[:g + 1], S.u[g])
                     src = S.u[g]
-                S.hr.append(self._new(N, h, w, r2 * F))
+                S.hr.append(alloc(f"hr{g}", t, N, h, w, r2 * F))
                 self._fwd(f"up{g}_dc", [src], S.hr[g])
                 if g == 0:
                     src = S.hr[0]
                 else:
-                    S.d.append(self._new(N, h, w, r2 * F))
+                    S.d.append(alloc(f"d{g}", t, N, h, w, r2 * F))
                     self._fwd(f"dn{g}_c1", [hv(z) for z in S.hr[:g + 1]], hv(S.d[g]))
                     src = S.d[g]
-                S.lr.append(self._new(N, h, w, F))
+                S.lr.append(alloc(f"lr{g + 1}", t, N, h, w, F))
                 self._fwd(f"dn{g}_sc", [src], S.lr[g + 1])
             if P.variant == "srfb":
                 # srfb_net.py:44-48: residual = r_block(f);  output = bilinear(input) + residual
-                S.f = self._new(N, h, w, F)
+                S.f = alloc("f", t, N, h, w, F)
                 S.feat = None
                 self._fwd("fout", S.lr[1:], S.f)
-                hr_out = self._new(N, h, w, r2 * F)
+                hr_out = alloc("s0", t, N, h, w, r2 * F)
                 self._fwd("rdc", [S.f], hr_out)
                 S.s = [hr_out]
                 res = self._new(N, P.cout, h * r, w * r, dtype=self.param_dtype)
@@ -139,12 +153,12 @@ class DrfEngine:
                 y = self._new(N, P.cout, h * r, w * r, dtype=self.param_dtype)
                 ops.add(up, res, y)
             else:
-                S.f, S.feat = self._new(N, h, w, F), self._new(N, h, w, F)
+                S.f, S.feat = alloc("f", t, N, h, w, F), alloc("s0", t, N, h, w, F)
                 self._fwd("fout", S.lr[1:], S.f, extra=EPI_OUT2, out2=S.feat, res2=S.inn)   # :46 global skip
                 S.s = [S.feat]
                 for lv in range(P.out_levels):
                     L = P.fwd[f"out{lv + 1}"]
-                    nxt = self._new(N, h, w, L.out_c)
+                    nxt = alloc(f"s{lv + 1}", t, N, h, w, L.out_c)
                     self._fwd(L.name, [S.s[-1]], nxt)
                     S.s.append(nxt)
                 y = self._new(N, P.cout, h * r, w * r, dtype=self.param_dtype)
@@ -156,6 +170,13 @@ class DrfEngine:
                 saved.append(S)
             else:
                 S = None
+        if stacked:
+            # hidden state seen by frame t (drf_net.py:42-43) as one stacked tensor: [inn_0, f_0, ..., f_{T-2}]
+            hid = self._new(T, *bufs["f"].shape[1:])
+            hid[0].copy_(bufs["inn"][0])
+            hid[1:].copy_(bufs["f"][:T - 1])
+            bufs["hidden"] = hid
+            saved[0].y = bufs          # the stacked buffers travel with the saved frames
         return outs, saved
 
     # ---- backward --------------------------------------------------------------------------
@@ -180,9 +201,25 @@ class DrfEngine:
             return partials[i]
 
         pending = {}     # layer -> [srcs, dz, workspace, slices used]: partials awaiting the per-step reduction
+        bufs = getattr(saved[0], "y", None) if T > 1 else None     # stacked activations (forward())
+        stacked = isinstance(bufs, dict)
+        dzb = {}         # stacked gradient maps: key -> [T, N, h, w, c]
+        deferred = {}    # layer -> (keys of the stacked sources, key of the stacked dz, view shape or None)
 
-        def wgrad(lname, srcs, dz):
+        def dz_alloc(key, t, *shape):
+            """gradient map that a weight gradient consumes: frame t's slice of a [T, ...] buffer"""
+            if not stacked:
+                return self._new(*shape)
+            b = dzb.get(key)
+            if b is None:
+                b = dzb[key] = self._new(T, *shape)
+            return b[t]
+
+        def wgrad(lname, srcs, dz, src_keys=None, dz_key=None, view=None):
             L = P.fwd[lname]
+            if stacked and src_keys is not None:
+                deferred[lname] = (src_keys, dz_key, view)      # one launch over all T frames after the loop
+                return
             if T > 1:
                 # same layer, same shapes every frame: accumulate split partials, reduce once (below)
                 # every frame writes its own workspace slice; one reduction per layer per step (below)
@@ -224,50 +261,52 @@ class DrfEngine:
             if d_out is None:
                 d_out = torch.zeros(N, P.cout, h * r, w * r, dtype=pd, device=dev)
             # ---- output block ----
-            d_s = new(S.s[-1].shape[-1])
+            n_lv = len(S.s) - 1
+            d_s = dz_alloc(f"ds{n_lv}", t, N, h, w, S.s[-1].shape[-1])
             ws = self._workspace("last", ops.conv3x3_last_bwd_workspace(S.s[-1], r, F, P.cout))
             ops.conv3x3_last_bwd(S.s[-1], r, F, P.phases, self._pview(self.flat, P.last_name + ".weight"),
                                  d_out.contiguous(), d_s, self._pview(gflat, P.last_name + ".weight"),
                                  self._pview(gflat, P.last_name + ".bias"), True, ws)
             for lv in reversed(range(P.out_levels)):
                 lname = f"out{lv + 1}"
-                wgrad(lname, [S.s[lv]], d_s)
-                d_prev = new(S.s[lv].shape[-1])
+                wgrad(lname, [S.s[lv]], d_s, [f"s{lv}"], f"ds{lv + 1}")
+                d_prev = dz_alloc(f"ds{lv}", t, N, h, w, S.s[lv].shape[-1])
                 dgrad(lname, [d_s], d_prev)
                 d_s = d_prev
             if P.variant == "srfb":
-                dz_r = new(r2 * F)
+                dz_r = dz_alloc("dz_r", t, N, h, w, r2 * F)
                 act_bwd(d_s, S.s[0], dz_r, P.fwd["rdc"].slope)       # r_block.prelu1
-                wgrad("rdc", [S.f], dz_r)
+                wgrad("rdc", [S.f], dz_r, ["f"], "dz_r")
                 d_s = new()
                 dgrad("rdc", [dz_r], d_s)
             d_feat = d_s
             # ---- feedback block output (+ hidden-state gradient of frame t+1: BPTT) ----
-            dz_f = new()
+            dz_f = dz_alloc("dz_f", t, N, h, w, F)
             fout = P.fwd["fout"]
             if next_dz_lr0 is not None:
                 dgrad("fin_hid", [next_dz_lr0], dz_f, aux=S.f, slope_ref=fout.slope, residual=d_feat)
             else:
                 act_bwd(d_feat, S.f, dz_f, fout.slope)
-            wgrad("fout", S.lr[1:], dz_f)
+            wgrad("fout", S.lr[1:], dz_f, [f"lr{j}" for j in range(1, G + 1)], "dz_f")
             dz_u, dz_d, p_hr0, p_lr0 = {}, {}, None, None
             for g in reversed(range(G)):
                 j = g + 1
                 srcs = [dz_f] + [dz_u[gg] for gg in range(max(j, 1), G)]
-                dz_lr = new()
+                dz_lr = dz_alloc(f"dz_lr{j}", t, N, h, w, F)
                 dgrad(f"lr{j}", srcs, dz_lr, aux=S.lr[j], slope_ref=P.fwd[f"dn{g}_sc"].slope)
                 # down-projection group g
-                wgrad(f"dn{g}_sc", [S.hr[0] if g == 0 else S.d[g]], dz_lr)
+                wgrad(f"dn{g}_sc", [S.hr[0] if g == 0 else S.d[g]], dz_lr, ["hr0" if g == 0 else f"d{g}"], f"dz_lr{j}")
                 if g >= 1:
-                    dz_d[g] = new(r2 * F)
+                    dz_d[g] = dz_alloc(f"dz_d{g}", t, N, h, w, r2 * F)
                     dgrad(f"dn{g}_sc", [dz_lr], dz_d[g], aux=S.d[g], slope_ref=P.fwd[f"dn{g}_c1"].slope)
-                    wgrad(f"dn{g}_c1", [hv(z) for z in S.hr[:g + 1]], hv(dz_d[g]))
+                    wgrad(f"dn{g}_c1", [hv(z) for z in S.hr[:g + 1]], hv(dz_d[g]), [f"hr{gg}" for gg in range(g + 1)],
+                          f"dz_d{g}", (h, w * r2, F))
                 else:
                     p_hr0 = new(r2 * F)
                     dgrad("dn0_sc", [dz_lr], p_hr0)
                 # gradient of hr_g
                 cons = [dz_d[gg] for gg in range(max(g, 1), G)]
-                dz_hr = new(r2 * F)
+                dz_hr = dz_alloc(f"dz_hr{g}", t, N, h, w, r2 * F)
                 up_slope = P.fwd[f"up{g}_dc"].slope
                 if cons:
                     dgrad(f"hr{g}", [hv(c) for c in cons], hv(dz_hr), aux=hv(S.hr[g]), slope_ref=up_slope,
@@ -275,24 +314,24 @@ class DrfEngine:
                 else:
                     act_bwd(p_hr0, S.hr[g], dz_hr, up_slope)
                 # up-projection group g
-                wgrad(f"up{g}_dc", [S.lr[0] if g == 0 else S.u[g]], dz_hr)
+                wgrad(f"up{g}_dc", [S.lr[0] if g == 0 else S.u[g]], dz_hr, ["lr0" if g == 0 else f"u{g}"], f"dz_hr{g}")
                 if g >= 1:
-                    dz_u[g] = new()
+                    dz_u[g] = dz_alloc(f"dz_u{g}", t, N, h, w, F)
                     dgrad(f"up{g}_dc", [dz_hr], dz_u[g], aux=S.u[g], slope_ref=P.fwd[f"up{g}_c1"].slope)
-                    wgrad(f"up{g}_c1", S.lr[:g + 1], dz_u[g])
+                    wgrad(f"up{g}_c1", S.lr[:g + 1], dz_u[g], [f"lr{jj}" for jj in range(g + 1)], f"dz_u{g}")
                 else:
                     p_lr0 = new()
                     dgrad("up0_dc", [dz_hr], p_lr0)
             # ---- feedback block input ----
-            dz_lr0 = new()
+            dz_lr0 = dz_alloc("dz_lr0", t, N, h, w, F)
             cons = [dz_u[gg] for gg in range(1, G)]
             fin = P.fwd["fin"]
             if cons:
                 dgrad("lr0", cons, dz_lr0, aux=S.lr[0], slope_ref=fin.slope, residual=p_lr0)
             else:
                 act_bwd(p_lr0, S.lr[0], dz_lr0, fin.slope)
-            wgrad("fin", [S.inn, S.hidden], dz_lr0)
-            dz_in = new()
+            wgrad("fin", [S.inn, S.hidden], dz_lr0, ["inn", "hidden"], "dz_lr0")
+            dz_in = dz_alloc("dz_in", t, N, h, w, F)
             in2 = P.fwd["in2"]
             skip = d_feat if P.variant == "drf" else None      # the feature skip exists in DRFNet only
             if t == 0:   # hidden == in_features at the first frame (drf_net.py:42-43)
@@ -300,13 +339,30 @@ class DrfEngine:
             else:
                 dgrad("fin_in", [dz_lr0], dz_in, aux=S.inn, slope_ref=in2.slope, residual=skip)
             # ---- input block ----
-            wgrad("in2", [S.a1], dz_in)
+            wgrad("in2", [S.a1], dz_in, ["a1"], "dz_in")
             dz_a1 = new(4 * F)
             dgrad("in2", [dz_in], dz_a1, aux=S.a1, slope_ref=P.params[f"{P.in_name}.prelu1.weight"])
             ws = self._workspace("first", ops.conv3x3_first_bwd_workspace(S.x, 4 * F))
             ops.conv3x3_first_bwd(S.x, dz_a1, self._pview(gflat, f"{P.in_name}.conv1.weight"),
                                   self._pview(gflat, f"{P.in_name}.conv1.bias"), True, ws)
             next_dz_lr0 = dz_lr0
+        for lname, (src_keys, dz_key, view) in deferred.items():
+            # weight (+ bias) gradient of the layer over all T frames in one launch: [T, N, ...] -> [T*N, ...]
+            L = P.fwd[lname]
+
+            def flat(b):
+                b = b.view(b.shape[0] * b.shape[1], *b.shape[2:])
+                return b if view is None else b.view(b.shape[0], *view)
+
+            srcs, dz = [flat(bufs[k]) for k in src_keys], flat(dzb[dz_key])
+            ws = self._workspace("wgrad", ops.tapgemm_wgrad_workspace(L.table, srcs, dz))
+            db = db_packed[L.b_off:L.b_off + L.bias_c]
+            fused = ops.tapgemm_wgrad(L.table, srcs, dz, dw_packed[L.w_off:L.w_off + L.w_numel], True, ws,
+                                      db=db, db_period=L.bias_c)
+            if not fused:
+                rows = dz.numel() // L.bias_c
+                wsb = self._workspace("colsum", ops.colsum_workspace(rows, L.bias_c))
+                ops.colsum(dz, rows, L.bias_c, db, True, wsb)
         for lname, (srcs, dz, wsl, used) in pending.items():
             L = P.fwd[lname]
             ops.tapgemm_wgrad_finish(L.table, srcs, dz, dw_packed[L.w_off:L.w_off + L.w_numel],
