@@ -106,7 +106,8 @@ __global__ void psnr_final_kernel(const float* __restrict__ ws, int n, int bps, 
 constexpr int kWin = 11, kSRows = 32, kSWarps = 4;
 __global__ void __launch_bounds__(kSWarps * 32) ssim_partial_kernel(
     const float* __restrict__ out, const float* __restrict__ tgt, int h, int w, const float* __restrict__ win,
-    float mean, float std, int denorm_on, float c1, float c2, int tiles_x, int tiles_y, float* __restrict__ ws) {
+    float mean, float std, int denorm_on, float c1, float c2, int tiles_x, int tiles_y, int srows,
+    float* __restrict__ ws) {
   __shared__ float rowbuf[kSWarps][2][48];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int tx = blockIdx.x * kSWarps + warp;             // column strip
@@ -117,8 +118,8 @@ __global__ void __launch_bounds__(kSWarps * 32) ssim_partial_kernel(
   float g[kWin];
 #pragma unroll
   for (int k = 0; k < kWin; ++k) g[k] = __ldg(win + k);
-  const int x0 = tx * 32, y0 = ty * kSRows;
-  const int rows_out = min(kSRows, oh - y0);
+  const int x0 = tx * 32, y0 = ty * srows;          // srows output rows per warp (host: enough warps to fill the GPU)
+  const int rows_out = min(srows, oh - y0);
   const int rows_in = rows_out + kWin - 1;
   const float* o = out + (size_t)ni * h * w;
   const float* t = tgt + (size_t)ni * h * w;
@@ -322,12 +323,16 @@ extern "C" int vsr_ssim(const float* out, const float* target, int32_t n, int32_
   VSR_CHECK_ARG(workspace && workspace_bytes >= vsr_metric_workspace(n, (int64_t)h * w_), "vsr_ssim: workspace too small");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int oh = h - 10, ow = w_ - 10;
-  const int tiles_x = (ow + 31) / 32, tiles_y = (oh + kSRows - 1) / kSRows;
+  const int tiles_x = (ow + 31) / 32;
+  int srows = kSRows;                                   // shorter strips until >= 8 warps per SM exist
+  while (srows > 8 && (long)tiles_x * ((oh + srows - 1) / srows) * n < (long)num_sms() * 8) srows >>= 1;
+  if ((size_t)tiles_x * ((oh + srows - 1) / srows) > (size_t)((int64_t)h * w_ / 256 + 64)) srows = kSRows;
+  const int tiles_y = (oh + srows - 1) / srows;
   VSR_CHECK_SUPPORTED(tiles_y <= 65535 && n <= 65535, "vsr_ssim: image too tall or batch too large");
   VSR_CHECK_SUPPORTED((size_t)tiles_x * tiles_y <= (size_t)((int64_t)h * w_ / 256 + 64), "vsr_ssim: degenerate aspect ratio");
   float* ws = static_cast<float*>(workspace);
   ssim_partial_kernel<<<dim3((tiles_x + kSWarps - 1) / kSWarps, tiles_y, n), kSWarps * 32, 0, s>>>(
-      out, target, h, w_, win11, mean, std, std > 0.f, c1, c2, tiles_x, tiles_y, ws);
+      out, target, h, w_, win11, mean, std, std > 0.f, c1, c2, tiles_x, tiles_y, srows, ws);
   VSR_CHECK_LAUNCH("vsr_ssim");
   ssim_final_kernel<<<(n + 127) / 128, 128, 0, s>>>(ws, n, tiles_x * tiles_y, 1.f / ((float)oh * (float)ow), ssim_out);
   VSR_CHECK_LAUNCH("vsr_ssim_final");
