@@ -323,15 +323,22 @@ def main():
         kernel_share = {k: {"ms_per_step": v[1] / prof_steps, "launches_per_step": v[2] / prof_steps,
                             "tflops": v[0] / (v[1] * 1e-3) / 1e12} for k, v in agg.items()}
         top = sorted(detail.items(), key=lambda kv: -kv[1][1])[:14]
-        kernel_detail = {k: {"ms_per_step": v[1] / prof_steps, "n_per_step": v[2] / prof_steps,
-                             "tflops": v[0] / (v[1] * 1e-3) / 1e12, "gbs": v[3] / (v[1] * 1e-3) / 1e9} for k, v in top}
+
+        def shape_row(v):
+            # every shape against ITS OWN bound: tensor if its algorithmic intensity is above the ridge of the
+            # measured peaks (FLOP/B), else HBM
+            tf, gb = v[0] / (v[1] * 1e-3) / 1e12, v[3] / (v[1] * 1e-3) / 1e9
+            tensor = v[0] / max(v[3], 1.0) > pk["bf16_tflops_sustained"] * 1e3 / pk["hbm_gbs"]
+            return {"ms_per_step": v[1] / prof_steps, "n_per_step": v[2] / prof_steps, "tflops": tf, "gbs": gb,
+                    "bound": "tensor" if tensor else "hbm",
+                    "frac": tf / pk["bf16_tflops_sustained"] if tensor else gb / pk["hbm_gbs"]}
+
+        kernel_detail = {k: shape_row(v) for k, v in top}
         step_flops = 3.0 * FWD_FLOPS_PER_LR_PIXEL * args.batch * T * LR * LR
         try:      # full per-shape table for the profile notes (scratch; the JSON line keeps the top 14)
             os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
             with open(os.path.join(ROOT, "gpurun_out", "kernel_detail_full.json"), "w") as f:
-                json.dump({k: {"ms_per_step": v[1] / prof_steps, "n_per_step": v[2] / prof_steps,
-                               "tflops": v[0] / (v[1] * 1e-3) / 1e12, "gbs": v[3] / (v[1] * 1e-3) / 1e9}
-                           for k, v in sorted(detail.items(), key=lambda kv: -kv[1][1])}, f, indent=1)
+                json.dump({k: shape_row(v) for k, v in sorted(detail.items(), key=lambda kv: -kv[1][1])}, f, indent=1)
         except OSError:
             pass
         line = {

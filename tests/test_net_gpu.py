@@ -99,3 +99,40 @@ def test_training_step_is_deterministic():
             opt.step()
         res.append(net.flat.clone())
     assert torch.equal(res[0], res[1])
+
+
+def test_config2_full_size_bf16_against_strict_fp32_mode():
+    """BASELINE config 2 at full size (DRFNet-L F64/G6 x4, 32 patches of LR 32x32, T=5): the tcgen05 bf16 path
+    against this library's strict fp32 mode (itself <= 1e-4 of the reference, tests above) - PSNR within
+    0.05 dB, outputs within 5e-2 of the output range, gradients within 5e-2 global relative L2 - and the
+    step twice is bit-identical (size-independent properties; the CPU oracle would need minutes here)."""
+    from bench import MODEL, make_batches
+    lrs, hrs = make_batches(1, 32, seed=3, pinned=False)[0]
+    x, y = [t.cuda() for t in lrs], [t.cuda() for t in hrs]
+    torch.manual_seed(0)
+    ref = DRFNet(precision="fp32", **MODEL).to("cuda")
+    net = DRFNet(precision="bf16", **MODEL)
+    net.load_state_dict(ref.state_dict())
+    net = net.to("cuda")
+    grads = []
+    outs_all = []
+    for m in (ref, net, net):
+        m.zero_grad()
+        outs = m(x)
+        loss = torch.stack([torch.nn.L1Loss()(o, t) for o, t in zip(outs, y)]).mean()
+        loss.backward()
+        grads.append({k: p.grad.clone() for k, p in m.named_parameters()})
+        outs_all.append([o.detach() for o in outs])
+    p_ref, _ = restated.vsr_metrics([o.cpu() for o in outs_all[0]], hrs)
+    p_got, _ = restated.vsr_metrics([o.cpu() for o in outs_all[1]], hrs)
+    assert abs(float(p_got) - float(p_ref)) <= 0.05, (float(p_got), float(p_ref))
+    for a, b in zip(outs_all[1], outs_all[0]):
+        assert (a - b).abs().max() <= 5e-2 * b.abs().max()
+    num = sum(float(((grads[1][k] - g) ** 2).sum()) for k, g in grads[0].items()) ** 0.5
+    den = sum(float((g ** 2).sum()) for g in grads[0].values()) ** 0.5
+    print("config-2 bf16 vs fp32-mode global grad rel L2 error:", num / den)
+    assert num / den <= 5e-2
+    for k in grads[1]:
+        assert torch.equal(grads[1][k], grads[2][k]), k
+    for a, b in zip(outs_all[1], outs_all[2]):
+        assert torch.equal(a, b)

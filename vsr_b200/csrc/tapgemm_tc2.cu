@@ -392,6 +392,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
     uint32_t in_phase = 0;
     const float slope = (epi & (VSR_EPI_PRELU | VSR_EPI_PRELU_BWD)) ? __ldg(a.slope) : 0.f;
     const float inv_slope = slope != 0.f ? 1.f / slope : 0.f;
+    const bool slope01 = slope >= 0.f && slope <= 1.f;
     float slope_acc = 0.f;
     long long e_wait = 0, e_in = 0, e_ld = 0, e_math = 0, e_st = 0, e_iss = 0, e_t0 = clock64();
 
@@ -493,8 +494,14 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
               }
             }
             if (epi & VSR_EPI_PRELU) {
+              if (slope01) {
+                // for 0 <= a <= 1: PReLU(v) = max(v, a*v) exactly (two instructions per element instead of three)
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : slope * v[i];
+                for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], slope * v[i]);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : slope * v[i];
+              }
             }
             if (epi & VSR_EPI_RELU) {
 #pragma unroll
@@ -514,8 +521,10 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
                     const bool pos = f > 0.f;
                     if (epi & VSR_EPI_PRELU_BWD) {
                       // out-of-image pixels read f = 0 from the TMA zero fill and contribute exactly 0
-                      slope_acc += pos ? 0.f : v[i] * (f * inv_slope);
-                      v[i] = pos ? v[i] : slope * v[i];
+                      // d(slope) = sum over y <= 0 of g * x with x = y / slope: accumulate g * min(y, 0) here and
+                      // scale by 1 / slope once per CTA
+                      slope_acc = fmaf(v[i], fminf(f, 0.f), slope_acc);
+                      v[i] *= pos ? 1.f : slope;
                     } else {
                       v[i] = pos ? v[i] : 0.f;
                     }
@@ -581,7 +590,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
       printf("tc2-prof epilogue warp %d: total %lld cyc, wait(tfull) %lld, operands %lld, tmem-ld %lld, math %lld, pack+sts %lld, fence+issue %lld\n",
              warp, clock64() - e_t0, e_wait, e_in, e_ld, e_math, e_st, e_iss);
     if (epi & VSR_EPI_PRELU_BWD) {
-      slope_acc = warp_sum(slope_acc);
+      slope_acc = warp_sum(slope_acc) * inv_slope;
       if (lane == 0) red[ew] = slope_acc;
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (ew == 0 && lane == 0)

@@ -127,6 +127,9 @@ class CudaOps:
             sig = f"taps{tab.n_taps_total}_nt{tab.nt}_g{tab.n_groups}_px{pix}_epi{epi}"
             es = out.element_size()
             nbytes = es * (sum(pix * s.shape[-1] for s in srcs) + pix * out.shape[-1])
+            # epilogue operands read (residual, saved activation, second residual) / written (second output)
+            n_extra = ((epi & EPI_RES_PRE) != 0) + ((epi & (EPI_PRELU_BWD | EPI_RELU_BWD)) != 0) + 2 * ((epi & EPI_OUT2) != 0)
+            nbytes += es * pix * out.shape[-1] * n_extra
             self.timing.append(("tapgemm", 2.0 * pix * tab.n_taps_total * tab.nt * tab.kc, e0, e1, sig, nbytes))
         else:
             check(fn(C.byref(d), _stream()), "vsr_tapgemm")
