@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define VSR_ABI_VERSION 2
+#define VSR_ABI_VERSION 3
 #define VSR_MAX_SRCS 8
 
 typedef enum VsrStatus {
@@ -102,6 +102,7 @@ typedef struct VsrTapGemmDesc {
   float* slope_partials; /* device, >= vsr_partials_len() floats: per-CTA partial slope grads */
   const int32_t* tap_tab_host; /* optional HOST copy of tap_tab (or NULL): lets the bf16 kernels plan shared loads
                                   for taps that differ only by a row shift; results do not depend on it */
+  const int32_t* group_tab_host; /* optional HOST copy of group_tab (or NULL): shared loads for tables with several groups */
 } VsrTapGemmDesc;
 
 int vsr_abi_version(void);

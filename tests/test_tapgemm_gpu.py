@@ -258,3 +258,21 @@ def test_wgrad_tc_shared_pair_loads(monkeypatch):
     monkeypatch.setenv("VSR_WG_TALL", "1")
     _wgrad_case(strided_conv_table(), n=4, h=16, w=32, src_c=1024, out_c=64, seed=25)
     _wgrad_case(strided_conv_table(), n=2, h=19, w=32, src_c=1024, out_c=64, seed=26)
+
+
+@pytest.mark.parametrize("n_groups,nt", [(4, 128), (2, 256), (4, 64)])
+def test_tc_bf16_shared_loads_several_groups_many_tiles(n_groups, nt, monkeypatch):
+    """deconv-like tables (every group: two columns of two row shifts) with more tiles than CTAs and a ring
+    shallower than the producer count - the case that exposed the mbarrier parity aliasing of a producer
+    that runs a whole ring ahead (tapgemm_tc2.cu: at most `stages` producers are active)."""
+    groups = []
+    for g in range(n_groups):
+        gy, gx = g // 2, g % 2
+        groups.append((g * nt, [(0, dy - 1 + gy, dx - 1 + gx, 0) for dy in (0, 1) for dx in (0, 1)]))
+    tab = TapTable(kc=64, nt=nt, groups=groups)
+    monkeypatch.setenv("VSR_TC_RESIDENT", "0")
+    _run_case(tab, n=20, h=32, w=32, src_c=64, out_c=n_groups * nt, dtype=torch.bfloat16, epi=L.EPI_BIAS | L.EPI_PRELU, seed=27)
+    monkeypatch.setenv("VSR_TC_STAGES", "2")
+    _run_case(tab, n=20, h=32, w=32, src_c=64, out_c=n_groups * nt, dtype=torch.bfloat16, epi=L.EPI_PRELU_BWD, seed=28)
+    monkeypatch.setenv("VSR_TC_STAGES", "1")
+    _run_case(tab, n=6, h=32, w=32, src_c=64, out_c=n_groups * nt, dtype=torch.bfloat16, epi=0, seed=29)

@@ -28,7 +28,7 @@ class VsrTapGemmDesc(C.Structure):
         ("epi", C.c_int32), ("out_scale", C.c_float),
         ("slope", C.c_void_p), ("residual", C.c_void_p), ("aux_y", C.c_void_p),
         ("out2", C.c_void_p), ("res2", C.c_void_p), ("slope_partials", C.c_void_p),
-        ("tap_tab_host", C.c_void_p),
+        ("tap_tab_host", C.c_void_p), ("group_tab_host", C.c_void_p),
     ]
 
 
@@ -123,7 +123,7 @@ def lib():
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
-        if handle.vsr_abi_version() != 2:
+        if handle.vsr_abi_version() != 3:
             raise VsrError("libvsr_sm100.so ABI version mismatch")
         _lib = handle
     return _lib

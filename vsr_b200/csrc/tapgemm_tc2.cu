@@ -40,6 +40,7 @@ constexpr int kTileBytes = 4096;              // epilogue tile: 32 pixels x 64 c
 constexpr int kMaxSmemGroups = 36;            // group table rows cached in smem (16 B each, ctrl[448..1024))
 constexpr int kMaxSmemTaps = 256;             // column entries cached in smem (8 B each)
 constexpr int kMaxParamCols = 32;             // host-built columns travel in the kernel arguments
+constexpr int kMaxTallGroups = 8;
 constexpr int kBiasFloats = 1024;
 constexpr int kCtrlBytes = 1024 + kMaxSmemTaps * 8 + kBiasFloats * 4;   // 7 KiB, keeps 1024-byte alignment
 constexpr int kTmemCols = 512;
@@ -55,6 +56,7 @@ struct Tc2Args {
   CUtensorMap tall_maps[VSR_MAX_SRCS];   // shared-load mode: box of mb*bh + ndy_max - 1 rows
   CUtensorMap out_map, res_map, aux_map, out2_map, res2_map;
   uint2 cols[kMaxParamCols];             // shared-load mode: {packed tap (dy = first row shift), slab0 | stride<<12 | ndy<<24}
+  int4 tgroups[kMaxTallGroups];          // shared-load mode: {o0, first column, columns, first tap | taps<<16}
   const int4* tap_tab;
   const int4* group_tab;
   const uint8_t* w;
@@ -169,11 +171,10 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
   // A "column" is one A load feeding ndy taps (weight slabs slab0 + j*stride) whose row shifts are
   // dy0 + j; plain mode: every tap is a column of its own.
   if (a.tall) {
-    if (threadIdx.x == 0) {
-      int4 g = __ldg(a.group_tab);
-      g.y = 0;
-      g.z = a.n_cols;
-      grp_s[0] = g;
+    if (threadIdx.x < a.n_groups) {
+      int4 g = a.tgroups[threadIdx.x];
+      if (g.x < 0) g.x = __ldg(a.group_tab + threadIdx.x).x;      // single group: the slice start lives in the device table
+      grp_s[threadIdx.x] = g;
     }
     for (int i = threadIdx.x; i < a.n_cols; i += blockDim.x) col_s[i] = a.cols[i];
   } else {
@@ -237,27 +238,33 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
       uint32_t phase = 0;
       int cur_g = -1;
       uint32_t gcount = 0;
-      int turn = 0;                               // position in the tap sequence modulo kProducers
+      // Producers take the columns in turn.  A producer only waits for the slots it fills itself, so it
+      // must not get a whole ring ahead of a slot it never waited on (the parity of an mbarrier phase
+      // aliases after two completions): at most `stages` producers may be active.
+      const int n_prod = a.stages < kProducers ? a.stages : kProducers;
+      int turn = 0;                               // position in the column sequence modulo n_prod
       long long p_wait = 0, p_n = 0, p_t0 = clock64();
       for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
         const TileCoord tc = decode_tile(a, tile);
         int4 grp = grp_in_smem ? grp_s[tc.g] : __ldg(a.group_tab + tc.g);
         grp.y = __shfl_sync(0xffffffffu, grp.y, 0);
         grp.z = __shfl_sync(0xffffffffu, grp.z, 0);
+        grp.w = __shfl_sync(0xffffffffu, grp.w, 0);
         if (a.resident && tc.g != cur_g && warp == 0) {
           // (re)load this group's weight slabs once all MMAs of the previous group are done
+          const int tap0 = a.tall ? (grp.w & 0xffff) : grp.y, ntap = a.tall ? (grp.w >> 16) : grp.z;
           ptx::mbar_wait(bres_empty, (gcount & 1u) ^ 1u);
           if (leader) {
-            ptx::mbar_arrive_expect_tx(bres_full, static_cast<uint32_t>(grp.z) * b_bytes);
-            for (int t = 0; t < grp.z; ++t)
-              ptx::bulk_load(res_base + t * b_bytes, a.w + static_cast<size_t>(grp.y + t) * b_bytes, b_bytes, bres_full);
+            ptx::mbar_arrive_expect_tx(bres_full, static_cast<uint32_t>(ntap) * b_bytes);
+            for (int t = 0; t < ntap; ++t)
+              ptx::bulk_load(res_base + t * b_bytes, a.w + static_cast<size_t>(tap0 + t) * b_bytes, b_bytes, bres_full);
           }
           cur_g = tc.g;
           ++gcount;
         }
         for (int t = 0; t < grp.z; ++t) {
           const bool mine = turn == warp;
-          if (++turn == kProducers) turn = 0;
+          if (++turn == n_prod) turn = 0;
           if (!mine) {
             if (++stage == a.stages) { stage = 0; phase ^= 1u; }
             continue;
@@ -306,7 +313,10 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
       for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++it) {
         const TileCoord tc = decode_tile(a, tile);
         int4 grp = grp_in_smem ? grp_s[tc.g] : __ldg(a.group_tab + tc.g);
+        grp.y = __shfl_sync(0xffffffffu, grp.y, 0);
         grp.z = __shfl_sync(0xffffffffu, grp.z, 0);
+        grp.w = __shfl_sync(0xffffffffu, grp.w, 0);
+        const int tap0 = a.tall ? (grp.w & 0xffff) : grp.y;      // first weight slab of the group
         if (a.resident && tc.g != cur_g) {
           ptx::mbar_wait(bres_full, gcount & 1u);
           cur_g = tc.g;
@@ -333,7 +343,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
             if (!(a.debug & 8)) {
               for (int j = 0; j < ndy; ++j) {
                 const uint64_t bdesc = ptx::make_sw128_desc(
-                    a.resident ? res_base + (slab0 + j * sstride - grp.y) * b_bytes : sa + a_bytes + j * b_bytes, 16, 1024);
+                    a.resident ? res_base + (slab0 + j * sstride - tap0) * b_bytes : sa + a_bytes + j * b_bytes, 16, 1024);
                 for (int m = 0; m < a.mb; ++m) {
                   // rows shifted by j (tap) and m*bh (sub-tile) inside the shared A box: whole pixel rows,
                   // i.e. multiples of 1024 bytes, so the swizzle phase of the descriptor is unchanged
@@ -613,10 +623,10 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
 
 // Host: fold the taps of a (single-group) table into columns = taps with equal (src, c0, dx), consecutive dy
 // and evenly spaced slab indices.  Returns the longest column (0 if the table does not fit the argument array).
-int build_columns(const int32_t* taps, int n_taps, uint2* cols, int* n_cols) {
+int build_columns(const int32_t* taps, int n_taps, int idx_base, int max_cols, uint2* cols, int* n_cols) {
   struct T { int src, dy, dx, c0, idx; };
   std::vector<T> v(n_taps);
-  for (int i = 0; i < n_taps; ++i) v[i] = T{taps[4 * i], taps[4 * i + 1], taps[4 * i + 2], taps[4 * i + 3], i};
+  for (int i = 0; i < n_taps; ++i) v[i] = T{taps[4 * i], taps[4 * i + 1], taps[4 * i + 2], taps[4 * i + 3], idx_base + i};
   for (const T& t : v)
     if (t.src < 0 || t.src > 15 || t.dy < -8 || t.dy > 7 || t.dx < -8 || t.dx > 7 || (t.c0 & 7)) return 0;
   std::stable_sort(v.begin(), v.end(), [](const T& x, const T& y) {
@@ -638,7 +648,7 @@ int build_columns(const int32_t* taps, int n_taps, uint2* cols, int* n_cols) {
       ++j;
     }
     const int ndy = (int)(j - i);
-    if (n >= kMaxParamCols) return 0;
+    if (n >= max_cols) return 0;
     const int4 first = make_int4(v[i].src, v[i].dy, v[i].dx, v[i].c0);
     cols[n].x = (uint32_t)first.x | ((uint32_t)(first.y + 8) << 4) | ((uint32_t)(first.z + 8) << 8) | ((uint32_t)(first.w >> 3) << 12);
     cols[n].y = (uint32_t)v[i].idx | ((uint32_t)(ndy > 1 ? stride : 0) << 12) | ((uint32_t)ndy << 24);
@@ -747,32 +757,52 @@ int tapgemm_tc2_launch(const VsrTapGemmDesc* d, cudaStream_t stream) {
   const char* env_dbg = getenv("VSR_TC_DEBUG");            // re-read per launch: attribution sweeps flip it
   a.debug = env_dbg ? atoi(env_dbg) : 0;
 
-  // ---- shared-load mode: taps that differ only by a row shift read one A box; two pixel tiles stacked
-  // in y share every weight slab.  Needs the host copy of the tap table (d->tap_tab_host).
+  // ---- shared-load mode: taps that differ only by a row shift read one A box; with nt <= 128 two pixel
+  // tiles stacked in y also share every weight slab.  Needs the host copies of the tables
+  // (d->tap_tab_host, and d->group_tab_host when there are several groups).
   a.mb = 1;
   a.a_bytes = kATileBytes;
   int ndy_max = 1;
+  const long res_need = (long)d->max_group_taps * b_bytes;
   {
     const char* env_tall = getenv("VSR_TC_TALL");
     const bool want = !(env_tall && env_tall[0] == '0');
-    if (want && d->tap_tab_host != nullptr && d->n_groups == 1 && d->nt <= 128 && bw >= 8 && bw * bh == kBlockM &&
-        d->n_taps_total <= 4095)
-      ndy_max = build_columns(d->tap_tab_host, d->n_taps_total, a.cols, &a.n_cols);
-    if (ndy_max >= 2) {
-      const int mb = (a.H >= 2 * bh) ? 2 : 1;
-      const int rows = mb * bh + ndy_max - 1;
-      const long stage = (long)rows * a.row_bytes + (long)ndy_max * b_bytes;
-      if (rows <= 256 && 3 * stage <= avail) {
+    bool ok = want && d->tap_tab_host != nullptr && bw >= 8 && bw * bh == kBlockM && d->n_taps_total <= 4095 &&
+              d->n_groups <= kMaxTallGroups && (d->n_groups == 1 || d->group_tab_host != nullptr);
+    int n_cols = 0, longest = 0;
+    for (int gi = 0; ok && gi < d->n_groups; ++gi) {
+      const int o0 = d->n_groups == 1 ? 0 : d->group_tab_host[4 * gi];
+      const int begin = d->n_groups == 1 ? 0 : d->group_tab_host[4 * gi + 1];
+      const int count = d->n_groups == 1 ? d->n_taps_total : d->group_tab_host[4 * gi + 2];
+      int nc = 0;
+      const int lg = build_columns(d->tap_tab_host + 4 * begin, count, begin, kMaxParamCols - n_cols, a.cols + n_cols, &nc);
+      if (lg == 0 || begin > 0xffff || count > 0x7fff) { ok = false; break; }
+      a.tgroups[gi] = make_int4(o0, n_cols, nc, begin | (count << 16));
+      n_cols += nc;
+      if (lg > longest) longest = lg;
+    }
+    if (ok && d->n_groups == 1) {
+      // the output slice of a single group comes from the device table (group_tab_host is optional)
+      a.tgroups[0].x = -1;
+    }
+    if (ok && longest >= 2) {
+      const int mb = (d->nt <= 128 && a.H >= 2 * bh) ? 2 : 1;
+      const int rows = mb * bh + longest - 1;
+      const long abox = (long)rows * a.row_bytes;
+      const bool res_ok = d->max_group_taps > 0 && d->nt > 64 && res_need <= avail - 3 * abox;
+      const bool stream_ok = 3 * (abox + (long)longest * b_bytes) <= avail;
+      if (rows <= 256 && (res_ok || stream_ok)) {
         a.tall = 1;
         a.mb = mb;
-        a.a_bytes = rows * a.row_bytes;
+        a.n_cols = n_cols;
+        a.a_bytes = (int)abox;
+        ndy_max = longest;
         for (int s = 0; s < d->n_srcs; ++s) {
           int rc = get_src_map_pub(d->srcs[s], bw, rows, &a.tall_maps[s]);
           if (rc != VSR_OK) return rc;
         }
       }
     }
-    if (!a.tall) ndy_max = 1;
   }
   a.tiles_x = (a.W + bw - 1) / bw;
   a.tiles_y = (a.H + bh * a.mb - 1) / (bh * a.mb);
@@ -780,18 +810,27 @@ int tapgemm_tc2_launch(const VsrTapGemmDesc* d, cudaStream_t stream) {
   VSR_CHECK_SUPPORTED(tiles < (1l << 30), "tapgemm(bf16): too many tiles");
   a.num_tiles = (int)tiles;
   a.m_tiles = a.N * a.tiles_x * a.tiles_y;
-  const long res_need = (long)d->max_group_taps * b_bytes;
   // weight-resident mode: the group's slabs stay in smem and >= 3 A stages remain; worth it when the
   // slabs are large next to the A tile (nt > 64) and every CTA sees few groups
   // (short nt=64 tables - the 1x1 convolutions on concatenations - were measured 5-10% slower resident:
   // tools/hr_sweep.py, so they stream their 8 KB slabs with the A tiles)
-  a.resident = !a.tall && d->max_group_taps > 0 && d->nt > 64 && res_need <= avail - 3 * kATileBytes &&
+  a.resident = d->max_group_taps > 0 && d->nt > 64 && res_need <= avail - 3 * (long)a.a_bytes &&
                tiles >= 2 * (long)num_sms();
   {
     const char* env_res = getenv("VSR_TC_RESIDENT");
     if (env_res && env_res[0] == '0') a.resident = 0;
-    if (env_res && env_res[0] == '1' && !a.tall && d->max_group_taps > 0 && res_need <= avail - 2 * kATileBytes)
+    if (env_res && env_res[0] == '1' && d->max_group_taps > 0 && res_need <= avail - 2 * (long)a.a_bytes)
       a.resident = 1;
+  }
+  if (a.tall && !a.resident && 2 * ((long)a.a_bytes + (long)ndy_max * b_bytes) > avail) {
+    // the shared box plus its slabs does not fit twice without resident weights: plain columns
+    a.tall = 0;
+    a.mb = 1;
+    a.a_bytes = kATileBytes;
+    ndy_max = 1;
+    a.tiles_y = (a.H + bh - 1) / bh;
+    a.num_tiles = (int)((long)a.n_groups * a.N * a.tiles_x * a.tiles_y);
+    a.m_tiles = a.N * a.tiles_x * a.tiles_y;
   }
   a.res_bytes = a.resident ? (int)res_need : 0;
   a.stage_bytes = a.resident ? a.a_bytes : a.a_bytes + ndy_max * b_bytes;
@@ -807,6 +846,15 @@ int tapgemm_tc2_launch(const VsrTapGemmDesc* d, cudaStream_t stream) {
   if (env_grid && atoi(env_grid) >= 1) grid = atoi(env_grid);
   if (grid > a.num_tiles) grid = a.num_tiles;
   if (grid > kPartialsLen) grid = kPartialsLen;
+  if (a.debug & 64) {
+    fprintf(stderr, "tc2 plan: nt %d groups %d taps %d | tall %d mb %d cols %d a_bytes %d | resident %d res_bytes %d | stages %d x %d, epi %d, smem %d, tiles %d (m %d), grid %d\n",
+            a.nt, a.n_groups, a.n_taps_total, a.tall, a.mb, a.n_cols, a.a_bytes, a.resident, a.res_bytes, a.stages,
+            a.stage_bytes, a.epi_bytes, smem, a.num_tiles, a.m_tiles, grid);
+    if (a.tall)
+      for (int gi = 0; gi < a.n_groups; ++gi)
+        fprintf(stderr, "  group %d: o0 %d cols [%d, +%d) taps [%d, +%d)\n", gi, a.tgroups[gi].x, a.tgroups[gi].y,
+                a.tgroups[gi].z, a.tgroups[gi].w & 0xffff, a.tgroups[gi].w >> 16);
+  }
   {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));

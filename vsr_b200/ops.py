@@ -68,6 +68,16 @@ class TapTable:
             self._dev["host"] = torch.tensor([list(t) for t in self.flat_taps()], dtype=torch.int32).contiguous()
         return self._dev["host"]
 
+    def host_groups(self):
+        """Host copy of the group table: VsrTapGemmDesc.group_tab_host."""
+        if "host_groups" not in self._dev:
+            rows, begin = [], 0
+            for o0, taps in self.groups:
+                rows.append([o0, begin, len(taps), 0])
+                begin += len(taps)
+            self._dev["host_groups"] = torch.tensor(rows, dtype=torch.int32).contiguous()
+        return self._dev["host_groups"]
+
 
 def _tensor4(t: torch.Tensor) -> VsrTensor4:
     n, h, w, c = t.shape
@@ -91,6 +101,7 @@ def _make_desc(tab: TapTable, srcs: Sequence[torch.Tensor], out: torch.Tensor):
     d.max_group_taps = max(len(t) for _, t in tab.groups)
     d.group_tab, d.tap_tab = gt.data_ptr(), tt.data_ptr()
     d.tap_tab_host = tab.host_taps().data_ptr()
+    d.group_tab_host = tab.host_groups().data_ptr()
     return d
 
 
