@@ -39,7 +39,7 @@ constexpr int kEpiWarps = 8;                  // two per TMEM lane quarter: even
 constexpr int kTileBytes = 4096;              // epilogue tile: 32 pixels x 64 channels bf16
 constexpr int kMaxSmemGroups = 36;            // group table rows cached in smem (16 B each, ctrl[448..1024))
 constexpr int kMaxSmemTaps = 256;             // column entries cached in smem (8 B each)
-constexpr int kMaxParamCols = 32;             // host-built columns travel in the kernel arguments
+constexpr int kMaxParamCols = 64;             // host-built columns travel in the kernel arguments
 constexpr int kMaxTallGroups = 8;
 constexpr int kBiasFloats = 1024;
 constexpr int kCtrlBytes = 1024 + kMaxSmemTaps * 8 + kBiasFloats * 4;   // 7 KiB, keeps 1024-byte alignment
@@ -84,6 +84,8 @@ struct Tc2Args {
   int row_bytes;           // bw * 128: bytes of one pixel row of the A box
   int stage_bytes;         // A box + the weight slabs of one column (none in resident mode)
 };
+
+static_assert(sizeof(Tc2Args) <= 4096, "kernel arguments are limited to 4 KB");
 
 // tap entry packed into 32 bits: src[0:4) | dy+8 [4:8) | dx+8 [8:12) | c0/8 [12:32)
 __device__ __forceinline__ uint32_t pack_tap(const int4& t) {
