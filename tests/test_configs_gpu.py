@@ -73,3 +73,31 @@ def test_config3_dsb15_full_fov_inference_metrics_on_device():
         den_o, den_t = restated.denormalize(o_bf[i].cpu(), "dsb15"), restated.denormalize(hrs[i], "dsb15")
         assert abs(float(restated.psnr(den_o, den_t)) - float(p_bf[i])) <= 1e-3
         assert abs(float(restated.ssim(den_o, den_t)) - float(s_bf[i])) <= 2e-5
+
+
+def test_predictor_on_device_batched(tmp_path):
+    """VSRPredictor on the GPU with a batch of 3 synthetic validation sequences: the log equals the mean of the
+    per-frame rows it exported, and the rows equal the stand-alone metric modules on the network outputs."""
+    import csv
+    from vsr_b200.data import Dataloader, SyntheticCineDataset
+    from vsr_b200.runner import VSRPredictor
+    ds = SyntheticCineDataset(4, type="valid", dataset="acdc", num_sequences=3, seed=3)
+    loader = Dataloader(ds, batch_size=3, shuffle=False, num_workers=0)
+    torch.manual_seed(4)
+    net = DRFNet(1, 1, 64, 2, 4, precision="bf16")
+    pred = VSRPredictor("cuda", loader, net, [torch.nn.L1Loss()], [1.0], [PSNR(), SSIM()], saved_dir=str(tmp_path),
+                        exported=True, dataset="acdc")
+    log = pred.predict()
+    rows = list(csv.reader(open(tmp_path / "results.csv")))
+    T = ds.T
+    assert rows[0] == ["name", "PSNR", "SSIM", "L1Loss"] and len(rows) == 1 + 3 * T
+    vals = torch.tensor([[float(v) for v in r[1:]] for r in rows[1:]])
+    assert abs(float(vals[:, 0].mean()) - log["PSNR"]) <= 1e-3
+    assert abs(float(vals[:, 1].mean()) - log["SSIM"]) <= 1e-5
+    assert abs(float(vals[:, 2].mean()) - log["L1Loss"]) <= 1e-5 and abs(log["Loss"] - log["L1Loss"]) <= 1e-6
+    batch = next(iter(loader))
+    x, y = [t.cuda() for t in batch["lr_imgs"]], [t.cuda() for t in batch["hr_imgs"]]
+    with torch.no_grad():
+        outs = pred.net(x)
+    p = PSNR(size_average=False, dataset="acdc").cuda()(outs[2], y[2])
+    assert abs(float(p[1]) - float(vals[1 * T + 2, 0])) <= 1e-3      # sequence 1, frame 3

@@ -125,3 +125,46 @@ def test_two_rank_data_parallel_equals_single_rank():
         assert p.exitcode == 0
     # mean of the per-rank mean-losses == whole-batch mean loss (equal shard sizes)
     assert (flat - net.flat).abs().max() <= 1e-6
+
+
+def test_predictor_log_and_csv_match_reference_loop(tmp_path):
+    """VSRPredictor.predict() (acdc_vsr_predictor.py:30-110) on CPU through the kernel emulation: the log and
+    the per-frame rows of results.csv equal the reference's loop body restated with the oracle."""
+    import csv
+    from vsr_b200.runner import VSRPredictor
+    fx = torch.load(os.path.join(GOLDEN, "drfnet_f8_g2_x2.pt"))
+    net = DRFNet(**fx["kwargs"])
+    net.load_state_dict(fx["state_dict"])
+    net._ops = EmuOps()
+    n = fx["inputs"][0].shape[0]
+
+    class OneBatch:            # a "dataloader" that yields the golden sequences as one batch
+        batch_size = n
+        dataset = type("D", (), {"data": None})()
+
+        def __iter__(self):
+            yield {"lr_imgs": fx["inputs"], "hr_imgs": fx["targets"], "index": torch.arange(n)}
+
+        def __len__(self):
+            return 1
+
+    pred = VSRPredictor("cpu", OneBatch(), net, [torch.nn.L1Loss()], [1.0], [PSNR(), SSIM()], saved_dir=str(tmp_path),
+                        exported=True, dataset="acdc")
+    log = pred.predict()
+    outs = restated.drfnet_forward(fx["inputs"], dict(fx["state_dict"]), fx["kwargs"]["upscale_factor"])
+    T = len(outs)
+    l1 = [float(restated.l1_loss(o, t)) for o, t in zip(outs, fx["targets"])]
+    den = lambda x: restated.denormalize(x.detach(), "acdc")
+    ps = [restated.psnr(den(o), den(t), size_average=False) for o, t in zip(outs, fx["targets"])]
+    ss = [restated.ssim(den(o), den(t), size_average=False) for o, t in zip(outs, fx["targets"])]
+    assert abs(log["L1Loss"] - sum(l1) / T) <= 1e-5 and abs(log["Loss"] - sum(l1) / T) <= 1e-5
+    assert abs(log["PSNR"] - float(torch.stack(ps).mean())) <= 1e-3
+    assert abs(log["SSIM"] - float(torch.stack(ss).mean())) <= 1e-4
+    rows = list(csv.reader(open(tmp_path / "results.csv")))
+    assert rows[0] == ["name", "PSNR", "SSIM", "L1Loss"] and len(rows) == 1 + n * T
+    assert rows[1][0] == "slice00000_frame01"
+    for i in range(n):
+        for t in range(T):
+            r = rows[1 + i * T + t]
+            assert abs(float(r[1]) - float(ps[t][i])) <= 1e-3 and abs(float(r[2]) - float(ss[t][i])) <= 1e-4
+            assert abs(float(r[3]) - l1[t]) <= 1e-5

@@ -223,6 +223,40 @@ class VSRTrainStep:
                 self._metrics(outs, targets, acc)
         return lvals, outs
 
+    @torch.no_grad()
+    def eval_frames(self, inputs, targets):
+        """The predictor's loop body (acdc_vsr_predictor.py:53-66) for a whole batch of sequences: forward under
+        no_grad, then on the device per-frame losses [T, n_loss] (batch means) and per-frame, per-sample metrics
+        [n_metric, T, N] with the denormalisation fused.  Returns (outputs, losses, metrics); nothing syncs."""
+        net = self.net
+        if not net._is_flat():
+            net._flatten()
+        ops = self._ops()
+        eng = self._engine()
+        eng.pack(net.flat, need_bwd=False)
+        outs, _ = eng.forward([x.contiguous() for x in inputs], save=False)
+        targets = [y.contiguous() for y in targets]
+        T, L, n, c = len(outs), len(self.losses), outs[0].shape[0], outs[0].shape[1]
+        partials = torch.zeros(L * T, ops.partials_len, device=outs[0].device)
+        for li, (kind, param) in enumerate(self.losses):
+            for t in range(T):
+                ops.loss_fwd_bwd(outs[t], targets[t], kind, param, 0.0, partials[li * T + t], None)
+        losses = (partials.sum(dim=1) / outs[0].numel()).view(L, T).t().contiguous()
+        per = outs[0].numel() // n
+        ws = self._buf("mws", (ops.metric_workspace(n * c, per) // 4 + 4,))
+        vals = torch.zeros(len(self.metric_names), T, n * c, device=outs[0].device)
+        for i, (name, fn) in enumerate(zip(self.metric_names, self.metric_fns)):
+            for t in range(T):
+                o, y = outs[t], targets[t]
+                if name == "PSNR":
+                    ops.psnr(o, y, self.mean, self.std, float(fn.max_value), vals[i, t, :n], ws)
+                else:
+                    ops.ssim(o.view(n * c, *o.shape[2:]), y.view(n * c, *y.shape[2:]), fn.window, self.mean,
+                             self.std, fn.c1, fn.c2, vals[i, t], ws)
+        metrics = torch.stack([vals[i, :, :n] if name == "PSNR" else vals[i].view(T, n, c).mean(dim=2)
+                               for i, name in enumerate(self.metric_names)]) if self.metric_names else vals
+        return outs, losses, metrics
+
     def _log(self, acc, lvals):
         w = self._bufs.get("lw")
         if w is None:
@@ -340,3 +374,79 @@ class VSRTrainer:
 
 
 AcdcVSRTrainer = VSRTrainer
+
+
+class VSRPredictor:
+    """Drop-in for AcdcVSRPredictor / Dsb15VSRPredictor (acdc_vsr_predictor.py:15-110; base_predictor.py:6-23):
+    same constructor keywords (`dataset` selects the denormalisation constants) and the same `predict()` log
+    (Loss, each loss, each metric; every sequence weighted by batch_size * T, :96-98,160-165).
+
+    Differences, all on purpose: any batch size (the reference insists on 1 because its metrics loop is
+    per-sequence; here losses and metrics of all frames of all sequences of a batch come from the fused device
+    kernels with one host read-back per batch), and `exported=True` writes `results.csv` only (one row per
+    sequence and frame: name_frameNN, metrics, losses - :70-73,101-104); PNG / GIF export stays with the
+    reference tooling (out of the hot path).  For batch_size > 1 the loss columns are batch
+    means."""
+
+    def __init__(self, device, test_dataloader, net, loss_fns, loss_weights, metric_fns, saved_dir=None,
+                 exported=False, dataset="acdc"):
+        self.device = torch.device(device)
+        self.test_dataloader = test_dataloader
+        self.net = net.to(self.device)
+        self.loss_fns, self.metric_fns = list(loss_fns), [m.to(self.device) for m in metric_fns]
+        self.loss_weights = torch.tensor(loss_weights, dtype=torch.float, device=self.device)
+        self.exported = exported
+        if exported:
+            from pathlib import Path
+            self.saved_dir = Path(saved_dir)
+        self.step = VSRTrainStep(self.net, self.loss_fns, list(loss_weights), self.metric_fns, None, dataset)
+
+    def _name(self, index):
+        data = getattr(self.test_dataloader.dataset, "data", None)
+        try:
+            entry = data[index][0]
+            return entry.parts[-1].split(".")[0]          # the reference's lr_path stem (:59-60)
+        except (AttributeError, TypeError, IndexError):
+            return f"sequence{int(index):05d}"
+
+    def _batches(self):
+        if self.device.type == "cuda":
+            from .data import DeviceStager
+            return DeviceStager(self.test_dataloader, self.device)
+        return self.test_dataloader
+
+    def predict(self):
+        import csv
+        self.net.eval()
+        keys = ["Loss"] + [f.__class__.__name__ for f in self.loss_fns] + [m.__class__.__name__ for m in self.metric_fns]
+        log = dict.fromkeys(keys, 0.0)
+        rows = [["name"] + keys[1 + len(self.loss_fns):] + keys[1:1 + len(self.loss_fns)]]
+        count = 0
+        for batch in self._batches():
+            inputs, targets, index = batch["lr_imgs"], batch["hr_imgs"], batch["index"]
+            bs, T = inputs[0].shape[0], len(inputs)
+            _, losses, metrics = self.step.eval_frames(inputs, targets)
+            loss = (losses.mean(dim=0) * self.loss_weights).sum()
+            host = torch.cat([loss.view(1), losses.mean(dim=0), metrics.mean(dim=(1, 2)) if metrics.numel() else metrics.view(0)])
+            vals = host.tolist()                                   # the one host read-back of the batch
+            for k, v in zip(keys, vals):
+                log[k] += v * bs * T
+            count += bs * T
+            if self.exported:
+                lt, mt = losses.tolist(), metrics.tolist()
+                idx = index.tolist() if torch.is_tensor(index) else list(index)
+                for i in range(bs):
+                    name = self._name(idx[i]).replace("2d+1d", "2d").replace("sequence", "slice")
+                    for t in range(T):
+                        rows.append([f"{name}_frame{t + 1:0>2d}"] + [m[t][i] for m in mt] + lt[t])
+        if self.exported:
+            self.saved_dir.mkdir(parents=True, exist_ok=True)
+            with open(self.saved_dir / "results.csv", "w", newline="") as f:
+                csv.writer(f).writerows(rows)
+        for k in log:
+            log[k] /= max(count, 1)
+        logging.info(f"Test log: {log}.")
+        return log
+
+
+AcdcVSRPredictor = Dsb15VSRPredictor = VSRPredictor
