@@ -10,7 +10,7 @@ from vsr_b200.ops import TapTable, cuda_ops  # noqa: E402
 
 def main():
     ops = cuda_ops()
-    N, h, w, F = 32, 32, 32, 64
+    N, h, w, F = 160, 32, 32, 64          # the T=5 frames of config 2 stacked (one launch per layer per step)
     taps = []
     for ky in range(8):
         for kx in range(8):

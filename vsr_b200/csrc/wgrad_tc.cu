@@ -30,7 +30,7 @@ namespace {
 
 constexpr int kTile = 128;
 constexpr int kTileBytes = kTile * 128;   // one [128 px x 64 ch] bf16 box
-constexpr int kMaxAStages = 6;            // ring of tap pairs (2 boxes each); as many as shared memory holds
+constexpr int kMaxAStages = 12;           // ring of tap pairs (2 boxes each); as many as shared memory holds
 constexpr int kMaxChunk = 8;              // taps per work item
 constexpr int kCtrl = 1024;
 constexpr int kThreads = 192;
@@ -47,6 +47,7 @@ struct WgArgs {
   int tall;                              // every pair (2p, 2p+1) is (tap, same tap one pixel row lower): one A load
   int row_bytes;                         // bw * 128
   int stages;                            // tap-pair ring depth
+  int slot_bytes;                        // bytes of one ring slot
   int debug;                             // VSR_WG_DEBUG: 32 = per-role cycle counts of block 0
   const int4* tap_tab;
   const int4* group_tab;
@@ -79,9 +80,10 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - ptx::smem_u32(smem_raw));
-  const uint32_t a_full = base, a_empty = base + 64, b_full = base + 128, b_empty = base + 144;
-  const uint32_t done_bar = base + 160, tmem_slot = base + 168;
-  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(gen + 168);
+  const uint32_t a_full = base, a_empty = base + 128, b_full = base + 256, b_empty = base + 272;   // 16 slots each for a_*
+  const uint32_t done_bar = base + 288, tmem_slot = base + 296;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(gen + 296);
+  const uint32_t slot_bytes = static_cast<uint32_t>(a.slot_bytes);   // one tap pair: two boxes, or one box of bh + 1 rows
   const int nb = a.ncta / 64;                                // dz boxes per tile
   const uint32_t b_bytes = nb * kTileBytes;
   const uint32_t b_base = base + kCtrl;                      // 2 buffers
@@ -166,7 +168,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
           if (prof) c0 = clock64();
           ptx::mbar_wait(a_empty + 8 * stage, phase ^ 1u);
           if (prof) p_wa += clock64() - c0;
-          const uint32_t sa = a_base + stage * 2 * kTileBytes;
+          const uint32_t sa = a_base + stage * slot_bytes;
           if (a.tall) {
             // the pair is (tap, tap shifted one pixel row down): one box of bh + 1 rows serves both
             int4 tap = taps[0];
@@ -220,7 +222,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
           ptx::mbar_wait(a_full + 8 * stage, phase);
           ptx::tc_fence_after();
           if (prof) { c1 = clock64(); m_wa += c1 - c0; }
-          const uint32_t sa = a_base + stage * 2 * kTileBytes;
+          const uint32_t sa = a_base + stage * slot_bytes;
           if (leader) {
 #pragma unroll
             for (int k = 0; k < kTile / 16; ++k) {
@@ -472,12 +474,11 @@ int wgrad_tc_partial(const VsrTapGemmDesc* d, int want_bias, int slice, int n_sl
     a.debug = env_dbg ? atoi(env_dbg) : 0;
   }
   {
-    // (opt-in with VSR_WG_TALL=1: measured no gain, the kernel is bound by the N=64 MMA rate - profiles/README.md)
     // shared-pair mode: reorder the taps of every group so that positions (2p, 2p+1) hold a tap and the tap
     // with the same source, channel slice and dx one pixel row lower; all pairs of the launch must be such
     const char* env_tall = getenv("VSR_WG_TALL");
     const int4* gt = nullptr;
-    if (env_tall && env_tall[0] == '1' && d->tap_tab_host && d->n_taps_total <= kMaxPerm && d->n_groups == 1 &&
+    if (!(env_tall && env_tall[0] == '0') && d->tap_tab_host && d->n_taps_total <= kMaxPerm && d->n_groups == 1 &&
         p.bw >= 8 && p.bw * p.bh == kTile && d->n_taps_total % 2 == 0 && pair_rows(d->tap_tab_host, d->n_taps_total, a.perm)) {
       a.use_perm = 1;
       a.tall = 1;
@@ -506,9 +507,12 @@ int wgrad_tc_partial(const VsrTapGemmDesc* d, int want_bias, int slice, int n_sl
   a.tiles_y = (a.H + p.bh - 1) / p.bh;
   a.num_ptiles = p.num_ptiles;
   const int nb = p.ncta / 64;
-  a.stages = (227 * 1024 - kCtrl - 1024 - 2 * nb * kTileBytes) / (2 * kTileBytes);
+  // the kernel is bound by the bytes it keeps in flight (frame-batched maps no longer fit the L2): a
+  // shared-pair slot is 20 KB instead of 32 KB, so the ring is 1.5x deeper in tap pairs
+  a.slot_bytes = a.tall ? kTileBytes + a.row_bytes : 2 * kTileBytes;
+  a.stages = (227 * 1024 - kCtrl - 1024 - 2 * nb * kTileBytes) / a.slot_bytes;
   if (a.stages > kMaxAStages) a.stages = kMaxAStages;
-  const int smem = kCtrl + 1024 + 2 * nb * kTileBytes + a.stages * 2 * kTileBytes;
+  const int smem = kCtrl + 1024 + 2 * nb * kTileBytes + a.stages * a.slot_bytes;
   {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
