@@ -207,6 +207,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
       const uint32_t lbo = a.tall ? a.row_bytes : kTileBytes;
       const bool prof = (a.debug & 32) != 0;
       long long m_wb = 0, m_wa = 0, m_is = 0, m_t0 = clock64(), c0 = 0, c1 = 0;
+      const uint64_t m_g0 = ptx::globaltimer_ns();
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -240,8 +241,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
       }
       if (leader) ptx::mma_commit(done_bar);
       if (prof && blockIdx.x == 0 && leader)
-        printf("wg-prof mma: total %lld cyc, wait(b_full) %lld, wait(a_full) %lld, issue %lld\n", clock64() - m_t0, m_wb,
-               m_wa, m_is);
+        printf("wg-prof mma: total %lld cyc in %llu ns, wait(b_full) %lld, wait(a_full) %lld, issue %lld\n", clock64() - m_t0,
+               (unsigned long long)(ptx::globaltimer_ns() - m_g0), m_wb, m_wa, m_is);
     }
   } else {
     const int quarter = warp & 3;
@@ -426,7 +427,8 @@ WgPlan make_plan(const VsrTapGemmDesc* d) {
   const int mg = d->max_group_taps > 0 ? d->max_group_taps : (d->n_taps_total + d->n_groups - 1) / d->n_groups;
   p.chunks = (mg + kMaxChunk - 1) / kMaxChunk;
   p.n_items = d->n_groups * (d->nt / p.ncta) * p.chunks;
-  int s = (num_sms() + p.n_items - 1) / p.n_items;   // one wave of equal-work CTAs
+  int s = num_sms() / p.n_items;   // ONE wave of equal-work CTAs: items * splits must not exceed the SM count
+                                   // (rounding up cost a second, nearly empty wave = 2x the kernel time)
   if (s > p.num_ptiles) s = p.num_ptiles;
   if (s < 1) s = 1;
   p.splits = s;
