@@ -334,6 +334,12 @@ def main():
                     "frac": tf / pk["bf16_tflops_sustained"] if tensor else gb / pk["hbm_gbs"]}
 
         kernel_detail = {k: shape_row(v) for k, v in top}
+        all_rows = [shape_row(v) for k, v in detail.items() if k.startswith(dom)]
+        t_all = sum(r["ms_per_step"] for r in all_rows)
+        # the dominant kernel runs tensor-bound and HBM-bound shapes: time-weighted mean of every shape's
+        # fraction of ITS OWN bound, and the split of its time between the two bounds
+        frac_own = sum(r["ms_per_step"] * r["frac"] for r in all_rows) / max(t_all, 1e-9)
+        hbm_share = sum(r["ms_per_step"] for r in all_rows if r["bound"] == "hbm") / max(t_all, 1e-9)
         step_flops = 3.0 * FWD_FLOPS_PER_LR_PIXEL * args.batch * T * LR * LR
         try:      # full per-shape table for the profile notes (scratch; the JSON line keeps the top 14)
             os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
@@ -356,6 +362,7 @@ def main():
                          "frac": achieved / peak, "traffic": traffic,
                          "algorithmic_bytes_per_launch": sum(v[3] for k, v in detail.items() if k.startswith(dom)) / max(cnt, 1),
                          "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk['source']})",
+                         "frac_time_weighted_own_bound": frac_own, "time_share_hbm_bound_shapes": hbm_share,
                          "launches": cnt, "kernels": kernel_share, "kernel_detail": kernel_detail,
                          "timing_pass": f"{prof_steps} extra steps of the same workload, CUDA events around each launch",
                          "step_tflops_algorithmic": step_flops / (ms * 1e-3) / 1e12 * world},
