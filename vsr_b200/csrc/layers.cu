@@ -254,8 +254,17 @@ __global__ void __launch_bounds__(256) rows_reduce_kernel(const float* __restric
   const int col = threadIdx.x & 63, part = threadIdx.x >> 6;
   const int i = blockIdx.x * 64 + col;
   float s = 0.f;
-  if (i < n)
-    for (int b = part; b < blocks; b += 4) s += ws[(size_t)b * n + i];
+  if (i < n) {
+    int b = part;
+    for (; b + 28 < blocks; b += 32) {     // eight loads in flight, additions in the order b = part, part+4, ...
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldg(ws + (size_t)(b + 4 * u) * n + i);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s += v[u];
+    }
+    for (; b < blocks; b += 4) s += ws[(size_t)b * n + i];
+  }
   sm[part][col] = s;
   __syncthreads();
   if (part == 0 && i < n) {
@@ -448,7 +457,15 @@ __global__ void conv_last_bwd_final_kernel(const float* __restrict__ ws, int blo
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= psz) return;
   float s = 0.f;
-  for (int b = 0; b < blocks; ++b) s += ws[(size_t)b * psz + i];
+  int b = 0;
+  for (; b + 8 <= blocks; b += 8) {        // eight loads in flight; the additions keep the order b = 0, 1, 2, ...
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __ldg(ws + (size_t)(b + u) * psz + i);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s += v[u];
+  }
+  for (; b < blocks; ++b) s += ws[(size_t)b * psz + i];
   float* dst;
   if (i < wsz) {
     const int co = i / (9 * c), rem = i % (9 * c), tap = rem / c, ci = rem % c;
@@ -957,6 +974,65 @@ __global__ void __launch_bounds__(256, 2) conv_last3_dw_kernel(const __nv_bfloat
   }
 }
 
+// data gradient of the last conv, v3 (bf16, C == 64, r == 4 with Z-order slots, cout == 1): one warp = one LR
+// block (4x4 HR pixels = 2 KB contiguous).  Lane = (pixel row pg = lane >> 3, channel octet cl = lane & 7): it
+// writes 16 bytes (8 channels) of the four pixels of its row, so a warp store covers 512 contiguous-by-128
+// bytes instead of 128, and the output address needs the centre block only.
+__global__ void __launch_bounds__(256, 2) conv_last3_dx_kernel(const __grid_constant__ LastGeom2 g,
+                                                              const float* __restrict__ wt, const float* __restrict__ dy,
+                                                              __nv_bfloat16* __restrict__ dx) {
+  const int lane = threadIdx.x & 31;
+  const int pg = lane >> 3, cl = lane & 7;
+  const int H = g.h * 4, W = g.w * 4;
+  const long total = (long)g.n * g.h * g.w;
+  const long warp0 = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+  float wr[9][8];                       // this lane's 8 channels of the 3x3 kernel (wt is [1][C][3][3])
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) wr[t][q] = __ldg(wt + (size_t)(cl * 8 + q) * 9 + t);
+  for (long item = warp0; item < total; item += nwarps) {
+    const int bx = (int)(item % g.w);
+    const int by = (int)((item / g.w) % g.h);
+    const int ni = (int)(item / ((long)g.w * g.h));
+    const int Y = by * 4 + pg, X0 = bx * 4;
+    // dy halo of this lane's pixel row: rows Y-1..Y+1, columns X0-1..X0+4 (zero outside the image)
+    float gy[3][6];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        const int yy = Y + i - 1, xx = X0 + j - 1;
+        const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
+        const float t = __ldg(dy + ((size_t)ni * H + min(max(yy, 0), H - 1)) * W + min(max(xx, 0), W - 1));
+        gy[i][j] = ok ? t : 0.f;
+      }
+    __nv_bfloat16* blk = dx + (((size_t)ni * g.h + by) * g.w + bx) * 16 * (size_t)g.c + cl * 8;
+#pragma unroll
+    for (int ox = 0; ox < 4; ++ox) {
+      float d[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) d[q] = 0.f;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          // dx(P) = sum_tap dy(P - off(tap)) w[tap]: P - off = (Y + 1 - ky, X + 1 - kx)
+          const float gn = gy[2 - ky][ox + 2 - kx];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) d[q] = fmaf(gn, wr[ky * 3 + kx][q], d[q]);
+        }
+      uint4 o;
+      o.x = pack_bf16x2(d[0], d[1]); o.y = pack_bf16x2(d[2], d[3]);
+      o.z = pack_bf16x2(d[4], d[5]); o.w = pack_bf16x2(d[6], d[7]);
+      // slot of phase (pg, ox) in the Z-order layout: ((py>>1)<<3) | ((px>>1)<<2) | ((py&1)<<1) | (px&1)
+      const int slot = ((pg >> 1) << 3) | ((ox >> 1) << 2) | ((pg & 1) << 1) | (ox & 1);
+      *reinterpret_cast<uint4*>(blk + (size_t)slot * g.c) = o;
+    }
+  }
+}
+
 bool last2_supported(int r, int c, int cout) { return cout == 1 && (c == 32 || c == 64 || c == 128) && r >= 2 && r <= 8; }
 
 int fill_geom2(LastGeom2* g, int n, int h, int w, int r, int c, const int32_t* phase_yx_host) {
@@ -1151,7 +1227,7 @@ extern "C" int vsr_conv3x3_last_bwd(const void* x, int32_t dtype, int32_t n, int
     if (dtype == VSR_BF16) {
       using B = __nv_bfloat16;
       if (c == 64 && geom_is_zr4(g2)) {
-        conv_last2_dx_kernel<B, 2, true><<<grid_dx, 256, smem_w, s2>>>(g2, w, dy, (B*)dx);
+        conv_last3_dx_kernel<<<grid_dx, 256, 0, s2>>>(g2, w, dy, (B*)dx);
         conv_last3_dw_kernel<true><<<blocks2, kLastBwdThreads, smem_p, s2>>>((const B*)x, g2, dy, ws2);
       } else if (c % 64 == 0 && geom_is_zr4(g2)) {
         conv_last2_dx_kernel<B, 2, true><<<grid_dx, 256, smem_w, s2>>>(g2, w, dy, (B*)dx);
