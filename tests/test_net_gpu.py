@@ -136,3 +136,28 @@ def test_config2_full_size_bf16_against_strict_fp32_mode():
         assert torch.equal(grads[1][k], grads[2][k]), k
     for a, b in zip(outs_all[1], outs_all[2]):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("r,hw", [(2, (24, 20)), (3, (16, 12)), (8, (12, 16))])
+def test_bf16_matches_strict_fp32_mode_other_upscale_factors(r, hw):
+    """every supported upscale factor through the tcgen05 path (6x6 s2, 7x7 s3, 12x12 s8 projection tables:
+    different column / shared-load structures) against this library's strict fp32 mode."""
+    torch.manual_seed(r)
+    kw = dict(in_channels=1, out_channels=1, num_features=64, num_groups=2, upscale_factor=r)
+    ref = DRFNet(precision="fp32", **kw).to("cuda")
+    net = DRFNet(precision="bf16", **kw)
+    net.load_state_dict(ref.state_dict())
+    net = net.to("cuda")
+    g = torch.Generator().manual_seed(10 + r)
+    x = [torch.randn(3, 1, *hw, generator=g).cuda() for _ in range(3)]
+    y = [torch.randn(3, 1, hw[0] * r, hw[1] * r, generator=g).cuda() for _ in range(3)]
+    res = []
+    for m in (ref, net):
+        outs = m(x)
+        torch.stack([torch.nn.L1Loss()(o, t) for o, t in zip(outs, y)]).mean().backward()
+        res.append(([o.detach() for o in outs], {k: p.grad.clone() for k, p in m.named_parameters()}))
+    for a, b in zip(res[1][0], res[0][0]):
+        assert (a - b).abs().max() <= 5e-2 * b.abs().max()
+    num = sum(float(((res[1][1][k] - gr) ** 2).sum()) for k, gr in res[0][1].items()) ** 0.5
+    den = sum(float((gr ** 2).sum()) for gr in res[0][1].values()) ** 0.5
+    assert num / den <= 5e-2, num / den
