@@ -75,6 +75,7 @@ struct Tc2Args {
   int resident;            // 1: the current group's weight slabs stay in smem across tiles
   int res_bytes;           // size of the resident weight region
   int epi_bytes;           // size of the epilogue tile region
+  uint32_t mg_groups, mg_mtiles, mg_tx, mg_ty;   // ceil(2^32 / d) of n_groups, m_tiles, tiles_x, tiles_y (0: d == 1)
   int m_tiles;             // pixel tiles per group
   int debug;               // timing-attribution switches (VSR_TC_DEBUG); results are wrong when non-zero
   int tall;                // 1: shared-load mode (columns from `cols`, one group)
@@ -101,20 +102,34 @@ struct TileCoord {
 
 // non-resident: groups vary fastest (concurrent CTAs share A tiles in L2);
 // resident: group-major, every CTA walks a contiguous tile range (the group rarely changes).
+// n / d and n % d through a host-made reciprocal (magic = ceil(2^32 / d), 0 for d == 1): every role decodes
+// every tile, and five emulated 32-bit divisions per tile were a third of the MMA warp's per-tile time on
+// the HBM-bound 1x1 convolutions (profiles/README.md)
+__device__ __forceinline__ void fast_divmod(int n, int d, uint32_t magic, int* q, int* r) {
+  if (magic == 0u) {
+    *q = n;
+    *r = 0;
+    return;
+  }
+  int qq = (int)__umulhi((uint32_t)n, magic);      // floor(n / d) or one more
+  int rr = n - qq * d;
+  if (rr < 0) {
+    --qq;
+    rr += d;
+  }
+  *q = qq;
+  *r = rr;
+}
 __device__ __forceinline__ TileCoord decode_tile(const Tc2Args& a, int tile) {
   TileCoord t;
-  int mt;
+  int mt, tx, ty;
   if (a.resident) {
-    t.g = tile / a.m_tiles;
-    mt = tile - t.g * a.m_tiles;
+    fast_divmod(tile, a.m_tiles, a.mg_mtiles, &t.g, &mt);
   } else {
-    t.g = tile % a.n_groups;
-    mt = tile / a.n_groups;
+    fast_divmod(tile, a.n_groups, a.mg_groups, &mt, &t.g);
   }
-  const int tx = mt % a.tiles_x;
-  mt /= a.tiles_x;
-  const int ty = mt % a.tiles_y;
-  t.n = mt / a.tiles_y;
+  fast_divmod(mt, a.tiles_x, a.mg_tx, &mt, &tx);
+  fast_divmod(mt, a.tiles_y, a.mg_ty, &t.n, &ty);
   t.x0 = tx * a.bw;
   t.y0 = ty * a.bh * a.mb;
   return t;
@@ -833,6 +848,14 @@ int tapgemm_tc2_launch(const VsrTapGemmDesc* d, cudaStream_t stream) {
     a.tiles_y = (a.H + bh - 1) / bh;
     a.num_tiles = (int)((long)a.n_groups * a.N * a.tiles_x * a.tiles_y);
     a.m_tiles = a.N * a.tiles_x * a.tiles_y;
+  }
+  {
+    auto magic = [](int d) -> uint32_t { return d <= 1 ? 0u : (uint32_t)(((1ull << 32) + (uint64_t)d - 1) / (uint64_t)d); };
+    // exact for every n < 2^32: ceil(2^32/d) overestimates 2^32/d by < 1, so the quotient by < n / 2^32 < 1
+    a.mg_groups = magic(a.n_groups);
+    a.mg_mtiles = magic(a.m_tiles);
+    a.mg_tx = magic(a.tiles_x);
+    a.mg_ty = magic(a.tiles_y);
   }
   a.res_bytes = a.resident ? (int)res_need : 0;
   a.stage_bytes = a.resident ? a.a_bytes : a.a_bytes + ndy_max * b_bytes;
