@@ -66,8 +66,7 @@ def main():
     print(f"graph of 100 tiny torch kernels: {a.elapsed_time(b) * 10:.2f} us per launch", flush=True)
 
 
-if __name__ == "__main__" and len(sys.argv) == 1:
-    main()
+
 
 
 def alternating():
@@ -109,5 +108,8 @@ def alternating():
         print(f"{name}: {a.elapsed_time(b) * 10:.2f} us per round of {len(fns)} launches", flush=True)
 
 
-if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "alt":
-    alternating()
+if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "alt":
+        alternating()
+    else:
+        main()
