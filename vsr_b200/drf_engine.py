@@ -106,16 +106,30 @@ class DrfEngine:
                 b = bufs[key] = self._new(T, *shape)
             return b[t]
 
+        flat_tn = lambda b: b.view(b.shape[0] * b.shape[1], *b.shape[2:])
+        batch_out = stacked and P.variant == "drf"
+        if stacked:
+            # the input block does not see the recurrence: one launch per layer for all T frames
+            N, _, h, w = frames[0].shape
+            x_all = bufs["x_all"] = torch.stack(frames)
+            a1_all = bufs["a1"] = self._new(T, N, h, w, 4 * F)
+            ops.conv3x3_first(flat_tn(x_all), self._pview(self.flat, f"{P.in_name}.conv1.weight"),
+                              self._pview(self.flat, f"{P.in_name}.conv1.bias"),
+                              self._slope(P.params[f"{P.in_name}.prelu1.weight"]), flat_tn(a1_all))
+            inn_all = bufs["inn"] = self._new(T, N, h, w, F)
+            self._fwd("in2", [flat_tn(a1_all)], flat_tn(inn_all))
         for t, x in enumerate(frames):
             N, _, h, w = x.shape
             S = _Frame()
             S.x = x
             S.a1 = alloc("a1", t, N, h, w, 4 * F)
-            ops.conv3x3_first(x, self._pview(self.flat, f"{P.in_name}.conv1.weight"),
-                              self._pview(self.flat, f"{P.in_name}.conv1.bias"),
-                              self._slope(P.params[f"{P.in_name}.prelu1.weight"]), S.a1)
+            if not stacked:
+                ops.conv3x3_first(x, self._pview(self.flat, f"{P.in_name}.conv1.weight"),
+                                  self._pview(self.flat, f"{P.in_name}.conv1.bias"),
+                                  self._slope(P.params[f"{P.in_name}.prelu1.weight"]), S.a1)
             S.inn = alloc("inn", t, N, h, w, F)
-            self._fwd("in2", [S.a1], S.inn)
+            if not stacked:
+                self._fwd("in2", [S.a1], S.inn)
             S.hidden = S.inn if t == 0 else prev_f                      # drf_net.py:42-43
             S.lr, S.hr, S.u, S.d = [alloc("lr0", t, N, h, w, F)], [], [None], [None]
             self._fwd("fin", [S.inn, S.hidden], S.lr[0])
@@ -156,20 +170,37 @@ class DrfEngine:
                 S.f, S.feat = alloc("f", t, N, h, w, F), alloc("s0", t, N, h, w, F)
                 self._fwd("fout", S.lr[1:], S.f, extra=EPI_OUT2, out2=S.feat, res2=S.inn)   # :46 global skip
                 S.s = [S.feat]
-                for lv in range(P.out_levels):
-                    L = P.fwd[f"out{lv + 1}"]
-                    nxt = alloc(f"s{lv + 1}", t, N, h, w, L.out_c)
-                    self._fwd(L.name, [S.s[-1]], nxt)
-                    S.s.append(nxt)
-                y = self._new(N, P.cout, h * r, w * r, dtype=self.param_dtype)
-                ops.conv3x3_last(S.s[-1], r, F, P.phases, self._pview(self.flat, P.last_name + ".weight"),
-                                 self._pview(self.flat, P.last_name + ".bias"), y)
+                y = None
+                if not batch_out:
+                    for lv in range(P.out_levels):
+                        L = P.fwd[f"out{lv + 1}"]
+                        nxt = alloc(f"s{lv + 1}", t, N, h, w, L.out_c)
+                        self._fwd(L.name, [S.s[-1]], nxt)
+                        S.s.append(nxt)
+                    y = self._new(N, P.cout, h * r, w * r, dtype=self.param_dtype)
+                    ops.conv3x3_last(S.s[-1], r, F, P.phases, self._pview(self.flat, P.last_name + ".weight"),
+                                     self._pview(self.flat, P.last_name + ".bias"), y)
             outs.append(y)
             prev_f = S.f
             if save:
                 saved.append(S)
             else:
                 S = None
+        if batch_out:
+            # neither does the output block (drf_net.py:136-147 acts on feat_t only): all T frames per launch
+            N, _, h, w = frames[0].shape
+            prev = bufs["s0"]
+            for lv in range(P.out_levels):
+                L = P.fwd[f"out{lv + 1}"]
+                nxt = bufs[f"s{lv + 1}"] = self._new(T, N, h, w, L.out_c)
+                self._fwd(L.name, [flat_tn(prev)], flat_tn(nxt))
+                for t in range(T):
+                    saved[t].s.append(nxt[t])
+                prev = nxt
+            y_all = self._new(T * N, P.cout, h * r, w * r, dtype=self.param_dtype)
+            ops.conv3x3_last(flat_tn(prev), r, F, P.phases, self._pview(self.flat, P.last_name + ".weight"),
+                             self._pview(self.flat, P.last_name + ".bias"), y_all)
+            outs = [y_all[t * N:(t + 1) * N] for t in range(T)]
         if stacked:
             # hidden state seen by frame t (drf_net.py:42-43) as one stacked tensor: [inn_0, f_0, ..., f_{T-2}]
             hid = self._new(T, *bufs["f"].shape[1:])
@@ -251,28 +282,60 @@ class DrfEngine:
         def act_bwd(dy, y, dz, slope_ref):
             ops.act_bwd(dy, y, dz, slope=self._slope(slope_ref), slope_partials=prow(slope_ref))
 
+        flat_tn = lambda b: b.view(b.shape[0] * b.shape[1], *b.shape[2:])
+        batch_io = stacked and "x_all" in bufs
+        batch_out = batch_io and P.variant == "drf"
+        if batch_out:
+            # output block of all T frames at once (it does not see the recurrence): last conv, then the
+            # data gradients of the out-level convolutions; their weight gradients are deferred like the rest
+            S0 = saved[0]
+            N, _, h, w = S0.x.shape
+            n_lv = len(S0.s) - 1
+            zero = None
+            douts = []
+            for d in d_outs:
+                if d is None:
+                    if zero is None:
+                        zero = torch.zeros(N, P.cout, h * r, w * r, dtype=pd, device=dev)
+                    d = zero
+                douts.append(d)
+            d_all = torch.stack(douts).view(T * N, P.cout, h * r, w * r)
+            d_s = dzb[f"ds{n_lv}"] = self._new(T, N, h, w, S0.s[-1].shape[-1])
+            ws = self._workspace("last", ops.conv3x3_last_bwd_workspace(flat_tn(bufs[f"s{n_lv}"]), r, F, P.cout))
+            ops.conv3x3_last_bwd(flat_tn(bufs[f"s{n_lv}"]), r, F, P.phases, self._pview(self.flat, P.last_name + ".weight"),
+                                 d_all, flat_tn(d_s), self._pview(gflat, P.last_name + ".weight"),
+                                 self._pview(gflat, P.last_name + ".bias"), True, ws)
+            for lv in reversed(range(P.out_levels)):
+                lname = f"out{lv + 1}"
+                deferred[lname] = ([f"s{lv}"], f"ds{lv + 1}", None)
+                d_prev = dzb[f"ds{lv}"] = self._new(T, N, h, w, S0.s[lv].shape[-1])
+                dgrad(lname, [flat_tn(d_s)], flat_tn(d_prev))
+                d_s = d_prev
         next_dz_lr0 = None
         for t in reversed(range(T)):
             S = saved[t]
             N, _, h, w = S.x.shape
             hv = lambda z: z.view(N, h, w * r2, F)
             new = lambda c=F: self._new(N, h, w, c)
-            d_out = d_outs[t]
-            if d_out is None:
-                d_out = torch.zeros(N, P.cout, h * r, w * r, dtype=pd, device=dev)
-            # ---- output block ----
-            n_lv = len(S.s) - 1
-            d_s = dz_alloc(f"ds{n_lv}", t, N, h, w, S.s[-1].shape[-1])
-            ws = self._workspace("last", ops.conv3x3_last_bwd_workspace(S.s[-1], r, F, P.cout))
-            ops.conv3x3_last_bwd(S.s[-1], r, F, P.phases, self._pview(self.flat, P.last_name + ".weight"),
-                                 d_out.contiguous(), d_s, self._pview(gflat, P.last_name + ".weight"),
-                                 self._pview(gflat, P.last_name + ".bias"), True, ws)
-            for lv in reversed(range(P.out_levels)):
-                lname = f"out{lv + 1}"
-                wgrad(lname, [S.s[lv]], d_s, [f"s{lv}"], f"ds{lv + 1}")
-                d_prev = dz_alloc(f"ds{lv}", t, N, h, w, S.s[lv].shape[-1])
-                dgrad(lname, [d_s], d_prev)
-                d_s = d_prev
+            if batch_out:
+                d_s = dzb["ds0"][t]
+            else:
+                d_out = d_outs[t]
+                if d_out is None:
+                    d_out = torch.zeros(N, P.cout, h * r, w * r, dtype=pd, device=dev)
+                # ---- output block ----
+                n_lv = len(S.s) - 1
+                d_s = dz_alloc(f"ds{n_lv}", t, N, h, w, S.s[-1].shape[-1])
+                ws = self._workspace("last", ops.conv3x3_last_bwd_workspace(S.s[-1], r, F, P.cout))
+                ops.conv3x3_last_bwd(S.s[-1], r, F, P.phases, self._pview(self.flat, P.last_name + ".weight"),
+                                     d_out.contiguous(), d_s, self._pview(gflat, P.last_name + ".weight"),
+                                     self._pview(gflat, P.last_name + ".bias"), True, ws)
+                for lv in reversed(range(P.out_levels)):
+                    lname = f"out{lv + 1}"
+                    wgrad(lname, [S.s[lv]], d_s, [f"s{lv}"], f"ds{lv + 1}")
+                    d_prev = dz_alloc(f"ds{lv}", t, N, h, w, S.s[lv].shape[-1])
+                    dgrad(lname, [d_s], d_prev)
+                    d_s = d_prev
             if P.variant == "srfb":
                 dz_r = dz_alloc("dz_r", t, N, h, w, r2 * F)
                 act_bwd(d_s, S.s[0], dz_r, P.fwd["rdc"].slope)       # r_block.prelu1
@@ -340,12 +403,22 @@ class DrfEngine:
                 dgrad("fin_in", [dz_lr0], dz_in, aux=S.inn, slope_ref=in2.slope, residual=skip)
             # ---- input block ----
             wgrad("in2", [S.a1], dz_in, ["a1"], "dz_in")
-            dz_a1 = new(4 * F)
-            dgrad("in2", [dz_in], dz_a1, aux=S.a1, slope_ref=P.params[f"{P.in_name}.prelu1.weight"])
-            ws = self._workspace("first", ops.conv3x3_first_bwd_workspace(S.x, 4 * F))
-            ops.conv3x3_first_bwd(S.x, dz_a1, self._pview(gflat, f"{P.in_name}.conv1.weight"),
-                                  self._pview(gflat, f"{P.in_name}.conv1.bias"), True, ws)
+            if not batch_io:
+                dz_a1 = new(4 * F)
+                dgrad("in2", [dz_in], dz_a1, aux=S.a1, slope_ref=P.params[f"{P.in_name}.prelu1.weight"])
+                ws = self._workspace("first", ops.conv3x3_first_bwd_workspace(S.x, 4 * F))
+                ops.conv3x3_first_bwd(S.x, dz_a1, self._pview(gflat, f"{P.in_name}.conv1.weight"),
+                                      self._pview(gflat, f"{P.in_name}.conv1.bias"), True, ws)
             next_dz_lr0 = dz_lr0
+        if batch_io:
+            # input block of all T frames at once: data gradient of conv2 (+ PReLU'), then the first conv
+            x_all = flat_tn(bufs["x_all"])
+            dz_a1 = self._new(*flat_tn(bufs["a1"]).shape)
+            dgrad("in2", [flat_tn(dzb["dz_in"])], dz_a1, aux=flat_tn(bufs["a1"]),
+                  slope_ref=P.params[f"{P.in_name}.prelu1.weight"])
+            ws = self._workspace("first", ops.conv3x3_first_bwd_workspace(x_all, 4 * F))
+            ops.conv3x3_first_bwd(x_all, dz_a1, self._pview(gflat, f"{P.in_name}.conv1.weight"),
+                                  self._pview(gflat, f"{P.in_name}.conv1.bias"), True, ws)
         for lname, (src_keys, dz_key, view) in deferred.items():
             # weight (+ bias) gradient of the layer over all T frames in one launch: [T, N, ...] -> [T*N, ...]
             L = P.fwd[lname]
