@@ -95,11 +95,13 @@ class DrfEngine:
         T = len(frames)
         # Saved activations of a layer live in ONE [T, N, h, w, c] buffer (frame t = slice t), so that the
         # weight gradient of the layer is a single launch over all T frames (backward()).
-        stacked = save and T > 1 and all(f.shape == frames[0].shape for f in frames)
+        uniform = T > 1 and all(f.shape == frames[0].shape for f in frames)
+        stacked = save and uniform
+        batch_io = uniform          # input / output blocks over all frames at once, also without saving (inference)
         bufs = {}
 
         def alloc(key, t, *shape):
-            if not stacked:
+            if not (stacked or (batch_io and key in ("a1", "inn", "s0"))):
                 return self._new(*shape)
             b = bufs.get(key)
             if b is None:
@@ -107,8 +109,8 @@ class DrfEngine:
             return b[t]
 
         flat_tn = lambda b: b.view(b.shape[0] * b.shape[1], *b.shape[2:])
-        batch_out = stacked and P.variant == "drf"
-        if stacked:
+        batch_out = batch_io and P.variant == "drf"
+        if batch_io:
             # the input block does not see the recurrence: one launch per layer for all T frames
             N, _, h, w = frames[0].shape
             x_all = bufs["x_all"] = torch.stack(frames)
@@ -123,12 +125,12 @@ class DrfEngine:
             S = _Frame()
             S.x = x
             S.a1 = alloc("a1", t, N, h, w, 4 * F)
-            if not stacked:
+            if not batch_io:
                 ops.conv3x3_first(x, self._pview(self.flat, f"{P.in_name}.conv1.weight"),
                                   self._pview(self.flat, f"{P.in_name}.conv1.bias"),
                                   self._slope(P.params[f"{P.in_name}.prelu1.weight"]), S.a1)
             S.inn = alloc("inn", t, N, h, w, F)
-            if not stacked:
+            if not batch_io:
                 self._fwd("in2", [S.a1], S.inn)
             S.hidden = S.inn if t == 0 else prev_f                      # drf_net.py:42-43
             S.lr, S.hr, S.u, S.d = [alloc("lr0", t, N, h, w, F)], [], [None], [None]
@@ -194,8 +196,8 @@ class DrfEngine:
                 L = P.fwd[f"out{lv + 1}"]
                 nxt = bufs[f"s{lv + 1}"] = self._new(T, N, h, w, L.out_c)
                 self._fwd(L.name, [flat_tn(prev)], flat_tn(nxt))
-                for t in range(T):
-                    saved[t].s.append(nxt[t])
+                for t, S in enumerate(saved):          # (empty when nothing is saved: inference)
+                    S.s.append(nxt[t])
                 prev = nxt
             y_all = self._new(T * N, P.cout, h * r, w * r, dtype=self.param_dtype)
             ops.conv3x3_last(flat_tn(prev), r, F, P.phases, self._pview(self.flat, P.last_name + ".weight"),
