@@ -20,8 +20,9 @@ import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-    os.environ["NCCL_DEBUG"] = "WARN"      # no version banner on stdout: rank 0 prints exactly one JSON line
+# NCCL writes its version banner / debug lines to stdout by default: send them to stderr so that rank 0's
+# stdout is exactly one JSON line whatever NCCL_DEBUG the box sets
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 MODEL = dict(in_channels=1, out_channels=1, num_features=64, num_groups=6, upscale_factor=4)
 BATCH, T, LR = 32, 5, 32
