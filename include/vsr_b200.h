@@ -275,6 +275,66 @@ int vsr_adam_flat_dev(float* p, const float* g, float* m, float* v, int64_t n, c
 int vsr_cast(const void* src, int32_t src_dtype, void* dst, int32_t dst_dtype, int64_t n,
              void* stream);
 
+/*
+ * ---- Conv3d network (DUFNet, duf_net.py:21-214): bandwidth-bound parts -----------------------------------
+ * The dense concatenation (duf_net.py:123-128) is ONE pixel-major map [frames*n*h*w][ld] (time-major: all
+ * pixels of frame 0, then frame 1, ...), so torch.cat is never executed: each layer reads the channel
+ * prefix [0, c) and its 3x3x3 convolution (a tap-GEMM whose sources are frame-shifted views of one map)
+ * appends a channel slice.  All windows below are [c0, c0+c) of rows with stride ld (elements); c0, c and
+ * ld must be multiples of 16 bytes.
+ */
+
+/* dst[row][c0_dst + j] = src[row][c0_src + j], j < c  (torch.stack of the per-frame head features,
+ * duf_net.py:57-61, into the concat map; and back for the head's weight gradient) */
+int vsr_copy_window(const void* src, int32_t ld_src, int32_t c0_src, void* dst, int32_t ld_dst,
+                    int32_t c0_dst, int32_t c, int64_t rows, int32_t dtype, void* stream);
+
+/* nn.BatchNorm3d batch statistics (duf_net.py:114,198,201,207,210), kept PER FRAME so that the temporal
+ * crop concat[:, :, 1:-1] (duf_net.py:126) re-uses them:
+ *   stats[f][0][s0 + j] = sum over the rows of frame f of x[row][c0 + j],  stats[f][1][s0 + j] = sum of squares
+ * (fp64, [frames][2][ld_stats]).  workspace >= vsr_bn_stats_workspace(frames, rows_per_frame, c). */
+size_t vsr_bn_stats_workspace(int32_t frames, int64_t rows_per_frame, int32_t c);
+int vsr_bn_stats(const void* x, int32_t dtype, int32_t ldx, int32_t c0, int32_t c, int32_t frames,
+                 int64_t rows_per_frame, double* stats, int32_t ld_stats, int32_t s0, void* workspace,
+                 size_t workspace_bytes, void* stream);
+
+/* One BatchNorm's affine map from the statistics of `frames` frames (training != 0: biased batch variance,
+ * running_mean / running_var updated with `momentum` and the unbiased variance when non-NULL) or from the
+ * running buffers (training == 0):  scale_shift = float[2][cp] {gamma*rstd, beta - mean*gamma*rstd}, zero
+ * for the padding channels [c, cp);  mean_rstd = float[2][c] (kept for the backward pass). */
+int vsr_bn_finalize(const double* stats, int32_t ld_stats, int32_t s0, int32_t frames, int64_t rows_per_frame,
+                    int32_t c, int32_t cp, const float* gamma, const float* beta, float eps, float momentum,
+                    float* running_mean, float* running_var, int32_t training, float* scale_shift,
+                    float* mean_rstd, void* stream);
+
+/* y[row][j] = max(0, x[row][c0 + j] * scale[j] + shift[j]) for j < c, 0 for c <= j < cp; y is dense
+ * [rows][cp]  (BatchNorm3d + ReLU in front of every Conv3d, duf_net.py:198-203,207-212,114-115). */
+int vsr_bn_relu(const void* x, int32_t dtype, int32_t ldx, int32_t c0, int32_t c, int64_t rows,
+                const float* scale_shift, int32_t cp, void* y, void* stream);
+
+/* Backward of the same (training mode): with g = dy where the forward output was positive, else 0, and
+ * xhat = (x - mean) * rstd:  dgamma_dbeta = float[2][c] {sum g*xhat, sum g} (written),
+ *   dx[row][c0_dx + j] (+)= gamma*rstd * (g - mean(g) - xhat * mean(g*xhat)),  zero for c <= j < cp_dx when
+ * not accumulating.  dy is [rows][ld_dy] (channels [0, c)).  Two passes, fixed summation order. */
+size_t vsr_bn_relu_bwd_workspace(int64_t rows, int32_t c);
+int vsr_bn_relu_bwd(const void* dy, int32_t ld_dy, const void* x, int32_t dtype, int32_t ldx, int32_t c0,
+                    int32_t c, int64_t rows, const float* scale_shift, int32_t cp, const float* mean_rstd,
+                    float* dgamma_dbeta, void* dx, int32_t ld_dx, int32_t c0_dx, int32_t cp_dx, int accumulate,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* Dynamic-upsampling-filter tail (duf_net.py:66-97): logits [n*h*w][ld_logits] with channel k*r*r + p
+ * (k = tap of the size_filter^2 window, p = sub-pixel), softmax over k, applied to the neighbourhood of the
+ * centre frame x (NCHW fp32 [n,cin,h,w], zero padded), + res[pix][c*r*r + p], pixel-shuffled into
+ * y (NCHW fp32 [n,cin,r*h,r*w]). */
+int vsr_duf_filter(const void* logits, int32_t ld_logits, const void* res, int32_t ld_res, int32_t dtype,
+                   const float* x, int32_t n, int32_t cin, int32_t h, int32_t w, int32_t size_filter, int32_t r,
+                   float* y, void* stream);
+/* its backward w.r.t. logits and res (x is data): dlogits [pix][ld_logits], dres [pix][ld_res], padding
+ * channels zeroed. */
+int vsr_duf_filter_bwd(const void* logits, int32_t ld_logits, int32_t dtype, const float* x, const float* dy,
+                       int32_t n, int32_t cin, int32_t h, int32_t w, int32_t size_filter, int32_t r, void* dlogits,
+                       void* dres, int32_t ld_res, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -214,3 +214,44 @@ def edsrnet_forward(x, sd, upscale, res_scale=0.1):
         y = F.pixel_shuffle(_conv(y, sd, f"tail.0.conv{i}", padding=1), 3 if upscale == 3 else 2)   # :60-65
         i += 1
     return _conv(y, sd, "tail.conv", padding=1)                                     # :32,37
+
+
+# ---- DUFNet (duf_net.py:9-214) ------------------------------------------------------------------------------
+def _bn3d(x, sd, key, training, eps=1e-5):
+    # nn.BatchNorm3d — duf_net.py:114,198,201,207,210: batch statistics (biased variance) when training
+    if training:
+        return F.batch_norm(x, None, None, sd[key + ".weight"], sd[key + ".bias"], True, 0.0, eps)
+    return F.batch_norm(x, sd[key + ".running_mean"], sd[key + ".running_var"], sd[key + ".weight"], sd[key + ".bias"],
+                        False, 0.0, eps)
+
+
+def dufnet_forward(inputs, sd, size_filter, upscale, training=True):
+    """DUFNet.forward — duf_net.py:51-99 (any backbone: the layer count is read from the state_dict)."""
+    T = len(inputs)
+    t = T // 2 if T % 2 == 1 else T // 2 - 1                                                   # :53
+    target = inputs[t].unsqueeze(2)
+    feats = torch.stack([F.conv2d(f, sd["head.weight"], sd["head.bias"], padding=1) for f in inputs], dim=2)   # :57-61
+    concat, i = feats, 0
+    while f"denseLayer.conv{i}.conv2.weight" in sd:                                            # _DenseLayer*.forward :119-130
+        p = f"denseLayer.conv{i}"
+        x = F.relu(_bn3d(concat, sd, p + ".bn1", training))
+        x = F.conv3d(x, sd[p + ".conv1.weight"], sd[p + ".conv1.bias"])
+        x = F.relu(_bn3d(x, sd, p + ".bn2", training))
+        valid_t = f"denseLayer.conv{i + 3}.conv2.weight" not in sd                             # the last three: _denseBlock2
+        x = F.conv3d(x, sd[p + ".conv2.weight"], sd[p + ".conv2.bias"], padding=(0, 1, 1) if valid_t else 1)
+        concat = torch.cat((concat[:, :, 1:-1] if valid_t else concat, x), dim=1)              # :125-128
+        i += 1
+    x = F.relu(_bn3d(concat, sd, "denseLayer.tail.bn", training))
+    feats = F.conv3d(x, sd["denseLayer.tail.conv.weight"], sd["denseLayer.tail.conv.bias"], padding=(0, 1, 1))
+    head2 = lambda p: F.conv3d(F.relu(F.conv3d(F.relu(feats), sd[p + ".conv1.weight"], sd[p + ".conv1.bias"])),
+                               sd[p + ".conv2.weight"], sd[p + ".conv2.bias"])                 # :37-48
+    k2, rr = size_filter ** 2, upscale ** 2
+    filters = head2("filterNet")
+    filters = torch.softmax(filters.reshape(filters.shape[0], k2, rr, *filters.shape[2:]), dim=1)[:, :, :, 0]   # :66-72
+    n, c, _, h, w = target.shape
+    nb = F.unfold(target[:, :, 0].reshape(n * c, 1, h, w), size_filter, padding=size_filter // 2)   # :79-82 (identity conv)
+    nb = nb.reshape(n, c, k2, h, w)
+    out = torch.einsum("nckhw,nkphw->ncphw", nb, filters).reshape(n, c * rr, h, w)             # :84-88
+    out = F.pixel_shuffle(out, upscale)                                                        # :89
+    residual = F.pixel_shuffle(head2("residualNet").squeeze(2), upscale)                       # :93-96
+    return out + residual

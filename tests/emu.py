@@ -257,6 +257,99 @@ class EmuOps:
     def zero_(self, t):
         t.zero_()
 
+    # ---- Conv3d network: BatchNorm3d + ReLU on channel windows, dynamic filter tail ---------
+    def copy_window(self, src, c0_src, dst, c0_dst, c):
+        dst[..., c0_dst:c0_dst + c] = src[..., c0_src:c0_src + c]
+        self.launches += 1
+
+    def bn_stats_workspace(self, frames, rows_per_frame, c):
+        return 16
+
+    def bn_stats(self, x, c0, c, frames, stats, s0, workspace):
+        v = x[..., c0:c0 + c].reshape(frames, -1, c).double()
+        stats[:, 0, s0:s0 + c] = v.sum(1)
+        stats[:, 1, s0:s0 + c] = (v * v).sum(1)
+        self.launches += 2
+
+    def bn_finalize(self, stats, s0, frames, rows_per_frame, c, gamma, beta, eps, momentum, running_mean,
+                    running_var, training, scale_shift, mean_rstd):
+        if training:
+            count = float(frames * rows_per_frame)
+            s = stats[:frames, 0, s0:s0 + c].sum(0)
+            q = stats[:frames, 1, s0:s0 + c].sum(0)
+            mean = s / count
+            var = (q / count - mean * mean).clamp_min(0)
+            if running_mean is not None:
+                unb = var * count / (count - 1) if count > 1 else var
+                running_mean.copy_(((1 - momentum) * running_mean.double() + momentum * mean).to(running_mean.dtype))
+                running_var.copy_(((1 - momentum) * running_var.double() + momentum * unb).to(running_var.dtype))
+        else:
+            mean, var = running_mean.double(), running_var.double()
+        rstd = 1.0 / torch.sqrt(var + eps)
+        sc = gamma.double() * rstd
+        scale_shift.zero_()
+        scale_shift[0, :c] = sc.to(scale_shift.dtype)
+        scale_shift[1, :c] = (beta.double() - mean * sc).to(scale_shift.dtype)
+        mean_rstd[0] = mean.to(mean_rstd.dtype)
+        mean_rstd[1] = rstd.to(mean_rstd.dtype)
+        self.launches += 1
+
+    def bn_relu(self, x, c0, c, scale_shift, y):
+        ct = torch.float64 if x.dtype == torch.float64 else torch.float32
+        v = x[..., c0:c0 + c].to(ct) * scale_shift[0, :c].to(ct) + scale_shift[1, :c].to(ct)
+        y.zero_()
+        y[..., :c] = v.clamp_min(0).to(y.dtype)
+        self.launches += 1
+
+    def bn_relu_bwd_workspace(self, rows, c):
+        return 16
+
+    def bn_relu_bwd(self, dy, x, c0, c, scale_shift, mean_rstd, dgamma_dbeta, dx, c0_dx, cp_dx, accumulate, workspace):
+        ct = torch.float64 if x.dtype == torch.float64 else torch.float32
+        xv = x[..., c0:c0 + c].to(ct)
+        sc, sh = scale_shift[0, :c].to(ct), scale_shift[1, :c].to(ct)
+        mu, rs = mean_rstd[0].to(ct), mean_rstd[1].to(ct)
+        g = torch.where(xv * sc + sh > 0, dy[..., :c].to(ct), torch.zeros((), dtype=ct, device=x.device))
+        xhat = (xv - mu) * rs
+        red = tuple(range(xv.dim() - 1))
+        sx, sg = (g * xhat).sum(red), g.sum(red)
+        dgamma_dbeta.view(2, c)[0] = sx.to(dgamma_dbeta.dtype)
+        dgamma_dbeta.view(2, c)[1] = sg.to(dgamma_dbeta.dtype)
+        n = xv.numel() // c
+        d = sc * (g - sg / n - xhat * (sx / n))
+        if accumulate:
+            dx[..., c0_dx:c0_dx + c] += d.to(dx.dtype)
+        else:
+            dx[..., c0_dx:c0_dx + cp_dx] = 0
+            dx[..., c0_dx:c0_dx + c] = d.to(dx.dtype)
+        self.launches += 3
+
+    @staticmethod
+    def _duf_apply(logits, res, x, sf, r):
+        n, cin, h, w = x.shape
+        ct = x.dtype
+        rr, k2 = r * r, sf * sf
+        f = torch.softmax(logits[..., :k2 * rr].to(ct).reshape(n, h, w, k2, rr), dim=3)
+        nb = F.unfold(x.reshape(n * cin, 1, h, w), sf, padding=sf // 2).reshape(n, cin, k2, h, w)
+        out = torch.einsum("nckhw,nhwkp->ncphw", nb, f)
+        out = out + res[..., :cin * rr].to(ct).reshape(n, h, w, cin, rr).permute(0, 3, 4, 1, 2)
+        return F.pixel_shuffle(out.reshape(n, cin * rr, h, w), r)
+
+    def duf_filter(self, logits, res, x, size_filter, r, y):
+        y.copy_(self._duf_apply(logits, res, x, size_filter, r))
+        self.launches += 1
+
+    def duf_filter_bwd(self, logits, x, dy, size_filter, r, dlogits, dres):
+        ct = x.dtype
+        lg = logits.detach().to(ct).requires_grad_(True)
+        rs = torch.zeros(*dres.shape, dtype=ct, device=x.device, requires_grad=True)
+        with torch.enable_grad():
+            out = self._duf_apply(lg, rs, x, size_filter, r)
+        gl, gr = torch.autograd.grad(out, (lg, rs), dy.to(ct))
+        dlogits.copy_(gl.to(dlogits.dtype))
+        dres.copy_(gr.to(dres.dtype))
+        self.launches += 1
+
     # ---- loss / metrics ----------------------------------------------------------------
     def loss_fwd_bwd(self, out, target, kind, param, grad_scale, partials, grad):
         d = out - target

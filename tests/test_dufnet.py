@@ -1,0 +1,198 @@
+"""DUFNet, the Conv3d network (reference duf_net.py:9-214): oracle restatement vs goldens made
+by the real reference, host logic on CPU through the kernel emulation (fp32 tables and the padded bf16 tables),
+and GPU parity through the C-ABI (fp32 strict mode, bf16 tcgen05 mode, each new kernel against the emulation)."""
+import glob
+import os
+
+import pytest
+import torch
+
+from oracle import restated
+from oracle.make_golden_duf import duf_fill
+from tests.emu import EmuOps
+from vsr_b200.duf import DUFNet
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+CASES = sorted(glob.glob(os.path.join(GOLDEN, "dufnet*.pt")))
+ids = lambda ps: [os.path.basename(p)[:-3] for p in ps]
+# bf16 storage of every activation of this BatchNorm-heavy net with random weights: the REFERENCE itself under
+# torch.autocast(bfloat16) has a global relative L2 gradient error of 0.17 (L1 loss; 0.15 with MSE) and an output
+# error of 1.5e-2 against its own fp32 run on these inputs (measured in the build container); the tcgen05 mode
+# is held to the same scale: <= 0.25 global L2 against the fp32 mode, digests within 0.2 of the largest gradient.
+BF16_GRAD_TOL = 0.2
+
+
+def _state(fx):
+    return duf_fill({k: torch.zeros(s, dtype=fx["state_dtypes"][k]) for k, s in fx["state_shapes"].items()},
+                    fx["state_seed"])
+
+
+def _rel(a, b):
+    return float((a - b).abs().max() / b.abs().max())
+
+
+def _check(net, fx, dev, out_tol, grad_tol, buf_tol):
+    inputs = [f.to(dev) for f in fx["inputs"]]
+    net.eval()
+    with torch.no_grad():
+        assert _rel(net(inputs).cpu(), fx["output_eval"]) <= out_tol        # running statistics
+    net.train()
+    out = net(inputs)
+    assert out.shape == fx["output"].shape
+    assert _rel(out.detach().cpu(), fx["output"]) <= out_tol                # batch statistics
+    loss = torch.nn.L1Loss()(out, fx["target"].to(dev))
+    loss.backward()
+    # gradient digests, normalised by the largest gradient norm of the net (gradients of the convolution
+    # biases in front of a BatchNorm are exactly zero in exact arithmetic)
+    gmax = max(float(d["norm"]) for d in fx["grad_digest"].values())
+    hmax = max(float(d["head"].abs().max()) for d in fx["grad_digest"].values())
+    for k, p in net.named_parameters():
+        d = fx["grad_digest"][k]
+        g = p.grad.detach().cpu()
+        assert abs(float(g.norm()) - float(d["norm"])) <= grad_tol * gmax, k
+        assert float((g.reshape(-1)[:16] - d["head"]).abs().max()) <= grad_tol * hmax, k
+    sd = net.state_dict()
+    for k, v in fx["buffers_after"].items():                                 # momentum update, unbiased variance
+        assert float((sd[k].cpu() - v).abs().max()) <= buf_tol, k
+    assert int(sd["denseLayer.tail.bn.num_batches_tracked"]) == 1
+    return float(loss.detach())
+
+
+@pytest.mark.parametrize("path", CASES, ids=ids(CASES))
+def test_restated_matches_reference_golden(path):
+    fx = torch.load(path)
+    kw, sd = fx["kwargs"], _state(fx)
+    o = restated.dufnet_forward(fx["inputs"], sd, kw["size_filter"], kw["upscale_factor"], training=True)
+    assert _rel(o, fx["output"]) <= 1e-6
+    o = restated.dufnet_forward(fx["inputs"], sd, kw["size_filter"], kw["upscale_factor"], training=False)
+    assert _rel(o, fx["output_eval"]) <= 1e-6
+
+
+@pytest.mark.parametrize("path", CASES[:3], ids=ids(CASES[:3]))
+def test_host_logic_fp32_matches_reference_golden(path):
+    fx = torch.load(path)
+    net = DUFNet(**fx["kwargs"])
+    assert list(net.state_dict()) == list(fx["state_shapes"])
+    net.load_state_dict(_state(fx))
+    net._ops = EmuOps()
+    loss = _check(net, fx, "cpu", 2e-5, 1e-4, 1e-5)
+    assert abs(loss - float(fx["loss_l1"])) <= 1e-5 * float(fx["loss_l1"])
+
+
+def test_host_logic_bf16_tables():
+    """the padded (multiple-of-64) tables and 64-wide growth tiles of the tcgen05 mode, emulated with bf16 storage"""
+    fx = torch.load(CASES[1])
+    net = DUFNet(precision="bf16", **fx["kwargs"])
+    net.load_state_dict(_state(fx))
+    net._ops = EmuOps()
+    _check(net, fx, "cpu", 5e-2, BF16_GRAD_TOL, 5e-3)
+
+
+def test_constructor_contract():
+    with pytest.raises(AssertionError):
+        DUFNet(1, 1, 7, 5, 4, "_DenseLayer99")
+    with pytest.raises(ValueError):
+        DUFNet(1, 1, 5, 5, 4, "_DenseLayer16")
+    net = DUFNet(1, 1, 7, 5, 4, "_DenseLayer16")
+    with pytest.raises(RuntimeError):
+        net([torch.zeros(1, 1, 8, 8)] * 7)          # no CPU fallback
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", CASES, ids=ids(CASES))
+def test_gpu_fp32_matches_reference_golden(path):
+    fx = torch.load(path)
+    net = DUFNet(precision="fp32", **fx["kwargs"])
+    net.load_state_dict(_state(fx))
+    net = net.to("cuda")
+    loss = _check(net, fx, "cuda", 1e-4, 1e-4, 1e-5)
+    assert abs(loss - float(fx["loss_l1"])) <= 1e-5 * float(fx["loss_l1"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", CASES, ids=ids(CASES))
+def test_gpu_bf16_close_to_reference(path):
+    fx = torch.load(path)
+    net = DUFNet(precision="bf16", **fx["kwargs"])
+    net.load_state_dict(_state(fx))
+    net = net.to("cuda")
+    _check(net, fx, "cuda", 5e-2, BF16_GRAD_TOL, 5e-3)
+    g16 = net.flat_grad.clone()
+    ref = DUFNet(precision="fp32", **fx["kwargs"])
+    ref.load_state_dict(_state(fx))
+    ref = ref.to("cuda").train()
+    torch.nn.L1Loss()(ref([f.cuda() for f in fx["inputs"]]), fx["target"].cuda()).backward()
+    assert float((g16 - ref.flat_grad).norm() / ref.flat_grad.norm()) <= 0.25
+    net.train()
+    with torch.no_grad():
+        out = net([f.cuda() for f in fx["inputs"]]).cpu()
+    den = lambda t: restated.denormalize(t, "acdc")
+    p_ref = restated.psnr(den(fx["output"]), den(fx["target"]))
+    p_got = restated.psnr(den(out), den(fx["target"]))
+    assert abs(float(p_ref) - float(p_got)) <= 0.05
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_gpu_dense3d_kernels_match_emulation(dtype):
+    """vsr_copy_window / vsr_bn_stats / vsr_bn_finalize / vsr_bn_relu / vsr_bn_relu_bwd / vsr_duf_filter{,_bwd}"""
+    from vsr_b200.ops import cuda_ops
+    ops, emu, dev = cuda_ops(), EmuOps(), "cuda"
+    g = torch.Generator(device="cpu").manual_seed(5)
+    F, N, h, w, ld, c0, c, cp = 3, 2, 9, 7, 160, 32, 96, 128
+    x = (torch.randn(F * N, h, w, ld, generator=g) * 1.5 + 0.3).to(dev).to(dtype)
+    ws = lambda nbytes: torch.empty(max(nbytes, 16) // 8 + 1, dtype=torch.float64, device=dev)
+    st_a = torch.zeros(F, 2, 200, dtype=torch.float64, device=dev)
+    st_b = torch.zeros_like(st_a)
+    ops.bn_stats(x, c0, c, F, st_a, 64, ws(ops.bn_stats_workspace(F, N * h * w, c)))
+    emu.bn_stats(x, c0, c, F, st_b, 64, None)
+    assert torch.allclose(st_a, st_b, rtol=1e-6, atol=1e-6)
+    gamma = (1 + 0.1 * torch.randn(c, generator=g)).to(dev)
+    beta = (0.1 * torch.randn(c, generator=g)).to(dev)
+    outs = []
+    for o in (ops, emu):
+        rm, rv = torch.zeros(c, device=dev), torch.ones(c, device=dev)
+        ss, mr = torch.empty(2, cp, device=dev), torch.empty(2, c, device=dev)
+        o.bn_finalize(st_b[1:], 64, 2, N * h * w, c, gamma, beta, 1e-5, 0.1, rm, rv, True, ss, mr)
+        outs.append((ss, mr, rm, rv))
+    for a, b in zip(*outs):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
+    ss, mr = outs[1][:2]
+    xs = x[N:]                                                   # the two frames the statistics cover
+    y_a, y_b = torch.empty(2 * N, h, w, cp, dtype=dtype, device=dev), torch.empty(2 * N, h, w, cp, dtype=dtype, device=dev)
+    ops.bn_relu(xs, c0, c, ss, y_a)
+    emu.bn_relu(xs, c0, c, ss, y_b)
+    assert torch.equal(y_a[..., c:], torch.zeros_like(y_a[..., c:]))
+    assert torch.allclose(y_a.float(), y_b.float(), rtol=1e-2 if dtype == torch.bfloat16 else 1e-6, atol=1e-6)
+    dy = torch.randn(2 * N, h, w, cp, generator=g).to(dev).to(dtype)
+    tol = dict(rtol=2e-2, atol=2e-2) if dtype == torch.bfloat16 else dict(rtol=1e-4, atol=1e-5)
+    for acc in (False, True):
+        res = []
+        for o in (ops, emu):
+            gb = torch.zeros(2 * c, device=dev)
+            dx = torch.ones(2 * N, h, w, ld, dtype=dtype, device=dev)
+            o.bn_relu_bwd(dy, xs, c0, c, ss, mr, gb, dx, 16, c if acc else 112, acc,
+                          ws(ops.bn_relu_bwd_workspace(2 * N * h * w, c)))
+            res.append((gb, dx.float()))
+        assert torch.allclose(res[0][0], res[1][0], rtol=1e-3, atol=1e-3)
+        assert torch.allclose(res[0][1], res[1][1], **tol)
+    d_a = torch.zeros(F * N, h, w, 64, dtype=dtype, device=dev)
+    ops.copy_window(x, c0, d_a, 16, 32)
+    assert torch.equal(d_a[..., 16:48], x[..., c0:c0 + 32]) and float(d_a[..., :16].abs().max()) == 0
+    for cin, sf, r in ((1, 5, 4), (2, 3, 3)):
+        cf, cr = sf * sf * r * r, cin * r * r
+        ldl, ldr = -(-cf // 64) * 64, 64
+        lg = torch.randn(N, h, w, ldl, generator=g).to(dev).to(dtype)
+        rs = torch.randn(N, h, w, ldr, generator=g).to(dev).to(dtype)
+        img = torch.randn(N, cin, h, w, generator=g).to(dev)
+        ya, yb = torch.empty(N, cin, h * r, w * r, device=dev), torch.empty(N, cin, h * r, w * r, device=dev)
+        ops.duf_filter(lg, rs, img, sf, r, ya)
+        emu.duf_filter(lg, rs, img, sf, r, yb)
+        assert torch.allclose(ya, yb, rtol=1e-4, atol=1e-5)
+        gy = torch.randn(N, cin, h * r, w * r, generator=g).to(dev)
+        ga = [torch.full((N, h, w, ldl), 7.0, dtype=dtype, device=dev), torch.full((N, h, w, ldr), 7.0, dtype=dtype, device=dev)]
+        gb_ = [torch.empty_like(ga[0]), torch.empty_like(ga[1])]
+        ops.duf_filter_bwd(lg, img, gy, sf, r, ga[0], ga[1])
+        emu.duf_filter_bwd(lg, img, gy, sf, r, gb_[0], gb_[1])
+        for a, b in zip(ga, gb_):
+            assert torch.allclose(a.float(), b.float(), **tol)

@@ -98,6 +98,24 @@ _SIGS = {
                                     C.c_void_p]),
     "vsr_scale": (C.c_int, [C.c_void_p, C.c_int64, C.c_float, C.c_void_p]),
     "vsr_cast": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p]),
+    "vsr_copy_window": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                  C.c_int64, C.c_int32, C.c_void_p]),
+    "vsr_bn_stats_workspace": (C.c_size_t, [C.c_int32, C.c_int64, C.c_int32]),
+    "vsr_bn_stats": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64,
+                               C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "vsr_bn_finalize": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32,
+                                  C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int32,
+                                  C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vsr_bn_relu": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p,
+                              C.c_int32, C.c_void_p, C.c_void_p]),
+    "vsr_bn_relu_bwd_workspace": (C.c_size_t, [C.c_int64, C.c_int32]),
+    "vsr_bn_relu_bwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                  C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                  C.c_int32, C.c_int32, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "vsr_duf_filter": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p] +
+                       [C.c_int32] * 6 + [C.c_void_p, C.c_void_p]),
+    "vsr_duf_filter_bwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p] + [C.c_int32] * 6 +
+                           [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
 }
 
 # every symbol include/vsr_b200.h declares (vsr_tapgemm_simt_bf16 is a test hook, not in the header)

@@ -1,0 +1,547 @@
+// dense3d.cu — the bandwidth-bound kernels of the Conv3d network (DUFNet, reference duf_net.py:21-214):
+// BatchNorm3d batch statistics / normalise + ReLU / their backward on channel windows of the dense-concat
+// map, channel-window copies, and the dynamic-upsampling-filter tail (softmax over the 5x5 taps, local
+// filtering of the centre frame, pixel shuffle, residual add) forward and backward.
+//
+// All maps are pixel-major [rows][ld] with the channel window [c0, c0+c) addressed explicitly, so the dense
+// concatenation (duf_net.py:123-128) is one buffer that every layer reads a prefix of and appends a slice to.
+// Every thread moves 16-byte vectors; a thread keeps the same channel vector for all of its rows, so the
+// per-channel constants live in registers.  Reductions are two-pass with a fixed summation order.
+#include "common.cuh"
+
+namespace vsr {
+namespace {
+
+constexpr int kThreads = 256;
+
+template <typename T>
+struct Vec;
+template <>
+struct Vec<float> {
+  static constexpr int V = 4;
+  static __device__ __forceinline__ void ld(const float* p, float* v) {
+    const float4 q = *reinterpret_cast<const float4*>(p);
+    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+  }
+  static __device__ __forceinline__ void st(float* p, const float* v) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <>
+struct Vec<__nv_bfloat16> {
+  static constexpr int V = 8;
+  static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float* v) {
+    const uint4 q = *reinterpret_cast<const uint4*>(p);
+    v[0] = bf16_lo(q.x); v[1] = bf16_hi(q.x); v[2] = bf16_lo(q.y); v[3] = bf16_hi(q.y);
+    v[4] = bf16_lo(q.z); v[5] = bf16_hi(q.z); v[6] = bf16_lo(q.w); v[7] = bf16_hi(q.w);
+  }
+  static __device__ __forceinline__ void st(__nv_bfloat16* p, const float* v) {
+    uint4 q;
+    q.x = pack_bf16x2(v[0], v[1]); q.y = pack_bf16x2(v[2], v[3]);
+    q.z = pack_bf16x2(v[4], v[5]); q.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(p) = q;
+  }
+};
+
+// rows of a [rows][.] map split over blocks: block b of `nb` gets [lo, hi)
+__device__ __forceinline__ void row_range(long rows, int b, int nb, long* lo, long* hi) {
+  const long per = (rows + nb - 1) / nb;
+  *lo = (long)b * per;
+  *hi = *lo + per < rows ? *lo + per : rows;
+}
+
+// ---- channel-window copy ---------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads) copy_window_kernel(const T* __restrict__ src, int lds, int s0,
+                                                               T* __restrict__ dst, int ldd, int d0, int c, long rows) {
+  constexpr int V = Vec<T>::V;
+  const int tpr = c / V;
+  const long total = rows * tpr;
+  for (long i = (long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long)gridDim.x * kThreads) {
+    const long row = i / tpr;
+    const int v = (int)(i - row * tpr) * V;
+    *reinterpret_cast<uint4*>(dst + row * ldd + d0 + v) = *reinterpret_cast<const uint4*>(src + row * lds + s0 + v);
+  }
+}
+
+// ---- batch statistics ------------------------------------------------------------------------------------
+// grid = frames * bpf blocks; block (f, b) reduces its rows of frame f to [2][c] doubles in ws.
+template <typename T>
+__global__ void __launch_bounds__(kThreads) bn_stats_kernel(const T* __restrict__ x, int ldx, int c0, int c,
+                                                            long rows_per_frame, int bpf, double* __restrict__ ws) {
+  constexpr int V = Vec<T>::V;
+  extern __shared__ double sm[];   // [rpp][2][c]
+  const int tpr = c / V, rpp = kThreads / tpr;
+  const int f = blockIdx.x / bpf, b = blockIdx.x % bpf;
+  const int r = threadIdx.x / tpr, v = (threadIdx.x % tpr) * V;
+  long lo, hi;
+  row_range(rows_per_frame, b, bpf, &lo, &hi);
+  float s[V], q[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) s[i] = q[i] = 0.f;
+  double ds[V], dq[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) ds[i] = dq[i] = 0.0;
+  if (r < rpp) {
+    const T* base = x + ((long)f * rows_per_frame) * ldx + c0 + v;
+    int run = 0;
+    for (long row = lo + r; row < hi; row += rpp) {
+      float t[V];
+      Vec<T>::ld(base + row * ldx, t);
+#pragma unroll
+      for (int i = 0; i < V; ++i) { s[i] += t[i]; q[i] = fmaf(t[i], t[i], q[i]); }
+      if (++run == 32) {   // short fp32 runs, double across runs: keeps E[x^2]-E[x]^2 well conditioned
+#pragma unroll
+        for (int i = 0; i < V; ++i) { ds[i] += s[i]; dq[i] += q[i]; s[i] = q[i] = 0.f; }
+        run = 0;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < V; ++i) { ds[i] += s[i]; dq[i] += q[i]; }
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      sm[(r * 2 + 0) * c + v + i] = ds[i];
+      sm[(r * 2 + 1) * c + v + i] = dq[i];
+    }
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < 2 * c; j += kThreads) {
+    double a = 0.0;
+    for (int rr = 0; rr < rpp; ++rr) a += sm[rr * 2 * c + j];
+    ws[(long)blockIdx.x * 2 * c + j] = a;
+  }
+}
+
+__global__ void bn_stats_final_kernel(const double* __restrict__ ws, int frames, int bpf, int c,
+                                      double* __restrict__ stats, int ld_stats, int s0) {
+  const int total = frames * 2 * c;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int f = i / (2 * c), j = i % (2 * c);
+    double a = 0.0;
+    for (int b = 0; b < bpf; ++b) a += ws[((long)(f * bpf + b)) * 2 * c + j];
+    stats[((long)f * 2 + j / c) * ld_stats + s0 + j % c] = a;
+  }
+}
+
+// scale/shift of one BatchNorm over `frames` frames of statistics (training) or from the running buffers.
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, int ld_stats, int s0, int frames, double count,
+                                   int c, int cp, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float eps, float momentum, float* running_mean, float* running_var, int training,
+                                   float* __restrict__ scale_shift, float* __restrict__ mean_rstd) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= cp) return;
+  if (j >= c) {
+    scale_shift[j] = 0.f;
+    scale_shift[cp + j] = 0.f;
+    return;
+  }
+  double mean, var;
+  if (training) {
+    double s = 0.0, q = 0.0;
+    for (int f = 0; f < frames; ++f) {
+      s += stats[((long)f * 2 + 0) * ld_stats + s0 + j];
+      q += stats[((long)f * 2 + 1) * ld_stats + s0 + j];
+    }
+    mean = s / count;
+    var = q / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    if (running_mean) {   // nn.BatchNorm3d: running stats with the unbiased variance (duf_net.py:198,201)
+      const double unb = count > 1.0 ? var * count / (count - 1.0) : var;
+      running_mean[j] = (float)((1.0 - momentum) * running_mean[j] + momentum * mean);
+      running_var[j] = (float)((1.0 - momentum) * running_var[j] + momentum * unb);
+    }
+  } else {
+    mean = running_mean[j];
+    var = running_var[j];
+  }
+  const double rstd = 1.0 / sqrt(var + (double)eps);
+  const double sc = (double)gamma[j] * rstd;
+  scale_shift[j] = (float)sc;
+  scale_shift[cp + j] = (float)((double)beta[j] - mean * sc);
+  mean_rstd[j] = (float)mean;
+  mean_rstd[c + j] = (float)rstd;
+}
+
+// ---- normalise + ReLU ------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads) bn_relu_kernel(const T* __restrict__ x, int ldx, int c0, int c, long rows,
+                                                           const float* __restrict__ scale_shift, int cp,
+                                                           T* __restrict__ y) {
+  constexpr int V = Vec<T>::V;
+  const int tpr = cp / V, rpp = kThreads / tpr;
+  const int r = threadIdx.x / tpr, v = (threadIdx.x % tpr) * V;
+  if (r >= rpp) return;
+  float sc[V], sh[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) { sc[i] = scale_shift[v + i]; sh[i] = scale_shift[cp + v + i]; }
+  const bool pad = v >= c;
+  for (long row = (long)blockIdx.x * rpp + r; row < rows; row += (long)gridDim.x * rpp) {
+    float t[V];
+    if (pad) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) t[i] = 0.f;
+    } else {
+      Vec<T>::ld(x + row * ldx + c0 + v, t);
+#pragma unroll
+      for (int i = 0; i < V; ++i) t[i] = fmaxf(fmaf(t[i], sc[i], sh[i]), 0.f);
+    }
+    Vec<T>::st(y + row * cp + v, t);
+  }
+}
+
+// backward, pass 1: per-block partial sums of g and g*xhat (g = dy where the forward output was positive)
+template <typename T>
+__global__ void __launch_bounds__(kThreads) bn_relu_bwd_reduce_kernel(const T* __restrict__ dy, int ld_dy,
+                                                                      const T* __restrict__ x, int ldx, int c0, int c,
+                                                                      long rows, const float* __restrict__ scale_shift,
+                                                                      int cp, const float* __restrict__ mean_rstd,
+                                                                      float* __restrict__ ws) {
+  constexpr int V = Vec<T>::V;
+  extern __shared__ float smf[];   // [rpp][2][c]
+  const int tpr = c / V, rpp = kThreads / tpr;
+  const int r = threadIdx.x / tpr, v = (threadIdx.x % tpr) * V;
+  long lo, hi;
+  row_range(rows, blockIdx.x, gridDim.x, &lo, &hi);
+  if (r < rpp) {
+    float sc[V], sh[V], mu[V], rs[V], sg[V], sx[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      sc[i] = scale_shift[v + i]; sh[i] = scale_shift[cp + v + i];
+      mu[i] = mean_rstd[v + i]; rs[i] = mean_rstd[c + v + i];
+      sg[i] = sx[i] = 0.f;
+    }
+    for (long row = lo + r; row < hi; row += rpp) {
+      float t[V], g[V];
+      Vec<T>::ld(x + row * ldx + c0 + v, t);
+      Vec<T>::ld(dy + row * ld_dy + v, g);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float gi = fmaf(t[i], sc[i], sh[i]) > 0.f ? g[i] : 0.f;
+        sg[i] += gi;
+        sx[i] = fmaf(gi, (t[i] - mu[i]) * rs[i], sx[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      smf[(r * 2 + 0) * c + v + i] = sx[i];   // row 0: d gamma
+      smf[(r * 2 + 1) * c + v + i] = sg[i];   // row 1: d beta
+    }
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < 2 * c; j += kThreads) {
+    float a = 0.f;
+    for (int rr = 0; rr < rpp; ++rr) a += smf[rr * 2 * c + j];
+    ws[(long)blockIdx.x * 2 * c + j] = a;
+  }
+}
+
+__global__ void bn_relu_bwd_final_kernel(const float* __restrict__ ws, int blocks, int c, float* __restrict__ out) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < 2 * c; j += gridDim.x * blockDim.x) {
+    double a = 0.0;
+    for (int b = 0; b < blocks; ++b) a += ws[(long)b * 2 * c + j];
+    out[j] = (float)a;
+  }
+}
+
+// backward, pass 2: dx = gamma*rstd * (g - mean(g) - xhat * mean(g*xhat)), written or accumulated into a window
+template <typename T>
+__global__ void __launch_bounds__(kThreads) bn_relu_bwd_apply_kernel(const T* __restrict__ dy, int ld_dy,
+                                                                     const T* __restrict__ x, int ldx, int c0, int c,
+                                                                     long rows, const float* __restrict__ scale_shift,
+                                                                     int cp, const float* __restrict__ mean_rstd,
+                                                                     const float* __restrict__ sums, float inv_count,
+                                                                     T* __restrict__ dx, int ld_dx, int c0_dx, int cp_dx,
+                                                                     int accumulate) {
+  constexpr int V = Vec<T>::V;
+  const int tpr = cp_dx / V, rpp = kThreads / tpr;
+  const int r = threadIdx.x / tpr, v = (threadIdx.x % tpr) * V;
+  if (r >= rpp) return;
+  const bool pad = v >= c;
+  float sc[V], sh[V], mu[V], rs[V], mg[V], mx[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    if (pad) { sc[i] = sh[i] = mu[i] = rs[i] = mg[i] = mx[i] = 0.f; continue; }
+    sc[i] = scale_shift[v + i]; sh[i] = scale_shift[cp + v + i];
+    mu[i] = mean_rstd[v + i]; rs[i] = mean_rstd[c + v + i];
+    mx[i] = sums[v + i] * inv_count;       // mean of g * xhat
+    mg[i] = sums[c + v + i] * inv_count;   // mean of g
+  }
+  for (long row = (long)blockIdx.x * rpp + r; row < rows; row += (long)gridDim.x * rpp) {
+    float o[V];
+    T* dst = dx + row * ld_dx + c0_dx + v;
+    if (pad) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) o[i] = 0.f;
+    } else {
+      float t[V], g[V];
+      Vec<T>::ld(x + row * ldx + c0 + v, t);
+      Vec<T>::ld(dy + row * ld_dy + v, g);
+      if (accumulate) Vec<T>::ld(dst, o);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float gi = fmaf(t[i], sc[i], sh[i]) > 0.f ? g[i] : 0.f;
+        const float d = sc[i] * (gi - mg[i] - (t[i] - mu[i]) * rs[i] * mx[i]);
+        o[i] = accumulate ? o[i] + d : d;
+      }
+    }
+    Vec<T>::st(dst, o);
+  }
+}
+
+// ---- dynamic upsampling filter tail (duf_net.py:66-97) -------------------------------------------------------
+// One thread per (low-resolution pixel, sub-pixel p): softmax over the sf*sf taps of logits[pix][k*r*r + p],
+// applied to the sf x sf neighbourhood of the centre frame (zero padded), + residual[pix][c*r*r + p], stored at
+// the pixel-shuffled position of the NCHW output.
+template <typename T>
+__global__ void __launch_bounds__(kThreads) duf_filter_kernel(const T* __restrict__ logits, int ld_l,
+                                                              const T* __restrict__ res, int ld_r,
+                                                              const float* __restrict__ x, int n, int cin, int h, int w,
+                                                              int sf, int r, float* __restrict__ y) {
+  const int rr = r * r, half = sf / 2, taps = sf * sf;
+  const long total = (long)n * h * w * rr;
+  for (long i = (long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long)gridDim.x * kThreads) {
+    const int p = (int)(i % rr);
+    const long pix = i / rr;
+    const int x0 = (int)(pix % w), y0 = (int)((pix / w) % h), nn = (int)(pix / ((long)w * h));
+    const T* lg = logits + pix * ld_l + p;
+    float mx = -INFINITY;
+    for (int k = 0; k < taps; ++k) mx = fmaxf(mx, Elem<T>::ld(lg + k * rr));
+    const int Y = y0 * r + p / r, X = x0 * r + p % r;
+    for (int c = 0; c < cin; ++c) {
+      const float* xc = x + ((long)nn * cin + c) * h * w;
+      float se = 0.f, sx = 0.f;
+      for (int k = 0; k < taps; ++k) {
+        const float e = __expf(Elem<T>::ld(lg + k * rr) - mx);
+        const int yy = y0 + k / sf - half, xx = x0 + k % sf - half;
+        const float xv = (yy >= 0 && yy < h && xx >= 0 && xx < w) ? __ldg(xc + (long)yy * w + xx) : 0.f;
+        se += e;
+        sx = fmaf(e, xv, sx);
+      }
+      y[(((long)nn * cin + c) * h * r + Y) * ((long)w * r) + X] = sx / se + Elem<T>::ld(res + pix * ld_r + c * rr + p);
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) duf_filter_bwd_kernel(const T* __restrict__ logits, int ld_l,
+                                                                  const float* __restrict__ x,
+                                                                  const float* __restrict__ dy, int n, int cin, int h,
+                                                                  int w, int sf, int r, T* __restrict__ dlogits,
+                                                                  T* __restrict__ dres, int ld_r) {
+  const int rr = r * r, half = sf / 2, taps = sf * sf;
+  const long total = (long)n * h * w * rr;
+  for (long i = (long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long)gridDim.x * kThreads) {
+    const int p = (int)(i % rr);
+    const long pix = i / rr;
+    const int x0 = (int)(pix % w), y0 = (int)((pix / w) % h), nn = (int)(pix / ((long)w * h));
+    const T* lg = logits + pix * ld_l + p;
+    const int Y = y0 * r + p / r, X = x0 * r + p % r;
+    float mx = -INFINITY;
+    for (int k = 0; k < taps; ++k) mx = fmaxf(mx, Elem<T>::ld(lg + k * rr));
+    // g_k = sum_c dy_c * x_c[k];  dlogit_k = s_k * (g_k - sum_j s_j g_j)
+    float se = 0.f, sg = 0.f;
+    for (int k = 0; k < taps; ++k) {
+      const float e = __expf(Elem<T>::ld(lg + k * rr) - mx);
+      const int yy = y0 + k / sf - half, xx = x0 + k % sf - half;
+      float g = 0.f;
+      if (yy >= 0 && yy < h && xx >= 0 && xx < w)
+        for (int c = 0; c < cin; ++c)
+          g = fmaf(__ldg(dy + (((long)nn * cin + c) * h * r + Y) * ((long)w * r) + X),
+                   __ldg(x + (((long)nn * cin + c) * h + yy) * w + xx), g);
+      se += e;
+      sg = fmaf(e, g, sg);
+    }
+    const float inv = 1.f / se, dot = sg * inv;
+    for (int k = 0; k < taps; ++k) {
+      const float s = __expf(Elem<T>::ld(lg + k * rr) - mx) * inv;
+      const int yy = y0 + k / sf - half, xx = x0 + k % sf - half;
+      float g = 0.f;
+      if (yy >= 0 && yy < h && xx >= 0 && xx < w)
+        for (int c = 0; c < cin; ++c)
+          g = fmaf(__ldg(dy + (((long)nn * cin + c) * h * r + Y) * ((long)w * r) + X),
+                   __ldg(x + (((long)nn * cin + c) * h + yy) * w + xx), g);
+      Elem<T>::st(dlogits + pix * ld_l + k * rr + p, s * (g - dot));
+    }
+    for (int c = 0; c < cin; ++c)
+      Elem<T>::st(dres + pix * ld_r + c * rr + p, __ldg(dy + (((long)nn * cin + c) * h * r + Y) * ((long)w * r) + X));
+  }
+}
+
+int stats_bpf(int frames, long rows_per_frame) {
+  long bpf = (rows_per_frame + 511) / 512;
+  const long cap = (4L * num_sms() + frames - 1) / frames;
+  if (bpf > cap) bpf = cap;
+  if (bpf < 1) bpf = 1;
+  return (int)bpf;
+}
+
+int reduce_blocks(long rows) {
+  long b = (rows + 255) / 256;
+  const long cap = 2L * num_sms();
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+template <typename T>
+bool window_ok(int ld, int c0, int c) {
+  constexpr int V = Vec<T>::V;
+  return c > 0 && c % V == 0 && c0 % V == 0 && ld % V == 0 && c / V <= kThreads;
+}
+
+#define VSR_DISPATCH_DTYPE(dtype, who, ...)                         \
+  if ((dtype) == VSR_F32) {                                         \
+    typedef float T;                                                \
+    __VA_ARGS__                                                     \
+  } else if ((dtype) == VSR_BF16) {                                 \
+    typedef __nv_bfloat16 T;                                        \
+    __VA_ARGS__                                                     \
+  } else {                                                          \
+    VSR_CHECK_ARG(false, "%s: bad dtype %d", who, (int)(dtype));    \
+  }
+
+}  // namespace
+}  // namespace vsr
+
+using namespace vsr;
+
+extern "C" int vsr_copy_window(const void* src, int32_t ld_src, int32_t c0_src, void* dst, int32_t ld_dst,
+                               int32_t c0_dst, int32_t c, int64_t rows, int32_t dtype, void* stream) {
+  VSR_CHECK_ARG(src && dst && rows > 0, "vsr_copy_window: bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  VSR_DISPATCH_DTYPE(dtype, "vsr_copy_window", {
+    VSR_CHECK_ARG((window_ok<T>(ld_src, c0_src, c) && window_ok<T>(ld_dst, c0_dst, c)),
+                  "vsr_copy_window: windows must be 16-byte aligned (ld %d/%d c0 %d/%d c %d)", ld_src, ld_dst, c0_src,
+                  c0_dst, c);
+    copy_window_kernel<T><<<grid_for(rows * (c / Vec<T>::V), kThreads), kThreads, 0, s>>>(
+        (const T*)src, ld_src, c0_src, (T*)dst, ld_dst, c0_dst, c, rows);
+  })
+  VSR_CHECK_LAUNCH("vsr_copy_window");
+  return VSR_OK;
+}
+
+extern "C" size_t vsr_bn_stats_workspace(int32_t frames, int64_t rows_per_frame, int32_t c) {
+  if (frames <= 0 || rows_per_frame <= 0 || c <= 0) return 0;
+  return (size_t)frames * stats_bpf(frames, rows_per_frame) * 2 * c * sizeof(double);
+}
+
+extern "C" int vsr_bn_stats(const void* x, int32_t dtype, int32_t ldx, int32_t c0, int32_t c, int32_t frames,
+                            int64_t rows_per_frame, double* stats, int32_t ld_stats, int32_t s0, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+  VSR_CHECK_ARG(x && stats && frames > 0 && rows_per_frame > 0, "vsr_bn_stats: bad arguments");
+  VSR_CHECK_ARG(workspace && workspace_bytes >= vsr_bn_stats_workspace(frames, rows_per_frame, c),
+                "vsr_bn_stats: workspace too small");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int bpf = stats_bpf(frames, rows_per_frame);
+  double* ws = static_cast<double*>(workspace);
+  VSR_DISPATCH_DTYPE(dtype, "vsr_bn_stats", {
+    VSR_CHECK_ARG(window_ok<T>(ldx, c0, c), "vsr_bn_stats: window must be 16-byte aligned (ld %d c0 %d c %d)", ldx, c0, c);
+    const int rpp = kThreads / (c / Vec<T>::V);
+    const size_t smem = (size_t)rpp * 2 * c * sizeof(double);
+    VSR_CHECK_SUPPORTED(smem <= 48 * 1024, "vsr_bn_stats: window of %d channels too wide", c);
+    bn_stats_kernel<T><<<frames * bpf, kThreads, smem, s>>>((const T*)x, ldx, c0, c, rows_per_frame, bpf, ws);
+  })
+  VSR_CHECK_LAUNCH("vsr_bn_stats");
+  bn_stats_final_kernel<<<grid_for((long)frames * 2 * c, 256), 256, 0, s>>>(ws, frames, bpf, c, stats, ld_stats, s0);
+  VSR_CHECK_LAUNCH("vsr_bn_stats_final");
+  return VSR_OK;
+}
+
+extern "C" int vsr_bn_finalize(const double* stats, int32_t ld_stats, int32_t s0, int32_t frames,
+                               int64_t rows_per_frame, int32_t c, int32_t cp, const float* gamma, const float* beta,
+                               float eps, float momentum, float* running_mean, float* running_var, int32_t training,
+                               float* scale_shift, float* mean_rstd, void* stream) {
+  VSR_CHECK_ARG(gamma && beta && scale_shift && mean_rstd && c > 0 && cp >= c, "vsr_bn_finalize: bad arguments");
+  VSR_CHECK_ARG(training ? (stats != nullptr && frames > 0 && rows_per_frame > 0) : (running_mean && running_var),
+                "vsr_bn_finalize: missing statistics");
+  bn_finalize_kernel<<<(cp + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      stats, ld_stats, s0, frames, (double)frames * (double)rows_per_frame, c, cp, gamma, beta, eps, momentum,
+      running_mean, running_var, training, scale_shift, mean_rstd);
+  VSR_CHECK_LAUNCH("vsr_bn_finalize");
+  return VSR_OK;
+}
+
+extern "C" int vsr_bn_relu(const void* x, int32_t dtype, int32_t ldx, int32_t c0, int32_t c, int64_t rows,
+                           const float* scale_shift, int32_t cp, void* y, void* stream) {
+  VSR_CHECK_ARG(x && y && scale_shift && rows > 0 && cp >= c, "vsr_bn_relu: bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  VSR_DISPATCH_DTYPE(dtype, "vsr_bn_relu", {
+    VSR_CHECK_ARG((window_ok<T>(ldx, c0, c) && window_ok<T>(cp, 0, cp)),
+                  "vsr_bn_relu: windows must be 16-byte aligned (ld %d c0 %d c %d cp %d)", ldx, c0, c, cp);
+    const int rpp = kThreads / (cp / Vec<T>::V);
+    bn_relu_kernel<T><<<grid_for(rows, rpp * 4), kThreads, 0, s>>>((const T*)x, ldx, c0, c, rows, scale_shift, cp, (T*)y);
+  })
+  VSR_CHECK_LAUNCH("vsr_bn_relu");
+  return VSR_OK;
+}
+
+extern "C" size_t vsr_bn_relu_bwd_workspace(int64_t rows, int32_t c) {
+  if (rows <= 0 || c <= 0) return 0;
+  return (size_t)reduce_blocks(rows) * 2 * c * sizeof(float);
+}
+
+extern "C" int vsr_bn_relu_bwd(const void* dy, int32_t ld_dy, const void* x, int32_t dtype, int32_t ldx, int32_t c0,
+                               int32_t c, int64_t rows, const float* scale_shift, int32_t cp, const float* mean_rstd,
+                               float* dgamma_dbeta, void* dx, int32_t ld_dx, int32_t c0_dx, int32_t cp_dx,
+                               int accumulate, void* workspace, size_t workspace_bytes, void* stream) {
+  VSR_CHECK_ARG(dy && x && dx && scale_shift && mean_rstd && dgamma_dbeta && rows > 0, "vsr_bn_relu_bwd: bad arguments");
+  VSR_CHECK_ARG(cp >= c && cp_dx >= c && !(accumulate && cp_dx != c), "vsr_bn_relu_bwd: bad channel counts");
+  VSR_CHECK_ARG(workspace && workspace_bytes >= vsr_bn_relu_bwd_workspace(rows, c), "vsr_bn_relu_bwd: workspace too small");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int blocks = reduce_blocks(rows);
+  float* ws = static_cast<float*>(workspace);
+  VSR_DISPATCH_DTYPE(dtype, "vsr_bn_relu_bwd", {
+    VSR_CHECK_ARG((window_ok<T>(ldx, c0, c) && window_ok<T>(ld_dy, 0, c) && window_ok<T>(ld_dx, c0_dx, cp_dx)),
+                  "vsr_bn_relu_bwd: windows must be 16-byte aligned");
+    const int rpp = kThreads / (c / Vec<T>::V);
+    const size_t smem = (size_t)rpp * 2 * c * sizeof(float);
+    VSR_CHECK_SUPPORTED(smem <= 48 * 1024, "vsr_bn_relu_bwd: window of %d channels too wide", c);
+    bn_relu_bwd_reduce_kernel<T><<<blocks, kThreads, smem, s>>>((const T*)dy, ld_dy, (const T*)x, ldx, c0, c, rows,
+                                                                scale_shift, cp, mean_rstd, ws);
+    VSR_CHECK_LAUNCH("vsr_bn_relu_bwd_reduce");
+    bn_relu_bwd_final_kernel<<<(2 * c + 127) / 128, 128, 0, s>>>(ws, blocks, c, dgamma_dbeta);
+    VSR_CHECK_LAUNCH("vsr_bn_relu_bwd_final");
+    const int rpp2 = kThreads / (cp_dx / Vec<T>::V);
+    bn_relu_bwd_apply_kernel<T><<<grid_for(rows, rpp2 * 4), kThreads, 0, s>>>(
+        (const T*)dy, ld_dy, (const T*)x, ldx, c0, c, rows, scale_shift, cp, mean_rstd, dgamma_dbeta,
+        (float)(1.0 / (double)rows), (T*)dx, ld_dx, c0_dx, cp_dx, accumulate);
+  })
+  VSR_CHECK_LAUNCH("vsr_bn_relu_bwd_apply");
+  return VSR_OK;
+}
+
+extern "C" int vsr_duf_filter(const void* logits, int32_t ld_logits, const void* res, int32_t ld_res, int32_t dtype,
+                              const float* x, int32_t n, int32_t cin, int32_t h, int32_t w, int32_t size_filter,
+                              int32_t r, float* y, void* stream) {
+  VSR_CHECK_ARG(logits && res && x && y && n > 0 && cin > 0 && h > 0 && w > 0, "vsr_duf_filter: bad arguments");
+  VSR_CHECK_ARG(size_filter >= 1 && size_filter % 2 == 1 && r >= 1 && ld_logits >= size_filter * size_filter * r * r &&
+                    ld_res >= cin * r * r, "vsr_duf_filter: bad filter size / strides");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const long total = (long)n * h * w * r * r;
+  VSR_DISPATCH_DTYPE(dtype, "vsr_duf_filter", {
+    duf_filter_kernel<T><<<grid_for(total, kThreads), kThreads, 0, s>>>((const T*)logits, ld_logits, (const T*)res, ld_res,
+                                                                      x, n, cin, h, w, size_filter, r, y);
+  })
+  VSR_CHECK_LAUNCH("vsr_duf_filter");
+  return VSR_OK;
+}
+
+extern "C" int vsr_duf_filter_bwd(const void* logits, int32_t ld_logits, int32_t dtype, const float* x, const float* dy,
+                                  int32_t n, int32_t cin, int32_t h, int32_t w, int32_t size_filter, int32_t r,
+                                  void* dlogits, void* dres, int32_t ld_res, void* stream) {
+  VSR_CHECK_ARG(logits && x && dy && dlogits && dres && n > 0 && cin > 0 && h > 0 && w > 0, "vsr_duf_filter_bwd: bad arguments");
+  VSR_CHECK_ARG(size_filter >= 1 && size_filter % 2 == 1 && r >= 1 && ld_logits >= size_filter * size_filter * r * r &&
+                    ld_res >= cin * r * r, "vsr_duf_filter_bwd: bad filter size / strides");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const long pix = (long)n * h * w;
+  const size_t es = dtype == VSR_F32 ? 4 : 2;
+  // channel padding of both gradient maps stays zero
+  if (ld_logits > size_filter * size_filter * r * r) cudaMemsetAsync(dlogits, 0, pix * ld_logits * es, s);
+  if (ld_res > cin * r * r) cudaMemsetAsync(dres, 0, pix * ld_res * es, s);
+  VSR_DISPATCH_DTYPE(dtype, "vsr_duf_filter_bwd", {
+    duf_filter_bwd_kernel<T><<<grid_for(pix * r * r, kThreads), kThreads, 0, s>>>(
+        (const T*)logits, ld_logits, x, dy, n, cin, h, w, size_filter, r, (T*)dlogits, (T*)dres, ld_res);
+  })
+  VSR_CHECK_LAUNCH("vsr_duf_filter_bwd");
+  return VSR_OK;
+}

@@ -429,6 +429,12 @@ class DrfPlan:
         bidx = np.full(self.n_params, -1, dtype=np.int32)
         for L in self.fwd.values():
             if L.bias_idx is not None:
+                bi = np.asarray(L.bias_idx, dtype=np.int64)
+                valid = bi >= 0
+                if not valid.all():      # padded / windowed output channels (-1): the period is the whole vector
+                    L.bias_c = len(bi)
+                    bidx[bi[valid]] = L.b_off + np.nonzero(valid)[0]
+                    continue
                 L.bias_c = int(len(np.unique(L.bias_idx)))
                 assert np.array_equal(L.bias_idx[:L.bias_c], L.bias_idx[L.bias_c:2 * L.bias_c]) or L.bias_c == L.out_c
                 bidx[np.asarray(L.bias_idx[:L.bias_c], dtype=np.int64)] = L.b_off + np.arange(L.bias_c)

@@ -1,2 +1,3 @@
 from ..nets import BaseNet, DRFNet, DRFSISRNet, SRFBNet  # noqa: F401
 from ..edsr import EDSRNet  # noqa: F401
+from ..duf import DUFNet  # noqa: F401

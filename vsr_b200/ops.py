@@ -300,6 +300,69 @@ class CudaOps:
     def zero_(self, t):
         t.zero_()  # cudaMemsetAsync on the current stream
 
+    # ---- Conv3d network: BatchNorm3d + ReLU on channel windows, dynamic filter tail ---------
+    @staticmethod
+    def _rows(t):
+        return t.numel() // t.shape[-1]
+
+    def copy_window(self, src, c0_src, dst, c0_dst, c):
+        _need_cuda(src, dst)
+        check(self.lib.vsr_copy_window(_p(src), src.shape[-1], c0_src, _p(dst), dst.shape[-1], c0_dst, c,
+                                       self._rows(src), _DT[src.dtype], _stream()), "vsr_copy_window")
+        self.launches += 1
+
+    def bn_stats_workspace(self, frames, rows_per_frame, c):
+        return self.lib.vsr_bn_stats_workspace(frames, rows_per_frame, c)
+
+    def bn_stats(self, x, c0, c, frames, stats, s0, workspace):
+        """per-frame sum / sum of squares of x[..., c0:c0+c] (x: `frames` stacked frames) -> stats[f, :, s0:s0+c]"""
+        _need_cuda(x, stats, workspace)
+        check(self.lib.vsr_bn_stats(_p(x), _DT[x.dtype], x.shape[-1], c0, c, frames, self._rows(x) // frames,
+                                    _p(stats), stats.shape[-1], s0, _p(workspace),
+                                    workspace.numel() * workspace.element_size(), _stream()), "vsr_bn_stats")
+        self.launches += 2
+
+    def bn_finalize(self, stats, s0, frames, rows_per_frame, c, gamma, beta, eps, momentum, running_mean,
+                    running_var, training, scale_shift, mean_rstd):
+        _need_cuda(stats, gamma, beta, running_mean, running_var, scale_shift, mean_rstd)
+        check(self.lib.vsr_bn_finalize(_p(stats), stats.shape[-1] if stats is not None else 0, s0, frames,
+                                       rows_per_frame, c, scale_shift.shape[-1], _p(gamma), _p(beta), eps, momentum,
+                                       _p(running_mean), _p(running_var), int(training), _p(scale_shift),
+                                       _p(mean_rstd), _stream()), "vsr_bn_finalize")
+        self.launches += 1
+
+    def bn_relu(self, x, c0, c, scale_shift, y):
+        _need_cuda(x, scale_shift, y)
+        check(self.lib.vsr_bn_relu(_p(x), _DT[x.dtype], x.shape[-1], c0, c, self._rows(x), _p(scale_shift),
+                                   y.shape[-1], _p(y), _stream()), "vsr_bn_relu")
+        self.launches += 1
+
+    def bn_relu_bwd_workspace(self, rows, c):
+        return self.lib.vsr_bn_relu_bwd_workspace(rows, c)
+
+    def bn_relu_bwd(self, dy, x, c0, c, scale_shift, mean_rstd, dgamma_dbeta, dx, c0_dx, cp_dx, accumulate, workspace):
+        _need_cuda(dy, x, scale_shift, mean_rstd, dgamma_dbeta, dx, workspace)
+        check(self.lib.vsr_bn_relu_bwd(_p(dy), dy.shape[-1], _p(x), _DT[x.dtype], x.shape[-1], c0, c, self._rows(x),
+                                       _p(scale_shift), scale_shift.shape[-1], _p(mean_rstd), _p(dgamma_dbeta),
+                                       _p(dx), dx.shape[-1], c0_dx, cp_dx, int(accumulate), _p(workspace),
+                                       workspace.numel() * workspace.element_size(), _stream()), "vsr_bn_relu_bwd")
+        self.launches += 3
+
+    def duf_filter(self, logits, res, x, size_filter, r, y):
+        _need_cuda(logits, res, x, y)
+        n, cin, h, w_ = x.shape
+        check(self.lib.vsr_duf_filter(_p(logits), logits.shape[-1], _p(res), res.shape[-1], _DT[logits.dtype], _p(x),
+                                      n, cin, h, w_, size_filter, r, _p(y), _stream()), "vsr_duf_filter")
+        self.launches += 1
+
+    def duf_filter_bwd(self, logits, x, dy, size_filter, r, dlogits, dres):
+        _need_cuda(logits, x, dy, dlogits, dres)
+        n, cin, h, w_ = x.shape
+        check(self.lib.vsr_duf_filter_bwd(_p(logits), logits.shape[-1], _DT[logits.dtype], _p(x), _p(dy), n, cin, h,
+                                          w_, size_filter, r, _p(dlogits), _p(dres), dres.shape[-1], _stream()),
+              "vsr_duf_filter_bwd")
+        self.launches += 1
+
     # ---- loss / metrics ----------------------------------------------------------------
     def loss_fwd_bwd(self, out, target, kind, param, grad_scale, partials, grad):
         _need_cuda(out, target, partials, grad)
