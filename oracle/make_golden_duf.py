@@ -60,7 +60,31 @@ def main():
         torch.manual_seed(idx)
         net = DUFNet(**kw)
         net.load_state_dict(duf_fill(net.state_dict(), 3000 + idx))
-        lrs, target = synth_frames(n, kw["num_frames"], h, w, kw["upscale_factor"], kw["in_channels"], 500 + idx)
+        # A ReLU input within fp32 round-off of zero makes the gradients of two CORRECT fp32 implementations differ
+        # by a whole element (measured: one such element among the 144 rows of the tail BatchNorm moved a slice of
+        # the gradients by 2e-3).  Pick, among a few input seeds, the one with the widest margin.
+        margins = {}
+        hooks = [m.register_forward_pre_hook(lambda mod, inp, name=name_: margins.__setitem__(
+            name, min(margins.get(name, 1e9), float(inp[0].abs().min())))) for name_, m in net.named_modules()
+            if isinstance(m, torch.nn.ReLU)]
+        best = None
+        net.train()
+        for k in range(16):
+            seed = 500 + idx + 100 * k
+            lrs, target = synth_frames(n, kw["num_frames"], h, w, kw["upscale_factor"], kw["in_channels"], seed)
+            margins.clear()
+            with torch.no_grad():
+                net(lrs)
+            small = min(v for k_, v in margins.items() if not k_.startswith("denseLayer.conv"))
+            dense = min(v for k_, v in margins.items() if k_.startswith("denseLayer.conv"))
+            score = min(small, 5 * dense)
+            if best is None or score > best[0]:
+                best = (score, seed, small, dense)
+        for hk in hooks:
+            hk.remove()
+        net.load_state_dict(duf_fill(net.state_dict(), 3000 + idx))      # undo the running-statistics updates
+        print(name, "input seed", best[1], "smallest |ReLU input|: tail/heads %.2e, dense layers %.2e" % best[2:])
+        lrs, target = synth_frames(n, kw["num_frames"], h, w, kw["upscale_factor"], kw["in_channels"], best[1])
         net.eval()
         with torch.no_grad():
             out_eval = net(lrs)

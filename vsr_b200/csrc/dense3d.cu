@@ -76,32 +76,39 @@ __global__ void __launch_bounds__(kThreads) bn_stats_kernel(const T* __restrict_
   const int r = threadIdx.x / tpr, v = (threadIdx.x % tpr) * V;
   long lo, hi;
   row_range(rows_per_frame, b, bpf, &lo, &hi);
-  float s[V], q[V];
+  // two-level fp32 accumulation (runs of 32 rows, then a sum of runs) keeps E[x^2] - E[x]^2 well conditioned;
+  // everything across threads and blocks is fp64
+  float s[V], q[V], s2[V], q2[V];
 #pragma unroll
-  for (int i = 0; i < V; ++i) s[i] = q[i] = 0.f;
-  double ds[V], dq[V];
-#pragma unroll
-  for (int i = 0; i < V; ++i) ds[i] = dq[i] = 0.0;
+  for (int i = 0; i < V; ++i) s[i] = q[i] = s2[i] = q2[i] = 0.f;
   if (r < rpp) {
     const T* base = x + ((long)f * rows_per_frame) * ldx + c0 + v;
     int run = 0;
-    for (long row = lo + r; row < hi; row += rpp) {
+    long row = lo + r;
+    for (; row + 3L * rpp < hi; row += 4L * rpp) {   // four independent 16-byte loads in flight per thread
+      float t[4][V];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) Vec<T>::ld(base + (row + (long)u * rpp) * ldx, t[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int i = 0; i < V; ++i) { s[i] += t[u][i]; q[i] = fmaf(t[u][i], t[u][i], q[i]); }
+      if (++run == 8) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) { s2[i] += s[i]; q2[i] += q[i]; s[i] = q[i] = 0.f; }
+        run = 0;
+      }
+    }
+    for (; row < hi; row += rpp) {
       float t[V];
       Vec<T>::ld(base + row * ldx, t);
 #pragma unroll
       for (int i = 0; i < V; ++i) { s[i] += t[i]; q[i] = fmaf(t[i], t[i], q[i]); }
-      if (++run == 32) {   // short fp32 runs, double across runs: keeps E[x^2]-E[x]^2 well conditioned
-#pragma unroll
-        for (int i = 0; i < V; ++i) { ds[i] += s[i]; dq[i] += q[i]; s[i] = q[i] = 0.f; }
-        run = 0;
-      }
     }
 #pragma unroll
-    for (int i = 0; i < V; ++i) { ds[i] += s[i]; dq[i] += q[i]; }
-#pragma unroll
     for (int i = 0; i < V; ++i) {
-      sm[(r * 2 + 0) * c + v + i] = ds[i];
-      sm[(r * 2 + 1) * c + v + i] = dq[i];
+      sm[(r * 2 + 0) * c + v + i] = (double)s2[i] + (double)s[i];
+      sm[(r * 2 + 1) * c + v + i] = (double)q2[i] + (double)q[i];
     }
   }
   __syncthreads();
@@ -112,15 +119,19 @@ __global__ void __launch_bounds__(kThreads) bn_stats_kernel(const T* __restrict_
   }
 }
 
+// one warp per output: lanes walk the per-block partials, then a shuffle tree (fixed order)
 __global__ void bn_stats_final_kernel(const double* __restrict__ ws, int frames, int bpf, int c,
                                       double* __restrict__ stats, int ld_stats, int s0) {
   const int total = frames * 2 * c;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int f = i / (2 * c), j = i % (2 * c);
-    double a = 0.0;
-    for (int b = 0; b < bpf; ++b) a += ws[((long)(f * bpf + b)) * 2 * c + j];
-    stats[((long)f * 2 + j / c) * ld_stats + s0 + j % c] = a;
-  }
+  const int lane = threadIdx.x & 31;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (i >= total) return;
+  const int f = i / (2 * c), j = i % (2 * c);
+  double a = 0.0;
+  for (int b = lane; b < bpf; b += 32) a += ws[((long)(f * bpf + b)) * 2 * c + j];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if (lane == 0) stats[((long)f * 2 + j / c) * ld_stats + s0 + j % c] = a;
 }
 
 // scale/shift of one BatchNorm over `frames` frames of statistics (training) or from the running buffers.
@@ -175,16 +186,31 @@ __global__ void __launch_bounds__(kThreads) bn_relu_kernel(const T* __restrict__
 #pragma unroll
   for (int i = 0; i < V; ++i) { sc[i] = scale_shift[v + i]; sh[i] = scale_shift[cp + v + i]; }
   const bool pad = v >= c;
-  for (long row = (long)blockIdx.x * rpp + r; row < rows; row += (long)gridDim.x * rpp) {
-    float t[V];
-    if (pad) {
+  const long stride = (long)gridDim.x * rpp;
+  long row = (long)blockIdx.x * rpp + r;
+  if (pad) {
+    float z[V];
 #pragma unroll
-      for (int i = 0; i < V; ++i) t[i] = 0.f;
-    } else {
-      Vec<T>::ld(x + row * ldx + c0 + v, t);
+    for (int i = 0; i < V; ++i) z[i] = 0.f;
+    for (; row < rows; row += stride) Vec<T>::st(y + row * cp + v, z);
+    return;
+  }
+  for (; row + 3 * stride < rows; row += 4 * stride) {   // four independent 16-byte loads in flight per thread
+    float t[4][V];
 #pragma unroll
-      for (int i = 0; i < V; ++i) t[i] = fmaxf(fmaf(t[i], sc[i], sh[i]), 0.f);
+    for (int u = 0; u < 4; ++u) Vec<T>::ld(x + (row + u * stride) * ldx + c0 + v, t[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) t[u][i] = fmaxf(fmaf(t[u][i], sc[i], sh[i]), 0.f);
+      Vec<T>::st(y + (row + u * stride) * cp + v, t[u]);
     }
+  }
+  for (; row < rows; row += stride) {
+    float t[V];
+    Vec<T>::ld(x + row * ldx + c0 + v, t);
+#pragma unroll
+    for (int i = 0; i < V; ++i) t[i] = fmaxf(fmaf(t[i], sc[i], sh[i]), 0.f);
     Vec<T>::st(y + row * cp + v, t);
   }
 }
@@ -210,7 +236,24 @@ __global__ void __launch_bounds__(kThreads) bn_relu_bwd_reduce_kernel(const T* _
       mu[i] = mean_rstd[v + i]; rs[i] = mean_rstd[c + v + i];
       sg[i] = sx[i] = 0.f;
     }
-    for (long row = lo + r; row < hi; row += rpp) {
+    long row = lo + r;
+    for (; row + rpp < hi; row += 2L * rpp) {   // four independent 16-byte loads in flight per thread
+      float t[2][V], g[2][V];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        Vec<T>::ld(x + (row + (long)u * rpp) * ldx + c0 + v, t[u]);
+        Vec<T>::ld(dy + (row + (long)u * rpp) * ld_dy + v, g[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          const float gi = fmaf(t[u][i], sc[i], sh[i]) > 0.f ? g[u][i] : 0.f;
+          sg[i] += gi;
+          sx[i] = fmaf(gi, (t[u][i] - mu[i]) * rs[i], sx[i]);
+        }
+    }
+    for (; row < hi; row += rpp) {
       float t[V], g[V];
       Vec<T>::ld(x + row * ldx + c0 + v, t);
       Vec<T>::ld(dy + row * ld_dy + v, g);
@@ -236,11 +279,14 @@ __global__ void __launch_bounds__(kThreads) bn_relu_bwd_reduce_kernel(const T* _
 }
 
 __global__ void bn_relu_bwd_final_kernel(const float* __restrict__ ws, int blocks, int c, float* __restrict__ out) {
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < 2 * c; j += gridDim.x * blockDim.x) {
-    double a = 0.0;
-    for (int b = 0; b < blocks; ++b) a += ws[(long)b * 2 * c + j];
-    out[j] = (float)a;
-  }
+  const int lane = threadIdx.x & 31;
+  const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // one warp per output
+  if (j >= 2 * c) return;
+  double a = 0.0;
+  for (int b = lane; b < blocks; b += 32) a += ws[(long)b * 2 * c + j];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if (lane == 0) out[j] = (float)a;
 }
 
 // backward, pass 2: dx = gamma*rstd * (g - mean(g) - xhat * mean(g*xhat)), written or accumulated into a window
@@ -266,23 +312,45 @@ __global__ void __launch_bounds__(kThreads) bn_relu_bwd_apply_kernel(const T* __
     mx[i] = sums[v + i] * inv_count;       // mean of g * xhat
     mg[i] = sums[c + v + i] * inv_count;   // mean of g
   }
-  for (long row = (long)blockIdx.x * rpp + r; row < rows; row += (long)gridDim.x * rpp) {
-    float o[V];
-    T* dst = dx + row * ld_dx + c0_dx + v;
-    if (pad) {
+  const long stride = (long)gridDim.x * rpp;
+  long row = (long)blockIdx.x * rpp + r;
+  if (pad) {
+    float z[V];
 #pragma unroll
-      for (int i = 0; i < V; ++i) o[i] = 0.f;
-    } else {
-      float t[V], g[V];
-      Vec<T>::ld(x + row * ldx + c0 + v, t);
-      Vec<T>::ld(dy + row * ld_dy + v, g);
-      if (accumulate) Vec<T>::ld(dst, o);
+    for (int i = 0; i < V; ++i) z[i] = 0.f;
+    for (; row < rows; row += stride) Vec<T>::st(dx + row * ld_dx + c0_dx + v, z);
+    return;
+  }
+  for (; row + stride < rows; row += 2 * stride) {   // two rows = four to six independent 16-byte loads in flight
+    float t[2][V], g[2][V], o[2][V];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      Vec<T>::ld(x + (row + u * stride) * ldx + c0 + v, t[u]);
+      Vec<T>::ld(dy + (row + u * stride) * ld_dy + v, g[u]);
+      if (accumulate) Vec<T>::ld(dx + (row + u * stride) * ld_dx + c0_dx + v, o[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
 #pragma unroll
       for (int i = 0; i < V; ++i) {
-        const float gi = fmaf(t[i], sc[i], sh[i]) > 0.f ? g[i] : 0.f;
-        const float d = sc[i] * (gi - mg[i] - (t[i] - mu[i]) * rs[i] * mx[i]);
-        o[i] = accumulate ? o[i] + d : d;
+        const float gi = fmaf(t[u][i], sc[i], sh[i]) > 0.f ? g[u][i] : 0.f;
+        const float d = sc[i] * (gi - mg[i] - (t[u][i] - mu[i]) * rs[i] * mx[i]);
+        o[u][i] = accumulate ? o[u][i] + d : d;
       }
+      Vec<T>::st(dx + (row + u * stride) * ld_dx + c0_dx + v, o[u]);
+    }
+  }
+  for (; row < rows; row += stride) {
+    float t[V], g[V], o[V];
+    T* dst = dx + row * ld_dx + c0_dx + v;
+    Vec<T>::ld(x + row * ldx + c0 + v, t);
+    Vec<T>::ld(dy + row * ld_dy + v, g);
+    if (accumulate) Vec<T>::ld(dst, o);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float gi = fmaf(t[i], sc[i], sh[i]) > 0.f ? g[i] : 0.f;
+      const float d = sc[i] * (gi - mg[i] - (t[i] - mu[i]) * rs[i] * mx[i]);
+      o[i] = accumulate ? o[i] + d : d;
     }
     Vec<T>::st(dst, o);
   }
@@ -442,7 +510,7 @@ extern "C" int vsr_bn_stats(const void* x, int32_t dtype, int32_t ldx, int32_t c
     bn_stats_kernel<T><<<frames * bpf, kThreads, smem, s>>>((const T*)x, ldx, c0, c, rows_per_frame, bpf, ws);
   })
   VSR_CHECK_LAUNCH("vsr_bn_stats");
-  bn_stats_final_kernel<<<grid_for((long)frames * 2 * c, 256), 256, 0, s>>>(ws, frames, bpf, c, stats, ld_stats, s0);
+  bn_stats_final_kernel<<<(frames * 2 * c + 7) / 8, 256, 0, s>>>(ws, frames, bpf, c, stats, ld_stats, s0);
   VSR_CHECK_LAUNCH("vsr_bn_stats_final");
   return VSR_OK;
 }
@@ -499,7 +567,7 @@ extern "C" int vsr_bn_relu_bwd(const void* dy, int32_t ld_dy, const void* x, int
     bn_relu_bwd_reduce_kernel<T><<<blocks, kThreads, smem, s>>>((const T*)dy, ld_dy, (const T*)x, ldx, c0, c, rows,
                                                                 scale_shift, cp, mean_rstd, ws);
     VSR_CHECK_LAUNCH("vsr_bn_relu_bwd_reduce");
-    bn_relu_bwd_final_kernel<<<(2 * c + 127) / 128, 128, 0, s>>>(ws, blocks, c, dgamma_dbeta);
+    bn_relu_bwd_final_kernel<<<(2 * c + 7) / 8, 256, 0, s>>>(ws, blocks, c, dgamma_dbeta);
     VSR_CHECK_LAUNCH("vsr_bn_relu_bwd_final");
     const int rpp2 = kThreads / (cp_dx / Vec<T>::V);
     bn_relu_bwd_apply_kernel<T><<<grid_for(rows, rpp2 * 4), kThreads, 0, s>>>(

@@ -346,7 +346,7 @@ class DUFNet(BaseNet):
                         bn.momentum if bn.momentum is not None else BN_MOMENTUM, bn.running_mean, bn.running_var,
                         training, ss, mr)
         if training:
-            bn.num_batches_tracked += 1
+            self._nbt.append(bn.num_batches_tracked)
         return ss, mr
 
     def _forward(self, frames, save):
@@ -361,6 +361,7 @@ class DUFNet(BaseNet):
         cat = torch.zeros(T + 2, N, h, w, P.ccat, dtype=act, device=dev)    # frames 0 and T+1: temporal padding
         stats = torch.zeros(T, 2, P.ctot, dtype=torch.float64, device=dev)
         need_stats = self.training
+        self._nbt = []
         head = new(T, 64)
         ops.conv3x3_first(x, self._pview(self.flat, "head.weight"), self._pview(self.flat, "head.bias"), None, m4(head))
         ops.copy_window(m4(head), 0, m4(cat[1:T + 1]), 0, 64)
@@ -412,6 +413,8 @@ class DUFNet(BaseNet):
         self._conv("r2", [m4(fr1)], m4(res))
         y = torch.empty(N, cin, h * P.r, w * P.r, dtype=self.flat.dtype, device=dev)
         ops.duf_filter(m4(logits), m4(res), centre.contiguous(), P.sf, P.r, y)
+        if self._nbt:
+            torch._foreach_add_(self._nbt, 1)                              # num_batches_tracked of all BatchNorms, one launch
         keep = (x, centre, cat, saved, sst, mrt, at, feat, fr1, logits) if save else None
         return y, keep
 

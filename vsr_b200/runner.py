@@ -277,6 +277,38 @@ class VSRTrainStep:
         return net._engine
 
 
+class MISRTrainStep(VSRTrainStep):
+    """The same fused step for the multi-image SR nets (reference: acdc_misr_trainer.py:8-50 — inputs are the
+    `num_frames` LR frames, the target ONE HR frame): DUFNet forward, fused loss, DUFNet backward into the flat
+    bucket, all-reduce, fused Adam, fused PSNR / SSIM; CUDA-graphed like the VSR step.  `targets` is a one-element
+    list.  Data parallel: every rank normalises with its own batch statistics (torch DDP's default; SyncBN is
+    not implemented)."""
+
+    def _device_fwd_bwd(self, inputs, targets):
+        net = self.net
+        net._pack(True)
+        y, saved = net._forward(inputs, True)
+        lvals, grads = self._loss([y], targets, True)
+        gflat = net._backward(saved, grads[0])
+        net.flat_grad = gflat
+        return lvals, [y], gflat
+
+    @torch.no_grad()
+    def eval_step(self, inputs, targets, acc=None):
+        net = self.net
+        if not net._is_flat():
+            net._flatten()
+        net._pack(False)
+        y, _ = net._forward([x.contiguous() for x in inputs], False)
+        targets = [t.contiguous() for t in targets]
+        lvals, _ = self._loss([y], targets, False)
+        if acc is not None:
+            self._log(acc, lvals)
+            if self.metric_names:
+                self._metrics([y], targets, acc)
+        return lvals, [y]
+
+
 class VSRTrainer:
     """Drop-in for AcdcVSRTrainer / Dsb15VSRTrainer (same constructor keywords; `dataset` selects
     the denormalisation constants, default 'acdc').  Under torchrun every rank runs this class on
