@@ -31,9 +31,37 @@ METRIC, UNIT = "hr_voxels_per_s_train_step", "HR voxels/s"
 FWD_FLOPS_PER_LR_PIXEL = 10.673e6
 
 
+# second workload (--workload duf): the Conv3d network of SURVEY §8 row a15, same contract
+DUF_MODEL = dict(in_channels=1, out_channels=1, num_frames=7, size_filter=5, upscale_factor=4, backbone="_DenseLayer16")
+WORKLOAD = "drf"
+
+
+def duf_fwd_flops_per_sample():
+    """algorithmic forward FLOPs of DUFNet-16 x4 per sample (7 frames of LR x LR): 2 * out pixels * Cout * Cin * taps"""
+    px, G, C = LR * LR, 32, [64 + 32 * i for i in range(7)]
+    total = 2.0 * px * 7 * 64 * 1 * 9
+    for i in range(6):
+        tin = 7 if i < 3 else 7 - 2 * (i - 3)
+        tout = tin if i < 3 else tin - 2
+        total += 2.0 * px * tin * C[i] * C[i] + 2.0 * px * tout * G * C[i] * 27
+    return total + 2.0 * px * (256 * 256 * 9 + 256 * 768 + 512 * 400 + 256 * 16)
+
+
 def workload_name(batch):
+    if WORKLOAD == "duf":
+        return (f"DUFNet-16 (Conv3d path) x4 train step, batch {batch} x 7 frames, LR {LR}x{LR} -> HR {4 * LR}x{4 * LR}, "
+                "L1 + Adam + PSNR/SSIM on training outputs")
     return (f"C2: DRFNet-L(F64,G6) x4 train step, batch {batch} x T{T}, LR {LR}x{LR} -> HR {4 * LR}x{4 * LR}, "
             "L1 + Adam + PSNR/SSIM on training outputs")
+
+
+def frames_in():
+    return 7 if WORKLOAD == "duf" else T
+
+
+def hr_voxels(batch):
+    """HR voxels produced per step: T frames per sequence (DRFNet), one centre frame per sequence (DUFNet)"""
+    return batch * (4 * LR) ** 2 * (1 if WORKLOAD == "duf" else T)
 
 
 def peaks():
@@ -97,15 +125,55 @@ def make_batches(n_batches, batch, seed, pinned):
     for _ in range(n_batches):
         hr = torch.rand(batch, 1, 4 * LR, 4 * LR, generator=g) * 255
         lrs, hrs = [], []
-        for t in range(T):
+        for t in range(frames_in()):
             f = (hr * (0.7 + 0.06 * t)).round().clamp(0, 255)
             l = torch.nn.functional.avg_pool2d(f, 4).round()
             hrs.append(((f - 54.089) / 48.084).contiguous())
             lrs.append(((l - 54.089) / 48.084).contiguous())
+        if WORKLOAD == "duf":
+            hrs = [hrs[3]]                       # the MISR target: the centre HR frame (acdc_misr_trainer.py:24)
         if pinned:
             lrs, hrs = [x.pin_memory() for x in lrs], [x.pin_memory() for x in hrs]
         out.append((lrs, hrs))
     return out
+
+
+def cpu_port(sample):
+    """the reference's algorithm (oracle/restated.py) as one training step on the host: returns (step fn, voxels)"""
+    from oracle import restated
+    torch.set_num_threads(os.cpu_count() or 1)      # torchrun pins OMP_NUM_THREADS=1: use every host core
+    torch.manual_seed(0)
+    lrs, hrs = make_batches(1, sample, 0, False)[0]
+    if WORKLOAD == "duf":
+        from vsr_b200.duf import DUFNet
+        net = DUFNet(**DUF_MODEL)            # parameter container only (same init as the reference class)
+        sd = {k: (v.detach().clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
+              for k, v in net.state_dict().items()}
+        opt = torch.optim.Adam([v for v in sd.values() if v.requires_grad], lr=1e-4)
+
+        def step():
+            out = restated.dufnet_forward(lrs, sd, 5, 4, training=True)
+            loss = restated.l1_loss(out, hrs[0])
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            restated.vsr_metrics([out.detach()], hrs)
+            return float(loss)
+    else:
+        from vsr_b200.nets import DRFNet
+        net = DRFNet(**MODEL)            # parameter container only (same init as the reference class)
+        sd = {k: v.detach().clone().requires_grad_(True) for k, v in net.state_dict().items()}
+        opt = torch.optim.Adam(list(sd.values()), lr=1e-4)
+
+        def step():
+            outs = restated.drfnet_forward(lrs, sd, 4)
+            loss = restated.vsr_loss(outs, hrs, restated.l1_loss)
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            restated.vsr_metrics([o.detach() for o in outs], hrs)
+            return float(loss)
+    return step, hr_voxels(sample)
 
 
 def run_reference(args):
@@ -115,25 +183,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import restated
-    from vsr_b200.nets import DRFNet
-    torch.set_num_threads(os.cpu_count() or 1)      # torchrun pins OMP_NUM_THREADS=1: use every host core
-    torch.manual_seed(0)
     sample = 2
-    net = DRFNet(**MODEL)            # parameter container only (same init as the reference class)
-    sd = {k: v.detach().clone().requires_grad_(True) for k, v in net.state_dict().items()}
-    opt = torch.optim.Adam(list(sd.values()), lr=1e-4)
-    lrs, hrs = make_batches(1, sample, 0, False)[0]
+    step, vox = cpu_port(sample)
     cores = torch.get_num_threads()
-
-    def step():
-        outs = restated.drfnet_forward(lrs, sd, 4)
-        loss = restated.vsr_loss(outs, hrs, restated.l1_loss)
-        opt.zero_grad()
-        loss.backward()
-        opt.step()
-        restated.vsr_metrics([o.detach() for o in outs], hrs)
-        return float(loss)
 
     for _ in range(args.warmup):
         step()
@@ -141,43 +193,30 @@ def run_reference(args):
     for _ in range(args.steps):
         step()
     dt = (time.perf_counter() - t0) / args.steps
-    vox = sample * T * (4 * LR) ** 2
     val = vox / dt
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(BATCH), "sample": f"{sample} of {BATCH} patches per step"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{sample} of {BATCH} patches x T{T} per step, torch {torch.__version__} CPU fp32"},
+                             "sample": f"{sample} of {BATCH} patches x T{frames_in()} per step, torch {torch.__version__} CPU fp32"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
 def cpu_baseline(budget_s=20.0):
     """oracle port timed on this box's host cores on a bounded sample (rank 0, N=1 only)."""
-    from oracle import restated
-    from vsr_b200.nets import DRFNet
-    torch.set_num_threads(os.cpu_count() or 1)
-    torch.manual_seed(0)
     sample = 2
-    net = DRFNet(**MODEL)
-    sd = {k: v.detach().clone().requires_grad_(True) for k, v in net.state_dict().items()}
-    opt = torch.optim.Adam(list(sd.values()), lr=1e-4)
-    lrs, hrs = make_batches(1, sample, 0, False)[0]
+    step, vox = cpu_port(sample)
     times = []
     t_start = time.perf_counter()
     while len(times) < 3 and (time.perf_counter() - t_start) < budget_s:
         t0 = time.perf_counter()
-        outs = restated.drfnet_forward(lrs, sd, 4)
-        loss = restated.vsr_loss(outs, hrs, restated.l1_loss)
-        opt.zero_grad()
-        loss.backward()
-        opt.step()
-        restated.vsr_metrics([o.detach() for o in outs], hrs)
+        step()
         times.append(time.perf_counter() - t0)
     dt = min(times)
-    return {"value": sample * T * (4 * LR) ** 2 / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{sample} of {BATCH} patches x T{T}, best of {len(times)} steps, torch {torch.__version__} CPU fp32"}
+    return {"value": vox / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{sample} of {BATCH} patches x T{frames_in()}, best of {len(times)} steps, torch {torch.__version__} CPU fp32"}
 
 
 def main():
@@ -189,8 +228,12 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="drf", choices=["drf", "duf"],
+                    help="drf = the headline (BASELINE configs[1], DRFNet-L); duf = the Conv3d network (DUFNet-16)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of one CUDA graph")
     args = ap.parse_args()
+    global WORKLOAD
+    WORKLOAD = args.workload
     if args.impl == "reference":
         run_reference(args)
         return
@@ -212,10 +255,16 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     torch.manual_seed(0)                               # identical initial weights on every rank
-    net = DRFNet(precision=args.precision, **MODEL).to(dev)
+    if WORKLOAD == "duf":
+        from vsr_b200.duf import DUFNet
+        from vsr_b200.runner import MISRTrainStep as StepCls
+        net = DUFNet(precision=args.precision, **DUF_MODEL).to(dev).train()
+    else:
+        StepCls = VSRTrainStep
+        net = DRFNet(precision=args.precision, **MODEL).to(dev)
     opt = FlatAdam(net.parameters(), lr=1e-4)
-    step = VSRTrainStep(net, [torch.nn.L1Loss()], [1.0], [PSNR().to(dev), SSIM().to(dev)], opt, "acdc",
-                        use_graph=not args.no_graph)
+    step = StepCls(net, [torch.nn.L1Loss()], [1.0], [PSNR().to(dev), SSIM().to(dev)], opt, "acdc",
+                   use_graph=not args.no_graph)
     ops = cuda_ops()
 
     n_host = 4
@@ -293,7 +342,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = t.tolist()
-    vox = world * args.batch * T * (4 * LR) ** 2
+    vox = world * hr_voxels(args.batch)
     value, value_e2e = vox / (ms * 1e-3), vox / (ms_e2e * 1e-3)
 
     if rank == 0:
@@ -314,7 +363,7 @@ def main():
         dom = max(agg, key=lambda k: agg[k][1])
         traffic = None
         try:       # per-launch dram__bytes_read+write of the same step under ncu (tools/ncu_summary.py)
-            with open(os.path.join(ROOT, "profiles", "r01_dram_by_kernel_v5.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "r01_duf_by_kernel_v2.json" if WORKLOAD == "duf" else "r01_dram_by_kernel_v5.json")) as f:
                 traffic = json.load(f).get({"tapgemm": "tapgemm_tc2_kernel", "wgrad": "wgrad_tc_kernel"}.get(dom, dom), {}).get("dram_bytes_per_launch")
         except (OSError, ValueError):
             pass
@@ -342,6 +391,8 @@ def main():
         frac_own = sum(r["ms_per_step"] * r["frac"] for r in all_rows) / max(t_all, 1e-9)
         hbm_share = sum(r["ms_per_step"] for r in all_rows if r["bound"] == "hbm") / max(t_all, 1e-9)
         step_flops = 3.0 * FWD_FLOPS_PER_LR_PIXEL * args.batch * T * LR * LR
+        if WORKLOAD == "duf":
+            step_flops = 3.0 * duf_fwd_flops_per_sample() * args.batch
         try:      # full per-shape table for the profile notes (scratch; the JSON line keeps the top 14)
             os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
             with open(os.path.join(ROOT, "gpurun_out", "kernel_detail_full.json"), "w") as f:
@@ -352,9 +403,10 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args.batch), "per_gpu_batch": args.batch, "frames": T,
+            "config": {"workload": workload_name(args.batch), "per_gpu_batch": args.batch, "frames": frames_in(),
                        "parallelism": f"dp{world}", "cuda_graph": not args.no_graph,
-                       "l2": "per-step working set (~5 GB of activations) exceeds the 126 MB L2; inputs rotate over 4 batches"},
+                       "l2": ("per-step working set (~5 GB of activations) exceeds the 126 MB L2; inputs rotate over 4 batches" if WORKLOAD == "drf"
+                              else "per-step working set (~1.5 GB of activations and gradients) exceeds the 126 MB L2; inputs rotate over 4 batches")},
             "clocks": sampler.result(),
             "e2e": {"value": value_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e, "last_loss": last_loss},

@@ -298,6 +298,17 @@ int vsr_bn_stats(const void* x, int32_t dtype, int32_t ldx, int32_t c0, int32_t 
                  int64_t rows_per_frame, double* stats, int32_t ld_stats, int32_t s0, void* workspace,
                  size_t workspace_bytes, void* stream);
 
+/* Temporal shift-add.  In tensor-core mode the three temporal taps of a 3x3x3 growth convolution
+ * (duf_net.py:203,212) are computed as extra OUTPUT columns of one (1,3,3) tap-GEMM (N = 3*g instead of g: the
+ * A operand is read once for all three), z[frame][row][kt*g + co]; this kernel finishes the convolution:
+ *   out[f][row][c0_out + co] = bias[co] + sum_kt z[f + kt - t_pad][row][kt*g + co],  f < frames_out
+ * (t_pad = 1: padding (1,1,1), frames_out = frames_in; t_pad = 0: padding (0,1,1), frames_out = frames_in - 2),
+ * and, if stats != NULL, the per-frame BatchNorm statistics of the new slice exactly as vsr_bn_stats would
+ * (workspace >= vsr_bn_stats_workspace(frames_out, rows_per_frame, g)). */
+int vsr_tshift_add(const void* z, int32_t dtype, int32_t ldz, int32_t g, int32_t frames_in, int64_t rows_per_frame,
+                   int32_t t_pad, const float* bias, void* out, int32_t ld_out, int32_t c0_out, int32_t frames_out,
+                   double* stats, int32_t ld_stats, int32_t s0, void* workspace, size_t workspace_bytes, void* stream);
+
 /* One BatchNorm's affine map from the statistics of `frames` frames (training != 0: biased batch variance,
  * running_mean / running_var updated with `momentum` and the unbiased variance when non-NULL) or from the
  * running buffers (training == 0):  scale_shift = float[2][cp] {gamma*rstd, beta - mean*gamma*rstd}, zero

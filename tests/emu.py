@@ -271,6 +271,21 @@ class EmuOps:
         stats[:, 1, s0:s0 + c] = (v * v).sum(1)
         self.launches += 2
 
+    def tshift_add(self, z, g, frames_in, t_pad, bias, out, c0_out, frames_out, stats, s0, workspace):
+        ct = torch.float64 if z.dtype == torch.float64 else torch.float32
+        zf = z.reshape(frames_in, -1, z.shape[-1]).to(ct)
+        of = out.reshape(frames_out, -1, out.shape[-1])
+        for f in range(frames_out):
+            acc = bias.to(ct).expand(zf.shape[1], g).clone()
+            for kt in range(3):
+                fi = f + kt - t_pad
+                if 0 <= fi < frames_in:
+                    acc += zf[fi, :, kt * g:(kt + 1) * g]
+            of[f, :, c0_out:c0_out + g] = acc.to(out.dtype)
+        if stats is not None:
+            self.bn_stats(out, c0_out, g, frames_out, stats, s0, None)
+        self.launches += 2 if stats is not None else 1
+
     def bn_finalize(self, stats, s0, frames, rows_per_frame, c, gamma, beta, eps, momentum, running_mean,
                     running_var, training, scale_shift, mean_rstd):
         if training:

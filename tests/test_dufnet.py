@@ -180,6 +180,16 @@ def test_gpu_dense3d_kernels_match_emulation(dtype):
             res.append((gb, dx.float()))
         assert torch.allclose(res[0][0], res[1][0], rtol=1e-3, atol=1e-3)
         assert torch.allclose(res[0][1], res[1][1], **tol)
+    for t_pad, f_out in ((1, F), (0, F - 2)):                    # temporal shift-add (+ statistics of the new slice)
+        zz = torch.randn(F * N, h, w, 128, generator=g).to(dev).to(dtype)
+        bias = torch.randn(32, generator=g).to(dev)
+        o_a, o_b = torch.zeros(f_out * N, h, w, ld, dtype=dtype, device=dev), torch.zeros(f_out * N, h, w, ld, dtype=dtype, device=dev)
+        s_a, s_b = torch.zeros(f_out, 2, 200, dtype=torch.float64, device=dev), torch.zeros(f_out, 2, 200, dtype=torch.float64, device=dev)
+        ops.tshift_add(zz, 32, F, t_pad, bias, o_a, 64, f_out, s_a, 96, ws(ops.bn_stats_workspace(f_out, N * h * w, 32)))
+        emu.tshift_add(zz, 32, F, t_pad, bias, o_b, 64, f_out, s_b, 96, None)
+        assert torch.allclose(o_a.float(), o_b.float(), rtol=1e-2 if dtype == torch.bfloat16 else 1e-6, atol=1e-5)
+        assert float(o_a[..., :64].abs().max()) == 0 and float(o_a[..., 96:].abs().max()) == 0
+        assert torch.allclose(s_a, s_b, rtol=2e-2 if dtype == torch.bfloat16 else 1e-5, atol=0.5 if dtype == torch.bfloat16 else 1e-4)
     d_a = torch.zeros(F * N, h, w, 64, dtype=dtype, device=dev)
     ops.copy_window(x, c0, d_a, 16, 32)
     assert torch.equal(d_a[..., 16:48], x[..., c0:c0 + 32]) and float(d_a[..., :16].abs().max()) == 0

@@ -435,6 +435,71 @@ __global__ void __launch_bounds__(kThreads) duf_filter_bwd_kernel(const T* __res
   }
 }
 
+// ---- temporal shift-add: the three temporal taps of a 3x3x3 convolution computed as extra OUTPUT columns ----
+// z[frame][row][kt*G + co] holds the (1,3,3) convolution of frame `frame` with temporal slice kt of the kernel;
+//   out[f][row][c0_out + co] = bias[co] + sum_kt z[f + kt - t_pad][row][kt*G + co]   (frames outside: zero)
+// and, when ws != NULL, the per-frame sum / sum of squares of the stored values (BatchNorm statistics of the
+// new concat slice) as bn_stats_kernel leaves them.
+template <typename T>
+__global__ void __launch_bounds__(kThreads) tshift_add_kernel(const T* __restrict__ z, int ldz, int G, int frames_in,
+                                                              long rows_per_frame, int t_pad,
+                                                              const float* __restrict__ bias, T* __restrict__ out,
+                                                              int ld_out, int c0_out, int bpf, double* __restrict__ ws) {
+  constexpr int V = Vec<T>::V;
+  extern __shared__ double sm[];   // [rpp][2][G]
+  const int tpr = G / V, rpp = kThreads / tpr;
+  const int f = blockIdx.x / bpf, b = blockIdx.x % bpf;
+  const int r = threadIdx.x / tpr, v = (threadIdx.x % tpr) * V;
+  long lo, hi;
+  row_range(rows_per_frame, b, bpf, &lo, &hi);
+  float s[V], q[V], bs[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) { s[i] = q[i] = 0.f; bs[i] = bias ? bias[v + i] : 0.f; }
+  bool ok[3];
+#pragma unroll
+  for (int kt = 0; kt < 3; ++kt) ok[kt] = f + kt - t_pad >= 0 && f + kt - t_pad < frames_in;
+  for (long row = lo + r; row < hi; row += rpp) {
+    float acc[V], t[3][V];
+#pragma unroll
+    for (int kt = 0; kt < 3; ++kt)
+      if (ok[kt]) Vec<T>::ld(z + ((long)(f + kt - t_pad) * rows_per_frame + row) * ldz + kt * G + v, t[kt]);
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[i] = bs[i];
+#pragma unroll
+    for (int kt = 0; kt < 3; ++kt)
+      if (ok[kt]) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[i] += t[kt][i];
+      }
+    T* dst = out + ((long)f * rows_per_frame + row) * ld_out + c0_out + v;
+    Vec<T>::st(dst, acc);
+    if (ws) {
+      float rd[V];
+      if constexpr (sizeof(T) == 2) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) rd[i] = __bfloat162float(__float2bfloat16_rn(acc[i]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < V; ++i) rd[i] = acc[i];
+      }
+#pragma unroll
+      for (int i = 0; i < V; ++i) { s[i] += rd[i]; q[i] = fmaf(rd[i], rd[i], q[i]); }
+    }
+  }
+  if (!ws) return;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    sm[(r * 2 + 0) * G + v + i] = (double)s[i];
+    sm[(r * 2 + 1) * G + v + i] = (double)q[i];
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < 2 * G; j += kThreads) {
+    double a = 0.0;
+    for (int rr = 0; rr < rpp; ++rr) a += sm[rr * 2 * G + j];
+    ws[(long)blockIdx.x * 2 * G + j] = a;
+  }
+}
+
 int stats_bpf(int frames, long rows_per_frame) {
   long bpf = (rows_per_frame + 511) / 512;
   const long cap = (4L * num_sms() + frames - 1) / frames;
@@ -512,6 +577,35 @@ extern "C" int vsr_bn_stats(const void* x, int32_t dtype, int32_t ldx, int32_t c
   VSR_CHECK_LAUNCH("vsr_bn_stats");
   bn_stats_final_kernel<<<(frames * 2 * c + 7) / 8, 256, 0, s>>>(ws, frames, bpf, c, stats, ld_stats, s0);
   VSR_CHECK_LAUNCH("vsr_bn_stats_final");
+  return VSR_OK;
+}
+
+extern "C" int vsr_tshift_add(const void* z, int32_t dtype, int32_t ldz, int32_t g, int32_t frames_in,
+                              int64_t rows_per_frame, int32_t t_pad, const float* bias, void* out, int32_t ld_out,
+                              int32_t c0_out, int32_t frames_out, double* stats, int32_t ld_stats, int32_t s0,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+  VSR_CHECK_ARG(z && out && frames_in > 0 && frames_out > 0 && rows_per_frame > 0 && (t_pad == 0 || t_pad == 1),
+                "vsr_tshift_add: bad arguments");
+  VSR_CHECK_ARG(ldz >= 3 * g, "vsr_tshift_add: z holds 3*g columns");
+  VSR_CHECK_ARG(!stats || (workspace && workspace_bytes >= vsr_bn_stats_workspace(frames_out, rows_per_frame, g)),
+                "vsr_tshift_add: workspace too small");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int bpf = stats_bpf(frames_out, rows_per_frame);
+  double* ws = stats ? static_cast<double*>(workspace) : nullptr;
+  VSR_DISPATCH_DTYPE(dtype, "vsr_tshift_add", {
+    VSR_CHECK_ARG((window_ok<T>(ldz, 0, g) && window_ok<T>(ld_out, c0_out, g)),
+                  "vsr_tshift_add: windows must be 16-byte aligned (ldz %d ld_out %d c0 %d g %d)", ldz, ld_out, c0_out, g);
+    const int rpp = kThreads / (g / Vec<T>::V);
+    const size_t smem = (size_t)rpp * 2 * g * sizeof(double);
+    VSR_CHECK_SUPPORTED(smem <= 48 * 1024, "vsr_tshift_add: %d channels too wide", g);
+    tshift_add_kernel<T><<<frames_out * bpf, kThreads, smem, s>>>((const T*)z, ldz, g, frames_in, rows_per_frame, t_pad,
+                                                                 bias, (T*)out, ld_out, c0_out, bpf, ws);
+  })
+  VSR_CHECK_LAUNCH("vsr_tshift_add");
+  if (stats) {
+    bn_stats_final_kernel<<<(frames_out * 2 * g + 7) / 8, 256, 0, s>>>(ws, frames_out, bpf, g, stats, ld_stats, s0);
+    VSR_CHECK_LAUNCH("vsr_tshift_add_final");
+  }
   return VSR_OK;
 }
 

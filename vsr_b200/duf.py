@@ -48,6 +48,7 @@ class DufPlan(DrfPlan):
         self.ctot = self.C[-1]
         self.ccat = self.ctot + (64 - G if bf16 else 0)
         self.nt2 = 64 if bf16 else G
+        self.ntz = -(-3 * G // 64) * 64                          # tensor-core forward of the growth convolutions
         self.cf, self.cr = size_filter * size_filter * r * r, in_channels * r * r
         self.cfp, self.crp = self.pad(self.cf), self.pad(self.cr)
         self.params, self.n_params, self.fwd, self.bwd = {}, 0, {}, {}
@@ -141,6 +142,17 @@ class DufPlan(DrfPlan):
                             slabs.append(m(W2, j, b * kc + k, kt, ky, kx))
             self.fwd[f"c2_{i}"] = Layer(f"c2_{i}", TapTable(kc, self.nt2, [(C[i], taps)]), slabs, self.ccat,
                                         self._mbias(p + ".conv2", self.ccat, at=C[i]))
+            if self.bf16:
+                # tensor-core forward: the three temporal taps as extra output columns of a (1,3,3) tap-GEMM
+                # (N = 3G, A read once for all three), finished by vsr_tshift_add
+                j, k = self._jk(self.ntz)
+                taps, slabs = [], []
+                for ky in range(3):
+                    for kx in range(3):
+                        for b in range(cp // kc):
+                            taps.append((0, ky - 1, kx - 1, b * kc))
+                            slabs.append(m(W2, np.where(j < 3 * G, j % G, -1), b * kc + k, j // G, ky, kx))
+                self.fwd[f"c2z_{i}"] = Layer(f"c2z_{i}", TapTable(kc, self.ntz, [(0, taps)]), slabs, self.ntz, None)
             # its data gradient: sources 0..2 = the concat gradient seen through frame shifts +1, 0, -1
             splits = self._split(cp)
             nt = splits[0][1]
@@ -325,6 +337,9 @@ class DUFNet(BaseNet):
 
     def _conv(self, lname, srcs, out, epi=0, **kw):
         st, L = self._state(), self._plan.fwd[lname]
+        if L.bias_idx is None:
+            self._backend().tapgemm(L.table, srcs, out, st["fwd_w"][L.w_off:L.w_off + L.w_numel], epi=epi, **kw)
+            return
         self._backend().tapgemm(L.table, srcs, out, st["fwd_w"][L.w_off:L.w_off + L.w_numel],
                                 bias=st["fwd_b"][L.b_off:L.b_off + len(L.bias_idx)], epi=EPI_BIAS | epi, **kw)
 
@@ -393,10 +408,17 @@ class DUFNet(BaseNet):
                 views = [m4(cbuf[kt:kt + tout]) for kt in range(3)]
             ops.bn_relu(m4(b), 0, C[i], ss2, m4(c))
             out = m4(cat[1 + fo:1 + fo + tout])
-            self._conv(f"c2_{i}", views, out)
-            if need_stats:
-                ops.bn_stats(out, C[i], G, tout, stats[fo:fo + tout], C[i],
-                             self._ws("stats", ops.bn_stats_workspace(tout, rpf, G)))
+            if P.bf16:
+                z = new(tin, P.ntz)
+                self._conv(f"c2z_{i}", [m4(c)], m4(z))
+                ops.tshift_add(m4(z), G, tin, 1 if i < P.n1 else 0, self._pview(self.flat, pn + ".conv2.bias"), out, C[i],
+                               tout, stats[fo:fo + tout] if need_stats else None, C[i],
+                               self._ws("stats", ops.bn_stats_workspace(tout, rpf, G)) if need_stats else None)
+            else:
+                self._conv(f"c2_{i}", views, out)
+                if need_stats:
+                    ops.bn_stats(out, C[i], G, tout, stats[fo:fo + tout], C[i],
+                                 self._ws("stats", ops.bn_stats_workspace(tout, rpf, G)))
             saved.append((a, b, cbuf, ss1, mr1, ss2, mr2))
         f0, tin, _, _ = P.frames_of(P.L)
         ctp = P.pad(P.ctot)

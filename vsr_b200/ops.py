@@ -322,6 +322,16 @@ class CudaOps:
                                     workspace.numel() * workspace.element_size(), _stream()), "vsr_bn_stats")
         self.launches += 2
 
+    def tshift_add(self, z, g, frames_in, t_pad, bias, out, c0_out, frames_out, stats, s0, workspace):
+        """out[f, ..., c0_out + co] = bias[co] + sum_kt z[f + kt - t_pad, ..., kt*g + co] (+ the slice's BatchNorm statistics)"""
+        _need_cuda(z, bias, out, stats, workspace)
+        check(self.lib.vsr_tshift_add(_p(z), _DT[z.dtype], z.shape[-1], g, frames_in, self._rows(z) // frames_in, t_pad,
+                                      _p(bias), _p(out), out.shape[-1], c0_out, frames_out, _p(stats),
+                                      stats.shape[-1] if stats is not None else 0, s0, _p(workspace),
+                                      workspace.numel() * workspace.element_size() if workspace is not None else 0,
+                                      _stream()), "vsr_tshift_add")
+        self.launches += 2 if stats is not None else 1
+
     def bn_finalize(self, stats, s0, frames, rows_per_frame, c, gamma, beta, eps, momentum, running_mean,
                     running_var, training, scale_shift, mean_rstd):
         _need_cuda(stats, gamma, beta, running_mean, running_var, scale_shift, mean_rstd)
