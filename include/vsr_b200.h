@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define VSR_ABI_VERSION 3
+#define VSR_ABI_VERSION 4
 #define VSR_MAX_SRCS 8
 
 typedef enum VsrStatus {
@@ -324,14 +324,19 @@ int vsr_bn_relu(const void* x, int32_t dtype, int32_t ldx, int32_t c0, int32_t c
                 const float* scale_shift, int32_t cp, void* y, void* stream);
 
 /* Backward of the same (training mode): with g = dy where the forward output was positive, else 0, and
- * xhat = (x - mean) * rstd:  dgamma_dbeta = float[2][c] {sum g*xhat, sum g} (written),
- *   dx[row][c0_dx + j] (+)= gamma*rstd * (g - mean(g) - xhat * mean(g*xhat)),  zero for c <= j < cp_dx when
- * not accumulating.  dy is [rows][ld_dy] (channels [0, c)).  Two passes, fixed summation order. */
+ * xhat = (x - mean) * rstd:
+ *   phase & 1:  dgamma_dbeta = float[2][c] {sum g*xhat, sum g} over this call's rows (written; two passes, fixed order)
+ *   phase & 2:  dx[row][c0_dx + j] (+)= gamma*rstd * (g - S_g/count - xhat * S_gx/count), zero for c <= j < cp_dx when
+ *               not accumulating; {S_gx, S_g} = `sums` (float[2][c]; NULL = dgamma_dbeta), count <= 0 = rows.
+ * phase 3 is the single-device backward.  With synchronised BatchNorm across ranks the caller runs phase 1, sums
+ * dgamma_dbeta over the ranks (NCCL) into `sums`, then phase 2 with count = rows of all ranks.
+ * dy is [rows][ld_dy] (channels [0, c)). */
 size_t vsr_bn_relu_bwd_workspace(int64_t rows, int32_t c);
 int vsr_bn_relu_bwd(const void* dy, int32_t ld_dy, const void* x, int32_t dtype, int32_t ldx, int32_t c0,
                     int32_t c, int64_t rows, const float* scale_shift, int32_t cp, const float* mean_rstd,
                     float* dgamma_dbeta, void* dx, int32_t ld_dx, int32_t c0_dx, int32_t cp_dx, int accumulate,
-                    void* workspace, size_t workspace_bytes, void* stream);
+                    int32_t phase, const float* sums, int64_t count, void* workspace, size_t workspace_bytes,
+                    void* stream);
 
 /* Dynamic-upsampling-filter tail (duf_net.py:66-97): logits [n*h*w][ld_logits] with channel k*r*r + p
  * (k = tap of the size_filter^2 window, p = sub-pixel), softmax over k, applied to the neighbourhood of the

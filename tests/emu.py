@@ -319,7 +319,8 @@ class EmuOps:
     def bn_relu_bwd_workspace(self, rows, c):
         return 16
 
-    def bn_relu_bwd(self, dy, x, c0, c, scale_shift, mean_rstd, dgamma_dbeta, dx, c0_dx, cp_dx, accumulate, workspace):
+    def bn_relu_bwd(self, dy, x, c0, c, scale_shift, mean_rstd, dgamma_dbeta, dx, c0_dx, cp_dx, accumulate, workspace,
+                    phase=3, sums=None, count=0):
         ct = torch.float64 if x.dtype == torch.float64 else torch.float32
         xv = x[..., c0:c0 + c].to(ct)
         sc, sh = scale_shift[0, :c].to(ct), scale_shift[1, :c].to(ct)
@@ -327,17 +328,19 @@ class EmuOps:
         g = torch.where(xv * sc + sh > 0, dy[..., :c].to(ct), torch.zeros((), dtype=ct, device=x.device))
         xhat = (xv - mu) * rs
         red = tuple(range(xv.dim() - 1))
-        sx, sg = (g * xhat).sum(red), g.sum(red)
-        dgamma_dbeta.view(2, c)[0] = sx.to(dgamma_dbeta.dtype)
-        dgamma_dbeta.view(2, c)[1] = sg.to(dgamma_dbeta.dtype)
-        n = xv.numel() // c
-        d = sc * (g - sg / n - xhat * (sx / n))
-        if accumulate:
-            dx[..., c0_dx:c0_dx + c] += d.to(dx.dtype)
-        else:
-            dx[..., c0_dx:c0_dx + cp_dx] = 0
-            dx[..., c0_dx:c0_dx + c] = d.to(dx.dtype)
-        self.launches += 3
+        if phase & 1:
+            dgamma_dbeta.view(2, c)[0] = (g * xhat).sum(red).to(dgamma_dbeta.dtype)
+            dgamma_dbeta.view(2, c)[1] = g.sum(red).to(dgamma_dbeta.dtype)
+        if phase & 2:
+            sv = (dgamma_dbeta if sums is None else sums).view(2, c).to(ct)
+            n = count if count > 0 else xv.numel() // c
+            d = sc * (g - sv[1] / n - xhat * (sv[0] / n))
+            if accumulate:
+                dx[..., c0_dx:c0_dx + c] += d.to(dx.dtype)
+            else:
+                dx[..., c0_dx:c0_dx + cp_dx] = 0
+                dx[..., c0_dx:c0_dx + c] = d.to(dx.dtype)
+        self.launches += (2 if phase & 1 else 0) + (1 if phase & 2 else 0)
 
     @staticmethod
     def _duf_apply(logits, res, x, sf, r):

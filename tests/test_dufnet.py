@@ -180,6 +180,14 @@ def test_gpu_dense3d_kernels_match_emulation(dtype):
             res.append((gb, dx.float()))
         assert torch.allclose(res[0][0], res[1][0], rtol=1e-3, atol=1e-3)
         assert torch.allclose(res[0][1], res[1][1], **tol)
+        # the two phases apart (synchronised BatchNorm runs an all-reduce between them) = the fused call
+        gb2 = torch.zeros(2 * c, device=dev)
+        dx2 = torch.ones(2 * N, h, w, ld, dtype=dtype, device=dev)
+        wsp = ws(ops.bn_relu_bwd_workspace(2 * N * h * w, c))
+        ops.bn_relu_bwd(dy, xs, c0, c, ss, mr, gb2, None, 0, c, False, wsp, phase=1)
+        ops.bn_relu_bwd(dy, xs, c0, c, ss, mr, gb2, dx2, 16, c if acc else 112, acc, wsp, phase=2, sums=gb2.clone(),
+                        count=2 * N * h * w)
+        assert torch.equal(gb2, res[0][0]) and torch.equal(dx2.float(), res[0][1])
     for t_pad, f_out in ((1, F), (0, F - 2)):                    # temporal shift-add (+ statistics of the new slice)
         zz = torch.randn(F * N, h, w, 128, generator=g).to(dev).to(dtype)
         bias = torch.randn(32, generator=g).to(dev)
@@ -210,3 +218,52 @@ def test_gpu_dense3d_kernels_match_emulation(dtype):
         emu.duf_filter_bwd(lg, img, gy, sf, r, gb_[0], gb_[1])
         for a, b in zip(ga, gb_):
             assert torch.allclose(a.float(), b.float(), **tol)
+
+
+# ---- data parallelism with synchronised BatchNorm, two gloo ranks on CPU through the emulation ----
+def _sync_worker(rank, world, port, path, ret):
+    import torch.distributed as dist
+    from vsr_b200.metrics import PSNR
+    from vsr_b200.optim import FlatAdam
+    from vsr_b200.runner import MISRTrainStep
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    fx = torch.load(path)
+    net = DUFNet(**fx["kwargs"])
+    net.load_state_dict(_state(fx))
+    net._ops = EmuOps()
+    net.train()
+    opt = FlatAdam(net.parameters(), lr=1e-3)
+    step = MISRTrainStep(net, [torch.nn.L1Loss()], [1.0], [PSNR()], opt, "acdc")
+    n = fx["inputs"][0].shape[0] // world
+    sl = slice(rank * n, (rank + 1) * n)
+    lv, outs = step.train_step([f[sl] for f in fx["inputs"]], [fx["target"][sl]])
+    if rank == 0:
+        ret["out"], ret["grad"] = outs[0].detach().clone(), net.flat_grad.detach().clone() / world
+        ret["rm"] = net.denseLayer.tail.bn.running_mean.clone()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_ranks_sync_bn_equal_one_rank_on_the_whole_batch():
+    import torch.multiprocessing as mp
+    from vsr_b200.metrics import PSNR
+    from vsr_b200.optim import FlatAdam
+    from vsr_b200.runner import MISRTrainStep
+    path = [p for p in CASES if p.endswith("dufnet16_x4.pt")][0]          # batch of 2
+    fx = torch.load(path)
+    net = DUFNet(**fx["kwargs"])
+    net.load_state_dict(_state(fx))
+    net._ops = EmuOps()
+    net.train()
+    step = MISRTrainStep(net, [torch.nn.L1Loss()], [1.0], [PSNR()], FlatAdam(net.parameters(), lr=1e-3), "acdc")
+    _, outs = step.train_step(fx["inputs"], [fx["target"]])
+    ret = mp.Manager().dict()
+    mp.spawn(_sync_worker, args=(2, 29500 + os.getpid() % 2000, path, ret), nprocs=2, join=True)
+    assert _rel(ret["out"], outs[0][:1].detach()) <= 1e-5                 # rank 0's half of the batch
+    # the all-reduced gradient (mean over ranks) equals the whole-batch gradient.  (Parameters after the Adam step are
+    # not compared: the convolution biases in front of a BatchNorm have zero gradient up to round-off, and Adam's
+    # first step moves them by lr * sign(noise).)
+    assert float((ret["grad"] - net.flat_grad).abs().max()) <= 1e-5 * float(net.flat_grad.abs().max())
+    assert float((ret["rm"] - net.denseLayer.tail.bn.running_mean).abs().max()) <= 1e-6

@@ -114,7 +114,8 @@ _SIGS = {
     "vsr_bn_relu_bwd_workspace": (C.c_size_t, [C.c_int64, C.c_int32]),
     "vsr_bn_relu_bwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                   C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
-                                  C.c_int32, C.c_int32, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+                                  C.c_int32, C.c_int32, C.c_int, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t,
+                                  C.c_void_p]),
     "vsr_duf_filter": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p] +
                        [C.c_int32] * 6 + [C.c_void_p, C.c_void_p]),
     "vsr_duf_filter_bwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p] + [C.c_int32] * 6 +
@@ -144,7 +145,7 @@ def lib():
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
-        if handle.vsr_abi_version() != 3:
+        if handle.vsr_abi_version() != 4:
             raise VsrError("libvsr_sm100.so ABI version mismatch")
         _lib = handle
     return _lib

@@ -645,30 +645,41 @@ extern "C" size_t vsr_bn_relu_bwd_workspace(int64_t rows, int32_t c) {
 extern "C" int vsr_bn_relu_bwd(const void* dy, int32_t ld_dy, const void* x, int32_t dtype, int32_t ldx, int32_t c0,
                                int32_t c, int64_t rows, const float* scale_shift, int32_t cp, const float* mean_rstd,
                                float* dgamma_dbeta, void* dx, int32_t ld_dx, int32_t c0_dx, int32_t cp_dx,
-                               int accumulate, void* workspace, size_t workspace_bytes, void* stream) {
-  VSR_CHECK_ARG(dy && x && dx && scale_shift && mean_rstd && dgamma_dbeta && rows > 0, "vsr_bn_relu_bwd: bad arguments");
-  VSR_CHECK_ARG(cp >= c && cp_dx >= c && !(accumulate && cp_dx != c), "vsr_bn_relu_bwd: bad channel counts");
-  VSR_CHECK_ARG(workspace && workspace_bytes >= vsr_bn_relu_bwd_workspace(rows, c), "vsr_bn_relu_bwd: workspace too small");
+                               int accumulate, int32_t phase, const float* sums, int64_t count, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+  VSR_CHECK_ARG(dy && x && scale_shift && mean_rstd && rows > 0, "vsr_bn_relu_bwd: bad arguments");
+  VSR_CHECK_ARG(phase >= 1 && phase <= 3, "vsr_bn_relu_bwd: phase must be 1 (sums), 2 (dx) or 3 (both)");
+  VSR_CHECK_ARG(!(phase & 1) || (dgamma_dbeta && workspace && workspace_bytes >= vsr_bn_relu_bwd_workspace(rows, c)),
+                "vsr_bn_relu_bwd: sums need dgamma_dbeta and a workspace");
+  VSR_CHECK_ARG(!(phase & 2) || (dx && (sums || dgamma_dbeta) && cp_dx >= c && !(accumulate && cp_dx != c)),
+                "vsr_bn_relu_bwd: dx needs an output window and the sums");
+  VSR_CHECK_ARG(cp >= c, "vsr_bn_relu_bwd: bad channel counts");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int blocks = reduce_blocks(rows);
   float* ws = static_cast<float*>(workspace);
+  if (!sums) sums = dgamma_dbeta;
+  if (count <= 0) count = rows;
   VSR_DISPATCH_DTYPE(dtype, "vsr_bn_relu_bwd", {
-    VSR_CHECK_ARG((window_ok<T>(ldx, c0, c) && window_ok<T>(ld_dy, 0, c) && window_ok<T>(ld_dx, c0_dx, cp_dx)),
-                  "vsr_bn_relu_bwd: windows must be 16-byte aligned");
-    const int rpp = kThreads / (c / Vec<T>::V);
-    const size_t smem = (size_t)rpp * 2 * c * sizeof(float);
-    VSR_CHECK_SUPPORTED(smem <= 48 * 1024, "vsr_bn_relu_bwd: window of %d channels too wide", c);
-    bn_relu_bwd_reduce_kernel<T><<<blocks, kThreads, smem, s>>>((const T*)dy, ld_dy, (const T*)x, ldx, c0, c, rows,
-                                                                scale_shift, cp, mean_rstd, ws);
-    VSR_CHECK_LAUNCH("vsr_bn_relu_bwd_reduce");
-    bn_relu_bwd_final_kernel<<<(2 * c + 7) / 8, 256, 0, s>>>(ws, blocks, c, dgamma_dbeta);
-    VSR_CHECK_LAUNCH("vsr_bn_relu_bwd_final");
-    const int rpp2 = kThreads / (cp_dx / Vec<T>::V);
-    bn_relu_bwd_apply_kernel<T><<<grid_for(rows, rpp2 * 4), kThreads, 0, s>>>(
-        (const T*)dy, ld_dy, (const T*)x, ldx, c0, c, rows, scale_shift, cp, mean_rstd, dgamma_dbeta,
-        (float)(1.0 / (double)rows), (T*)dx, ld_dx, c0_dx, cp_dx, accumulate);
+    VSR_CHECK_ARG((window_ok<T>(ldx, c0, c) && window_ok<T>(ld_dy, 0, c)), "vsr_bn_relu_bwd: windows must be 16-byte aligned");
+    if (phase & 1) {
+      const int rpp = kThreads / (c / Vec<T>::V);
+      const size_t smem = (size_t)rpp * 2 * c * sizeof(float);
+      VSR_CHECK_SUPPORTED(smem <= 48 * 1024, "vsr_bn_relu_bwd: window of %d channels too wide", c);
+      bn_relu_bwd_reduce_kernel<T><<<blocks, kThreads, smem, s>>>((const T*)dy, ld_dy, (const T*)x, ldx, c0, c, rows,
+                                                                  scale_shift, cp, mean_rstd, ws);
+      VSR_CHECK_LAUNCH("vsr_bn_relu_bwd_reduce");
+      bn_relu_bwd_final_kernel<<<(2 * c + 7) / 8, 256, 0, s>>>(ws, blocks, c, dgamma_dbeta);
+      VSR_CHECK_LAUNCH("vsr_bn_relu_bwd_final");
+    }
+    if (phase & 2) {
+      VSR_CHECK_ARG(window_ok<T>(ld_dx, c0_dx, cp_dx), "vsr_bn_relu_bwd: dx window must be 16-byte aligned");
+      const int rpp2 = kThreads / (cp_dx / Vec<T>::V);
+      bn_relu_bwd_apply_kernel<T><<<grid_for(rows, rpp2 * 4), kThreads, 0, s>>>(
+          (const T*)dy, ld_dy, (const T*)x, ldx, c0, c, rows, scale_shift, cp, mean_rstd, sums,
+          (float)(1.0 / (double)count), (T*)dx, ld_dx, c0_dx, cp_dx, accumulate);
+      VSR_CHECK_LAUNCH("vsr_bn_relu_bwd_apply");
+    }
   })
-  VSR_CHECK_LAUNCH("vsr_bn_relu_bwd_apply");
   return VSR_OK;
 }
 

@@ -19,6 +19,7 @@ output tiles whose upper half lands on the not-yet-written slices of the followi
 """
 import numpy as np
 import torch
+import torch.distributed as dist
 import torch.nn as nn
 
 from ._lib import EPI_BIAS, EPI_RELU, EPI_RELU_BWD
@@ -268,7 +269,16 @@ class DUFNet(BaseNet):
         self._ops = None          # tests may set an emulated backend here; the product uses CudaOps
         self._dev_state = None
         self.flat = self.flat_grad = None
+        self._sync_group, self._sync_world = None, 1
         self._flatten()
+
+    def enable_sync_bn(self, process_group=None):
+        """Synchronised BatchNorm for data parallelism: every BatchNorm3d normalises with the
+        statistics of the GLOBAL batch — one small all-reduce of {sum, sum of squares} per BatchNorm in forward and
+        of {sum g*xhat, sum g} in backward — so N ranks with batch B reproduce one device with batch N*B."""
+        self._sync_group = process_group
+        self._sync_world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        return self
 
     # ---- flat parameter bucket (same scheme as the DRF nets) ----
     def _flatten(self):
@@ -356,6 +366,10 @@ class DUFNet(BaseNet):
         if self.flat.dtype == torch.float64:
             ss, mr = ss.double(), mr.double()
         training = self.training                     # nn.BatchNorm3d(track_running_stats=True): batch statistics when training
+        if training and self._sync_world > 1:
+            stats = stats[:frames, :, s0:s0 + c].sum(0, keepdim=True).contiguous()     # this rank's sums, [1, 2, c]
+            dist.all_reduce(stats, group=self._sync_group)
+            s0, frames, rows_per_frame = 0, 1, frames * rows_per_frame * self._sync_world
         ops.bn_finalize(stats if training else None, s0, frames, rows_per_frame, c,
                         self._pview(self.flat, pname + ".weight"), self._pview(self.flat, pname + ".bias"), bn.eps,
                         bn.momentum if bn.momentum is not None else BN_MOMENTUM, bn.running_mean, bn.running_var,
@@ -463,8 +477,17 @@ class DUFNet(BaseNet):
 
         def bn_bwd(pname, dyv, xv, c, ss, mr, dxv, c0_dx, cp_dx, accumulate):
             pw = P.params[pname + ".weight"]                                # weight then bias: adjacent in the bucket
-            ops.bn_relu_bwd(dyv, xv, 0, c, ss, mr, gflat[pw.offset:pw.offset + 2 * c], dxv, c0_dx, cp_dx, accumulate,
-                            self._ws("bnbwd", ops.bn_relu_bwd_workspace(xv.numel() // xv.shape[-1], c)))
+            rows = xv.numel() // xv.shape[-1]
+            ws = self._ws("bnbwd", ops.bn_relu_bwd_workspace(rows, c))
+            gsl = gflat[pw.offset:pw.offset + 2 * c]
+            if self._sync_world > 1:                                        # synchronised BatchNorm: global sums for dx
+                ops.bn_relu_bwd(dyv, xv, 0, c, ss, mr, gsl, None, 0, c, False, ws, phase=1)
+                tot = gsl.clone()
+                dist.all_reduce(tot, group=self._sync_group)
+                ops.bn_relu_bwd(dyv, xv, 0, c, ss, mr, gsl, dxv, c0_dx, cp_dx, accumulate, ws, phase=2, sums=tot,
+                                count=rows * self._sync_world)
+            else:
+                ops.bn_relu_bwd(dyv, xv, 0, c, ss, mr, gsl, dxv, c0_dx, cp_dx, accumulate, ws)
 
         f0, tin, _, _ = P.frames_of(P.L)
         dlogits, dres = new(tin, P.cfp), new(tin, P.crp)

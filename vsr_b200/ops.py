@@ -350,13 +350,17 @@ class CudaOps:
     def bn_relu_bwd_workspace(self, rows, c):
         return self.lib.vsr_bn_relu_bwd_workspace(rows, c)
 
-    def bn_relu_bwd(self, dy, x, c0, c, scale_shift, mean_rstd, dgamma_dbeta, dx, c0_dx, cp_dx, accumulate, workspace):
-        _need_cuda(dy, x, scale_shift, mean_rstd, dgamma_dbeta, dx, workspace)
+    def bn_relu_bwd(self, dy, x, c0, c, scale_shift, mean_rstd, dgamma_dbeta, dx, c0_dx, cp_dx, accumulate, workspace,
+                    phase=3, sums=None, count=0):
+        """phase 1: dgamma_dbeta = {sum g*xhat, sum g} of this rank's rows; phase 2: dx from `sums` (default
+        dgamma_dbeta) over `count` rows (default: this call's); 3: both (single device)."""
+        _need_cuda(dy, x, scale_shift, mean_rstd, dgamma_dbeta, dx, workspace, sums)
         check(self.lib.vsr_bn_relu_bwd(_p(dy), dy.shape[-1], _p(x), _DT[x.dtype], x.shape[-1], c0, c, self._rows(x),
                                        _p(scale_shift), scale_shift.shape[-1], _p(mean_rstd), _p(dgamma_dbeta),
-                                       _p(dx), dx.shape[-1], c0_dx, cp_dx, int(accumulate), _p(workspace),
+                                       _p(dx), dx.shape[-1] if dx is not None else 0, c0_dx, cp_dx, int(accumulate),
+                                       phase, _p(sums), int(count), _p(workspace),
                                        workspace.numel() * workspace.element_size(), _stream()), "vsr_bn_relu_bwd")
-        self.launches += 3
+        self.launches += (2 if phase & 1 else 0) + (1 if phase & 2 else 0)
 
     def duf_filter(self, logits, res, x, size_filter, r, y):
         _need_cuda(logits, res, x, y)

@@ -281,8 +281,16 @@ class MISRTrainStep(VSRTrainStep):
     """The same fused step for the multi-image SR nets (reference: acdc_misr_trainer.py:8-50 — inputs are the
     `num_frames` LR frames, the target ONE HR frame): DUFNet forward, fused loss, DUFNet backward into the flat
     bucket, all-reduce, fused Adam, fused PSNR / SSIM; CUDA-graphed like the VSR step.  `targets` is a one-element
-    list.  Data parallel: every rank normalises with its own batch statistics (torch DDP's default; SyncBN is
-    not implemented)."""
+    list.  Data parallel: `sync_bn=True` (default) synchronises every BatchNorm over the ranks (DUFNet.enable_sync_bn),
+    so G ranks with batch B reproduce one device with batch G*B; `sync_bn=False` = rank-local statistics (torch DDP's
+    default), which keeps the step inside one CUDA graph."""
+
+    def __init__(self, net, loss_fns, loss_weights, metric_fns, optimizer, dataset="acdc", process_group=None,
+                 use_graph=False, sync_bn=True):
+        super().__init__(net, loss_fns, loss_weights, metric_fns, optimizer, dataset, process_group, use_graph)
+        if self.world > 1 and sync_bn:
+            net.enable_sync_bn(process_group)
+            self.use_graph = False          # the BatchNorm all-reduces sit inside forward / backward: launched eagerly
 
     def _device_fwd_bwd(self, inputs, targets):
         net = self.net
