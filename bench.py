@@ -404,7 +404,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": workload_name(args.batch), "per_gpu_batch": args.batch, "frames": frames_in(),
-                       "parallelism": f"dp{world}", "cuda_graph": not args.no_graph,
+                       "parallelism": f"dp{world}", "cuda_graph": bool(step.use_graph),
                        "l2": ("per-step working set (~5 GB of activations) exceeds the 126 MB L2; inputs rotate over 4 batches" if WORKLOAD == "drf"
                               else "per-step working set (~1.5 GB of activations and gradients) exceeds the 126 MB L2; inputs rotate over 4 batches")},
             "clocks": sampler.result(),
