@@ -267,3 +267,27 @@ def test_two_ranks_sync_bn_equal_one_rank_on_the_whole_batch():
     # first step moves them by lr * sign(noise).)
     assert float((ret["grad"] - net.flat_grad).abs().max()) <= 1e-5 * float(net.flat_grad.abs().max())
     assert float((ret["rm"] - net.denseLayer.tail.bn.running_mean).abs().max()) <= 1e-6
+
+
+def test_misr_trainer_epoch_on_cpu():
+    """MISRTrainer = AcdcMISRTrainer's epoch loop (base_trainer.py:99-144) over the synthetic MISR dataset
+    (acdc_misr_dataset.py contract), through the emulation: the log has the reference's keys and the loss falls."""
+    from vsr_b200.data import Dataloader, SyntheticCineDataset
+    from vsr_b200.metrics import PSNR, SSIM
+    from vsr_b200.optim import FlatAdam
+    from vsr_b200.runner import MISRTrainer
+    ds = SyntheticCineDataset(4, num_frames=7, temporal_order="middle", type="train", num_sequences=1, patch_size=(12, 12),
+                              misr=True)
+    item = ds[3]
+    assert len(item["lr_imgs"]) == 7 and item["lr_imgs"][0].shape == (1, 12, 12) and item["hr_img"].shape == (1, 48, 48)
+    ds.data = ds.data[:4]
+    loader = Dataloader(ds, batch_size=2, pin_memory=False)
+    net = DUFNet(1, 1, 7, 5, 4, "_DenseLayer16")
+    net._ops = EmuOps()
+    tr = MISRTrainer("cpu", loader, loader, net, [torch.nn.L1Loss()], [1.0], [PSNR(), SSIM()],
+                     FlatAdam(net.parameters(), lr=2e-3), None, None, None, 1)
+    logs = [tr._run_epoch("training")[0] for _ in range(3)]
+    assert list(logs[0]) == ["Loss", "L1Loss", "PSNR", "SSIM"]
+    assert logs[2]["Loss"] < logs[0]["Loss"]
+    vlog, _, out = tr._run_epoch("validation")
+    assert out.shape == (2, 1, 48, 48) and vlog["Loss"] > 0

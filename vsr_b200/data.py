@@ -56,12 +56,15 @@ class SyntheticCineDataset(Dataset):
     patch_size (LR crop for training, RandomCropPatch.size) and seed."""
 
     def __init__(self, downscale_factor, num_frames=5, temporal_order="last", type="train", dataset="acdc",
-                 num_sequences=16, patch_size=(32, 32), seed=0):
+                 num_sequences=16, patch_size=(32, 32), seed=0, misr=False):
         if downscale_factor not in [2, 3, 4]:
             raise ValueError(f"The downscale factor should be 2, 3, 4. Got {downscale_factor}.")
         if temporal_order not in ["last", "middle"]:
             raise ValueError(f"The temporal order should be 'last' or 'middle'. Got {temporal_order}.")
         self.r, self.num_frames, self.temporal_order, self.type = downscale_factor, num_frames, temporal_order, type
+        # misr=True: the AcdcMISRDataset contract (acdc_misr_dataset.py:46-88): every item, training or validation, is
+        # a window of num_frames LR frames and ONE target, `hr_img` = the HR frame at num_frames // 2
+        self.misr = misr
         self.patch = tuple(patch_size) if patch_size else None
         self.mean, self.std = DATASET_STATS[dataset]
         shape = SHAPES[dataset]
@@ -75,7 +78,7 @@ class SyntheticCineDataset(Dataset):
             self.lr.append(np.stack([downscale(f, self.r) for f in cine]))
         self.T = shape["frames"]
         self.rng = np.random.default_rng(seed + 1)
-        self.data = [(s, t) for s in range(num_sequences) for t in range(self.T)] if type == "train" \
+        self.data = [(s, t) for s in range(num_sequences) for t in range(self.T)] if type == "train" or misr \
             else [(s, None) for s in range(num_sequences)]
 
     def __len__(self):
@@ -91,7 +94,7 @@ class SyntheticCineDataset(Dataset):
 
     def __getitem__(self, index):
         s, t = self.data[index]
-        idx = self._window(t) if self.type == "train" else list(range(self.T))
+        idx = self._window(t) if self.type == "train" or self.misr else list(range(self.T))
         lr, hr = self.lr[s][idx], self.hr[s][idx]
         if self.type == "train":
             if self.rng.random() < 0.5:
@@ -106,6 +109,10 @@ class SyntheticCineDataset(Dataset):
                 hr = hr[:, y0 * self.r:(y0 + ph) * self.r, x0 * self.r:(x0 + pw) * self.r]
         norm = lambda a: torch.from_numpy(((np.ascontiguousarray(a) - self.mean) / self.std).astype(np.float32))
         lr, hr = norm(lr), norm(hr)
+        if self.misr:
+            n = self.num_frames
+            return {"lr_imgs": [f.unsqueeze(0) for f in lr], "hr_img": hr[n // 2 if n % 2 == 1 else n // 2 - 1].unsqueeze(0),
+                    "index": index}
         return {"lr_imgs": [f.unsqueeze(0) for f in lr], "hr_imgs": [f.unsqueeze(0) for f in hr], "index": index}
 
 

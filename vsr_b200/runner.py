@@ -421,6 +421,50 @@ class VSRTrainer:
 AcdcVSRTrainer = VSRTrainer
 
 
+class MISRTrainer(VSRTrainer):
+    """Drop-in for AcdcMISRTrainer (acdc_misr_trainer.py:8-50 on base_trainer.py:99-144): batches carry
+    `lr_imgs` (list of num_frames tensors) and ONE `hr_img`; the log weights every batch by the loader's batch
+    size.  The step is MISRTrainStep (DUFNet, synchronised BatchNorm across ranks)."""
+
+    def __init__(self, device, train_dataloader, valid_dataloader, net, loss_fns, loss_weights, metric_fns,
+                 optimizer, lr_scheduler, logger, monitor, num_epochs, dataset="acdc", use_graph=False):
+        super().__init__(device, train_dataloader, valid_dataloader, net, loss_fns, loss_weights, metric_fns,
+                         optimizer, lr_scheduler, logger, monitor, num_epochs, dataset)
+        self.step = MISRTrainStep(self.net, self.loss_fns, self.loss_weights, self.metric_fns, optimizer, dataset,
+                                  use_graph=use_graph)
+
+    def _run_epoch(self, mode):
+        from .data import DeviceStager
+        training = mode == "training"
+        self.net.train(training)
+        loader = self.train_dataloader if training else self.valid_dataloader
+        keys = self._keys()
+        acc = torch.zeros(len(keys), device=self.device)
+        count, batch, outputs = 0, None, None
+        batches = DeviceStager(loader, self.device) if self.device.type == "cuda" else loader
+        for batch in batches:
+            inputs, targets = batch["lr_imgs"], [batch["hr_img"]]          # acdc_misr_trainer.py:16-25
+            step_acc = torch.zeros_like(acc)
+            if training:
+                _, outs = self.step.train_step(inputs, targets, step_acc)
+            else:
+                _, outs = self.step.eval_step(inputs, targets, step_acc)
+            outputs = outs[0]
+            bs = loader.batch_size or inputs[0].shape[0]                   # base_trainer.py:139-141
+            acc += step_acc * bs
+            count += bs
+        if self.step.world > 1:
+            cnt = torch.tensor([float(count)], device=self.device)
+            dist.all_reduce(acc)
+            dist.all_reduce(cnt)
+            count = cnt.item()
+        vals = (acc / max(count, 1)).tolist()          # the one host sync of the epoch
+        return dict(zip(keys, vals)), batch, outputs
+
+
+AcdcMISRTrainer = MISRTrainer
+
+
 class VSRPredictor:
     """Drop-in for AcdcVSRPredictor / Dsb15VSRPredictor (acdc_vsr_predictor.py:15-110; base_predictor.py:6-23):
     same constructor keywords (`dataset` selects the denormalisation constants) and the same `predict()` log
