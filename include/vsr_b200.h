@@ -309,6 +309,12 @@ int vsr_tshift_add(const void* z, int32_t dtype, int32_t ldz, int32_t g, int32_t
                    int32_t t_pad, const float* bias, void* out, int32_t ld_out, int32_t c0_out, int32_t frames_out,
                    double* stats, int32_t ld_stats, int32_t s0, void* workspace, size_t workspace_bytes, void* stream);
 
+/* The gradient side of vsr_tshift_add, feeding the weight gradient of the (1,3,3) form:
+ *   dz[f][row][kt*g + co] = dy[f - kt + t_pad][row][c0 + co]  (zero outside the frames_out frames of dy and for the
+ * padding columns [3g, ldz)), f < frames_in. */
+int vsr_tshift_gather(const void* dy, int32_t dtype, int32_t ld_dy, int32_t c0, int32_t g, int32_t frames_out,
+                      int64_t rows_per_frame, int32_t t_pad, void* dz, int32_t ldz, int32_t frames_in, void* stream);
+
 /* One BatchNorm's affine map from the statistics of `frames` frames (training != 0: biased batch variance,
  * running_mean / running_var updated with `momentum` and the unbiased variance when non-NULL) or from the
  * running buffers (training == 0):  scale_shift = float[2][cp] {gamma*rstd, beta - mean*gamma*rstd}, zero

@@ -276,7 +276,9 @@ class EmuOps:
         zf = z.reshape(frames_in, -1, z.shape[-1]).to(ct)
         of = out.reshape(frames_out, -1, out.shape[-1])
         for f in range(frames_out):
-            acc = bias.to(ct).expand(zf.shape[1], g).clone()
+            acc = torch.zeros(zf.shape[1], g, dtype=ct, device=z.device)
+            if bias is not None:
+                acc += bias.to(ct)
             for kt in range(3):
                 fi = f + kt - t_pad
                 if 0 <= fi < frames_in:
@@ -285,6 +287,17 @@ class EmuOps:
         if stats is not None:
             self.bn_stats(out, c0_out, g, frames_out, stats, s0, None)
         self.launches += 2 if stats is not None else 1
+
+    def tshift_gather(self, dy, c0, g, frames_out, t_pad, dz, frames_in):
+        yf = dy.reshape(frames_out, -1, dy.shape[-1])
+        zf = dz.reshape(frames_in, -1, dz.shape[-1])
+        zf.zero_()
+        for f in range(frames_in):
+            for kt in range(3):
+                fo = f - kt + t_pad
+                if 0 <= fo < frames_out:
+                    zf[f, :, kt * g:(kt + 1) * g] = yf[fo, :, c0:c0 + g]
+        self.launches += 1
 
     def bn_finalize(self, stats, s0, frames, rows_per_frame, c, gamma, beta, eps, momentum, running_mean,
                     running_var, training, scale_shift, mean_rstd):

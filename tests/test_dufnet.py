@@ -198,6 +198,12 @@ def test_gpu_dense3d_kernels_match_emulation(dtype):
         assert torch.allclose(o_a.float(), o_b.float(), rtol=1e-2 if dtype == torch.bfloat16 else 1e-6, atol=1e-5)
         assert float(o_a[..., :64].abs().max()) == 0 and float(o_a[..., 96:].abs().max()) == 0
         assert torch.allclose(s_a, s_b, rtol=2e-2 if dtype == torch.bfloat16 else 1e-5, atol=0.5 if dtype == torch.bfloat16 else 1e-4)
+    for t_pad, f_out in ((1, F), (0, F - 2)):                    # and its inverse for the weight gradient
+        gy = torch.randn(f_out * N, h, w, ld, generator=g).to(dev).to(dtype)
+        z_a, z_b = torch.full((F * N, h, w, 128), 3.0, dtype=dtype, device=dev), torch.empty(F * N, h, w, 128, dtype=dtype, device=dev)
+        ops.tshift_gather(gy, 64, 32, f_out, t_pad, z_a, F)
+        emu.tshift_gather(gy, 64, 32, f_out, t_pad, z_b, F)
+        assert torch.equal(z_a, z_b)
     d_a = torch.zeros(F * N, h, w, 64, dtype=dtype, device=dev)
     ops.copy_window(x, c0, d_a, 16, 32)
     assert torch.equal(d_a[..., 16:48], x[..., c0:c0 + 32]) and float(d_a[..., :16].abs().max()) == 0

@@ -1,6 +1,6 @@
 """Run ONE tap-GEMM shape a few times (for `ncu --set full --import-source on -k regex:tapgemm_tc2 -s 4 -c 1`).
 
-    python tools/one_shape.py hr2 | hr6 | deconv | conv8 | deconv_bwd
+    python tools/one_shape.py hr2 | hr6 | deconv | conv8 | deconv_bwd | duf_c2z | duf_c2 | duf_dgrad
 """
 import os
 import sys
@@ -22,6 +22,22 @@ def main():
         return
     res = []
     kbench.CASES = None
+    if which.startswith("duf"):
+        # growth convolution of DUFNet-16, second dense layer (96 -> 32 channels, stored as 128), batch 32 x 7 frames
+        n, h, w = 7 * 32, 32, 32
+        kbench.EPI = 0
+        sp = [(ky - 1, kx - 1) for ky in range(3) for kx in range(3)]
+        if which == "duf_c2z":      # temporal taps as output columns: one source, 9 x 2 taps, N = 96 of 128
+            tab = TapTable(64, 128, [(0, [(0, dy, dx, b * 64) for dy, dx in sp for b in range(2)])])
+            kbench.tapgemm_case("duf_c2z", tab, n, h, w, [128], 128, torch.bfloat16, 3, flush, res)
+        elif which == "duf_c2":     # direct form: three frame-shifted sources, 27 x 2 taps, N = 32 of 64
+            kbench.EPI = 1
+            tab = TapTable(64, 64, [(96, [(kt, dy, dx, b * 64) for kt in range(3) for dy, dx in sp for b in range(2)])])
+            kbench.tapgemm_case("duf_c2", tab, n, h, w, [128, 128, 128], 288, torch.bfloat16, 3, flush, res)
+        else:                       # its data gradient: 27 taps of the 64-wide gradient window, N = 128
+            tab = TapTable(64, 128, [(0, [(kt, -dy, -dx, 96) for kt in range(3) for dy, dx in sp])])
+            kbench.tapgemm_case("duf_dgrad", tab, n, h, w, [288, 288, 288], 128, torch.bfloat16, 3, flush, res)
+        return
     N, h, w, F = 32, 32, 32, 64
     if which in ("deconv", "deconv_bwd"):
         groups = []

@@ -500,6 +500,29 @@ __global__ void __launch_bounds__(kThreads) tshift_add_kernel(const T* __restric
   }
 }
 
+// inverse of the shift-add, for the weight gradient of the same convolution in its (1,3,3) form:
+//   dz[f][row][kt*G + co] = dy[f - kt + t_pad][row][c0 + co]   (zero for frames outside [0, frames_out) and for the
+// channel padding [3G, ldz)), f < frames_in.
+template <typename T>
+__global__ void __launch_bounds__(kThreads) tshift_gather_kernel(const T* __restrict__ dy, int ld_dy, int c0, int G,
+                                                                 int frames_out, long rows_per_frame, int t_pad,
+                                                                 T* __restrict__ dz, int ldz, int frames_in) {
+  constexpr int V = Vec<T>::V;
+  const int tpr = ldz / V;
+  const long total = (long)frames_in * rows_per_frame * tpr;
+  for (long i = (long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long)gridDim.x * kThreads) {
+    const long frow = i / tpr;
+    const int ch = (int)(i - frow * tpr) * V;
+    const int f = (int)(frow / rows_per_frame);
+    const long row = frow - (long)f * rows_per_frame;
+    const int kt = ch / G, fo = f - kt + t_pad;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (kt < 3 && fo >= 0 && fo < frames_out)
+      v = *reinterpret_cast<const uint4*>(dy + ((long)fo * rows_per_frame + row) * ld_dy + c0 + (ch - kt * G));
+    *reinterpret_cast<uint4*>(dz + frow * ldz + ch) = v;
+  }
+}
+
 int stats_bpf(int frames, long rows_per_frame) {
   long bpf = (rows_per_frame + 511) / 512;
   const long cap = (4L * num_sms() + frames - 1) / frames;
@@ -606,6 +629,22 @@ extern "C" int vsr_tshift_add(const void* z, int32_t dtype, int32_t ldz, int32_t
     bn_stats_final_kernel<<<(frames_out * 2 * g + 7) / 8, 256, 0, s>>>(ws, frames_out, bpf, g, stats, ld_stats, s0);
     VSR_CHECK_LAUNCH("vsr_tshift_add_final");
   }
+  return VSR_OK;
+}
+
+extern "C" int vsr_tshift_gather(const void* dy, int32_t dtype, int32_t ld_dy, int32_t c0, int32_t g, int32_t frames_out,
+                                 int64_t rows_per_frame, int32_t t_pad, void* dz, int32_t ldz, int32_t frames_in,
+                                 void* stream) {
+  VSR_CHECK_ARG(dy && dz && frames_in > 0 && frames_out > 0 && rows_per_frame > 0 && (t_pad == 0 || t_pad == 1) &&
+                    ldz >= 3 * g, "vsr_tshift_gather: bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  VSR_DISPATCH_DTYPE(dtype, "vsr_tshift_gather", {
+    VSR_CHECK_ARG((window_ok<T>(ld_dy, c0, g) && ldz % Vec<T>::V == 0),
+                  "vsr_tshift_gather: windows must be 16-byte aligned (ld_dy %d c0 %d g %d ldz %d)", ld_dy, c0, g, ldz);
+    tshift_gather_kernel<T><<<grid_for((long)frames_in * rows_per_frame * (ldz / Vec<T>::V), kThreads), kThreads, 0, s>>>(
+        (const T*)dy, ld_dy, c0, g, frames_out, rows_per_frame, t_pad, (T*)dz, ldz, frames_in);
+  })
+  VSR_CHECK_LAUNCH("vsr_tshift_gather");
   return VSR_OK;
 }
 

@@ -810,7 +810,12 @@ int tapgemm_tc2_launch(const VsrTapGemmDesc* d, cudaStream_t stream) {
       const int rows = mb * bh + longest - 1;
       const long abox = (long)rows * a.row_bytes;
       const bool res_ok = d->max_group_taps > 0 && d->nt > 64 && res_need <= avail - 3 * abox;
-      const bool stream_ok = 3 * (abox + (long)longest * b_bytes) <= avail;
+      // streamed slabs: three stages of {shared box + its slabs} when they fit; two are enough when a stage is long
+      // (3 taps x mb sub-tiles x 4 MMAs) and the alternative is one load per tap (3x the L2 -> SM traffic: the
+      // 3x3(x3) convolutions of the Conv3d path, profiles/README.md).  VSR_TC_TALL_STAGES=3 restores the old rule.
+      static const char* env_ts = getenv("VSR_TC_TALL_STAGES");
+      const int min_stages = (env_ts && env_ts[0] == '3') ? 3 : 2;
+      const bool stream_ok = min_stages * (abox + (long)longest * b_bytes) <= avail;
       if (rows <= 256 && (res_ok || stream_ok)) {
         a.tall = 1;
         a.mb = mb;

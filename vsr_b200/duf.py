@@ -141,11 +141,13 @@ class DufPlan(DrfPlan):
                         for b in range(cp // kc):
                             taps.append((kt, ky - 1, kx - 1, b * kc))
                             slabs.append(m(W2, j, b * kc + k, kt, ky, kx))
-            self.fwd[f"c2_{i}"] = Layer(f"c2_{i}", TapTable(kc, self.nt2, [(C[i], taps)]), slabs, self.ccat,
-                                        self._mbias(p + ".conv2", self.ccat, at=C[i]))
+            if not self.bf16:
+                self.fwd[f"c2_{i}"] = Layer(f"c2_{i}", TapTable(kc, self.nt2, [(C[i], taps)]), slabs, self.ccat,
+                                            self._mbias(p + ".conv2", self.ccat, at=C[i]))
             if self.bf16:
-                # tensor-core forward: the three temporal taps as extra output columns of a (1,3,3) tap-GEMM
-                # (N = 3G, A read once for all three), finished by vsr_tshift_add
+                # tensor-core forward AND weight gradient: the three temporal taps as extra output columns of a
+                # (1,3,3) tap-GEMM (N = 3G, A read once for all three); vsr_tshift_add / vsr_tshift_gather move
+                # between the [.., 3G] column form and the concat slice
                 j, k = self._jk(self.ntz)
                 taps, slabs = [], []
                 for ky in range(3):
@@ -153,7 +155,10 @@ class DufPlan(DrfPlan):
                         for b in range(cp // kc):
                             taps.append((0, ky - 1, kx - 1, b * kc))
                             slabs.append(m(W2, np.where(j < 3 * G, j % G, -1), b * kc + k, j // G, ky, kx))
-                self.fwd[f"c2z_{i}"] = Layer(f"c2z_{i}", TapTable(kc, self.ntz, [(0, taps)]), slabs, self.ntz, None)
+                # the bias rides in the centre block (kt = 1: always a valid frame), so the shift-add adds it once and
+                # its gradient is the centre block of the column sums of dz
+                self.fwd[f"c2z_{i}"] = Layer(f"c2z_{i}", TapTable(kc, self.ntz, [(0, taps)]), slabs, self.ntz,
+                                             self._mbias(p + ".conv2", self.ntz, at=G))
             # its data gradient: sources 0..2 = the concat gradient seen through frame shifts +1, 0, -1
             splits = self._split(cp)
             nt = splits[0][1]
@@ -162,8 +167,8 @@ class DufPlan(DrfPlan):
             for o0, _ in splits:
                 taps = []
                 for kt in range(3):
-                    for ky in range(3):
-                        for kx in range(3):
+                    for ky in (2, 1, 0):          # row shifts ascending with the slab index: the tensor-core kernel
+                        for kx in (2, 1, 0):      # then loads ONE taller box for the three taps of a column
                             taps.append((kt, -(ky - 1), -(kx - 1), C[i]))
                             slabs.append(m(W2, k, o0 + j, kt, ky, kx))
                 groups.append((o0, taps))
@@ -412,7 +417,10 @@ class DUFNet(BaseNet):
             if need_stats:
                 ops.bn_stats(m4(b), 0, C[i], 1, st2, 0, self._ws("stats", ops.bn_stats_workspace(1, tin * rpf, C[i])))
             ss2, mr2 = self._bn(blk.bn2, pn + ".bn2", st2, 0, 1, tin * rpf, C[i], cp)
-            if i < P.n1:                                                     # padding (1,1,1): zero frames at both ends
+            if P.bf16:                                                       # (1,3,3) form: no frame-shifted views
+                c = cbuf = new(tin, cp)
+                views = None
+            elif i < P.n1:                                                   # padding (1,1,1): zero frames at both ends
                 cbuf = new(tin + 2, cp)
                 cbuf[0].zero_(); cbuf[tin + 1].zero_()
                 c = cbuf[1:tin + 1]
@@ -425,7 +433,7 @@ class DUFNet(BaseNet):
             if P.bf16:
                 z = new(tin, P.ntz)
                 self._conv(f"c2z_{i}", [m4(c)], m4(z))
-                ops.tshift_add(m4(z), G, tin, 1 if i < P.n1 else 0, self._pview(self.flat, pn + ".conv2.bias"), out, C[i],
+                ops.tshift_add(m4(z), G, tin, 1 if i < P.n1 else 0, None, out, C[i],
                                tout, stats[fo:fo + tout] if need_stats else None, C[i],
                                self._ws("stats", ops.bn_stats_workspace(tout, rpf, G)) if need_stats else None)
             else:
@@ -513,12 +521,16 @@ class DUFNet(BaseNet):
             cp = a.shape[-1]
             dz = m4(dcat[1 + fo:1 + fo + tout])
             if i < P.n1:
-                views = [m4(cbuf[kt:kt + tin]) for kt in range(3)]
                 gviews = [m4(dcat[1 + f0 + 1 - kt:1 + f0 + 1 - kt + tin]) for kt in range(3)]
             else:
-                views = [m4(cbuf[kt:kt + tout]) for kt in range(3)]
                 gviews = [m4(dcat[f0 + 2 - kt:f0 + 2 - kt + tin]) for kt in range(3)]
-            wgrad(f"c2_{i}", views, dz)
+            if P.bf16:
+                dzz = new(tin, P.ntz)
+                ops.tshift_gather(dz, C[i], G, tout, 1 if i < P.n1 else 0, m4(dzz), tin)
+                wgrad(f"c2z_{i}", [m4(cbuf)], m4(dzz))
+            else:
+                views = [m4(cbuf[kt:kt + (tin if i < P.n1 else tout)]) for kt in range(3)]
+                wgrad(f"c2_{i}", views, dz)
             dc = new(tin, cp)
             self._dgrad(f"c2_{i}", gviews, m4(dc))
             dbm = new(tin, cp)

@@ -332,6 +332,14 @@ class CudaOps:
                                       _stream()), "vsr_tshift_add")
         self.launches += 2 if stats is not None else 1
 
+    def tshift_gather(self, dy, c0, g, frames_out, t_pad, dz, frames_in):
+        """dz[f, ..., kt*g + co] = dy[f - kt + t_pad, ..., c0 + co] (zero outside dy's frames / in the column padding)"""
+        _need_cuda(dy, dz)
+        check(self.lib.vsr_tshift_gather(_p(dy), _DT[dy.dtype], dy.shape[-1], c0, g, frames_out,
+                                         self._rows(dy) // frames_out, t_pad, _p(dz), dz.shape[-1], frames_in,
+                                         _stream()), "vsr_tshift_gather")
+        self.launches += 1
+
     def bn_finalize(self, stats, s0, frames, rows_per_frame, c, gamma, beta, eps, momentum, running_mean,
                     running_var, training, scale_shift, mean_rstd):
         _need_cuda(stats, gamma, beta, running_mean, running_var, scale_shift, mean_rstd)
