@@ -207,7 +207,7 @@ def test_gpu_dense3d_kernels_match_emulation(dtype):
     d_a = torch.zeros(F * N, h, w, 64, dtype=dtype, device=dev)
     ops.copy_window(x, c0, d_a, 16, 32)
     assert torch.equal(d_a[..., 16:48], x[..., c0:c0 + 32]) and float(d_a[..., :16].abs().max()) == 0
-    for cin, sf, r in ((1, 5, 4), (2, 3, 3)):
+    for cin, sf, r in ((1, 5, 4), (2, 3, 3), (1, 7, 2)):
         cf, cr = sf * sf * r * r, cin * r * r
         ldl, ldr = -(-cf // 64) * 64, 64
         lg = torch.randn(N, h, w, ldl, generator=g).to(dev).to(dtype)

@@ -390,12 +390,15 @@ __global__ void __launch_bounds__(kThreads) duf_filter_kernel(const T* __restric
   }
 }
 
-template <typename T>
+// SF = filter size known at compile time (logits and tap gradients of a thread stay in registers: one read of the
+// logits), SF = 0: any size (three passes).
+template <typename T, int SF>
 __global__ void __launch_bounds__(kThreads) duf_filter_bwd_kernel(const T* __restrict__ logits, int ld_l,
                                                                   const float* __restrict__ x,
                                                                   const float* __restrict__ dy, int n, int cin, int h,
-                                                                  int w, int sf, int r, T* __restrict__ dlogits,
+                                                                  int w, int sf_rt, int r, T* __restrict__ dlogits,
                                                                   T* __restrict__ dres, int ld_r) {
+  const int sf = SF > 0 ? SF : sf_rt;
   const int rr = r * r, half = sf / 2, taps = sf * sf;
   const long total = (long)n * h * w * rr;
   for (long i = (long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long)gridDim.x * kThreads) {
@@ -404,34 +407,48 @@ __global__ void __launch_bounds__(kThreads) duf_filter_bwd_kernel(const T* __res
     const int x0 = (int)(pix % w), y0 = (int)((pix / w) % h), nn = (int)(pix / ((long)w * h));
     const T* lg = logits + pix * ld_l + p;
     const int Y = y0 * r + p / r, X = x0 * r + p % r;
-    float mx = -INFINITY;
-    for (int k = 0; k < taps; ++k) mx = fmaxf(mx, Elem<T>::ld(lg + k * rr));
+    const float* dyp = dy + ((long)nn * cin * h * r + Y) * ((long)w * r) + X;   // + c * (h*r) * (w*r)
+    const long dy_cs = (long)h * r * w * r;
     // g_k = sum_c dy_c * x_c[k];  dlogit_k = s_k * (g_k - sum_j s_j g_j)
-    float se = 0.f, sg = 0.f;
-    for (int k = 0; k < taps; ++k) {
-      const float e = __expf(Elem<T>::ld(lg + k * rr) - mx);
+    auto tap_grad = [&](int k) {
       const int yy = y0 + k / sf - half, xx = x0 + k % sf - half;
       float g = 0.f;
       if (yy >= 0 && yy < h && xx >= 0 && xx < w)
         for (int c = 0; c < cin; ++c)
-          g = fmaf(__ldg(dy + (((long)nn * cin + c) * h * r + Y) * ((long)w * r) + X),
-                   __ldg(x + (((long)nn * cin + c) * h + yy) * w + xx), g);
-      se += e;
-      sg = fmaf(e, g, sg);
+          g = fmaf(__ldg(dyp + c * dy_cs), __ldg(x + (((long)nn * cin + c) * h + yy) * w + xx), g);
+      return g;
+    };
+    if constexpr (SF > 0) {
+      constexpr int TAPS = SF * SF;
+      float e[TAPS], gk[TAPS];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < TAPS; ++k) { e[k] = Elem<T>::ld(lg + k * rr); mx = fmaxf(mx, e[k]); }
+      float se = 0.f, sg = 0.f;
+#pragma unroll
+      for (int k = 0; k < TAPS; ++k) {
+        e[k] = __expf(e[k] - mx);
+        gk[k] = tap_grad(k);
+        se += e[k];
+        sg = fmaf(e[k], gk[k], sg);
+      }
+      const float inv = 1.f / se, dot = sg * inv;
+#pragma unroll
+      for (int k = 0; k < TAPS; ++k) Elem<T>::st(dlogits + pix * ld_l + k * rr + p, e[k] * inv * (gk[k] - dot));
+    } else {
+      float mx = -INFINITY;
+      for (int k = 0; k < taps; ++k) mx = fmaxf(mx, Elem<T>::ld(lg + k * rr));
+      float se = 0.f, sg = 0.f;
+      for (int k = 0; k < taps; ++k) {
+        const float e = __expf(Elem<T>::ld(lg + k * rr) - mx);
+        se += e;
+        sg = fmaf(e, tap_grad(k), sg);
+      }
+      const float inv = 1.f / se, dot = sg * inv;
+      for (int k = 0; k < taps; ++k)
+        Elem<T>::st(dlogits + pix * ld_l + k * rr + p, __expf(Elem<T>::ld(lg + k * rr) - mx) * inv * (tap_grad(k) - dot));
     }
-    const float inv = 1.f / se, dot = sg * inv;
-    for (int k = 0; k < taps; ++k) {
-      const float s = __expf(Elem<T>::ld(lg + k * rr) - mx) * inv;
-      const int yy = y0 + k / sf - half, xx = x0 + k % sf - half;
-      float g = 0.f;
-      if (yy >= 0 && yy < h && xx >= 0 && xx < w)
-        for (int c = 0; c < cin; ++c)
-          g = fmaf(__ldg(dy + (((long)nn * cin + c) * h * r + Y) * ((long)w * r) + X),
-                   __ldg(x + (((long)nn * cin + c) * h + yy) * w + xx), g);
-      Elem<T>::st(dlogits + pix * ld_l + k * rr + p, s * (g - dot));
-    }
-    for (int c = 0; c < cin; ++c)
-      Elem<T>::st(dres + pix * ld_r + c * rr + p, __ldg(dy + (((long)nn * cin + c) * h * r + Y) * ((long)w * r) + X));
+    for (int c = 0; c < cin; ++c) Elem<T>::st(dres + pix * ld_r + c * rr + p, __ldg(dyp + c * dy_cs));
   }
 }
 
@@ -751,8 +768,16 @@ extern "C" int vsr_duf_filter_bwd(const void* logits, int32_t ld_logits, int32_t
   if (ld_logits > size_filter * size_filter * r * r) cudaMemsetAsync(dlogits, 0, pix * ld_logits * es, s);
   if (ld_res > cin * r * r) cudaMemsetAsync(dres, 0, pix * ld_res * es, s);
   VSR_DISPATCH_DTYPE(dtype, "vsr_duf_filter_bwd", {
-    duf_filter_bwd_kernel<T><<<grid_for(pix * r * r, kThreads), kThreads, 0, s>>>(
-        (const T*)logits, ld_logits, x, dy, n, cin, h, w, size_filter, r, (T*)dlogits, (T*)dres, ld_res);
+    const int grid = grid_for(pix * r * r, kThreads);
+    if (size_filter == 5)
+      duf_filter_bwd_kernel<T, 5><<<grid, kThreads, 0, s>>>((const T*)logits, ld_logits, x, dy, n, cin, h, w, size_filter, r,
+                                                          (T*)dlogits, (T*)dres, ld_res);
+    else if (size_filter == 3)
+      duf_filter_bwd_kernel<T, 3><<<grid, kThreads, 0, s>>>((const T*)logits, ld_logits, x, dy, n, cin, h, w, size_filter, r,
+                                                          (T*)dlogits, (T*)dres, ld_res);
+    else
+      duf_filter_bwd_kernel<T, 0><<<grid, kThreads, 0, s>>>((const T*)logits, ld_logits, x, dy, n, cin, h, w, size_filter, r,
+                                                          (T*)dlogits, (T*)dres, ld_res);
   })
   VSR_CHECK_LAUNCH("vsr_duf_filter_bwd");
   return VSR_OK;

@@ -144,19 +144,24 @@ __global__ void __launch_bounds__(256) conv_first2_kernel(const float* __restric
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int groups = cout >> 3;
-  const bool live = lane < groups;
+  // a warp covers ppw pixels x `groups` 8-channel groups: 1 pixel at 256 channels, 4 at 64 (no idle lanes)
+  const int ppw = (groups <= 16 && (groups & (groups - 1)) == 0) ? 32 / groups : 1;
+  const int gl = ppw > 1 ? lane % groups : lane, sub = ppw > 1 ? lane / groups : 0;
+  const bool live = gl < groups;
   float wr[8][9], br[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    br[j] = live ? sw2[256 * 9 + lane * 8 + j] : 0.f;
+    br[j] = live ? sw2[256 * 9 + gl * 8 + j] : 0.f;
 #pragma unroll
-    for (int t = 0; t < 9; ++t) wr[j][t] = live ? sw2[(lane * 8 + j) * 9 + t] : 0.f;
+    for (int t = 0; t < 9; ++t) wr[j][t] = live ? sw2[(gl * 8 + j) * 9 + t] : 0.f;
   }
   const float a = slope_p ? __ldg(slope_p) : 1.f;
   const long total = (long)n * h * w;
   const long warp0 = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
-  for (long pix = warp0; pix < total; pix += nwarps) {
+  for (long pix0 = warp0 * ppw; pix0 < total; pix0 += nwarps * ppw) {
+    const long pix = pix0 + sub;
+    if (pix >= total) continue;
     const int px = (int)(pix % w);
     const long q = pix / w;
     const int py = (int)(q % h);
@@ -180,7 +185,7 @@ __global__ void __launch_bounds__(256) conv_first2_kernel(const float* __restric
       acc[j] = s > 0.f ? s : a * s;
     }
     if (live) {
-      T* yp = y + pix * cout + lane * 8;
+      T* yp = y + pix * cout + gl * 8;
       if constexpr (sizeof(T) == 2) {
         uint4 o;
         o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
@@ -194,56 +199,66 @@ __global__ void __launch_bounds__(256) conv_first2_kernel(const float* __restric
   }
 }
 
-// first conv backward, v2 (cin == 1): block = 64 pixels, 4 pixel-lanes x 256 channel threads
-// (1024 threads); thread accumulates dw[co][9], db[co] over its 16 pixels, fixed-order smem fold
-// over the 4 pixel-lanes -> ws[block][cout][10]; parallel fixed-order final reduce.
+// first conv backward, v2 (cin == 1): a block walks 64-pixel chunks (chunk = blockIdx.x, += gridDim.x); its 1024
+// threads are LANES pixel-lanes x (1024 / LANES) channel threads (4 x 256 for up to 256 channels, 16 x 64 for up to
+// 64); a thread accumulates dw[co][9], db[co] over its pixels of every chunk in registers; fixed-order smem fold over
+// the pixel-lanes -> ws[block][cout][10]; parallel fixed-order final reduce over the (few) blocks.
 constexpr int kF2Pix = 64;
-template <typename T>
+template <typename T, int LANES>
 __global__ void __launch_bounds__(1024) conv_first2_bwd_kernel(const float* __restrict__ x, int n, int h, int w,
                                                               const T* __restrict__ dz, int cout, float* __restrict__ ws) {
+  constexpr int CT = 1024 / LANES;       // channel threads
+  constexpr int PPL = kF2Pix / LANES;    // pixels per lane and chunk
   __shared__ float xs[kF2Pix][9];
-  __shared__ float part[4][256][10];
+  __shared__ float part[1024][10];       // [lane][co]
   const long total = (long)n * h * w;
-  const long p0 = (long)blockIdx.x * kF2Pix;
-  for (int i = threadIdx.x; i < kF2Pix * 9; i += blockDim.x) {
-    const int pl = i / 9, t = i % 9;
-    const long p = p0 + pl;
-    float v = 0.f;
-    if (p < total) {
-      const int px = (int)(p % w);
-      const long q = p / w;
-      const int py = (int)(q % h);
-      const int yy = py + t / 3 - 1, xx = px + t % 3 - 1;
-      if (yy >= 0 && yy < h && xx >= 0 && xx < w) v = __ldg(x + (q / h) * (size_t)h * w + (size_t)yy * w + xx);
-    }
-    xs[pl][t] = v;
-  }
-  __syncthreads();
-  const int co = threadIdx.x & 255, pl4 = threadIdx.x >> 8;
+  const long chunks = (total + kF2Pix - 1) / kF2Pix;
+  const int co = threadIdx.x % CT, pl4 = threadIdx.x / CT;
   float acc[10];
 #pragma unroll
   for (int i = 0; i < 10; ++i) acc[i] = 0.f;
-  if (co < cout) {
-    float g[kF2Pix / 4];
-#pragma unroll
-    for (int i = 0; i < kF2Pix / 4; ++i) {
-      const long p = p0 + pl4 * (kF2Pix / 4) + i;
-      g[i] = p < total ? Elem<T>::ld(dz + p * cout + co) : 0.f;
+  for (long chunk = blockIdx.x; chunk < chunks; chunk += gridDim.x) {
+    const long p0 = chunk * kF2Pix;
+    __syncthreads();
+    for (int i = threadIdx.x; i < kF2Pix * 9; i += blockDim.x) {
+      const int pl = i / 9, t = i % 9;
+      const long p = p0 + pl;
+      float v = 0.f;
+      if (p < total) {
+        const int px = (int)(p % w);
+        const long q = p / w;
+        const int py = (int)(q % h);
+        const int yy = py + t / 3 - 1, xx = px + t % 3 - 1;
+        if (yy >= 0 && yy < h && xx >= 0 && xx < w) v = __ldg(x + (q / h) * (size_t)h * w + (size_t)yy * w + xx);
+      }
+      xs[pl][t] = v;
     }
+    __syncthreads();
+    if (co < cout) {
+      float g[PPL];
 #pragma unroll
-    for (int i = 0; i < kF2Pix / 4; ++i) {
-      const int pl = pl4 * (kF2Pix / 4) + i;
-      acc[9] += g[i];
+      for (int i = 0; i < PPL; ++i) {
+        const long p = p0 + pl4 * PPL + i;
+        g[i] = p < total ? Elem<T>::ld(dz + p * cout + co) : 0.f;
+      }
 #pragma unroll
-      for (int t = 0; t < 9; ++t) acc[t] = fmaf(g[i], xs[pl][t], acc[t]);
+      for (int i = 0; i < PPL; ++i) {
+        const int pl = pl4 * PPL + i;
+        acc[9] += g[i];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) acc[t] = fmaf(g[i], xs[pl][t], acc[t]);
+      }
     }
   }
 #pragma unroll
-  for (int i = 0; i < 10; ++i) part[pl4][co][i] = acc[i];
+  for (int i = 0; i < 10; ++i) part[pl4 * CT + co][i] = acc[i];
   __syncthreads();
   for (int i = threadIdx.x; i < cout * 10; i += blockDim.x) {
     const int c = i / 10, r = i % 10;
-    ws[(size_t)blockIdx.x * cout * 10 + i] = ((part[0][c][r] + part[1][c][r]) + part[2][c][r]) + part[3][c][r];
+    float t = 0.f;
+#pragma unroll
+    for (int l = 0; l < LANES; ++l) t += part[l * CT + c][r];
+    ws[(size_t)blockIdx.x * cout * 10 + i] = t;
   }
 }
 // out[i] (+)= sum_b ws[b][i], i < n: 256-thread blocks, 64 outputs x 4 block-lanes, fixed order
@@ -1128,10 +1143,16 @@ extern "C" int vsr_conv3x3_first_bwd(const float* x, int32_t n, int32_t cin, int
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const long pixels = (long)n * h * w_;
   if (cin == 1 && cout <= 256 && (dtype == VSR_F32 || dtype == VSR_BF16)) {
-    const int blocks2 = (int)((pixels + kF2Pix - 1) / kF2Pix);
+    int blocks2 = (int)((pixels + kF2Pix - 1) / kF2Pix);
+    if (blocks2 > 2 * num_sms()) blocks2 = 2 * num_sms();     // two 1024-thread blocks per SM; every block walks its chunks
     float* ws2 = static_cast<float*>(workspace);
-    if (dtype == VSR_F32) conv_first2_bwd_kernel<float><<<blocks2, 1024, 0, s>>>(x, n, h, w_, (const float*)dz, cout, ws2);
-    else conv_first2_bwd_kernel<__nv_bfloat16><<<blocks2, 1024, 0, s>>>(x, n, h, w_, (const __nv_bfloat16*)dz, cout, ws2);
+    if (cout <= 64) {
+      if (dtype == VSR_F32) conv_first2_bwd_kernel<float, 16><<<blocks2, 1024, 0, s>>>(x, n, h, w_, (const float*)dz, cout, ws2);
+      else conv_first2_bwd_kernel<__nv_bfloat16, 16><<<blocks2, 1024, 0, s>>>(x, n, h, w_, (const __nv_bfloat16*)dz, cout, ws2);
+    } else {
+      if (dtype == VSR_F32) conv_first2_bwd_kernel<float, 4><<<blocks2, 1024, 0, s>>>(x, n, h, w_, (const float*)dz, cout, ws2);
+      else conv_first2_bwd_kernel<__nv_bfloat16, 4><<<blocks2, 1024, 0, s>>>(x, n, h, w_, (const __nv_bfloat16*)dz, cout, ws2);
+    }
     VSR_CHECK_LAUNCH("vsr_conv3x3_first_bwd(v2)");
     const int nout = cout * 10;
     rows_reduce_kernel<<<(nout + 63) / 64, 256, 0, s>>>(ws2, blocks2, nout, dw, db, cout, accumulate);
