@@ -297,3 +297,40 @@ def test_misr_trainer_epoch_on_cpu():
     assert logs[2]["Loss"] < logs[0]["Loss"]
     vlog, _, out = tr._run_epoch("validation")
     assert out.shape == (2, 1, 48, 48) and vlog["Loss"] > 0
+
+
+def test_misr_predictor_on_cpu(tmp_path):
+    """MISRPredictor = AcdcMISRPredictor's loop (acdc_misr_predictor.py:31-110) through the emulation: the PSNR it logs
+    equals the oracle's PSNR of the oracle's (eval-mode) output, and results.csv has one row per item."""
+    from vsr_b200.data import Dataloader, SyntheticCineDataset
+    from vsr_b200.metrics import PSNR
+    from vsr_b200.runner import MISRPredictor
+    ds = SyntheticCineDataset(2, num_frames=7, temporal_order="middle", type="valid", num_sequences=1, patch_size=None,
+                              misr=True)
+    ds.data = ds.data[:3]
+    crop = lambda it: {"lr_imgs": [f[:, :12, :12].contiguous() for f in it["lr_imgs"]],
+                       "hr_img": it["hr_img"][:, :24, :24].contiguous(), "index": it["index"]}
+    items = [crop(ds[i]) for i in range(3)]
+
+    class Small(torch.utils.data.Dataset):
+        data = ds.data
+
+        def __len__(self):
+            return 3
+
+        def __getitem__(self, i):
+            return items[i]
+
+    net = DUFNet(1, 1, 7, 5, 2, "_DenseLayer16")
+    net._ops = EmuOps()
+    pred = MISRPredictor("cpu", Dataloader(Small(), batch_size=3, pin_memory=False), net, [torch.nn.L1Loss()], [1.0],
+                         [PSNR()], saved_dir=str(tmp_path), exported=True)
+    log = pred.predict()
+    sd = {k: v.detach() for k, v in net.state_dict().items()}
+    want = []
+    for it in items:
+        o = restated.dufnet_forward([f[None] for f in it["lr_imgs"]], sd, 5, 2, training=False)
+        want.append(float(restated.psnr(restated.denormalize(o, "acdc"), restated.denormalize(it["hr_img"][None], "acdc"))))
+    assert abs(log["PSNR"] - sum(want) / 3) <= 1e-3
+    rows = (tmp_path / "results.csv").read_text().strip().splitlines()
+    assert rows[0] == "name,PSNR,L1Loss" and len(rows) == 4 and rows[2].startswith("slice00000_frame02,")

@@ -233,9 +233,7 @@ class VSRTrainStep:
         if not net._is_flat():
             net._flatten()
         ops = self._ops()
-        eng = self._engine()
-        eng.pack(net.flat, need_bwd=False)
-        outs, _ = eng.forward([x.contiguous() for x in inputs], save=False)
+        outs = self._infer(inputs)
         targets = [y.contiguous() for y in targets]
         T, L, n, c = len(outs), len(self.losses), outs[0].shape[0], outs[0].shape[1]
         partials = torch.zeros(L * T, ops.partials_len, device=outs[0].device)
@@ -257,6 +255,13 @@ class VSRTrainStep:
         metrics = torch.stack([vals[i, :, :n] if name == "PSNR" else vals[i].view(T, n, c).mean(dim=2)
                                for i, name in enumerate(self.metric_names)]) if self.metric_names else vals
         return outs, losses, metrics
+
+    def _infer(self, inputs):
+        """forward without saving activations -> list of output frames"""
+        eng = self._engine()
+        eng.pack(self.net.flat, need_bwd=False)
+        outs, _ = eng.forward([x.contiguous() for x in inputs], save=False)
+        return outs
 
     def _log(self, acc, lvals):
         w = self._bufs.get("lw")
@@ -306,13 +311,16 @@ class MISRTrainStep(VSRTrainStep):
         net.flat_grad = gflat
         return lvals, [y], gflat
 
+    def _infer(self, inputs):
+        self.net._pack(False)
+        return [self.net._forward([x.contiguous() for x in inputs], False)[0]]
+
     @torch.no_grad()
     def eval_step(self, inputs, targets, acc=None):
         net = self.net
         if not net._is_flat():
             net._flatten()
-        net._pack(False)
-        y, _ = net._forward([x.contiguous() for x in inputs], False)
+        y = self._infer(inputs)[0]
         targets = [t.contiguous() for t in targets]
         lvals, _ = self._loss([y], targets, False)
         if acc is not None:
@@ -494,6 +502,8 @@ class VSRPredictor:
         data = getattr(self.test_dataloader.dataset, "data", None)
         try:
             entry = data[index][0]
+            if isinstance(entry, (int, np.integer)):      # synthetic loader: (sequence number, frame)
+                return f"sequence{int(entry):05d}"
             return entry.parts[-1].split(".")[0]          # the reference's lr_path stem (:59-60)
         except (AttributeError, TypeError, IndexError):
             return f"sequence{int(index):05d}"
@@ -539,3 +549,55 @@ class VSRPredictor:
 
 
 AcdcVSRPredictor = Dsb15VSRPredictor = VSRPredictor
+
+
+class MISRPredictor(VSRPredictor):
+    """Drop-in for AcdcMISRPredictor / Dsb15MISRPredictor (acdc_misr_predictor.py:15-110): every item is a window of
+    `num_frames` LR frames and one target frame; the log weights items by the batch size (:96-98); `exported=True`
+    writes `results.csv` with one row per item, `<sequence>_frame<t+1>` (:66-73).  Any batch size (the reference
+    insists on 1); losses and metrics come from the fused device kernels, one host read-back per batch."""
+
+    def __init__(self, device, test_dataloader, net, loss_fns, loss_weights, metric_fns, saved_dir=None,
+                 exported=False, dataset="acdc"):
+        super().__init__(device, test_dataloader, net, loss_fns, loss_weights, metric_fns, saved_dir, exported, dataset)
+        self.step = MISRTrainStep(self.net, self.loss_fns, list(loss_weights), self.metric_fns, None, dataset)
+
+    def predict(self):
+        import csv
+        self.net.eval()
+        keys = ["Loss"] + [f.__class__.__name__ for f in self.loss_fns] + [m.__class__.__name__ for m in self.metric_fns]
+        log = dict.fromkeys(keys, 0.0)
+        rows = [["name"] + keys[1 + len(self.loss_fns):] + keys[1:1 + len(self.loss_fns)]]
+        data = getattr(self.test_dataloader.dataset, "data", None)
+        count = 0
+        for batch in self._batches():
+            inputs, target, index = batch["lr_imgs"], batch["hr_img"], batch["index"]
+            bs = inputs[0].shape[0]
+            _, losses, metrics = self.step.eval_frames(inputs, [target])        # losses [1, L], metrics [M, 1, bs]
+            loss = (losses[0] * self.loss_weights).sum()
+            host = torch.cat([loss.view(1), losses[0], metrics.mean(dim=(1, 2)) if metrics.numel() else metrics.view(0)])
+            vals = host.tolist()                                               # the one host read-back of the batch
+            for k, v in zip(keys, vals):
+                log[k] += v * bs
+            count += bs
+            if self.exported:
+                lt, mt = losses[0].tolist(), metrics.tolist()
+                idx = index.tolist() if torch.is_tensor(index) else list(index)
+                for i in range(bs):
+                    name = self._name(idx[i]).replace("2d+1d", "2d").replace("sequence", "slice")
+                    try:
+                        t = int(data[idx[i]][-1])
+                    except (TypeError, IndexError, ValueError):
+                        t = 0
+                    rows.append([f"{name}_frame{t + 1:0>2d}"] + [m[0][i] for m in mt] + lt)
+        if self.exported:
+            self.saved_dir.mkdir(parents=True, exist_ok=True)
+            with open(self.saved_dir / "results.csv", "w", newline="") as f:
+                csv.writer(f).writerows(rows)
+        for k in log:
+            log[k] /= max(count, 1)
+        logging.info(f"Test log: {log}.")
+        return log
+
+
+AcdcMISRPredictor = Dsb15MISRPredictor = MISRPredictor
