@@ -392,7 +392,9 @@ class DUFNet(BaseNet):
         m4 = lambda t: t.reshape(-1, h, w, t.shape[-1])                     # [frames, N, h, w, c] -> [frames*N, h, w, c]
         x = torch.stack(frames).reshape(T * N, cin, h, w)                   # duf_net.py:57-61 (time-major)
         centre = frames[T // 2 if T % 2 == 1 else T // 2 - 1]               # duf_net.py:53-54
-        cat = torch.zeros(T + 2, N, h, w, P.ccat, dtype=act, device=dev)    # frames 0 and T+1: temporal padding
+        # the concat buffer (frame f of the net = index f + 1, mirroring its gradient buffer).  Every layer reads only
+        # channels and frames written before it, so it is not cleared
+        cat = torch.empty(T + 2, N, h, w, P.ccat, dtype=act, device=dev)
         stats = torch.zeros(T, 2, P.ctot, dtype=torch.float64, device=dev)
         need_stats = self.training
         self._nbt = []
