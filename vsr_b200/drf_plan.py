@@ -311,8 +311,8 @@ class DrfPlan:
         kb_out = (m * F) // self.kc
         for slot, (py, px) in enumerate(in_phases):
             taps = []
-            for ky in range(3):
-                for kx in range(3):
+            for ky in (2, 1, 0):        # row shifts ascending with the slab index: the tensor-core kernel then shares
+                for kx in (2, 1, 0):    # one taller A box between the taps of a column (tapgemm_tc2.cu build_columns)
                     dY, qy = divmod(py - (ky - 1), in_r)
                     dX, qx = divmod(px - (kx - 1), in_r)
                     for b in range(kb_out):

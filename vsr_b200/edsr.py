@@ -65,7 +65,8 @@ class EdsrPlan(DrfPlan):
                     btaps.append((0, -(ky - 1), -(kx - 1), b * self.kc))       # data-gradient: flipped taps
                     bslabs.append(W.idx(b * self.kc + k, j, ky, kx))
         self.fwd[lname] = Layer(lname, TapTable(self.kc, F, [(0, taps)]), slabs, F, self._bias_idx(wname))
-        self.bwd[lname] = Layer(lname, TapTable(self.kc, F, [(0, btaps)]), bslabs, F)
+        # reversed: row shifts ascending with the slab index, so the tensor-core kernel shares one taller A box per column
+        self.bwd[lname] = Layer(lname, TapTable(self.kc, F, [(0, btaps[::-1])]), bslabs[::-1], F)
 
     def _build_layers(self):
         # order matters: all conv2 layers are contiguous in the packed gradient buffers (res_scale)
