@@ -541,8 +541,8 @@ __global__ void __launch_bounds__(kThreads) tshift_gather_kernel(const T* __rest
 }
 
 int stats_bpf(int frames, long rows_per_frame) {
-  long bpf = (rows_per_frame + 511) / 512;
-  const long cap = (4L * num_sms() + frames - 1) / frames;
+  long bpf = (rows_per_frame + 255) / 256;
+  const long cap = (8L * num_sms() + frames - 1) / frames;
   if (bpf > cap) bpf = cap;
   if (bpf < 1) bpf = 1;
   return (int)bpf;
