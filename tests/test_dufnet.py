@@ -334,3 +334,12 @@ def test_misr_predictor_on_cpu(tmp_path):
     assert abs(log["PSNR"] - sum(want) / 3) <= 1e-3
     rows = (tmp_path / "results.csv").read_text().strip().splitlines()
     assert rows[0] == "name,PSNR,L1Loss" and len(rows) == 4 and rows[2].startswith("slice00000_frame02,")
+
+
+def test_config_driven_construction():
+    """getattr(src.model.nets, 'DUFNet')(**kwargs) of main.py:56,167-178 resolves to the drop-in"""
+    from vsr_b200.config import build_net
+    net = build_net({"net": {"name": "DUFNet", "kwargs": dict(in_channels=1, out_channels=1, num_frames=7, size_filter=5,
+                                                               upscale_factor=4, backbone="_DenseLayer16")}})
+    assert isinstance(net, DUFNet) and net.precision == "fp32"
+    assert sum(p.numel() for p in net.parameters()) == net._plan.n_params == net.flat.numel()
