@@ -75,6 +75,29 @@ def peaks():
     return p
 
 
+# Whatever a library writes to the process's stdout (NCCL prints its version banner there on some boxes, even
+# with NCCL_DEBUG_FILE set) goes to stderr: file descriptor 1 is pointed at stderr for the whole run and the ONE
+# JSON line is written to the saved original descriptor.
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 class ClockSampler(threading.Thread):
     """samples SM clocks and throttle reasons with NVML while the timed region runs."""
 
@@ -158,7 +181,7 @@ def cpu_port(sample):
             loss.backward()
             opt.step()
             restated.vsr_metrics([out.detach()], hrs)
-            return float(loss)
+            return float(loss.detach())
     else:
         from vsr_b200.nets import DRFNet
         net = DRFNet(**MODEL)            # parameter container only (same init as the reference class)
@@ -172,7 +195,7 @@ def cpu_port(sample):
             loss.backward()
             opt.step()
             restated.vsr_metrics([o.detach() for o in outs], hrs)
-            return float(loss)
+            return float(loss.detach())
     return step, hr_voxels(sample)
 
 
@@ -201,7 +224,7 @@ def run_reference(args):
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{sample} of {BATCH} patches x T{frames_in()} per step, torch {torch.__version__} CPU fp32"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def cpu_baseline(budget_s=20.0):
@@ -234,6 +257,7 @@ def main():
     args = ap.parse_args()
     global WORKLOAD
     WORKLOAD = args.workload
+    capture_stdout()
     if args.impl == "reference":
         run_reference(args)
         return
@@ -422,7 +446,7 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
-        print(json.dumps(line), flush=True)
+        emit(line)
     # hang-proof exit: synchronise, then leave without tearing NCCL / CUDA graphs down
     torch.cuda.synchronize()
     if world > 1:
