@@ -343,3 +343,34 @@ def test_config_driven_construction():
                                                                upscale_factor=4, backbone="_DenseLayer16")}})
     assert isinstance(net, DUFNet) and net.precision == "fp32"
     assert sum(p.numel() for p in net.parameters()) == net._plan.n_params == net.flat.numel()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(1, 9, 11), (3, 7, 20)], ids=["1x9x11", "3x7x20"])
+def test_gpu_ragged_sizes_match_emulation(shape):
+    """frame sizes that are no multiple of any pixel box (partial TMA tiles, ragged row splits in the BatchNorm passes):
+    the CUDA path in fp32 against the torch emulation on the same device, forward and every gradient; bf16 against fp32."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    n, h, w = shape
+    g = torch.Generator().manual_seed(11)
+    frames = [torch.randn(n, 1, h, w, generator=g).cuda() for _ in range(7)]
+    target = torch.randn(n, 1, 2 * h, 2 * w, generator=g).cuda()
+    fx = torch.load([p for p in CASES if p.endswith("dufnet16_x2.pt")][0])
+    res = {}
+    for which in ("cuda", "emu", "bf16"):
+        net = DUFNet(1, 1, 7, 5, 2, "_DenseLayer16", precision="bf16" if which == "bf16" else "fp32")
+        net.load_state_dict(_state(fx))
+        net = net.cuda().train()
+        if which == "emu":
+            net._ops = EmuOps()
+        out = net(frames)
+        torch.nn.MSELoss()(out, target).backward()
+        res[which] = (out.detach(), net.flat_grad.clone())
+    assert _rel(res["cuda"][0], res["emu"][0]) <= 1e-5
+    # random inputs, no control of ReLU ties: with 99 rows per frame ONE flipped mask element moves a gradient by ~1e-3
+    # of the largest one (see the fixture generator); an indexing bug shows as >= 1e-1
+    assert float((res["cuda"][1] - res["emu"][1]).abs().max()) <= 3e-3 * float(res["emu"][1].abs().max())
+    assert float((res["cuda"][1] - res["emu"][1]).norm() / res["emu"][1].norm()) <= 3e-3
+    assert _rel(res["bf16"][0], res["emu"][0]) <= 5e-2
+    assert float((res["bf16"][1] - res["emu"][1]).norm() / res["emu"][1].norm()) <= 0.25
