@@ -395,8 +395,10 @@ class DUFNet(BaseNet):
         # the concat buffer (frame f of the net = index f + 1, mirroring its gradient buffer).  Every layer reads only
         # channels and frames written before it, so it is not cleared
         cat = torch.empty(T + 2, N, h, w, P.ccat, dtype=act, device=dev)
-        stats = torch.zeros(T, 2, P.ctot, dtype=torch.float64, device=dev)
         need_stats = self.training
+        # per-frame {sum, sum of squares} of every concat channel, and of every 1x1x1 convolution's output (one clear)
+        stats = torch.zeros(T + P.L, 2, P.pad(P.ctot), dtype=torch.float64, device=dev) if need_stats else None
+        stats, stats2 = (stats[:T], stats[T:]) if need_stats else (None, None)
         self._nbt = []
         head = new(T, 64)
         ops.conv3x3_first(x, self._pview(self.flat, "head.weight"), self._pview(self.flat, "head.bias"), None, m4(head))
@@ -410,12 +412,12 @@ class DUFNet(BaseNet):
             pn = f"denseLayer.conv{i}"
             cp = P.pad(C[i])
             X = m4(cat[1 + f0:1 + f0 + tin])
-            ss1, mr1 = self._bn(blk.bn1, pn + ".bn1", stats[f0:f0 + tin], 0, tin, rpf, C[i], cp)
+            ss1, mr1 = self._bn(blk.bn1, pn + ".bn1", stats[f0:f0 + tin] if need_stats else None, 0, tin, rpf, C[i], cp)
             a = new(tin, cp)
             ops.bn_relu(X, 0, C[i], ss1, m4(a))
             b = new(tin, cp)
             self._conv(f"c1_{i}", [m4(a)], m4(b))
-            st2 = torch.zeros(1, 2, cp, dtype=torch.float64, device=dev)
+            st2 = stats2[i:i + 1] if need_stats else None
             if need_stats:
                 ops.bn_stats(m4(b), 0, C[i], 1, st2, 0, self._ws("stats", ops.bn_stats_workspace(1, tin * rpf, C[i])))
             ss2, mr2 = self._bn(blk.bn2, pn + ".bn2", st2, 0, 1, tin * rpf, C[i], cp)
@@ -447,7 +449,8 @@ class DUFNet(BaseNet):
         f0, tin, _, _ = P.frames_of(P.L)
         ctp = P.pad(P.ctot)
         Xt = m4(cat[1 + f0:1 + f0 + tin])
-        sst, mrt = self._bn(self.denseLayer.tail.bn, "denseLayer.tail.bn", stats[f0:f0 + tin], 0, tin, rpf, P.ctot, ctp)
+        sst, mrt = self._bn(self.denseLayer.tail.bn, "denseLayer.tail.bn", stats[f0:f0 + tin] if need_stats else None, 0, tin,
+                            rpf, P.ctot, ctp)
         at = new(tin, ctp)
         ops.bn_relu(Xt, 0, P.ctot, sst, m4(at))
         feat = new(tin, 256)
