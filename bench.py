@@ -387,7 +387,7 @@ def main():
         dom = max(agg, key=lambda k: agg[k][1])
         traffic = None
         try:       # per-launch dram__bytes_read+write of the same step under ncu (tools/ncu_summary.py)
-            with open(os.path.join(ROOT, "profiles", "r01_duf_by_kernel_v3.json" if WORKLOAD == "duf" else "r01_dram_by_kernel_v5.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "r01_duf_by_kernel_v3.json" if WORKLOAD == "duf" else "r01_dram_by_kernel_v9.json")) as f:
                 traffic = json.load(f).get({"tapgemm": "tapgemm_tc2_kernel", "wgrad": "wgrad_tc_kernel"}.get(dom, dom), {}).get("dram_bytes_per_launch")
         except (OSError, ValueError):
             pass
