@@ -17,6 +17,7 @@ CASES = [
     ("dufnet16_x2", dict(in_channels=1, out_channels=1, num_frames=7, size_filter=5, upscale_factor=2, backbone="_DenseLayer16"), 1, 16, 12),
     ("dufnet16_x3_c2", dict(in_channels=2, out_channels=2, num_frames=7, size_filter=3, upscale_factor=3, backbone="_DenseLayer16"), 1, 12, 12),
     ("dufnet28_x2", dict(in_channels=1, out_channels=1, num_frames=7, size_filter=5, upscale_factor=2, backbone="_DenseLayer28"), 1, 12, 12),
+    ("dufnet52_x2", dict(in_channels=1, out_channels=1, num_frames=7, size_filter=5, upscale_factor=2, backbone="_DenseLayer52"), 1, 10, 12),
 ]
 
 
@@ -56,7 +57,11 @@ def synth_frames(n, t, h, w, r, cin, seed):
 def main():
     ref = load_reference.load()
     DUFNet = load_reference._load("src.model.nets.duf_net", "src/model/nets/duf_net.py").DUFNet
+    import sys
+    only = set(sys.argv[1:])
     for idx, (name, kw, n, h, w) in enumerate(CASES):
+        if only and name not in only:
+            continue
         torch.manual_seed(idx)
         net = DUFNet(**kw)
         net.load_state_dict(duf_fill(net.state_dict(), 3000 + idx))
