@@ -137,3 +137,24 @@ def test_restated_matches_live_reference(r, G):
     got = restated.drfnet_forward(x, dict(net.state_dict()), r)
     for a, b in zip(got, want):
         assert (a - b).abs().max() <= 1e-5 * b.abs().max()
+
+
+@pytest.mark.skipif(not load_reference.available(), reason="/root/reference not mounted")
+@pytest.mark.parametrize("backbone,r,cin", [("_DenseLayer16", 4, 1), ("_DenseLayer28", 3, 2), ("_DenseLayer52", 2, 1)])
+def test_restated_dufnet_matches_live_reference(backbone, r, cin):
+    """oracle.restated.dufnet_forward against the reference's own DUFNet (duf_net.py:9-99), default initialisation,
+    training (batch statistics) and evaluation (running statistics) mode"""
+    load_reference.load()
+    DUFNet = load_reference._load("src.model.nets.duf_net", "src/model/nets/duf_net.py").DUFNet
+    torch.manual_seed(r)
+    net = DUFNet(cin, cin, 7, 5, r, backbone)
+    x = [torch.randn(2, cin, 9, 8) for _ in range(7)]
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    net.train()
+    want = net(x)
+    got = restated.dufnet_forward(x, sd, 5, r, training=True)
+    assert (got - want).abs().max() <= 1e-5 * want.abs().max()
+    net.eval()
+    want = net(x)
+    got = restated.dufnet_forward(x, dict(net.state_dict()), 5, r, training=False)
+    assert (got - want).abs().max() <= 1e-5 * want.abs().max()
