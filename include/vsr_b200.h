@@ -357,6 +357,19 @@ int vsr_duf_filter_bwd(const void* logits, int32_t ld_logits, int32_t dtype, con
                        int32_t n, int32_t cin, int32_t h, int32_t w, int32_t size_filter, int32_t r, void* dlogits,
                        void* dres, int32_t ld_res, void* stream);
 
+/*
+ * Device-side data front end (the callers of the path).  One batch of training items from cine volumes
+ * resident in device memory, vol = [seqs][frames][h][w] fp32 intensities (LR volume: r = 1; HR volume: r = upscale):
+ * per item the temporal window (acdc_vsr_dataset.py:59-78), RandomHorizontalFlip / RandomVerticalFlip /
+ * RandomCropPatch (transforms.py:321-450: the crop is taken from the flipped image), Normalize (:154-168) and the
+ * default collate, written as frames out = [f_count][n][ph*r][pw*r] (frames f_first .. f_first+f_count-1 of the window).
+ * tab: device int32 [n][5 + nf] = {sequence, flip_x, flip_y, y0, x0, frame_0 .. frame_{nf-1}}, y0 / x0 / ph / pw in
+ * LR pixels.  The random decisions are the caller's (the reference draws them with Python's `random`).
+ */
+int vsr_cine_gather(const float* vol, int32_t seqs, int32_t frames, int32_t h, int32_t w_, const int32_t* tab,
+                    int32_t n, int32_t nf, int32_t r, int32_t f_first, int32_t f_count, int32_t ph, int32_t pw,
+                    float mean, float std, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -381,6 +381,22 @@ class EmuOps:
         dres.copy_(gr.to(dres.dtype))
         self.launches += 1
 
+    # ---- device-side data front end --------------------------------------------------------
+    def cine_gather(self, vol, tab, r, f_first, f_count, mean, std, out):
+        H, W = vol.shape[-2:]
+        ph, pw = out.shape[-2], out.shape[-1]
+        for i, row in enumerate(tab.tolist()):
+            seq, fx, fy, y0, x0 = row[:5]
+            for f in range(f_count):
+                img = vol[seq, row[5 + f_first + f]]
+                if fx:
+                    img = img.flip(1)
+                if fy:
+                    img = img.flip(0)
+                crop = img[y0 * r:y0 * r + ph, x0 * r:x0 * r + pw]
+                out[f, i, 0] = (crop - torch.tensor(mean, dtype=crop.dtype)) / torch.tensor(std, dtype=crop.dtype)
+        self.launches += 1
+
     # ---- loss / metrics ----------------------------------------------------------------
     def loss_fwd_bwd(self, out, target, kind, param, grad_scale, partials, grad):
         d = out - target

@@ -223,3 +223,23 @@ def test_upsample_linear_fwd_bwd(ac, three_d):
     dx = torch.empty_like(x)
     ops.upsample_linear_bwd(dy, dx, ac)
     assert (dx - xr.grad).abs().max() <= 1e-4
+
+
+@pytest.mark.gpu
+def test_device_cine_loader_bit_exact_vs_host_loader():
+    """vsr_cine_gather (window + flips + crop + Normalize + collate on the device) against the host loader: bit-exact"""
+    import torch
+    from vsr_b200.data import Dataloader, DeviceCineLoader, SyntheticCineDataset
+    for misr, r in ((False, 4), (True, 2), (False, 3)):
+        kw = dict(downscale_factor=r, num_frames=7 if misr else 5, temporal_order="middle" if misr else "last",
+                  type="train", num_sequences=2, patch_size=(13, 10), seed=5, misr=misr)
+        host_ds, dev_ds = SyntheticCineDataset(**kw), SyntheticCineDataset(**kw)
+        host = iter(Dataloader(host_ds, batch_size=4, pin_memory=False))
+        dev = iter(DeviceCineLoader(dev_ds, "cuda", batch_size=4))
+        for _ in range(3):
+            a, b = next(host), next(dev)
+            assert all(torch.equal(x, y.cpu()) for x, y in zip(a["lr_imgs"], b["lr_imgs"]))
+            if misr:
+                assert torch.equal(a["hr_img"], b["hr_img"].cpu())
+            else:
+                assert all(torch.equal(x, y.cpu()) for x, y in zip(a["hr_imgs"], b["hr_imgs"]))

@@ -118,3 +118,26 @@ def test_sisr_net_is_the_vsr_net_on_a_repeated_frame():
     ref = restated.drfnet_forward([x, x, x], fx["state_dict"], kw["upscale_factor"])
     for a, b in zip(outs, ref):
         assert (a - b).abs().max() <= 2e-5 * b.abs().max()
+
+
+def test_device_cine_loader_equals_host_loader():
+    """DeviceCineLoader (volumes resident on the device, one gather kernel per batch) yields bit-identical batches to
+    Dataloader(SyntheticCineDataset): same windows, flips, crops, normalisation (transforms.py:154-168,321-450)."""
+    import torch
+    from tests.emu import EmuOps
+    from vsr_b200.data import Dataloader, DeviceCineLoader, SyntheticCineDataset
+    for misr in (False, True):
+        kw = dict(downscale_factor=4, num_frames=5 if not misr else 7, temporal_order="last" if not misr else "middle",
+                  type="train", num_sequences=2, patch_size=(12, 10), seed=3, misr=misr)
+        host_ds, dev_ds = SyntheticCineDataset(**kw), SyntheticCineDataset(**kw)
+        host = iter(Dataloader(host_ds, batch_size=3, pin_memory=False))
+        dev = iter(DeviceCineLoader(dev_ds, "cpu", batch_size=3, ops=EmuOps()))
+        for _ in range(3):
+            a, b = next(host), next(dev)
+            for x, y in zip(a["lr_imgs"], b["lr_imgs"]):
+                assert x.shape == y.shape == (3, 1, 12, 10) and torch.equal(x, y)
+            if misr:
+                assert torch.equal(a["hr_img"], b["hr_img"]) and b["hr_img"].shape == (3, 1, 48, 40)
+            else:
+                assert len(b["hr_imgs"]) == 5 and all(torch.equal(x, y) for x, y in zip(a["hr_imgs"], b["hr_imgs"]))
+            assert torch.equal(a["index"], b["index"])

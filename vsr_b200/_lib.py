@@ -98,6 +98,8 @@ _SIGS = {
                                     C.c_void_p]),
     "vsr_scale": (C.c_int, [C.c_void_p, C.c_int64, C.c_float, C.c_void_p]),
     "vsr_cast": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p]),
+    "vsr_cine_gather": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p] + [C.c_int32] * 7 +
+                        [C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
     "vsr_copy_window": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                   C.c_int64, C.c_int32, C.c_void_p]),
     "vsr_bn_stats_workspace": (C.c_size_t, [C.c_int32, C.c_int64, C.c_int32]),

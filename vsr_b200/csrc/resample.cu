@@ -223,3 +223,47 @@ extern "C" int vsr_upsample_linear_bwd(const float* dy, float* dx, int32_t nc, i
   VSR_CHECK_LAUNCH("vsr_upsample_linear_bwd");
   return VSR_OK;
 }
+
+// ---- device-side data front end ---------------------------------------------------------------------------
+// One batch of training items from cine volumes resident in device memory: temporal window, horizontal / vertical
+// flip, crop (taken from the flipped image) and normalisation, written as collated frames.
+// tab: int32 [n][5 + nf] = {sequence, flip_x, flip_y, y0, x0, frame_0 .. frame_{nf-1}} (y0, x0 in LR pixels).
+namespace vsr {
+namespace {
+__global__ void __launch_bounds__(256) cine_gather_kernel(const float* __restrict__ vol, int T, int H, int W,
+                                                         const int* __restrict__ tab, int ld, int n, int r, int f_first,
+                                                         int f_count, int PH, int PW, float mean, float std,
+                                                         float* __restrict__ out) {
+  const long total = (long)f_count * n * PH * PW;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % PW);
+    long q = i / PW;
+    const int y = (int)(q % PH);
+    q /= PH;
+    const int item = (int)(q % n), f = (int)(q / n);
+    const int* t = tab + (long)item * ld;
+    int sy = __ldg(t + 3) * r + y, sx = __ldg(t + 4) * r + x;
+    if (__ldg(t + 2)) sy = H - 1 - sy;
+    if (__ldg(t + 1)) sx = W - 1 - sx;
+    const float v = __ldg(vol + (((long)__ldg(t) * T + __ldg(t + 5 + f_first + f)) * H + sy) * W + sx);
+    out[i] = __fdiv_rn(__fsub_rn(v, mean), std);      // Normalize (transforms.py:154-168) in the host's fp32 order
+  }
+}
+}  // namespace
+}  // namespace vsr
+
+extern "C" int vsr_cine_gather(const float* vol, int32_t seqs, int32_t frames, int32_t h, int32_t w_, const int32_t* tab,
+                               int32_t n, int32_t nf, int32_t r, int32_t f_first, int32_t f_count, int32_t ph, int32_t pw,
+                               float mean, float std, float* out, void* stream) {
+  using namespace vsr;
+  VSR_CHECK_ARG(vol && tab && out && seqs > 0 && frames > 0 && h > 0 && w_ > 0 && n > 0 && nf > 0 && r >= 1,
+                "vsr_cine_gather: bad arguments");
+  VSR_CHECK_ARG(f_first >= 0 && f_count > 0 && f_first + f_count <= nf && ph > 0 && pw > 0 && ph * r <= h && pw * r <= w_,
+                "vsr_cine_gather: frame range / patch outside the volume");
+  VSR_CHECK_ARG(std != 0.f, "vsr_cine_gather: std must not be zero");
+  const long total = (long)f_count * n * ph * r * pw * r;
+  cine_gather_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      vol, frames, h, w_, tab, 5 + nf, n, r, f_first, f_count, ph * r, pw * r, mean, std, out);
+  VSR_CHECK_LAUNCH("vsr_cine_gather");
+  return VSR_OK;
+}

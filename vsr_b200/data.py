@@ -92,21 +92,34 @@ class SyntheticCineDataset(Dataset):
             start, end = t - (n - 1) // 2, t + ((n - 1) - (n - 1) // 2) + 1
         return [i % T for i in range(start, end)]
 
-    def __getitem__(self, index):
+    def draw(self, index):
+        """The random decisions of one item, in the order __getitem__ consumes the generator:
+        (sequence, frame indices, flip_x, flip_y, y0, x0, patch_h, patch_w) — the crop is taken from the flipped image
+        (transforms.py:321-450: RandomHorizontalFlip, RandomVerticalFlip, then RandomCropPatch)."""
         s, t = self.data[index]
         idx = self._window(t) if self.type == "train" or self.misr else list(range(self.T))
-        lr, hr = self.lr[s][idx], self.hr[s][idx]
+        h, w = self.lr[s].shape[1:]
+        fx = fy = False
+        y0 = x0 = 0
+        ph, pw = h, w
         if self.type == "train":
-            if self.rng.random() < 0.5:
-                lr, hr = lr[:, :, ::-1], hr[:, :, ::-1]
-            if self.rng.random() < 0.5:
-                lr, hr = lr[:, ::-1], hr[:, ::-1]
+            fx = bool(self.rng.random() < 0.5)
+            fy = bool(self.rng.random() < 0.5)
             if self.patch:
                 ph, pw = self.patch
-                y0 = int(self.rng.integers(0, lr.shape[1] - ph + 1))
-                x0 = int(self.rng.integers(0, lr.shape[2] - pw + 1))
-                lr = lr[:, y0:y0 + ph, x0:x0 + pw]
-                hr = hr[:, y0 * self.r:(y0 + ph) * self.r, x0 * self.r:(x0 + pw) * self.r]
+                y0 = int(self.rng.integers(0, h - ph + 1))
+                x0 = int(self.rng.integers(0, w - pw + 1))
+        return s, idx, fx, fy, y0, x0, ph, pw
+
+    def __getitem__(self, index):
+        s, idx, fx, fy, y0, x0, ph, pw = self.draw(index)
+        lr, hr = self.lr[s][idx], self.hr[s][idx]
+        if fx:
+            lr, hr = lr[:, :, ::-1], hr[:, :, ::-1]
+        if fy:
+            lr, hr = lr[:, ::-1], hr[:, ::-1]
+        lr = lr[:, y0:y0 + ph, x0:x0 + pw]
+        hr = hr[:, y0 * self.r:(y0 + ph) * self.r, x0 * self.r:(x0 + pw) * self.r]
         norm = lambda a: torch.from_numpy(((np.ascontiguousarray(a) - self.mean) / self.std).astype(np.float32))
         lr, hr = norm(lr), norm(hr)
         if self.misr:
@@ -179,3 +192,56 @@ class DeviceStager:
             nxt = fetch()
             torch.cuda.current_stream(self.device).wait_event(ev)
             yield dev
+
+
+class DeviceCineLoader:
+    """The same batches as `Dataloader(SyntheticCineDataset(...))` without the host in the loop (SURVEY §8f rank 3,
+    the augmentation half): the cine volumes live in device memory, and one kernel per batch (`vsr_cine_gather`) does
+    what the reference does per item on the host — temporal window (acdc_vsr_dataset.py:59-78), RandomHorizontalFlip /
+    RandomVerticalFlip / RandomCropPatch (transforms.py:321-450), Normalize (:154-168), ToTensor and the default
+    collate — writing the collated `[N,1,h,w]` frames directly.  The random decisions come from the dataset's own
+    generator in the dataset's own order (`SyntheticCineDataset.draw`), so a batch is bit-identical to the host
+    loader's batch of the same items.  Sequences of one dataset share a shape."""
+
+    def __init__(self, dataset, device, batch_size=1, shuffle=False, drop_last=False, ops=None):
+        self.dataset, self.device, self.batch_size = dataset, torch.device(device), batch_size
+        self.shuffle, self.drop_last, self._ops = shuffle, drop_last, ops
+        self.lr = torch.from_numpy(np.stack(dataset.lr).astype(np.float32)).to(self.device)      # [S, T, h, w]
+        self.hr = torch.from_numpy(np.stack(dataset.hr).astype(np.float32)).to(self.device)      # [S, T, rh, rw]
+
+    def __len__(self):
+        n = len(self.dataset)
+        return n // self.batch_size if self.drop_last else -(-n // self.batch_size)
+
+    def _backend(self):
+        if self._ops is not None:
+            return self._ops
+        from .ops import cuda_ops
+        return cuda_ops()
+
+    def batch(self, indices):
+        ds, ops = self.dataset, self._backend()
+        draws = [ds.draw(int(i)) for i in indices]
+        nf = len(draws[0][1])
+        ph, pw = draws[0][6], draws[0][7]
+        n = len(draws)
+        # per item: sequence, flip_x, flip_y, y0, x0, then the nf frame indices
+        tab = torch.tensor([[d[0], int(d[2]), int(d[3]), d[4], d[5]] + list(d[1]) for d in draws], dtype=torch.int32)
+        tab = tab.to(self.device, non_blocking=True)
+        hr_frames = [nf // 2 if nf % 2 == 1 else nf // 2 - 1] if ds.misr else list(range(nf))
+        lr = torch.empty(nf, n, 1, ph, pw, device=self.device)
+        hr = torch.empty(len(hr_frames), n, 1, ph * ds.r, pw * ds.r, device=self.device)
+        ops.cine_gather(self.lr, tab, 1, 0, nf, ds.mean, ds.std, lr)
+        ops.cine_gather(self.hr, tab, ds.r, hr_frames[0], len(hr_frames), ds.mean, ds.std, hr)
+        out = {"lr_imgs": list(lr.unbind(0)), "index": torch.as_tensor(list(indices))}
+        if ds.misr:
+            out["hr_img"] = hr[0]
+        else:
+            out["hr_imgs"] = list(hr.unbind(0))
+        return out
+
+    def __iter__(self):
+        n = len(self.dataset)
+        order = np.random.permutation(n) if self.shuffle else np.arange(n)
+        for b in range(len(self)):
+            yield self.batch(order[b * self.batch_size:(b + 1) * self.batch_size])

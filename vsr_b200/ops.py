@@ -385,6 +385,16 @@ class CudaOps:
               "vsr_duf_filter_bwd")
         self.launches += 1
 
+    # ---- device-side data front end --------------------------------------------------------
+    def cine_gather(self, vol, tab, r, f_first, f_count, mean, std, out):
+        """out[f, i] = normalised crop of frame tab[i, 5 + f_first + f] of sequence tab[i, 0] (flips, crop from `tab`)"""
+        _need_cuda(vol, tab, out)
+        s_, t_, h, w_ = vol.shape
+        check(self.lib.vsr_cine_gather(_p(vol), s_, t_, h, w_, _p(tab), tab.shape[0], tab.shape[1] - 5, r, f_first, f_count,
+                                       out.shape[-2] // r, out.shape[-1] // r, float(mean), float(std), _p(out), _stream()),
+              "vsr_cine_gather")
+        self.launches += 1
+
     # ---- loss / metrics ----------------------------------------------------------------
     def loss_fwd_bwd(self, out, target, kind, param, grad_scale, partials, grad):
         _need_cuda(out, target, partials, grad)
