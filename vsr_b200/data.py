@@ -161,7 +161,8 @@ class DeviceStager:
 
     def _move(self, obj):
         if isinstance(obj, torch.Tensor):
-            if obj.device == self.device:              # DeviceCineLoader batches are already there
+            if obj.device.type == self.device.type and self.device.index in (None, obj.device.index):
+                # DeviceCineLoader batches are already there
                 return obj
             src = obj if obj.is_pinned() else obj.pin_memory()
             return src.to(self.device, non_blocking=True)
