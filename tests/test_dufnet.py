@@ -378,3 +378,26 @@ def test_gpu_ragged_sizes_match_emulation(shape):
     assert float((res["cuda"][1] - res["emu"][1]).norm() / res["emu"][1].norm()) <= 3e-3
     assert _rel(res["bf16"][0], res["emu"][0]) <= 5e-2
     assert float((res["bf16"][1] - res["emu"][1]).norm() / res["emu"][1].norm()) <= 0.25
+
+
+@pytest.mark.gpu
+def test_gpu_misr_trainer_with_device_loader():
+    """the whole training path on the device: DeviceCineLoader -> MISRTrainer (CUDA-graphed fused step) -> log"""
+    from vsr_b200.data import DeviceCineLoader, SyntheticCineDataset
+    from vsr_b200.metrics import PSNR, SSIM
+    from vsr_b200.optim import FlatAdam
+    from vsr_b200.runner import MISRTrainer
+    ds = SyntheticCineDataset(4, num_frames=7, temporal_order="middle", type="train", num_sequences=1, patch_size=(16, 16),
+                              misr=True)
+    ds.data = ds.data[:8]
+    loader = DeviceCineLoader(ds, "cuda:0", batch_size=4)
+    torch.manual_seed(0)
+    net = DUFNet(1, 1, 7, 5, 4, "_DenseLayer16", precision="bf16")
+    tr = MISRTrainer("cuda:0", loader, loader, net, [torch.nn.L1Loss()], [1.0], [PSNR(), SSIM()],
+                     FlatAdam(net.parameters(), lr=1e-3), None, None, None, 1, use_graph=True)
+    logs = [tr._run_epoch("training")[0] for _ in range(4)]          # 8 steps: eager, eager, capture, replays
+    assert list(logs[0]) == ["Loss", "L1Loss", "PSNR", "SSIM"]
+    assert all(torch.isfinite(torch.tensor(list(l.values()))).all() for l in logs)
+    assert logs[-1]["Loss"] < logs[0]["Loss"]
+    vlog, _, out = tr._run_epoch("validation")
+    assert out.shape == (4, 1, 64, 64) and vlog["PSNR"] > 0
