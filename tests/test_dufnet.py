@@ -401,3 +401,36 @@ def test_gpu_misr_trainer_with_device_loader():
     assert logs[-1]["Loss"] < logs[0]["Loss"]
     vlog, _, out = tr._run_epoch("validation")
     assert out.shape == (4, 1, 64, 64) and vlog["PSNR"] > 0
+
+
+def test_checkpoint_interchange_with_live_reference(tmp_path):
+    """base_trainer.py:229-237 / base_predictor.py:135-136: a checkpoint written from the drop-in loads (strict) into
+    the reference's DUFNet and back, and both nets then agree (training mode: outputs, running buffers)."""
+    from oracle import load_reference
+    if not load_reference.available():
+        pytest.skip("/root/reference not mounted")
+    load_reference.load()
+    Ref = load_reference._load("src.model.nets.duf_net", "src/model/nets/duf_net.py").DUFNet
+    kw = dict(in_channels=1, out_channels=1, num_frames=7, size_filter=5, upscale_factor=3, backbone="_DenseLayer16")
+    torch.manual_seed(1)
+    ours = DUFNet(**kw)
+    ours._ops = EmuOps()
+    torch.save({"net": ours.state_dict()}, tmp_path / "ck.pth")
+    ref = Ref(**kw)
+    ref.load_state_dict(torch.load(tmp_path / "ck.pth")["net"], strict=True)
+    x = [torch.randn(2, 1, 9, 10) for _ in range(7)]
+    ours.train(), ref.train()
+    with torch.no_grad():
+        a, b = ours(x), ref(x)
+    assert _rel(a, b) <= 2e-5
+    sa, sb = ours.state_dict(), ref.state_dict()
+    assert list(sa) == list(sb)
+    for k in sa:
+        if "running" in k or "num_batches" in k:
+            assert torch.allclose(sa[k].double(), sb[k].double(), rtol=1e-5, atol=1e-6), k
+    ours2 = DUFNet(**kw)
+    ours2.load_state_dict(ref.state_dict(), strict=True)          # and back, buffers included
+    ours2._ops = EmuOps()
+    ours2.eval(), ref.eval()
+    with torch.no_grad():
+        assert _rel(ours2(x), ref(x)) <= 2e-5
