@@ -1,21 +1,24 @@
 """DUFNet — the Conv3d network of the reference (src/model/nets/duf_net.py:9-214) on the tap-GEMM kernels.
 
 Layout: every feature map is pixel-major and TIME-MAJOR, [frames, N, h, w, C] (C contiguous), so that
-  * a temporal tap of a Conv3d is the same map seen through a pointer shifted by whole frames: the 3x3x3
-    convolutions are tap-GEMMs with three frame-shifted source views (zero frames at both ends give the
-    temporal padding of `_denseBlock1`; `_denseBlock2` simply produces two frames fewer),
+  * a temporal tap of a Conv3d is the same map seen through a pointer shifted by whole frames: the data gradient
+    of a 3x3x3 growth convolution is a 27-tap tap-GEMM over three frame-shifted views of the concat gradient
+    (a zero frame at both ends gives the temporal padding of `_denseBlock1`; `_denseBlock2` has two frames fewer),
+  * its forward pass and weight gradient use the (1,3,3) COLUMN FORM: the three temporal taps are extra output
+    columns of a 9-tap tap-GEMM (N = 3G instead of G, one source, the A operand read once for all three) and
+    `vsr_tshift_add` / `vsr_tshift_gather` move between the [.., 3G] columns and the concat slice,
   * the temporal crop `concat[:, :, 1:-1]` (duf_net.py:126) is a pointer offset,
   * the dense concatenation (duf_net.py:123-128) is ONE buffer: each layer reads the channel prefix and
-    its 3x3x3 convolution writes its growth slice in place; `torch.cat` never runs.
+    its growth convolution writes its slice in place; `torch.cat` never runs.
 BatchNorm3d statistics are kept per frame and per channel of that buffer (each slice is reduced once, when
-it is produced) and combined per layer over its frame range.  BatchNorm + ReLU is one bandwidth-bound pass
-in front of every convolution (`vsr_bn_relu`), its backward two passes (`vsr_bn_relu_bwd`).  The tail —
-softmax over the 5x5 taps, local filtering of the centre frame, pixel shuffle, residual add
+it is produced, in the shift-add pass) and combined per layer over its frame range.  BatchNorm + ReLU is one
+bandwidth-bound pass in front of every convolution (`vsr_bn_relu`), its backward two passes (`vsr_bn_relu_bwd`).
+The tail — softmax over the 5x5 taps, local filtering of the centre frame, pixel shuffle, residual add
 (duf_net.py:66-97) — is one kernel each way (`vsr_duf_filter`).
 
 bf16 mode runs every convolution on the tcgen05 tap-GEMM: channel counts are padded to multiples of 64 with
-structural-zero weights (64 + 32 i -> 64, 128, 128, 192, 192, 256) and the growth convolutions use 64-wide
-output tiles whose upper half lands on the not-yet-written slices of the following layers.
+structural-zero weights (64 + 32 i -> 64, 128, 128, 192, 192, 256; 3G = 96 columns -> 128); the concat gradient
+buffer is one 64-channel window wider than the net needs so that every growth slice can be read as a window.
 """
 import numpy as np
 import torch
@@ -48,8 +51,9 @@ class DufPlan(DrfPlan):
         self.C = [64 + G * i for i in range(self.L + 1)]       # input channels of layer i; C[L] feeds the tail
         self.ctot = self.C[-1]
         self.ccat = self.ctot + (64 - G if bf16 else 0)
-        self.nt2 = 64 if bf16 else G
-        self.ntz = -(-3 * G // 64) * 64                          # tensor-core forward of the growth convolutions
+        # growth convolutions, forward and weight gradient: the three temporal taps as output columns (3G, padded to a
+        # multiple of 64 for the tensor-core kernels)
+        self.ntz = -(-3 * G // 64) * 64 if bf16 else 3 * G
         self.cf, self.cr = size_filter * size_filter * r * r, in_channels * r * r
         self.cfp, self.crp = self.pad(self.cf), self.pad(self.cr)
         self.params, self.n_params, self.fwd, self.bwd = {}, 0, {}, {}
@@ -132,33 +136,20 @@ class DufPlan(DrfPlan):
             W1, W2 = self._W(p + ".conv1"), self._W(p + ".conv2")
             self._pointwise(f"c1_{i}", lambda o, c, W=W1: m(W, o, c, 0, 0, 0), cp, cp, self._mbias(p + ".conv1", cp))
             self._pointwise(f"c1_{i}", lambda o, c, W=W1: m(W, c, o, 0, 0, 0), cp, cp, None, store=self.bwd)
-            # 3x3x3 growth convolution: sources 0..2 = the input seen through frame shifts -1, 0, +1
-            j, k = self._jk(self.nt2)
+            # 3x3x3 growth convolution, forward AND weight gradient: the three temporal taps as extra output columns of a
+            # (1,3,3) tap-GEMM (N = 3G: one source, the A operand read once for all three); vsr_tshift_add /
+            # vsr_tshift_gather move between the [.., 3G] column form and the concat slice.  The bias rides in the
+            # centre block (kt = 1: always a valid frame), so the shift-add adds it once and its gradient is the centre
+            # block of the column sums of dz.
+            j, k = self._jk(self.ntz)
             taps, slabs = [], []
-            for kt in range(3):
-                for ky in range(3):
-                    for kx in range(3):
-                        for b in range(cp // kc):
-                            taps.append((kt, ky - 1, kx - 1, b * kc))
-                            slabs.append(m(W2, j, b * kc + k, kt, ky, kx))
-            if not self.bf16:
-                self.fwd[f"c2_{i}"] = Layer(f"c2_{i}", TapTable(kc, self.nt2, [(C[i], taps)]), slabs, self.ccat,
-                                            self._mbias(p + ".conv2", self.ccat, at=C[i]))
-            if self.bf16:
-                # tensor-core forward AND weight gradient: the three temporal taps as extra output columns of a
-                # (1,3,3) tap-GEMM (N = 3G, A read once for all three); vsr_tshift_add / vsr_tshift_gather move
-                # between the [.., 3G] column form and the concat slice
-                j, k = self._jk(self.ntz)
-                taps, slabs = [], []
-                for ky in range(3):
-                    for kx in range(3):
-                        for b in range(cp // kc):
-                            taps.append((0, ky - 1, kx - 1, b * kc))
-                            slabs.append(m(W2, np.where(j < 3 * G, j % G, -1), b * kc + k, j // G, ky, kx))
-                # the bias rides in the centre block (kt = 1: always a valid frame), so the shift-add adds it once and
-                # its gradient is the centre block of the column sums of dz
-                self.fwd[f"c2z_{i}"] = Layer(f"c2z_{i}", TapTable(kc, self.ntz, [(0, taps)]), slabs, self.ntz,
-                                             self._mbias(p + ".conv2", self.ntz, at=G))
+            for ky in range(3):
+                for kx in range(3):
+                    for b in range(cp // kc):
+                        taps.append((0, ky - 1, kx - 1, b * kc))
+                        slabs.append(m(W2, np.where(j < 3 * G, j % G, -1), b * kc + k, j // G, ky, kx))
+            self.fwd[f"c2z_{i}"] = Layer(f"c2z_{i}", TapTable(kc, self.ntz, [(0, taps)]), slabs, self.ntz,
+                                         self._mbias(p + ".conv2", self.ntz, at=G))
             # its data gradient: sources 0..2 = the concat gradient seen through frame shifts +1, 0, -1
             splits = self._split(cp)
             nt = splits[0][1]
@@ -421,31 +412,15 @@ class DUFNet(BaseNet):
             if need_stats:
                 ops.bn_stats(m4(b), 0, C[i], 1, st2, 0, self._ws("stats", ops.bn_stats_workspace(1, tin * rpf, C[i])))
             ss2, mr2 = self._bn(blk.bn2, pn + ".bn2", st2, 0, 1, tin * rpf, C[i], cp)
-            if P.bf16:                                                       # (1,3,3) form: no frame-shifted views
-                c = cbuf = new(tin, cp)
-                views = None
-            elif i < P.n1:                                                   # padding (1,1,1): zero frames at both ends
-                cbuf = new(tin + 2, cp)
-                cbuf[0].zero_(); cbuf[tin + 1].zero_()
-                c = cbuf[1:tin + 1]
-                views = [m4(cbuf[kt:kt + tin]) for kt in range(3)]
-            else:                                                            # padding (0,1,1): two frames fewer
-                c = cbuf = new(tin, cp)
-                views = [m4(cbuf[kt:kt + tout]) for kt in range(3)]
+            c = new(tin, cp)
             ops.bn_relu(m4(b), 0, C[i], ss2, m4(c))
             out = m4(cat[1 + fo:1 + fo + tout])
-            if P.bf16:
-                z = new(tin, P.ntz)
-                self._conv(f"c2z_{i}", [m4(c)], m4(z))
-                ops.tshift_add(m4(z), G, tin, 1 if i < P.n1 else 0, None, out, C[i],
-                               tout, stats[fo:fo + tout] if need_stats else None, C[i],
-                               self._ws("stats", ops.bn_stats_workspace(tout, rpf, G)) if need_stats else None)
-            else:
-                self._conv(f"c2_{i}", views, out)
-                if need_stats:
-                    ops.bn_stats(out, C[i], G, tout, stats[fo:fo + tout], C[i],
-                                 self._ws("stats", ops.bn_stats_workspace(tout, rpf, G)))
-            saved.append((a, b, cbuf, ss1, mr1, ss2, mr2))
+            z = new(tin, P.ntz)
+            self._conv(f"c2z_{i}", [m4(c)], m4(z))                          # (1,3,3) column form ...
+            ops.tshift_add(m4(z), G, tin, 1 if i < P.n1 else 0, None, out, C[i],     # ... summed over the temporal taps
+                           tout, stats[fo:fo + tout] if need_stats else None, C[i],
+                           self._ws("stats", ops.bn_stats_workspace(tout, rpf, G)) if need_stats else None)
+            saved.append((a, b, c, ss1, mr1, ss2, mr2))
         f0, tin, _, _ = P.frames_of(P.L)
         ctp = P.pad(P.ctot)
         Xt = m4(cat[1 + f0:1 + f0 + tin])
@@ -522,20 +497,16 @@ class DUFNet(BaseNet):
         for i in reversed(range(P.L)):
             f0, tin, fo, tout = P.frames_of(i)
             pn = f"denseLayer.conv{i}"
-            a, b, cbuf, ss1, mr1, ss2, mr2 = saved[i]
+            a, b, c, ss1, mr1, ss2, mr2 = saved[i]
             cp = a.shape[-1]
             dz = m4(dcat[1 + fo:1 + fo + tout])
             if i < P.n1:
                 gviews = [m4(dcat[1 + f0 + 1 - kt:1 + f0 + 1 - kt + tin]) for kt in range(3)]
             else:
                 gviews = [m4(dcat[f0 + 2 - kt:f0 + 2 - kt + tin]) for kt in range(3)]
-            if P.bf16:
-                dzz = new(tin, P.ntz)
-                ops.tshift_gather(dz, C[i], G, tout, 1 if i < P.n1 else 0, m4(dzz), tin)
-                wgrad(f"c2z_{i}", [m4(cbuf)], m4(dzz))
-            else:
-                views = [m4(cbuf[kt:kt + (tin if i < P.n1 else tout)]) for kt in range(3)]
-                wgrad(f"c2_{i}", views, dz)
+            dzz = new(tin, P.ntz)
+            ops.tshift_gather(dz, C[i], G, tout, 1 if i < P.n1 else 0, m4(dzz), tin)
+            wgrad(f"c2z_{i}", [m4(c)], m4(dzz))
             dc = new(tin, cp)
             self._dgrad(f"c2_{i}", gviews, m4(dc))
             dbm = new(tin, cp)
