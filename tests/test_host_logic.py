@@ -141,3 +141,56 @@ def test_device_cine_loader_equals_host_loader():
             else:
                 assert len(b["hr_imgs"]) == 5 and all(torch.equal(x, y) for x, y in zip(a["hr_imgs"], b["hr_imgs"]))
             assert torch.equal(a["index"], b["index"])
+
+
+def test_predictor_cardiac_metrics_match_oracle(tmp_path):
+    """CardiacPSNR / CardiacSSIM inside the predictor's fused loop (acdc_vsr_predictor.py:134-154, metrics.py:116-165):
+    per-sample bounding boxes looked up by patient name, against the oracle on the cropped frames."""
+    import pickle
+    from pathlib import Path
+
+    import torch
+    from oracle import restated
+    from tests.emu import EmuOps
+    from vsr_b200.data import Dataloader
+    from vsr_b200.metrics import PSNR, CardiacPSNR, CardiacSSIM
+    from vsr_b200.nets import DRFNet
+    from vsr_b200.runner import VSRPredictor
+    boxes = {"patient001": (2, 30, 4, 32), "patient002": (0, 24, 8, 36)}
+    with open(tmp_path / "boxes.pkl", "wb") as f:
+        pickle.dump(boxes, f)
+    g = torch.Generator().manual_seed(3)
+    items = [{"lr_imgs": [torch.randn(1, 10, 10, generator=g) for _ in range(2)],
+              "hr_imgs": [torch.randn(1, 40, 40, generator=g) for _ in range(2)], "index": i} for i in range(2)]
+
+    class Two(torch.utils.data.Dataset):
+        data = [(Path("patient001_2d+1d_sequence03.nii.gz"),), (Path("patient002_2d+1d_sequence01.nii.gz"),)]
+
+        def __len__(self):
+            return 2
+
+        def __getitem__(self, i):
+            return items[i]
+
+    torch.manual_seed(0)
+    net = DRFNet(1, 1, 8, 2, 4)
+    net._ops = EmuOps()
+    metrics = [PSNR(), CardiacPSNR(str(tmp_path / "boxes.pkl")), CardiacSSIM(str(tmp_path / "boxes.pkl"))]
+    pred = VSRPredictor("cpu", Dataloader(Two(), batch_size=2, pin_memory=False), net, [torch.nn.L1Loss()], [1.0], metrics,
+                        saved_dir=str(tmp_path), exported=True)
+    log = pred.predict()
+    sd = {k: v.detach() for k, v in net.state_dict().items()}
+    want_p, want_s = [], []
+    for it, who in zip(items, ("patient001", "patient002")):
+        outs = restated.drfnet_forward([f[None] for f in it["lr_imgs"]], sd, 4)
+        h0, hn, w0, wn = boxes[who]
+        for o, y in zip(outs, it["hr_imgs"]):
+            a = restated.denormalize(o, "acdc")[..., h0:hn, w0:wn]
+            b = restated.denormalize(y[None], "acdc")[..., h0:hn, w0:wn]
+            want_p.append(float(restated.psnr(a, b)))
+            want_s.append(float(restated.ssim(a, b)))
+    assert abs(log["CardiacPSNR"] - sum(want_p) / 4) <= 1e-3
+    assert abs(log["CardiacSSIM"] - sum(want_s) / 4) <= 1e-4
+    rows = (tmp_path / "results.csv").read_text().strip().splitlines()
+    assert rows[0] == "name,PSNR,CardiacPSNR,CardiacSSIM,L1Loss" and len(rows) == 5
+    assert rows[1].startswith("patient001_2d_slice03_frame01,")

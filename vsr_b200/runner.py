@@ -46,8 +46,8 @@ class VSRTrainStep:
         self.loss_weights = [float(w) for w in loss_weights]
         self.metric_names = [m.__class__.__name__ for m in metric_fns]
         for m in self.metric_names:
-            if m not in ("PSNR", "SSIM"):
-                raise NotImplementedError(f"metric {m} has no fused kernel (supported: PSNR, SSIM)")
+            if m not in ("PSNR", "SSIM", "CardiacPSNR", "CardiacSSIM"):
+                raise NotImplementedError(f"metric {m} has no fused kernel (supported: PSNR, SSIM, CardiacPSNR, CardiacSSIM)")
         self.metric_fns = metric_fns
         self.mean, self.std = DATASET_STATS[dataset]
         self.pg = process_group
@@ -75,6 +75,9 @@ class VSRTrainStep:
         ws = self._buf("mws", (ops.metric_workspace(n * outs[0].shape[1], per) // 4 + 4,))
         vals = self._buf("mvals", (len(self.metric_names), T, n * outs[0].shape[1]))
         for i, (name, fn) in enumerate(zip(self.metric_names, self.metric_fns)):
+            if name.startswith("Cardiac"):
+                raise NotImplementedError("Cardiac* metrics need the patient of every sample: predictors only "
+                                          "(acdc_vsr_predictor.py:134-154); the reference's trainers do not use them")
             for t in range(T):
                 o, y = outs[t], targets[t]
                 if name == "PSNR":
@@ -225,10 +228,12 @@ class VSRTrainStep:
         return lvals, outs
 
     @torch.no_grad()
-    def eval_frames(self, inputs, targets):
+    def eval_frames(self, inputs, targets, patients=None):
         """The predictor's loop body (acdc_vsr_predictor.py:53-66) for a whole batch of sequences: forward under
         no_grad, then on the device per-frame losses [T, n_loss] (batch means) and per-frame, per-sample metrics
-        [n_metric, T, N] with the denormalisation fused.  Returns (outputs, losses, metrics); nothing syncs."""
+        [n_metric, T, N] with the denormalisation fused.  CardiacPSNR / CardiacSSIM (metrics.py:116-165) run the same
+        kernels on every sample's bounding box (`patients`: one name per sample, :134-154).
+        Returns (outputs, losses, metrics); nothing syncs."""
         net = self.net
         if not net._is_flat():
             net._flatten()
@@ -245,6 +250,21 @@ class VSRTrainStep:
         ws = self._buf("mws", (ops.metric_workspace(n * c, per) // 4 + 4,))
         vals = torch.zeros(len(self.metric_names), T, n * c, device=outs[0].device)
         for i, (name, fn) in enumerate(zip(self.metric_names, self.metric_fns)):
+            if name.startswith("Cardiac"):
+                if patients is None or len(patients) != n:
+                    raise ValueError(f"{name} needs the patient name of every sample of the batch")
+                m = fn.metric
+                for s_, who in enumerate(patients):
+                    h0, hn, w0, wn = fn.coordinates[who]
+                    for t in range(T):
+                        o = outs[t][s_:s_ + 1, :, h0:hn, w0:wn].contiguous()
+                        y = targets[t][s_:s_ + 1, :, h0:hn, w0:wn].contiguous()
+                        if name == "CardiacPSNR":
+                            ops.psnr(o, y, self.mean, self.std, float(m.max_value), vals[i, t, s_:s_ + 1], ws)
+                        else:
+                            ops.ssim(o.view(c, *o.shape[2:]), y.view(c, *y.shape[2:]), m.window, self.mean, self.std,
+                                     m.c1, m.c2, vals[i, t, s_ * c:(s_ + 1) * c], ws)
+                continue
             for t in range(T):
                 o, y = outs[t], targets[t]
                 if name == "PSNR":
@@ -252,7 +272,7 @@ class VSRTrainStep:
                 else:
                     ops.ssim(o.view(n * c, *o.shape[2:]), y.view(n * c, *y.shape[2:]), fn.window, self.mean,
                              self.std, fn.c1, fn.c2, vals[i, t], ws)
-        metrics = torch.stack([vals[i, :, :n] if name == "PSNR" else vals[i].view(T, n, c).mean(dim=2)
+        metrics = torch.stack([vals[i, :, :n] if name.endswith("PSNR") else vals[i].view(T, n, c).mean(dim=2)
                                for i, name in enumerate(self.metric_names)]) if self.metric_names else vals
         return outs, losses, metrics
 
@@ -508,6 +528,14 @@ class VSRPredictor:
         except (AttributeError, TypeError, IndexError):
             return f"sequence{int(index):05d}"
 
+    def _patients(self, index):
+        """patient name of every sample (`patient_..._sid` file stems, acdc_vsr_predictor.py:59-61) when a Cardiac*
+        metric asks for bounding boxes"""
+        if not any(m.__class__.__name__.startswith("Cardiac") for m in self.metric_fns):
+            return None
+        idx = index.tolist() if torch.is_tensor(index) else list(index)
+        return [self._name(i).split("_")[0] for i in idx]
+
     def _batches(self):
         if self.device.type == "cuda":
             from .data import DeviceStager
@@ -524,7 +552,7 @@ class VSRPredictor:
         for batch in self._batches():
             inputs, targets, index = batch["lr_imgs"], batch["hr_imgs"], batch["index"]
             bs, T = inputs[0].shape[0], len(inputs)
-            _, losses, metrics = self.step.eval_frames(inputs, targets)
+            _, losses, metrics = self.step.eval_frames(inputs, targets, self._patients(index))
             loss = (losses.mean(dim=0) * self.loss_weights).sum()
             host = torch.cat([loss.view(1), losses.mean(dim=0), metrics.mean(dim=(1, 2)) if metrics.numel() else metrics.view(0)])
             vals = host.tolist()                                   # the one host read-back of the batch
@@ -573,7 +601,7 @@ class MISRPredictor(VSRPredictor):
         for batch in self._batches():
             inputs, target, index = batch["lr_imgs"], batch["hr_img"], batch["index"]
             bs = inputs[0].shape[0]
-            _, losses, metrics = self.step.eval_frames(inputs, [target])        # losses [1, L], metrics [M, 1, bs]
+            _, losses, metrics = self.step.eval_frames(inputs, [target], self._patients(index))   # [1, L], [M, 1, bs]
             loss = (losses[0] * self.loss_weights).sum()
             host = torch.cat([loss.view(1), losses[0], metrics.mean(dim=(1, 2)) if metrics.numel() else metrics.view(0)])
             vals = host.tolist()                                               # the one host read-back of the batch
