@@ -242,6 +242,36 @@ def cpu_baseline(budget_s=20.0):
             "sample": f"{sample} of {BATCH} patches x T{frames_in()}, best of {len(times)} steps, torch {torch.__version__} CPU fp32"}
 
 
+def psnr_delta(precision, dev):
+    """BASELINE.json's "PSNR delta vs CPU ref": PSNR (after denormalize, src/utils.py:1-20) of the GPU path's output and
+    of the CPU reference port's output, both against the synthetic target, on the same inputs (2 patches) and the same
+    initial weights (seed 0, the reference's default initialisation); plus the largest tensor-normalised output error."""
+    from oracle import restated
+    lrs, hrs = make_batches(1, 2, 0, False)[0]
+    torch.manual_seed(0)
+    with torch.no_grad():
+        if WORKLOAD == "duf":
+            from vsr_b200.duf import DUFNet
+            net = DUFNet(precision=precision, **DUF_MODEL)
+            sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+            refs = [restated.dufnet_forward(lrs, sd, 5, 4, training=True)]
+            net = net.to(dev).train()
+            outs = [net([x.to(dev) for x in lrs]).float().cpu()]
+        else:
+            from vsr_b200.nets import DRFNet
+            net = DRFNet(precision=precision, **MODEL)
+            sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+            refs = restated.drfnet_forward(lrs, sd, 4)
+            net = net.to(dev)
+            outs = [o.float().cpu() for o in net([x.to(dev) for x in lrs])]
+        den = lambda t: restated.denormalize(t, "acdc")
+        p_ref = sum(float(restated.psnr(den(r), den(h))) for r, h in zip(refs, hrs)) / len(refs)
+        p_gpu = sum(float(restated.psnr(den(o), den(h))) for o, h in zip(outs, hrs)) / len(outs)
+        err = max(float((o - r).abs().max() / r.abs().max()) for o, r in zip(outs, refs))
+    return {"value": p_gpu - p_ref, "unit": "dB", "gpu_db": p_gpu, "cpu_ref_db": p_ref, "max_rel_output_error": err,
+            "sample": "2 patches, all frames, initial weights (seed 0), oracle port on the host"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -446,6 +476,10 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
+            try:
+                line["psnr_delta"] = psnr_delta(args.precision, dev)
+            except Exception as e:      # a reporting extra must never cost the bench line
+                line["psnr_delta"] = {"error": f"{type(e).__name__}: {e}"}
         emit(line)
     # hang-proof exit: synchronise, then leave without tearing NCCL / CUDA graphs down
     torch.cuda.synchronize()
