@@ -434,3 +434,35 @@ def test_checkpoint_interchange_with_live_reference(tmp_path):
     ours2.eval(), ref.eval()
     with torch.no_grad():
         assert _rel(ours2(x), ref(x)) <= 2e-5
+
+
+@pytest.mark.parametrize("backbone", ["_DenseLayer16", "_DenseLayer28", "_DenseLayer52"])
+@pytest.mark.parametrize("bf16", [False, True], ids=["fp32", "bf16"])
+def test_plan_invariants(backbone, bf16):
+    """structure of the packed tables: every convolution weight / bias is read by exactly one forward slab position
+    (so one un-pack pass returns its gradient), every data-gradient table covers the same weights, taps stay inside
+    their sources, and tensor-core tables have the shapes the tcgen05 kernels take."""
+    import numpy as np
+    from vsr_b200.duf import DufPlan
+    P = DufPlan(1, 7, 5, 4, backbone, bf16)
+    conv_w = [p for n, p in P.params.items() if n.endswith(".weight") and len(p.shape) >= 4 and not n.startswith("head")]
+    fwd = np.concatenate([np.stack(L.slabs).reshape(-1) for L in P.fwd.values()])
+    bwd = np.concatenate([np.stack(L.slabs).reshape(-1) for L in P.bwd.values()])
+    for p in conv_w:
+        n = int(np.prod(p.shape))
+        for arr in (fwd, bwd):
+            hit = arr[(arr >= p.offset) & (arr < p.offset + n)]
+            assert len(hit) == n and len(np.unique(hit)) == n, p.name
+    assert len(P.unpack_passes) == 1
+    biases = [p for n, p in P.params.items() if n.endswith(".bias") and ".bn" not in n and not n.startswith("head")]
+    packed_b = np.concatenate([np.asarray(L.bias_idx) for L in P.fwd.values() if L.bias_idx is not None])
+    for p in biases:
+        assert np.count_nonzero((packed_b >= p.offset) & (packed_b < p.offset + p.shape[0])) == p.shape[0], p.name
+    for store in (P.fwd, P.bwd):
+        for L in store.values():
+            t = L.table
+            assert all(c0 % 8 == 0 and c0 >= 0 for _, taps in t.groups for (_, _, _, c0) in taps)
+            assert len({len(taps) for _, taps in t.groups}) == 1            # equal groups: one launch geometry
+            if bf16:
+                assert t.kc == 64 and t.nt % 64 == 0 and 64 <= t.nt <= 256, L.name
+    assert P.ntz == (128 if bf16 and P.Gr == 32 else 64 if bf16 else 3 * P.Gr)
