@@ -194,3 +194,25 @@ def test_predictor_cardiac_metrics_match_oracle(tmp_path):
     rows = (tmp_path / "results.csv").read_text().strip().splitlines()
     assert rows[0] == "name,PSNR,CardiacPSNR,CardiacSSIM,L1Loss" and len(rows) == 5
     assert rows[1].startswith("patient001_2d_slice03_frame01,")
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the arm the driver times next to ours): exactly one JSON line on stdout with the
+    contract's keys, for the headline workload and for the Conv3d path."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for extra in ([], ["--workload", "duf"]):
+        r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"] + extra,
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-500:]
+        lines = [l for l in r.stdout.splitlines() if l.strip()]
+        assert len(lines) == 1
+        d = json.loads(lines[0])
+        assert d["impl"] == "reference" and d["metric"] == "hr_voxels_per_s_train_step" and d["higher_is_better"] is True
+        assert d["value"] > 0 and d["unit"] == "HR voxels/s" and d["vs_baseline"] is None
+        assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+        assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+        assert "workload" in d["config"] and "sample" in d["config"]
