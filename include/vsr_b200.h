@@ -109,6 +109,9 @@ int vsr_abi_version(void);
 const char* vsr_last_error(void);
 /* number of floats a slope_partials row must hold (upper bound of any grid) */
 int vsr_partials_len(void);
+/* re-read the tuning overrides from the environment (VSR_TC_*, VSR_WG_*, VSR_PDL: attribution tools and tests;
+ * not part of the reference-facing contract).  They are read once at the first launch otherwise. */
+void vsr_reload_tunables(void);
 
 /* forward / data-gradient tap-GEMM (see above) */
 int vsr_tapgemm(const VsrTapGemmDesc* d, void* stream);
@@ -214,6 +217,15 @@ int64_t vsr_slab_index(int32_t j, int32_t k);
  */
 int vsr_loss_fwd_bwd(const float* out, const float* target, int64_t numel, int32_t kind, float param,
                      float grad_scale, float* loss_partials, float* grad, void* stream);
+/*
+ * The same over `n_segments` equally sized, consecutive segments of `numel` elements each in ONE launch - the T
+ * frames of a step, whose per-frame means the trainer averages (acdc_vsr_trainer.py:74-88) and the predictor logs
+ * per frame (acdc_vsr_predictor.py:119-133): segment s writes row s of loss_partials
+ * ([n_segments][vsr_partials_len()]).  16-byte vector path only when every segment of every tensor is 16-byte
+ * aligned; any other shape / slice takes the scalar loop (never a misaligned access).
+ */
+int vsr_loss_fwd_bwd_seg(const float* out, const float* target, int64_t numel, int32_t n_segments, int32_t kind,
+                         float param, float grad_scale, float* loss_partials, float* grad, void* stream);
 
 /*
  * Fused denormalize + PSNR (src/utils.py:1-20 + metrics.py:20-36): per sample

@@ -255,3 +255,45 @@ def dufnet_forward(inputs, sd, size_filter, upscale, training=True):
     out = F.pixel_shuffle(out, upscale)                                                        # :89
     residual = F.pixel_shuffle(head2("residualNet").squeeze(2), upscale)                       # :93-96
     return out + residual
+
+
+def drfnet_init(in_channels, out_channels, num_features, num_groups, upscale_factor):
+    """state_dict of a freshly constructed DRFNet (drf_net.py:23-36,52-58,61-106,136-147): the reference's own
+    torch.nn modules built in the reference's construction order, hence the reference's default initialisation
+    under the current torch seed.  Lets bench.py's CPU arms run without importing the product package."""
+    import collections
+    import torch.nn as nn
+    F_, G, r = num_features, num_groups, upscale_factor
+    k, s, p = PROJ[r]
+    sd = collections.OrderedDict()
+
+    def put(prefix, mod):
+        for name, v in mod.state_dict().items():
+            sd[f"{prefix}.{name}"] = v.detach().clone()
+
+    put("in_block.conv1", nn.Conv2d(in_channels, 4 * F_, 3, padding=1)); put("in_block.prelu1", nn.PReLU(1, 0.2))
+    put("in_block.conv2", nn.Conv2d(4 * F_, F_, 1)); put("in_block.prelu2", nn.PReLU(1, 0.2))
+    put("f_block.in_block.conv", nn.Conv2d(2 * F_, F_, 1)); put("f_block.in_block.prelu", nn.PReLU(1, 0.2))
+    ups, downs = collections.OrderedDict(), collections.OrderedDict()
+    for g in range(G):                                 # drf_net.py:78-102: up block then down block of every group
+        u, d = f"f_block.up_blocks.{g}", f"f_block.down_blocks.{g}"
+        if g == 0:
+            ups[f"{u}.deconv"] = nn.ConvTranspose2d(F_, F_, k, s, p); ups[f"{u}.prelu"] = nn.PReLU(1, 0.2)
+            downs[f"{d}.conv"] = nn.Conv2d(F_, F_, k, s, p); downs[f"{d}.prelu"] = nn.PReLU(1, 0.2)
+        else:
+            ups[f"{u}.conv1"] = nn.Conv2d(F_ * (g + 1), F_, 1); ups[f"{u}.prelu1"] = nn.PReLU(1, 0.2)
+            ups[f"{u}.deconv2"] = nn.ConvTranspose2d(F_, F_, k, s, p); ups[f"{u}.prelu2"] = nn.PReLU(1, 0.2)
+            downs[f"{d}.conv1"] = nn.Conv2d(F_ * (g + 1), F_, 1); downs[f"{d}.prelu1"] = nn.PReLU(1, 0.2)
+            downs[f"{d}.conv2"] = nn.Conv2d(F_, F_, k, s, p); downs[f"{d}.prelu2"] = nn.PReLU(1, 0.2)
+    for name, m in list(ups.items()) + list(downs.items()):      # state_dict order: all up_blocks, then all down_blocks
+        put(name, m)
+    put("f_block.out_block.conv", nn.Conv2d(F_ * G, F_, 1)); put("f_block.out_block.prelu", nn.PReLU(1, 0.2))
+    if math.log(r, 2) % 1 == 0:
+        n = int(math.log(r, 2))
+        for i in range(n):
+            put(f"out_block.conv{i + 1}", nn.Conv2d(F_, 4 * F_, 3, padding=1))
+        put(f"out_block.conv{n + 1}", nn.Conv2d(F_, out_channels, 3, padding=1))
+    else:
+        put("out_block.conv1", nn.Conv2d(F_, 9 * F_, 3, padding=1))
+        put("out_block.conv2", nn.Conv2d(F_, out_channels, 3, padding=1))
+    return sd

@@ -48,6 +48,36 @@ def swizzle_slabs(w_plain):
     return out.reshape(-1)
 
 
+_INT = {torch.float32: torch.int32, torch.bfloat16: torch.int16, torch.float64: torch.int64}
+PRELU_TINY = 2.0 ** -24
+
+
+def prelu_fwd(v, slope, out_dtype):
+    """PReLU as the kernels store it (csrc/common.cuh `Prelu`): slope 0 multiplies the non-positive side by 2^-24,
+    a negative slope stores [x > 0] in the mantissa LSB of y.  Returns (stored y, y in v's precision)."""
+    a = float(slope)
+    fwd = a if a != 0.0 else PRELU_TINY
+    y = torch.where(v > 0, v, fwd * v)
+    st = y.to(out_dtype)
+    if a < 0:
+        bits = st.contiguous().view(_INT[out_dtype])
+        st = ((bits & ~1) | (v > 0).to(bits.dtype)).view(out_dtype)
+    return st, y
+
+
+def prelu_bwd(g, y_stored, slope, ct):
+    """(dL/dx, d(slope) contribution) from dL/dy and the stored y"""
+    a = float(slope)
+    fwd = a if a != 0.0 else PRELU_TINY
+    if a < 0:
+        pos = (y_stored.contiguous().view(_INT[y_stored.dtype]) & 1) != 0
+    else:
+        pos = y_stored > 0
+    y = y_stored.to(ct)
+    da = torch.where(pos, torch.zeros_like(g), g * (y * (1.0 / fwd))).sum()
+    return torch.where(pos, g, a * g), da
+
+
 class EmuOps:
     """Same interface as CudaOps; computes in fp32 (or fp64 if the tensors are fp64) with torch ops.
     `swizzled` says whether bf16 weight slabs are in the swizzled image (as the product packs them).
@@ -84,23 +114,19 @@ class EmuOps:
                 v = v * out_scale
             if epi & E.EPI_RES_PRE:
                 v = v + residual[..., sl].to(ct)
-            if epi & E.EPI_PRELU:
-                a = slope.to(ct).reshape(())
-                v = torch.where(v > 0, v, a * v)
             if epi & E.EPI_RELU:
                 v = v.clamp_min(0)
             if epi & E.EPI_PRELU_BWD:
-                a = slope.to(ct).reshape(())
-                y = aux_y[..., sl].to(ct)
-                pos = y > 0
-                inv = 1.0 / a if float(a) != 0.0 else torch.zeros_like(a)
-                contrib = torch.where(pos, torch.zeros_like(v), v * (y * inv)).sum()
+                v, contrib = prelu_bwd(v, aux_y[..., sl], slope, ct)
                 slope_partials.view(-1)[0] += contrib.to(slope_partials.dtype)
-                v = torch.where(pos, v, a * v)
             elif epi & E.EPI_RELU_BWD:
                 y = aux_y[..., sl].to(ct)
                 v = torch.where(y > 0, v, torch.zeros_like(v))
-            out[..., sl] = v.to(out.dtype)
+            if epi & E.EPI_PRELU:
+                stored, v = prelu_fwd(v, slope, out.dtype)
+                out[..., sl] = stored
+            else:
+                out[..., sl] = v.to(out.dtype)
             if epi & E.EPI_OUT2:
                 # the kernels add in fp32 from the unrounded value
                 out2[..., sl] = (v + res2[..., sl].to(ct)).to(out2.dtype)
@@ -149,7 +175,10 @@ class EmuOps:
         ct = x.dtype
         z = F.conv2d(x, w.to(ct), bias.to(ct) if bias is not None else None, padding=1)
         if slope is not None:
-            z = torch.where(z > 0, z, slope.to(ct).reshape(()) * z)
+            st, _ = prelu_fwd(z.permute(0, 2, 3, 1).contiguous(), slope, y.dtype)
+            y.copy_(st)
+            self.launches += 1
+            return
         y.copy_(z.permute(0, 2, 3, 1).to(y.dtype))
         self.launches += 1
 
@@ -215,16 +244,13 @@ class EmuOps:
 
     def act_bwd(self, dy, y, dz, slope=None, slope_partials=None):
         ct = torch.float64 if dy.dtype == torch.float64 else torch.float32
-        g, v = dy.to(ct), y.to(ct)
-        pos = v > 0
+        g = dy.to(ct)
         if slope is not None:
-            a = slope.to(ct).reshape(())
-            inv = 1.0 / a if float(a) != 0.0 else torch.zeros_like(a)
-            slope_partials.view(-1)[0] += torch.where(pos, torch.zeros_like(g), g * (v * inv)).sum().to(
-                slope_partials.dtype)
-            dz.copy_(torch.where(pos, g, a * g).to(dz.dtype))
+            gx, da = prelu_bwd(g, y, slope, ct)
+            slope_partials.view(-1)[0] += da.to(slope_partials.dtype)
+            dz.copy_(gx.to(dz.dtype))
         else:
-            dz.copy_(torch.where(pos, g, torch.zeros_like(g)).to(dz.dtype))
+            dz.copy_(torch.where(y.to(ct) > 0, g, torch.zeros_like(g)).to(dz.dtype))
         self.launches += 1
 
     def add(self, a, b, out):
@@ -416,6 +442,13 @@ class EmuOps:
         if grad is not None:
             grad.copy_((g * grad_scale).to(grad.dtype))
         self.launches += 1
+
+    def loss_fwd_bwd_seg(self, out, target, n_segments, kind, param, grad_scale, partials, grad):
+        o, t = out.reshape(n_segments, -1), target.reshape(n_segments, -1)
+        g = grad.view(n_segments, -1) if grad is not None else [None] * n_segments
+        for s_ in range(n_segments):
+            self.loss_fwd_bwd(o[s_], t[s_], kind, param, grad_scale, partials[s_], g[s_])
+        self.launches -= n_segments - 1
 
     def metric_workspace(self, n, per_sample):
         return 16

@@ -206,13 +206,58 @@ def test_bench_reference_arm_contract():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     for extra in ([], ["--workload", "duf"]):
         r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"] + extra,
-                           capture_output=True, text=True, timeout=600)
+                           capture_output=True, text=True, timeout=600,
+                           env=dict(os.environ, VSR_REF_FULL="0", VSR_REF_SAMPLE="2"))
         assert r.returncode == 0, r.stderr[-500:]
         lines = [l for l in r.stdout.splitlines() if l.strip()]
         assert len(lines) == 1
         d = json.loads(lines[0])
         assert d["impl"] == "reference" and d["metric"] == "hr_voxels_per_s_train_step" and d["higher_is_better"] is True
         assert d["value"] > 0 and d["unit"] == "HR voxels/s" and d["vs_baseline"] is None
-        assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+        assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
         assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
         assert "workload" in d["config"] and "sample" in d["config"]
+
+
+def _odd_slopes(sd):
+    """every PReLU slope of the net replaced by a value from {-0.1, 0, 0.2, -0.35}: nn.PReLU's slope is an
+    unconstrained parameter (drf_net.py:56) and may cross zero while training"""
+    vals = [-0.1, 0.0, 0.2, -0.35]
+    out, i = {}, 0
+    for k, v in sd.items():
+        if "prelu" in k:
+            out[k] = torch.full_like(v, vals[i % len(vals)])
+            i += 1
+        else:
+            out[k] = v.clone()
+    return out
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 2e-6), (torch.float32, 1e-4)])
+def test_prelu_slopes_zero_and_negative(dtype, tol):
+    """outputs and every gradient (the slope gradients included) against the fp64 oracle when slopes are 0 or
+    negative: the backward pass recovers the branch and the pre-activation from the stored post-activation
+    (csrc/common.cuh `Prelu`)."""
+    fx = torch.load(os.path.join(GOLDEN, "drfnet_f8_g3_x4.pt"))
+    sd0 = _odd_slopes(fx["state_dict"])
+    net = DRFNet(**fx["kwargs"])
+    net.load_state_dict(sd0)
+    if dtype == torch.float64:
+        net = net.double()
+    net._ops = EmuOps()
+    x = [t.to(dtype) for t in fx["inputs"]]
+    y = [t.to(dtype) for t in fx["targets"]]
+    outs = net(x)
+    loss = torch.stack([((o - t) ** 2).mean() for o, t in zip(outs, y)]).mean()
+    loss.backward()
+    sd = {k: v.double().clone().requires_grad_(True) for k, v in sd0.items()}
+    ref_outs = restated.drfnet_forward([t.double() for t in x], sd, 4)
+    ref_loss = torch.stack([((o - t.double()) ** 2).mean() for o, t in zip(ref_outs, y)]).mean()
+    ref_loss.backward()
+    for o, r in zip(outs, ref_outs):
+        assert (o.double() - r).abs().max() <= tol * r.abs().max()
+    gmax = max(float(v.grad.abs().max()) for v in sd.values())
+    for k, p in net.named_parameters():
+        assert (p.grad.double() - sd[k].grad).abs().max() <= tol * gmax, k
+    slopes = [k for k in sd if "prelu" in k]
+    assert any(float(sd[k].grad.abs()) > 1e-3 * gmax for k in slopes)      # the slope gradients are exercised

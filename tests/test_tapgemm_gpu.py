@@ -34,6 +34,21 @@ def grouped_table(kc, nt, n_groups, n_phase):
     return TapTable(kc=kc, nt=nt, groups=groups)
 
 
+def _setenv(monkeypatch, key, value):
+    """tuning overrides are read once by the library: set the variable and have it re-read"""
+    monkeypatch.setenv(key, value)
+    _ops().lib.vsr_reload_tunables()
+
+
+@pytest.fixture(autouse=True)
+def _fresh_tunables():
+    yield
+    import os
+    for k in [k for k in os.environ if k.startswith(("VSR_TC_", "VSR_WG_", "VSR_PDL"))]:
+        del os.environ[k]
+    _ops().lib.vsr_reload_tunables()
+
+
 def _rand(shape, dtype, gen, scale=1.0):
     return (torch.randn(shape, generator=gen, device="cuda") * scale).to(dtype)
 
@@ -59,7 +74,10 @@ def _run_case(tab, n, h, w, src_c, out_c, dtype, epi, seed=0, n_srcs=1):
         outs.append((out.float(), out2.float(), part.sum()))
     torch.cuda.synchronize()
     (a, a2, ap), (b, b2, bp) = outs
-    tol = 2e-2 if dtype == torch.bfloat16 else 2e-5
+    # bf16: kernel and emulation accumulate the same bf16 inputs in fp32; after the final rounding to bf16 they can differ
+    # by one ulp where the fp32 sums straddle a rounding boundary (<= 2^-7 of the tensor maximum): 8.5e-3 leaves no room
+    # for a dropped tap (one of 64 taps is ~3 % of the output range)
+    tol = 8.5e-3 if dtype == torch.bfloat16 else 2e-5
     scale = b.abs().max().item() + 1e-6
     assert (a - b).abs().max().item() / scale < tol, f"out mismatch {(a - b).abs().max().item() / scale}"
     if epi & L.EPI_OUT2:
@@ -228,7 +246,7 @@ def test_tc_bf16_strided_conv_shared_loads(h, w, epi, monkeypatch):
     (tapgemm_tc2.cu shared-load mode); the same launch with the mode off must agree with the emulation too."""
     tab = strided_conv_table()
     _run_case(tab, n=3, h=h, w=w, src_c=1024, out_c=64, dtype=torch.bfloat16, epi=epi, seed=21)
-    monkeypatch.setenv("VSR_TC_TALL", "0")
+    _setenv(monkeypatch, "VSR_TC_TALL", "0")
     _run_case(tab, n=3, h=h, w=w, src_c=1024, out_c=64, dtype=torch.bfloat16, epi=epi, seed=21)
 
 
@@ -242,20 +260,18 @@ def test_tc_bf16_resident_and_streamed_weights_agree(monkeypatch):
     # deconv shape: 4 groups x 4 taps, nt 256; enough tiles for the weight-resident mode
     tab = grouped_table(64, 256, 4, 1)
     for mode in ("1", "0"):
-        monkeypatch.setenv("VSR_TC_RESIDENT", mode)
+        _setenv(monkeypatch, "VSR_TC_RESIDENT", mode)
         _run_case(tab, n=20, h=32, w=32, src_c=64, out_c=1024, dtype=torch.bfloat16, epi=L.EPI_BIAS | L.EPI_PRELU, seed=23)
 
 
-def test_tc_bf16_no_pdl_and_first_generation_kernel(monkeypatch):
+def test_tc_bf16_without_programmatic_dependent_launch(monkeypatch):
     tab = conv3x3_table(64, 64)
-    monkeypatch.setenv("VSR_PDL", "0")
-    _run_case(tab, n=2, h=20, w=32, src_c=64, out_c=64, dtype=torch.bfloat16, epi=L.EPI_BIAS | L.EPI_PRELU, seed=24)
-    monkeypatch.setenv("VSR_TC_V1", "1")
+    _setenv(monkeypatch, "VSR_PDL", "0")
     _run_case(tab, n=2, h=20, w=32, src_c=64, out_c=64, dtype=torch.bfloat16, epi=L.EPI_BIAS | L.EPI_PRELU, seed=24)
 
 
 def test_wgrad_tc_shared_pair_loads(monkeypatch):
-    monkeypatch.setenv("VSR_WG_TALL", "1")
+    _setenv(monkeypatch, "VSR_WG_TALL", "1")
     _wgrad_case(strided_conv_table(), n=4, h=16, w=32, src_c=1024, out_c=64, seed=25)
     _wgrad_case(strided_conv_table(), n=2, h=19, w=32, src_c=1024, out_c=64, seed=26)
 
@@ -270,9 +286,9 @@ def test_tc_bf16_shared_loads_several_groups_many_tiles(n_groups, nt, monkeypatc
         gy, gx = g // 2, g % 2
         groups.append((g * nt, [(0, dy - 1 + gy, dx - 1 + gx, 0) for dy in (0, 1) for dx in (0, 1)]))
     tab = TapTable(kc=64, nt=nt, groups=groups)
-    monkeypatch.setenv("VSR_TC_RESIDENT", "0")
+    _setenv(monkeypatch, "VSR_TC_RESIDENT", "0")
     _run_case(tab, n=20, h=32, w=32, src_c=64, out_c=n_groups * nt, dtype=torch.bfloat16, epi=L.EPI_BIAS | L.EPI_PRELU, seed=27)
-    monkeypatch.setenv("VSR_TC_STAGES", "2")
+    _setenv(monkeypatch, "VSR_TC_STAGES", "2")
     _run_case(tab, n=20, h=32, w=32, src_c=64, out_c=n_groups * nt, dtype=torch.bfloat16, epi=L.EPI_PRELU_BWD, seed=28)
-    monkeypatch.setenv("VSR_TC_STAGES", "1")
+    _setenv(monkeypatch, "VSR_TC_STAGES", "1")
     _run_case(tab, n=6, h=32, w=32, src_c=64, out_c=n_groups * nt, dtype=torch.bfloat16, epi=0, seed=29)

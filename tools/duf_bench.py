@@ -92,14 +92,13 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms_graph = e0.elapsed_time(e1) / a.steps
-    ops.timing = []
+    ops.start_timing()
     step()
     torch.cuda.synchronize()
     detail = {}
-    for kind, fl, s, e, sig, nbytes in ops.timing:
+    for kind, fl, s, e, sig, nbytes in ops.gemm_records(ops.stop_timing()):
         d = detail.setdefault(f"{kind}:{sig}", {"n": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
         d["n"] += 1; d["ms"] += s.elapsed_time(e); d["flops"] += fl; d["bytes"] += nbytes
-    ops.timing = None
     for d in detail.values():
         d["tflops_padded"] = d["flops"] / d["ms"] / 1e9
         d["gbs"] = d["bytes"] / d["ms"] / 1e6

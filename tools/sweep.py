@@ -39,13 +39,13 @@ def one(F, d, s, T, pk):
     acc = torch.zeros(4, device=dev)
     step.train_step(x, y, acc)
     torch.cuda.synchronize()
-    ops.timing = []
+    ops.start_timing()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     step.train_step(x, y, acc)
     b.record()
     torch.cuda.synchronize()
-    timing, ops.timing = ops.timing, None
+    timing = ops.gemm_records(ops.stop_timing())
     detail = {}
     for kind, flops, e0, e1, sig, nbytes in timing:
         q = detail.setdefault(f"{kind}:{sig}", [0.0, 0.0, 0, 0.0])

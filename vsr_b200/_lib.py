@@ -36,6 +36,7 @@ _SIGS = {
     "vsr_abi_version": (C.c_int, []),
     "vsr_last_error": (C.c_char_p, []),
     "vsr_partials_len": (C.c_int, []),
+    "vsr_reload_tunables": (None, []),
     "vsr_tapgemm": (C.c_int, [C.POINTER(VsrTapGemmDesc), C.c_void_p]),
     "vsr_tapgemm_simt_bf16": (C.c_int, [C.POINTER(VsrTapGemmDesc), C.c_void_p]),
     "vsr_tapgemm_wgrad_workspace": (C.c_size_t, [C.POINTER(VsrTapGemmDesc)]),
@@ -75,6 +76,8 @@ _SIGS = {
     "vsr_slab_index": (C.c_int64, [C.c_int32, C.c_int32]),
     "vsr_loss_fwd_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_float,
                                    C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vsr_loss_fwd_bwd_seg": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_float,
+                                       C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vsr_metric_workspace": (C.c_size_t, [C.c_int32, C.c_int64]),
     "vsr_psnr": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_float,
                            C.c_float, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIBPATH = os.path.join(LIBDIR, "libvsr_sm100.so")
-SOURCES = ["core.cu", "tapgemm_simt.cu", "tapgemm_tc.cu", "tapgemm_tc2.cu", "wgrad_tc.cu", "layers.cu", "metrics.cu",
+SOURCES = ["core.cu", "tapgemm_simt.cu", "tma_host.cu", "tapgemm_tc2.cu", "wgrad_tc.cu", "layers.cu", "metrics.cu",
            "resample.cu", "dense3d.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
@@ -40,7 +40,8 @@ def up_to_date():
     return all(os.path.getmtime(d) <= t for d in _deps())
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, attrib=False):
+    """attrib=True adds -DVSR_ATTRIB: the timing-attribution build of the tensor-core kernels (tools/attrib.py)"""
     if not force and up_to_date():
         return LIBPATH
     os.makedirs(LIBDIR, exist_ok=True)
@@ -51,7 +52,7 @@ def build(force=False, verbose=False):
 
     def compile_one(src):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + (["-DVSR_ATTRIB"] if attrib else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
@@ -69,4 +70,4 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    print(build(force="--force" in sys.argv or "--attrib" in sys.argv, verbose=True, attrib="--attrib" in sys.argv))

@@ -79,14 +79,16 @@ template <typename T, bool kPrelu>
 __global__ void act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ dz,
                                long n, const float* __restrict__ slope_p, float* __restrict__ partials) {
   __shared__ float red[32];
-  const float a = kPrelu ? __ldg(slope_p) : 0.f;
-  const float inv_a = a != 0.f ? 1.f / a : 0.f;
+  const Prelu a = make_prelu(kPrelu ? __ldg(slope_p) : 1.f);
   float acc = 0.f;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-    const float g = Elem<T>::ld(dy + i), v = Elem<T>::ld(y + i);
-    const bool pos = v > 0.f;
-    if (kPrelu) acc += pos ? 0.f : g * (v * inv_a);
-    Elem<T>::st(dz + i, pos ? g : a * g);
+    float g = Elem<T>::ld(dy + i);
+    if (kPrelu) {
+      acc += prelu_bwd(y + i, g, a);
+    } else {
+      g = Elem<T>::ld(y + i) > 0.f ? g : 0.f;
+    }
+    Elem<T>::st(dz + i, g);
   }
   if (kPrelu) {
     const float s = block_sum(acc, red);

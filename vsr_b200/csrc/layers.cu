@@ -27,7 +27,7 @@ __global__ void conv_first_kernel(const float* __restrict__ x, int n, int cin, i
   }
   for (int i = threadIdx.x; i < cout; i += blockDim.x) sb[i] = bias ? bias[i] : 0.f;
   __syncthreads();
-  const float a = slope_p ? __ldg(slope_p) : 1.f;
+  const Prelu a = make_prelu(slope_p ? __ldg(slope_p) : 1.f);
   const int groups = cout / 8;
   const long total = (long)n * h * w * groups;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -56,18 +56,7 @@ __global__ void conv_first_kernel(const float* __restrict__ x, int n, int cin, i
         }
       }
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = acc[j] > 0.f ? acc[j] : a * acc[j];
-    T* yp = y + pix * cout + gq * 8;
-    if constexpr (sizeof(T) == 2) {
-      uint4 o;
-      o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
-      o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
-      *reinterpret_cast<uint4*>(yp) = o;
-    } else {
-      reinterpret_cast<float4*>(yp)[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-      reinterpret_cast<float4*>(yp)[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
-    }
+    prelu_store8(y + pix * cout + gq * 8, acc, a);      // slope 1 (no PReLU) is the identity
   }
 }
 
@@ -155,7 +144,7 @@ __global__ void __launch_bounds__(256) conv_first2_kernel(const float* __restric
 #pragma unroll
     for (int t = 0; t < 9; ++t) wr[j][t] = live ? sw2[(gl * 8 + j) * 9 + t] : 0.f;
   }
-  const float a = slope_p ? __ldg(slope_p) : 1.f;
+  const Prelu a = make_prelu(slope_p ? __ldg(slope_p) : 1.f);
   const long total = (long)n * h * w;
   const long warp0 = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
@@ -182,20 +171,9 @@ __global__ void __launch_bounds__(256) conv_first2_kernel(const float* __restric
       float s = br[j];
 #pragma unroll
       for (int t = 0; t < 9; ++t) s = fmaf(v[t], wr[j][t], s);
-      acc[j] = s > 0.f ? s : a * s;
+      acc[j] = s;
     }
-    if (live) {
-      T* yp = y + pix * cout + gl * 8;
-      if constexpr (sizeof(T) == 2) {
-        uint4 o;
-        o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
-        o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
-        *reinterpret_cast<uint4*>(yp) = o;
-      } else {
-        reinterpret_cast<float4*>(yp)[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-        reinterpret_cast<float4*>(yp)[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
-      }
-    }
+    if (live) prelu_store8(y + pix * cout + gl * 8, acc, a);
   }
 }
 

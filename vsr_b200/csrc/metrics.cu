@@ -1,6 +1,8 @@
 // metrics.cu — fused loss forward+backward, denormalize+PSNR, denormalize+SSIM.
 // All are single-pass, 8 (resp. 12) bytes per element, bound by HBM; reductions are two-level
 // with a fixed order (deterministic).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace vsr {
@@ -10,12 +12,18 @@ namespace {
 // losses: torch.nn.L1Loss / MSELoss (main.py:60-63), CharbonnierLoss (losses.py:23-34),
 // HuberLoss (losses.py:5-20); mean reduction; grad = dL/dout * grad_scale.
 // ------------------------------------------------------------------------------------------
-template <int KIND, bool GRAD>
-__global__ void loss_kernel(const float4* __restrict__ out, const float4* __restrict__ tgt, long n4,
-                            const float* __restrict__ out_s, const float* __restrict__ tgt_s, long n,
-                            float param, float gscale, float* __restrict__ partials,
-                            float4* __restrict__ grad, float* __restrict__ grad_s) {
+// One launch covers `gridDim.y` equally sized segments (the T frames of a step: acdc_vsr_trainer.py:86 averages
+// per-frame means); segment s writes its partial sums to row s of `partials`.  VEC: 16-byte loads / stores with
+// four of each in flight per thread (the host checks the alignment of every pointer and of the segment size).
+template <int KIND, bool GRAD, bool VEC>
+__global__ void __launch_bounds__(256) loss_kernel(const float* __restrict__ out, const float* __restrict__ tgt, long n,
+                                                  float param, float gscale, float* __restrict__ partials,
+                                                  float* __restrict__ grad) {
   __shared__ float red[32];
+  const long base = (long)blockIdx.y * n;
+  out += base;
+  tgt += base;
+  if (GRAD) grad += base;
   float acc = 0.f;
   auto one = [&](float o, float t, float& g) {
     const float d = o - t;
@@ -37,20 +45,40 @@ __global__ void loss_kernel(const float4* __restrict__ out, const float4* __rest
       g = (ad < param ? d : param * sgn) * gscale;
     }
   };
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
-    const float4 o = __ldg(out + i), t = __ldg(tgt + i);
-    float4 g;
-    one(o.x, t.x, g.x); one(o.y, t.y, g.y); one(o.z, t.z, g.z); one(o.w, t.w, g.w);
-    if (GRAD) grad[i] = g;
-  }
-  // scalar tail (n % 4)
-  for (long i = n4 * 4 + blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-    float g;
-    one(out_s[i], tgt_s[i], g);
-    if (GRAD) grad_s[i] = g;
+  if (VEC) {
+    const long n4 = n >> 2;
+    const float4* o4 = reinterpret_cast<const float4*>(out);
+    const float4* t4 = reinterpret_cast<const float4*>(tgt);
+    float4* g4 = reinterpret_cast<float4*>(grad);
+    for (long i0 = (long)blockIdx.x * 1024 + threadIdx.x; i0 < n4; i0 += (long)gridDim.x * 1024) {
+      float4 o[4], t[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long i = i0 + u * 256;
+        if (i < n4) {
+          o[u] = __ldcs(o4 + i);
+          t[u] = __ldcs(t4 + i);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long i = i0 + u * 256;
+        if (i < n4) {
+          float4 g;
+          one(o[u].x, t[u].x, g.x); one(o[u].y, t[u].y, g.y); one(o[u].z, t[u].z, g.z); one(o[u].w, t[u].w, g.w);
+          if (GRAD) g4[i] = g;
+        }
+      }
+    }
+  } else {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+      float g;
+      one(__ldg(out + i), __ldg(tgt + i), g);
+      if (GRAD) grad[i] = g;
+    }
   }
   const float s = block_sum(acc, red);
-  if (threadIdx.x == 0) partials[blockIdx.x] = s;
+  if (threadIdx.x == 0) partials[(size_t)blockIdx.y * kPartialsLen + blockIdx.x] = s;
 }
 
 __device__ __forceinline__ float denorm(float v, float mean, float std, bool on) {
@@ -60,24 +88,39 @@ __device__ __forceinline__ float denorm(float v, float mean, float std, bool on)
   return fminf(fmaxf(r, 0.f), 255.f);
 }
 
-// PSNR pass 1: grid (blocks_per_sample, n): partial sum of squared error (16-byte loads when aligned)
+// PSNR pass 1: grid (blocks_per_sample, n): partial sum of squared error; `vec`: 16-byte loads, four of each input
+// in flight per thread (the host checks pointer alignment and per_sample % 4)
 __global__ void __launch_bounds__(256) psnr_partial_kernel(const float* __restrict__ out, const float* __restrict__ tgt,
-                                                          long per_sample, float mean, float std, int denorm_on,
+                                                          long per_sample, float mean, float std, int denorm_on, int vec,
                                                           float* __restrict__ ws) {
   __shared__ float red[32];
   const float* o = out + (size_t)blockIdx.y * per_sample;
   const float* t = tgt + (size_t)blockIdx.y * per_sample;
   float acc = 0.f;
-  if ((per_sample & 3) == 0) {
+  if (vec) {
     const float4* o4 = reinterpret_cast<const float4*>(o);
     const float4* t4 = reinterpret_cast<const float4*>(t);
-    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < per_sample / 4; i += (long)gridDim.x * blockDim.x) {
-      const float4 a = __ldg(o4 + i), b = __ldg(t4 + i);
-      const float d0 = denorm(a.x, mean, std, denorm_on) - denorm(b.x, mean, std, denorm_on);
-      const float d1 = denorm(a.y, mean, std, denorm_on) - denorm(b.y, mean, std, denorm_on);
-      const float d2 = denorm(a.z, mean, std, denorm_on) - denorm(b.z, mean, std, denorm_on);
-      const float d3 = denorm(a.w, mean, std, denorm_on) - denorm(b.w, mean, std, denorm_on);
-      acc = fmaf(d0, d0, acc); acc = fmaf(d1, d1, acc); acc = fmaf(d2, d2, acc); acc = fmaf(d3, d3, acc);
+    const long n4 = per_sample >> 2;
+    for (long i0 = (long)blockIdx.x * 1024 + threadIdx.x; i0 < n4; i0 += (long)gridDim.x * 1024) {
+      float4 a[4], b[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long i = i0 + u * 256;
+        if (i < n4) {
+          a[u] = __ldg(o4 + i);
+          b[u] = __ldg(t4 + i);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (i0 + u * 256 < n4) {
+          const float d0 = denorm(a[u].x, mean, std, denorm_on) - denorm(b[u].x, mean, std, denorm_on);
+          const float d1 = denorm(a[u].y, mean, std, denorm_on) - denorm(b[u].y, mean, std, denorm_on);
+          const float d2 = denorm(a[u].z, mean, std, denorm_on) - denorm(b[u].z, mean, std, denorm_on);
+          const float d3 = denorm(a[u].w, mean, std, denorm_on) - denorm(b[u].w, mean, std, denorm_on);
+          acc = fmaf(d0, d0, acc); acc = fmaf(d1, d1, acc); acc = fmaf(d2, d2, acc); acc = fmaf(d3, d3, acc);
+        }
+      }
     }
   } else {
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < per_sample; i += (long)gridDim.x * blockDim.x) {
@@ -271,20 +314,27 @@ int psnr_bps(long per_sample, int n) {
 
 using namespace vsr;
 
-extern "C" int vsr_loss_fwd_bwd(const float* out, const float* target, int64_t numel, int32_t kind, float param,
-                                float grad_scale, float* loss_partials, float* grad, void* stream) {
-  VSR_CHECK_ARG(out && target && loss_partials && numel > 0, "vsr_loss_fwd_bwd: bad arguments");
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+extern "C" int vsr_loss_fwd_bwd_seg(const float* out, const float* target, int64_t numel, int32_t n_segments, int32_t kind,
+                                    float param, float grad_scale, float* loss_partials, float* grad, void* stream) {
+  VSR_CHECK_ARG(out && target && loss_partials && numel > 0 && n_segments >= 1 && n_segments <= 65535,
+                "vsr_loss_fwd_bwd: bad arguments");
   VSR_CHECK_ARG(kind >= 0 && kind <= 3, "vsr_loss_fwd_bwd: kind must be 0..3");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const long n4 = numel / 4;
-  int grid = grid_for(n4 > 0 ? n4 : 1, 256, 4);
-  if (grid > kPartialsLen) grid = kPartialsLen;
-  const float4* o4 = reinterpret_cast<const float4*>(out);
-  const float4* t4 = reinterpret_cast<const float4*>(target);
-  float4* g4 = reinterpret_cast<float4*>(grad);
-#define VSR_LOSS(K)                                                                                          \
-  if (grad) loss_kernel<K, true><<<grid, 256, 0, s>>>(o4, t4, n4, out, target, numel, param, grad_scale, loss_partials, g4, grad); \
-  else loss_kernel<K, false><<<grid, 256, 0, s>>>(o4, t4, n4, out, target, numel, param, grad_scale, loss_partials, nullptr, nullptr);
+  // 16-byte path only when every segment of every tensor starts on a 16-byte boundary (slices of a stacked buffer
+  // with an odd frame size do not: ADVICE r1) - otherwise the scalar loop takes everything
+  const bool vec = (numel & 3) == 0 && aligned16(out) && aligned16(target) && (!grad || aligned16(grad));
+  long per_block = vec ? 4096 : 1024;                 // elements per block and loop trip
+  long gx = (numel + per_block - 1) / per_block;
+  const long cap = std::max<long>(1, (long)num_sms() * 8 / n_segments);
+  if (gx > cap) gx = cap;
+  if (gx > kPartialsLen) gx = kPartialsLen;
+  const dim3 grid((unsigned)gx, (unsigned)n_segments);
+#define VSR_LOSS2(K, G, V) loss_kernel<K, G, V><<<grid, 256, 0, s>>>(out, target, numel, param, grad_scale, loss_partials, grad)
+#define VSR_LOSS(K)                                               \
+  if (grad) { if (vec) VSR_LOSS2(K, true, true); else VSR_LOSS2(K, true, false); } \
+  else { if (vec) VSR_LOSS2(K, false, true); else VSR_LOSS2(K, false, false); }
   switch (kind) {
     case 0: VSR_LOSS(0) break;
     case 1: VSR_LOSS(1) break;
@@ -292,8 +342,14 @@ extern "C" int vsr_loss_fwd_bwd(const float* out, const float* target, int64_t n
     default: VSR_LOSS(3) break;
   }
 #undef VSR_LOSS
+#undef VSR_LOSS2
   VSR_CHECK_LAUNCH("vsr_loss_fwd_bwd");
   return VSR_OK;
+}
+
+extern "C" int vsr_loss_fwd_bwd(const float* out, const float* target, int64_t numel, int32_t kind, float param,
+                                float grad_scale, float* loss_partials, float* grad, void* stream) {
+  return vsr_loss_fwd_bwd_seg(out, target, numel, 1, kind, param, grad_scale, loss_partials, grad, stream);
 }
 
 extern "C" size_t vsr_metric_workspace(int32_t n, int64_t per_sample) {
@@ -308,7 +364,8 @@ extern "C" int vsr_psnr(const float* out, const float* target, int32_t n, int64_
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int bps = psnr_bps(per_sample, n);
   float* ws = static_cast<float*>(workspace);
-  psnr_partial_kernel<<<dim3(bps, n), 256, 0, s>>>(out, target, per_sample, mean, std, std > 0.f, ws);
+  const int vec = (per_sample & 3) == 0 && aligned16(out) && aligned16(target);
+  psnr_partial_kernel<<<dim3(bps, n), 256, 0, s>>>(out, target, per_sample, mean, std, std > 0.f, vec, ws);
   VSR_CHECK_LAUNCH("vsr_psnr");
   psnr_final_kernel<<<(n + 127) / 128, 128, 0, s>>>(ws, n, bps, per_sample, max_value, psnr_out);
   VSR_CHECK_LAUNCH("vsr_psnr_final");

@@ -43,8 +43,7 @@ __global__ void __launch_bounds__(kThreads) tapgemm_simt_kernel(const __grid_con
 
   const int tid = threadIdx.x;
   const int ty = tid >> 4, tx = tid & 15;   // 16 x 16 threads, 4x4 outputs each
-  const float slope = (a.epi & (VSR_EPI_PRELU | VSR_EPI_PRELU_BWD)) ? __ldg(a.slope) : 0.f;
-  const float inv_slope = slope != 0.f ? 1.f / slope : 0.f;
+  const Prelu prelu = make_prelu((a.epi & (VSR_EPI_PRELU | VSR_EPI_PRELU_BWD)) ? __ldg(a.slope) : 1.f);
   float slope_acc = 0.f;
 
   const long tiles = (long)a.m_tiles * a.n_tiles * a.n_groups;
@@ -140,18 +139,19 @@ __global__ void __launch_bounds__(kThreads) tapgemm_simt_kernel(const __grid_con
         if (a.epi & VSR_EPI_BIAS) v += __ldg(a.bias + grp.x + jj);
         if (a.epi & VSR_EPI_SCALE) v *= a.out_scale;
         if (a.epi & VSR_EPI_RES_PRE) v += Elem<T>::ld(a.residual + rowoff + jj);
-        if (a.epi & VSR_EPI_PRELU) v = v > 0.f ? v : slope * v;
         if (a.epi & VSR_EPI_RELU) v = fmaxf(v, 0.f);
         if (a.epi & VSR_EPI_PRELU_BWD) {
-          const float y = Elem<T>::ld(a.aux_y + rowoff + jj);
-          const bool pos = y > 0.f;
-          slope_acc += pos ? 0.f : v * (y * inv_slope);
-          v = pos ? v : slope * v;
+          slope_acc += prelu_bwd(a.aux_y + rowoff + jj, v, prelu);
         } else if (a.epi & VSR_EPI_RELU_BWD) {
           const float y = Elem<T>::ld(a.aux_y + rowoff + jj);
           v = y > 0.f ? v : 0.f;
         }
-        Elem<T>::st(a.out + rowoff + jj, v);
+        if (a.epi & VSR_EPI_PRELU) {
+          prelu_store(a.out + rowoff + jj, v, prelu);      // (the branch of a negative slope travels in y's LSB)
+          v = v > 0.f ? v : prelu.fwd * v;
+        } else {
+          Elem<T>::st(a.out + rowoff + jj, v);
+        }
         if (a.epi & VSR_EPI_OUT2)
           Elem<T>::st(a.out2 + rowoff + jj, v + Elem<T>::ld(a.res2 + rowoff + jj));
       }
@@ -361,7 +361,7 @@ int launch_wgrad(const VsrTapGemmDesc* d, float* dw, int accumulate, void* works
 
 }  // namespace
 
-int tapgemm_tc_launch(const VsrTapGemmDesc* d, cudaStream_t stream);  // tapgemm_tc.cu
+int tapgemm_tc2_launch(const VsrTapGemmDesc* d, cudaStream_t stream);  // tapgemm_tc2.cu
 bool wgrad_tc_supported(const VsrTapGemmDesc* d);                       // wgrad_tc.cu
 size_t wgrad_tc_workspace(const VsrTapGemmDesc* d);
 int wgrad_tc_launch(const VsrTapGemmDesc* d, float* dw, float* db, int db_period, int accumulate, void* workspace,
@@ -403,7 +403,7 @@ extern "C" int vsr_tapgemm(const VsrTapGemmDesc* d, void* stream) {
   if (d->epi & VSR_EPI_PRELU_BWD) VSR_CHECK_ARG(d->slope_partials, "vsr_tapgemm: PRELU_BWD without slope_partials");
   if (d->epi & VSR_EPI_OUT2) VSR_CHECK_ARG(d->out2 && d->res2, "vsr_tapgemm: OUT2 without out2/res2");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (d->dtype == VSR_BF16) return tapgemm_tc_launch(d, s);
+  if (d->dtype == VSR_BF16) return tapgemm_tc2_launch(d, s);
   return launch_simt<float>(d, s);
 }
 

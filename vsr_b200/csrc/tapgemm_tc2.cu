@@ -25,10 +25,19 @@
 
 namespace vsr {
 
-int get_src_map_pub(const VsrTensor4& t, int bw, int bh, CUtensorMap* out);   // tapgemm_tc.cu
+int get_src_map_pub(const VsrTensor4& t, int bw, int bh, CUtensorMap* out);   // tma_host.cu
 void pick_box_pub(int h, int w, int* bw, int* bh);
 
 namespace {
+
+// timing attribution (tools/attrib.py: parts of the kernel switched off through VSR_TC_DEBUG bits, per-role clock64
+// sums, printf) exists only in builds with -DVSR_ATTRIB (python -m vsr_b200.build --attrib); the product kernel carries
+// none of it
+#ifdef VSR_ATTRIB
+constexpr bool kAttrib = true;
+#else
+constexpr bool kAttrib = false;
+#endif
 
 constexpr int kBlockM = 128;
 constexpr int kKc = 64;                       // bf16 channels per tap = one 128-byte row
@@ -162,7 +171,8 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 template <int FIXED_EPI>
 __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_constant__ Tc2Args a) {
   const int epi = FIXED_EPI >= 0 ? FIXED_EPI : a.epi;
-  const uint64_t g_t0 = ptx::globaltimer_ns();
+  const int dbg = kAttrib ? a.debug : 0;
+  const uint64_t g_t0 = kAttrib ? ptx::globaltimer_ns() : 0;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = ptx::smem_u32(smem_raw);
   uint8_t* smem_gen = smem_raw;
@@ -215,7 +225,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const bool prof = (a.debug & 32) != 0;
+  const bool prof = (dbg & 32) != 0;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < a.stages; ++s) {
@@ -246,7 +256,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
   ptx::tc_fence_after();
   ptx::pdl_launch_dependents();
   const uint32_t tmem_base = *tmem_slot_gen;
-  const uint64_t g_t1 = ptx::globaltimer_ns();
+  const uint64_t g_t1 = kAttrib ? ptx::globaltimer_ns() : 0;
 
   if (warp < kProducers) {
     // ===================== TMA producers =====================
@@ -263,7 +273,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
       // aliases after two completions): at most `stages` producers may be active.
       const int n_prod = a.stages < kProducers ? a.stages : kProducers;
       int turn = 0;                               // position in the column sequence modulo n_prod
-      long long p_wait = 0, p_n = 0, p_t0 = clock64();
+      long long p_wait = 0, p_n = 0, p_t0 = kAttrib ? clock64() : 0;
       for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
         const TileCoord tc = decode_tile(a, tile);
         int4 grp = grp_in_smem ? grp_s[tc.g] : __ldg(a.group_tab + tc.g);
@@ -304,7 +314,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
           const CUtensorMap* map = (a.tall ? a.tall_maps : a.maps) + tap.x;
           if (leader) {
             // attribution runs skip the A (debug & 2) and/or B (debug & 4) transfer, keeping the protocol
-            const bool do_a = !(a.debug & 2), do_b = !(a.debug & 4) && !a.resident;
+            const bool do_a = !(dbg & 2), do_b = !(dbg & 4) && !a.resident;
             const uint32_t tx = (do_a ? a_bytes : 0u) + (do_b ? static_cast<uint32_t>(ndy) * b_bytes : 0u);
             if (tx == 0) { ptx::mbar_arrive(fb); } else { ptx::mbar_arrive_expect_tx(fb, tx); }
             if (do_a) ptx::tma_load_4d(sa, map, fb, tap.w, tc.x0 + tap.z, tc.y0 + tap.y, tc.n);
@@ -329,7 +339,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
       int it = 0;
       int cur_g = -1;
       uint32_t gcount = 0;
-      long long m_wfull = 0, m_wtmem = 0, m_issue = 0, m_n = 0, m_t0 = clock64();
+      long long m_wfull = 0, m_wtmem = 0, m_issue = 0, m_n = 0, m_t0 = kAttrib ? clock64() : 0;
       for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++it) {
         const TileCoord tc = decode_tile(a, tile);
         int4 grp = grp_in_smem ? grp_s[tc.g] : __ldg(a.group_tab + tc.g);
@@ -360,7 +370,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
           if (prof) c1 = clock64();
           const uint32_t sa = stage_base + stage * stage_bytes;
           if (leader) {
-            if (!(a.debug & 8)) {
+            if (!(dbg & 8)) {
               for (int j = 0; j < ndy; ++j) {
                 const uint64_t bdesc = ptx::make_sw128_desc(
                     a.resident ? res_base + (slab0 + j * sstride - tap0) * b_bytes : sa + a_bytes + j * b_bytes, 16, 1024);
@@ -407,7 +417,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
     // this warp's 32 pixels as a sub-box of the bw x bh tile (the epilogue maps have box ew x eh)
     const int sub_x = (quarter * 32) & (a.bw - 1);
     const int sub_y = (quarter * 32) >> a.bw_shift;
-    const bool skip = (a.debug & 1) != 0;
+    const bool skip = (dbg & 1) != 0;
     const bool has_in = (epi & kEpiIn) != 0 && !skip;
     const int n_in = ((epi & VSR_EPI_RES_PRE) ? 1 : 0) + ((epi & (VSR_EPI_PRELU_BWD | VSR_EPI_RELU_BWD)) ? 1 : 0) +
                      ((epi & VSR_EPI_OUT2) ? 1 : 0);
@@ -420,11 +430,11 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
     const uint32_t res2_t = nxt;
     const uint32_t in_bar = in_bar0 + 8 * ew;
     uint32_t in_phase = 0;
-    const float slope = (epi & (VSR_EPI_PRELU | VSR_EPI_PRELU_BWD)) ? __ldg(a.slope) : 0.f;
-    const float inv_slope = slope != 0.f ? 1.f / slope : 0.f;
-    const bool slope01 = slope >= 0.f && slope <= 1.f;
+    // (slope == 0 and slope < 0: see Prelu in common.cuh)
+    const Prelu pr = make_prelu((epi & (VSR_EPI_PRELU | VSR_EPI_PRELU_BWD)) ? __ldg(a.slope) : 1.f);
+    const bool slope01 = pr.fwd >= 0.f && pr.fwd <= 1.f;
     float slope_acc = 0.f;
-    long long e_wait = 0, e_in = 0, e_ld = 0, e_math = 0, e_st = 0, e_iss = 0, e_t0 = clock64();
+    long long e_wait = 0, e_in = 0, e_ld = 0, e_math = 0, e_st = 0, e_iss = 0, e_t0 = kAttrib ? clock64() : 0;
 
     // one elected lane fetches the epilogue operands of a 64-channel chunk through TMA
     auto issue_in = [&](int n, int y0, int x0, int c0) {
@@ -523,14 +533,19 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
                 v[8 * j + 6] += bf16_lo(rq.w); v[8 * j + 7] += bf16_hi(rq.w);
               }
             }
+            uint32_t posmask = 0u;                   // negative slope only: [x > 0] travels in the LSB of y
             if (epi & VSR_EPI_PRELU) {
               if (slope01) {
                 // for 0 <= a <= 1: PReLU(v) = max(v, a*v) exactly (two instructions per element instead of three)
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], slope * v[i]);
+                for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], pr.fwd * v[i]);
               } else {
+                if (pr.tag) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : slope * v[i];
+                  for (int i = 0; i < 32; ++i) posmask |= (v[i] > 0.f ? 1u : 0u) << i;
+                }
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : pr.fwd * v[i];
               }
             }
             if (epi & VSR_EPI_RELU) {
@@ -548,13 +563,14 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
                   for (int p = 0; p < 2; ++p) {
                     const float f = p ? bf16_hi(w4[q]) : bf16_lo(w4[q]);
                     const int i = 8 * j + 2 * q + p;
-                    const bool pos = f > 0.f;
+                    bool pos = f > 0.f;
                     if (epi & VSR_EPI_PRELU_BWD) {
+                      if (pr.tag) pos = ((w4[q] >> (16 * p)) & 1u) != 0u;
                       // out-of-image pixels read f = 0 from the TMA zero fill and contribute exactly 0
-                      // d(slope) = sum over y <= 0 of g * x with x = y / slope: accumulate g * min(y, 0) here and
+                      // d(slope) = sum over x <= 0 of g * x with x = y / slope: accumulate g * y here and
                       // scale by 1 / slope once per CTA
-                      slope_acc = fmaf(v[i], fminf(f, 0.f), slope_acc);
-                      v[i] *= pos ? 1.f : slope;
+                      slope_acc = fmaf(v[i], pos ? 0.f : f, slope_acc);
+                      v[i] *= pos ? 1.f : pr.slope;
                     } else {
                       v[i] = pos ? v[i] : 0.f;
                     }
@@ -570,6 +586,13 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
               o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
               o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
               o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+              if ((epi & VSR_EPI_PRELU) && pr.tag) {
+                const uint32_t m8 = posmask >> (8 * j);
+                o.x = (o.x & 0xfffefffeu) | (m8 & 1u) | (((m8 >> 1) & 1u) << 16);
+                o.y = (o.y & 0xfffefffeu) | ((m8 >> 2) & 1u) | (((m8 >> 3) & 1u) << 16);
+                o.z = (o.z & 0xfffefffeu) | ((m8 >> 4) & 1u) | (((m8 >> 5) & 1u) << 16);
+                o.w = (o.w & 0xfffefffeu) | ((m8 >> 6) & 1u) | (((m8 >> 7) & 1u) << 16);
+              }
               st_shared_v4(tile_addr(out_t, lane, 4 * h + j), o);
             }
             if (epi & VSR_EPI_OUT2) {
@@ -596,7 +619,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
-            if (!(a.debug & 16)) {
+            if (!(dbg & 16)) {
               tma_store_4d(&a.out_map, out_t, grp.x + c, tc.x0 + sub_x, tc.y0 + m * a.bh + sub_y, tc.n);
               if (epi & VSR_EPI_OUT2)
                 tma_store_4d(&a.out2_map, res2_t, grp.x + c, tc.x0 + sub_x, tc.y0 + m * a.bh + sub_y, tc.n);
@@ -620,7 +643,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
       printf("tc2-prof epilogue warp %d: total %lld cyc, wait(tfull) %lld, operands %lld, tmem-ld %lld, math %lld, pack+sts %lld, fence+issue %lld\n",
              warp, clock64() - e_t0, e_wait, e_in, e_ld, e_math, e_st, e_iss);
     if (epi & VSR_EPI_PRELU_BWD) {
-      slope_acc = warp_sum(slope_acc) * inv_slope;
+      slope_acc = warp_sum(slope_acc) * pr.inv;
       if (lane == 0) red[ew] = slope_acc;
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (ew == 0 && lane == 0)
@@ -628,7 +651,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
     }
   }
 
-  const uint64_t g_t2 = ptx::globaltimer_ns();
+  const uint64_t g_t2 = kAttrib ? ptx::globaltimer_ns() : 0;
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == kMmaWarp) {
@@ -774,8 +797,8 @@ int tapgemm_tc2_launch(const VsrTapGemmDesc* d, cudaStream_t stream) {
   a.epi_bytes = kEpiWarps * (1 + n_in) * kTileBytes;
   const int b_bytes = d->nt * 128;
   const long avail = kSmemBudget - kCtrlBytes - a.epi_bytes;
-  const char* env_dbg = getenv("VSR_TC_DEBUG");            // re-read per launch: attribution sweeps flip it
-  a.debug = env_dbg ? atoi(env_dbg) : 0;
+  const Tunables& tn = tunables();
+  a.debug = tn.tc_debug > 0 ? tn.tc_debug : 0;
 
   // ---- shared-load mode: taps that differ only by a row shift read one A box; with nt <= 128 two pixel
   // tiles stacked in y also share every weight slab.  Needs the host copies of the tables
@@ -785,8 +808,7 @@ int tapgemm_tc2_launch(const VsrTapGemmDesc* d, cudaStream_t stream) {
   int ndy_max = 1;
   const long res_need = (long)d->max_group_taps * b_bytes;
   {
-    const char* env_tall = getenv("VSR_TC_TALL");
-    const bool want = !(env_tall && env_tall[0] == '0');
+    const bool want = tn.tc_tall != 0;
     bool ok = want && d->tap_tab_host != nullptr && bw >= 8 && bw * bh == kBlockM && d->n_taps_total <= 4095 &&
               d->n_groups <= kMaxTallGroups && (d->n_groups == 1 || d->group_tab_host != nullptr);
     int n_cols = 0, longest = 0;
@@ -813,8 +835,7 @@ int tapgemm_tc2_launch(const VsrTapGemmDesc* d, cudaStream_t stream) {
       // streamed slabs: three stages of {shared box + its slabs} when they fit; two are enough when a stage is long
       // (3 taps x mb sub-tiles x 4 MMAs) and the alternative is one load per tap (3x the L2 -> SM traffic: the
       // 3x3(x3) convolutions of the Conv3d path, profiles/README.md).  VSR_TC_TALL_STAGES=3 restores the old rule.
-      static const char* env_ts = getenv("VSR_TC_TALL_STAGES");
-      const int min_stages = (env_ts && env_ts[0] == '3') ? 3 : 2;
+      const int min_stages = tn.tc_tall_stages == 3 ? 3 : 2;
       const bool stream_ok = min_stages * (abox + (long)longest * b_bytes) <= avail;
       if (rows <= 256 && (res_ok || stream_ok)) {
         a.tall = 1;
@@ -844,9 +865,8 @@ int tapgemm_tc2_launch(const VsrTapGemmDesc* d, cudaStream_t stream) {
   // (resident slabs for the short nt = 64 tables of the 1x1 convolutions were measured neutral to slightly slower,
   //  with either tile walk: tools/hr_sweep.py; VSR_TC_RESIDENT=1 forces them)
   {
-    const char* env_res = getenv("VSR_TC_RESIDENT");
-    if (env_res && env_res[0] == '0') a.resident = 0;
-    if (env_res && env_res[0] == '1' && d->max_group_taps > 0 && res_need <= avail - 2 * (long)a.a_bytes)
+    if (tn.tc_resident == 0) a.resident = 0;
+    if (tn.tc_resident == 1 && d->max_group_taps > 0 && res_need <= avail - 2 * (long)a.a_bytes)
       a.resident = 1;
   }
   if (a.tall && !a.resident && 2 * ((long)a.a_bytes + (long)ndy_max * b_bytes) > avail) {
@@ -872,14 +892,12 @@ int tapgemm_tc2_launch(const VsrTapGemmDesc* d, cudaStream_t stream) {
   a.stage_bytes = a.resident ? a.a_bytes : a.a_bytes + ndy_max * b_bytes;
   int stages = (int)((avail - a.res_bytes) / a.stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
-  const char* env_stg = getenv("VSR_TC_STAGES");
-  if (env_stg && atoi(env_stg) >= 1 && atoi(env_stg) < stages) stages = atoi(env_stg);
+  if (tn.tc_stages >= 1 && tn.tc_stages < stages) stages = tn.tc_stages;
   VSR_CHECK_SUPPORTED(stages >= 1, "tapgemm(bf16, v2): no room for a pipeline stage");
   a.stages = stages;
   const int smem = kCtrlBytes + a.epi_bytes + a.res_bytes + stages * a.stage_bytes;
   int grid = num_sms();
-  const char* env_grid = getenv("VSR_TC_GRID");
-  if (env_grid && atoi(env_grid) >= 1) grid = atoi(env_grid);
+  if (tn.tc_grid >= 1) grid = tn.tc_grid;
   if (grid > a.num_tiles) grid = a.num_tiles;
   if (grid > kPartialsLen) grid = kPartialsLen;
   if (a.debug & 64) {
@@ -901,8 +919,7 @@ int tapgemm_tc2_launch(const VsrTapGemmDesc* d, cudaStream_t stream) {
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
-    const char* env_pdl = getenv("VSR_PDL");
-    if (!(env_pdl && env_pdl[0] == '0')) {
+    if (tn.pdl != 0) {
       cfg.attrs = attr;
       cfg.numAttrs = 1;
     }

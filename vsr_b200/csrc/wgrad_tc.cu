@@ -22,11 +22,17 @@
 
 namespace vsr {
 
-// from tapgemm_tc.cu
+// from tma_host.cu
 int get_src_map_pub(const VsrTensor4& t, int bw, int bh, CUtensorMap* out);
 void pick_box_pub(int h, int w, int* bw, int* bh);
 
 namespace {
+
+#ifdef VSR_ATTRIB        // timing attribution (tools/wg_attrib.py) exists only in builds with -DVSR_ATTRIB
+constexpr bool kAttrib = true;
+#else
+constexpr bool kAttrib = false;
+#endif
 
 constexpr int kTile = 128;
 constexpr int kTileBytes = kTile * 128;   // one [128 px x 64 ch] bf16 box
@@ -135,8 +141,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
     // uniform datapath (see tapgemm_tc2.cu).
     {
       const bool leader = ptx::elect_one();
-      const bool prof = (a.debug & 32) != 0;
-      long long p_wb = 0, p_wa = 0, p_t0 = clock64(), c0 = 0;
+      const bool prof = kAttrib && (a.debug & 32) != 0;
+      long long p_wb = 0, p_wa = 0, p_t0 = kAttrib ? clock64() : 0, c0 = 0;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -205,9 +211,9 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
       const uint32_t idesc = ptx::make_idesc_bf16(128, a.ncta, 1, 1);
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t lbo = a.tall ? a.row_bytes : kTileBytes;
-      const bool prof = (a.debug & 32) != 0;
-      long long m_wb = 0, m_wa = 0, m_is = 0, m_t0 = clock64(), c0 = 0, c1 = 0;
-      const uint64_t m_g0 = ptx::globaltimer_ns();
+      const bool prof = kAttrib && (a.debug & 32) != 0;
+      long long m_wb = 0, m_wa = 0, m_is = 0, m_t0 = kAttrib ? clock64() : 0, c0 = 0, c1 = 0;
+      const uint64_t m_g0 = kAttrib ? ptx::globaltimer_ns() : 0;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -271,12 +277,12 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
         if (lane == 0) ptx::mbar_arrive(b_empty + 8 * bb);
       }
     }
-    const long long e_t0 = clock64();
+    const long long e_t0 = kAttrib ? clock64() : 0;
     if (pt1 > pt0) {
       ptx::mbar_wait(done_bar, 0);
       ptx::tc_fence_after();
     }
-    const long long e_t1 = clock64();
+    const long long e_t1 = kAttrib ? clock64() : 0;
     float* wsp = a.ws + (size_t)split * a.n_taps_total * a.nt * 64;
     for (int p = 0; p < n_pairs; ++p) {
       const int tl = 2 * p + half;
@@ -299,7 +305,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
         }
       }
     }
-    if ((a.debug & 32) && blockIdx.x == 0 && warp == 2 && lane == 0)
+    if (kAttrib && (a.debug & 32) && blockIdx.x == 0 && warp == 2 && lane == 0)
       printf("wg-prof epilogue: wait(done) %lld cyc, drain %lld cyc\n", e_t1 - e_t0, clock64() - e_t1);
     cs0_out = cs0;
     cs1_out = cs1;
@@ -472,15 +478,12 @@ int wgrad_tc_partial(const VsrTapGemmDesc* d, int want_bias, int slice, int n_sl
   a.group_tab = reinterpret_cast<const int4*>(d->group_tab);
   a.row_bytes = p.bw * 128;
   {
-    const char* env_dbg = getenv("VSR_WG_DEBUG");
-    a.debug = env_dbg ? atoi(env_dbg) : 0;
+    a.debug = tunables().wg_debug > 0 ? tunables().wg_debug : 0;
   }
   {
     // shared-pair mode: reorder the taps of every group so that positions (2p, 2p+1) hold a tap and the tap
     // with the same source, channel slice and dx one pixel row lower; all pairs of the launch must be such
-    const char* env_tall = getenv("VSR_WG_TALL");
-    const int4* gt = nullptr;
-    if (!(env_tall && env_tall[0] == '0') && d->tap_tab_host && d->n_taps_total <= kMaxPerm && d->n_groups == 1 &&
+    if (tunables().wg_tall != 0 && d->tap_tab_host && d->n_taps_total <= kMaxPerm && d->n_groups == 1 &&
         p.bw >= 8 && p.bw * p.bh == kTile && d->n_taps_total % 2 == 0 && pair_rows(d->tap_tab_host, d->n_taps_total, a.perm)) {
       a.use_perm = 1;
       a.tall = 1;
@@ -489,7 +492,6 @@ int wgrad_tc_partial(const VsrTapGemmDesc* d, int want_bias, int slice, int n_sl
         if (rc != VSR_OK) return rc;
       }
     }
-    (void)gt;
   }
   // workspace: [n_slices * splits][n] weight partials, then [n_slices * splits][cout] bias partials
   const size_t n_w = (size_t)d->n_taps_total * d->nt * 64;
@@ -525,8 +527,7 @@ int wgrad_tc_partial(const VsrTapGemmDesc* d, int want_bias, int slice, int n_sl
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
-    const char* env_pdl = getenv("VSR_PDL");
-    if (!(env_pdl && env_pdl[0] == '0')) {
+    if (tunables().pdl != 0) {
       cfg.attrs = attr;
       cfg.numAttrs = 1;
     }

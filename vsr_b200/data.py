@@ -150,6 +150,60 @@ class Dataloader(DataLoader):
         np.random.seed((np.random.get_state()[1][0] + worker_id) % (2 ** 32))
 
 
+class ShardedSampler(torch.utils.data.Sampler):
+    """Rank-aware, seed-deterministic sampler for the data-parallel trainer.  The reference reseeds
+    numpy once per epoch (base_trainer.py:54) and shuffles inside its single process; here every rank draws the SAME
+    permutation from the epoch's seed (`set_epoch_seed`, called by VSRTrainer with that very seed) and takes every
+    world-th index starting at its rank.  The index list is padded by wrap-around to a multiple of the world size
+    (as torch's DistributedSampler does), so all ranks see the same number of batches - a rank that ran out early
+    would leave the others blocked in the gradient all-reduce."""
+
+    def __init__(self, n, rank, world, shuffle):
+        self.n, self.rank, self.world, self.shuffle = int(n), int(rank), int(world), bool(shuffle)
+        self.seed = 0
+
+    def set_epoch_seed(self, seed):
+        self.seed = int(seed) % (2 ** 32)
+
+    def indices(self):
+        order = np.random.RandomState(self.seed).permutation(self.n) if self.shuffle else np.arange(self.n)
+        total = -(-self.n // self.world) * self.world
+        if total > self.n:
+            order = np.concatenate([order, order[:total - self.n]])
+        return order[self.rank::self.world]
+
+    def __iter__(self):
+        return iter(self.indices().tolist())
+
+    def __len__(self):
+        return -(-self.n // self.world)
+
+
+def shard_loader(loader, rank, world):
+    """the same loader restricted to this rank's shard; returns (loader, sampler or None).  torch DataLoaders are
+    rebuilt around a ShardedSampler (same dataset, batch size, workers, collate, pinning); DeviceCineLoader takes the
+    sampler directly; anything else is returned unchanged (the trainer then checks the batch counts across ranks)."""
+    if world <= 1:
+        return loader, None
+    if isinstance(loader, DeviceCineLoader):
+        sampler = ShardedSampler(len(loader.dataset), rank, world, loader.shuffle)
+        loader.sampler = sampler
+        return loader, sampler
+    if isinstance(loader, DataLoader):
+        if isinstance(loader.sampler, (ShardedSampler, torch.utils.data.distributed.DistributedSampler)):
+            return loader, loader.sampler if isinstance(loader.sampler, ShardedSampler) else None
+        if loader.batch_sampler is None or loader.batch_size is None:
+            return loader, None
+        shuffle = isinstance(loader.sampler, torch.utils.data.RandomSampler)
+        sampler = ShardedSampler(len(loader.dataset), rank, world, shuffle)
+        new = loader.__class__.__new__(loader.__class__)
+        DataLoader.__init__(new, loader.dataset, batch_size=loader.batch_size, sampler=sampler,
+                            num_workers=loader.num_workers, collate_fn=loader.collate_fn, pin_memory=loader.pin_memory,
+                            drop_last=loader.drop_last, timeout=loader.timeout, worker_init_fn=loader.worker_init_fn)
+        return new, sampler
+    return loader, None
+
+
 class DeviceStager:
     """Wraps a batch iterator: copies each batch from pinned host memory to the device on a side
     stream one step ahead of the consumer (replaces the blocking, pageable `tensor.to(device)` of
@@ -189,11 +243,27 @@ class DeviceStager:
                 ev.record(self.stream)
             return dev, ev
 
+        def claim(obj, stream):
+            # the staged tensors were allocated on the side stream: tell the caching allocator that the consumer's
+            # stream uses them, so that their blocks are not handed to a later prefetch (whose H2D copy has no
+            # dependency on the consumer) before the queued kernels have read them
+            if isinstance(obj, torch.Tensor):
+                if obj.is_cuda:
+                    obj.record_stream(stream)
+            elif isinstance(obj, dict):
+                for v in obj.values():
+                    claim(v, stream)
+            elif isinstance(obj, (list, tuple)):
+                for v in obj:
+                    claim(v, stream)
+
         nxt = fetch()
         while nxt is not None:
             dev, ev = nxt
             nxt = fetch()
-            torch.cuda.current_stream(self.device).wait_event(ev)
+            cur = torch.cuda.current_stream(self.device)
+            cur.wait_event(ev)
+            claim(dev, cur)
             yield dev
 
 
@@ -209,11 +279,12 @@ class DeviceCineLoader:
     def __init__(self, dataset, device, batch_size=1, shuffle=False, drop_last=False, ops=None):
         self.dataset, self.device, self.batch_size = dataset, torch.device(device), batch_size
         self.shuffle, self.drop_last, self._ops = shuffle, drop_last, ops
+        self.sampler = None          # a ShardedSampler under the data-parallel trainer (shard_loader)
         self.lr = torch.from_numpy(np.stack(dataset.lr).astype(np.float32)).to(self.device)      # [S, T, h, w]
         self.hr = torch.from_numpy(np.stack(dataset.hr).astype(np.float32)).to(self.device)      # [S, T, rh, rw]
 
     def __len__(self):
-        n = len(self.dataset)
+        n = len(self.sampler) if self.sampler is not None else len(self.dataset)
         return n // self.batch_size if self.drop_last else -(-n // self.batch_size)
 
     def _backend(self):
@@ -244,7 +315,10 @@ class DeviceCineLoader:
         return out
 
     def __iter__(self):
-        n = len(self.dataset)
-        order = np.random.permutation(n) if self.shuffle else np.arange(n)
+        if self.sampler is not None:
+            order = self.sampler.indices()
+        else:
+            n = len(self.dataset)
+            order = np.random.permutation(n) if self.shuffle else np.arange(n)
         for b in range(len(self)):
             yield self.batch(order[b * self.batch_size:(b + 1) * self.batch_size])

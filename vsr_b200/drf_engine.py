@@ -15,6 +15,25 @@ from ._lib import EPI_BIAS, EPI_OUT2, EPI_PRELU, EPI_PRELU_BWD, EPI_RES_PRE
 from .drf_plan import DrfPlan
 
 
+def _stacked_view(ts):
+    """[T, ...] view of T equally shaped tensors that are consecutive slices of one buffer (outputs of the batched
+    output block, gradients written by the segmented loss kernel, batches of DeviceCineLoader), else None"""
+    t0 = ts[0]
+    step = t0.numel() * t0.element_size()
+    if t0.is_contiguous() and all(t.shape == t0.shape and t.dtype == t0.dtype and t.is_contiguous() and
+                                  t.data_ptr() == t0.data_ptr() + i * step for i, t in enumerate(ts)):
+        room = (t0.untyped_storage().nbytes() - t0.storage_offset() * t0.element_size()) // max(step, 1)
+        if room >= len(ts):
+            return t0.as_strided((len(ts), *t0.shape), (t0.numel(), *t0.stride()))
+    return None
+
+
+def _as_stacked(ts):
+    """[T, ...] tensor of T equally shaped tensors: a view when possible (_stacked_view), else one copy"""
+    v = _stacked_view(ts)
+    return v if v is not None else torch.stack([t.contiguous() for t in ts])
+
+
 class _Frame:
     __slots__ = ("x", "a1", "inn", "hidden", "lr", "u", "hr", "d", "f", "feat", "s", "y")
 
@@ -30,10 +49,18 @@ class DrfEngine:
         self.fwd_w_idx = torch.from_numpy(plan.fwd_w_idx).to(dev)
         self.bwd_w_idx = torch.from_numpy(plan.bwd_w_idx).to(dev)
         self.fwd_b_idx = torch.from_numpy(plan.fwd_b_idx).to(dev)
-        self.unpack = [(lo, torch.from_numpy(idx).to(dev)) for lo, idx in plan.unpack_passes]
-        b = plan.bias_unpack_idx
-        nz = (b >= 0).nonzero()[0]
-        self.bias_unpack = (int(nz.min()), torch.from_numpy(b[nz.min():nz.max() + 1].copy()).to(dev))
+        # un-packing maps (packed weight / bias gradients -> flat bucket), cut at the gradient-bucket boundaries
+        self.buckets = []
+        for blo, bhi, names in plan.grad_buckets(3):
+            wparts = []
+            for lo, idx in plan.unpack_passes:
+                a, b_ = max(lo, blo), min(lo + len(idx), bhi)
+                if a < b_ and (idx[a - lo:b_ - lo] >= 0).any():
+                    wparts.append((a, torch.from_numpy(idx[a - lo:b_ - lo].copy()).to(dev)))
+            b = plan.bias_unpack_idx[blo:bhi]
+            nz = (b >= 0).nonzero()[0]
+            bpart = (blo + int(nz.min()), torch.from_numpy(b[nz.min():nz.max() + 1].copy()).to(dev)) if len(nz) else None
+            self.buckets.append((blo, bhi, names, wparts, bpart))
         self._ws = {}
         self._row_dst = {}
         self.flat = None
@@ -213,8 +240,10 @@ class DrfEngine:
         return outs, saved
 
     # ---- backward --------------------------------------------------------------------------
-    def backward(self, saved, d_outs):
-        """d_outs: list of T [N,Cout,rh,rw] gradients (None = zero). Returns the flat gradient."""
+    def backward(self, saved, d_outs, on_bucket=None):
+        """d_outs: list of T [N,Cout,rh,rw] gradients (None = zero). Returns the flat gradient.
+        `on_bucket(gflat, lo, hi)` is called as soon as gflat[lo:hi] is final (ranges of DrfPlan.grad_buckets, in
+        order): the data-parallel trainer starts that range's all-reduce while the next range is computed."""
         P, ops = self.plan, self.ops
         F, G, r = P.F, P.G, P.r
         r2 = r * r
@@ -301,7 +330,7 @@ class DrfEngine:
                         zero = torch.zeros(N, P.cout, h * r, w * r, dtype=pd, device=dev)
                     d = zero
                 douts.append(d)
-            d_all = torch.stack(douts).view(T * N, P.cout, h * r, w * r)
+            d_all = _as_stacked(douts).view(T * N, P.cout, h * r, w * r)
             d_s = dzb[f"ds{n_lv}"] = self._new(T, N, h, w, S0.s[-1].shape[-1])
             ws = self._workspace("last", ops.conv3x3_last_bwd_workspace(flat_tn(bufs[f"s{n_lv}"]), r, F, P.cout))
             ops.conv3x3_last_bwd(flat_tn(bufs[f"s{n_lv}"]), r, F, P.phases, self._pview(self.flat, P.last_name + ".weight"),
@@ -421,8 +450,16 @@ class DrfEngine:
             ws = self._workspace("first", ops.conv3x3_first_bwd_workspace(x_all, 4 * F))
             ops.conv3x3_first_bwd(x_all, dz_a1, self._pview(gflat, f"{P.in_name}.conv1.weight"),
                                   self._pview(gflat, f"{P.in_name}.conv1.bias"), True, ws)
-        for lname, (src_keys, dz_key, view) in deferred.items():
+        # PReLU slope gradients: every partial row exists by now (data gradients only)
+        rd = self._row_dst.get(T)
+        if rd is None or rd.numel() != len(row_dst):        # the launch sequence is a function of T only
+            rd = torch.tensor(row_dst, dtype=torch.int32, device=dev)
+            self._row_dst[T] = rd
+        ops.reduce_partials(partials, row[0], rd, gflat)
+
+        def deferred_wgrad(lname):
             # weight (+ bias) gradient of the layer over all T frames in one launch: [T, N, ...] -> [T*N, ...]
+            src_keys, dz_key, view = deferred[lname]
             L = P.fwd[lname]
 
             def flat(b):
@@ -438,18 +475,20 @@ class DrfEngine:
                 rows = dz.numel() // L.bias_c
                 wsb = self._workspace("colsum", ops.colsum_workspace(rows, L.bias_c))
                 ops.colsum(dz, rows, L.bias_c, db, True, wsb)
+
         for lname, (srcs, dz, wsl, used) in pending.items():
             L = P.fwd[lname]
             ops.tapgemm_wgrad_finish(L.table, srcs, dz, dw_packed[L.w_off:L.w_off + L.w_numel],
                                      db_packed[L.b_off:L.b_off + L.bias_c], L.bias_c, True, used, T, wsl)
-        # ---- un-pack: weights, biases, PReLU slopes ----
-        for lo, idx in self.unpack:
-            ops.gather_add(dw_packed, idx, gflat[lo:lo + idx.numel()])
-        lo, idx = self.bias_unpack
-        ops.gather_add(db_packed, idx, gflat[lo:lo + idx.numel()])
-        rd = self._row_dst.get(T)
-        if rd is None or rd.numel() != len(row_dst):        # the launch sequence is a function of T only
-            rd = torch.tensor(row_dst, dtype=torch.int32, device=dev)
-            self._row_dst[T] = rd
-        ops.reduce_partials(partials, row[0], rd, gflat)
+        # ---- bucket by bucket: deferred weight gradients, un-pack (weights, biases), hand the range over ----
+        for blo, bhi, names, wparts, bpart in self.buckets:
+            for lname in names:
+                if lname in deferred:
+                    deferred_wgrad(lname)
+            for lo, idx in wparts:
+                ops.gather_add(dw_packed, idx, gflat[lo:lo + idx.numel()])
+            if bpart is not None:
+                ops.gather_add(db_packed, bpart[1], gflat[bpart[0]:bpart[0] + bpart[1].numel()])
+            if on_bucket is not None:
+                on_bucket(gflat, blo, bhi)
         return gflat

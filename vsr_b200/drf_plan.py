@@ -376,6 +376,37 @@ class DrfPlan:
             for lv in range(self.out_levels):
                 self._out_level(lv, f"out_block.conv{lv + 1}")
 
+    # ---- gradient buckets ------------------------------------------------------------------
+    def grad_buckets(self, n_buckets=3):
+        """Contiguous ranges [lo, hi) of the flat gradient bucket with the tap-GEMM layers whose weight and bias
+        gradients land inside each: the engine finishes the ranges one after the other at the end of backward, so
+        that the data-parallel trainer can all-reduce range k while the weight gradients of range k+1 are still
+        being computed.  The ranges tile [0, n_params); a layer's parameters never straddle a boundary."""
+        spans = []
+        for L in self.fwd.values():
+            idx = np.concatenate([np.asarray(sl).reshape(-1) for sl in L.slabs])
+            idx = idx[idx >= 0]
+            lo, hi = int(idx.min()), int(idx.max()) + 1
+            if L.bias_idx is not None:
+                b = np.asarray(L.bias_idx)
+                b = b[b >= 0]
+                lo, hi = min(lo, int(b.min())), max(hi, int(b.max()) + 1)
+            spans.append((lo, hi, L.name))
+        spans.sort()
+        for (l0, h0, n0), (l1, h1, n1) in zip(spans, spans[1:]):
+            assert h0 <= l1, f"layers {n0} and {n1} share parameters: gradient ranges would overlap"
+        total = sum(h - l for l, h, _ in spans)
+        buckets, cur, acc, lo = [], [], 0, 0
+        for i, (l, h, name) in enumerate(spans):
+            cur.append(name)
+            acc += h - l
+            last = i == len(spans) - 1
+            if last or (len(buckets) < n_buckets - 1 and acc >= total * (len(buckets) + 1) / n_buckets):
+                hi = self.n_params if last else spans[i + 1][0]
+                buckets.append((lo, hi, cur))
+                cur, lo = [], hi
+        return buckets
+
     # ---- packing maps ----------------------------------------------------------------------
     def _finalize(self):
         def pack(store):

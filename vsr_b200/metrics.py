@@ -54,7 +54,7 @@ class SSIM(nn.Module):
         self.c1, self.c2 = (0.01 * value_range) ** 2, (0.03 * value_range) ** 2
         i = torch.arange(11, dtype=torch.float32)
         g = 1 / (1.5 * math.sqrt(2 * math.pi)) * torch.exp(-((i - 5) / (2 * 1.5)) ** 2)
-        self.register_buffer("window", g / g.sum())
+        self.register_buffer("window", g / g.sum(), persistent=False)   # not in the reference state_dict
         # the reference registers the full 2-D kernel as `weight`; keep the buffer for state parity
         k = torch.outer(g, g) if dim == 2 else torch.einsum("i,j,k->ijk", g, g, g)
         self.register_buffer("weight", (k / k.sum()).view(1, 1, *k.shape).repeat(channels, *[1] * (dim + 1)))

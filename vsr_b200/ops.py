@@ -105,6 +105,33 @@ def _make_desc(tab: TapTable, srcs: Sequence[torch.Tensor], out: torch.Tensor):
     return d
 
 
+class _TimedLib:
+    """bench.py's per-kernel pass: the ctypes handle with a CUDA-event pair around every kernel-launching entry
+    point.  Records (entry name, start, end, meta, return code) where meta = (family, flops, shape signature, algorithmic bytes) for
+    the tap-GEMM family (set by the calling CudaOps method) and None for the others."""
+
+    _QUERIES = ("vsr_abi_version", "vsr_last_error", "vsr_partials_len", "vsr_slab_index", "vsr_metric_workspace",
+                "vsr_reload_tunables")
+
+    def __init__(self, lib, ops, sink):
+        self._lib, self._ops, self._sink = lib, ops, sink
+
+    def __getattr__(self, name):
+        fn = getattr(self._lib, name)
+        if not name.startswith("vsr_") or name.endswith("_workspace") or name in self._QUERIES:
+            return fn
+        ops, sink = self._ops, self._sink
+
+        def timed(*a):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = fn(*a)
+            e1.record()
+            sink.append((name, e0, e1, ops._meta, rc))
+            return rc
+        return timed
+
+
 class CudaOps:
     """The product backend: every method is one or two kernel launches on the current stream."""
     name = "cuda"
@@ -113,7 +140,23 @@ class CudaOps:
         self.lib = _lib.lib()
         self.partials_len = self.lib.vsr_partials_len()
         self.launches = 0
-        self.timing = None      # set to a list to record (kind, flops, start_event, end_event)
+        self.timing = None      # a list while bench.py's per-kernel pass runs (start_timing / stop_timing)
+        self._meta = None
+
+    def start_timing(self):
+        """CUDA events around every kernel-launching C-ABI call from now on (bench.py; not for production runs)"""
+        self.timing = []
+        self.lib = _TimedLib(_lib.lib(), self, self.timing)
+
+    def stop_timing(self):
+        t, self.timing, self.lib = self.timing, None, _lib.lib()
+        return t
+
+    @staticmethod
+    def gemm_records(records):
+        """(family, flops, start, end, shape signature, algorithmic bytes) of the tap-GEMM / weight-gradient launches"""
+        return [(m[0], m[1], e0, e1, m[2], m[3]) for name, e0, e1, m, rc in records
+                if m is not None and not (name == "vsr_tapgemm_wgrad_partial" and rc != 1)]
 
     # ---- tap-GEMM ----------------------------------------------------------------------
     def tapgemm(self, tab, srcs, out, w, bias=None, epi=0, out_scale=1.0, slope=None, residual=None,
@@ -130,10 +173,6 @@ class CudaOps:
         d.slope_partials = slope_partials.data_ptr() if slope_partials is not None else None
         fn = self.lib.vsr_tapgemm_simt_bf16 if force_simt else self.lib.vsr_tapgemm
         if self.timing is not None:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            check(fn(C.byref(d), _stream()), "vsr_tapgemm")
-            e1.record()
             pix = out.shape[0] * out.shape[1] * out.shape[2]
             sig = f"taps{tab.n_taps_total}_nt{tab.nt}_g{tab.n_groups}_px{pix}_epi{epi}"
             es = out.element_size()
@@ -141,9 +180,9 @@ class CudaOps:
             # epilogue operands read (residual, saved activation, second residual) / written (second output)
             n_extra = ((epi & EPI_RES_PRE) != 0) + ((epi & (EPI_PRELU_BWD | EPI_RELU_BWD)) != 0) + 2 * ((epi & EPI_OUT2) != 0)
             nbytes += es * pix * out.shape[-1] * n_extra
-            self.timing.append(("tapgemm", 2.0 * pix * tab.n_taps_total * tab.nt * tab.kc, e0, e1, sig, nbytes))
-        else:
-            check(fn(C.byref(d), _stream()), "vsr_tapgemm")
+            self._meta = ("tapgemm", 2.0 * pix * tab.n_taps_total * tab.nt * tab.kc, sig, nbytes)
+        check(fn(C.byref(d), _stream()), "vsr_tapgemm")
+        self._meta = None
         self.launches += 1
 
     def tapgemm_wgrad_workspace(self, tab, srcs, dz):
@@ -154,8 +193,7 @@ class CudaOps:
         d = _make_desc(tab, srcs, dz)
         _need_cuda(dw, workspace, db)
         if self.timing is not None:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
+            self._meta = self._wgrad_meta(tab, srcs, dz)
         fused = False
         nbytes_ws = workspace.numel() * workspace.element_size()
         if db is not None:
@@ -167,34 +205,29 @@ class CudaOps:
         else:
             check(self.lib.vsr_tapgemm_wgrad(C.byref(d), _p(dw), int(accumulate), _p(workspace), nbytes_ws,
                                              _stream()), "vsr_tapgemm_wgrad")
-        if self.timing is not None:
-            e1.record()
-            pix = dz.shape[0] * dz.shape[1] * dz.shape[2]
-            sig = f"taps{tab.n_taps_total}_nt{tab.nt}_g{tab.n_groups}_px{pix}"
-            es = dz.element_size()
-            nbytes = es * (sum(pix * s.shape[-1] for s in srcs) + pix * dz.shape[-1])
-            self.timing.append(("wgrad", 2.0 * pix * tab.n_taps_total * tab.nt * tab.kc, e0, e1, sig, nbytes))
+        self._meta = None
         self.launches += 2
         return fused
+
+    @staticmethod
+    def _wgrad_meta(tab, srcs, dz):
+        pix = dz.shape[0] * dz.shape[1] * dz.shape[2]
+        sig = f"taps{tab.n_taps_total}_nt{tab.nt}_g{tab.n_groups}_px{pix}"
+        nbytes = dz.element_size() * (sum(pix * s.shape[-1] for s in srcs) + pix * dz.shape[-1])
+        return ("wgrad", 2.0 * pix * tab.n_taps_total * tab.nt * tab.kc, sig, nbytes)
 
     def tapgemm_wgrad_partial(self, tab, srcs, dz, workspace, slice_, n_slices, db_period):
         """per-split partials of dw / db into slice `slice_` of `workspace`; False if unsupported."""
         d = _make_desc(tab, srcs, dz)
         _need_cuda(workspace)
         if self.timing is not None:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
+            self._meta = self._wgrad_meta(tab, srcs, dz)
         rc = self.lib.vsr_tapgemm_wgrad_partial(C.byref(d), db_period, int(slice_), int(n_slices), _p(workspace),
                                                 workspace.numel() * workspace.element_size(), _stream())
+        self._meta = None
         if rc < 0:
             check(rc, "vsr_tapgemm_wgrad_partial")
         if rc == 1:
-            if self.timing is not None:
-                e1.record()
-                pix = dz.shape[0] * dz.shape[1] * dz.shape[2]
-                sig = f"taps{tab.n_taps_total}_nt{tab.nt}_g{tab.n_groups}_px{pix}"
-                nbytes = dz.element_size() * (sum(pix * s.shape[-1] for s in srcs) + pix * dz.shape[-1])
-                self.timing.append(("wgrad", 2.0 * pix * tab.n_taps_total * tab.nt * tab.kc, e0, e1, sig, nbytes))
             self.launches += 1
         return rc == 1
 
@@ -400,6 +433,14 @@ class CudaOps:
         _need_cuda(out, target, partials, grad)
         check(self.lib.vsr_loss_fwd_bwd(_p(out), _p(target), out.numel(), kind, param, grad_scale,
                                         _p(partials), _p(grad), _stream()), "vsr_loss_fwd_bwd")
+        self.launches += 1
+
+    def loss_fwd_bwd_seg(self, out, target, n_segments, kind, param, grad_scale, partials, grad):
+        """all `n_segments` equally sized frames of out / target (one contiguous tensor each) in one launch; row s of
+        `partials` [n_segments, partials_len] receives the partial sums of frame s"""
+        _need_cuda(out, target, partials, grad)
+        check(self.lib.vsr_loss_fwd_bwd_seg(_p(out), _p(target), out.numel() // n_segments, n_segments, kind, param,
+                                            grad_scale, _p(partials), _p(grad), _stream()), "vsr_loss_fwd_bwd_seg")
         self.launches += 1
 
     def metric_workspace(self, n, per_sample):

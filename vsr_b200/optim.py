@@ -5,14 +5,21 @@ import torch
 
 
 class FlatAdam(torch.optim.Optimizer):
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, net=None):
+    _RING = 4      # pinned hyper-parameter buffers in flight (the host may run this many steps ahead of the device)
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, amsgrad=False, net=None):
         params = list(params)
+        if amsgrad:
+            raise NotImplementedError("FlatAdam: amsgrad is not implemented by the fused kernel (use torch.optim.Adam)")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        if len(self.param_groups) != 1:
+            raise NotImplementedError("FlatAdam optimises ONE parameter group (the net's flat bucket); got "
+                                      f"{len(self.param_groups)} groups")
         self._net = net
         self._m = self._v = None
         self._step = 0
         self.grad_scale = 1.0
-        self._hyper_host = self._hyper_dev = None
+        self._hyper_host, self._hyper_ev, self._hyper_dev, self._hyper_i = [], [], None, 0
 
     def bind(self, net):
         """bind to a vsr_b200 net (its parameters must be exactly this optimizer's parameters)."""
@@ -47,13 +54,27 @@ class FlatAdam(torch.optim.Optimizer):
         self._step += 1
         vals = [float(grp["lr"]), grp["betas"][0], grp["betas"][1], grp["eps"], grp["weight_decay"],
                 float(self._step), self.grad_scale]
+        if len(self.param_groups) != 1:
+            raise NotImplementedError("FlatAdam optimises ONE parameter group (add_param_group is not supported)")
         if self._hyper_dev is None or self._hyper_dev.device != flat.device:
-            self._hyper_host = torch.zeros(7, dtype=torch.float32)
-            if flat.is_cuda:
-                self._hyper_host = self._hyper_host.pin_memory()
             self._hyper_dev = torch.zeros(7, dtype=torch.float32, device=flat.device)
-        self._hyper_host.copy_(torch.tensor(vals, dtype=torch.float32))
-        self._hyper_dev.copy_(self._hyper_host, non_blocking=True)
+            self._hyper_host = [torch.zeros(7, dtype=torch.float32) for _ in range(self._RING)]
+            self._hyper_ev = [None] * self._RING
+            if flat.is_cuda:
+                self._hyper_host = [h.pin_memory() for h in self._hyper_host]
+        # The H2D copy below is asynchronous and the host runs ahead of the device (graph replay, one sync per epoch):
+        # a pinned buffer is rewritten only after the copy that last read it has executed (ring + events), otherwise
+        # step k could see the step count / lr of step k+1.
+        i = self._hyper_i
+        self._hyper_i = (i + 1) % self._RING
+        if self._hyper_ev[i] is not None:
+            self._hyper_ev[i].synchronize()
+        self._hyper_host[i].copy_(torch.tensor(vals, dtype=torch.float32))
+        self._hyper_dev.copy_(self._hyper_host[i], non_blocking=True)
+        if flat.is_cuda:
+            ev = self._hyper_ev[i] or torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(flat.device))
+            self._hyper_ev[i] = ev
 
     def launch(self, flat_grad):
         """device side of a step: one fused kernel (graph-capturable)."""

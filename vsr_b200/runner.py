@@ -18,6 +18,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
+from .drf_engine import _as_stacked, _stacked_view
 from .losses import LOSS_KINDS
 from .optim import FlatAdam
 from .utils import DATASET_STATS
@@ -52,6 +53,7 @@ class VSRTrainStep:
         self.mean, self.std = DATASET_STATS[dataset]
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self._comm_stream, self._comm_pending = None, False
         if isinstance(optimizer, FlatAdam):
             optimizer.bind(net)
             optimizer.grad_scale = 1.0 / self.world
@@ -67,50 +69,63 @@ class VSRTrainStep:
     def _ops(self):
         return self.net._backend()
 
+    def _metric_values(self, outs, targets):
+        """[n_metric, T, N*C] per-frame, per-image metric values (PSNR fills [:, :, :N]): ONE launch pair per metric
+        over all T frames (they are consecutive slices of one buffer, or stacked into one here)."""
+        ops = self._ops()
+        T, n, c = len(outs), outs[0].shape[0], outs[0].shape[1]
+        o_all, y_all = _as_stacked(outs), _as_stacked(targets)          # [T, N, C, H, W]
+        per = outs[0].numel() // n
+        ws = self._buf("mws", (ops.metric_workspace(T * n * c, per) // 4 + 4,))
+        vals = self._buf("mvals", (len(self.metric_names), T, n * c))
+        for i, (name, fn) in enumerate(zip(self.metric_names, self.metric_fns)):
+            if name == "PSNR":
+                flat = self._buf("mpsnr", (T * n,))
+                ops.psnr(o_all.view(T * n, -1), y_all.view(T * n, -1), self.mean, self.std, float(fn.max_value), flat, ws)
+                vals[i, :, :n].copy_(flat.view(T, n))
+            else:
+                hw = outs[0].shape[2:]
+                ops.ssim(o_all.view(T * n * c, *hw), y_all.view(T * n * c, *hw), fn.window, self.mean, self.std,
+                         fn.c1, fn.c2, vals[i].view(-1), ws)
+        return vals
+
     def _metrics(self, outs, targets, acc):
         """acc[1 + n_loss + i] += mean over frames of metric i (fused denormalize)."""
-        ops = self._ops()
-        T, n = len(outs), outs[0].shape[0]
-        per = outs[0].numel() // n
-        ws = self._buf("mws", (ops.metric_workspace(n * outs[0].shape[1], per) // 4 + 4,))
-        vals = self._buf("mvals", (len(self.metric_names), T, n * outs[0].shape[1]))
-        for i, (name, fn) in enumerate(zip(self.metric_names, self.metric_fns)):
+        for name in self.metric_names:
             if name.startswith("Cardiac"):
                 raise NotImplementedError("Cardiac* metrics need the patient of every sample: predictors only "
                                           "(acdc_vsr_predictor.py:134-154); the reference's trainers do not use them")
-            for t in range(T):
-                o, y = outs[t], targets[t]
-                if name == "PSNR":
-                    ops.psnr(o, y, self.mean, self.std, float(fn.max_value), vals[i, t, :n], ws)
-                else:
-                    c = o.shape[1]
-                    ops.ssim(o.view(n * c, *o.shape[2:]), y.view(n * c, *y.shape[2:]), fn.window, self.mean,
-                             self.std, fn.c1, fn.c2, vals[i, t], ws)
+        n = outs[0].shape[0]
+        vals = self._metric_values(outs, targets)
         k = 1 + len(self.losses)
-        nvalid = vals.shape[2] if "SSIM" in self.metric_names else n
         for i, name in enumerate(self.metric_names):
             cnt = vals.shape[2] if name == "SSIM" else n
             acc[k + i] += vals[i, :, :cnt].mean()
-        del nvalid
 
-    def _loss(self, outs, targets, want_grad):
-        """fused losses over all frames: returns ([L] loss values on device, list of dL/dout)."""
+    def _loss_partials(self, outs, targets, want_grad):
+        """fused losses, ONE launch per loss over all T frames: (partials [L*T, partials_len], dL/dout frames)"""
         ops = self._ops()
-        T = len(outs)
-        L = len(self.losses)
+        T, L = len(outs), len(self.losses)
+        o_all, y_all = _as_stacked(outs), _as_stacked(targets)
+        numel = outs[0].numel()
         partials = self._buf("lpart", (L * T, ops.partials_len))
         partials.zero_()
-        grads = [torch.empty_like(o) for o in outs] if want_grad else [None] * T
+        g_all = torch.empty_like(o_all) if want_grad else None
         for li, (kind, param) in enumerate(self.losses):
-            for t in range(T):
-                numel = outs[t].numel()
-                g = grads[t]
-                if want_grad and li > 0:
-                    g = self._buf("gtmp", outs[t].shape)
-                ops.loss_fwd_bwd(outs[t], targets[t], kind, param, self.loss_weights[li] / (numel * T),
-                                 partials[li * T + t], g)
-                if want_grad and li > 0:
-                    ops.add(grads[t], g, grads[t])
+            g = g_all
+            if want_grad and li > 0:
+                g = self._buf("gtmp", o_all.shape)
+            ops.loss_fwd_bwd_seg(o_all, y_all, T, kind, param, self.loss_weights[li] / (numel * T),
+                                 partials[li * T:(li + 1) * T], g)
+            if want_grad and li > 0:
+                ops.add(g_all, g, g_all)
+        return partials, (list(g_all.unbind(0)) if want_grad else [None] * T)
+
+    def _loss(self, outs, targets, want_grad):
+        """returns ([L] loss values on device: mean over frames of the per-frame means, list of dL/dout)."""
+        ops = self._ops()
+        T, L = len(outs), len(self.losses)
+        partials, grads = self._loss_partials(outs, targets, want_grad)
         sums = self._buf("lsum", (L,))
         sums.zero_()
         rd = self._bufs.get("lrd")
@@ -128,14 +143,33 @@ class VSRTrainStep:
         eng.pack(net.flat, need_bwd=True)
         outs, saved = eng.forward(inputs, save=True)
         lvals, grads = self._loss(outs, targets, True)
-        gflat = eng.backward(saved, grads)
+        gflat = eng.backward(saved, grads, on_bucket=self._reduce_bucket if self.world > 1 else None)
         net.flat_grad = gflat
         return lvals, outs, gflat
 
+    def _reduce_bucket(self, gflat, lo, hi):
+        """all-reduce (sum; the 1/world mean is folded into Adam) of a finished range of the flat gradient bucket on
+        a side stream, so that NCCL over NVLink runs while the weight gradients of the next range are computed; the
+        fork / join are stream dependencies, hence captured with the rest of the step in its CUDA graph."""
+        if not gflat.is_cuda:
+            dist.all_reduce(gflat[lo:hi], group=self.pg)
+            return
+        cur = torch.cuda.current_stream(gflat.device)
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(device=gflat.device)
+        self._comm_stream.wait_stream(cur)
+        with torch.cuda.stream(self._comm_stream):
+            dist.all_reduce(gflat[lo:hi], group=self.pg)
+        self._comm_pending = True
+
+    def _join_comm(self, gflat):
+        if self._comm_pending:
+            torch.cuda.current_stream(gflat.device).wait_stream(self._comm_stream)
+            self._comm_pending = False
+
     def _device_update(self, lvals, outs, targets, gflat, acc, with_metrics):
-        """gradient all-reduce (NCCL over NVLink) + fused Adam + logging / metrics."""
-        if self.world > 1:
-            dist.all_reduce(gflat, group=self.pg)        # sum; the 1/world mean is folded into Adam
+        """(join the gradient all-reduces) + fused Adam + logging / metrics."""
+        self._join_comm(gflat)
         if isinstance(self.optimizer, FlatAdam):
             self.optimizer.launch(gflat)
         if acc is not None:
@@ -156,12 +190,12 @@ class VSRTrainStep:
         if not net._is_flat():
             net._flatten()
         inputs = [x.contiguous() for x in inputs]
-        targets = [y.contiguous() for y in targets]
         flat_adam = isinstance(self.optimizer, FlatAdam)
         if flat_adam:
             self.optimizer.prepare_step()
         if self.use_graph and net.flat.is_cuda:
             return self._graphed_step(inputs, targets, acc, with_metrics)
+        targets = list(_as_stacked(targets).unbind(0))      # one buffer: loss / metric kernels take all frames at once
         lvals, outs, gflat = self._device_step(inputs, targets, acc, with_metrics)
         if not flat_adam:
             if self.world > 1:
@@ -179,36 +213,40 @@ class VSRTrainStep:
             lvals, outs, _ = self._device_step(inputs, targets, acc, with_metrics)
             return lvals, outs
         g = self._graphs.get(key)
-        single = self.world == 1
         if g is None:
             dev = self.net.flat.device
-            st = {"in": [torch.empty_like(x) for x in inputs], "tg": [torch.empty_like(y) for y in targets],
+            T = len(inputs)
+            # static inputs / targets as ONE [T, N, ...] buffer each: the loss and metric kernels take all frames
+            # in one launch
+            tin = torch.empty(T, *inputs[0].shape, dtype=inputs[0].dtype, device=dev)
+            ttg = torch.empty(len(targets), *targets[0].shape, dtype=targets[0].dtype, device=dev)
+            st = {"in_all": tin, "tg_all": ttg, "in": list(tin.unbind(0)), "tg": list(ttg.unbind(0)),
                   "acc": torch.zeros(1 + len(self.losses) + len(self.metric_names), device=dev)}
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream(dev))
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.stream(side):
-                # one rank: the whole step is one graph.  Several ranks: the graph ends before the
-                # NCCL all-reduce, which (with Adam and the metrics, ~30 launches) is issued eagerly.
+                # the whole step is one graph, on one rank or many: forward, fused loss, backward, the NCCL
+                # all-reduces of the gradient ranges (forked onto a communication stream inside the capture),
+                # Adam, metrics
                 with torch.cuda.graph(graph, stream=side, capture_error_mode="thread_local"):
                     st["lvals"], st["outs"], st["gflat"] = self._device_fwd_bwd(st["in"], st["tg"])
-                    if single:
-                        st["acc"].zero_()
-                        self._device_update(st["lvals"], st["outs"], st["tg"], st["gflat"], st["acc"], with_metrics)
+                    st["acc"].zero_()
+                    self._device_update(st["lvals"], st["outs"], st["tg"], st["gflat"], st["acc"], with_metrics)
             torch.cuda.current_stream(dev).wait_stream(side)
             st["graph"] = graph
             self._graphs[key] = g = st
-        for d, s_ in zip(g["in"], inputs):
-            d.copy_(s_, non_blocking=True)
-        for d, s_ in zip(g["tg"], targets):
-            d.copy_(s_, non_blocking=True)
+        for dst_all, dst, src in ((g["in_all"], g["in"], inputs), (g["tg_all"], g["tg"], targets)):
+            v = _stacked_view(src)
+            if v is not None:
+                dst_all.copy_(v, non_blocking=True)           # one copy for all frames
+            else:
+                for d, s_ in zip(dst, src):
+                    d.copy_(s_, non_blocking=True)
         g["graph"].replay()
         self.net.flat_grad = g["gflat"]
-        if single:
-            if acc is not None:
-                acc += g["acc"]
-        else:
-            self._device_update(g["lvals"], g["outs"], g["tg"], g["gflat"], acc, with_metrics)
+        if acc is not None:
+            acc += g["acc"]
         return g["lvals"], g["outs"]
 
     @torch.no_grad()
@@ -219,7 +257,7 @@ class VSRTrainStep:
         eng = self._engine()
         eng.pack(net.flat, need_bwd=False)
         outs, _ = eng.forward([x.contiguous() for x in inputs], save=False)
-        targets = [y.contiguous() for y in targets]
+        targets = list(_as_stacked(targets).unbind(0))
         lvals, _ = self._loss(outs, targets, False)
         if acc is not None:
             self._log(acc, lvals)
@@ -239,39 +277,43 @@ class VSRTrainStep:
             net._flatten()
         ops = self._ops()
         outs = self._infer(inputs)
-        targets = [y.contiguous() for y in targets]
+        targets = list(_as_stacked(targets).unbind(0))
         T, L, n, c = len(outs), len(self.losses), outs[0].shape[0], outs[0].shape[1]
-        partials = torch.zeros(L * T, ops.partials_len, device=outs[0].device)
-        for li, (kind, param) in enumerate(self.losses):
-            for t in range(T):
-                ops.loss_fwd_bwd(outs[t], targets[t], kind, param, 0.0, partials[li * T + t], None)
+        partials, _ = self._loss_partials(outs, targets, False)                 # one launch per loss, all frames
         losses = (partials.sum(dim=1) / outs[0].numel()).view(L, T).t().contiguous()
-        per = outs[0].numel() // n
-        ws = self._buf("mws", (ops.metric_workspace(n * c, per) // 4 + 4,))
+        cardiac = [i for i, name in enumerate(self.metric_names) if name.startswith("Cardiac")]
+        plain = [i for i in range(len(self.metric_names)) if i not in cardiac]
         vals = torch.zeros(len(self.metric_names), T, n * c, device=outs[0].device)
-        for i, (name, fn) in enumerate(zip(self.metric_names, self.metric_fns)):
-            if name.startswith("Cardiac"):
-                if patients is None or len(patients) != n:
-                    raise ValueError(f"{name} needs the patient name of every sample of the batch")
+        if plain:
+            names, fns = self.metric_names, self.metric_fns
+            self.metric_names, self.metric_fns = [names[i] for i in plain], [fns[i] for i in plain]
+            try:
+                vals[plain] = self._metric_values(outs, targets)                # one launch pair per metric
+            finally:
+                self.metric_names, self.metric_fns = names, fns
+        if cardiac:
+            if patients is None or len(patients) != n:
+                raise ValueError(f"{self.metric_names[cardiac[0]]} needs the patient name of every sample of the batch")
+            o_all, y_all = _as_stacked(outs), _as_stacked(targets)              # [T, N, C, H, W]
+            per = outs[0].numel() // n
+            ws = self._buf("mws", (ops.metric_workspace(T * n * c, per) // 4 + 4,))
+            for i in cardiac:
+                fn = self.metric_fns[i]
                 m = fn.metric
                 for s_, who in enumerate(patients):
+                    # one crop (all frames of the sample) and one launch pair per sample: boxes differ per patient
                     h0, hn, w0, wn = fn.coordinates[who]
-                    for t in range(T):
-                        o = outs[t][s_:s_ + 1, :, h0:hn, w0:wn].contiguous()
-                        y = targets[t][s_:s_ + 1, :, h0:hn, w0:wn].contiguous()
-                        if name == "CardiacPSNR":
-                            ops.psnr(o, y, self.mean, self.std, float(m.max_value), vals[i, t, s_:s_ + 1], ws)
-                        else:
-                            ops.ssim(o.view(c, *o.shape[2:]), y.view(c, *y.shape[2:]), m.window, self.mean, self.std,
-                                     m.c1, m.c2, vals[i, t, s_ * c:(s_ + 1) * c], ws)
-                continue
-            for t in range(T):
-                o, y = outs[t], targets[t]
-                if name == "PSNR":
-                    ops.psnr(o, y, self.mean, self.std, float(fn.max_value), vals[i, t, :n], ws)
-                else:
-                    ops.ssim(o.view(n * c, *o.shape[2:]), y.view(n * c, *y.shape[2:]), fn.window, self.mean,
-                             self.std, fn.c1, fn.c2, vals[i, t], ws)
+                    o = o_all[:, s_, :, h0:hn, w0:wn].contiguous()              # [T, C, bh, bw]
+                    y = y_all[:, s_, :, h0:hn, w0:wn].contiguous()
+                    if self.metric_names[i] == "CardiacPSNR":
+                        tmp = self._buf("cpsnr", (T,))
+                        ops.psnr(o.view(T, -1), y.view(T, -1), self.mean, self.std, float(m.max_value), tmp, ws)
+                        vals[i, :, s_].copy_(tmp)
+                    else:
+                        tmp = self._buf("cssim", (T * c,))
+                        ops.ssim(o.view(T * c, *o.shape[2:]), y.view(T * c, *y.shape[2:]), m.window, self.mean, self.std,
+                                 m.c1, m.c2, tmp, ws)
+                        vals[i, :, s_ * c:(s_ + 1) * c].copy_(tmp.view(T, c))
         metrics = torch.stack([vals[i, :, :n] if name.endswith("PSNR") else vals[i].view(T, n, c).mean(dim=2)
                                for i, name in enumerate(self.metric_names)]) if self.metric_names else vals
         return outs, losses, metrics
@@ -328,6 +370,8 @@ class MISRTrainStep(VSRTrainStep):
         y, saved = net._forward(inputs, True)
         lvals, grads = self._loss([y], targets, True)
         gflat = net._backward(saved, grads[0])
+        if self.world > 1:
+            self._reduce_bucket(gflat, 0, gflat.numel())
         net.flat_grad = gflat
         return lvals, [y], gflat
 
@@ -352,21 +396,45 @@ class MISRTrainStep(VSRTrainStep):
 
 class VSRTrainer:
     """Drop-in for AcdcVSRTrainer / Dsb15VSRTrainer (same constructor keywords; `dataset` selects
-    the denormalisation constants, default 'acdc').  Under torchrun every rank runs this class on
-    its own shard of the batches; rank 0 logs and checkpoints."""
+    the denormalisation constants, default 'acdc').  Under torchrun (an initialised process group) every rank runs
+    this class on its own shard of the samples: the loaders are re-built around a rank-aware sampler that is
+    deterministic under the reference's per-epoch reseed (data.ShardedSampler, base_trainer.py:54), the step is the
+    CUDA-graphed fused step with the gradient all-reduce inside it (`use_graph`, `process_group`), every rank takes
+    the same early-stopping decision, and rank 0 alone logs and checkpoints."""
+
+    _step_cls = None        # set below (VSRTrainStep; MISRTrainer: MISRTrainStep)
 
     def __init__(self, device, train_dataloader, valid_dataloader, net, loss_fns, loss_weights, metric_fns,
-                 optimizer, lr_scheduler, logger, monitor, num_epochs, dataset="acdc"):
+                 optimizer, lr_scheduler, logger, monitor, num_epochs, dataset="acdc", use_graph=True,
+                 process_group=None):
+        from .data import shard_loader
         self.device = torch.device(device)
-        self.train_dataloader, self.valid_dataloader = train_dataloader, valid_dataloader
+        self.rank = dist.get_rank(process_group) if dist.is_available() and dist.is_initialized() else 0
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self.pg = process_group
+        self.train_dataloader, self._train_sampler = shard_loader(train_dataloader, self.rank, self.world)
+        self.valid_dataloader, self._valid_sampler = shard_loader(valid_dataloader, self.rank, self.world)
         self.net = net.to(self.device)
         self.loss_fns, self.metric_fns = list(loss_fns), [m.to(self.device) for m in metric_fns]
         self.loss_weights = list(loss_weights)
         self.optimizer, self.lr_scheduler = optimizer, lr_scheduler
         self.logger, self.monitor, self.num_epochs = logger, monitor, num_epochs
         self.epoch, self.np_random_seeds = 1, None
-        self.rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
-        self.step = VSRTrainStep(self.net, self.loss_fns, self.loss_weights, self.metric_fns, optimizer, dataset)
+        self.step = self._make_step(dataset, use_graph and self.device.type == "cuda")
+
+    def _make_step(self, dataset, use_graph):
+        return VSRTrainStep(self.net, self.loss_fns, self.loss_weights, self.metric_fns, self.optimizer, dataset,
+                            process_group=self.pg, use_graph=use_graph)
+
+    def _check_batch_counts(self, loader):
+        """every rank must run the same number of steps (each step holds a collective)"""
+        if self.world > 1 and hasattr(loader, "__len__"):
+            n = torch.tensor([len(loader), -len(loader)], dtype=torch.int64, device=self.device)
+            dist.all_reduce(n, op=dist.ReduceOp.MAX, group=self.pg)
+            if int(n[0]) != -int(n[1]):
+                raise RuntimeError(f"rank {self.rank}: {len(loader)} batches per epoch, but the ranks disagree "
+                                   f"(max {int(n[0])}, min {-int(n[1])}): shard the loader with equal lengths "
+                                   "(vsr_b200.data.ShardedSampler)")
 
     def _keys(self):
         return ["Loss"] + [f.__class__.__name__ for f in self.loss_fns] + [m.__class__.__name__ for m in self.metric_fns]
@@ -376,10 +444,11 @@ class VSRTrainer:
         training = mode == "training"
         self.net.train(training)
         loader = self.train_dataloader if training else self.valid_dataloader
+        self._check_batch_counts(loader)
         keys = self._keys()
         acc = torch.zeros(len(keys), device=self.device)
         count, batch, outputs = 0, None, None
-        for batch in DeviceStager(loader, self.device):
+        for batch in (DeviceStager(loader, self.device) if self.device.type == "cuda" else loader):
             inputs, targets = batch["lr_imgs"], batch["hr_imgs"]
             bs, T = inputs[0].shape[0], len(inputs)
             step_acc = torch.zeros_like(acc)
@@ -391,17 +460,30 @@ class VSRTrainer:
             count += bs * T
         if self.step.world > 1:
             cnt = torch.tensor([float(count)], device=self.device)
-            dist.all_reduce(acc)
-            dist.all_reduce(cnt)
+            dist.all_reduce(acc, group=self.pg)
+            dist.all_reduce(cnt, group=self.pg)
             count = cnt.item()
         vals = (acc / max(count, 1)).tolist()          # the one host sync of the epoch
         return dict(zip(keys, vals)), batch, outputs
 
+    def _sync_seeds(self):
+        """one seed list for all ranks (rank 0's): the per-epoch permutation must be the same everywhere"""
+        if self.world > 1:
+            t = torch.tensor(self.np_random_seeds, dtype=torch.int64, device=self.device)
+            dist.broadcast(t, src=dist.get_global_rank(self.pg, 0) if self.pg is not None else 0, group=self.pg)
+            self.np_random_seeds = t.tolist()
+
     def train(self):
         if self.np_random_seeds is None:
             self.np_random_seeds = random.sample(range(10000000), k=self.num_epochs)
+        self._sync_seeds()
         while self.epoch <= self.num_epochs:
-            np.random.seed(self.np_random_seeds[self.epoch - 1])
+            seed = self.np_random_seeds[self.epoch - 1]
+            # base_trainer.py:54; ranks > 0 offset the numpy stream so that their host-side augmentation draws differ
+            np.random.seed((seed + self.rank) % (2 ** 32))
+            for smp in (self._train_sampler, self._valid_sampler):
+                if smp is not None:
+                    smp.set_epoch_seed(seed)
             logging.info(f"Epoch {self.epoch}.")
             train_log, train_batch, train_outputs = self._run_epoch("training")
             logging.info(f"Train log: {train_log}.")
@@ -412,19 +494,21 @@ class VSRTrainer:
                     self.lr_scheduler.step(valid_log["Loss"])
                 else:
                     self.lr_scheduler.step()
-            if self.rank == 0:
-                if self.logger is not None:
-                    self.logger.write(self.epoch, train_log, train_batch, train_outputs, valid_log, valid_batch,
-                                      valid_outputs)
-                if self.monitor is not None:
-                    saved_path = self.monitor.is_saved(self.epoch)
-                    if saved_path:
-                        self.save(saved_path)
-                    saved_path = self.monitor.is_best(valid_log)
-                    if saved_path:
-                        self.save(saved_path)
-            if self.monitor is not None and self.monitor.is_early_stopped():
-                break
+            if self.rank == 0 and self.logger is not None:
+                self.logger.write(self.epoch, train_log, train_batch, train_outputs, valid_log, valid_batch,
+                                  valid_outputs)
+            if self.monitor is not None:
+                # Monitor.is_best updates the early-stopping counter (monitor.py:38-63): EVERY rank calls it with the
+                # same all-reduced valid_log, so every rank leaves the loop at the same epoch (a rank that kept going
+                # would block in the next all-reduce); only rank 0 writes the checkpoints
+                saved_path = self.monitor.is_saved(self.epoch)
+                if saved_path and self.rank == 0:
+                    self.save(saved_path)
+                saved_path = self.monitor.is_best(valid_log)
+                if saved_path and self.rank == 0:
+                    self.save(saved_path)
+                if self.monitor.is_early_stopped():
+                    break
             self.epoch += 1
 
     def save(self, path):
@@ -455,17 +539,21 @@ class MISRTrainer(VSRTrainer):
     size.  The step is MISRTrainStep (DUFNet, synchronised BatchNorm across ranks)."""
 
     def __init__(self, device, train_dataloader, valid_dataloader, net, loss_fns, loss_weights, metric_fns,
-                 optimizer, lr_scheduler, logger, monitor, num_epochs, dataset="acdc", use_graph=False):
+                 optimizer, lr_scheduler, logger, monitor, num_epochs, dataset="acdc", use_graph=True,
+                 process_group=None):
         super().__init__(device, train_dataloader, valid_dataloader, net, loss_fns, loss_weights, metric_fns,
-                         optimizer, lr_scheduler, logger, monitor, num_epochs, dataset)
-        self.step = MISRTrainStep(self.net, self.loss_fns, self.loss_weights, self.metric_fns, optimizer, dataset,
-                                  use_graph=use_graph)
+                         optimizer, lr_scheduler, logger, monitor, num_epochs, dataset, use_graph, process_group)
+
+    def _make_step(self, dataset, use_graph):
+        return MISRTrainStep(self.net, self.loss_fns, self.loss_weights, self.metric_fns, self.optimizer, dataset,
+                             process_group=self.pg, use_graph=use_graph)
 
     def _run_epoch(self, mode):
         from .data import DeviceStager
         training = mode == "training"
         self.net.train(training)
         loader = self.train_dataloader if training else self.valid_dataloader
+        self._check_batch_counts(loader)
         keys = self._keys()
         acc = torch.zeros(len(keys), device=self.device)
         count, batch, outputs = 0, None, None
@@ -483,8 +571,8 @@ class MISRTrainer(VSRTrainer):
             count += bs
         if self.step.world > 1:
             cnt = torch.tensor([float(count)], device=self.device)
-            dist.all_reduce(acc)
-            dist.all_reduce(cnt)
+            dist.all_reduce(acc, group=self.pg)
+            dist.all_reduce(cnt, group=self.pg)
             count = cnt.item()
         vals = (acc / max(count, 1)).tolist()          # the one host sync of the epoch
         return dict(zip(keys, vals)), batch, outputs
