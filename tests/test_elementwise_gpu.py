@@ -49,19 +49,29 @@ def test_conv3x3_first_and_bwd(dtype, cin):
     assert (rs[0][1] - rs[1][1]).abs().max() <= 1e-4 * rs[1][1].abs().max()
 
 
+@pytest.mark.parametrize("r,c,h,w", [(4, 64, 11, 9), (3, 64, 13, 12), (2, 128, 20, 17), (8, 64, 5, 9)])
+def test_conv3x3_last_tensor_core_path_several_tiles(r, c, h, w):
+    """bf16 maps through lastconv_mma.cu with more than one 32x32 output tile per image and partial tiles on both axes"""
+    test_conv3x3_last_and_bwd(torch.bfloat16, r, c, n=3, h=h, w=w)
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("r,c", [(2, 64), (4, 64), (3, 8), (8, 16), (4, 128)])
-def test_conv3x3_last_and_bwd(dtype, r, c):
+def test_conv3x3_last_and_bwd(dtype, r, c, n=2, h=5, w=6):
     ops, emu, g = _ops(), EmuOps(), _g(2)
-    n, h, w = 2, 5, 6
     ph = phase_table(r)
     x = torch.randn(n, h, w, r * r * c, device="cuda", generator=g).to(dtype)
     wt = torch.randn(1, c, 3, 3, device="cuda", generator=g) * 0.1
     b = torch.randn(1, device="cuda", generator=g)
+    # bf16 maps with 64 / 128 channels take the tensor-core kernels (lastconv_mma.cu): like every tensor-core layer their
+    # operands are bf16 (weights and dy are rounded inside the kernel, accumulation is fp32) - the emulation gets the same
+    # rounded operands, so that what is compared is the arithmetic, at the fp32 tolerances
+    mma = dtype == torch.bfloat16 and c in (64, 128)
+    rnd = (lambda t: t.bfloat16().float()) if mma else (lambda t: t)
     ys = []
     for o in (ops, emu):
         y = torch.zeros(n, 1, h * r, w * r, device="cuda")
-        o.conv3x3_last(x, r, c, ph, wt, b, y)
+        o.conv3x3_last(x, r, c, ph, wt if o is ops else rnd(wt), b, y)
         ys.append(y)
     assert (ys[0] - ys[1]).abs().max() <= 1e-4 * ys[1].abs().max()
     dy = torch.randn(n, 1, h * r, w * r, device="cuda", generator=g)
@@ -70,7 +80,12 @@ def test_conv3x3_last_and_bwd(dtype, r, c):
         dx = torch.zeros_like(x)
         dw, db = torch.zeros_like(wt), torch.zeros_like(b)
         ws = torch.empty(max(16, o.conv3x3_last_bwd_workspace(x, r, c, 1)) // 4 + 4, device="cuda")
-        o.conv3x3_last_bwd(x, r, c, ph, wt, dy, dx, dw, db, False, ws)
+        if o is ops:
+            o.conv3x3_last_bwd(x, r, c, ph, wt, dy, dx, dw, db, False, ws)
+        else:
+            o.conv3x3_last_bwd(x, r, c, ph, rnd(wt), rnd(dy), dx, dw, db, False, ws)
+            if mma:
+                db.copy_(dy.sum().view(1))          # the bias gradient sums the fp32 dy
         rs.append((dx.float(), dw, db))
     tol = 1e-2 if dtype == torch.bfloat16 else 1e-5
     assert (rs[0][0] - rs[1][0]).abs().max() <= tol * rs[1][0].abs().max()

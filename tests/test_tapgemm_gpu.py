@@ -292,3 +292,28 @@ def test_tc_bf16_shared_loads_several_groups_many_tiles(n_groups, nt, monkeypatc
     _run_case(tab, n=20, h=32, w=32, src_c=64, out_c=n_groups * nt, dtype=torch.bfloat16, epi=L.EPI_PRELU_BWD, seed=28)
     _setenv(monkeypatch, "VSR_TC_STAGES", "1")
     _run_case(tab, n=6, h=32, w=32, src_c=64, out_c=n_groups * nt, dtype=torch.bfloat16, epi=0, seed=29)
+
+
+@pytest.mark.parametrize("pair", ["0", "1"])
+def test_tc_bf16_cta_pairs_and_single_ctas_agree_with_the_emulation(pair, monkeypatch):
+    """every mode of the kernel with CTA pairs forced on (tcgen05 cta_group::2: M = 256 over two CTAs, half of every
+    weight slab per CTA) and forced off: odd pixel-tile counts (the last pair's second CTA works on an out-of-range
+    tile), resident weights with several groups, shared loads with two stacked sub-tiles, streamed slabs, every
+    epilogue operand path"""
+    _setenv(monkeypatch, "VSR_TC_PAIR", pair)
+    # 3 pixel tiles (odd), one tap, plain epilogue
+    _run_case(multi_src_table(64, 64, 1), n=3, h=4, w=32, src_c=64, out_c=64, dtype=torch.bfloat16, epi=0, seed=31)
+    # 3x3, partial tiles on every side, odd tile count, bias + PReLU
+    _run_case(conv3x3_table(64, 128), n=3, h=19, w=21, src_c=64, out_c=128, dtype=torch.bfloat16, epi=L.EPI_BIAS | L.EPI_PRELU, seed=32)
+    # deconv shape: 4 groups x 4 taps, nt 256, resident weights, contiguous tile ranges
+    _run_case(grouped_table(64, 256, 4, 1), n=21, h=32, w=32, src_c=64, out_c=1024, dtype=torch.bfloat16,
+              epi=L.EPI_BIAS | L.EPI_PRELU, seed=33)
+    # strided-convolution shape: 64 taps, nt 64, shared loads, PReLU' with residual
+    _run_case(strided_conv_table(), n=5, h=32, w=32, src_c=1024, out_c=64, dtype=torch.bfloat16,
+              epi=L.EPI_RES_PRE | L.EPI_PRELU_BWD, seed=34)
+    # second output + second residual, several sources
+    _run_case(multi_src_table(64, 64, 4), n=7, h=8, w=32, src_c=64, out_c=64, dtype=torch.bfloat16,
+              epi=L.EPI_BIAS | L.EPI_PRELU | L.EPI_OUT2, seed=35, n_srcs=4)
+    # more tiles than CTA pairs, two TMEM buffers in flight, PReLU' on a wide output
+    _run_case(grouped_table(64, 256, 4, 1), n=40, h=32, w=32, src_c=64, out_c=1024, dtype=torch.bfloat16,
+              epi=L.EPI_PRELU_BWD, seed=36)

@@ -61,6 +61,12 @@ __global__ void add_f32_kernel(const float4* __restrict__ a, const float4* __res
     o[i] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
   }
 }
+// any length / alignment (odd frame sizes of x3 nets): one element per thread and trip
+template <typename T>
+__global__ void add_scalar_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ o, long n) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    Elem<T>::st(o + i, Elem<T>::ld(a + i) + Elem<T>::ld(b + i));
+}
 __global__ void add_bf16_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b,
                                 uint4* __restrict__ o, long n8) {
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n8; i += (long)gridDim.x * blockDim.x) {
@@ -284,12 +290,18 @@ extern "C" int vsr_add(const void* a, const void* b, void* out, int32_t dtype, i
   VSR_CHECK_ARG(a && b && out && numel >= 0, "vsr_add: bad arguments");
   if (numel == 0) return VSR_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool al16 = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0;
   if (dtype == VSR_F32) {
-    VSR_CHECK_ARG(numel % 4 == 0, "vsr_add: fp32 numel must be a multiple of 4");
-    add_f32_kernel<<<grid_for(numel / 4, 256), 256, 0, s>>>((const float4*)a, (const float4*)b, (float4*)out, numel / 4);
+    if (al16 && numel % 4 == 0)
+      add_f32_kernel<<<grid_for(numel / 4, 256), 256, 0, s>>>((const float4*)a, (const float4*)b, (float4*)out, numel / 4);
+    else
+      add_scalar_kernel<float><<<grid_for(numel, 256), 256, 0, s>>>((const float*)a, (const float*)b, (float*)out, numel);
   } else if (dtype == VSR_BF16) {
-    VSR_CHECK_ARG(numel % 8 == 0, "vsr_add: bf16 numel must be a multiple of 8");
-    add_bf16_kernel<<<grid_for(numel / 8, 256), 256, 0, s>>>((const uint4*)a, (const uint4*)b, (uint4*)out, numel / 8);
+    using B = __nv_bfloat16;
+    if (al16 && numel % 8 == 0)
+      add_bf16_kernel<<<grid_for(numel / 8, 256), 256, 0, s>>>((const uint4*)a, (const uint4*)b, (uint4*)out, numel / 8);
+    else
+      add_scalar_kernel<B><<<grid_for(numel, 256), 256, 0, s>>>((const B*)a, (const B*)b, (B*)out, numel);
   } else {
     VSR_CHECK_ARG(false, "vsr_add: bad dtype %d", dtype);
   }

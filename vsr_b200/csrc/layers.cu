@@ -1154,6 +1154,15 @@ extern "C" int vsr_conv3x3_first_bwd(const float* x, int32_t n, int32_t cin, int
   return VSR_OK;
 }
 
+namespace vsr {      // lastconv_mma.cu: bf16, cout == 1 on the tensor cores (mma.sync)
+bool lastconv_mma_supported(int dtype, int r, int c, int cout);
+int lastconv_mma_blocks();
+int lastconv_mma_fwd(const void* x, int n, int h, int w, int r, int c, const int32_t* phase_yx, const float* wt,
+                     const float* bias, float* y, cudaStream_t s);
+int lastconv_mma_bwd(const void* x, int n, int h, int w, int r, int c, const int32_t* phase_yx, const float* wt,
+                     const float* dy, void* dx, float* ws, cudaStream_t s);
+}  // namespace vsr
+
 extern "C" int vsr_conv3x3_last(const void* x, int32_t dtype, int32_t n, int32_t h, int32_t w_, int32_t r,
                                 int32_t c, const int32_t* phase_yx, const float* w, const float* bias,
                                 float* y, int32_t cout, void* stream) {
@@ -1161,6 +1170,7 @@ extern "C" int vsr_conv3x3_last(const void* x, int32_t dtype, int32_t n, int32_t
   VSR_CHECK_SUPPORTED(r >= 1 && r <= 8, "vsr_conv3x3_last: r must be in [1,8]");
   VSR_CHECK_SUPPORTED(cout >= 1 && cout <= kMaxCoutLast, "vsr_conv3x3_last: cout must be in [1,%d]", kMaxCoutLast);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (lastconv_mma_supported(dtype, r, c, cout)) return lastconv_mma_fwd(x, n, h, w_, r, c, phase_yx, w, bias, y, s);
   if (last2_supported(r, c, cout) && (dtype == VSR_F32 || dtype == VSR_BF16)) {
     LastGeom2 g2;
     VSR_CHECK_ARG(fill_geom2(&g2, n, h, w_, r, c, phase_yx) == 0, "vsr_conv3x3_last: bad phase table");
@@ -1209,6 +1219,18 @@ extern "C" int vsr_conv3x3_last_bwd(const void* x, int32_t dtype, int32_t n, int
                                     void* workspace, size_t workspace_bytes, void* stream) {
   VSR_CHECK_ARG(x && w && dy && dx && dw && db && phase_yx, "vsr_conv3x3_last_bwd: bad arguments");
   VSR_CHECK_SUPPORTED(r >= 1 && r <= 8, "vsr_conv3x3_last_bwd: r must be in [1,8]");
+  if (lastconv_mma_supported(dtype, r, c, cout)) {
+    VSR_CHECK_ARG(workspace && workspace_bytes >= vsr_conv3x3_last_bwd_workspace(n, h, w_, r, c, cout),
+                  "vsr_conv3x3_last_bwd: workspace too small");
+    cudaStream_t sm = static_cast<cudaStream_t>(stream);
+    float* wsm = static_cast<float*>(workspace);
+    int rc = lastconv_mma_bwd(x, n, h, w_, r, c, phase_yx, w, dy, dx, wsm, sm);
+    if (rc != VSR_OK) return rc;
+    const int pszm = 9 * c + 1;
+    conv_last_bwd_final_kernel<<<(pszm + 127) / 128, 128, 0, sm>>>(wsm, lastconv_mma_blocks(), 1, c, dw, db, accumulate);
+    VSR_CHECK_LAUNCH("vsr_conv3x3_last_bwd_final(mma)");
+    return VSR_OK;
+  }
   if (last2_supported(r, c, cout) && (dtype == VSR_F32 || dtype == VSR_BF16)) {
     VSR_CHECK_ARG(workspace && workspace_bytes >= vsr_conv3x3_last_bwd_workspace(n, h, w_, r, c, cout),
                   "vsr_conv3x3_last_bwd: workspace too small");

@@ -46,7 +46,7 @@ constexpr int kMaxStages = 12;
 constexpr int kSmemBudget = 227 * 1024;
 constexpr int kEpiWarps = 8;                  // two per TMEM lane quarter: even / odd 64-channel chunks
 constexpr int kTileBytes = 4096;              // epilogue tile: 32 pixels x 64 channels bf16
-constexpr int kMaxSmemGroups = 36;            // group table rows cached in smem (16 B each, ctrl[448..1024))
+constexpr int kMaxSmemGroups = 20;            // group table rows cached in smem (16 B each, ctrl[448..768))
 constexpr int kMaxSmemTaps = 256;             // column entries cached in smem (8 B each)
 constexpr int kMaxParamCols = 64;             // host-built columns travel in the kernel arguments
 constexpr int kMaxTallGroups = 8;
@@ -94,6 +94,9 @@ struct Tc2Args {
   int a_bytes;             // bytes of one A box
   int row_bytes;           // bw * 128: bytes of one pixel row of the A box
   int stage_bytes;         // A box + the weight slabs of one column (none in resident mode)
+  int epi_obuf;            // output staging tiles per epilogue warp (1 or 2: the store of a chunk overlaps the next chunk)
+  int epi_ibuf;            // epilogue operand sets per warp (1 or 2: operands are fetched two chunks ahead)
+  int pair;                // 1: CTA pairs (clusters of 2, tcgen05 cta_group::2): m_tiles / num_tiles count PAIRS of pixel tiles
 };
 
 static_assert(sizeof(Tc2Args) <= 4096, "kernel arguments are limited to 4 KB");
@@ -130,7 +133,9 @@ __device__ __forceinline__ void fast_divmod(int n, int d, uint32_t magic, int* q
   *q = qq;
   *r = rr;
 }
-__device__ __forceinline__ TileCoord decode_tile(const Tc2Args& a, int tile) {
+// pair mode: `tile` counts pairs of pixel tiles, CTA `rank` of the pair takes pixel tile 2 * pair + rank (an odd tile
+// count leaves the last pair's second CTA with n == N: its loads are zero-filled and its stores clipped by the TMA unit)
+__device__ __forceinline__ TileCoord decode_tile(const Tc2Args& a, int tile, int rank) {
   TileCoord t;
   int mt, tx, ty;
   if (a.contig) {
@@ -138,6 +143,7 @@ __device__ __forceinline__ TileCoord decode_tile(const Tc2Args& a, int tile) {
   } else {
     fast_divmod(tile, a.n_groups, a.mg_groups, &mt, &t.g);
   }
+  if (a.pair) mt = 2 * mt + rank;
   fast_divmod(mt, a.tiles_x, a.mg_tx, &mt, &tx);
   fast_divmod(mt, a.tiles_y, a.mg_ty, &t.n, &ty);
   t.x0 = tx * a.bw;
@@ -164,11 +170,18 @@ __device__ __forceinline__ void tma_store_4d(const void* map, uint32_t src, int 
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // FIXED_EPI >= 0: the epilogue flag set is a compile-time constant; FIXED_EPI < 0: read from the arguments.
-template <int FIXED_EPI>
+// PAIR: two CTAs of one TPC (a cluster of 2) work on two pixel tiles of the same group with ONE stream of M = 256
+// tcgen05.mma.cta_group::2 instructions issued by the leader CTA (rank 0): every CTA loads its own A box and only HALF of
+// every weight slab (rows [rank * nt/2, +nt/2)), so the weight traffic L2 -> SM, the resident-weight footprint and the
+// shared-memory reads per MMA of the B operand halve.  Both CTAs run every role on their own tile; the peer's MMA warp
+// relays "my stage is loaded" to the leader (remote mbarrier arrive), the leader's commits arrive in both CTAs
+// (multicast), and the peer's epilogue frees the accumulator on the leader's barrier.
+template <int FIXED_EPI, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_constant__ Tc2Args a) {
   const int epi = FIXED_EPI >= 0 ? FIXED_EPI : a.epi;
   const int dbg = kAttrib ? a.debug : 0;
@@ -185,7 +198,13 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
   const uint32_t tempty_bar = smem_base + 272;             // 2 x 8 B
   const uint32_t tmem_slot = smem_base + 288;              // u32
   const uint32_t bres_full = smem_base + 296, bres_empty = smem_base + 304;
-  const uint32_t in_bar0 = smem_base + 312;                // kEpiWarps x 8 B (..376)
+  const uint32_t in_bar0 = smem_base + 768;                // kEpiWarps x 2 x 8 B (..896): operand sets of the epilogue warps
+  const uint32_t peer_bres_full = smem_base + 416;         // pair mode, leader: the peer's resident slabs have landed
+  const uint32_t peer_full_bar = smem_base + 896;          // pair mode, leader: kMaxStages x 8 B, the peer's stage is loaded
+  const int cta_rank = PAIR ? (int)ptx::cluster_ctarank() : 0;
+  const bool leader_cta = cta_rank == 0;
+  const int walker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;          // tile walker: a CTA, or a CTA pair
+  const int n_walkers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + 288);
   float* red = reinterpret_cast<float*>(smem_gen + 384);   // kEpiWarps floats
   int4* grp_s = reinterpret_cast<int4*>(smem_gen + 448);        // group table (<= 36 rows)
@@ -213,15 +232,17 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
         col_s[i] = make_uint2(pack_tap(__ldg(a.tap_tab + i)), (uint32_t)i | (1u << 24));
   }
   const bool bias_in_smem = (epi & VSR_EPI_BIAS) && a.Cout <= kBiasFloats;
-  const uint32_t b_bytes = static_cast<uint32_t>(a.nt) * 128u;
+  const uint32_t b_full = static_cast<uint32_t>(a.nt) * 128u;      // one weight slab in global memory
+  const uint32_t b_bytes = PAIR ? b_full / 2 : b_full;             // the rows of it this CTA holds
+  const uint8_t* const wbase = a.w + (PAIR ? cta_rank * b_bytes : 0u);
   const uint32_t a_bytes = static_cast<uint32_t>(a.a_bytes);
   const uint32_t stage_bytes = static_cast<uint32_t>(a.stage_bytes);
   // tile walk of this CTA
   // (one group: resident weights never change, so the CTAs keep the interleaved walk whose concurrent
   //  tiles are neighbours in memory - measured 5-10 % faster than contiguous ranges on the 1x1 convolutions)
-  const int tile_begin = a.contig ? (int)((long)a.num_tiles * blockIdx.x / gridDim.x) : (int)blockIdx.x;
-  const int tile_end = a.contig ? (int)((long)a.num_tiles * (blockIdx.x + 1) / gridDim.x) : a.num_tiles;
-  const int tile_step = a.contig ? 1 : (int)gridDim.x;
+  const int tile_begin = a.contig ? (int)((long)a.num_tiles * walker / n_walkers) : walker;
+  const int tile_end = a.contig ? (int)((long)a.num_tiles * (walker + 1) / n_walkers) : a.num_tiles;
+  const int tile_step = a.contig ? 1 : n_walkers;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -234,16 +255,26 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
     }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(tfull_bar + 8 * b, 1);
-      ptx::mbar_init(tempty_bar + 8 * b, a.nt > 64 ? kEpiWarps : kEpiWarps / 2);
+      // (pair mode: the epilogue warps of BOTH CTAs arrive on the leader's barrier)
+      ptx::mbar_init(tempty_bar + 8 * b, (a.nt > 64 ? kEpiWarps : kEpiWarps / 2) * (PAIR ? 2 : 1));
     }
     ptx::mbar_init(bres_full, 1);
     ptx::mbar_init(bres_empty, 1);
-    for (int w = 0; w < kEpiWarps; ++w) ptx::mbar_init(in_bar0 + 8 * w, 1);
+    if (PAIR) {
+      for (int s = 0; s < a.stages; ++s) ptx::mbar_init(peer_full_bar + 8 * s, 1);
+      ptx::mbar_init(peer_bres_full, 1);
+    }
+    for (int w = 0; w < 2 * kEpiWarps; ++w) ptx::mbar_init(in_bar0 + 8 * w, 1);
     ptx::fence_mbar_init();
   }
   if (warp == kMmaWarp) {
-    ptx::tmem_alloc(tmem_slot, kTmemCols);
-    ptx::tmem_relinquish();
+    if (PAIR) {
+      ptx::tmem_alloc2(tmem_slot, kTmemCols);
+      ptx::tmem_relinquish2();
+    } else {
+      ptx::tmem_alloc(tmem_slot, kTmemCols);
+      ptx::tmem_relinquish();
+    }
   }
   // Everything above reads only launch-time constants (tables uploaded when the layer plan was built,
   // kernel arguments) and this CTA's own shared / tensor memory; tensors written by earlier kernels
@@ -252,7 +283,8 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
   if (bias_in_smem)
     for (int i = threadIdx.x; i < a.Cout; i += blockDim.x) bias_s[i] = __ldg(a.bias + i);
   ptx::tc_fence_before();
-  __syncthreads();
+  if (PAIR) ptx::cluster_sync();       // the peer's barriers are initialised before anything arrives on them
+  else __syncthreads();
   ptx::tc_fence_after();
   ptx::pdl_launch_dependents();
   const uint32_t tmem_base = *tmem_slot_gen;
@@ -275,7 +307,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
       int turn = 0;                               // position in the column sequence modulo n_prod
       long long p_wait = 0, p_n = 0, p_t0 = kAttrib ? clock64() : 0;
       for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
-        const TileCoord tc = decode_tile(a, tile);
+        const TileCoord tc = decode_tile(a, tile, cta_rank);
         int4 grp = grp_in_smem ? grp_s[tc.g] : __ldg(a.group_tab + tc.g);
         grp.y = __shfl_sync(0xffffffffu, grp.y, 0);
         grp.z = __shfl_sync(0xffffffffu, grp.z, 0);
@@ -287,7 +319,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
           if (leader) {
             ptx::mbar_arrive_expect_tx(bres_full, static_cast<uint32_t>(ntap) * b_bytes);
             for (int t = 0; t < ntap; ++t)
-              ptx::bulk_load(res_base + t * b_bytes, a.w + static_cast<size_t>(tap0 + t) * b_bytes, b_bytes, bres_full);
+              ptx::bulk_load(res_base + t * b_bytes, wbase + static_cast<size_t>(tap0 + t) * b_full, b_bytes, bres_full);
           }
           cur_g = tc.g;
           ++gcount;
@@ -320,7 +352,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
             if (do_a) ptx::tma_load_4d(sa, map, fb, tap.w, tc.x0 + tap.z, tc.y0 + tap.y, tc.n);
             if (do_b)
               for (int j = 0; j < ndy; ++j)
-                ptx::bulk_load(sa + a_bytes + j * b_bytes, a.w + static_cast<size_t>(slab0 + j * sstride) * b_bytes, b_bytes, fb);
+                ptx::bulk_load(sa + a_bytes + j * b_bytes, wbase + static_cast<size_t>(slab0 + j * sstride) * b_full, b_bytes, fb);
           }
           if (++stage == a.stages) { stage = 0; phase ^= 1u; }
         }
@@ -328,11 +360,40 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
       if (prof && blockIdx.x == 0 && leader && warp == 0)
         printf("tc2-prof producer: total %lld cyc, %lld taps, wait(empty) %lld\n", clock64() - p_t0, p_n, p_wait);
     }
+  } else if (warp == kMmaWarp && PAIR && !leader_cta) {
+    // ===================== pair mode, peer CTA: relay "my stage is loaded" to the leader =====================
+    // Same walk as the leader's MMA issuer; instead of issuing, arrive on the leader's peer_full barrier of the stage
+    // (and on peer_bres_full when this CTA's resident slabs have landed).  The stage cannot be refilled before the
+    // leader's commit of its MMAs arrives on this CTA's empty barrier, so no arrival is ever ahead by a whole phase.
+    {
+      const bool leader = ptx::elect_one();
+      const uint32_t r_full = ptx::mapa(peer_full_bar, 0), r_bres = ptx::mapa(peer_bres_full, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int cur_g = -1;
+      uint32_t gcount = 0;
+      for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
+        const TileCoord tc = decode_tile(a, tile, cta_rank);
+        int4 grp = grp_in_smem ? grp_s[tc.g] : __ldg(a.group_tab + tc.g);
+        grp.z = __shfl_sync(0xffffffffu, grp.z, 0);
+        if (a.resident && tc.g != cur_g) {
+          ptx::mbar_wait(bres_full, gcount & 1u);
+          if (leader) ptx::mbar_arrive_remote(r_bres);
+          cur_g = tc.g;
+          ++gcount;
+        }
+        for (int t = 0; t < grp.z; ++t) {
+          ptx::mbar_wait(full_bar + 8 * stage, phase);
+          if (leader) ptx::mbar_arrive_remote(r_full + 8 * stage);
+          if (++stage == a.stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer (one elected lane, warp-uniform control flow) =====================
     {
       const bool leader = ptx::elect_one();
-      const uint32_t idesc = ptx::make_idesc_bf16(kBlockM, a.nt, 0, 0);
+      const uint32_t idesc = ptx::make_idesc_bf16(PAIR ? 2 * kBlockM : kBlockM, a.nt, 0, 0);
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -341,7 +402,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
       uint32_t gcount = 0;
       long long m_wfull = 0, m_wtmem = 0, m_issue = 0, m_n = 0, m_t0 = kAttrib ? clock64() : 0;
       for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++it) {
-        const TileCoord tc = decode_tile(a, tile);
+        const TileCoord tc = decode_tile(a, tile, cta_rank);
         int4 grp = grp_in_smem ? grp_s[tc.g] : __ldg(a.group_tab + tc.g);
         grp.y = __shfl_sync(0xffffffffu, grp.y, 0);
         grp.z = __shfl_sync(0xffffffffu, grp.z, 0);
@@ -349,6 +410,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
         const int tap0 = a.tall ? (grp.w & 0xffff) : grp.y;      // first weight slab of the group
         if (a.resident && tc.g != cur_g) {
           ptx::mbar_wait(bres_full, gcount & 1u);
+          if (PAIR) ptx::mbar_wait(peer_bres_full, gcount & 1u);
           cur_g = tc.g;
           ++gcount;
         }
@@ -366,6 +428,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
           const int slab0 = (int)(col.y & 0xfffu), sstride = (int)((col.y >> 12) & 0xfffu), ndy = (int)(col.y >> 24);
           if (prof) c0 = clock64();
           ptx::mbar_wait(full_bar + 8 * stage, phase);
+          if (PAIR) ptx::mbar_wait(peer_full_bar + 8 * stage, phase);
           ptx::tc_fence_after();
           if (prof) c1 = clock64();
           const uint32_t sa = stage_base + stage * stage_bytes;
@@ -381,20 +444,28 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
 #pragma unroll
                   for (int k = 0; k < kKc / 16; ++k) {
                     // advancing K by 16 bf16 = 32 bytes = 2 descriptor address units
-                    ptx::mma_bf16_ss(d_tmem + m * a.nt, adesc + 2 * k, bdesc + 2 * k, idesc, (t | j | k) != 0);
+                    if (PAIR) ptx::mma_bf16_ss2(d_tmem + m * a.nt, adesc + 2 * k, bdesc + 2 * k, idesc, (t | j | k) != 0);
+                    else ptx::mma_bf16_ss(d_tmem + m * a.nt, adesc + 2 * k, bdesc + 2 * k, idesc, (t | j | k) != 0);
                   }
                 }
               }
             }
-            ptx::mma_commit(empty_bar + 8 * stage);
+            if (PAIR) ptx::mma_commit2(empty_bar + 8 * stage);     // frees the stage in both CTAs
+            else ptx::mma_commit(empty_bar + 8 * stage);
           }
           if (prof) { m_wfull += c1 - c0; m_issue += clock64() - c1; ++m_n; }
           if (++stage == a.stages) { stage = 0; phase ^= 1u; }
         }
-        if (leader) ptx::mma_commit(tfull_bar + 8 * buf);
+        if (leader) {
+          if (PAIR) ptx::mma_commit2(tfull_bar + 8 * buf);
+          else ptx::mma_commit(tfull_bar + 8 * buf);
+        }
         if (a.resident) {
           const int next = tile + tile_step;
-          if ((next >= tile_end || decode_tile(a, next).g != cur_g) && leader) ptx::mma_commit(bres_empty);
+          if ((next >= tile_end || decode_tile(a, next, cta_rank).g != cur_g) && leader) {
+            if (PAIR) ptx::mma_commit2(bres_empty);
+            else ptx::mma_commit(bres_empty);
+          }
         }
       }
       if (prof && blockIdx.x == 0 && leader)
@@ -413,7 +484,6 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
     const int c_first = by_tile ? 0 : 64 * chalf;
     const int my_step = by_tile ? 2 * tile_step : tile_step;       // distance between this warp's tiles
     const int my_begin = by_tile ? tile_begin + chalf * tile_step : tile_begin;
-    const int slot = ew;
     // this warp's 32 pixels as a sub-box of the bw x bh tile (the epilogue maps have box ew x eh)
     const int sub_x = (quarter * 32) & (a.bw - 1);
     const int sub_y = (quarter * 32) >> a.bw_shift;
@@ -421,50 +491,55 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
     const bool has_in = (epi & kEpiIn) != 0 && !skip;
     const int n_in = ((epi & VSR_EPI_RES_PRE) ? 1 : 0) + ((epi & (VSR_EPI_PRELU_BWD | VSR_EPI_RELU_BWD)) ? 1 : 0) +
                      ((epi & VSR_EPI_OUT2) ? 1 : 0);
-    const uint32_t out_t = epi_base + slot * (1 + n_in) * kTileBytes;
-    uint32_t nxt = out_t + kTileBytes;
-    const uint32_t res_t = nxt;
-    if (epi & VSR_EPI_RES_PRE) nxt += kTileBytes;
-    const uint32_t aux_t = nxt;
-    if (epi & (VSR_EPI_PRELU_BWD | VSR_EPI_RELU_BWD)) nxt += kTileBytes;
-    const uint32_t res2_t = nxt;
-    const uint32_t in_bar = in_bar0 + 8 * ew;
-    uint32_t in_phase = 0;
+    // staging of this warp: [obuf output tiles][ibuf sets of n_in operand tiles].  With two output tiles the TMA store of
+    // a chunk reads its tile while the next chunk is computed; with two operand sets the residual / saved-activation
+    // tiles of chunk q + 2 are fetched while chunks q and q + 1 are processed (one set: chunk q + 1 while q is stored,
+    // which exposed most of the L2 latency in the chunk-parity mode - the PReLU' data gradients ran 15 us behind
+    // their forward twins).
+    const int obuf = a.epi_obuf, ibuf = a.epi_ibuf;
+    const uint32_t warp_t = epi_base + ew * (obuf + ibuf * n_in) * kTileBytes;
+    const uint32_t in_t0 = warp_t + obuf * kTileBytes;
+    const uint32_t aux_o = (epi & VSR_EPI_RES_PRE) ? kTileBytes : 0;
+    const uint32_t res2_o = aux_o + ((epi & (VSR_EPI_PRELU_BWD | VSR_EPI_RELU_BWD)) ? kTileBytes : 0);
+    const uint32_t in_bar = in_bar0 + 16 * ew;
     // (slope == 0 and slope < 0: see Prelu in common.cuh)
     const Prelu pr = make_prelu((epi & (VSR_EPI_PRELU | VSR_EPI_PRELU_BWD)) ? __ldg(a.slope) : 1.f);
     const bool slope01 = pr.fwd >= 0.f && pr.fwd <= 1.f;
     float slope_acc = 0.f;
     long long e_wait = 0, e_in = 0, e_ld = 0, e_math = 0, e_st = 0, e_iss = 0, e_t0 = kAttrib ? clock64() : 0;
 
-    // one elected lane fetches the epilogue operands of a 64-channel chunk through TMA
-    auto issue_in = [&](int n, int y0, int x0, int c0) {
-      ptx::mbar_arrive_expect_tx(in_bar, static_cast<uint32_t>(n_in) * kTileBytes);
-      if (epi & VSR_EPI_RES_PRE) ptx::tma_load_4d(res_t, &a.res_map, in_bar, c0, x0 + sub_x, y0 + sub_y, n);
-      if (epi & (VSR_EPI_PRELU_BWD | VSR_EPI_RELU_BWD))
-        ptx::tma_load_4d(aux_t, &a.aux_map, in_bar, c0, x0 + sub_x, y0 + sub_y, n);
-      if (epi & VSR_EPI_OUT2) ptx::tma_load_4d(res2_t, &a.res2_map, in_bar, c0, x0 + sub_x, y0 + sub_y, n);
+    // the chunks of this warp in processing order: (tile, sub-tile m, first channel c)
+    struct Chunk { int tile, m, c; };
+    auto next_chunk = [&](Chunk& k) {
+      if (k.c + 128 < a.nt) { k.c += 128; return true; }
+      k.c = c_first;
+      if (k.m + 1 < a.mb) { ++k.m; return true; }
+      k.m = 0;
+      k.tile += my_step;
+      return k.tile < tile_end;
     };
-    auto issue_next_in = [&](int tile, int m, int c, const TileCoord& tc, int o0) {
-      if (c + 128 < a.nt) {
-        issue_in(tc.n, tc.y0 + m * a.bh, tc.x0, o0 + c + 128);
-      } else if (m + 1 < a.mb) {
-        issue_in(tc.n, tc.y0 + (m + 1) * a.bh, tc.x0, o0 + c_first);
-      } else if (tile + my_step < tile_end) {
-        const TileCoord t2 = decode_tile(a, tile + my_step);
-        const int4 g2 = grp_in_smem ? grp_s[t2.g] : __ldg(a.group_tab + t2.g);
-        issue_in(t2.n, t2.y0, t2.x0, g2.x + c_first);
-      }
+    // one elected lane fetches the epilogue operands of a 64-channel chunk into operand set b through TMA
+    auto issue_chunk = [&](const Chunk& k, int b) {
+      const TileCoord t = decode_tile(a, k.tile, cta_rank);
+      const int4 g = grp_in_smem ? grp_s[t.g] : __ldg(a.group_tab + t.g);
+      const uint32_t bar = in_bar + 8 * b, base = in_t0 + b * n_in * kTileBytes;
+      const int c0 = g.x + k.c, x0 = t.x0 + sub_x, y0 = t.y0 + k.m * a.bh + sub_y;
+      ptx::mbar_arrive_expect_tx(bar, static_cast<uint32_t>(n_in) * kTileBytes);
+      if (epi & VSR_EPI_RES_PRE) ptx::tma_load_4d(base, &a.res_map, bar, c0, x0, y0, t.n);
+      if (epi & (VSR_EPI_PRELU_BWD | VSR_EPI_RELU_BWD)) ptx::tma_load_4d(base + aux_o, &a.aux_map, bar, c0, x0, y0, t.n);
+      if (epi & VSR_EPI_OUT2) ptx::tma_load_4d(base + res2_o, &a.res2_map, bar, c0, x0, y0, t.n);
     };
-
-    if (has_in && lane == 0 && my_begin < tile_end) {
-      const TileCoord t0 = decode_tile(a, my_begin);
-      const int4 g0 = grp_in_smem ? grp_s[t0.g] : __ldg(a.group_tab + t0.g);
-      issue_in(t0.n, t0.y0, t0.x0, g0.x + c_first);
+    Chunk la = {my_begin, 0, c_first};             // look-ahead: the next chunk whose operands are to be fetched
+    bool la_ok = has_in && my_begin < tile_end;
+    for (int d = 0; d < ibuf && la_ok; ++d) {
+      if (lane == 0) issue_chunk(la, d);
+      la_ok = next_chunk(la);
     }
+    uint32_t q = 0;                                // chunks processed by this warp
     int it = 0;
     for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++it) {
       if (by_tile && (it & 1) != chalf) continue;
-      const TileCoord tc = decode_tile(a, tile);
+      const TileCoord tc = decode_tile(a, tile, cta_rank);
       const int4 grp = grp_in_smem ? grp_s[tc.g] : __ldg(a.group_tab + tc.g);
       const int buf = it & 1;
       const uint32_t bphase = (it >> 1) & 1;
@@ -482,12 +557,15 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
           const uint32_t taddr = tmem_base + static_cast<uint32_t>((buf * a.mb + m) * a.nt) +
                                  (static_cast<uint32_t>(quarter * 32) << 16);
           if (prof) q0 = clock64();
-          if (has_in) {
-            ptx::mbar_wait(in_bar, in_phase);
-            in_phase ^= 1u;
+          const int ib = (int)(q & (uint32_t)(ibuf - 1)), ob = (int)(q & (uint32_t)(obuf - 1));
+          const uint32_t out_t = warp_t + ob * kTileBytes;
+          const uint32_t res_t = in_t0 + ib * n_in * kTileBytes, aux_t = res_t + aux_o, res2_t = res_t + res2_o;
+          if (has_in) ptx::mbar_wait(in_bar + 8 * ib, (q >> (ibuf - 1)) & 1u);
+          // the TMA store that last used this staging tile must have read it before it is rewritten
+          if (lane == 0) {
+            if (obuf == 2) bulk_wait_read1();
+            else bulk_wait_read0();
           }
-          // the previous chunk's TMA store must have read the staging tile before it is rewritten
-          if (lane == 0) bulk_wait_read0();
           __syncwarp();
           if (prof) { q1 = clock64(); e_in += q1 - q0; }
 #pragma unroll 1
@@ -612,9 +690,12 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
           }
           if (prof) q1 = clock64();
           if (has_in && !(epi & VSR_EPI_OUT2)) {
-            // the operand tiles have been consumed: fetch the next chunk's while this one is stored
+            // this operand set has been consumed: refill it with the look-ahead chunk's operands
             __syncwarp();
-            if (lane == 0) issue_next_in(tile, m, c, tc, grp.x);
+            if (la_ok) {
+              if (lane == 0) issue_chunk(la, ib);
+              la_ok = next_chunk(la);
+            }
           }
           fence_proxy_async();
           __syncwarp();
@@ -626,17 +707,23 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
             }
             bulk_commit();
             if (epi & VSR_EPI_OUT2) {
-              // the res2 tile doubles as the out2 staging tile: refill it only after the store has read it
+              // the res2 tile doubles as the out2 staging tile (one operand set): refill it only after the store has read it
               bulk_wait_read0();
-              issue_next_in(tile, m, c, tc, grp.x);
+              if (la_ok) issue_chunk(la, ib);
             }
           }
+          if ((epi & VSR_EPI_OUT2) && has_in && la_ok) la_ok = next_chunk(la);
+          ++q;
           if (prof) e_iss += clock64() - q1;
         }
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(tempty_bar + 8 * buf);
+      if (lane == 0) {
+        // (pair mode: the accumulator of BOTH CTAs is rewritten by the leader's next MMAs - free it on the leader's barrier)
+        if (PAIR && !leader_cta) ptx::mbar_arrive_remote(ptx::mapa(tempty_bar + 8 * buf, 0));
+        else ptx::mbar_arrive(tempty_bar + 8 * buf);
+      }
     }
     if (lane == 0) bulk_wait0();                 // all output bytes are written before the CTA retires
     if (prof && blockIdx.x == 0 && lane == 0 && (ew & 3) == 0)
@@ -653,10 +740,12 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
 
   const uint64_t g_t2 = kAttrib ? ptx::globaltimer_ns() : 0;
   ptx::tc_fence_before();
-  __syncthreads();
+  if (PAIR) ptx::cluster_sync();       // no CTA of the pair leaves while the other may still touch its shared / tensor memory
+  else __syncthreads();
   if (warp == kMmaWarp) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, kTmemCols);
+    if (PAIR) ptx::tmem_dealloc2(tmem_base, kTmemCols);
+    else ptx::tmem_dealloc(tmem_base, kTmemCols);
   }
   if (prof && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1))
     printf("tc2-prof block %d: start %llu ns, setup %llu ns, role done (producer) +%llu ns, exit +%llu ns\n", (int)blockIdx.x,
@@ -703,9 +792,9 @@ int build_columns(const int32_t* taps, int n_taps, int idx_base, int max_cols, u
   return longest;
 }
 
-template <int EPI>
+template <int EPI, bool PAIR>
 cudaError_t prepare() {
-  return cudaFuncSetAttribute(tapgemm_tc2_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+  return cudaFuncSetAttribute(tapgemm_tc2_kernel<EPI, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
 }
 
 }  // namespace
@@ -716,22 +805,23 @@ int tapgemm_tc2_launch(const VsrTapGemmDesc* d, cudaStream_t stream) {
                       "tapgemm(bf16, v2): nt must be a multiple of 64 in [64,256], got %d", d->nt);
   VSR_CHECK_ARG(d->out.c % 8 == 0 && d->out.c >= 64, "tapgemm(bf16): out.c must be a multiple of 8 and >= 64");
   typedef void (*KernelFn)(const Tc2Args);
-  static const struct { int epi; KernelFn fn; cudaError_t (*prep)(); } kVariants[] = {
-      {-1, tapgemm_tc2_kernel<-1>, prepare<-1>},
-      {0, tapgemm_tc2_kernel<0>, prepare<0>},
-      {VSR_EPI_BIAS, tapgemm_tc2_kernel<VSR_EPI_BIAS>, prepare<VSR_EPI_BIAS>},
-      {VSR_EPI_RES_PRE, tapgemm_tc2_kernel<VSR_EPI_RES_PRE>, prepare<VSR_EPI_RES_PRE>},
-      {VSR_EPI_BIAS | VSR_EPI_PRELU, tapgemm_tc2_kernel<VSR_EPI_BIAS | VSR_EPI_PRELU>, prepare<VSR_EPI_BIAS | VSR_EPI_PRELU>},
-      {VSR_EPI_BIAS | VSR_EPI_PRELU | VSR_EPI_OUT2, tapgemm_tc2_kernel<VSR_EPI_BIAS | VSR_EPI_PRELU | VSR_EPI_OUT2>,
-       prepare<VSR_EPI_BIAS | VSR_EPI_PRELU | VSR_EPI_OUT2>},
-      {VSR_EPI_PRELU_BWD, tapgemm_tc2_kernel<VSR_EPI_PRELU_BWD>, prepare<VSR_EPI_PRELU_BWD>},
-      {VSR_EPI_PRELU_BWD | VSR_EPI_RES_PRE, tapgemm_tc2_kernel<VSR_EPI_PRELU_BWD | VSR_EPI_RES_PRE>,
-       prepare<VSR_EPI_PRELU_BWD | VSR_EPI_RES_PRE>},
+#define VSR_TC2_VARIANT(E) {E, tapgemm_tc2_kernel<E, false>, tapgemm_tc2_kernel<E, true>, prepare<E, false>, prepare<E, true>}
+  static const struct { int epi; KernelFn fn, fn_pair; cudaError_t (*prep)(); cudaError_t (*prep_pair)(); } kVariants[] = {
+      VSR_TC2_VARIANT(-1),
+      VSR_TC2_VARIANT(0),
+      VSR_TC2_VARIANT(VSR_EPI_BIAS),
+      VSR_TC2_VARIANT(VSR_EPI_RES_PRE),
+      VSR_TC2_VARIANT(VSR_EPI_BIAS | VSR_EPI_PRELU),
+      VSR_TC2_VARIANT(VSR_EPI_BIAS | VSR_EPI_PRELU | VSR_EPI_OUT2),
+      VSR_TC2_VARIANT(VSR_EPI_PRELU_BWD),
+      VSR_TC2_VARIANT(VSR_EPI_PRELU_BWD | VSR_EPI_RES_PRE),
   };
+#undef VSR_TC2_VARIANT
   static bool attr_set = false;
   if (!attr_set) {
     for (const auto& v : kVariants) {
       cudaError_t e = v.prep();
+      if (e == cudaSuccess) e = v.prep_pair();
       if (e != cudaSuccess) {
         set_error("cudaFuncSetAttribute(smem) failed: %s", cudaGetErrorString(e));
         return VSR_ERR_CUDA;
@@ -739,9 +829,9 @@ int tapgemm_tc2_launch(const VsrTapGemmDesc* d, cudaStream_t stream) {
     }
     attr_set = true;
   }
-  KernelFn kernel = kVariants[0].fn;
+  const auto* variant = &kVariants[0];
   for (const auto& v : kVariants)
-    if (v.epi == d->epi) kernel = v.fn;
+    if (v.epi == d->epi) variant = &v;
 
   Tc2Args a;
   memset(&a, 0, sizeof(a));
@@ -794,115 +884,184 @@ int tapgemm_tc2_launch(const VsrTapGemmDesc* d, cudaStream_t stream) {
   a.row_bytes = bw * 128;
   const int n_in = ((d->epi & VSR_EPI_RES_PRE) ? 1 : 0) + ((d->epi & (VSR_EPI_PRELU_BWD | VSR_EPI_RELU_BWD)) ? 1 : 0) +
                    ((d->epi & VSR_EPI_OUT2) ? 1 : 0);
-  a.epi_bytes = kEpiWarps * (1 + n_in) * kTileBytes;
-  const int b_bytes = d->nt * 128;
-  const long avail = kSmemBudget - kCtrlBytes - a.epi_bytes;
   const Tunables& tn = tunables();
-  a.debug = tn.tc_debug > 0 ? tn.tc_debug : 0;
-
-  // ---- shared-load mode: taps that differ only by a row shift read one A box; with nt <= 128 two pixel
-  // tiles stacked in y also share every weight slab.  Needs the host copies of the tables
-  // (d->tap_tab_host, and d->group_tab_host when there are several groups).
-  a.mb = 1;
-  a.a_bytes = kATileBytes;
-  int ndy_max = 1;
-  const long res_need = (long)d->max_group_taps * b_bytes;
+  // ---- CTA pairs (cta_group::2): every CTA holds half of each weight slab.  Worth it where the B operand weighs: wide
+  // slabs (nt >= 128: their shared-memory reads and their resident footprint halve) and long tables of narrow ones (the
+  // strided k x k convolutions: slab traffic L2 -> SM halves); the short nt = 64 tables of the 1x1 convolutions are
+  // HBM-bound and keep single CTAs.  VSR_TC_PAIR=0 / 1 forces none / all.
   {
-    const bool want = tn.tc_tall != 0;
-    bool ok = want && d->tap_tab_host != nullptr && bw >= 8 && bw * bh == kBlockM && d->n_taps_total <= 4095 &&
-              d->n_groups <= kMaxTallGroups && (d->n_groups == 1 || d->group_tab_host != nullptr);
-    int n_cols = 0, longest = 0;
-    for (int gi = 0; ok && gi < d->n_groups; ++gi) {
-      const int o0 = d->n_groups == 1 ? 0 : d->group_tab_host[4 * gi];
-      const int begin = d->n_groups == 1 ? 0 : d->group_tab_host[4 * gi + 1];
-      const int count = d->n_groups == 1 ? d->n_taps_total : d->group_tab_host[4 * gi + 2];
-      int nc = 0;
-      const int lg = build_columns(d->tap_tab_host + 4 * begin, count, begin, kMaxParamCols - n_cols, a.cols + n_cols, &nc);
-      if (lg == 0 || begin > 0xffff || count > 0x7fff) { ok = false; break; }
-      a.tgroups[gi] = make_int4(o0, n_cols, nc, begin | (count << 16));
-      n_cols += nc;
-      if (lg > longest) longest = lg;
+    const long px_tiles = (long)d->out.n * ((d->out.w + bw - 1) / bw) * ((d->out.h + bh - 1) / bh);
+    bool want = d->nt >= 128 || (d->max_group_taps >= 16 && d->n_groups == 1);
+    if (tn.tc_pair == 0) want = false;
+    if (tn.tc_pair == 1) want = true;
+    a.pair = want && d->nt % 32 == 0 && px_tiles >= 2 && num_sms() >= 2;
+  }
+  const int b_bytes = d->nt * 128 / (a.pair ? 2 : 1);      // bytes of a weight slab held by one CTA
+  // ---- epilogue staging: in the chunk-parity mode (nt > 64: a warp processes chunk after chunk of the same tile) a
+  // second output tile lets the TMA store of a chunk overlap the next chunk, and a second operand set lets the
+  // residual / saved-activation tiles arrive two chunks ahead; taken when >= 3 pipeline stages remain
+  // (nt <= 64: the warp sets alternate tiles, which already hides both)
+  int cand[4][2], n_cand = 0;
+  if (d->nt > 64 && !(d->epi & VSR_EPI_OUT2)) {
+    if (n_in > 0) {
+      cand[n_cand][0] = 2; cand[n_cand++][1] = 2;
+      cand[n_cand][0] = 1; cand[n_cand++][1] = 2;
     }
-    if (ok && d->n_groups == 1) {
-      // the output slice of a single group comes from the device table (group_tab_host is optional)
-      a.tgroups[0].x = -1;
-    }
-    if (ok && longest >= 2) {
-      const int mb = (d->nt <= 128 && a.H >= 2 * bh) ? 2 : 1;
-      const int rows = mb * bh + longest - 1;
-      const long abox = (long)rows * a.row_bytes;
-      const bool res_ok = d->max_group_taps > 0 && d->nt > 64 && res_need <= avail - 3 * abox;
-      // streamed slabs: three stages of {shared box + its slabs} when they fit; two are enough when a stage is long
-      // (3 taps x mb sub-tiles x 4 MMAs) and the alternative is one load per tap (3x the L2 -> SM traffic: the
-      // 3x3(x3) convolutions of the Conv3d path, profiles/README.md).  VSR_TC_TALL_STAGES=3 restores the old rule.
-      const int min_stages = tn.tc_tall_stages == 3 ? 3 : 2;
-      const bool stream_ok = min_stages * (abox + (long)longest * b_bytes) <= avail;
-      if (rows <= 256 && (res_ok || stream_ok)) {
-        a.tall = 1;
-        a.mb = mb;
-        a.n_cols = n_cols;
-        a.a_bytes = (int)abox;
-        ndy_max = longest;
-        for (int s = 0; s < d->n_srcs; ++s) {
-          int rc = get_src_map_pub(d->srcs[s], bw, rows, &a.tall_maps[s]);
-          if (rc != VSR_OK) return rc;
+    cand[n_cand][0] = 2; cand[n_cand++][1] = 1;
+  }
+  cand[n_cand][0] = 1; cand[n_cand++][1] = 1;
+  int ndy_max = 1;
+  for (int ci = 0; ci < n_cand; ++ci) {
+    a.epi_obuf = cand[ci][0];
+    a.epi_ibuf = cand[ci][1];
+    a.epi_bytes = kEpiWarps * (a.epi_obuf + a.epi_ibuf * n_in) * kTileBytes;
+    a.tall = 0;
+    a.n_cols = 0;
+    ndy_max = 1;
+    const long avail = kSmemBudget - kCtrlBytes - a.epi_bytes;
+    a.debug = tn.tc_debug > 0 ? tn.tc_debug : 0;
+
+    // ---- shared-load mode: taps that differ only by a row shift read one A box; with nt <= 128 two pixel
+    // tiles stacked in y also share every weight slab.  Needs the host copies of the tables
+    // (d->tap_tab_host, and d->group_tab_host when there are several groups).
+    a.mb = 1;
+    a.a_bytes = kATileBytes;
+    const long res_need = (long)d->max_group_taps * b_bytes;
+    {
+      const bool want = tn.tc_tall != 0;
+      bool ok = want && d->tap_tab_host != nullptr && bw >= 8 && bw * bh == kBlockM && d->n_taps_total <= 4095 &&
+                d->n_groups <= kMaxTallGroups && (d->n_groups == 1 || d->group_tab_host != nullptr);
+      int n_cols = 0, longest = 0;
+      for (int gi = 0; ok && gi < d->n_groups; ++gi) {
+        const int o0 = d->n_groups == 1 ? 0 : d->group_tab_host[4 * gi];
+        const int begin = d->n_groups == 1 ? 0 : d->group_tab_host[4 * gi + 1];
+        const int count = d->n_groups == 1 ? d->n_taps_total : d->group_tab_host[4 * gi + 2];
+        int nc = 0;
+        const int lg = build_columns(d->tap_tab_host + 4 * begin, count, begin, kMaxParamCols - n_cols, a.cols + n_cols, &nc);
+        if (lg == 0 || begin > 0xffff || count > 0x7fff) { ok = false; break; }
+        a.tgroups[gi] = make_int4(o0, n_cols, nc, begin | (count << 16));
+        n_cols += nc;
+        if (lg > longest) longest = lg;
+      }
+      if (ok && d->n_groups == 1) {
+        // the output slice of a single group comes from the device table (group_tab_host is optional)
+        a.tgroups[0].x = -1;
+      }
+      if (ok && longest >= 2) {
+        const int mb = (d->nt <= 128 && a.H >= 2 * bh) ? 2 : 1;
+        const int rows = mb * bh + longest - 1;
+        const long abox = (long)rows * a.row_bytes;
+        const bool res_ok = d->max_group_taps > 0 && d->nt > 64 && res_need <= avail - 3 * abox;
+        // streamed slabs: three stages of {shared box + its slabs} when they fit; two are enough when a stage is long
+        // (3 taps x mb sub-tiles x 4 MMAs) and the alternative is one load per tap (3x the L2 -> SM traffic: the
+        // 3x3(x3) convolutions of the Conv3d path, profiles/README.md).  VSR_TC_TALL_STAGES=3 restores the old rule.
+        const int min_stages = tn.tc_tall_stages == 3 ? 3 : 2;
+        const bool stream_ok = min_stages * (abox + (long)longest * b_bytes) <= avail;
+        if (rows <= 256 && (res_ok || stream_ok)) {
+          a.tall = 1;
+          a.mb = mb;
+          a.n_cols = n_cols;
+          a.a_bytes = (int)abox;
+          ndy_max = longest;
+          for (int s = 0; s < d->n_srcs; ++s) {
+            int rc = get_src_map_pub(d->srcs[s], bw, rows, &a.tall_maps[s]);
+            if (rc != VSR_OK) return rc;
+          }
         }
       }
     }
-  }
-  a.tiles_x = (a.W + bw - 1) / bw;
-  a.tiles_y = (a.H + bh * a.mb - 1) / (bh * a.mb);
-  const long tiles = (long)a.n_groups * a.N * a.tiles_x * a.tiles_y;
-  VSR_CHECK_SUPPORTED(tiles < (1l << 30), "tapgemm(bf16): too many tiles");
-  a.num_tiles = (int)tiles;
-  a.m_tiles = a.N * a.tiles_x * a.tiles_y;
-  // weight-resident mode: the group's slabs stay in smem and >= 3 A stages remain; worth it when the
-  // slabs are large next to the A tile (nt > 64) and every CTA sees few groups
-  // (short nt=64 tables - the 1x1 convolutions on concatenations - were measured 5-10% slower resident:
-  // tools/hr_sweep.py, so they stream their 8 KB slabs with the A tiles)
-  a.resident = d->max_group_taps > 0 && d->nt > 64 && res_need <= avail - 3 * (long)a.a_bytes &&
-               tiles >= 2 * (long)num_sms();
-  // (resident slabs for the short nt = 64 tables of the 1x1 convolutions were measured neutral to slightly slower,
-  //  with either tile walk: tools/hr_sweep.py; VSR_TC_RESIDENT=1 forces them)
-  {
-    if (tn.tc_resident == 0) a.resident = 0;
-    if (tn.tc_resident == 1 && d->max_group_taps > 0 && res_need <= avail - 2 * (long)a.a_bytes)
-      a.resident = 1;
-  }
-  if (a.tall && !a.resident && 2 * ((long)a.a_bytes + (long)ndy_max * b_bytes) > avail) {
-    // the shared box plus its slabs does not fit twice without resident weights: plain columns
-    a.tall = 0;
-    a.mb = 1;
-    a.a_bytes = kATileBytes;
-    ndy_max = 1;
-    a.tiles_y = (a.H + bh - 1) / bh;
-    a.num_tiles = (int)((long)a.n_groups * a.N * a.tiles_x * a.tiles_y);
+    a.tiles_x = (a.W + bw - 1) / bw;
+    a.tiles_y = (a.H + bh * a.mb - 1) / (bh * a.mb);
+    const long tiles = (long)a.n_groups * a.N * a.tiles_x * a.tiles_y;
+    VSR_CHECK_SUPPORTED(tiles < (1l << 30), "tapgemm(bf16): too many tiles");
+    a.num_tiles = (int)tiles;
     a.m_tiles = a.N * a.tiles_x * a.tiles_y;
+    // weight-resident mode: the group's slabs stay in smem and >= 3 A stages remain; worth it when the
+    // slabs are large next to the A tile (nt > 64) and every CTA sees few groups
+    // (short nt=64 tables - the 1x1 convolutions on concatenations - were measured 5-10% slower resident:
+    // tools/hr_sweep.py, so they stream their 8 KB slabs with the A tiles)
+    a.resident = d->max_group_taps > 0 && d->nt > 64 && res_need <= avail - 3 * (long)a.a_bytes &&
+                 tiles >= 2 * (long)num_sms();
+    // (resident slabs for the short nt = 64 tables of the 1x1 convolutions were measured neutral to slightly slower,
+    //  with either tile walk: tools/hr_sweep.py; VSR_TC_RESIDENT=1 forces them)
+    {
+      if (tn.tc_resident == 0) a.resident = 0;
+      if (tn.tc_resident == 1 && d->max_group_taps > 0 && res_need <= avail - 2 * (long)a.a_bytes)
+        a.resident = 1;
+    }
+    if (a.tall && !a.resident && 2 * ((long)a.a_bytes + (long)ndy_max * b_bytes) > avail) {
+      // the shared box plus its slabs does not fit twice without resident weights: plain columns
+      a.tall = 0;
+      a.mb = 1;
+      a.a_bytes = kATileBytes;
+      ndy_max = 1;
+      a.tiles_y = (a.H + bh - 1) / bh;
+      a.num_tiles = (int)((long)a.n_groups * a.N * a.tiles_x * a.tiles_y);
+      a.m_tiles = a.N * a.tiles_x * a.tiles_y;
+    }
+    if (a.pair) {
+      // the walk counts PAIRS of pixel tiles (decode_tile: CTA `rank` takes pixel tile 2 * pair + rank)
+      a.m_tiles = (a.m_tiles + 1) / 2;
+      a.num_tiles = a.n_groups * a.m_tiles;
+    }
+    {
+      auto magic = [](int d) -> uint32_t { return d <= 1 ? 0u : (uint32_t)(((1ull << 32) + (uint64_t)d - 1) / (uint64_t)d); };
+      // exact for every n < 2^32: ceil(2^32/d) overestimates 2^32/d by < 1, so the quotient by < n / 2^32 < 1
+      a.mg_groups = magic(a.n_groups);
+      a.mg_mtiles = magic(a.m_tiles);
+      a.mg_tx = magic(a.tiles_x);
+      a.mg_ty = magic(a.tiles_y);
+    }
+    a.contig = a.resident && d->n_groups > 1;
+    a.res_bytes = a.resident ? (int)res_need : 0;
+    a.stage_bytes = a.resident ? a.a_bytes : a.a_bytes + ndy_max * b_bytes;
+    int stages = (int)((avail - a.res_bytes) / a.stage_bytes);
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (tn.tc_stages >= 1 && tn.tc_stages < stages) stages = tn.tc_stages;
+    if (stages < 1 && ci + 1 < n_cand) continue;
+    VSR_CHECK_SUPPORTED(stages >= 1, "tapgemm(bf16, v2): no room for a pipeline stage");
+    a.stages = stages;
+    if (stages >= 3 || ci + 1 == n_cand) break;
   }
-  {
-    auto magic = [](int d) -> uint32_t { return d <= 1 ? 0u : (uint32_t)(((1ull << 32) + (uint64_t)d - 1) / (uint64_t)d); };
-    // exact for every n < 2^32: ceil(2^32/d) overestimates 2^32/d by < 1, so the quotient by < n / 2^32 < 1
-    a.mg_groups = magic(a.n_groups);
-    a.mg_mtiles = magic(a.m_tiles);
-    a.mg_tx = magic(a.tiles_x);
-    a.mg_ty = magic(a.tiles_y);
-  }
-  a.contig = a.resident && d->n_groups > 1;
-  a.res_bytes = a.resident ? (int)res_need : 0;
-  a.stage_bytes = a.resident ? a.a_bytes : a.a_bytes + ndy_max * b_bytes;
-  int stages = (int)((avail - a.res_bytes) / a.stage_bytes);
-  if (stages > kMaxStages) stages = kMaxStages;
-  if (tn.tc_stages >= 1 && tn.tc_stages < stages) stages = tn.tc_stages;
-  VSR_CHECK_SUPPORTED(stages >= 1, "tapgemm(bf16, v2): no room for a pipeline stage");
-  a.stages = stages;
-  const int smem = kCtrlBytes + a.epi_bytes + a.res_bytes + stages * a.stage_bytes;
+  const int smem = kCtrlBytes + a.epi_bytes + a.res_bytes + a.stages * a.stage_bytes;
   int grid = num_sms();
   if (tn.tc_grid >= 1) grid = tn.tc_grid;
-  if (grid > a.num_tiles) grid = a.num_tiles;
   if (grid > kPartialsLen) grid = kPartialsLen;
+  KernelFn kernel = a.pair ? variant->fn_pair : variant->fn;
+  if (a.pair) {
+    // one CTA pair per TPC - but not every TPC can host a cluster (GPCs with an odd number of live SMs): a persistent
+    // kernel must not launch more pairs than are co-resident, or the rest would run as a second wave
+    static int max_pairs = -1;
+    if (max_pairs < 0) {
+      cudaLaunchConfig_t q;
+      memset(&q, 0, sizeof(q));
+      q.gridDim = dim3(num_sms());
+      q.blockDim = dim3(kThreads);
+      q.dynamicSmemBytes = kSmemBudget;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = 2;
+      qa[0].val.clusterDim.y = 1;
+      qa[0].val.clusterDim.z = 1;
+      q.attrs = qa;
+      q.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kernel, &q) != cudaSuccess || n < 1) {
+        cudaGetLastError();
+        n = num_sms() / 2;
+      }
+      max_pairs = n;
+    }
+    int walkers = grid / 2;
+    if (walkers > max_pairs) walkers = max_pairs;
+    if (walkers > a.num_tiles) walkers = a.num_tiles;
+    grid = 2 * walkers;
+  } else if (grid > a.num_tiles) {
+    grid = a.num_tiles;
+  }
   if (a.debug & 64) {
-    fprintf(stderr, "tc2 plan: nt %d groups %d taps %d | tall %d mb %d cols %d a_bytes %d | resident %d res_bytes %d | stages %d x %d, epi %d, smem %d, tiles %d (m %d), grid %d\n",
-            a.nt, a.n_groups, a.n_taps_total, a.tall, a.mb, a.n_cols, a.a_bytes, a.resident, a.res_bytes, a.stages,
+    fprintf(stderr, "tc2 plan: epi bufs %d/%d pair %d nt %d groups %d taps %d | tall %d mb %d cols %d a_bytes %d | resident %d res_bytes %d | stages %d x %d, epi %d, smem %d, tiles %d (m %d), grid %d\n",
+            a.epi_obuf, a.epi_ibuf, a.pair, a.nt, a.n_groups, a.n_taps_total, a.tall, a.mb, a.n_cols, a.a_bytes, a.resident, a.res_bytes, a.stages,
             a.stage_bytes, a.epi_bytes, smem, a.num_tiles, a.m_tiles, grid);
     if (a.tall)
       for (int gi = 0; gi < a.n_groups; ++gi)
@@ -916,12 +1075,23 @@ int tapgemm_tc2_launch(const VsrTapGemmDesc* d, cudaStream_t stream) {
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    int n_attr = 0;
     if (tn.pdl != 0) {
+      attr[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[n_attr].val.programmaticStreamSerializationAllowed = 1;
+      ++n_attr;
+    }
+    if (a.pair) {
+      attr[n_attr].id = cudaLaunchAttributeClusterDimension;
+      attr[n_attr].val.clusterDim.x = 2;
+      attr[n_attr].val.clusterDim.y = 1;
+      attr[n_attr].val.clusterDim.z = 1;
+      ++n_attr;
+    }
+    if (n_attr) {
       cfg.attrs = attr;
-      cfg.numAttrs = 1;
+      cfg.numAttrs = n_attr;
     }
     cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, a);
     if (e != cudaSuccess) {

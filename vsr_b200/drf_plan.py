@@ -306,9 +306,37 @@ class DrfPlan:
         lname = f"out{level + 1}"
         self.fwd[lname] = Layer(lname, TapTable(self.kc, nt, fgroups), fslabs, n_slots * m * F, bias)
         # data-gradient: d_in(P, ci) = sum_{ky,kx,co} dz(P - (ky-1,kx-1), co) W[co,ci,ky,kx]
+        kb_out = (m * F) // self.kc
+        if in_r >= 2 and n_slots % 4 == 0 and 4 * F <= MAX_NT:
+            # The four phase slots of a 2x2 block (nested order: slots 4b .. 4b+3) are produced TOGETHER (nt = 4F): they
+            # read the same 4x4 neighbourhood of dz positions, each with its own kernel offset (or none: structural
+            # zero rows).  One A tile then feeds 4F output channels instead of F - the N = 64 form ran at a third of the
+            # tensor peak (smem operand reads per MMA) and loaded 144 A tiles per pixel tile instead of 64.
+            jj, k2 = self._jk(4 * F)
+            oi, oj, ci = (jj // F) // 2, (jj // F) % 2, jj % F          # output slot (i, j) of the block, input channel
+            bgroups, bslabs = [], []
+            parents = phase_table(in_r // 2)
+            for b, (Py, Px) in enumerate(parents):
+                assert [in_phases[4 * b + 2 * i + j] for i in (0, 1) for j in (0, 1)] == \
+                    [(2 * Py + i, 2 * Px + j) for i in (0, 1) for j in (0, 1)]
+                taps = []
+                rows = sorted(range(2 * Py - 1, 2 * Py + 3), key=lambda R: (R % in_r, R // in_r))
+                for C in range(2 * Px - 1, 2 * Px + 3):
+                    dX, qx = divmod(C, in_r)
+                    for bk in range(kb_out):
+                        for R in rows:      # same row phase -> consecutive row shifts, ascending (shared A box)
+                            dY, qy = divmod(R, in_r)
+                            taps.append((0, dY, dX, in_slot[(qy, qx)] * m * F + bk * self.kc))
+                            ky, kx = 2 * Py + oi - R + 1, 2 * Px + oj - C + 1
+                            ok = (ky >= 0) & (ky <= 2) & (kx >= 0) & (kx <= 2)
+                            idx = W.idx(perm(bk * self.kc + k2), ci, np.clip(ky, 0, 2), np.clip(kx, 0, 2))
+                            bslabs.append(np.where(ok, idx, -1))
+                bgroups.append((4 * b * F, taps))
+            # (9 of the 16 source positions of a block carry a kernel tap for a given output slot)
+            self.bwd[lname] = Layer(lname, TapTable(self.kc, 4 * F, bgroups, useful=9.0 / 16.0), bslabs, n_slots * F)
+            return
         j2, k2 = self._jk(F)
         bgroups, bslabs = [], []
-        kb_out = (m * F) // self.kc
         for slot, (py, px) in enumerate(in_phases):
             taps = []
             for ky in (2, 1, 0):        # row shifts ascending with the slab index: the tensor-core kernel then shares

@@ -38,6 +38,7 @@ class TapTable:
     nt: int
     groups: List[Tuple[int, List[Tuple[int, int, int, int]]]]
     _dev: dict = field(default_factory=dict, repr=False)
+    useful: float = 1.0      # share of the table's MACs that are algorithmic (< 1: structural-zero weight rows)
 
     @property
     def n_groups(self):
@@ -180,7 +181,7 @@ class CudaOps:
             # epilogue operands read (residual, saved activation, second residual) / written (second output)
             n_extra = ((epi & EPI_RES_PRE) != 0) + ((epi & (EPI_PRELU_BWD | EPI_RELU_BWD)) != 0) + 2 * ((epi & EPI_OUT2) != 0)
             nbytes += es * pix * out.shape[-1] * n_extra
-            self._meta = ("tapgemm", 2.0 * pix * tab.n_taps_total * tab.nt * tab.kc, sig, nbytes)
+            self._meta = ("tapgemm", 2.0 * pix * tab.n_taps_total * tab.nt * tab.kc * tab.useful, sig, nbytes)
         check(fn(C.byref(d), _stream()), "vsr_tapgemm")
         self._meta = None
         self.launches += 1
