@@ -54,7 +54,8 @@ enum {
   VSR_EPI_PRELU_BWD = 16, /* y=aux_y: v = y>0 ? v : a*v ; slope grad += v_in * y/a     */
   VSR_EPI_RELU_BWD = 32,  /* y=aux_y: v = y>0 ? v : 0                                  */
   VSR_EPI_OUT2 = 64,      /* out2[pix][o] = v + res2[pix][o]   (after the activation)  */
-  VSR_EPI_SCALE = 128     /* v *= out_scale   (after bias, before the residual)        */
+  VSR_EPI_SCALE = 128,    /* v *= out_scale   (after bias, before the residual)        */
+  VSR_EPI_OUT2_SUB = 256  /* with OUT2: out2[pix][o] = v - res2[pix][o]  (rbp_net.py:274,284: l0 - x, h0 - x)  */
 };
 
 typedef struct VsrTensor4 {
@@ -203,6 +204,10 @@ int vsr_reduce_partials(const float* partials, int32_t rows, int32_t len, const 
  * parameters into tap slabs (dst dtype) and un-packs slab gradients (fp32 -> fp32). */
 int vsr_gather(const float* src, const int32_t* idx, void* dst, int32_t dst_dtype, int64_t n,
                void* stream);
+/* out[i] = alpha * a[i] + beta * b[i]  (fp32 or bf16 maps; b may be NULL when beta == 0; out may alias a or b):
+ * the residual sums / differences between feature maps of rbp_net.py:84-87,274-275,284-285 in the backward pass */
+int vsr_axpby(const void* a, const void* b, void* out, int32_t dtype, int64_t numel, float alpha, float beta, void* stream);
+
 /* dst[i] += src[idx[i]] for idx[i] >= 0 (fp32) */
 int vsr_gather_add(const float* src, const int32_t* idx, float* dst, int64_t n, void* stream);
 
@@ -381,6 +386,18 @@ int vsr_duf_filter_bwd(const void* logits, int32_t ld_logits, int32_t dtype, con
 int vsr_cine_gather(const float* vol, int32_t seqs, int32_t frames, int32_t h, int32_t w_, const int32_t* tab,
                     int32_t n, int32_t nf, int32_t r, int32_t f_first, int32_t f_count, int32_t ph, int32_t pw,
                     float mean, float std, float* out, void* stream);
+
+/*
+ * The reference's offline `Downscale` (acdc_preprocess.py:102-180: centred k-space truncation to 1/r per axis, |.|, round,
+ * cv2.INTER_CUBIC resize by 1/r, round, clip to [0, 255]) for n frames resident in device memory: the low-resolution side
+ * of a dataset without the host.  hr: [n][h][w] fp32 integer-valued; ph / pw: the h x h / w x w complex matrices of the 1-D
+ * low-pass operator (interleaved re, im, fp64, built per (size, r) by vsr_b200.data.lowpass_matrix); lr: [n][h/r][w/r] fp32.
+ * h, w multiples of r.  FP64 arithmetic: bit-identical to the reference's numpy path unless an exact low-pass value lies
+ * within ~1e-10 of x.5.  workspace >= vsr_downscale_workspace(n, h, w) bytes.
+ */
+size_t vsr_downscale_workspace(int32_t n, int32_t h, int32_t w);
+int vsr_downscale(const float* hr, int32_t n, int32_t h, int32_t w, int32_t r, const double* ph, const double* pw, float* lr,
+                  void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -50,6 +50,7 @@ def load():
     ns.DRFSISRNet = _load("src.model.nets.drf_sisr_net", "src/model/nets/drf_sisr_net.py").DRFSISRNet
     ns.SRFBNet = _load("src.model.nets.srfb_net", "src/model/nets/srfb_net.py").SRFBNet
     ns.EDSRNet = _load("src.model.nets.edsr_net", "src/model/nets/edsr_net.py").EDSRNet
+    ns.RBPNet = _load("src.model.nets.rbp_net", "src/model/nets/rbp_net.py").RBPNet
     losses = _load("src.model.losses", "src/model/losses.py")
     metrics = _load("src.model.metrics", "src/model/metrics.py")
     utils = _load("src.utils", "src/utils.py")

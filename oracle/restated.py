@@ -297,3 +297,57 @@ def drfnet_init(in_channels, out_channels, num_features, num_groups, upscale_fac
         put("out_block.conv1", nn.Conv2d(F_, 9 * F_, 3, padding=1))
         put("out_block.conv2", nn.Conv2d(F_, out_channels, 3, padding=1))
     return sd
+
+
+# ---- RBPNet (rbp_net.py:8-285) ----------------------------------------------------------------------------------------
+def rbpnet_forward(inputs, sd, upscale, num_frames):
+    """RBPNet.forward - rbp_net.py:65-91 with DBPNet.forward :129-139, UpBlock :268-276, DownBlock :278-285,
+    ResnetBlock.forward :227-246 (norm=None, the block's single PReLU applied twice), ConvBlock / DeconvBlock :142-219."""
+    k, s, pad = PROJ[upscale]
+    inputs = list(inputs)
+    t = num_frames // 2 if num_frames % 2 == 1 else num_frames // 2 - 1            # :14
+    x = inputs.pop(t)                                                               # :66
+    act = lambda v, p: F.prelu(v, sd[p + ".act.weight"])
+    cb = lambda v, p, **kw: act(_conv(v, sd, p + ".conv", **kw), p)                 # ConvBlock with PReLU
+    db = lambda v, p: act(_deconv(v, sd, p + ".deconv", stride=s, padding=pad), p)  # DeconvBlock with PReLU
+    proj = dict(stride=s, padding=pad)
+
+    def resblock(v, p):
+        out = act(_conv(v, sd, p + ".conv1", padding=1), p)
+        return act(_conv(out, sd, p + ".conv2", padding=1) + v, p)
+
+    def seq(v, p, last):
+        i = 0
+        while f"{p}.{i}.conv1.weight" in sd:
+            v = resblock(v, f"{p}.{i}")
+            i += 1
+        return last(v, f"{p}.{i}")
+
+    def up(v, p):
+        h0 = db(v, p + ".up_conv1")
+        l0 = cb(h0, p + ".up_conv2", **proj)
+        return db(l0 - v, p + ".up_conv3") + h0
+
+    def down(v, p):
+        l0 = cb(v, p + ".down_conv1", **proj)
+        h0 = db(l0, p + ".down_conv2")
+        return cb(h0 - v, p + ".down_conv3", **proj) + l0
+
+    def dbp(v):
+        v = cb(v, "dbp_net.feat1")
+        h1 = up(v, "dbp_net.up1")
+        h2 = up(down(h1, "dbp_net.down1"), "dbp_net.up2")
+        h3 = up(down(h2, "dbp_net.down2"), "dbp_net.up3")
+        return _conv(torch.cat((h3, h2, h1), 1), sd, "dbp_net.output.conv")         # :137 (no activation)
+
+    feat_input = cb(x, "feat0", padding=1)                                          # :70
+    feat_frame = [cb(torch.cat([x, nb], dim=1), "feat1", padding=1) for nb in inputs]   # :71-73
+    Ht = []
+    for j in range(len(inputs)):                                                    # :77-86
+        h0 = dbp(feat_input)
+        h1 = seq(feat_frame[j], "res_feat1", db)
+        e = seq(h0 - h1, "res_feat2", lambda v, p: cb(v, p, padding=1))
+        h = h0 + e
+        Ht.append(h)
+        feat_input = seq(h, "res_feat3", lambda v, p: cb(v, p, **proj))
+    return _conv(torch.cat(Ht, dim=1), sd, "output.conv", padding=1)                # :89-90

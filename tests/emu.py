@@ -129,7 +129,8 @@ class EmuOps:
                 out[..., sl] = v.to(out.dtype)
             if epi & E.EPI_OUT2:
                 # the kernels add in fp32 from the unrounded value
-                out2[..., sl] = (v + res2[..., sl].to(ct)).to(out2.dtype)
+                r2 = res2[..., sl].to(ct)
+                out2[..., sl] = (v - r2 if epi & E.EPI_OUT2_SUB else v + r2).to(out2.dtype)
         self.launches += 1
 
     def tapgemm_wgrad_workspace(self, tab, srcs, dz):
@@ -256,6 +257,14 @@ class EmuOps:
     def add(self, a, b, out):
         ct = torch.float64 if a.dtype == torch.float64 else torch.float32
         out.copy_((a.to(ct) + b.to(ct)).to(out.dtype))
+        self.launches += 1
+
+    def axpby(self, a, b, out, alpha, beta):
+        ct = torch.float64 if a.dtype == torch.float64 else torch.float32
+        v = alpha * a.to(ct)
+        if b is not None and beta != 0:
+            v = v + beta * b.to(ct)
+        out.copy_(v.to(out.dtype))
         self.launches += 1
 
     def reduce_partials(self, partials, rows, row_dst, dst):

@@ -158,3 +158,17 @@ def test_restated_dufnet_matches_live_reference(backbone, r, cin):
     want = net(x)
     got = restated.dufnet_forward(x, dict(net.state_dict()), 5, r, training=False)
     assert (got - want).abs().max() <= 1e-5 * want.abs().max()
+
+
+def test_host_downscale_restatement_equals_reference_downscale():
+    """vsr_b200.data.downscale (the numpy / cv2 restatement the synthetic dataset uses on the host) against the REAL
+    reference Downscale class (acdc_preprocess.py:102-180; tests/golden/downscale.pt, oracle/make_golden_downscale.py):
+    every pixel of every case is the same integer"""
+    import numpy as np
+    from vsr_b200.data import downscale, lowpass_matrix
+    for c in torch.load(os.path.join(GOLDEN, "downscale.pt")):
+        hr, lr = c["hr"].float().numpy(), c["lr"].float().numpy()
+        got = np.stack([downscale(f, c["r"]) for f in hr])
+        assert np.array_equal(got, lr)
+    P = lowpass_matrix(12, 4)
+    assert P.shape == (12, 12, 2) and abs(P[..., 0].sum(axis=1) - 1.0).max() < 1e-12     # the DC component passes unchanged

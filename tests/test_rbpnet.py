@@ -1,0 +1,129 @@
+"""RBPNet (rbp_net.py:8-285) drop-in: state_dict contract, the oracle restatement against the real reference's goldens
+(tests/golden/rbpnet_*.pt, oracle/make_golden_rbp.py), the plan + recorded backward through the kernel emulation on CPU,
+and the CUDA path (fp32 strict mode, bf16 tcgen05 mode) against the same goldens."""
+import glob
+import os
+
+import pytest
+import torch
+
+from oracle import restated
+from tests.emu import EmuOps
+from vsr_b200.rbpn import RBPNet
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+SMALL = sorted(p for p in glob.glob(os.path.join(GOLDEN, "rbpnet_*.pt")) if "b64" not in p)
+BIG = os.path.join(GOLDEN, "rbpnet_b64_f64_x4.pt")
+
+
+def _state(fx, idx_seed=None):
+    """the fixture's state_dict; the large fixture stores only its seed and slopes (the product class has the
+    reference's construction order, hence its default initialisation under the same seed)"""
+    if fx["state_dict"] is not None:
+        return fx["state_dict"]
+    torch.manual_seed(fx["state_seed"])
+    sd = {k: v.clone() for k, v in RBPNet(**fx["kwargs"]).state_dict().items()}
+    sd.update(fx["slopes"])
+    return sd
+
+
+def _check(net, fx, out_tol, grad_tol, device="cpu"):
+    x = [t.to(device) for t in fx["inputs"]]
+    out = net(x)
+    ref = fx["output"]
+    assert out.shape == ref.shape
+    assert (out.detach().cpu().float() - ref).abs().max() <= out_tol * ref.abs().max()
+    loss = torch.nn.L1Loss()(out, fx["target"].to(device))
+    loss.backward()
+    got = {k: p.grad.detach().cpu() for k, p in net.named_parameters()}
+    if fx["grads"] is not None:
+        gmax = max(float(g.abs().max()) for g in fx["grads"].values())
+        num = sum(float(((got[k] - g) ** 2).sum()) for k, g in fx["grads"].items()) ** 0.5
+        den = sum(float((g ** 2).sum()) for g in fx["grads"].values()) ** 0.5
+        assert num / den <= grad_tol, num / den
+        for k, g in fx["grads"].items():
+            assert (got[k] - g).abs().max() <= grad_tol * gmax, k
+    else:
+        for k, dg in fx["grad_digest"].items():
+            assert abs(float(got[k].norm()) - float(dg["norm"])) <= 2 * grad_tol * float(dg["norm"]) + 1e-6, k
+
+
+@pytest.mark.parametrize("path", SMALL + [BIG], ids=lambda p: os.path.basename(p)[:-3])
+def test_oracle_restatement_matches_reference_golden(path):
+    fx = torch.load(path)
+    sd = _state(fx)
+    out = restated.rbpnet_forward(fx["inputs"], sd, fx["kwargs"]["upscale_factor"], fx["kwargs"]["num_frames"])
+    assert (out - fx["output"]).abs().max() <= 2e-6 * fx["output"].abs().max()
+
+
+def test_state_dict_contract_and_default_init():
+    fx = torch.load(SMALL[0])
+    torch.manual_seed(100)                       # the seed the golden generator constructed the reference class under
+    net = RBPNet(**fx["kwargs"])
+    sd = net.state_dict()
+    assert list(sd) == list(fx["state_dict"])
+    for k, v in fx["state_dict"].items():
+        assert sd[k].shape == v.shape
+        if not k.endswith("act.weight"):         # (the generator perturbed the PReLU slopes after construction)
+            assert torch.equal(sd[k], v), k
+    assert all(float(v) == 0.25 for k, v in sd.items() if k.endswith("act.weight"))      # nn.PReLU() default
+    with pytest.raises(ValueError, match="upscale factor"):
+        RBPNet(1, 1, 16, 8, 3, 1, 3, 5)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        net([torch.zeros(1, 1, 8, 8)] * 3)
+
+
+@pytest.mark.parametrize("path", SMALL, ids=lambda p: os.path.basename(p)[:-3])
+def test_plan_and_recorded_backward_through_the_emulation(path):
+    fx = torch.load(path)
+    net = RBPNet(**fx["kwargs"])
+    net.load_state_dict(_state(fx))
+    net._ops = EmuOps()
+    _check(net, fx, 2e-5, 1e-4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", SMALL, ids=lambda p: os.path.basename(p)[:-3])
+def test_gpu_fp32_mode_matches_reference_golden(path):
+    fx = torch.load(path)
+    net = RBPNet(precision="fp32", **fx["kwargs"])
+    net.load_state_dict(_state(fx))
+    _check(net.cuda(), fx, 1e-4, 1e-4, "cuda")
+
+
+@pytest.mark.gpu
+def test_gpu_bf16_mode_matches_reference_golden():
+    """tcgen05 path (base_filter = feat = 64, x4): output within 5e-2 of the output range, gradient norms within the bf16
+    tolerance (the stated bf16 bars of DESIGN.md §1)"""
+    fx = torch.load(BIG)
+    net = RBPNet(precision="bf16", **fx["kwargs"])
+    net.load_state_dict(_state(fx))
+    _check(net.cuda(), fx, 5e-2, 5e-2, "cuda")
+
+
+def test_misr_train_step_with_rbpnet_equals_reference_step():
+    """the fused MISR step (acdc_misr_trainer.py:8-50: net -> L1 on the centre frame -> backward -> Adam -> PSNR / SSIM) with
+    RBPNet on the kernel emulation against the oracle stepped with torch.optim.Adam: loss per step and weights after 2
+    steps (eps = 1e-4: see tests/test_trainstep_gpu.py on why)"""
+    from vsr_b200.metrics import PSNR
+    from vsr_b200.optim import FlatAdam
+    from vsr_b200.runner import MISRTrainStep
+    fx = torch.load(SMALL[0])
+    kw = fx["kwargs"]
+    net = RBPNet(**kw)
+    net.load_state_dict(_state(fx))
+    net._ops = EmuOps()
+    opt = FlatAdam(net.parameters(), lr=1e-3, eps=1e-4)
+    step = MISRTrainStep(net, [torch.nn.L1Loss()], [1.0], [PSNR()], opt, "acdc")
+    sd = {k: v.clone().requires_grad_(True) for k, v in _state(fx).items()}
+    ref_opt = torch.optim.Adam(list(sd.values()), lr=1e-3, eps=1e-4)
+    for _ in range(2):
+        lv, _ = step.train_step(list(fx["inputs"]), [fx["target"]])
+        out = restated.rbpnet_forward(fx["inputs"], sd, kw["upscale_factor"], kw["num_frames"])
+        loss = restated.l1_loss(out, fx["target"])
+        ref_opt.zero_grad()
+        loss.backward()
+        ref_opt.step()
+        assert abs(float(lv[0]) - float(loss.detach())) <= 2e-5 * abs(float(loss.detach()))
+    for k, p in net.named_parameters():
+        assert (p.data - sd[k].data).abs().max() <= 2e-5, k

@@ -12,6 +12,7 @@ VSR_MAX_SRCS = 8
 
 EPI_BIAS, EPI_RES_PRE, EPI_PRELU, EPI_RELU = 1, 2, 4, 8
 EPI_PRELU_BWD, EPI_RELU_BWD, EPI_OUT2, EPI_SCALE = 16, 32, 64, 128
+EPI_OUT2_SUB = 256
 
 
 class VsrTensor4(C.Structure):
@@ -68,6 +69,7 @@ _SIGS = {
                                        C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "vsr_act_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p,
                               C.c_void_p, C.c_void_p]),
+    "vsr_axpby": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_float, C.c_void_p]),
     "vsr_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p]),
     "vsr_reduce_partials": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                       C.c_void_p]),
@@ -103,6 +105,9 @@ _SIGS = {
     "vsr_cast": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p]),
     "vsr_cine_gather": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p] + [C.c_int32] * 7 +
                         [C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
+    "vsr_downscale_workspace": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
+    "vsr_downscale": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_void_p, C.c_size_t, C.c_void_p]),
     "vsr_copy_window": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                   C.c_int64, C.c_int32, C.c_void_p]),
     "vsr_bn_stats_workspace": (C.c_size_t, [C.c_int32, C.c_int64, C.c_int32]),

@@ -286,6 +286,54 @@ extern "C" int vsr_cast(const void* src, int32_t sd, void* dst, int32_t dd, int6
   return VSR_OK;
 }
 
+namespace vsr {
+namespace {
+template <typename T>
+__global__ void axpby_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ o, long n, float alpha, float beta) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    float v = alpha * Elem<T>::ld(a + i);
+    if (b) v = fmaf(beta, Elem<T>::ld(b + i), v);
+    Elem<T>::st(o + i, v);
+  }
+}
+__global__ void axpby_bf16x8_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ o, long n8,
+                                    float alpha, float beta) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n8; i += (long)gridDim.x * blockDim.x) {
+    const uint4 x = __ldg(a + i);
+    const uint4 y = b ? __ldg(b + i) : make_uint4(0u, 0u, 0u, 0u);
+    uint4 r;
+    r.x = pack_bf16x2(fmaf(beta, bf16_lo(y.x), alpha * bf16_lo(x.x)), fmaf(beta, bf16_hi(y.x), alpha * bf16_hi(x.x)));
+    r.y = pack_bf16x2(fmaf(beta, bf16_lo(y.y), alpha * bf16_lo(x.y)), fmaf(beta, bf16_hi(y.y), alpha * bf16_hi(x.y)));
+    r.z = pack_bf16x2(fmaf(beta, bf16_lo(y.z), alpha * bf16_lo(x.z)), fmaf(beta, bf16_hi(y.z), alpha * bf16_hi(x.z)));
+    r.w = pack_bf16x2(fmaf(beta, bf16_lo(y.w), alpha * bf16_lo(x.w)), fmaf(beta, bf16_hi(y.w), alpha * bf16_hi(x.w)));
+    o[i] = r;
+  }
+}
+}  // namespace
+}  // namespace vsr
+
+extern "C" int vsr_axpby(const void* a, const void* b, void* out, int32_t dtype, int64_t numel, float alpha, float beta,
+                         void* stream) {
+  VSR_CHECK_ARG(a && out && numel >= 0 && (b || beta == 0.f), "vsr_axpby: bad arguments");
+  if (numel == 0) return VSR_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (beta == 0.f) b = nullptr;
+  const bool al16 = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0;
+  if (dtype == VSR_F32) {
+    axpby_kernel<float><<<grid_for(numel, 256), 256, 0, s>>>((const float*)a, (const float*)b, (float*)out, numel, alpha, beta);
+  } else if (dtype == VSR_BF16) {
+    using B = __nv_bfloat16;
+    if (al16 && numel % 8 == 0)
+      axpby_bf16x8_kernel<<<grid_for(numel / 8, 256), 256, 0, s>>>((const uint4*)a, (const uint4*)b, (uint4*)out, numel / 8, alpha, beta);
+    else
+      axpby_kernel<B><<<grid_for(numel, 256), 256, 0, s>>>((const B*)a, (const B*)b, (B*)out, numel, alpha, beta);
+  } else {
+    VSR_CHECK_ARG(false, "vsr_axpby: bad dtype %d", dtype);
+  }
+  VSR_CHECK_LAUNCH("vsr_axpby");
+  return VSR_OK;
+}
+
 extern "C" int vsr_add(const void* a, const void* b, void* out, int32_t dtype, int64_t numel, void* stream) {
   VSR_CHECK_ARG(a && b && out && numel >= 0, "vsr_add: bad arguments");
   if (numel == 0) return VSR_OK;

@@ -152,8 +152,10 @@ __global__ void __launch_bounds__(kThreads) tapgemm_simt_kernel(const __grid_con
         } else {
           Elem<T>::st(a.out + rowoff + jj, v);
         }
-        if (a.epi & VSR_EPI_OUT2)
-          Elem<T>::st(a.out2 + rowoff + jj, v + Elem<T>::ld(a.res2 + rowoff + jj));
+        if (a.epi & VSR_EPI_OUT2) {
+          const float r2 = Elem<T>::ld(a.res2 + rowoff + jj);
+          Elem<T>::st(a.out2 + rowoff + jj, (a.epi & VSR_EPI_OUT2_SUB) ? v - r2 : v + r2);
+        }
       }
     }
   }

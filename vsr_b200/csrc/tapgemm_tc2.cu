@@ -674,15 +674,16 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
               st_shared_v4(tile_addr(out_t, lane, 4 * h + j), o);
             }
             if (epi & VSR_EPI_OUT2) {
-              // out2 = v + res2, staged in place of the res2 tile (every thread owns its row)
+              // out2 = v + res2 (v - res2 with OUT2_SUB), staged in place of the res2 tile (every thread owns its row)
+              const float s2 = (epi & VSR_EPI_OUT2_SUB) ? -1.f : 1.f;
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 uint4 o;
                 const uint4 sq = ld_shared_v4(tile_addr(res2_t, lane, 4 * h + j));
-                o.x = pack_bf16x2(v[8 * j + 0] + bf16_lo(sq.x), v[8 * j + 1] + bf16_hi(sq.x));
-                o.y = pack_bf16x2(v[8 * j + 2] + bf16_lo(sq.y), v[8 * j + 3] + bf16_hi(sq.y));
-                o.z = pack_bf16x2(v[8 * j + 4] + bf16_lo(sq.z), v[8 * j + 5] + bf16_hi(sq.z));
-                o.w = pack_bf16x2(v[8 * j + 6] + bf16_lo(sq.w), v[8 * j + 7] + bf16_hi(sq.w));
+                o.x = pack_bf16x2(fmaf(s2, bf16_lo(sq.x), v[8 * j + 0]), fmaf(s2, bf16_hi(sq.x), v[8 * j + 1]));
+                o.y = pack_bf16x2(fmaf(s2, bf16_lo(sq.y), v[8 * j + 2]), fmaf(s2, bf16_hi(sq.y), v[8 * j + 3]));
+                o.z = pack_bf16x2(fmaf(s2, bf16_lo(sq.z), v[8 * j + 4]), fmaf(s2, bf16_hi(sq.z), v[8 * j + 5]));
+                o.w = pack_bf16x2(fmaf(s2, bf16_lo(sq.w), v[8 * j + 6]), fmaf(s2, bf16_hi(sq.w), v[8 * j + 7]));
                 st_shared_v4(tile_addr(res2_t, lane, 4 * h + j), o);
               }
             }

@@ -40,14 +40,50 @@ def downscale(img, r):
     """reference Downscale (acdc_preprocess.py:111-180) for one [h,w] image."""
     import cv2
     from numpy.fft import fftn, fftshift, ifftn, ifftshift
+    img = np.asarray(img, dtype=np.float64)      # numpy 1.16 (the reference's pin) transforms in double precision
     k = fftshift(fftn(ifftshift(img), norm="ortho"))
     rect = np.zeros_like(k)
     kx, ky = k.shape[0] // 2, k.shape[1] // 2
     lx, ly = k.shape[0] // r, k.shape[1] // r
     rect[kx - lx // 2:kx + (lx - lx // 2), ky - ly // 2:ky + (ly - ly // 2)] = 1
-    out = np.around(np.abs(fftshift(ifftn(ifftshift(rect * k), norm="ortho")))).astype(np.float32)
+    out = np.around(np.abs(fftshift(ifftn(ifftshift(rect * k), norm="ortho"))))
     out = cv2.resize(out, (img.shape[1] // r, img.shape[0] // r), interpolation=cv2.INTER_CUBIC)
-    return np.clip(out.round(), 0, 255)
+    return np.clip(out.round(), 0, 255).astype(np.float32)
+
+
+def lowpass_matrix(n, r):
+    """The n x n complex matrix of the 1-D operator behind Downscale._truncate_kspace (acdc_preprocess.py:141-180):
+    v -> fftshift(ifft(ifftshift(mask * fftshift(fft(ifftshift(v)))))) with mask = 1 on the centred n // r frequencies.
+    The 2-D truncation of a frame X is  P_h @ X @ P_w.T  (all steps are separable).  [n, n, 2] float64 (re, im)."""
+    from numpy.fft import fft, fftshift, ifft, ifftshift
+    mask = np.zeros(n)
+    k, l = n // 2, n // r
+    mask[k - l // 2:k + (l - l // 2)] = 1
+    eye = np.eye(n)
+    P = fftshift(ifft(ifftshift(mask[:, None] * fftshift(fft(ifftshift(eye, axes=0), axis=0), axes=0), axes=0), axis=0), axes=0)
+    return np.stack([P.real, P.imag], axis=-1).astype(np.float64)
+
+
+_LOWPASS = {}
+
+
+def downscale_device(hr, r, ops=None):
+    """`downscale` for a stack of frames [n, h, w] already on the device (fp32, integer-valued): k-space truncation as two
+    complex FP64 GEMMs per frame + integer-ratio bicubic + round + clip in three kernels (csrc/downscale.cu); bit-identical
+    to the reference's Downscale (tests/golden/downscale.pt)."""
+    if ops is None:
+        from .ops import cuda_ops
+        ops = cuda_ops()
+    n, h, w = hr.shape
+    mats = []
+    for size in (h, w):
+        key = (size, r, str(hr.device))
+        if key not in _LOWPASS:
+            _LOWPASS[key] = torch.from_numpy(lowpass_matrix(size, r)).to(hr.device)
+        mats.append(_LOWPASS[key])
+    lr = torch.empty(n, h // r, w // r, device=hr.device)
+    ops.downscale(hr.contiguous().float(), r, mats[0], mats[1], lr)
+    return lr
 
 
 class SyntheticCineDataset(Dataset):
@@ -56,7 +92,7 @@ class SyntheticCineDataset(Dataset):
     patch_size (LR crop for training, RandomCropPatch.size) and seed."""
 
     def __init__(self, downscale_factor, num_frames=5, temporal_order="last", type="train", dataset="acdc",
-                 num_sequences=16, patch_size=(32, 32), seed=0, misr=False):
+                 num_sequences=16, patch_size=(32, 32), seed=0, misr=False, device=None):
         if downscale_factor not in [2, 3, 4]:
             raise ValueError(f"The downscale factor should be 2, 3, 4. Got {downscale_factor}.")
         if temporal_order not in ["last", "middle"]:
@@ -75,7 +111,14 @@ class SyntheticCineDataset(Dataset):
         for _ in range(num_sequences):
             cine = synth_cine(h, w, shape["frames"], rng)
             self.hr.append(cine)
-            self.lr.append(np.stack([downscale(f, self.r) for f in cine]))
+            if device is None:
+                self.lr.append(np.stack([downscale(f, self.r) for f in cine]))
+        if device is not None:
+            # `device`: the reference's Downscale for all frames of all sequences on the GPU (downscale_device: the same
+            # integers as the host path, tests/test_elementwise_gpu.py) instead of one numpy FFT + cv2 call per frame
+            hr_t = torch.from_numpy(np.stack(self.hr).astype(np.float32)).to(device)
+            lr_t = downscale_device(hr_t.view(-1, h, w), self.r).view(num_sequences, shape["frames"], h // self.r, w // self.r)
+            self.lr = list(lr_t.cpu().numpy())
         self.T = shape["frames"]
         self.rng = np.random.default_rng(seed + 1)
         self.data = [(s, t) for s in range(num_sequences) for t in range(self.T)] if type == "train" or misr \

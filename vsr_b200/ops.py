@@ -9,7 +9,7 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import (EPI_BIAS, EPI_OUT2, EPI_PRELU, EPI_PRELU_BWD, EPI_RELU, EPI_RELU_BWD,  # noqa: F401
+from ._lib import (EPI_BIAS, EPI_OUT2, EPI_OUT2_SUB, EPI_PRELU, EPI_PRELU_BWD, EPI_RELU, EPI_RELU_BWD,  # noqa: F401
                    EPI_RES_PRE, EPI_SCALE, VSR_BF16, VSR_F32, VsrTapGemmDesc, VsrTensor4, check)
 
 _DT = {torch.float32: VSR_F32, torch.bfloat16: VSR_BF16}
@@ -308,6 +308,12 @@ class CudaOps:
         check(self.lib.vsr_add(_p(a), _p(b), _p(out), _DT[a.dtype], a.numel(), _stream()), "vsr_add")
         self.launches += 1
 
+    def axpby(self, a, b, out, alpha, beta):
+        """out = alpha * a + beta * b (b may be None when beta == 0)"""
+        _need_cuda(a, b, out)
+        check(self.lib.vsr_axpby(_p(a), _p(b), _p(out), _DT[a.dtype], a.numel(), float(alpha), float(beta), _stream()), "vsr_axpby")
+        self.launches += 1
+
     def reduce_partials(self, partials, rows, row_dst, dst):
         _need_cuda(partials, row_dst, dst)
         check(self.lib.vsr_reduce_partials(_p(partials), rows, partials.shape[-1], _p(row_dst), _p(dst),
@@ -428,6 +434,17 @@ class CudaOps:
                                        out.shape[-2] // r, out.shape[-1] // r, float(mean), float(std), _p(out), _stream()),
               "vsr_cine_gather")
         self.launches += 1
+
+    def downscale(self, hr, r, ph, pw, lr):
+        """lr[i] = Downscale(r)(hr[i]) of acdc_preprocess.py:102-180 for frames [n, h, w] on the device; ph / pw: the complex
+        low-pass matrices of the two axes ([h, h, 2] / [w, w, 2] fp64, data.lowpass_matrix)"""
+        _need_cuda(hr, ph, pw, lr)
+        n, h, w_ = hr.shape
+        nbytes = self.lib.vsr_downscale_workspace(n, h, w_)
+        ws = torch.empty((nbytes + 7) // 8, dtype=torch.float64, device=hr.device)
+        check(self.lib.vsr_downscale(_p(hr), n, h, w_, r, _p(ph), _p(pw), _p(lr), _p(ws), ws.numel() * 8, _stream()),
+              "vsr_downscale")
+        self.launches += 3
 
     # ---- loss / metrics ----------------------------------------------------------------
     def loss_fwd_bwd(self, out, target, kind, param, grad_scale, partials, grad):
