@@ -224,5 +224,7 @@ def test_two_rank_nccl_graphed_step_equals_one_rank_on_the_whole_batch(tmp_path)
     # a rank's loss is the mean over its own patches; the mean over ranks is the whole-batch loss
     for a, b in zip(two["losses"], losses):
         assert abs(a - b) <= 1e-5 * abs(b)
-    assert (two["flat"] - flat).abs().max() <= 2e-5 * flat.abs().max()
+    # (the fp32 summation order of the weight gradients differs: 2 + 2 patches and an all-reduce vs 4 patches in one
+    #  launch; Adam turns 1e-7-relative gradient differences into ~1e-5-relative weight differences - the fp32 bar is 1e-4)
+    assert (two["flat"] - flat).abs().max() <= 1e-4 * flat.abs().max()
     assert torch.equal(two["flat"], two["flat_rank1"])            # both ranks hold the same weights

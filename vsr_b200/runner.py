@@ -190,6 +190,7 @@ class VSRTrainStep:
         if not net._is_flat():
             net._flatten()
         inputs = [x.contiguous() for x in inputs]
+        self._loss_weights_dev(inputs[0].device)
         flat_adam = isinstance(self.optimizer, FlatAdam)
         if flat_adam:
             self.optimizer.prepare_step()
@@ -325,11 +326,16 @@ class VSRTrainStep:
         outs, _ = eng.forward([x.contiguous() for x in inputs], save=False)
         return outs
 
-    def _log(self, acc, lvals):
+    def _loss_weights_dev(self, device):
+        """the loss weights on the device (made outside any graph capture: a host -> device copy is not capturable)"""
         w = self._bufs.get("lw")
-        if w is None:
-            w = torch.tensor(self.loss_weights, device=lvals.device)
+        if w is None or w.device != device:
+            w = torch.tensor(self.loss_weights, device=device)
             self._bufs["lw"] = w
+        return w
+
+    def _log(self, acc, lvals):
+        w = self._loss_weights_dev(lvals.device)
         # the kernels already applied the weights to the gradients; the logged values follow the
         # reference: Loss = sum_i w_i * loss_i, then each unweighted loss_i (acdc_vsr_trainer.py:43)
         acc[0] += (lvals * w).sum()
