@@ -189,8 +189,24 @@ def test_gpu_bf16_close_to_reference(path):
     ref.load_state_dict(_state(fx))
     ref = ref.to("cuda").train()
     torch.nn.L1Loss()(ref([f.cuda() for f in fx["inputs"]]), fx["target"].cuda()).backward()
-    # (24 dense layers: 0.24 in the emulation with bf16 storage)
-    assert float((g16 - ref.flat_grad).norm() / ref.flat_grad.norm()) <= (0.4 if "52" in fx["kwargs"]["backbone"] else 0.25)
+    # The bar is the REFERENCE ALGORITHM's own sensitivity to bf16, measured here on the same fixture: the oracle under
+    # torch.autocast(bfloat16) (convolutions in bf16, BatchNorm in fp32) against the oracle in fp32.  The tcgen05 mode
+    # additionally STORES every activation and gradient map in bf16 and still has to stay within 1.1x that error (measured:
+    # 0.095-0.19 against 0.107-0.23); round 1 quoted the reference-under-autocast figure from a one-off measurement.
+    kw = fx["kwargs"]
+    flat = {}
+    for amp in (False, True):
+        sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
+              for k, v in _state(fx).items()}
+        with torch.autocast("cpu", dtype=torch.bfloat16, enabled=amp):
+            o = restated.dufnet_forward(fx["inputs"], sd, kw["size_filter"], kw["upscale_factor"], training=True)
+            l = restated.l1_loss(o.float(), fx["target"])
+        l.backward()
+        flat[amp] = torch.cat([sd[k].grad.reshape(-1) for k, _ in net.named_parameters()])
+    e_ref = float((flat[True] - flat[False]).norm() / flat[False].norm())
+    e_got = float((g16 - ref.flat_grad).norm() / ref.flat_grad.norm())
+    print(f"{os.path.basename(path)}: bf16 gradient error (global rel L2) {e_got:.3f}; the oracle under autocast(bf16): {e_ref:.3f}")
+    assert e_got <= 1.1 * e_ref
     net.train()
     with torch.no_grad():
         out = net([f.cuda() for f in fx["inputs"]]).cpu()
