@@ -1,5 +1,5 @@
 """Timing attribution of the tcgen05 tap-GEMM: re-times the config-2 convolution shapes with parts of
-the kernel switched off (VSR_TC_DEBUG bits: 1 no epilogue, 16 no epilogue stores, 2 no A loads,
+the kernel switched off (needs the attribution build, `python -m vsr_b200.build --attrib`; VSR_TC_DEBUG bits: 1 no epilogue, 16 no epilogue stores, 2 no A loads,
 4 no B loads, 8 no MMAs).  Results are WRONG by construction; only the times mean anything.
 
     python tools/attrib.py --json gpurun_out/attrib.json
@@ -13,6 +13,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import kbench  # noqa: E402
+from vsr_b200.ops import cuda_ops  # noqa: E402
 
 
 def main():
@@ -28,6 +29,7 @@ def main():
             for mode in args.modes.split(","):
                 os.environ["VSR_TC_DEBUG"] = mode
                 os.environ["VSR_TC_RESIDENT"] = res
+                cuda_ops().lib.vsr_reload_tunables()
                 sys.argv = ["kbench", "--cases", case, "--iters", str(args.iters)]
                 results = []
                 kbench.CASES = {case}
@@ -43,6 +45,7 @@ def main():
                     out.append(r)
                     print(f"{r['kernel']:18s} res={res} dbg={int(mode):2d}  {r['ms'] * 1e3:8.1f} us  {r['tflops']:7.1f} TF/s", flush=True)
     os.environ["VSR_TC_DEBUG"] = "0"
+    cuda_ops().lib.vsr_reload_tunables()
     if args.json:
         with open(args.json, "w") as f:
             json.dump(out, f, indent=1)

@@ -34,6 +34,7 @@ def main(path, out):
             v *= 1e9
         per[key][metric] += v
         launches[key].add(r["ID"])
+    per.pop("spin_kernel", None)                 # bench.py's head-start kernel of the per-kernel pass: not part of a step
     total = sum(d["gpu__time_duration.sum"] for d in per.values())
     res = {}
     for k, d in sorted(per.items(), key=lambda kv: -kv[1]["gpu__time_duration.sum"]):

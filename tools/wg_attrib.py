@@ -1,4 +1,5 @@
-"""Per-role cycle counts of the tcgen05 weight-gradient kernel at the config-2 strided-conv shape."""
+"""Per-role cycle counts of the tcgen05 weight-gradient kernel at the config-2 strided-conv shape
+(needs the attribution build: `python -m vsr_b200.build --attrib`)."""
 import os
 import sys
 
@@ -26,6 +27,7 @@ def main():
     for tall in ("0", "1"):
         os.environ["VSR_WG_TALL"] = tall
         os.environ["VSR_WG_DEBUG"] = "0"
+        ops.lib.vsr_reload_tunables()
         for _ in range(3):
             ops.tapgemm_wgrad(tab, [src], dz, dw, False, ws)
         torch.cuda.synchronize()
@@ -41,6 +43,7 @@ def main():
         ts.sort()
         print(f"wgrad conv8x8s4 tall={tall}: {ts[len(ts) // 2] * 1e3:.1f} us (kernel + split reduce)", flush=True)
         os.environ["VSR_WG_DEBUG"] = "32"
+        ops.lib.vsr_reload_tunables()
         ops.tapgemm_wgrad(tab, [src], dz, dw, False, ws)
         torch.cuda.synchronize()
 

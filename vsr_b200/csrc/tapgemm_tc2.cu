@@ -903,7 +903,7 @@ int tapgemm_tc2_launch(const VsrTapGemmDesc* d, cudaStream_t stream) {
   // residual / saved-activation tiles arrive two chunks ahead; taken when >= 3 pipeline stages remain
   // (nt <= 64: the warp sets alternate tiles, which already hides both)
   int cand[4][2], n_cand = 0;
-  if (d->nt > 64 && !(d->epi & VSR_EPI_OUT2)) {
+  if (d->nt > 64 && !(d->epi & VSR_EPI_OUT2) && tn.tc_epibuf != 1) {      // (VSR_TC_EPIBUF=1: single staging, for A/B runs)
     if (n_in > 0) {
       cand[n_cand][0] = 2; cand[n_cand++][1] = 2;
       cand[n_cand][0] = 1; cand[n_cand++][1] = 2;

@@ -32,6 +32,7 @@ void load_tunables() {
   t.tc_grid = env_int("VSR_TC_GRID");
   t.tc_square = env_int("VSR_TC_SQUARE");
   t.tc_pair = env_int("VSR_TC_PAIR");
+  t.tc_epibuf = env_int("VSR_TC_EPIBUF");
   t.pdl = env_int("VSR_PDL");
   t.wg_debug = env_int("VSR_WG_DEBUG");
   t.wg_tall = env_int("VSR_WG_TALL");
