@@ -266,6 +266,39 @@ def test_upsample_linear_staged_kernels(ac, shape, size):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("shape,r", [((3, 1, 32, 32), 4),          # the global skip of config 2
+                                     ((2, 2, 1, 1), 4), ((1, 1, 1, 70), 2), ((1, 1, 70, 1), 8),   # degenerate axes, clamps everywhere
+                                     ((1, 3, 67, 95), 2), ((2, 1, 129, 61), 4), ((1, 1, 40, 31), 8),   # several warps / strips, ragged
+                                     ((1, 2, 1, 9, 11), 2), ((2, 1, 5, 33, 35), 2), ((1, 1, 3, 18, 31), 4)])   # trilinear
+def test_upsample_integer_ratio_kernels(shape, r):
+    """resample_int.cu (align_corners = False, ratio 2 / 4 / 8: periodic weights, one input column per thread) against torch,
+    forward and backward, and against this library's generic kernels (VSR_UP_GENERIC=1)"""
+    ops, g = _ops(), _g(23)
+    x = torch.randn(*shape, device="cuda", generator=g)
+    mode = "trilinear" if len(shape) == 5 else "bilinear"
+    xr = x.clone().requires_grad_(True)
+    want = F.interpolate(xr, scale_factor=r, mode=mode, align_corners=False)
+    y = torch.full_like(want, float("nan"))
+    ops.upsample_linear(x, y, False)
+    assert (y - want).abs().max() <= 1e-5
+    dy = torch.randn(want.shape, device="cuda", generator=g)
+    want.backward(dy)
+    dx = torch.full_like(x, float("nan"))
+    ops.upsample_linear_bwd(dy, dx, False)
+    assert (dx - xr.grad).abs().max() <= 2e-5 * max(1.0, float(xr.grad.abs().max()))
+    os.environ["VSR_UP_GENERIC"] = "1"
+    ops.lib.vsr_reload_tunables()
+    try:
+        y2, dx2 = torch.empty_like(y), torch.empty_like(dx)
+        ops.upsample_linear(x, y2, False)
+        ops.upsample_linear_bwd(dy, dx2, False)
+    finally:
+        del os.environ["VSR_UP_GENERIC"]
+        ops.lib.vsr_reload_tunables()
+    assert (y - y2).abs().max() <= 1e-5 and (dx - dx2).abs().max() <= 2e-4 * max(1.0, float(dx2.abs().max()))
+
+
+@pytest.mark.gpu
 def test_device_cine_loader_bit_exact_vs_host_loader():
     """vsr_cine_gather (window + flips + crop + Normalize + collate on the device) against the host loader: bit-exact"""
     import torch

@@ -452,6 +452,12 @@ __global__ void __launch_bounds__(256) upsample_linear_bwd_kernel(const float* _
 }  // namespace
 }  // namespace vsr
 
+namespace vsr {
+// resample_int.cu: integer power-of-two ratios with align_corners = False; false when the shape is not covered
+bool upsample_int_fwd(const float* x, float* y, int nc, int d, int h, int w, int od, int oh, int ow, int ac, cudaStream_t s);
+bool upsample_int_bwd(const float* dy, float* dx, int nc, int d, int h, int w, int od, int oh, int ow, int ac, cudaStream_t s);
+}  // namespace vsr
+
 using namespace vsr;
 
 extern "C" int vsr_pixel_shuffle(const float* x, float* y, int32_t n, int32_t c, int32_t h, int32_t w_,
@@ -467,6 +473,10 @@ extern "C" int vsr_pixel_shuffle(const float* x, float* y, int32_t n, int32_t c,
 extern "C" int vsr_upsample_linear(const float* x, float* y, int32_t nc, int32_t d, int32_t h, int32_t w_,
                                    int32_t od, int32_t oh, int32_t ow, int align_corners, void* stream) {
   VSR_CHECK_ARG(x && y && nc > 0 && d > 0 && h > 0 && w_ > 0 && od > 0 && oh > 0 && ow > 0, "vsr_upsample_linear: bad arguments");
+  if (tunables().up_generic != 1 && upsample_int_fwd(x, y, nc, d, h, w_, od, oh, ow, align_corners, static_cast<cudaStream_t>(stream))) {
+    VSR_CHECK_LAUNCH("vsr_upsample_linear(integer ratio)");
+    return VSR_OK;
+  }
   VSR_CHECK_SUPPORTED((long)nc * od <= 65535 && oh <= 65535, "vsr_upsample_linear: nc*od and oh must be <= 65535");
   dim3 grid((ow + kUpTile - 1) / kUpTile, (oh + kRowsPerBlock - 1) / kRowsPerBlock, nc * od);
   // staged kernel when the input rows of a block (32 output rows x 1024 output columns) fit its staging buffer - any
@@ -484,6 +494,10 @@ extern "C" int vsr_upsample_linear(const float* x, float* y, int32_t nc, int32_t
 extern "C" int vsr_upsample_linear_bwd(const float* dy, float* dx, int32_t nc, int32_t d, int32_t h, int32_t w_,
                                        int32_t od, int32_t oh, int32_t ow, int align_corners, void* stream) {
   VSR_CHECK_ARG(dy && dx && nc > 0 && d > 0 && h > 0 && w_ > 0 && od > 0 && oh > 0 && ow > 0, "vsr_upsample_linear_bwd: bad arguments");
+  if (tunables().up_generic != 1 && upsample_int_bwd(dy, dx, nc, d, h, w_, od, oh, ow, align_corners, static_cast<cudaStream_t>(stream))) {
+    VSR_CHECK_LAUNCH("vsr_upsample_linear_bwd(integer ratio)");
+    return VSR_OK;
+  }
   VSR_CHECK_SUPPORTED((long)nc * d <= 65535 && h <= 65535, "vsr_upsample_linear_bwd: nc*d and h must be <= 65535");
   // staged transposed stencil for up-scaling by at most 8 per axis (at most kBwdK outputs touch an input column and the
   // dy segment of 256 input columns fits kBwdSeg); the generic gather kernel otherwise
