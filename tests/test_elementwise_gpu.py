@@ -49,6 +49,46 @@ def test_conv3x3_first_and_bwd(dtype, cin):
     assert (rs[0][1] - rs[1][1]).abs().max() <= 1e-4 * rs[1][1].abs().max()
 
 
+@pytest.mark.parametrize("cout,n,h,w,slope", [(256, 5, 32, 32, 0.2), (256, 3, 19, 23, -0.3), (128, 2, 33, 17, 0.0), (64, 7, 9, 11, 0.25),
+                                             (32, 1, 16, 17, None)])
+def test_conv3x3_first_tensor_core_path(cout, n, h, w, slope):
+    """firstconv_mma.cu (bf16 maps, split-bf16 operands on mma.sync) against an fp64 convolution, and against this library's
+    CUDA-core kernels (VSR_FC_SIMT=1): forward within one bf16 rounding of the exact result, weight / bias gradient at fp32
+    accuracy; several CTA tiles, ragged last tile, slope > 0 / < 0 / = 0 / no activation"""
+    ops, g = _ops(), _g(5)
+    x = torch.randn(n, 1, h, w, device="cuda", generator=g)
+    wt = torch.randn(cout, 1, 3, 3, device="cuda", generator=g) * 0.3
+    b = torch.randn(cout, device="cuda", generator=g)
+    a = None if slope is None else torch.tensor([slope], device="cuda")
+    z = F.conv2d(x.double(), wt.double(), b.double(), padding=1).permute(0, 2, 3, 1)
+    want = z if slope is None else torch.where(z > 0, z, z * (slope if slope != 0.0 else 2.0 ** -24))
+    dz = torch.randn(n, h, w, cout, device="cuda", generator=g).to(torch.bfloat16)
+    res = {}
+    for simt in ("0", "1"):
+        os.environ["VSR_FC_SIMT"] = simt
+        ops.lib.vsr_reload_tunables()
+        try:
+            y = torch.zeros(n, h, w, cout, device="cuda", dtype=torch.bfloat16)
+            ops.conv3x3_first(x, wt, b, a, y)
+            dw, db = torch.zeros_like(wt), torch.zeros_like(b)
+            ws = torch.empty(ops.conv3x3_first_bwd_workspace(x, cout) // 4 + 4, device="cuda")
+            ops.conv3x3_first_bwd(x, dz, dw, db, False, ws)
+            res[simt] = (y.double(), dw, db)
+        finally:
+            del os.environ["VSR_FC_SIMT"]
+            ops.lib.vsr_reload_tunables()
+    xd = F.unfold(x.double(), 3, padding=1).transpose(1, 2).reshape(-1, 9)                   # [pixels][9]
+    dw_ref = (dz.double().reshape(-1, cout).t() @ xd).reshape(cout, 1, 3, 3)
+    db_ref = dz.double().sum((0, 1, 2))
+    for simt in ("0", "1"):
+        y, dw, db = res[simt]
+        rnd = 2.0 ** -8 if slope is None or slope >= 0 else 2.0 ** -6                         # one bf16 rounding (+ the sign tag in the LSB)
+        # (+ the dropped xl * wl term of the split operands: 2^-16 of the sum of |x w|)
+        assert ((y - want).abs() <= rnd * want.abs() + (1e-4 if simt == "0" else 1e-6)).all(), simt
+        assert (dw.double() - dw_ref).abs().max() <= 2e-5 * dw_ref.abs().max(), simt
+        assert (db.double() - db_ref).abs().max() <= 2e-5 * db_ref.abs().max(), simt
+
+
 @pytest.mark.parametrize("r,c,h,w", [(4, 64, 11, 9), (3, 64, 13, 12), (2, 128, 20, 17), (8, 64, 5, 9)])
 def test_conv3x3_last_tensor_core_path_several_tiles(r, c, h, w):
     """bf16 maps through lastconv_mma.cu with more than one 32x32 output tile per image and partial tiles on both axes"""

@@ -44,8 +44,11 @@ def _check(net, fx, out_tol, grad_tol, device="cpu"):
         for k, g in fx["grads"].items():
             assert (got[k] - g).abs().max() <= grad_tol * gmax, k
     else:
+        # per-parameter norms; the scalar PReLU slopes have gradients ~1e-3 of the weights' (sums of cancelling terms), so the
+        # absolute slack is tied to the global gradient norm: 1e-2 of what the global L2 bar itself allows
+        total = sum(float(dg["norm"]) ** 2 for dg in fx["grad_digest"].values()) ** 0.5
         for k, dg in fx["grad_digest"].items():
-            assert abs(float(got[k].norm()) - float(dg["norm"])) <= 2 * grad_tol * float(dg["norm"]) + 1e-6, k
+            assert abs(float(got[k].norm()) - float(dg["norm"])) <= 2 * grad_tol * float(dg["norm"]) + 1e-2 * grad_tol * total, k
 
 
 @pytest.mark.parametrize("path", SMALL + [BIG], ids=lambda p: os.path.basename(p)[:-3])

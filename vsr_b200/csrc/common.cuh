@@ -16,7 +16,7 @@ int num_sms();
 // tuning overrides from the environment (VSR_TC_*, VSR_WG_*, VSR_PDL; not part of the ABI): read once, -1 = unset.
 // vsr_reload_tunables() re-reads them (tests / tools); the launch path never calls getenv.
 struct Tunables {
-  int tc_debug, tc_tall, tc_tall_stages, tc_resident, tc_stages, tc_grid, tc_square, tc_pair, tc_epibuf, pdl, wg_debug, wg_tall, up_generic;
+  int tc_debug, tc_tall, tc_tall_stages, tc_resident, tc_stages, tc_grid, tc_square, tc_pair, tc_epibuf, pdl, wg_debug, wg_tall, up_generic, fc_simt;
 };
 const Tunables& tunables();      // tma_host.cu
 

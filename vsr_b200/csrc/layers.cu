@@ -1074,6 +1074,14 @@ int fill_geom(LastGeom* g, int n, int h, int w, int r, int c, int cout, const in
 }  // namespace
 }  // namespace vsr
 
+namespace vsr {      // firstconv_mma.cu: bf16 output, cin == 1 on the tensor cores (mma.sync, split-bf16 operands)
+bool firstconv_mma_supported(int dtype, int cin, int cout);
+bool firstconv_mma_bwd_supported(int dtype, int cin, int cout);
+void firstconv_mma_fwd(const float* x, int n, int h, int w, const float* wt, const float* bias, const float* slope, void* y,
+                       int cout, cudaStream_t s);
+int firstconv_mma_bwd(const float* x, int n, int h, int w, const void* dz, int cout, float* ws, int max_blocks, cudaStream_t s);
+}  // namespace vsr
+
 using namespace vsr;
 
 extern "C" int vsr_conv3x3_first(const float* x, int32_t n, int32_t cin, int32_t h, int32_t w_, const float* w,
@@ -1085,6 +1093,11 @@ extern "C" int vsr_conv3x3_first(const float* x, int32_t n, int32_t cin, int32_t
   const size_t smem = ((size_t)cin * 9 * cout + cout) * sizeof(float);
   VSR_CHECK_SUPPORTED(smem <= 48 * 1024, "vsr_conv3x3_first: cin*cout too large for shared memory");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (firstconv_mma_supported(dtype, cin, cout) && (long)n * h * w_ < 2147000000l) {
+    firstconv_mma_fwd(x, n, h, w_, w, bias, slope, y, cout, s);
+    VSR_CHECK_LAUNCH("vsr_conv3x3_first(mma)");
+    return VSR_OK;
+  }
   if (cin == 1 && cout <= 256 && (dtype == VSR_F32 || dtype == VSR_BF16)) {
     const int grid2 = grid_for((long)n * h * w_, 8 * 8, 2);      // >= 8 pixels per warp
     if (dtype == VSR_F32) conv_first2_kernel<float><<<grid2, 256, 0, s>>>(x, n, h, w_, w, bias, slope, (float*)y, cout);
@@ -1120,6 +1133,15 @@ extern "C" int vsr_conv3x3_first_bwd(const float* x, int32_t n, int32_t cin, int
                 "vsr_conv3x3_first_bwd: workspace too small");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const long pixels = (long)n * h * w_;
+  if (firstconv_mma_bwd_supported(dtype, cin, cout) && pixels < 2147000000l) {
+    float* wsm = static_cast<float*>(workspace);
+    const int blocks = firstconv_mma_bwd(x, n, h, w_, dz, cout, wsm, (int)((pixels + kF2Pix - 1) / kF2Pix), s);
+    VSR_CHECK_LAUNCH("vsr_conv3x3_first_bwd(mma)");
+    const int nout = cout * 10;
+    rows_reduce_kernel<<<(nout + 63) / 64, 256, 0, s>>>(wsm, blocks, nout, dw, db, cout, accumulate);
+    VSR_CHECK_LAUNCH("vsr_conv3x3_first_bwd_final(mma)");
+    return VSR_OK;
+  }
   if (cin == 1 && cout <= 256 && (dtype == VSR_F32 || dtype == VSR_BF16)) {
     int blocks2 = (int)((pixels + kF2Pix - 1) / kF2Pix);
     if (blocks2 > 2 * num_sms()) blocks2 = 2 * num_sms();     // two 1024-thread blocks per SM; every block walks its chunks

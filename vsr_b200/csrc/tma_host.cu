@@ -36,6 +36,7 @@ void load_tunables() {
   t.pdl = env_int("VSR_PDL");
   t.wg_debug = env_int("VSR_WG_DEBUG");
   t.wg_tall = env_int("VSR_WG_TALL");
+  t.fc_simt = env_int("VSR_FC_SIMT");           // 1: CUDA-core first convolution in bf16 mode too (A/B)
   t.up_generic = env_int("VSR_UP_GENERIC");     // 1: skip the integer-ratio up-sampling kernels (A/B)
   g_tunables = t;
 }
