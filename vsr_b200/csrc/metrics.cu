@@ -175,17 +175,26 @@ __global__ void __launch_bounds__(kSWarps * 32) ssim_partial_kernel(
     for (int k = 0; k < kWin; ++k) wv[q][k] = 0.f;
   float acc = 0.f;
   const bool col_ok = (x0 + lane) < ow;
+  // the row segment [x0, x0 + 42) (denormalised) of input row y0 + r: lanes 0..31 and, for the last 10 columns, lanes 0..9
+  const int xa = x0 + lane, xb = x0 + 32 + lane;
+  const bool ok_a = xa < w, ok_b = lane < kWin - 1 && xb < w;
+  auto fetch = [&](int r, float& a0, float& b0, float& a1, float& b1) {
+    a0 = b0 = a1 = b1 = 0.f;
+    if (r >= rows_in) return;
+    const size_t ro = (size_t)(y0 + r) * w;
+    if (ok_a) { a0 = __ldg(o + ro + xa); b0 = __ldg(t + ro + xa); }
+    if (ok_b) { a1 = __ldg(o + ro + xb); b1 = __ldg(t + ro + xb); }
+  };
+  float na0, nb0, na1, nb1;                                // the next row, in flight while this one is filtered
+  fetch(0, na0, nb0, na1, nb1);
   for (int base = 0; base < rows_in; base += kWin) {
 #pragma unroll
     for (int j = 0; j < kWin; ++j) {
       const int r = base + j;
       if (r < rows_in) {                                   // warp-uniform
-        const int yy = y0 + r;
-        // stage the row segment [x0, x0 + 42) (denormalised) for this warp
-        const int xa = x0 + lane, xb = x0 + 32 + lane;
-        float a0 = 0.f, b0 = 0.f, a1 = 0.f, b1 = 0.f;
-        if (xa < w) { a0 = denorm(__ldg(o + (size_t)yy * w + xa), mean, std, denorm_on); b0 = denorm(__ldg(t + (size_t)yy * w + xa), mean, std, denorm_on); }
-        if (lane < kWin - 1 && xb < w) { a1 = denorm(__ldg(o + (size_t)yy * w + xb), mean, std, denorm_on); b1 = denorm(__ldg(t + (size_t)yy * w + xb), mean, std, denorm_on); }
+        const float a0 = ok_a ? denorm(na0, mean, std, denorm_on) : 0.f, b0 = ok_a ? denorm(nb0, mean, std, denorm_on) : 0.f;
+        const float a1 = ok_b ? denorm(na1, mean, std, denorm_on) : 0.f, b1 = ok_b ? denorm(nb1, mean, std, denorm_on) : 0.f;
+        fetch(r + 1, na0, nb0, na1, nb1);
         __syncwarp();
         bx[lane] = a0; by[lane] = b0;
         if (lane < kWin - 1) { bx[32 + lane] = a1; by[32 + lane] = b1; }

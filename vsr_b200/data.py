@@ -266,6 +266,15 @@ class DeviceStager:
         if isinstance(obj, dict):
             return {k: self._move(v) for k, v in obj.items()}
         if isinstance(obj, (list, tuple)):
+            frames = list(obj)
+            if (self.device.type == "cuda" and len(frames) > 1 and all(isinstance(v, torch.Tensor) and not v.is_cuda for v in frames)
+                    and all(v.shape == frames[0].shape and v.dtype == frames[0].dtype for v in frames)):
+                # the T frames of a sequence land in ONE [T, ...] device buffer (a copy per frame, no host-side stack):
+                # the fused step then takes all frames with one device copy and one loss / metric launch
+                buf = torch.empty(len(frames), *frames[0].shape, dtype=frames[0].dtype, device=self.device)
+                for dst, v in zip(buf.unbind(0), frames):
+                    dst.copy_(v if v.is_pinned() else v.pin_memory(), non_blocking=True)
+                return type(obj)(buf.unbind(0))
             return type(obj)(self._move(v) for v in obj)
         return obj
 
