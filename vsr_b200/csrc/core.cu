@@ -165,8 +165,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, lo
 #pragma unroll
   for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
   if (ro < rpp) {
-    for (long r = r0 + ro; r < r1; r += rpp) {
-      const uint4 q = __ldg(reinterpret_cast<const uint4*>(x + r * c + cg * VEC));
+    auto add = [&](const uint4& q) {
       if constexpr (sizeof(T) == 2) {
         acc[0] += bf16_lo(q.x); acc[1] += bf16_hi(q.x); acc[2] += bf16_lo(q.y); acc[3] += bf16_hi(q.y);
         acc[4] += bf16_lo(q.z); acc[5] += bf16_hi(q.z); acc[6] += bf16_lo(q.w); acc[7] += bf16_hi(q.w);
@@ -174,7 +173,16 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, lo
         acc[0] += __uint_as_float(q.x); acc[1] += __uint_as_float(q.y);
         acc[2] += __uint_as_float(q.z); acc[3] += __uint_as_float(q.w);
       }
+    };
+    long r = r0 + ro;
+    for (; r + 3l * rpp < r1; r += 4l * rpp) {             // four loads in flight, added in row order
+      uint4 q[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) q[u] = __ldg(reinterpret_cast<const uint4*>(x + (r + (long)u * rpp) * c + cg * VEC));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) add(q[u]);
     }
+    for (; r < r1; r += rpp) add(__ldg(reinterpret_cast<const uint4*>(x + r * c + cg * VEC)));
 #pragma unroll
     for (int i = 0; i < VEC; ++i) sm[ro * c + cg * VEC + i] = acc[i];
   }
@@ -198,25 +206,31 @@ __global__ void colsum_scalar_kernel(const T* __restrict__ x, long rows, int c, 
     ws[(size_t)blockIdx.x * c + col] = s;
   }
 }
-// pass 2: one block; thread (part, col) sums every parts-th partial row, then a fixed-order fold
+// pass 2: a block owns 64 columns; thread (part, col) sums every 4th partial row (eight loads in flight, fixed order), then
+// a fixed-order fold over the four parts
 __global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ ws, int blocks, int c,
                                                           float* __restrict__ db, int accumulate) {
-  extern __shared__ float sm[];           // [parts][cw]
-  const int cw = c < 256 ? c : 256;       // columns per pass
-  const int parts = 256 / cw;
-  for (int c0 = 0; c0 < c; c0 += cw) {
-    const int col = c0 + threadIdx.x % cw, part = threadIdx.x / cw;
-    float s = 0.f;
-    if (col < c && part < parts)
-      for (int b = part; b < blocks; b += parts) s += ws[(size_t)b * c + col];
-    __syncthreads();
-    if (part < parts) sm[part * cw + threadIdx.x % cw] = s;
-    __syncthreads();
-    if (threadIdx.x < cw && c0 + threadIdx.x < c) {
-      float t = accumulate ? db[c0 + threadIdx.x] : 0.f;
-      for (int q = 0; q < parts; ++q) t += sm[q * cw + threadIdx.x];
-      db[c0 + threadIdx.x] = t;
+  __shared__ float sm[4][64];
+  const int col = blockIdx.x * 64 + (threadIdx.x & 63), part = threadIdx.x >> 6;
+  float s = 0.f;
+  if (col < c) {
+    int b = part;
+    for (; b + 28 < blocks; b += 32) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldg(ws + (size_t)(b + 4 * u) * c + col);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s += v[u];
     }
+    for (; b < blocks; b += 4) s += ws[(size_t)b * c + col];
+  }
+  sm[part][threadIdx.x & 63] = s;
+  __syncthreads();
+  if (threadIdx.x < 64 && col < c) {
+    float t = accumulate ? db[col] : 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) t += sm[q][threadIdx.x];
+    db[col] = t;
   }
 }
 
@@ -457,7 +471,7 @@ extern "C" int vsr_act_bwd(const void* dy, const void* y, void* dz, int32_t dtyp
 
 static int colsum_blocks(int64_t rows) {
   int64_t b = (rows + 255) / 256;
-  const int64_t cap = (int64_t)num_sms();
+  const int64_t cap = 4 * (int64_t)num_sms();            // four 256-thread blocks per SM, four 16-byte loads in flight each
   if (b > cap) b = cap;
   if (b < 1) b = 1;
   return (int)b;
@@ -498,7 +512,7 @@ extern "C" int vsr_colsum(const void* x, int32_t dtype, int64_t rows, int32_t c,
   else
     VSR_CHECK_ARG(false, "vsr_colsum: bad dtype %d", dtype);
   VSR_CHECK_LAUNCH("vsr_colsum");
-  colsum_final_kernel<<<1, 256, 256 * sizeof(float), s>>>(ws, blocks, c, db, accumulate);
+  colsum_final_kernel<<<(c + 63) / 64, 256, 0, s>>>(ws, blocks, c, db, accumulate);
   VSR_CHECK_LAUNCH("vsr_colsum_final");
   return VSR_OK;
 }
