@@ -833,199 +833,6 @@ __global__ void __launch_bounds__(256, 2) conv_last2_dw_kernel(const T* __restri
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// last conv, v3 (bf16 features, C == 64, cout == 1, sub-block 4x4): as v2, but all 36 halo pixels of
-// the item are requested before the first FMA (36 independent 128-byte warp loads in flight instead
-// of 6: v2 ran at ~12 % of HBM bandwidth, latency-bound) and every pixel is unpacked once.
-// ------------------------------------------------------------------------------------------
-template <bool ZR4>
-__device__ __forceinline__ void load_halo36(const __nv_bfloat16* __restrict__ x, const LastGeom2& g, const HaloIdx& hi,
-                                            int c0, uint32_t (&raw)[kSBMax + 2][kSBMax + 2]) {
-#pragma unroll
-  for (int i = 0; i < kSBMax + 2; ++i)
-#pragma unroll
-    for (int j = 0; j < kSBMax + 2; ++j)
-      raw[i][j] = __ldg(reinterpret_cast<const uint32_t*>(x + halo_off<ZR4>(g, hi, i, j) + c0));
-#pragma unroll
-  for (int i = 0; i < kSBMax + 2; ++i)
-#pragma unroll
-    for (int j = 0; j < kSBMax + 2; ++j)
-      raw[i][j] = (((hi.rowok >> i) & 1u) && ((hi.colok >> j) & 1u)) ? raw[i][j] : 0u;
-}
-
-template <bool ZR4>
-__global__ void __launch_bounds__(256, 2) conv_last3_kernel(const __nv_bfloat16* __restrict__ x,
-                                                           const __grid_constant__ LastGeom2 g,
-                                                           const float* __restrict__ wt, const float* __restrict__ bias,
-                                                           float* __restrict__ y) {
-  const int lane = threadIdx.x & 31;
-  const int H = g.h * g.r, W = g.w * g.r;
-  const long total = (long)g.n * g.h * g.w * g.nsb * g.nsb;
-  const long warp0 = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
-  const float b0 = bias ? __ldg(bias) : 0.f;
-  const int c0 = lane * 2;
-  float wr[9][2];                       // this lane's two channels of the 3x3 kernel (wt is [1][C][3][3])
-#pragma unroll
-  for (int t = 0; t < 9; ++t) {
-    wr[t][0] = __ldg(wt + (size_t)c0 * 9 + t);
-    wr[t][1] = __ldg(wt + (size_t)(c0 + 1) * 9 + t);
-  }
-  for (long item = warp0; item < total; item += nwarps) {
-    const SubBlock sbk = decode_sb(g, item);
-    HaloIdx hi;
-    halo_index<ZR4>(g, sbk, &hi);
-    uint32_t raw[kSBMax + 2][kSBMax + 2];
-    load_halo36<ZR4>(x, g, hi, c0, raw);
-    float acc[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-#pragma unroll
-    for (int i = 0; i < kSBMax + 2; ++i)
-#pragma unroll
-      for (int j = 0; j < kSBMax + 2; ++j) {
-        const float v0 = bf16_lo(raw[i][j]), v1 = bf16_hi(raw[i][j]);
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-          for (int kx = 0; kx < 3; ++kx) {
-            const int oy = i - ky, ox = j - kx;               // output pixel fed by halo (i,j) through tap (ky,kx)
-            if (oy >= 0 && oy < kSBMax && ox >= 0 && ox < kSBMax)
-              acc[oy * kSBMax + ox] = fmaf(v1, wr[ky * 3 + kx][1], fmaf(v0, wr[ky * 3 + kx][0], acc[oy * kSBMax + ox]));
-          }
-      }
-    const float tot = transpose_reduce16(acc, lane);
-    const int q = lane >> 1, oy = q / kSBMax, ox = q % kSBMax;
-    if ((lane & 1) == 0 && oy < g.sb && ox < g.sb)
-      y[((size_t)sbk.ni * H + sbk.Y0 + oy) * W + sbk.X0 + ox] = tot + b0;
-  }
-}
-
-// weight / bias gradient of the last conv, v3: the forward's all-at-once halo, accumulators
-// dw[tap][2 channels] per lane -> block fold (fixed warp order) -> ws -> final reduce.
-template <bool ZR4>
-__global__ void __launch_bounds__(256, 2) conv_last3_dw_kernel(const __nv_bfloat16* __restrict__ x,
-                                                              const __grid_constant__ LastGeom2 g,
-                                                              const float* __restrict__ dy, float* __restrict__ ws) {
-  extern __shared__ float sm[];    // block partial [nw][9*C + 1]
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  const int H = g.h * g.r, W = g.w * g.r;
-  const long total = (long)g.n * g.h * g.w * g.nsb * g.nsb;
-  const long warp0 = (long)blockIdx.x * nw + warp;
-  const long nwarps = (long)gridDim.x * nw;
-  const int c0 = lane * 2;
-  float dwacc[9][2];
-#pragma unroll
-  for (int t = 0; t < 9; ++t) dwacc[t][0] = dwacc[t][1] = 0.f;
-  float dbacc = 0.f;
-  for (long item = warp0; item < total; item += nwarps) {
-    const SubBlock sbk = decode_sb(g, item);
-    HaloIdx hi;
-    halo_index<ZR4>(g, sbk, &hi);
-    uint32_t raw[kSBMax + 2][kSBMax + 2];
-    load_halo36<ZR4>(x, g, hi, c0, raw);
-    float gc[16];
-#pragma unroll
-    for (int oy = 0; oy < kSBMax; ++oy)
-#pragma unroll
-      for (int ox = 0; ox < kSBMax; ++ox) {
-        const bool ok = oy < g.sb && ox < g.sb;
-        const int Yc = min(sbk.Y0 + oy, H - 1), Xc = min(sbk.X0 + ox, W - 1);
-        const float t = __ldg(dy + ((size_t)sbk.ni * H + Yc) * W + Xc);
-        gc[oy * kSBMax + ox] = ok ? t : 0.f;
-        dbacc += ok ? t : 0.f;
-      }
-#pragma unroll
-    for (int i = 0; i < kSBMax + 2; ++i)
-#pragma unroll
-      for (int j = 0; j < kSBMax + 2; ++j) {
-        const float v0 = bf16_lo(raw[i][j]), v1 = bf16_hi(raw[i][j]);
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-          for (int kx = 0; kx < 3; ++kx) {
-            const int oy = i - ky, ox = j - kx;
-            if (oy >= 0 && oy < kSBMax && ox >= 0 && ox < kSBMax) {
-              dwacc[ky * 3 + kx][0] = fmaf(gc[oy * kSBMax + ox], v0, dwacc[ky * 3 + kx][0]);
-              dwacc[ky * 3 + kx][1] = fmaf(gc[oy * kSBMax + ox], v1, dwacc[ky * 3 + kx][1]);
-            }
-          }
-      }
-  }
-  const int wsz = 9 * g.c, psz = wsz + 1;
-#pragma unroll
-  for (int t = 0; t < 9; ++t) {
-    sm[(size_t)warp * psz + t * g.c + c0] = dwacc[t][0];
-    sm[(size_t)warp * psz + t * g.c + c0 + 1] = dwacc[t][1];
-  }
-  if (lane == 0) sm[(size_t)warp * psz + wsz] = dbacc;   // every lane accumulated the same db
-  __syncthreads();
-  for (int i = threadIdx.x; i < psz; i += blockDim.x) {
-    float s2 = 0.f;
-    for (int wv = 0; wv < nw; ++wv) s2 += sm[(size_t)wv * psz + i];
-    ws[(size_t)blockIdx.x * psz + i] = s2;
-  }
-}
-
-// data gradient of the last conv, v3 (bf16, C == 64, r == 4 with Z-order slots, cout == 1): one warp = one LR
-// block (4x4 HR pixels = 2 KB contiguous).  Lane = (pixel row pg = lane >> 3, channel octet cl = lane & 7): it
-// writes 16 bytes (8 channels) of the four pixels of its row, so a warp store covers 512 contiguous-by-128
-// bytes instead of 128, and the output address needs the centre block only.
-__global__ void __launch_bounds__(256, 2) conv_last3_dx_kernel(const __grid_constant__ LastGeom2 g,
-                                                              const float* __restrict__ wt, const float* __restrict__ dy,
-                                                              __nv_bfloat16* __restrict__ dx) {
-  const int lane = threadIdx.x & 31;
-  const int pg = lane >> 3, cl = lane & 7;
-  const int H = g.h * 4, W = g.w * 4;
-  const long total = (long)g.n * g.h * g.w;
-  const long warp0 = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
-  float wr[9][8];                       // this lane's 8 channels of the 3x3 kernel (wt is [1][C][3][3])
-#pragma unroll
-  for (int t = 0; t < 9; ++t)
-#pragma unroll
-    for (int q = 0; q < 8; ++q) wr[t][q] = __ldg(wt + (size_t)(cl * 8 + q) * 9 + t);
-  for (long item = warp0; item < total; item += nwarps) {
-    const int bx = (int)(item % g.w);
-    const int by = (int)((item / g.w) % g.h);
-    const int ni = (int)(item / ((long)g.w * g.h));
-    const int Y = by * 4 + pg, X0 = bx * 4;
-    // dy halo of this lane's pixel row: rows Y-1..Y+1, columns X0-1..X0+4 (zero outside the image)
-    float gy[3][6];
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-      for (int j = 0; j < 6; ++j) {
-        const int yy = Y + i - 1, xx = X0 + j - 1;
-        const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
-        const float t = __ldg(dy + ((size_t)ni * H + min(max(yy, 0), H - 1)) * W + min(max(xx, 0), W - 1));
-        gy[i][j] = ok ? t : 0.f;
-      }
-    __nv_bfloat16* blk = dx + (((size_t)ni * g.h + by) * g.w + bx) * 16 * (size_t)g.c + cl * 8;
-#pragma unroll
-    for (int ox = 0; ox < 4; ++ox) {
-      float d[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) d[q] = 0.f;
-#pragma unroll
-      for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          // dx(P) = sum_tap dy(P - off(tap)) w[tap]: P - off = (Y + 1 - ky, X + 1 - kx)
-          const float gn = gy[2 - ky][ox + 2 - kx];
-#pragma unroll
-          for (int q = 0; q < 8; ++q) d[q] = fmaf(gn, wr[ky * 3 + kx][q], d[q]);
-        }
-      uint4 o;
-      o.x = pack_bf16x2(d[0], d[1]); o.y = pack_bf16x2(d[2], d[3]);
-      o.z = pack_bf16x2(d[4], d[5]); o.w = pack_bf16x2(d[6], d[7]);
-      // slot of phase (pg, ox) in the Z-order layout: ((py>>1)<<3) | ((px>>1)<<2) | ((py&1)<<1) | (px&1)
-      const int slot = ((pg >> 1) << 3) | ((ox >> 1) << 2) | ((pg & 1) << 1) | (ox & 1);
-      *reinterpret_cast<uint4*>(blk + (size_t)slot * g.c) = o;
-    }
-  }
-}
-
 bool last2_supported(int r, int c, int cout) { return cout == 1 && (c == 32 || c == 64 || c == 128) && r >= 2 && r <= 8; }
 
 int fill_geom2(LastGeom2* g, int n, int h, int w, int r, int c, const int32_t* phase_yx_host) {
@@ -1200,11 +1007,8 @@ extern "C" int vsr_conv3x3_last(const void* x, int32_t dtype, int32_t n, int32_t
     const int grid2 = grid_for(items, 8, 8);
     const size_t smem2 = (size_t)9 * c * sizeof(float);
     if (dtype == VSR_BF16) {
-      // (the compile-time-phase variant <.., true> spills under the 128-register cap here and measured slower;
-      //  the backward kernels use it)
-      if (c == 64 && g2.sb == 4 && geom_is_zr4(g2)) conv_last3_kernel<true><<<grid2, 256, 0, s>>>((const __nv_bfloat16*)x, g2, w, bias, y);
-      else if (c == 64 && g2.sb == 4) conv_last3_kernel<false><<<grid2, 256, 0, s>>>((const __nv_bfloat16*)x, g2, w, bias, y);
-      else if (c % 64 == 0) conv_last2_kernel<__nv_bfloat16, 2><<<grid2, 256, smem2, s>>>((const __nv_bfloat16*)x, g2, w, bias, y);
+      // (c == 64 / 128 go to lastconv_mma.cu above; this branch serves c == 32)
+      if (c % 64 == 0) conv_last2_kernel<__nv_bfloat16, 2><<<grid2, 256, smem2, s>>>((const __nv_bfloat16*)x, g2, w, bias, y);
       else conv_last2_kernel<__nv_bfloat16, 1><<<grid2, 256, smem2, s>>>((const __nv_bfloat16*)x, g2, w, bias, y);
     } else {
       if (c % 64 == 0) conv_last2_kernel<float, 2><<<grid2, 256, smem2, s>>>((const float*)x, g2, w, bias, y);
@@ -1269,10 +1073,7 @@ extern "C" int vsr_conv3x3_last_bwd(const void* x, int32_t dtype, int32_t n, int
     const int grid_dx = grid_for(items, 8, 8);
     if (dtype == VSR_BF16) {
       using B = __nv_bfloat16;
-      if (c == 64 && geom_is_zr4(g2)) {
-        conv_last3_dx_kernel<<<grid_dx, 256, 0, s2>>>(g2, w, dy, (B*)dx);
-        conv_last3_dw_kernel<true><<<blocks2, kLastBwdThreads, smem_p, s2>>>((const B*)x, g2, dy, ws2);
-      } else if (c % 64 == 0 && geom_is_zr4(g2)) {
+      if (c % 64 == 0 && geom_is_zr4(g2)) {
         conv_last2_dx_kernel<B, 2, true><<<grid_dx, 256, smem_w, s2>>>(g2, w, dy, (B*)dx);
         conv_last2_dw_kernel<B, 2, true><<<blocks2, kLastBwdThreads, smem_p, s2>>>((const B*)x, g2, dy, ws2);
       } else if (c % 64 == 0) {
