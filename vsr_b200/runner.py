@@ -400,6 +400,51 @@ class MISRTrainStep(VSRTrainStep):
         return lvals, [y]
 
 
+class SISRTrainStep(MISRTrainStep):
+    """The fused step for the single-image nets with ONE output (reference: acdc_sisr_trainer.py:8-48 on
+    base_trainer.py:99-144; EDSRNet): `inputs` / `targets` are one-element lists [lr_img] / [hr_img]."""
+
+    def __init__(self, net, loss_fns, loss_weights, metric_fns, optimizer, dataset="acdc", process_group=None,
+                 use_graph=False):
+        super().__init__(net, loss_fns, loss_weights, metric_fns, optimizer, dataset, process_group, use_graph,
+                         sync_bn=False)
+
+    def _device_fwd_bwd(self, inputs, targets):
+        net = self.net
+        net._pack(True)
+        y, saved = net._forward(inputs[0], True)
+        lvals, grads = self._loss([y], targets, True)
+        gflat = net._backward(saved, grads[0])
+        if self.world > 1:
+            self._reduce_bucket(gflat, 0, gflat.numel())
+        net.flat_grad = gflat
+        return lvals, [y], gflat
+
+    def _infer(self, inputs):
+        self.net._pack(False)
+        return [self.net._forward(inputs[0].contiguous(), False)[0]]
+
+
+class SISRSRFBTrainStep(VSRTrainStep):
+    """The fused step for the single-image nets that return one output per feedback step (reference:
+    acdc_sisr_srfb_trainer.py:8-38; SRFBNet, DRFSISRNet): every loss is the mean over the steps against the SAME target
+    (:22-24), the metrics see the last step's output only (:36).  `inputs` / `targets` are [lr_img] / [hr_img]; the
+    recurrent engine runs `net.num_steps` iterations on the one image, exactly as the nets' own forward does."""
+
+    def _expand(self, inputs, targets):
+        S = self.net.num_steps
+        return [inputs[0]] * S, [targets[0]] * S
+
+    def train_step(self, inputs, targets, acc=None, with_metrics=True):
+        return super().train_step(*self._expand(inputs, targets), acc, with_metrics)
+
+    def eval_step(self, inputs, targets, acc=None):
+        return super().eval_step(*self._expand(inputs, targets), acc)
+
+    def _metrics(self, outs, targets, acc):
+        super()._metrics(outs[-1:], targets[-1:], acc)
+
+
 class VSRTrainer:
     """Drop-in for AcdcVSRTrainer / Dsb15VSRTrainer (same constructor keywords; `dataset` selects
     the denormalisation constants, default 'acdc').  Under torchrun (an initialised process group) every rank runs
@@ -554,6 +599,9 @@ class MISRTrainer(VSRTrainer):
         return MISRTrainStep(self.net, self.loss_fns, self.loss_weights, self.metric_fns, self.optimizer, dataset,
                              process_group=self.pg, use_graph=use_graph)
 
+    def _get_inputs_targets(self, batch):
+        return batch["lr_imgs"], [batch["hr_img"]]                         # acdc_misr_trainer.py:16-25
+
     def _run_epoch(self, mode):
         from .data import DeviceStager
         training = mode == "training"
@@ -565,13 +613,13 @@ class MISRTrainer(VSRTrainer):
         count, batch, outputs = 0, None, None
         batches = DeviceStager(loader, self.device) if self.device.type == "cuda" else loader
         for batch in batches:
-            inputs, targets = batch["lr_imgs"], [batch["hr_img"]]          # acdc_misr_trainer.py:16-25
+            inputs, targets = self._get_inputs_targets(batch)
             step_acc = torch.zeros_like(acc)
             if training:
                 _, outs = self.step.train_step(inputs, targets, step_acc)
             else:
                 _, outs = self.step.eval_step(inputs, targets, step_acc)
-            outputs = outs[0]
+            outputs = outs[0] if len(outs) == 1 else list(outs)
             bs = loader.batch_size or inputs[0].shape[0]                   # base_trainer.py:139-141
             acc += step_acc * bs
             count += bs
@@ -585,6 +633,32 @@ class MISRTrainer(VSRTrainer):
 
 
 AcdcMISRTrainer = MISRTrainer
+
+
+class SISRTrainer(MISRTrainer):
+    """Drop-in for AcdcSISRTrainer (acdc_sisr_trainer.py:8-48): batches carry ONE `lr_img` and ONE `hr_img`; the net
+    returns one image (EDSRNet).  Same epoch loop, log weighting, sharding and checkpoints as the other trainers; the
+    step is the fused, CUDA-graphed SISRTrainStep."""
+
+    def _make_step(self, dataset, use_graph):
+        return SISRTrainStep(self.net, self.loss_fns, self.loss_weights, self.metric_fns, self.optimizer, dataset,
+                             process_group=self.pg, use_graph=use_graph)
+
+    def _get_inputs_targets(self, batch):
+        return [batch["lr_img"]], [batch["hr_img"]]                        # acdc_sisr_trainer.py:15-24
+
+
+class SISRSRFBTrainer(SISRTrainer):
+    """Drop-in for AcdcSISRSRFBTrainer (acdc_sisr_srfb_trainer.py:8-38): nets with one output per feedback step
+    (SRFBNet, DRFSISRNet) - losses averaged over the steps, metrics on the last step."""
+
+    def _make_step(self, dataset, use_graph):
+        return SISRSRFBTrainStep(self.net, self.loss_fns, self.loss_weights, self.metric_fns, self.optimizer, dataset,
+                                 process_group=self.pg, use_graph=use_graph)
+
+
+AcdcSISRTrainer = SISRTrainer
+AcdcSISRSRFBTrainer = SISRSRFBTrainer
 
 
 class VSRPredictor:
