@@ -137,12 +137,14 @@ def main():
     a16, b16 = torch.randn(P, device=dev).to(torch.bfloat16), torch.randn(P, device=dev).to(torch.bfloat16)
     o16 = torch.empty_like(a16)
     rec("add (bf16)", f"large: {P} elements", 6 * P, lambda: ops.add(a16, b16, o16))
+    big16 = torch.randn(8 * P, device=dev, dtype=torch.bfloat16)      # 1 GB
     for c in (64, 256):                                  # bias gradients: column sums of a [rows][c] bf16 map
-        nrow = P // c
+        nrow = 8 * P // c
         dbias = torch.zeros(c, device=dev)
         wsc = torch.empty(ops.colsum_workspace(nrow, c) // 4 + 4, device=dev)
-        rec("column sums (bias gradient, bf16)", f"large: {nrow} x {c}", 2 * P,
-            lambda nrow=nrow, c=c, dbias=dbias, wsc=wsc: ops.colsum(a16, nrow, c, dbias, False, wsc))
+        rec("column sums (bias gradient, bf16)", f"large: {nrow} x {c}", 2 * 8 * P,
+            lambda nrow=nrow, c=c, dbias=dbias, wsc=wsc: ops.colsum(big16, nrow, c, dbias, False, wsc))
+    del big16
     part = torch.zeros(ops.partials_len, device=dev)
     rec("PReLU backward (act_bwd, bf16)", f"large: {P} elements", 6 * P, lambda: ops.act_bwd(a16, b16, o16, slope, part))
     res = {"what": "bandwidth-bound kernels alone: us per launch (median), algorithmic bytes / time, fraction of the measured copy "
