@@ -642,6 +642,10 @@ def build_line(args, r, world):
     kms *= scale
     achieved = flops / (kms * 1e-3) / 1e12
     peak = pk["bf16_tflops_sustained"]
+    fam_bytes = sum(v[3] for k, v in detail.items() if k.startswith(dom))
+    gbs_fam = fam_bytes / (kms * 1e-3) / 1e9
+    intensity = flops / max(fam_bytes, 1.0)
+    ridge = pk["bf16_tflops_sustained"] * 1e3 / pk["hbm_gbs"]
     kernel_share = {k: {"ms_per_step": v[1] * scale / prof_steps, "calls_per_step": v[2] / prof_steps,
                         **({"tflops": v[0] / (v[1] * scale * 1e-3) / 1e12} if v[0] else {})}
                     for k, v in sorted(fam.items(), key=lambda kv: -kv[1][1])}
@@ -691,10 +695,22 @@ def build_line(args, r, world):
                 "path": "DeviceStager (the trainer's loader wrapper): pinned-host batch of step k+1 copied on a copy stream "
                         "while step k computes; loss read back every step"},
         "gpu_launches": r["launches"],
-        "roofline": {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                     "frac": achieved / peak, "traffic": traffic,
-                     "algorithmic_bytes_per_launch": sum(v[3] for k, v in detail.items() if k.startswith(dom)) / max(cnt, 1),
-                     "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk['source']})",
+        # The roofline of the dominant kernel as a whole: its launches move `fam_bytes` algorithmic bytes for `flops`
+        # algorithmic FLOPs; below the ridge of the measured peaks (FLOP/B) the HBM roof is the binding one, above it the
+        # tensor roof.  Both views are always reported.
+        "roofline": {**({"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak}
+                        if intensity > ridge else
+                        {"bound": "hbm", "achieved": gbs_fam, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs_fam / pk["hbm_gbs"]}),
+                     "kernel": dom, "traffic": traffic,
+                     **({"note": "FLOPs and bytes are those of the channel-padded tap tables (64 + 32 i channels padded to multiples "
+                                 "of 64 with structural-zero weights, the (1,3,3) column form computes 128 columns for 96): about "
+                                 "3/4 of them are useful work (DESIGN.md section 3b)"} if WORKLOAD == "duf" else {}),
+                     "algorithmic_bytes_per_launch": fam_bytes / max(cnt, 1),
+                     "algorithmic_flops_per_launch": flops / max(cnt, 1),
+                     "intensity_flop_per_byte": intensity, "ridge_flop_per_byte": ridge,
+                     "tensor_view": {"achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak},
+                     "hbm_view": {"achieved": gbs_fam, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs_fam / pk["hbm_gbs"]},
+                     "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained / hbm_gbs ({pk['source']})",
                      "frac_time_weighted_own_bound": frac_own, "time_share_hbm_bound_shapes": hbm_share,
                      "frac_tensor_bound_shapes": frac_tensor,
                      "launches": cnt, "kernels": kernel_share, "kernel_detail": kernel_detail,
