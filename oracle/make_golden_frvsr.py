@@ -1,0 +1,49 @@
+"""Generate tests/golden/frvsrnet_*.pt by running the REAL reference FRVSRNet (stub-loaded from /root/reference,
+src/model/nets/frvsr_net.py) on seeded inputs.  The net has 1.9 M parameters (FNet is fixed at 32 .. 256 channels), so the
+fixture stores the seed of the weights (oracle.make_golden.seeded_fill), the inputs / targets, the outputs (sr_imgs and
+lr_imgs), the two losses of acdc_frvsr_trainer.py:85-88 and a digest of every parameter gradient of flow_loss + sr_loss.
+Run in the build container only:   python -m oracle.make_golden_frvsr"""
+import os
+
+import torch
+
+from oracle import load_reference
+from oracle.make_golden import grad_digest, seeded_fill
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+CASES = [
+    # name, kwargs, N, T, h, w
+    ("frvsrnet_b2_x4", dict(in_channels=1, out_channels=1, upscale_factor=4, num_resblocks=2), 2, 3, 16, 16),
+    ("frvsrnet_b1_x4_pad", dict(in_channels=1, out_channels=1, upscale_factor=4, num_resblocks=1), 1, 2, 12, 20),
+]
+
+
+def main():
+    ref = load_reference.load()
+    for idx, (name, kw, n, t, h, w) in enumerate(CASES):
+        torch.manual_seed(300 + idx)
+        net = ref.FRVSRNet(**kw)
+        sd = seeded_fill({k: v for k, v in net.state_dict().items()}, 300 + idx)
+        net.load_state_dict(sd)
+        g = torch.Generator().manual_seed(400 + idx)
+        r = kw["upscale_factor"]
+        # smooth-ish frames so that the flow net sees correlated neighbours
+        base = torch.randn(n, 1, h, w, generator=g)
+        inputs = [base + 0.3 * torch.randn(n, 1, h, w, generator=g) for _ in range(t)]
+        targets = [torch.randn(n, 1, h * r, w * r, generator=g) for _ in range(t)]
+        sr_imgs, lr_imgs = net(list(inputs))
+        l1 = torch.nn.L1Loss()
+        flow_loss = torch.stack([l1(a, b) for a, b in zip(lr_imgs, inputs)]).mean()     # acdc_frvsr_trainer.py:86
+        sr_loss = torch.stack([l1(a, b) for a, b in zip(sr_imgs, targets)]).mean()      # :87
+        (flow_loss + sr_loss).backward()
+        fx = {"kwargs": kw, "state_seed": 300 + idx, "state_shapes": {k: tuple(v.shape) for k, v in sd.items()},
+              "inputs": inputs, "targets": targets, "sr_imgs": [o.detach().clone() for o in sr_imgs],
+              "lr_imgs": [o.detach().clone() for o in lr_imgs], "flow_loss": flow_loss.detach().clone(),
+              "sr_loss": sr_loss.detach().clone(),
+              "grad_digest": {k: grad_digest(p.grad) for k, p in net.named_parameters()}}
+        torch.save(fx, os.path.join(OUT, name + ".pt"))
+        print(name, os.path.getsize(os.path.join(OUT, name + ".pt")), "bytes", float(flow_loss), float(sr_loss))
+
+
+if __name__ == "__main__":
+    main()

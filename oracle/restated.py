@@ -351,3 +351,78 @@ def rbpnet_forward(inputs, sd, upscale, num_frames):
         Ht.append(h)
         feat_input = seq(h, "res_feat3", lambda v, p: cb(v, p, **proj))
     return _conv(torch.cat(Ht, dim=1), sd, "output.conv", padding=1)                # :89-90
+
+
+# ---- FRVSRNet (frvsr_net.py:11-239) -----------------------------------------------------------------------------------
+def stn_mesh(h, w, dtype=torch.float32):
+    """STN.nd_meshgrid(h, w, permute=[1, 0]) - frvsr_net.py:228-239: [h, w, 2] with (x, y) in linspace(-1, 1)"""
+    ys = torch.linspace(-1, 1, h, dtype=torch.float64)
+    xs = torch.linspace(-1, 1, w, dtype=torch.float64)
+    gy, gx = torch.meshgrid(ys, xs, indexing="ij")
+    return torch.stack([gx, gy], dim=-1).to(dtype)
+
+
+def stn_warp(img, u, v):
+    """STN(mode='bilinear', padding_mode='border', normalize=False).forward - frvsr_net.py:205-226 (grid_sample with
+    the framework's default align_corners, i.e. False on the torch of this image)"""
+    mesh = stn_mesh(*img.shape[-2:], dtype=img.dtype).unsqueeze(0) + torch.stack([u, v], dim=-1)
+    return F.grid_sample(img, mesh, mode="bilinear", padding_mode="border", align_corners=False)
+
+
+def space_to_depth(x, r):   # SpaceToDepth.forward - frvsr_net.py:178-191
+    n, c, h, w = x.shape
+    return x.contiguous().view(n, c, h // r, r, w // r, r).permute(0, 1, 3, 5, 2, 4).contiguous().view(n, c * r * r, h // r, w // r)
+
+
+def frvsr_fnet(a, b, sd, p="fnet"):
+    """FNet.forward - frvsr_net.py:108-163"""
+    x = torch.cat([a, b], dim=1)
+    N, C, H, W = x.shape
+    pad = None
+    if H % 8 != 0 or W % 8 != 0:
+        hd = 8 - H % 8 if H % 8 != 0 else 0
+        wd = 8 - W % 8 if W % 8 != 0 else 0
+        pad = (wd // 2, wd - wd // 2, hd // 2, hd - hd // 2)
+        x = F.pad(x, pad, value=float(x.min()))
+    lrelu = lambda v: F.leaky_relu(v, 0.2)
+    for i in range(6):
+        x = lrelu(_conv(x, sd, f"{p}.body.conv{i + 1}_1", padding=1))
+        x = lrelu(_conv(x, sd, f"{p}.body.conv{i + 1}_2", padding=1))
+        x = F.max_pool2d(x, 2) if i < 3 else F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False)
+    x = lrelu(_conv(x, sd, f"{p}.tail.conv1", padding=1))
+    x = torch.tanh(_conv(x, sd, f"{p}.tail.conv2", padding=1))
+    if pad is not None:
+        w0, wn, h0, hn = pad
+        x = x[..., h0:x.size(-2) - hn, w0:x.size(-1) - wn]
+    return x
+
+
+def frvsr_srnet(s2d, lr, sd, p="srnet"):
+    """SRNet.forward - frvsr_net.py:66-93 (+ _ResBlock :96-105)"""
+    x = F.relu(_conv(torch.cat([s2d, lr], dim=1), sd, f"{p}.head.conv", padding=1))
+    i = 0
+    while f"{p}.body.{i}.body.conv1.weight" in sd:
+        t = F.relu(_conv(x, sd, f"{p}.body.{i}.body.conv1", padding=1))
+        x = x + _conv(t, sd, f"{p}.body.{i}.body.conv2", padding=1)
+        i += 1
+    x = F.relu(_deconv(x, sd, f"{p}.tail.deconv1", stride=2, padding=1, output_padding=1))
+    x = F.relu(_deconv(x, sd, f"{p}.tail.deconv2", stride=2, padding=1, output_padding=1))
+    return _conv(x, sd, f"{p}.tail.conv", padding=1)
+
+
+def frvsrnet_forward(inputs, sd, upscale):
+    """FRVSRNet.forward - frvsr_net.py:40-61: (sr_imgs, lr_imgs)"""
+    sr_imgs, lr_imgs = [], []
+    n, c, h, w = inputs[0].shape
+    lr_last = inputs[0]
+    sr_last = torch.zeros(n, c, h * upscale, w * upscale, dtype=inputs[0].dtype)
+    for x in inputs:
+        lr_flow = frvsr_fnet(lr_last, x, sd)
+        sr_flow = F.interpolate(lr_flow, scale_factor=upscale, mode="bilinear", align_corners=True)
+        warped = stn_warp(sr_last.detach(), sr_flow[:, 0], sr_flow[:, 1])
+        sr_img = frvsr_srnet(space_to_depth(warped, upscale), x, sd)
+        sr_imgs.append(sr_img)
+        sr_last = sr_img
+        lr_imgs.append(stn_warp(lr_last, lr_flow[:, 0], lr_flow[:, 1]))
+        lr_last = x
+    return sr_imgs, lr_imgs
