@@ -399,6 +399,33 @@ size_t vsr_downscale_workspace(int32_t n, int32_t h, int32_t w);
 int vsr_downscale(const float* hr, int32_t n, int32_t h, int32_t w, int32_t r, const double* ph, const double* pw, float* lr,
                   void* workspace, size_t workspace_bytes, void* stream);
 
+/*
+ * Element-wise pieces of the flow-based recurrent net FRVSRNet (frvsr_net.py:11-239), fp32 maps.
+ *   vsr_maxpool2x2{,_bwd}      nn.MaxPool2d(2) of FNet (:127) on a pixel-major map [n][h][w][c] -> [n][h/2][w/2][c]; idx keeps
+ *                              the window position of every maximum (torch's scan order: a later element wins when greater)
+ *   vsr_upsample2x_nhwc{,_bwd} BilinerUp(2) = F.interpolate(x2, bilinear, align_corners=False) (:135,166-172) on a pixel-major map
+ *   vsr_flow_tanh{,_bwd}       nn.Tanh on the two flow channels of the last FNet convolution (:142) + the crop that undoes FNet's
+ *                              padding (:147-161): z [n][hp][wp][cz] -> flow [n][2][h][w] taken at offset (y0, x0)
+ *   vsr_grid_warp{,_bwd}       STN.forward (:205-226): grid = linspace(-1, 1) mesh + flow, F.grid_sample(bilinear, border,
+ *                              align_corners=False) of a one-channel image; the backward gives d(flow) only (the warped image is
+ *                              data or a detached output, :47,53)
+ *   vsr_s2d_cat{,_bwd}         SpaceToDepth(r) of the warped HR image + torch.cat with the LR frame (:47-48,88,175-191) as the
+ *                              pixel-major SRNet input [n][h][w][cpad] (channels r*r+1 .. cpad-1 zero); backward: d(warped image)
+ */
+int vsr_maxpool2x2(const float* x, int32_t n, int32_t h, int32_t w, int32_t c, float* y, uint8_t* idx, void* stream);
+int vsr_maxpool2x2_bwd(const float* dy, const uint8_t* idx, int32_t n, int32_t h, int32_t w, int32_t c, float* dx, void* stream);
+int vsr_upsample2x_nhwc(const float* x, int32_t n, int32_t h, int32_t w, int32_t c, float* y, void* stream);
+int vsr_upsample2x_nhwc_bwd(const float* dy, int32_t n, int32_t h, int32_t w, int32_t c, float* dx, void* stream);
+int vsr_flow_tanh(const float* z, int32_t n, int32_t hp, int32_t wp, int32_t cz, int32_t y0, int32_t x0, int32_t h, int32_t w,
+                  float* flow, void* stream);
+int vsr_flow_tanh_bwd(const float* dflow, const float* flow, int32_t n, int32_t hp, int32_t wp, int32_t cz, int32_t y0, int32_t x0,
+                      int32_t h, int32_t w, float* dz, void* stream);
+int vsr_grid_warp(const float* img, const float* flow, int32_t n, int32_t h, int32_t w, float* out, void* stream);
+int vsr_grid_warp_bwd(const float* img, const float* flow, const float* dout, int32_t n, int32_t h, int32_t w, float* dflow,
+                      void* stream);
+int vsr_s2d_cat(const float* hr, const float* lr, int32_t n, int32_t h, int32_t w, int32_t r, int32_t cpad, float* out, void* stream);
+int vsr_s2d_cat_bwd(const float* dout, int32_t n, int32_t h, int32_t w, int32_t r, int32_t cpad, float* dhr, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -502,9 +502,78 @@ class EmuOps:
 
     def upsample_linear_bwd(self, dy, dx, align_corners):
         mode = "bilinear" if dx.dim() == 4 else "trilinear"
-        x = torch.zeros_like(dx, requires_grad=True)
-        y = F.interpolate(x, size=dy.shape[2:], mode=mode, align_corners=bool(align_corners))
-        dx.copy_(torch.autograd.grad(y, x, dy)[0])
+        with torch.enable_grad():
+            x = torch.zeros_like(dx, requires_grad=True)
+            y = F.interpolate(x, size=dy.shape[2:], mode=mode, align_corners=bool(align_corners))
+            dx.copy_(torch.autograd.grad(y, x, dy)[0])
+        self.launches += 1
+
+    # ---- flow-based recurrent net (csrc/flow.cu) ----
+    def maxpool2x2(self, x, y, idx):
+        v, i = F.max_pool2d(x.permute(0, 3, 1, 2), 2, return_indices=True)
+        n, h, w, c = x.shape
+        iy, ix = i // w, i % w
+        y.copy_(v.permute(0, 2, 3, 1))
+        idx.copy_(((iy % 2) * 2 + ix % 2).permute(0, 2, 3, 1).to(idx.dtype))
+        self.launches += 1
+
+    def maxpool2x2_bwd(self, dy, idx, dx):
+        n, h, w, c = dx.shape
+        d = dx.view(n, h // 2, 2, w // 2, 2, c)
+        for k in range(4):
+            d[:, :, k // 2, :, k % 2, :] = torch.where(idx == k, dy, torch.zeros_like(dy))
+        self.launches += 1
+
+    def upsample2x_nhwc(self, x, y):
+        y.copy_(F.interpolate(x.permute(0, 3, 1, 2), scale_factor=2, mode="bilinear", align_corners=False).permute(0, 2, 3, 1))
+        self.launches += 1
+
+    def upsample2x_nhwc_bwd(self, dy, dx):
+        with torch.enable_grad():
+            x = torch.zeros_like(dx, requires_grad=True)
+            y = F.interpolate(x.permute(0, 3, 1, 2), scale_factor=2, mode="bilinear", align_corners=False).permute(0, 2, 3, 1)
+            dx.copy_(torch.autograd.grad(y, x, dy)[0])
+        self.launches += 1
+
+    def flow_tanh(self, z, y0, x0, flow):
+        h, w = flow.shape[2:]
+        flow.copy_(torch.tanh(z[:, y0:y0 + h, x0:x0 + w, :2]).permute(0, 3, 1, 2))
+        self.launches += 1
+
+    def flow_tanh_bwd(self, dflow, flow, y0, x0, dz):
+        h, w = flow.shape[2:]
+        dz.zero_()
+        dz[:, y0:y0 + h, x0:x0 + w, :2] = (dflow * (1 - flow * flow)).permute(0, 2, 3, 1)
+        self.launches += 1
+
+    @staticmethod
+    def _stn_grid(flow):
+        n, _, h, w = flow.shape
+        ys = torch.linspace(-1, 1, h, dtype=torch.float64)
+        xs = torch.linspace(-1, 1, w, dtype=torch.float64)
+        gy, gx = torch.meshgrid(ys, xs, indexing="ij")
+        mesh = torch.stack([gx, gy], dim=-1).to(flow.dtype).to(flow.device)
+        return mesh.unsqueeze(0) + flow.permute(0, 2, 3, 1)
+
+    def grid_warp(self, img, flow, out):
+        out.copy_(F.grid_sample(img, self._stn_grid(flow), mode="bilinear", padding_mode="border", align_corners=False))
+        self.launches += 1
+
+    def grid_warp_bwd(self, img, flow, dout, dflow):
+        with torch.enable_grad():
+            f = flow.detach().clone().requires_grad_(True)
+            o = F.grid_sample(img, self._stn_grid(f), mode="bilinear", padding_mode="border", align_corners=False)
+            dflow.copy_(torch.autograd.grad(o, f, dout)[0])
+        self.launches += 1
+
+    def s2d_cat(self, hr, lr, r, out):
+        out.zero_()
+        out[..., :r * r] = F.pixel_unshuffle(hr, r).permute(0, 2, 3, 1)
+        out[..., r * r] = lr[:, 0]
+        self.launches += 1
+
+    def s2d_cat_bwd(self, dout, r, dhr):
+        dhr.copy_(F.pixel_shuffle(dout[..., :r * r].permute(0, 3, 1, 2), r))
         self.launches += 1
 
     def adam_flat(self, p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):

@@ -19,7 +19,7 @@ def _state(fx):
 
 
 def _losses(sr_imgs, lr_imgs, fx):
-    l1 = torch.nn.L1Loss()
+    l1 = torch.nn.MSELoss()         # the fixtures use a smooth loss (oracle/make_golden_frvsr.py)
     flow = torch.stack([l1(a, b.to(a.device)) for a, b in zip(lr_imgs, fx["inputs"])]).mean()      # acdc_frvsr_trainer.py:86
     sr = torch.stack([l1(a, b.to(a.device)) for a, b in zip(sr_imgs, fx["targets"])]).mean()       # :87
     return flow, sr
@@ -45,3 +45,155 @@ def test_oracle_restatement_matches_reference_golden(path):
     for k, dg in fx["grad_digest"].items():
         assert abs(float(grads[k].norm()) - float(dg["norm"])) <= 1e-4 * float(dg["norm"]) + 1e-9, k
         assert (grads[k].reshape(-1)[:16] - dg["head"]).abs().max() <= 1e-4 * float(grads[k].abs().max()) + 1e-9, k
+
+
+def _oracle_grads64(fx):
+    fx64 = dict(fx, inputs=[x.double() for x in fx["inputs"]], targets=[x.double() for x in fx["targets"]])
+    sd = {k: v.double().requires_grad_(True) for k, v in _state(fx).items()}
+    sr, lr = restated.frvsrnet_forward(fx64["inputs"], sd, fx["kwargs"]["upscale_factor"])
+    flow_loss, sr_loss = _losses(sr, lr, fx64)
+    (flow_loss + sr_loss).backward()
+    return fx64, sr, lr, {k: v.grad for k, v in sd.items()}
+
+
+def _grad_err(got, ref64):
+    """(largest element error / largest gradient element, global relative L2) against the float64 oracle"""
+    gmax = max(float(g.abs().max()) for g in ref64.values())
+    worst = num = den = 0.0
+    for k, g in ref64.items():
+        d = got[k].double().cpu() - g
+        worst = max(worst, float(d.abs().max()) / gmax)
+        num += float((d ** 2).sum())
+        den += float((g ** 2).sum())
+    return worst, (num / den) ** 0.5
+
+
+def _check_net(net, fx, device, out_tol, grad_tol):
+    """outputs against the golden of the real reference; gradients against the oracle evaluated in FLOAT64.  d(loss)/d(flow)
+    is a difference of neighbouring pixels of the (detached) previous output times w / 2, so the flow net's gradients are
+    ill-conditioned in fp32 whoever computes them (1e-4 .. 2e-3 of the largest gradient for the reference's own fp32
+    arithmetic, depending on the input): the bar is `grad_tol` or four times the error the fp32 oracle has against float64
+    on the same input, whichever is larger.  test_host_logic_exact_in_float64 shows the logic itself is exact."""
+    _, _, _, _, g32 = _oracle_grads(fx)
+    _, _, _, g64 = _oracle_grads64(fx)
+    e_ref = _grad_err(g32, g64)
+    sr, lr = net([x.to(device) for x in fx["inputs"]])
+    for o, ref in zip(sr, fx["sr_imgs"]):
+        assert o.shape == ref.shape
+        assert (o.detach().cpu() - ref).abs().max() <= out_tol * ref.abs().max()
+    for o, ref in zip(lr, fx["lr_imgs"]):
+        assert (o.detach().cpu() - ref).abs().max() <= out_tol * ref.abs().max()
+    flow_loss, sr_loss = _losses(sr, lr, fx)
+    assert abs(float(flow_loss) - float(fx["flow_loss"])) <= 1e-5 and abs(float(sr_loss) - float(fx["sr_loss"])) <= 1e-5
+    (flow_loss + sr_loss).backward()
+    e_got = _grad_err({k: p.grad.detach() for k, p in net.named_parameters()}, g64)
+    print(f"gradient error vs the float64 oracle: ours {e_got[0]:.2e} / {e_got[1]:.2e}, the fp32 oracle {e_ref[0]:.2e} / {e_ref[1]:.2e}")
+    assert e_got[0] <= max(grad_tol, 4 * e_ref[0]) and e_got[1] <= max(grad_tol, 4 * e_ref[1])
+
+
+def test_host_logic_exact_in_float64():
+    """tables, packing maps and the recorded backward in float64 through the emulation = the float64 oracle to round-off:
+    whatever differs in fp32 is arithmetic, not logic"""
+    from tests.emu import EmuOps
+    from vsr_b200.frvsr import FRVSRNet
+    for path in CASES:
+        fx = torch.load(path)
+        fx64, sr, lr, g64 = _oracle_grads64(fx)
+        net = FRVSRNet(**fx["kwargs"])
+        net.load_state_dict(_state(fx))
+        net = net.double()
+        net._ops = EmuOps()
+        s2, l2 = net(fx64["inputs"])
+        for a, b in zip(s2 + l2, sr + lr):
+            assert (a.detach() - b.detach()).abs().max() <= 1e-10
+        f2, ss2 = _losses(s2, l2, fx64)
+        (f2 + ss2).backward()
+        worst, l2err = _grad_err({k: p.grad.detach() for k, p in net.named_parameters()}, g64)
+        assert worst <= 1e-10 and l2err <= 1e-10
+
+
+def test_state_dict_contract():
+    from vsr_b200.frvsr import FRVSRNet
+    fx = torch.load(CASES[0])
+    net = FRVSRNet(**fx["kwargs"])
+    assert {k: tuple(v.shape) for k, v in net.state_dict().items()} == fx["state_shapes"]
+    assert list(net.state_dict()) == list(fx["state_shapes"])
+    with pytest.raises(ValueError):
+        FRVSRNet(1, 1, 2)
+    with pytest.raises(ValueError):
+        FRVSRNet(1, 1, 4, precision="bf16")
+
+
+@pytest.mark.parametrize("path", CASES, ids=ids)
+def test_plan_and_recorded_backward_through_the_emulation(path):
+    from tests.emu import EmuOps
+    from vsr_b200.frvsr import FRVSRNet
+    fx = torch.load(path)
+    net = FRVSRNet(**fx["kwargs"])
+    net.load_state_dict(_state(fx))
+    net._ops = EmuOps()
+    _check_net(net, fx, "cpu", 1e-4, 1e-4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", CASES, ids=ids)
+def test_gpu_matches_reference_golden(path):
+    from vsr_b200.frvsr import FRVSRNet
+    fx = torch.load(path)
+    net = FRVSRNet(**fx["kwargs"])
+    net.load_state_dict(_state(fx))
+    _check_net(net.cuda(), fx, "cuda", 1e-4, 1e-4)
+
+
+@pytest.mark.gpu
+def test_flow_kernels_match_the_emulation():
+    """csrc/flow.cu against the torch emulation: max pooling (+ indices), bilinear x2 of pixel-major maps, flow head with the
+    crop, STN warp (in-range, clipped and border samples) and its flow gradient, space-to-depth + concatenation"""
+    from tests.emu import EmuOps
+    from vsr_b200.ops import cuda_ops
+    ops, emu = cuda_ops(), EmuOps()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    rnd = lambda *s: torch.randn(*s, device="cuda", generator=g)
+
+    def both(fn, outs):
+        res = []
+        for o in (ops, emu):
+            bufs = [torch.full_like(t, 7) if t.is_floating_point() else torch.zeros_like(t) for t in outs]
+            fn(o, *bufs)
+            res.append(bufs)
+        return res
+
+    x = rnd(2, 6, 10, 24)
+    (y, i), (ye, ie) = both(lambda o, y, i: o.maxpool2x2(x, y, i), [torch.empty(2, 3, 5, 24, device="cuda"), torch.empty(2, 3, 5, 24, device="cuda", dtype=torch.uint8)])
+    assert torch.equal(y, ye) and torch.equal(i, ie)
+    dy = rnd(2, 3, 5, 24)
+    (dx,), (dxe,) = both(lambda o, d: o.maxpool2x2_bwd(dy, i, d), [torch.empty_like(x)])
+    assert torch.equal(dx, dxe)
+    for shp in ((2, 5, 7, 8), (1, 1, 1, 4), (1, 1, 3, 40)):
+        x = rnd(*shp)
+        up = torch.empty(shp[0], 2 * shp[1], 2 * shp[2], shp[3], device="cuda")
+        (y,), (ye,) = both(lambda o, y: o.upsample2x_nhwc(x, y), [up])
+        assert (y - ye).abs().max() <= 1e-6
+        dy = rnd(*up.shape)
+        (dx,), (dxe,) = both(lambda o, d: o.upsample2x_nhwc_bwd(dy, d), [torch.empty_like(x)])
+        assert (dx - dxe).abs().max() <= 1e-5
+    z = rnd(2, 16, 24, 32)
+    (f,), (fe,) = both(lambda o, f: o.flow_tanh(z, 2, 3, f), [torch.empty(2, 2, 12, 20, device="cuda")])
+    assert (f - fe).abs().max() <= 1e-6
+    df = rnd(2, 2, 12, 20)
+    (dz,), (dze,) = both(lambda o, d: o.flow_tanh_bwd(df, fe, 2, 3, d), [torch.empty_like(z)])
+    assert (dz - dze).abs().max() <= 1e-6
+    for (h, w, scale) in ((16, 16, 0.3), (12, 20, 2.5), (5, 1, 0.5), (64, 64, 0.05)):
+        img, flow, dout = rnd(2, 1, h, w), rnd(2, 2, h, w) * scale, rnd(2, 1, h, w)
+        (o1,), (o2,) = both(lambda o, out: o.grid_warp(img, flow, out), [torch.empty_like(img)])
+        assert (o1 - o2).abs().max() <= 2e-5 * max(1.0, float(img.abs().max()))
+        (d1,), (d2,) = both(lambda o, d: o.grid_warp_bwd(img, flow, dout, d), [torch.empty_like(flow)])
+        # a sample within round-off of a cell boundary may take the neighbouring cell: allow a few such elements
+        bad = (d1 - d2).abs() > 1e-4 * max(1.0, float(d2.abs().max()))
+        assert int(bad.sum()) <= 2, int(bad.sum())
+    hr, lr = rnd(2, 1, 24, 32), rnd(2, 1, 6, 8)
+    (s,), (se,) = both(lambda o, out: o.s2d_cat(hr, lr, 4, out), [torch.empty(2, 6, 8, 32, device="cuda")])
+    assert torch.equal(s, se)
+    ds = rnd(2, 6, 8, 32)
+    (dh,), (dhe,) = both(lambda o, d: o.s2d_cat_bwd(ds, 4, d), [torch.empty_like(hr)])
+    assert torch.equal(dh, dhe)

@@ -105,6 +105,16 @@ _SIGS = {
     "vsr_cast": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p]),
     "vsr_cine_gather": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p] + [C.c_int32] * 7 +
                         [C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
+    "vsr_maxpool2x2": (C.c_int, [C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p] * 3),
+    "vsr_maxpool2x2_bwd": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p] * 2),
+    "vsr_upsample2x_nhwc": (C.c_int, [C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p] * 2),
+    "vsr_upsample2x_nhwc_bwd": (C.c_int, [C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p] * 2),
+    "vsr_flow_tanh": (C.c_int, [C.c_void_p] + [C.c_int32] * 8 + [C.c_void_p] * 2),
+    "vsr_flow_tanh_bwd": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 8 + [C.c_void_p] * 2),
+    "vsr_grid_warp": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 3 + [C.c_void_p] * 2),
+    "vsr_grid_warp_bwd": (C.c_int, [C.c_void_p] * 3 + [C.c_int32] * 3 + [C.c_void_p] * 2),
+    "vsr_s2d_cat": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 5 + [C.c_void_p] * 2),
+    "vsr_s2d_cat_bwd": (C.c_int, [C.c_void_p] + [C.c_int32] * 5 + [C.c_void_p] * 2),
     "vsr_downscale_workspace": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
     "vsr_downscale": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_size_t, C.c_void_p]),

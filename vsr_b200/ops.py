@@ -446,6 +446,70 @@ class CudaOps:
               "vsr_downscale")
         self.launches += 3
 
+    # ---- flow-based recurrent net (FRVSRNet): pooling / up-sampling of pixel-major maps, flow head, warp ----------
+    def maxpool2x2(self, x, y, idx):
+        _need_cuda(x, y, idx)
+        n, h, w_, c = x.shape
+        check(self.lib.vsr_maxpool2x2(_p(x), n, h, w_, c, _p(y), _p(idx), _stream()), "vsr_maxpool2x2")
+        self.launches += 1
+
+    def maxpool2x2_bwd(self, dy, idx, dx):
+        _need_cuda(dy, idx, dx)
+        n, h, w_, c = dx.shape
+        check(self.lib.vsr_maxpool2x2_bwd(_p(dy), _p(idx), n, h, w_, c, _p(dx), _stream()), "vsr_maxpool2x2_bwd")
+        self.launches += 1
+
+    def upsample2x_nhwc(self, x, y):
+        _need_cuda(x, y)
+        n, h, w_, c = x.shape
+        check(self.lib.vsr_upsample2x_nhwc(_p(x), n, h, w_, c, _p(y), _stream()), "vsr_upsample2x_nhwc")
+        self.launches += 1
+
+    def upsample2x_nhwc_bwd(self, dy, dx):
+        _need_cuda(dy, dx)
+        n, h, w_, c = dx.shape
+        check(self.lib.vsr_upsample2x_nhwc_bwd(_p(dy), n, h, w_, c, _p(dx), _stream()), "vsr_upsample2x_nhwc_bwd")
+        self.launches += 1
+
+    def flow_tanh(self, z, y0, x0, flow):
+        """flow [n, 2, h, w] = tanh(z[:, y0:y0+h, x0:x0+w, :2]) for a pixel-major z [n, hp, wp, cz]"""
+        _need_cuda(z, flow)
+        n, hp, wp, cz = z.shape
+        check(self.lib.vsr_flow_tanh(_p(z), n, hp, wp, cz, y0, x0, flow.shape[2], flow.shape[3], _p(flow), _stream()),
+              "vsr_flow_tanh")
+        self.launches += 1
+
+    def flow_tanh_bwd(self, dflow, flow, y0, x0, dz):
+        _need_cuda(dflow, flow, dz)
+        n, hp, wp, cz = dz.shape
+        check(self.lib.vsr_flow_tanh_bwd(_p(dflow), _p(flow), n, hp, wp, cz, y0, x0, flow.shape[2], flow.shape[3], _p(dz),
+                                         _stream()), "vsr_flow_tanh_bwd")
+        self.launches += 1
+
+    def grid_warp(self, img, flow, out):
+        _need_cuda(img, flow, out)
+        n, _, h, w_ = img.shape
+        check(self.lib.vsr_grid_warp(_p(img), _p(flow), n, h, w_, _p(out), _stream()), "vsr_grid_warp")
+        self.launches += 1
+
+    def grid_warp_bwd(self, img, flow, dout, dflow):
+        _need_cuda(img, flow, dout, dflow)
+        n, _, h, w_ = img.shape
+        check(self.lib.vsr_grid_warp_bwd(_p(img), _p(flow), _p(dout), n, h, w_, _p(dflow), _stream()), "vsr_grid_warp_bwd")
+        self.launches += 1
+
+    def s2d_cat(self, hr, lr, r, out):
+        _need_cuda(hr, lr, out)
+        n, h, w_, cpad = out.shape
+        check(self.lib.vsr_s2d_cat(_p(hr), _p(lr), n, h, w_, r, cpad, _p(out), _stream()), "vsr_s2d_cat")
+        self.launches += 1
+
+    def s2d_cat_bwd(self, dout, r, dhr):
+        _need_cuda(dout, dhr)
+        n, h, w_, cpad = dout.shape
+        check(self.lib.vsr_s2d_cat_bwd(_p(dout), n, h, w_, r, cpad, _p(dhr), _stream()), "vsr_s2d_cat_bwd")
+        self.launches += 1
+
     # ---- loss / metrics ----------------------------------------------------------------
     def loss_fwd_bwd(self, out, target, kind, param, grad_scale, partials, grad):
         _need_cuda(out, target, partials, grad)
