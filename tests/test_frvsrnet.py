@@ -205,3 +205,60 @@ def test_flow_kernels_match_the_emulation():
     ds = rnd(2, 6, 8, 32)
     (dh,), (dhe,) = both(lambda o, d: o.s2d_cat_bwd(ds, 4, d), [torch.empty_like(hr)])
     assert torch.equal(dh, dhe)
+
+
+def _frvsr_step_vs_oracle(device, steps, use_graph, w_tol, l_tol):
+    """FRVSRTrainStep against the oracle stepped with torch.optim.Adam (acdc_frvsr_trainer.py:41-50,85-88): both losses of
+    every step, PSNR / SSIM of the SR frames, the weights after `steps` steps (eps = 1e-4: tests/test_trainstep_gpu.py)"""
+    from tests.emu import EmuOps
+    from vsr_b200.frvsr import FRVSRNet
+    from vsr_b200.metrics import PSNR, SSIM
+    from vsr_b200.optim import FlatAdam
+    from vsr_b200.runner import FRVSRTrainStep
+    kw = dict(in_channels=1, out_channels=1, upscale_factor=4, num_resblocks=1)
+    shapes = {k: tuple(v.shape) for k, v in FRVSRNet(**kw).state_dict().items()}
+    sd0 = seeded_fill({k: torch.zeros(s) for k, s in shapes.items()}, 11)
+    g = torch.Generator().manual_seed(12)
+    base = torch.randn(2, 1, 8, 8, generator=g)
+    lrs = [base + 0.3 * torch.randn(2, 1, 8, 8, generator=g) for _ in range(2)]
+    hrs = [torch.randn(2, 1, 32, 32, generator=g) for _ in range(2)]
+    net = FRVSRNet(**kw)
+    net.load_state_dict(sd0)
+    if device == "cpu":
+        net._ops = EmuOps()
+    net = net.to(device)
+    opt = FlatAdam(net.parameters(), lr=1e-3, eps=1e-4)
+    step = FRVSRTrainStep(net, [torch.nn.L1Loss(), torch.nn.MSELoss()], [1.0, 0.5], [PSNR().to(device), SSIM().to(device)], opt,
+                          "acdc", use_graph=use_graph)
+    sd = {k: v.clone().requires_grad_(True) for k, v in sd0.items()}
+    ref_opt = torch.optim.Adam(list(sd.values()), lr=1e-3, eps=1e-4)
+    for _ in range(steps):
+        acc = torch.zeros(5, device=device)
+        lv, outs = step.train_step([x.to(device) for x in lrs], [y.to(device) for y in hrs], acc)
+        sr, lr = restated.frvsrnet_forward(lrs, sd, 4)
+        flow_loss = torch.stack([restated.l1_loss(a, b) for a, b in zip(lr, lrs)]).mean()
+        sr_loss = torch.stack([restated.mse_loss(a, b) for a, b in zip(sr, hrs)]).mean()
+        psnr, ssim = restated.vsr_metrics([o.detach() for o in sr], hrs)
+        ref_opt.zero_grad()
+        (flow_loss + 0.5 * sr_loss).backward()
+        ref_opt.step()
+        assert abs(float(lv[0]) - float(flow_loss)) <= l_tol * float(flow_loss)
+        assert abs(float(lv[1]) - float(sr_loss)) <= l_tol * float(sr_loss)
+        assert abs(float(acc[0]) - float(flow_loss + 0.5 * sr_loss)) <= l_tol * float(flow_loss + 0.5 * sr_loss)
+        assert abs(float(acc[3]) - float(psnr)) <= 2e-3 and abs(float(acc[4]) - float(ssim)) <= 1e-4
+    wmax = max(float(v.abs().max()) for v in sd.values())
+    for k, p in net.named_parameters():
+        assert (p.data.cpu() - sd[k].data).abs().max() <= w_tol * wmax, k
+
+
+def test_frvsr_train_step_matches_reference_step_host_logic():
+    _frvsr_step_vs_oracle("cpu", 2, False, 2e-5, 2e-5)
+
+
+@pytest.mark.gpu
+def test_frvsr_train_step_gpu_graphed():
+    """through the C-ABI, the step replayed as a CUDA graph (2 eager + capture + replay).  The losses of every step check
+    the weights the previous steps produced at 1e-4; the weights themselves after 4 steps at 1e-3 of the largest weight:
+    Adam divides by sqrt(v) + eps, so the flow net's ill-conditioned fp32 gradients (_check_net) move elements with small
+    gradients by a visible fraction of lr = 1e-3 per step"""
+    _frvsr_step_vs_oracle("cuda", 4, True, 1e-3, 1e-4)

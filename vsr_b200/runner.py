@@ -445,6 +445,79 @@ class SISRSRFBTrainStep(VSRTrainStep):
         super()._metrics(outs[-1:], targets[-1:], acc)
 
 
+class FRVSRTrainStep(VSRTrainStep):
+    """The fused step for FRVSRNet (reference: acdc_frvsr_trainer.py:8-120): the net returns (sr_imgs, lr_imgs);
+    losses = [flow_loss, sr_loss] with flow_loss = mean over frames of loss_fns[0](warped previous LR frame, LR frame)
+    and sr_loss = mean over frames of loss_fns[1](SR frame, HR frame) (:85-88); the metrics see the SR frames (:99-107).
+    Forward with the launch record, the two fused losses (one launch each for all frames), the recorded backward,
+    all-reduce, fused Adam, fused PSNR / SSIM; CUDA-graphed when the frame size is a multiple of 8 (FNet's padding reads
+    the minimum of the frames on the host, frvsr_net.py:149-156)."""
+
+    def __init__(self, net, loss_fns, loss_weights, metric_fns, optimizer, dataset="acdc", process_group=None,
+                 use_graph=False):
+        if len(loss_fns) != 2:
+            raise ValueError("FRVSR takes two losses: [flow loss, SR loss] (acdc_frvsr_trainer.py:85-88)")
+        super().__init__(net, loss_fns, loss_weights, metric_fns, optimizer, dataset, process_group, use_graph)
+
+    def _pair_loss(self, li, outs, refs, want_grad):
+        """loss li between two lists of frames: (its value [1] on the device, weight * dL/d(outs) per frame)"""
+        ops = self._ops()
+        T = len(outs)
+        o_all, y_all = _as_stacked(outs), _as_stacked(refs)
+        numel = outs[0].numel()
+        partials = self._buf(f"lpart{li}", (T, ops.partials_len))
+        partials.zero_()
+        g_all = torch.empty_like(o_all) if want_grad else None
+        kind, param = self.losses[li]
+        ops.loss_fwd_bwd_seg(o_all, y_all, T, kind, param, self.loss_weights[li] / (numel * T), partials, g_all)
+        total = self._buf(f"lsum{li}", (1,))
+        total.zero_()
+        rd = self._bufs.get(f"lrd{li}")
+        if rd is None or rd.numel() != T:
+            rd = torch.zeros(T, dtype=torch.int32, device=self.net.flat.device)
+            self._bufs[f"lrd{li}"] = rd
+        ops.reduce_partials(partials, T, rd, total)
+        return total / (numel * T), (list(g_all.unbind(0)) if want_grad else None)
+
+    def _device_fwd_bwd(self, inputs, targets):
+        net = self.net
+        net._pack(True)
+        sr, lr, tape = net._forward(inputs, True)
+        l_flow, g_lr = self._pair_loss(0, lr, inputs, True)
+        l_sr, g_sr = self._pair_loss(1, sr, targets, True)
+        gflat = net._backward(tape, g_sr, g_lr)
+        if self.world > 1:
+            self._reduce_bucket(gflat, 0, gflat.numel())
+        net.flat_grad = gflat
+        return torch.cat([l_flow, l_sr]), sr, gflat
+
+    def train_step(self, inputs, targets, acc=None, with_metrics=True):
+        graph = self.use_graph
+        if inputs[0].shape[-2] % 8 or inputs[0].shape[-1] % 8:
+            self.use_graph = False
+        try:
+            return super().train_step(inputs, targets, acc, with_metrics)
+        finally:
+            self.use_graph = graph
+
+    @torch.no_grad()
+    def eval_step(self, inputs, targets, acc=None):
+        net = self.net
+        if not net._is_flat():
+            net._flatten()
+        inputs = [x.contiguous() for x in inputs]
+        self._loss_weights_dev(inputs[0].device)
+        net._pack(False)
+        sr, lr, _ = net._forward(inputs, False)
+        targets = list(_as_stacked(targets).unbind(0))
+        lvals = torch.cat([self._pair_loss(0, lr, inputs, False)[0], self._pair_loss(1, sr, targets, False)[0]])
+        if acc is not None:
+            self._log(acc, lvals)
+            if self.metric_names:
+                self._metrics(sr, targets, acc)
+        return lvals, sr
+
+
 class VSRTrainer:
     """Drop-in for AcdcVSRTrainer / Dsb15VSRTrainer (same constructor keywords; `dataset` selects
     the denormalisation constants, default 'acdc').  Under torchrun (an initialised process group) every rank runs
@@ -659,6 +732,18 @@ class SISRSRFBTrainer(SISRTrainer):
 
 AcdcSISRTrainer = SISRTrainer
 AcdcSISRSRFBTrainer = SISRSRFBTrainer
+
+
+class FRVSRTrainer(VSRTrainer):
+    """Drop-in for AcdcFRVSRTrainer / Dsb15FRVSRTrainer (acdc_frvsr_trainer.py:8-120): `lr_imgs` / `hr_imgs` batches, the log
+    weights every batch by batch_size * T like the VSR trainer; the step is FRVSRTrainStep."""
+
+    def _make_step(self, dataset, use_graph):
+        return FRVSRTrainStep(self.net, self.loss_fns, self.loss_weights, self.metric_fns, self.optimizer, dataset,
+                              process_group=self.pg, use_graph=use_graph)
+
+
+AcdcFRVSRTrainer = FRVSRTrainer
 
 
 class VSRPredictor:
