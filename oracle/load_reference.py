@@ -52,6 +52,7 @@ def load():
     ns.EDSRNet = _load("src.model.nets.edsr_net", "src/model/nets/edsr_net.py").EDSRNet
     ns.RBPNet = _load("src.model.nets.rbp_net", "src/model/nets/rbp_net.py").RBPNet
     ns.FRVSRNet = _load("src.model.nets.frvsr_net", "src/model/nets/frvsr_net.py").FRVSRNet
+    ns.TOFlowNet = _load("src.model.nets.toflow_net", "src/model/nets/toflow_net.py").TOFlowNet
     losses = _load("src.model.losses", "src/model/losses.py")
     metrics = _load("src.model.metrics", "src/model/metrics.py")
     utils = _load("src.utils", "src/utils.py")

@@ -426,3 +426,78 @@ def frvsrnet_forward(inputs, sd, upscale):
         lr_imgs.append(stn_warp(lr_last, lr_flow[:, 0], lr_flow[:, 1]))
         lr_last = x
     return sr_imgs, lr_imgs
+
+
+# ---- TOFlowNet (toflow_net.py:8-138) ----------------------------------------------------------------------------------
+def toflow_warp(x, flow):
+    """flow_warp(x, flow, 'bilinear', 'zeros') - toflow_net.py:117-138; flow [N, 2, H, W] here (the reference permutes to
+    [N, H, W, 2] before the call, :60,85)"""
+    B, C, H, W = x.shape
+    gy, gx = torch.meshgrid(torch.arange(0, H), torch.arange(0, W), indexing="ij")
+    vx = gx.to(x.dtype) + flow[:, 0]
+    vy = gy.to(x.dtype) + flow[:, 1]
+    grid = torch.stack((2.0 * vx / max(W - 1, 1) - 1.0, 2.0 * vy / max(H - 1, 1) - 1.0), dim=3)
+    return F.grid_sample(x, grid, mode="bilinear", padding_mode="zeros", align_corners=False)
+
+
+def _bn2d(x, sd, key, training, buffers=None, eps=1e-5, momentum=0.1):
+    """nn.BatchNorm2d - toflow_net.py:96-106.  training: batch statistics; `buffers` (a dict of running_mean / running_var
+    clones) receives the momentum update exactly as the module's forward does"""
+    if training:
+        rm = buffers[key + ".running_mean"] if buffers is not None else None
+        rv = buffers[key + ".running_var"] if buffers is not None else None
+        return F.batch_norm(x, rm, rv, sd[key + ".weight"], sd[key + ".bias"], True, momentum if buffers is not None else 0.0, eps)
+    return F.batch_norm(x, sd[key + ".running_mean"], sd[key + ".running_var"], sd[key + ".weight"], sd[key + ".bias"],
+                        False, 0.0, eps)
+
+
+def spynet_block(x, sd, p, training, buffers=None):   # SpyNet_Block - toflow_net.py:93-112
+    for i in range(4):
+        x = _conv(x, sd, f"{p}.block.{3 * i}", padding=3)
+        x = F.relu(_bn2d(x, sd, f"{p}.block.{3 * i + 1}", training, buffers))
+    return _conv(x, sd, f"{p}.block.12", padding=3)
+
+
+def spynet(ref, nbr, sd, training, buffers=None, p="spy_net"):   # SpyNet.forward - toflow_net.py:72-90
+    B, C, H, W = ref.shape
+    refs, nbrs = [ref], [nbr]
+    for _ in range(3):
+        refs.insert(0, F.avg_pool2d(refs[0], kernel_size=2, stride=2, count_include_pad=False))
+        nbrs.insert(0, F.avg_pool2d(nbrs[0], kernel_size=2, stride=2, count_include_pad=False))
+    flow = torch.zeros(B, 2, H // 16, W // 16, dtype=ref.dtype)
+    for i in range(4):
+        flow_up = F.interpolate(flow, scale_factor=2, mode="bilinear", align_corners=True) * 2.0
+        flow = flow_up + spynet_block(torch.cat([refs[i], toflow_warp(nbrs[i], flow_up), flow_up], dim=1), sd,
+                                      f"{p}.blocks.{i}", training, buffers)
+    return flow
+
+
+def toflownet_forward(inputs, sd, upscale, training=True, buffers=None):
+    """TOFlowNet.forward - toflow_net.py:33-65"""
+    T = len(inputs)
+    ref_idx = T // 2 if T % 2 == 1 else T // 2 - 1
+    x = torch.stack([F.interpolate(f, scale_factor=upscale, mode="bicubic", align_corners=False) for f in inputs], dim=1)
+    B, T, C, H, W = x.shape
+    pad = None
+    if H % 16 != 0 or W % 16 != 0:
+        hd = 16 - H % 16 if H % 16 != 0 else 0
+        wd = 16 - W % 16 if W % 16 != 0 else 0
+        pad = (wd // 2, wd - wd // 2, hd // 2, hd - hd // 2)
+        x = F.pad(x, pad, value=float(x.min()))
+        B, T, C, H, W = x.shape
+    x_ref = x[:, ref_idx]
+    warped = []
+    for i in range(T):
+        if i == ref_idx:
+            warped.append(x_ref)
+        else:
+            warped.append(toflow_warp(x[:, i], spynet(x_ref, x[:, i], sd, training, buffers)))
+    y = torch.stack(warped, dim=1).view(B, -1, H, W)
+    y = F.relu(_conv(y, sd, "out_block.0", padding=4))
+    y = F.relu(_conv(y, sd, "out_block.2", padding=4))
+    y = F.relu(_conv(y, sd, "out_block.4"))
+    out = _conv(y, sd, "out_block.6") + x_ref
+    if pad is not None:
+        w0, wn, h0, hn = pad
+        out = out[..., h0:out.size(-2) - hn, w0:out.size(-1) - wn]
+    return out
