@@ -8,7 +8,8 @@ configs[1]: DRFNet-L F=64 G=6, x4, batch of 32 cropped 2D+t patches LR 32x32, T=
 A step = forward over T frames + fused L1 loss + full BPTT backward + (NCCL all-reduce) + Adam +
 PSNR/SSIM of the training outputs (what acdc_vsr_trainer.py:41-55 does per batch).
 Prints ONE JSON line on rank 0.  At N=1 the line also carries `infer` (BASELINE configs[2]: full-FOV DSB15-shaped
-cine inference with PSNR/SSIM on the device) and `fp32` (the same training step in the strict fp32 mode).
+cine inference with PSNR/SSIM on the device), `fp32` (the same training step in the strict fp32 mode on CUDA cores) and
+`bf16x3` (the strict mode on tensor cores).
 """
 import argparse
 import json
@@ -417,7 +418,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "bf16x3"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the `infer` and `fp32` sub-lines")
@@ -444,6 +445,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ops = cuda_ops()
+    if args.precision == "bf16x3":
+        from vsr_b200.ops import split_ops
+        ops = split_ops()
 
     def barrier():
         if world > 1:
@@ -471,6 +475,21 @@ def main():
                                     "clocks": r32["clocks"]}
                 except Exception as e:
                     line["fp32"] = {"error": f"{type(e).__name__}: {e}"}
+                try:
+                    # the same strict bar on the tensor cores: fp32 maps, three bf16 tcgen05 products per product
+                    from vsr_b200.ops import split_ops
+                    rx3 = train_bench(args, "bf16x3", 5, 3, 1, 0, dev, split_ops(), barrier, with_e2e=False, with_kernels=False)
+                    line["bf16x3"] = {"workload": workload_name(args.batch) + ", precision='bf16x3' (strict mode on tensor cores: "
+                                      "<= 1e-4 of the reference; fp32 maps, xh*wh + xl*wh + xh*wl on tcgen05)",
+                                      "metric": METRIC, "unit": UNIT, "value": rx3["value"], "ms_per_step": rx3["ms"],
+                                      "ms_per_step_median": rx3["ms_median"], "steps": 5, "warmup": 3,
+                                      "cuda_graph": rx3["cuda_graph"], "gpu_launches_per_step": rx3["launches_per_step"],
+                                      "step_tflops_algorithmic": rx3["step_flops"] / (rx3["ms"] * 1e-3) / 1e12,
+                                      "speedup_vs_fp32_mode": (line["fp32"]["ms_per_step"] / rx3["ms"]
+                                                               if "ms_per_step" in line.get("fp32", {}) else None),
+                                      "clocks": rx3["clocks"]}
+                except Exception as e:
+                    line["bf16x3"] = {"error": f"{type(e).__name__}: {e}"}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
             try:

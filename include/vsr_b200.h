@@ -43,7 +43,12 @@ typedef enum VsrStatus {
   VSR_ERR_DRIVER = -4
 } VsrStatus;
 
-typedef enum VsrDType { VSR_F32 = 0, VSR_BF16 = 1 } VsrDType;
+/* VSR_BF16X2 (tap-GEMM only): the strict mode on tensor cores.  An fp32 map travels as two bf16 planes
+ * [2][n][h][w][c] (x = plane 0 + plane 1 to 16 significant bits, vsr_split_planes); srcs[i].ptr points at plane 0 and
+ * srcs[i].n stays the logical n; bit 3 of a tap's source index selects plane 1; `out` receives the raw fp32
+ * accumulators (epi must be 0: vsr_tap_epilogue applies the epilogue in fp32 afterwards); weights are bf16 slabs as for
+ * VSR_BF16.  The caller expresses x*w = xh*wh + xl*wh + xh*wl as three taps with slabs [wh | wh | wl] (vsr_gather_split). */
+typedef enum VsrDType { VSR_F32 = 0, VSR_BF16 = 1, VSR_BF16X2 = 2 } VsrDType;
 
 /* epilogue flags of the tap-GEMM (applied in this order) */
 enum {
@@ -145,6 +150,22 @@ int vsr_tapgemm_wgrad_partial(const VsrTapGemmDesc* d, int32_t db_period, int32_
 int vsr_tapgemm_wgrad_finish(const VsrTapGemmDesc* d, float* dw, float* db, int32_t db_period, int accumulate,
                              int32_t used_slices, int32_t n_slices, void* workspace, size_t workspace_bytes,
                              void* stream);
+
+/* ---- strict mode on tensor cores (precision='bf16x3'): error-compensated bf16 pairs, csrc/split.cu ----
+ * Same call sites as vsr_tapgemm (drf_net.py:55-106,141-147) with fp32 maps on the caller's side:
+ *   vsr_split_planes(x)                         -> planes the VSR_BF16X2 tap-GEMM (and, plane by plane as VSR_BF16 maps,
+ *                                                  vsr_tapgemm_wgrad_partial) reads;  numel % 8 == 0
+ *   vsr_tapgemm(dtype = VSR_BF16X2, epi = 0)    -> raw fp32 accumulators in `out`
+ *   vsr_tap_epilogue(out, ...)                  -> the VSR_EPI_* flags of vsr_tapgemm applied in place, in fp32, in the
+ *                                                  order listed above ([rows][c] maps, c % 4 == 0; bias[c]; PRELU_BWD
+ *                                                  writes one partial per block into slope_partials)
+ *   vsr_gather_split(src, idx, dst, n)          -> dst[i] = bf16 high part of src[idx[i]], or its low part
+ *                                                  bf16(src - high) when bit 30 of idx[i] is set; 0 for idx[i] < 0 */
+int vsr_split_planes(const float* x, void* planes, int64_t numel, void* stream);
+int vsr_tap_epilogue(float* out, int64_t rows, int32_t c, const float* bias, int32_t epi, float out_scale,
+                     const float* slope, const float* residual, const float* aux_y, float* out2, const float* res2,
+                     float* slope_partials, void* stream);
+int vsr_gather_split(const float* src, const int32_t* idx, void* dst, int64_t n, void* stream);
 
 /* colsum: db[c] (+)= sum over pixels x[pix][c]  (bias gradient; fixed order).
  * workspace >= vsr_colsum_workspace(rows, c) bytes. */

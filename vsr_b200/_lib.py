@@ -7,7 +7,7 @@ import os
 
 from . import build as _build
 
-VSR_F32, VSR_BF16 = 0, 1
+VSR_F32, VSR_BF16, VSR_BF16X2 = 0, 1, 2
 VSR_MAX_SRCS = 8
 
 EPI_BIAS, EPI_RES_PRE, EPI_PRELU, EPI_RELU = 1, 2, 4, 8
@@ -76,6 +76,9 @@ _SIGS = {
     "vsr_gather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p]),
     "vsr_gather_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "vsr_slab_index": (C.c_int64, [C.c_int32, C.c_int32]),
+    "vsr_split_planes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "vsr_tap_epilogue": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_float] + [C.c_void_p] * 7),
+    "vsr_gather_split": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "vsr_loss_fwd_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_float,
                                    C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vsr_loss_fwd_bwd_seg": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_float,

@@ -375,7 +375,7 @@ bool wgrad_tc_bias_ok(const VsrTapGemmDesc* d, int db_period);
 
 int validate_desc(const VsrTapGemmDesc* d, const char* who) {
   VSR_CHECK_ARG(d != nullptr, "%s: null descriptor", who);
-  VSR_CHECK_ARG(d->dtype == VSR_F32 || d->dtype == VSR_BF16, "%s: bad dtype %d", who, d->dtype);
+  VSR_CHECK_ARG(d->dtype == VSR_F32 || d->dtype == VSR_BF16 || d->dtype == VSR_BF16X2, "%s: bad dtype %d", who, d->dtype);
   VSR_CHECK_ARG(d->n_srcs >= 1 && d->n_srcs <= VSR_MAX_SRCS, "%s: n_srcs=%d out of range", who, d->n_srcs);
   VSR_CHECK_ARG(d->kc >= 1 && d->nt >= 1, "%s: kc/nt must be positive", who);
   VSR_CHECK_ARG(d->n_groups >= 1 && d->n_taps_total >= 1, "%s: empty group/tap table", who);
@@ -405,7 +405,7 @@ extern "C" int vsr_tapgemm(const VsrTapGemmDesc* d, void* stream) {
   if (d->epi & VSR_EPI_PRELU_BWD) VSR_CHECK_ARG(d->slope_partials, "vsr_tapgemm: PRELU_BWD without slope_partials");
   if (d->epi & VSR_EPI_OUT2) VSR_CHECK_ARG(d->out2 && d->res2, "vsr_tapgemm: OUT2 without out2/res2");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (d->dtype == VSR_BF16) return tapgemm_tc2_launch(d, s);
+  if (d->dtype == VSR_BF16 || d->dtype == VSR_BF16X2) return tapgemm_tc2_launch(d, s);
   return launch_simt<float>(d, s);
 }
 
@@ -435,6 +435,7 @@ extern "C" int vsr_tapgemm_wgrad(const VsrTapGemmDesc* d, float* dw, int accumul
                 vsr_tapgemm_wgrad_workspace(d));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (wgrad_tc_supported(d)) return wgrad_tc_launch(d, dw, nullptr, 0, accumulate, workspace, s);
+  VSR_CHECK_SUPPORTED(d->dtype != VSR_BF16X2, "vsr_tapgemm_wgrad: VSR_BF16X2 is a forward / data-gradient mode (weight gradients take the planes one by one as VSR_BF16)");
   if (d->dtype == VSR_BF16) return launch_wgrad<__nv_bfloat16>(d, dw, accumulate, workspace, s);
   return launch_wgrad<float>(d, dw, accumulate, workspace, s);
 }

@@ -26,6 +26,7 @@
 namespace vsr {
 
 int get_src_map_pub(const VsrTensor4& t, int bw, int bh, CUtensorMap* out);   // tma_host.cu
+int get_f32_map_pub(const VsrTensor4& t, int bw, int bh, CUtensorMap* out);   // fp32 map, box of 32 channels
 void pick_box_pub(int h, int w, int* bw, int* bh);
 
 namespace {
@@ -59,6 +60,10 @@ constexpr int kEpiWarp0 = kProducers + 1;      // first epilogue warp (a multipl
 constexpr int kThreads = 32 * (kEpiWarp0 + kEpiWarps);
 
 constexpr int kEpiIn = VSR_EPI_RES_PRE | VSR_EPI_PRELU_BWD | VSR_EPI_RELU_BWD | VSR_EPI_OUT2;
+// internal flag (never in VsrTapGemmDesc.epi): the split-bf16 mode (dtype VSR_BF16X2) writes the raw fp32 accumulators -
+// one 32-pixel x 64-channel chunk leaves as two [32 x 32 fp32] tiles through an fp32 tensor map; vsr_tap_epilogue
+// applies bias / activation / residuals afterwards in fp32
+constexpr int kEpiF32Out = 0x4000;
 
 struct Tc2Args {
   CUtensorMap maps[VSR_MAX_SRCS];
@@ -343,13 +348,15 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
           if (prof) { p_wait += clock64() - c0; ++p_n; }
           const uint32_t fb = full_bar + 8 * stage;
           const uint32_t sa = stage_base + stage * stage_bytes;
-          const CUtensorMap* map = (a.tall ? a.tall_maps : a.maps) + tap.x;
+          // (split-bf16 mode: bit 3 of the source index selects the low-order plane = images [N, 2N) of the map)
+          const CUtensorMap* map = (a.tall ? a.tall_maps : a.maps) + (tap.x & 7);
+          const int n_img = tc.n + (tap.x >> 3) * a.N;
           if (leader) {
             // attribution runs skip the A (debug & 2) and/or B (debug & 4) transfer, keeping the protocol
             const bool do_a = !(dbg & 2), do_b = !(dbg & 4) && !a.resident;
             const uint32_t tx = (do_a ? a_bytes : 0u) + (do_b ? static_cast<uint32_t>(ndy) * b_bytes : 0u);
             if (tx == 0) { ptx::mbar_arrive(fb); } else { ptx::mbar_arrive_expect_tx(fb, tx); }
-            if (do_a) ptx::tma_load_4d(sa, map, fb, tap.w, tc.x0 + tap.z, tc.y0 + tap.y, tc.n);
+            if (do_a) ptx::tma_load_4d(sa, map, fb, tap.w, tc.x0 + tap.z, tc.y0 + tap.y, n_img);
             if (do_b)
               for (int j = 0; j < ndy; ++j)
                 ptx::bulk_load(sa + a_bytes + j * b_bytes, wbase + static_cast<size_t>(slab0 + j * sstride) * b_full, b_bytes, fb);
@@ -563,7 +570,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
           if (has_in) ptx::mbar_wait(in_bar + 8 * ib, (q >> (ibuf - 1)) & 1u);
           // the TMA store that last used this staging tile must have read it before it is rewritten
           if (lane == 0) {
-            if (obuf == 2) bulk_wait_read1();
+            if (obuf == 2 && !(epi & kEpiF32Out)) bulk_wait_read1();
             else bulk_wait_read0();
           }
           __syncwarp();
@@ -657,6 +664,15 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
               }
             }
             if (prof) { q1 = clock64(); e_math += q1 - q0; }
+            if (epi & kEpiF32Out) {
+              // raw accumulators: half h = 32 channels x 4 bytes = one 128-byte row of staging tile h
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                st_shared_v4(tile_addr(warp_t + h * kTileBytes, lane, j),
+                             make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
+                                        __float_as_uint(v[4 * j + 3])));
+              continue;
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint4 o;
@@ -701,7 +717,10 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
-            if (!(dbg & 16)) {
+            if (epi & kEpiF32Out) {
+              tma_store_4d(&a.out_map, warp_t, grp.x + c, tc.x0 + sub_x, tc.y0 + m * a.bh + sub_y, tc.n);
+              tma_store_4d(&a.out_map, warp_t + kTileBytes, grp.x + c + 32, tc.x0 + sub_x, tc.y0 + m * a.bh + sub_y, tc.n);
+            } else if (!(dbg & 16)) {
               tma_store_4d(&a.out_map, out_t, grp.x + c, tc.x0 + sub_x, tc.y0 + m * a.bh + sub_y, tc.n);
               if (epi & VSR_EPI_OUT2)
                 tma_store_4d(&a.out2_map, res2_t, grp.x + c, tc.x0 + sub_x, tc.y0 + m * a.bh + sub_y, tc.n);
@@ -816,6 +835,7 @@ int tapgemm_tc2_launch(const VsrTapGemmDesc* d, cudaStream_t stream) {
       VSR_TC2_VARIANT(VSR_EPI_BIAS | VSR_EPI_PRELU | VSR_EPI_OUT2),
       VSR_TC2_VARIANT(VSR_EPI_PRELU_BWD),
       VSR_TC2_VARIANT(VSR_EPI_PRELU_BWD | VSR_EPI_RES_PRE),
+      VSR_TC2_VARIANT(kEpiF32Out),
   };
 #undef VSR_TC2_VARIANT
   static bool attr_set = false;
@@ -830,23 +850,31 @@ int tapgemm_tc2_launch(const VsrTapGemmDesc* d, cudaStream_t stream) {
     }
     attr_set = true;
   }
+  const bool split = d->dtype == VSR_BF16X2;
+  if (split) {
+    VSR_CHECK_SUPPORTED(d->epi == 0, "tapgemm(bf16x2): the tensor-core pass writes raw accumulators; run vsr_tap_epilogue for epi %d", d->epi);
+    VSR_CHECK_SUPPORTED(d->n_srcs <= 8, "tapgemm(bf16x2): at most 8 sources (bit 3 of a tap's source index is the plane)");
+  }
+  const int epi_k = split ? kEpiF32Out : d->epi;
   const auto* variant = &kVariants[0];
   for (const auto& v : kVariants)
-    if (v.epi == d->epi) variant = &v;
+    if (v.epi == epi_k) variant = &v;
 
   Tc2Args a;
   memset(&a, 0, sizeof(a));
   int bw, bh;
   pick_box_pub(d->out.h, d->out.w, &bw, &bh);
+  // split-bf16 mode: a source is two bf16 planes [2][n][h][w][c] = one map of 2n images
+  auto planes = [split](VsrTensor4 t) { if (split) t.n *= 2; return t; };
   for (int s = 0; s < d->n_srcs; ++s) {
     VSR_CHECK_ARG(d->srcs[s].c % 8 == 0, "tapgemm(bf16): src channels must be a multiple of 8");
-    int rc = get_src_map_pub(d->srcs[s], bw, bh, &a.maps[s]);
+    int rc = get_src_map_pub(planes(d->srcs[s]), bw, bh, &a.maps[s]);
     if (rc != VSR_OK) return rc;
   }
   // epilogue tensors: one warp = 32 consecutive tile pixels = an ew x eh sub-box
   const int ew = bw < 32 ? bw : 32, eh = 32 / ew;
   {
-    int rc = get_src_map_pub(d->out, ew, eh, &a.out_map);
+    int rc = split ? get_f32_map_pub(d->out, ew, eh, &a.out_map) : get_src_map_pub(d->out, ew, eh, &a.out_map);
     if (rc != VSR_OK) return rc;
     VsrTensor4 t = d->out;
     if (d->epi & VSR_EPI_RES_PRE) {
@@ -874,7 +902,7 @@ int tapgemm_tc2_launch(const VsrTapGemmDesc* d, cudaStream_t stream) {
   a.slope = d->slope;
   a.slope_partials = d->slope_partials;
   a.out_scale = d->out_scale;
-  a.epi = d->epi;
+  a.epi = epi_k;
   a.nt = d->nt;
   a.n_groups = d->n_groups;
   a.N = d->out.n; a.H = d->out.h; a.W = d->out.w; a.Cout = d->out.c;
@@ -903,14 +931,16 @@ int tapgemm_tc2_launch(const VsrTapGemmDesc* d, cudaStream_t stream) {
   // residual / saved-activation tiles arrive two chunks ahead; taken when >= 3 pipeline stages remain
   // (nt <= 64: the warp sets alternate tiles, which already hides both)
   int cand[4][2], n_cand = 0;
-  if (d->nt > 64 && !(d->epi & VSR_EPI_OUT2) && tn.tc_epibuf != 1) {      // (VSR_TC_EPIBUF=1: single staging, for A/B runs)
+  if (split) {
+    cand[n_cand][0] = 2; cand[n_cand++][1] = 1;       // two fp32 half-chunk tiles per warp
+  } else if (d->nt > 64 && !(d->epi & VSR_EPI_OUT2) && tn.tc_epibuf != 1) {      // (VSR_TC_EPIBUF=1: single staging, for A/B runs)
     if (n_in > 0) {
       cand[n_cand][0] = 2; cand[n_cand++][1] = 2;
       cand[n_cand][0] = 1; cand[n_cand++][1] = 2;
     }
     cand[n_cand][0] = 2; cand[n_cand++][1] = 1;
   }
-  cand[n_cand][0] = 1; cand[n_cand++][1] = 1;
+  if (!split) { cand[n_cand][0] = 1; cand[n_cand++][1] = 1; }
   int ndy_max = 1;
   for (int ci = 0; ci < n_cand; ++ci) {
     a.epi_obuf = cand[ci][0];
@@ -965,7 +995,7 @@ int tapgemm_tc2_launch(const VsrTapGemmDesc* d, cudaStream_t stream) {
           a.a_bytes = (int)abox;
           ndy_max = longest;
           for (int s = 0; s < d->n_srcs; ++s) {
-            int rc = get_src_map_pub(d->srcs[s], bw, rows, &a.tall_maps[s]);
+            int rc = get_src_map_pub(planes(d->srcs[s]), bw, rows, &a.tall_maps[s]);
             if (rc != VSR_OK) return rc;
           }
         }

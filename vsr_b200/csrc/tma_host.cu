@@ -70,15 +70,16 @@ EncodeTiledFn get_encode_fn() {
 struct MapKey {
   const void* ptr;
   int n, h, w, c, bw, bh;
+  int f32;      // 1: fp32 map with a box of 32 channels (raw-accumulator output of the split-bf16 mode)
   bool operator==(const MapKey& o) const {
-    return ptr == o.ptr && n == o.n && h == o.h && w == o.w && c == o.c && bw == o.bw && bh == o.bh;
+    return ptr == o.ptr && n == o.n && h == o.h && w == o.w && c == o.c && bw == o.bw && bh == o.bh && f32 == o.f32;
   }
 };
 struct MapKeyHash {
   size_t operator()(const MapKey& k) const {
     size_t h = reinterpret_cast<size_t>(k.ptr);
     auto mix = [&h](size_t v) { h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
-    mix(k.n); mix(k.h); mix(k.w); mix(k.c); mix(k.bw); mix(k.bh);
+    mix(k.n); mix(k.h); mix(k.w); mix(k.c); mix(k.bw); mix(k.bh); mix(k.f32);
     return h;
   }
 };
@@ -86,9 +87,10 @@ struct MapKeyHash {
 std::mutex g_map_mu;
 std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_map_cache;
 
-// 4-D bf16 map over a dense [n][h][w][c] map; box = 64 channels x bw x bh x 1, 128B swizzle.
-int get_src_map(const VsrTensor4& t, int bw, int bh, CUtensorMap* out) {
-  MapKey key{t.ptr, t.n, t.h, t.w, t.c, bw, bh};
+// 4-D bf16 map over a dense [n][h][w][c] map; box = 64 channels x bw x bh x 1, 128B swizzle
+// (f32: fp32 elements, box = 32 channels - the same 128-byte rows).
+int get_src_map(const VsrTensor4& t, int bw, int bh, CUtensorMap* out, int f32 = 0) {
+  MapKey key{t.ptr, t.n, t.h, t.w, t.c, bw, bh, f32};
   {
     std::lock_guard<std::mutex> lk(g_map_mu);
     auto it = g_map_cache.find(key);
@@ -103,12 +105,13 @@ int get_src_map(const VsrTensor4& t, int bw, int bh, CUtensorMap* out) {
     return VSR_ERR_DRIVER;
   }
   cuuint64_t dims[4] = {(cuuint64_t)t.c, (cuuint64_t)t.w, (cuuint64_t)t.h, (cuuint64_t)t.n};
-  cuuint64_t strides[3] = {(cuuint64_t)t.c * 2, (cuuint64_t)t.w * t.c * 2,
-                           (cuuint64_t)t.h * t.w * t.c * 2};
-  cuuint32_t box[4] = {(cuuint32_t)kKc, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+  const cuuint64_t es = f32 ? 4 : 2;
+  cuuint64_t strides[3] = {(cuuint64_t)t.c * es, (cuuint64_t)t.w * t.c * es,
+                           (cuuint64_t)t.h * t.w * t.c * es};
+  cuuint32_t box[4] = {(cuuint32_t)(f32 ? kKc / 2 : kKc), (cuuint32_t)bw, (cuuint32_t)bh, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUtensorMap m;
-  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, t.ptr, dims, strides, box, estr,
+  CUresult r = enc(&m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, t.ptr, dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -151,6 +154,7 @@ void pick_box(int h, int w, int* bw_out, int* bh_out) {
 }  // namespace
 
 int get_src_map_pub(const VsrTensor4& t, int bw, int bh, CUtensorMap* out) { return get_src_map(t, bw, bh, out); }
+int get_f32_map_pub(const VsrTensor4& t, int bw, int bh, CUtensorMap* out) { return get_src_map(t, bw, bh, out, 1); }
 void pick_box_pub(int h, int w, int* bw, int* bh) { pick_box(h, w, bw, bh); }
 
 

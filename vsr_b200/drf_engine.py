@@ -43,11 +43,15 @@ class DrfEngine:
         self.plan, self.ops, self.device = plan, ops, device
         self.act_dtype, self.param_dtype = act_dtype, param_dtype
         dev = device
-        self.fwd_w = torch.empty(plan.fwd_w_numel, dtype=act_dtype, device=dev)
-        self.bwd_w = torch.empty(plan.bwd_w_numel, dtype=act_dtype, device=dev)
+        # precision='bf16x3' (ops.SplitOps): fp32 maps, bf16 weight slabs tripled as [wh | wh | wl] (DrfPlan.split_index)
+        self.split = bool(getattr(ops, "split", False))
+        self.wmul = 3 if self.split else 1
+        w_dtype = torch.bfloat16 if self.split else act_dtype
+        self.fwd_w = torch.empty(self.wmul * plan.fwd_w_numel, dtype=w_dtype, device=dev)
+        self.bwd_w = torch.empty(self.wmul * plan.bwd_w_numel, dtype=w_dtype, device=dev)
         self.fwd_b = torch.empty(plan.fwd_b_numel, dtype=param_dtype, device=dev)
-        self.fwd_w_idx = torch.from_numpy(plan.fwd_w_idx).to(dev)
-        self.bwd_w_idx = torch.from_numpy(plan.bwd_w_idx).to(dev)
+        self.fwd_w_idx = torch.from_numpy(plan.split_index("fwd") if self.split else plan.fwd_w_idx).to(dev)
+        self.bwd_w_idx = torch.from_numpy(plan.split_index("bwd") if self.split else plan.bwd_w_idx).to(dev)
         self.fwd_b_idx = torch.from_numpy(plan.fwd_b_idx).to(dev)
         # un-packing maps (packed weight / bias gradients -> flat bucket), cut at the gradient-bucket boundaries
         self.buckets = []
@@ -91,16 +95,17 @@ class DrfEngine:
     def pack(self, flat, need_bwd):
         """flat fp32 parameter bucket -> packed slabs (one gather kernel per buffer)."""
         self.flat = flat
-        self.ops.gather(flat, self.fwd_w_idx, self.fwd_w)
+        gather_w = self.ops.gather_split if self.split else self.ops.gather
+        gather_w(flat, self.fwd_w_idx, self.fwd_w)
         self.ops.gather(flat, self.fwd_b_idx, self.fwd_b)
         if need_bwd:
-            self.ops.gather(flat, self.bwd_w_idx, self.bwd_w)
+            gather_w(flat, self.bwd_w_idx, self.bwd_w)
 
     def _fw(self, L):
-        return self.fwd_w[L.w_off:L.w_off + L.w_numel]
+        return self.fwd_w[self.wmul * L.w_off:self.wmul * (L.w_off + L.w_numel)]
 
     def _bw(self, L):
-        return self.bwd_w[L.w_off:L.w_off + L.w_numel]
+        return self.bwd_w[self.wmul * L.w_off:self.wmul * (L.w_off + L.w_numel)]
 
     def _fwd(self, lname, srcs, out, extra=0, **kw):
         L = self.plan.fwd[lname]

@@ -404,6 +404,27 @@ class DrfPlan:
             for lv in range(self.out_levels):
                 self._out_level(lv, f"out_block.conv{lv + 1}")
 
+    # ---- precision='bf16x3' (ops.SplitOps): three slabs per tap ------------------------------
+    def split_index(self, which):
+        """packing map of the strict tensor-core mode for `which` in ('fwd', 'bwd'): every layer's slabs tripled group by
+        group as [wh of the group's taps | wh again | wl] (bit 30 of an index = the low-order bf16 part of the parameter:
+        vsr_gather_split), matching SplitOps.table3; layer L's slabs start at 3 * L.w_off"""
+        if which not in self._split_idx:
+            assert self.bf16 and self.kc == 64, "bf16x3 mode uses the bf16 slab layout"
+            base = self.fwd_w_idx if which == "fwd" else self.bwd_w_idx
+            store = self.fwd if which == "fwd" else self.bwd
+            chunks = []
+            for L in store.values():
+                slab = L.table.nt * 64
+                begin = L.w_off
+                for _, taps in L.table.groups:
+                    g = base[begin:begin + len(taps) * slab].astype(np.int64)
+                    chunks += [g, g, np.where(g >= 0, g | (1 << 30), -1)]
+                    begin += len(taps) * slab
+                assert begin == L.w_off + L.w_numel
+            self._split_idx[which] = np.concatenate(chunks).astype(np.int32)
+        return self._split_idx[which]
+
     # ---- gradient buckets ------------------------------------------------------------------
     def grad_buckets(self, n_buckets=3):
         """Contiguous ranges [lo, hi) of the flat gradient bucket with the tap-GEMM layers whose weight and bias
@@ -463,6 +484,7 @@ class DrfPlan:
 
         self.fwd_w_idx, self.fwd_b_idx = pack(self.fwd)
         self.bwd_w_idx, _ = pack(self.bwd)
+        self._split_idx = {}
         # weight-gradient un-packing: packed dW is in PLAIN [T][nt][kc] order at the same offsets.
         # For every parameter element list the packed positions that accumulate into it.
         pidx_all, ppos_all = [], []

@@ -17,7 +17,11 @@ import torch.nn as nn
 from .drf_engine import DrfEngine
 from .drf_plan import PROJ, DrfPlan
 
-_PRECISIONS = {"fp32": torch.float32, "bf16": torch.bfloat16}
+# 'fp32': CUDA-core strict mode; 'bf16': bf16 storage + tcgen05; 'bf16x3' (alias 'tf32': the reference configs' name for
+# "tensor cores, fp32 storage"): fp32 storage, every product as three bf16 tcgen05 products (ops.SplitOps) - strict
+# mode accuracy (<= 1e-4 of the reference) on tensor cores
+_PRECISIONS = {"fp32": torch.float32, "bf16": torch.bfloat16, "bf16x3": torch.float32, "tf32": torch.float32}
+_TC_LAYOUT = ("bf16", "bf16x3", "tf32")      # plans with 64-channel taps and swizzled bf16 weight slabs
 
 
 class BaseNet(nn.Module):
@@ -138,7 +142,7 @@ class _DRFBase(BaseNet):
             self.r_block = _seq(deconv1=nn.ConvTranspose2d(F, F, k, s_, p_), prelu1=_prelu(),
                                 conv2=nn.Conv2d(F, out_channels, 3, padding=1))
         self._plan = DrfPlan(in_channels, out_channels, F, num_groups, upscale_factor,
-                             bf16=(precision == "bf16"), variant=self._variant)
+                             bf16=(precision in _TC_LAYOUT), variant=self._variant)
         names = [n for n, _ in self.named_parameters()]
         assert names == list(self._plan.params), "parameter order differs from the plan"
         self._engine = None
@@ -178,8 +182,8 @@ class _DRFBase(BaseNet):
             return self._ops
         if self.flat.device.type != "cuda":
             raise RuntimeError("vsr_b200 nets run on CUDA only (there is no CPU fallback); call .to('cuda')")
-        from .ops import cuda_ops
-        return cuda_ops()
+        from .ops import cuda_ops, split_ops
+        return split_ops() if self.precision in ("bf16x3", "tf32") else cuda_ops()
 
     def _run(self, frames):
         if not self._is_flat():
@@ -208,7 +212,8 @@ class DRFNet(_DRFBase):
     """Deep Recurrent Feedback Network for video SR (reference: drf_net.py:8-49).
 
     Args: in_channels, out_channels, num_features, num_groups, upscale_factor (2, 3, 4 or 8) — as the
-    reference; precision ('fp32' = CUDA-core strict mode, 'bf16' = tcgen05 tensor-core mode).
+    reference; precision ('fp32' = CUDA-core strict mode, 'bf16' = tcgen05 tensor-core mode, 'bf16x3' / 'tf32' = strict
+    accuracy on tensor cores: fp32 maps, three bf16 tcgen05 products per product; num_features % 64 == 0).
     forward(list of T tensors [N,C,h,w]) -> list of T tensors [N,C,r*h,r*w].
     """
 

@@ -604,7 +604,143 @@ class CudaOps:
         self.launches += 1
 
 
+LO_FLAG = 1 << 30      # vsr_gather_split: bit 30 of an index = the low-order bf16 part of the parameter
+
+
+class SplitOps(CudaOps):
+    """precision='bf16x3': the strict mode on tensor cores (csrc/split.cu, VSR_BF16X2 in include/vsr_b200.h).
+
+    The engine keeps fp32 maps; a tap-GEMM here is  split every source into two bf16 planes -> the tcgen05 kernel on a
+    3x-expanded tap table (xh*wh + xl*wh + xh*wl, raw fp32 accumulators into `out`) -> the epilogue in fp32, in place.
+    A weight gradient is three launches of the tcgen05 weight-gradient kernel on the ORIGINAL table
+    (src_h x dz_h, src_l x dz_h, src_h x dz_l: the planes are plain bf16 maps) reduced together in a fixed order.
+    Weight buffers hold [wh | wh | wl] slabs per group (DrfPlan.split_index).  Everything else (first / last
+    convolution, activations, losses, Adam) is the fp32 arithmetic of precision='fp32'."""
+    name = "cuda-bf16x3"
+    split = True
+
+    def __init__(self):
+        super().__init__()
+        self._wg_ws = None
+        self._db_dummy = None
+
+    def _planes(self, t, cache=None):
+        """fp32 [n,h,w,c] -> bf16 [2,n,h,w,c]: t = planes[0] + planes[1] to 16 significant bits"""
+        if cache is not None and t.data_ptr() in cache:
+            return cache[t.data_ptr()]
+        _need_cuda(t)
+        if t.dtype != torch.float32:
+            raise _lib.VsrError("bf16x3 mode takes fp32 maps")
+        pl = torch.empty((2, *t.shape), dtype=torch.bfloat16, device=t.device)
+        check(self.lib.vsr_split_planes(_p(t), _p(pl), t.numel(), _stream()), "vsr_split_planes")
+        self.launches += 1
+        if cache is not None:
+            cache[t.data_ptr()] = pl
+        return pl
+
+    @staticmethod
+    def table3(tab: TapTable) -> TapTable:
+        """every tap (s, dy, dx, c0) -> high plane x wh, low plane (source index | 8) x wh, high plane x wl; the slabs of a
+        group are ordered [wh of all taps | wh of all taps | wl of all taps] like its taps"""
+        t3 = tab._dev.get("x3")
+        if t3 is None:
+            groups = []
+            for o0, taps in tab.groups:
+                for s, _, _, _ in taps:
+                    if s >= 8:
+                        raise _lib.VsrError("bf16x3: at most 8 sources per tap-GEMM")
+                groups.append((o0, list(taps) + [(s | 8, dy, dx, c0) for s, dy, dx, c0 in taps] + list(taps)))
+            t3 = tab._dev["x3"] = TapTable(tab.kc, tab.nt, groups, useful=tab.useful)
+        return t3
+
+    def tapgemm(self, tab, srcs, out, w, bias=None, epi=0, out_scale=1.0, slope=None, residual=None,
+                aux_y=None, out2=None, res2=None, slope_partials=None, force_simt=False):
+        _need_cuda(out, w, bias, slope, residual, aux_y, out2, res2, slope_partials)
+        if out.dtype != torch.float32 or w.dtype != torch.bfloat16:
+            raise _lib.VsrError("bf16x3 mode: fp32 maps, bf16 [wh | wh | wl] weight slabs")
+        cache = {}
+        planes = [self._planes(s, cache) for s in srcs]
+        t3 = self.table3(tab)
+        if w.numel() != t3.n_taps_total * t3.nt * t3.kc:
+            raise _lib.VsrError("bf16x3 mode: the weight buffer must hold three slabs per tap")
+        d = VsrTapGemmDesc()
+        d.dtype = _lib.VSR_BF16X2
+        d.kc, d.nt, d.n_srcs = t3.kc, t3.nt, len(srcs)
+        for i, (s, pl) in enumerate(zip(srcs, planes)):
+            n, h, w_, c = s.shape
+            d.srcs[i] = VsrTensor4(pl.data_ptr(), n, h, w_, c)
+        d.out = _tensor4(out)
+        gt, tt = t3.device_tabs(out.device)
+        d.n_groups, d.n_taps_total = t3.n_groups, t3.n_taps_total
+        d.max_group_taps = max(len(t) for _, t in t3.groups)
+        d.group_tab, d.tap_tab = gt.data_ptr(), tt.data_ptr()
+        d.tap_tab_host = t3.host_taps().data_ptr()
+        d.group_tab_host = t3.host_groups().data_ptr()
+        d.w, d.epi, d.out_scale = w.data_ptr(), 0, 1.0
+        pix = out.shape[0] * out.shape[1] * out.shape[2]
+        if self.timing is not None:
+            sig = f"x3_taps{tab.n_taps_total}_nt{tab.nt}_g{tab.n_groups}_px{pix}_epi{epi}"
+            nbytes = 4 * (sum(pix * s.shape[-1] for s in srcs) + pix * out.shape[-1])
+            self._meta = ("tapgemm", 2.0 * pix * tab.n_taps_total * tab.nt * tab.kc * tab.useful, sig, nbytes)
+        check(self.lib.vsr_tapgemm(C.byref(d), _stream()), "vsr_tapgemm(bf16x2)")
+        self._meta = None
+        check(self.lib.vsr_tap_epilogue(_p(out), pix, out.shape[-1], _p(bias), epi, float(out_scale), _p(slope), _p(residual),
+                                        _p(aux_y), _p(out2), _p(res2), _p(slope_partials), _stream()), "vsr_tap_epilogue")
+        self.launches += 2 if epi else 1
+
+    def tapgemm_wgrad_workspace(self, tab, srcs, dz):
+        return 16            # the three-slice workspace is this backend's own (tapgemm_wgrad)
+
+    def tapgemm_wgrad_partial(self, tab, srcs, dz, workspace, slice_, n_slices, db_period):
+        return False         # per-frame deferral is not used in this mode: one three-term launch set per call
+
+    def tapgemm_wgrad(self, tab, srcs, dz, dw, accumulate, workspace, db=None, db_period=0):
+        """dw (+)= src_h x dz_h + src_l x dz_h + src_h x dz_l; returns False: the bias gradient is the caller's fp32 colsum"""
+        _need_cuda(dw, dz, *srcs)
+        cache = {}
+        pl_s = [self._planes(s, cache) for s in srcs]
+        pl_z = self._planes(dz, cache)
+        hi, lo = [p[0] for p in pl_s], [p[1] for p in pl_s]
+        period = dz.shape[-1]
+        terms = ((hi, pl_z[0]), (lo, pl_z[0]), (hi, pl_z[1]))
+        descs = [_make_desc(tab, ss, zz) for ss, zz in terms]
+        need = 3 * self.lib.vsr_tapgemm_wgrad_workspace(C.byref(descs[0]))
+        if self._wg_ws is None or self._wg_ws.numel() * 4 < need or self._wg_ws.device != dz.device:
+            self._wg_ws = torch.empty((need + 3) // 4, dtype=torch.float32, device=dz.device)
+        if self._db_dummy is None or self._db_dummy.numel() < period or self._db_dummy.device != dz.device:
+            self._db_dummy = torch.empty(max(period, 1024), dtype=torch.float32, device=dz.device)
+        ws, nbytes = self._wg_ws, self._wg_ws.numel() * 4
+        if self.timing is not None:
+            m = self._wgrad_meta(tab, srcs, dz)
+            self._meta = (m[0], m[1], "x3_" + m[2], m[3])
+        deferred = True
+        for k, d in enumerate(descs):
+            rc = self.lib.vsr_tapgemm_wgrad_partial(C.byref(d), period, k, 3, _p(ws), nbytes, _stream())
+            if rc < 0:
+                check(rc, "vsr_tapgemm_wgrad_partial")
+            if rc != 1:          # a shape outside the one-reduction path (maps wider than 1024 channels, ...): term by term
+                deferred = False
+                break
+        if deferred:
+            check(self.lib.vsr_tapgemm_wgrad_finish(C.byref(descs[0]), _p(dw), _p(self._db_dummy), period, int(accumulate), 3, 3,
+                                                    _p(ws), nbytes, _stream()), "vsr_tapgemm_wgrad_finish")
+            self.launches += 4
+        else:
+            for k, d in enumerate(descs):
+                check(self.lib.vsr_tapgemm_wgrad(C.byref(d), _p(dw), int(accumulate or k > 0), _p(ws), nbytes, _stream()),
+                      "vsr_tapgemm_wgrad")
+            self.launches += 6
+        self._meta = None
+        return False
+
+    def gather_split(self, src, idx, dst):
+        _need_cuda(src, idx, dst)
+        check(self.lib.vsr_gather_split(_p(src), _p(idx), _p(dst), idx.numel(), _stream()), "vsr_gather_split")
+        self.launches += 1
+
+
 _OPS = None
+_SPLIT_OPS = None
 
 
 def cuda_ops() -> CudaOps:
@@ -612,6 +748,13 @@ def cuda_ops() -> CudaOps:
     if _OPS is None:
         _OPS = CudaOps()
     return _OPS
+
+
+def split_ops() -> SplitOps:
+    global _SPLIT_OPS
+    if _SPLIT_OPS is None:
+        _SPLIT_OPS = SplitOps()
+    return _SPLIT_OPS
 
 
 def slab_index(j, k):
