@@ -619,23 +619,52 @@ class SplitOps(CudaOps):
     name = "cuda-bf16x3"
     split = True
 
+    # Plane cache: a map is split once per step, not once per consumer (an LR feature map of DRFNet feeds up to G 1x1
+    # convolutions, a gradient map several data gradients and a weight gradient).  An entry is keyed by the byte range of
+    # the fp32 map; it dies when a tap-GEMM of this backend writes an overlapping range (`out` / `out2`) and ALL entries
+    # die on every other kernel-launching method (they may write maps: first / last convolution, activation backward, ...;
+    # `gather_split`, the first launch of every step, clears the cache too).  Only methods that cannot write a map are
+    # exempt (_READ_ONLY).  Tensors written behind this backend's back (torch ops) must be complete before the next
+    # cache-clearing launch: the engines only do that to raw frames and to the stacked hidden state, both assembled before
+    # the last convolution of the forward pass.
+    _READ_ONLY = ("tapgemm", "tapgemm_wgrad", "tapgemm_wgrad_workspace", "tapgemm_wgrad_partial", "colsum", "colsum_workspace",
+                  "reduce_partials", "gather", "gather_add", "conv3x3_first_bwd", "conv3x3_first_bwd_workspace",
+                  "conv3x3_last_bwd_workspace", "metric_workspace", "start_timing", "stop_timing", "gemm_records", "table3")
+
     def __init__(self):
         super().__init__()
         self._wg_ws = None
         self._db_dummy = None
+        self._cache = {}
 
-    def _planes(self, t, cache=None):
+    def __getattribute__(self, name):
+        attr = object.__getattribute__(self, name)
+        if name.startswith("_") or not callable(attr) or name in SplitOps._READ_ONLY:
+            return attr
+        object.__getattribute__(self, "_cache").clear()       # a launch that may write maps: every cached plane pair dies
+        return attr
+
+    def _invalidate(self, t):
+        if t is None or not self._cache:
+            return
+        lo = t.data_ptr()
+        hi = lo + t.numel() * t.element_size()
+        for k in [k for k in self._cache if k[0] < hi and lo < k[1]]:
+            del self._cache[k]
+
+    def _planes(self, t, cached=True):
         """fp32 [n,h,w,c] -> bf16 [2,n,h,w,c]: t = planes[0] + planes[1] to 16 significant bits"""
-        if cache is not None and t.data_ptr() in cache:
-            return cache[t.data_ptr()]
+        key = (t.data_ptr(), t.data_ptr() + t.numel() * 4)
+        if cached and key in self._cache:
+            return self._cache[key]
         _need_cuda(t)
         if t.dtype != torch.float32:
             raise _lib.VsrError("bf16x3 mode takes fp32 maps")
         pl = torch.empty((2, *t.shape), dtype=torch.bfloat16, device=t.device)
         check(self.lib.vsr_split_planes(_p(t), _p(pl), t.numel(), _stream()), "vsr_split_planes")
         self.launches += 1
-        if cache is not None:
-            cache[t.data_ptr()] = pl
+        if cached:
+            self._cache[key] = pl
         return pl
 
     @staticmethod
@@ -658,8 +687,9 @@ class SplitOps(CudaOps):
         _need_cuda(out, w, bias, slope, residual, aux_y, out2, res2, slope_partials)
         if out.dtype != torch.float32 or w.dtype != torch.bfloat16:
             raise _lib.VsrError("bf16x3 mode: fp32 maps, bf16 [wh | wh | wl] weight slabs")
-        cache = {}
-        planes = [self._planes(s, cache) for s in srcs]
+        self._invalidate(out)
+        self._invalidate(out2)
+        planes = [self._planes(s) for s in srcs]
         t3 = self.table3(tab)
         if w.numel() != t3.n_taps_total * t3.nt * t3.kc:
             raise _lib.VsrError("bf16x3 mode: the weight buffer must hold three slabs per tap")
@@ -697,9 +727,9 @@ class SplitOps(CudaOps):
     def tapgemm_wgrad(self, tab, srcs, dz, dw, accumulate, workspace, db=None, db_period=0):
         """dw (+)= src_h x dz_h + src_l x dz_h + src_h x dz_l; returns False: the bias gradient is the caller's fp32 colsum"""
         _need_cuda(dw, dz, *srcs)
-        cache = {}
-        pl_s = [self._planes(s, cache) for s in srcs]
-        pl_z = self._planes(dz, cache)
+        # (saved activations feed several weight gradients - the LR / HR feature lists of DRFNet - so their planes are cached
+        # like the tap-GEMM sources; a gradient map feeds one weight gradient: split, not kept)
+        pl_s, pl_z = [self._planes(s) for s in srcs], self._planes(dz, cached=False)
         hi, lo = [p[0] for p in pl_s], [p[1] for p in pl_s]
         period = dz.shape[-1]
         terms = ((hi, pl_z[0]), (lo, pl_z[0]), (hi, pl_z[1]))
