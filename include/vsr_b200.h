@@ -447,6 +447,37 @@ int vsr_grid_warp_bwd(const float* img, const float* flow, const float* dout, in
 int vsr_s2d_cat(const float* hr, const float* lr, int32_t n, int32_t h, int32_t w, int32_t r, int32_t cpad, float* out, void* stream);
 int vsr_s2d_cat_bwd(const float* dout, int32_t n, int32_t h, int32_t w, int32_t r, int32_t cpad, float* dhr, void* stream);
 
+/*
+ * ---- TOFlowNet (toflow_net.py:33-138): bicubic input up-sampling, padding with the batch minimum, SpyNet's pyramid, the flow
+ * warp fused with the concatenations, the flow update and the output head.  Images and flows are planar ([n][k][h][w]),
+ * feature maps pixel-major [n][h][w][c]; the convolutions and BatchNorm2d run on vsr_tapgemm / vsr_bn_*. --------------------- */
+/* F.interpolate(scale_factor=r, mode='bicubic', align_corners=False) (toflow_net.py:34-36): [nc][h][w] -> [nc][rh][rw] */
+int vsr_upsample_bicubic(const float* x, int32_t nc, int32_t h, int32_t w, int32_t r, float* y, void* stream);
+/* x.min() kept on the device (toflow_net.py:47 pads with it): `partials` (vsr_partials_len() floats) receives partial minima
+ * (+inf in the unused rows); vsr_pad_fill folds them and writes F.pad(x, (x0, wp-w-x0, y0, hp-h-y0), value=min) */
+int vsr_min_partials(const float* x, int64_t numel, float* partials, void* stream);
+int vsr_pad_fill(const float* x, int32_t nc, int32_t h, int32_t w, int32_t y0, int32_t x0, int32_t hp, int32_t wp,
+                 const float* partials, float* out, void* stream);
+/* F.avg_pool2d(x, 2, 2) of planar images, even sizes (SpyNet.forward, toflow_net.py:76-78) */
+int vsr_avgpool2x2(const float* x, int32_t nc, int32_t h, int32_t w, float* y, void* stream);
+/* torch.cat([ref, flow_warp(nbr, scale * flow), scale * flow]) into channels c_ref, c_w, c_flow..c_flow+1 of a pixel-major map
+ * (toflow_net.py:83-85; ref / nbr may be NULL, c_flow < 0 = no flow channels; other channels are not written); flow_warp =
+ * grid_sample(bilinear, zeros) of the pixel mesh + flow (toflow_net.py:117-138).  _bwd: gradient w.r.t. the stored flow. */
+int vsr_warp_cat(float* out, int32_t n, int32_t h, int32_t w, int32_t cpad, int32_t c_ref, const float* ref, int32_t c_w,
+                 const float* nbr, const float* flow, float scale, int32_t c_flow, void* stream);
+int vsr_warp_cat_bwd(const float* dout, int32_t n, int32_t h, int32_t w, int32_t cpad, int32_t c_w, const float* nbr,
+                     const float* flow, float scale, int32_t c_flow, float* dflow, void* stream);
+/* flow[n][2][h][w] = scale * flow_up + z[..., 0:2] (toflow_net.py:82-83) */
+int vsr_flow_add(const float* z, int32_t n, int32_t h, int32_t w, int32_t cz, const float* flow_up, float scale, float* flow,
+                 void* stream);
+/* dz[n][hp][wp][cz] = d[n][kc][h][w] in channels < kc of the window at (y0, x0), zero elsewhere (gradient of "first kc
+ * channels of a pixel-major map, cropped": the flow update and the output head) */
+int vsr_planar_to_nhwc(const float* d, int32_t n, int32_t kc, int32_t hp, int32_t wp, int32_t cz, int32_t y0, int32_t x0,
+                       int32_t h, int32_t w, float* dz, void* stream);
+/* out[n][1][h][w] = z[n][y+y0][x+x0][0] + xref[n][y+y0][x+x0] (toflow_net.py:59-65: out_block(x) + x_ref, un-padded) */
+int vsr_head_add(const float* z, int32_t n, int32_t hp, int32_t wp, int32_t cz, const float* xref, int32_t y0, int32_t x0,
+                 int32_t h, int32_t w, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -576,6 +576,74 @@ class EmuOps:
         dhr.copy_(F.pixel_shuffle(dout[..., :r * r].permute(0, 3, 1, 2), r))
         self.launches += 1
 
+    # ---- TOFlowNet (csrc/toflow.cu) ----
+    def upsample_bicubic(self, x, r, y):
+        y.copy_(F.interpolate(x.reshape(-1, 1, *x.shape[-2:]), scale_factor=r, mode="bicubic", align_corners=False).reshape(y.shape))
+        self.launches += 1
+
+    def min_partials(self, x, partials):
+        partials.fill_(float("inf"))
+        partials[0] = x.min()
+        self.launches += 1
+
+    def pad_fill(self, x, y0, x0, partials, out):
+        h, w = x.shape[-2:]
+        out.copy_(torch.full_like(out, float(partials.min())))
+        out[..., y0:y0 + h, x0:x0 + w] = x
+        self.launches += 1
+
+    def avgpool2x2(self, x, y):
+        y.copy_(F.avg_pool2d(x.reshape(-1, 1, *x.shape[-2:]), 2, 2).reshape(y.shape))
+        self.launches += 1
+
+    @staticmethod
+    def _toflow_warp(nbr, flow):
+        n, _, h, w = flow.shape
+        gy, gx = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
+        vx = gx.to(flow.dtype).to(flow.device) + flow[:, 0]
+        vy = gy.to(flow.dtype).to(flow.device) + flow[:, 1]
+        grid = torch.stack((2.0 * vx / max(w - 1, 1) - 1.0, 2.0 * vy / max(h - 1, 1) - 1.0), dim=3)
+        return F.grid_sample(nbr.reshape(n, 1, h, w), grid, mode="bilinear", padding_mode="zeros", align_corners=False)[:, 0]
+
+    def warp_cat(self, out, c_ref, ref, c_w, nbr, flow, scale, c_flow):
+        n, h, w, _ = out.shape
+        if ref is not None:
+            out[..., c_ref] = ref.reshape(n, h, w)
+        f = scale * flow if flow is not None else torch.zeros(n, 2, h, w, dtype=out.dtype, device=out.device)
+        if nbr is not None:
+            out[..., c_w] = self._toflow_warp(nbr, f)
+        if c_flow >= 0:
+            out[..., c_flow:c_flow + 2] = f.permute(0, 2, 3, 1)
+        self.launches += 1
+
+    def warp_cat_bwd(self, dout, c_w, nbr, flow, scale, c_flow, dflow):
+        g = torch.zeros_like(flow)
+        if nbr is not None:
+            with torch.enable_grad():
+                f = flow.detach().clone().requires_grad_(True)
+                o = self._toflow_warp(nbr, scale * f)
+                g = torch.autograd.grad(o, f, dout[..., c_w].contiguous())[0]
+        if c_flow >= 0:
+            g = g + scale * dout[..., c_flow:c_flow + 2].permute(0, 3, 1, 2)
+        dflow.copy_(g)
+        self.launches += 1
+
+    def flow_add(self, z, flow_up, scale, flow):
+        flow.copy_(scale * flow_up + z[..., :2].permute(0, 3, 1, 2))
+        self.launches += 1
+
+    def planar_to_nhwc(self, d, y0, x0, dz):
+        n, kc, h, w = d.shape
+        dz.zero_()
+        dz[:, y0:y0 + h, x0:x0 + w, :kc] = d.permute(0, 2, 3, 1)
+        self.launches += 1
+
+    def head_add(self, z, xref, y0, x0, out):
+        h, w = out.shape[-2:]
+        n = z.shape[0]
+        out.copy_((z[:, y0:y0 + h, x0:x0 + w, 0] + xref.reshape(n, *z.shape[1:3])[:, y0:y0 + h, x0:x0 + w]).reshape(out.shape))
+        self.launches += 1
+
     def adam_flat(self, p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
         gi = g * grad_scale
         if weight_decay != 0:

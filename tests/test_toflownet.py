@@ -38,3 +38,186 @@ def test_oracle_restatement_matches_reference_golden(path):
         assert abs(float(grads[k].norm()) - float(dg["norm"])) <= 1e-3 * float(dg["norm"]) + 1e-8, k
     for k, v in buffers.items():
         assert (v - fx["buffers_after"][k]).abs().max() <= 1e-5 * max(1.0, float(fx["buffers_after"][k].abs().max())), k
+
+
+def _oracle64(fx):
+    return _oracle(fx, torch.float64)
+
+
+def _grad_err(got, ref64):
+    gmax = max(float(g.abs().max()) for g in ref64.values())
+    worst = num = den = 0.0
+    for k, g in ref64.items():
+        d = got[k].double().cpu() - g
+        worst = max(worst, float(d.abs().max()) / gmax)
+        num += float((d ** 2).sum())
+        den += float((g ** 2).sum())
+    return worst, (num / den) ** 0.5
+
+
+def _load(fx, dtype=torch.float32):
+    from vsr_b200.toflow import TOFlowNet
+    net = TOFlowNet(**fx["kwargs"])
+    net.load_state_dict(_state(fx))
+    return net.to(dtype).train()
+
+
+def test_state_dict_contract():
+    from vsr_b200.toflow import TOFlowNet
+    fx = torch.load(CASES[0])
+    net = TOFlowNet(**fx["kwargs"])
+    sd = net.state_dict()
+    assert list(sd) == list(fx["state_shapes"])
+    assert {k: tuple(v.shape) for k, v in sd.items()} == fx["state_shapes"]
+    assert {k: v.dtype for k, v in sd.items()} == fx["state_dtypes"]
+    assert net.ref_idx == 1 and TOFlowNet(1, 1, 4, 2).ref_idx == 1 and TOFlowNet(1, 1, 7, 4).ref_idx == 3     # toflow_net.py:21
+    with pytest.raises(ValueError):
+        TOFlowNet(1, 1, 3, 2, precision="bf16")
+    with pytest.raises(RuntimeError):
+        net([torch.zeros(1, 1, 8, 8)] * 3)           # no CPU fallback
+
+
+@pytest.mark.parametrize("path", CASES, ids=ids)
+def test_host_logic_exact_in_float64(path):
+    """tables, packing maps, the recorded backward and the BatchNorm buffer updates in float64 through the emulation = the
+    float64 oracle to round-off: whatever differs in fp32 is arithmetic, not logic"""
+    from tests.emu import EmuOps
+    fx = torch.load(path)
+    out64, loss64, g64, buf64 = _oracle64(fx)
+    net = _load(fx, torch.float64)
+    net._ops = EmuOps()
+    out = net([x.double() for x in fx["inputs"]])
+    assert out.shape == fx["output"].shape
+    assert (out.detach() - out64.detach()).abs().max() <= 1e-9 * float(out64.abs().max())
+    restated.mse_loss(out, fx["target"].double()).backward()
+    worst, l2 = _grad_err({k: p.grad.detach() for k, p in net.named_parameters()}, g64)
+    assert worst <= 1e-9 and l2 <= 1e-9, (worst, l2)
+    sd = net.state_dict()
+    for k, v in buf64.items():
+        assert (sd[k].double() - v).abs().max() <= 1e-9 * max(1.0, float(v.abs().max())), k
+    for k, v in fx["buffers_after"].items():
+        if "num_batches" in k:
+            assert int(sd[k]) == int(v), k
+
+
+def _check_net(net, fx, device, grad_floor):
+    """outputs, loss and running buffers against the golden of the real reference at 1e-4 / 1e-5; gradients against the
+    oracle in FLOAT64.  d(loss)/d(flow) is a difference of neighbouring pixels of the warped frame and the SpyNet pyramid is
+    full of kinks (ReLU after every BatchNorm, the warp's cell): like FRVSRNet's flow net the fp32 gradients are
+    ill-conditioned whoever computes them - the bar is `grad_floor` or four times the fp32 oracle's own distance from
+    float64, whichever is larger (stated; measured values are printed)."""
+    _, _, g32, _ = _oracle(fx)
+    _, _, g64, _ = _oracle64(fx)
+    out = net([x.to(device) for x in fx["inputs"]])
+    assert out.shape == fx["output"].shape
+    assert (out.detach().cpu() - fx["output"]).abs().max() <= 1e-4 * fx["output"].abs().max()
+    loss = torch.nn.MSELoss()(out, fx["target"].to(device))
+    assert abs(float(loss) - float(fx["loss"])) <= 1e-5 * float(fx["loss"])
+    loss.backward()
+    sd = net.state_dict()
+    for k, v in fx["buffers_after"].items():
+        if "num_batches" in k:
+            assert int(sd[k]) == int(v), k
+        else:
+            assert (sd[k].cpu() - v).abs().max() <= 1e-5 * max(1.0, float(v.abs().max())), k
+    e_ref = _grad_err(g32, g64)
+    e_got = _grad_err({k: p.grad.detach() for k, p in net.named_parameters()}, g64)
+    print(f"TOFlowNet gradient error vs the float64 oracle (worst / L2): ours {e_got[0]:.2e} / {e_got[1]:.2e}, "
+          f"the fp32 oracle {e_ref[0]:.2e} / {e_ref[1]:.2e}")
+    assert e_got[0] <= max(grad_floor, 4 * e_ref[0]) and e_got[1] <= max(grad_floor, 4 * e_ref[1])
+
+
+@pytest.mark.parametrize("path", CASES, ids=ids)
+def test_plan_and_recorded_backward_through_the_emulation(path):
+    from tests.emu import EmuOps
+    fx = torch.load(path)
+    net = _load(fx)
+    net._ops = EmuOps()
+    _check_net(net, fx, "cpu", 1e-4)
+
+
+def test_eval_mode_uses_running_buffers():
+    from tests.emu import EmuOps
+    fx = torch.load(CASES[0])
+    net = _load(fx).eval()
+    net._ops = EmuOps()
+    sd = {k: v.clone() for k, v in _state(fx).items()}
+    with torch.no_grad():
+        out = net(fx["inputs"])
+        ref = restated.toflownet_forward(fx["inputs"], sd, fx["kwargs"]["upscale_factor"], training=False)
+    assert (out - ref).abs().max() <= 1e-4 * ref.abs().max()
+    for k, v in net.state_dict().items():
+        assert torch.equal(v, sd[k]), k              # buffers untouched
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", CASES, ids=ids)
+def test_gpu_matches_reference_golden(path):
+    fx = torch.load(path)
+    _check_net(_load(fx).cuda(), fx, "cuda", 1e-4)
+
+
+@pytest.mark.gpu
+def test_gpu_eval_mode_and_larger_frames():
+    """eval mode (running buffers) and a batch of larger, non-padded frames on the device against the oracle"""
+    fx = torch.load(CASES[0])
+    net = _load(fx).cuda().eval()
+    sd = _state(fx)
+    g = torch.Generator().manual_seed(5)
+    base = torch.randn(3, 1, 24, 32, generator=g)
+    inputs = [base + 0.2 * torch.randn(3, 1, 24, 32, generator=g) for _ in range(3)]
+    with torch.no_grad():
+        out = net([x.cuda() for x in inputs])
+        ref = restated.toflownet_forward(inputs, sd, fx["kwargs"]["upscale_factor"], training=False)
+    assert (out.cpu() - ref).abs().max() <= 1e-4 * ref.abs().max()
+
+
+@pytest.mark.gpu
+def test_toflow_kernels_match_the_emulation():
+    """csrc/toflow.cu against the torch emulation: bicubic up-sampling, minimum + padding, average pooling, warp + concat and
+    its flow gradient, flow update, channel scatter, output head"""
+    from tests.emu import EmuOps
+    from vsr_b200.ops import cuda_ops
+    ops, emu = cuda_ops(), EmuOps()
+    g = torch.Generator(device="cuda").manual_seed(4)
+    rnd = lambda *s: torch.randn(*s, device="cuda", generator=g)
+
+    def both(fn, outs):
+        res = []
+        for o in (ops, emu):
+            bufs = [torch.full_like(t, 7) for t in outs]
+            fn(o, *bufs)
+            res.append(bufs)
+        return res
+
+    for r, (h, w) in ((2, (16, 16)), (4, (6, 10)), (3, (5, 7))):
+        x = rnd(3, 2, h, w)
+        (y,), (ye,) = both(lambda o, y: o.upsample_bicubic(x, r, y), [torch.empty(3, 2, h * r, w * r, device="cuda")])
+        assert (y - ye).abs().max() <= 2e-6 * float(ye.abs().max())
+    x = rnd(4, 3, 24, 40)
+    (p,), (pe,) = both(lambda o, p: o.min_partials(x, p), [torch.empty(ops.partials_len, device="cuda")])
+    assert float(p.min()) == float(x.min()) == float(pe.min())
+    (q,), (qe,) = both(lambda o, q: o.pad_fill(x, 4, 3, p, q), [torch.empty(4, 3, 32, 48, device="cuda")])
+    assert torch.equal(q, qe)
+    (a,), (ae,) = both(lambda o, a: o.avgpool2x2(x, a), [torch.empty(4, 3, 12, 20, device="cuda")])
+    assert (a - ae).abs().max() <= 1e-6
+    for (h, w, mag, scale) in ((16, 16, 0.7, 2.0), (12, 20, 3.0, 1.0), (2, 2, 0.5, 2.0), (48, 32, 0.1, 1.0)):
+        ref, nbr, flow = rnd(2, h, w), rnd(2, h, w), rnd(2, 2, h, w) * mag
+        (o1,), (o2,) = both(lambda o, out: (out.zero_(), o.warp_cat(out, 0, ref, 1, nbr, flow, scale, 2)), [torch.empty(2, h, w, 16, device="cuda")])
+        assert (o1 - o2).abs().max() <= 2e-5 * max(1.0, float(nbr.abs().max()))
+        dout = rnd(2, h, w, 16)
+        (d1,), (d2,) = both(lambda o, d: o.warp_cat_bwd(dout, 1, nbr, flow, scale, 2, d), [torch.empty_like(flow)])
+        bad = (d1 - d2).abs() > 1e-4 * max(1.0, float(d2.abs().max()))       # a sample on a cell boundary may take the next cell
+        assert int(bad.sum()) <= 2, int(bad.sum())
+        (d1,), (d2,) = both(lambda o, d: o.warp_cat_bwd(dout, 5, nbr, flow, scale, -1, d), [torch.empty_like(flow)])
+        bad = (d1 - d2).abs() > 1e-4 * max(1.0, float(d2.abs().max()))
+        assert int(bad.sum()) <= 2, int(bad.sum())
+    z, fup = rnd(2, 12, 20, 16), rnd(2, 2, 12, 20)
+    (f,), (fe,) = both(lambda o, f: o.flow_add(z, fup, 2.0, f), [torch.empty(2, 2, 12, 20, device="cuda")])
+    assert (f - fe).abs().max() <= 1e-6
+    d = rnd(2, 2, 8, 14)
+    (dz,), (dze,) = both(lambda o, t: o.planar_to_nhwc(d, 3, 2, t), [torch.empty(2, 12, 20, 16, device="cuda")])
+    assert torch.equal(dz, dze)
+    xr = rnd(2, 12, 20)
+    (o1,), (o2,) = both(lambda o, t: o.head_add(z, xr, 3, 2, t), [torch.empty(2, 1, 8, 14, device="cuda")])
+    assert torch.equal(o1, o2)

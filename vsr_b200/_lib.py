@@ -118,6 +118,17 @@ _SIGS = {
     "vsr_grid_warp_bwd": (C.c_int, [C.c_void_p] * 3 + [C.c_int32] * 3 + [C.c_void_p] * 2),
     "vsr_s2d_cat": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 5 + [C.c_void_p] * 2),
     "vsr_s2d_cat_bwd": (C.c_int, [C.c_void_p] + [C.c_int32] * 5 + [C.c_void_p] * 2),
+    "vsr_upsample_bicubic": (C.c_int, [C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p] * 2),
+    "vsr_min_partials": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "vsr_pad_fill": (C.c_int, [C.c_void_p] + [C.c_int32] * 7 + [C.c_void_p] * 3),
+    "vsr_avgpool2x2": (C.c_int, [C.c_void_p] + [C.c_int32] * 3 + [C.c_void_p] * 2),
+    "vsr_warp_cat": (C.c_int, [C.c_void_p] + [C.c_int32] * 5 + [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_float, C.c_int32,
+                                                              C.c_void_p]),
+    "vsr_warp_cat_bwd": (C.c_int, [C.c_void_p] + [C.c_int32] * 5 + [C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_void_p,
+                                                                  C.c_void_p]),
+    "vsr_flow_add": (C.c_int, [C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
+    "vsr_planar_to_nhwc": (C.c_int, [C.c_void_p] + [C.c_int32] * 9 + [C.c_void_p] * 2),
+    "vsr_head_add": (C.c_int, [C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p] * 2),
     "vsr_downscale_workspace": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
     "vsr_downscale": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -510,6 +510,67 @@ class CudaOps:
         check(self.lib.vsr_s2d_cat_bwd(_p(dout), n, h, w_, r, cpad, _p(dhr), _stream()), "vsr_s2d_cat_bwd")
         self.launches += 1
 
+    # ---- TOFlowNet: bicubic input up-sampling, min padding, pyramid, warp + concat, flow update, head ---------------------
+    def upsample_bicubic(self, x, r, y):
+        _need_cuda(x, y)
+        h, w_ = x.shape[-2:]
+        check(self.lib.vsr_upsample_bicubic(_p(x), x.numel() // (h * w_), h, w_, r, _p(y), _stream()), "vsr_upsample_bicubic")
+        self.launches += 1
+
+    def min_partials(self, x, partials):
+        _need_cuda(x, partials)
+        check(self.lib.vsr_min_partials(_p(x), x.numel(), _p(partials), _stream()), "vsr_min_partials")
+        self.launches += 1
+
+    def pad_fill(self, x, y0, x0, partials, out):
+        _need_cuda(x, partials, out)
+        h, w_ = x.shape[-2:]
+        check(self.lib.vsr_pad_fill(_p(x), x.numel() // (h * w_), h, w_, y0, x0, out.shape[-2], out.shape[-1], _p(partials), _p(out),
+                                    _stream()), "vsr_pad_fill")
+        self.launches += 1
+
+    def avgpool2x2(self, x, y):
+        _need_cuda(x, y)
+        h, w_ = x.shape[-2:]
+        check(self.lib.vsr_avgpool2x2(_p(x), x.numel() // (h * w_), h, w_, _p(y), _stream()), "vsr_avgpool2x2")
+        self.launches += 1
+
+    def warp_cat(self, out, c_ref, ref, c_w, nbr, flow, scale, c_flow):
+        """out[..., c_ref] = ref, out[..., c_w] = flow_warp(nbr, scale * flow), out[..., c_flow:c_flow+2] = scale * flow"""
+        _need_cuda(out, ref, nbr, flow)
+        n, h, w_, cpad = out.shape
+        check(self.lib.vsr_warp_cat(_p(out), n, h, w_, cpad, c_ref, _p(ref), c_w, _p(nbr), _p(flow), float(scale), c_flow, _stream()),
+              "vsr_warp_cat")
+        self.launches += 1
+
+    def warp_cat_bwd(self, dout, c_w, nbr, flow, scale, c_flow, dflow):
+        _need_cuda(dout, nbr, flow, dflow)
+        n, h, w_, cpad = dout.shape
+        check(self.lib.vsr_warp_cat_bwd(_p(dout), n, h, w_, cpad, c_w, _p(nbr), _p(flow), float(scale), c_flow, _p(dflow), _stream()),
+              "vsr_warp_cat_bwd")
+        self.launches += 1
+
+    def flow_add(self, z, flow_up, scale, flow):
+        _need_cuda(z, flow_up, flow)
+        n, h, w_, cz = z.shape
+        check(self.lib.vsr_flow_add(_p(z), n, h, w_, cz, _p(flow_up), float(scale), _p(flow), _stream()), "vsr_flow_add")
+        self.launches += 1
+
+    def planar_to_nhwc(self, d, y0, x0, dz):
+        """dz[n, hp, wp, cz] = d[n, kc, h, w] in the first kc channels of the window at (y0, x0), zero elsewhere"""
+        _need_cuda(d, dz)
+        n, kc, h, w_ = d.shape
+        check(self.lib.vsr_planar_to_nhwc(_p(d), n, kc, dz.shape[1], dz.shape[2], dz.shape[3], y0, x0, h, w_, _p(dz), _stream()),
+              "vsr_planar_to_nhwc")
+        self.launches += 1
+
+    def head_add(self, z, xref, y0, x0, out):
+        _need_cuda(z, xref, out)
+        n, hp, wp, cz = z.shape
+        check(self.lib.vsr_head_add(_p(z), n, hp, wp, cz, _p(xref), y0, x0, out.shape[-2], out.shape[-1], _p(out), _stream()),
+              "vsr_head_add")
+        self.launches += 1
+
     # ---- loss / metrics ----------------------------------------------------------------
     def loss_fwd_bwd(self, out, target, kind, param, grad_scale, partials, grad):
         _need_cuda(out, target, partials, grad)
