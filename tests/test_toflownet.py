@@ -221,3 +221,91 @@ def test_toflow_kernels_match_the_emulation():
     xr = rnd(2, 12, 20)
     (o1,), (o2,) = both(lambda o, t: o.head_add(z, xr, 3, 2, t), [torch.empty(2, 1, 8, 14, device="cuda")])
     assert torch.equal(o1, o2)
+
+
+def _misr_step_vs_oracle(device, steps, use_graph, w_tol, l_tol):
+    """the fused MISR step (acdc_misr_trainer.py:8-50: net -> loss on the centre frame -> backward -> Adam -> PSNR / SSIM) with
+    TOFlowNet against the oracle stepped with torch.optim.Adam: loss of every step, the BatchNorm running buffers (every
+    SpyNet block runs once per neighbour frame and step) and the weights after `steps` steps (eps = 1e-4: see
+    tests/test_trainstep_gpu.py on why)"""
+    from tests.emu import EmuOps
+    from vsr_b200.metrics import PSNR, SSIM
+    from vsr_b200.optim import FlatAdam
+    from vsr_b200.runner import MISRTrainStep
+    fx = torch.load(CASES[0])
+    r = fx["kwargs"]["upscale_factor"]
+    net = _load(fx)
+    if device == "cpu":
+        net._ops = EmuOps()
+    net = net.to(device)
+    opt = FlatAdam(net.parameters(), lr=1e-4, eps=1e-4)
+    step = MISRTrainStep(net, [torch.nn.MSELoss()], [1.0], [PSNR().to(device), SSIM().to(device)], opt, "acdc", use_graph=use_graph)
+    sd = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running_" not in k else v.clone())
+          for k, v in _state(fx).items()}
+    buffers = {k: v for k, v in sd.items() if "running_" in k}
+    ref_opt = torch.optim.Adam([v for v in sd.values() if v.requires_grad], lr=1e-4, eps=1e-4)
+    for _ in range(steps):
+        acc = torch.zeros(4, device=device)
+        lv, _ = step.train_step([x.to(device) for x in fx["inputs"]], [fx["target"].to(device)], acc)
+        out = restated.toflownet_forward(fx["inputs"], sd, r, True, buffers)
+        loss = restated.mse_loss(out, fx["target"])
+        psnr, ssim = restated.vsr_metrics([out.detach()], [fx["target"]])
+        ref_opt.zero_grad()
+        loss.backward()
+        ref_opt.step()
+        print(f"   step loss {float(lv[0]):.6f} oracle {float(loss):.6f} rel {abs(float(lv[0]) - float(loss)) / float(loss):.1e}")
+        assert abs(float(lv[0]) - float(loss)) <= l_tol * float(loss)
+        assert abs(float(acc[2]) - float(psnr)) <= 2e-3 and abs(float(acc[3]) - float(ssim)) <= 1e-4
+    wmax = max(float(v.abs().max()) for v in sd.values() if v.requires_grad)
+    got = net.state_dict()
+    worst = 0.0
+    for k, v in sd.items():
+        if "num_batches" in k:
+            assert int(got[k]) == steps * (fx["kwargs"]["num_frames"] - 1), k
+        elif "running_" in k:
+            assert (got[k].cpu() - v).abs().max() <= 1e-4 * max(1.0, float(v.abs().max())), k
+        else:
+            worst = max(worst, float((got[k].cpu() - v.data).abs().max()) / wmax)
+    print(f"TOFlowNet MISR step on {device}: weights after {steps} steps within {worst:.2e} of the largest weight")
+    # (lr = 1e-4: at the fixture's random weights one Adam step of 1e-3 on every weight raises the largest gradient 15x -
+    # the flow pyramid is chaotic there and round-off differences of 3e-5 grow to 1e-2 within a step, in the oracle's own
+    # fp32 arithmetic as well.)  Adam moves every element by ~lr per step whatever the size of its gradient: what is left
+    # are the ill-conditioned fp32 flow gradients (_check_net) as a fraction of lr in elements with small gradients
+    assert worst <= w_tol
+
+
+def test_misr_train_step_with_toflownet_host_logic():
+    _misr_step_vs_oracle("cpu", 2, False, 2e-4, 2e-5)
+
+
+@pytest.mark.gpu
+def test_misr_train_step_with_toflownet_gpu():
+    """through the C-ABI against the oracle's Adam steps.  Two steps: at the fixture's random weights the flow pyramid is
+    chaotic under training (the per-step loss error grows 7e-8 -> 2e-6 -> 1.5e-3 from round-off alone, in eager and graphed
+    runs alike), so longer runs are compared with themselves (next test), not with the oracle"""
+    _misr_step_vs_oracle("cuda", 2, False, 1e-3, 1e-4)
+
+
+@pytest.mark.gpu
+def test_misr_train_step_with_toflownet_graph_replay_equals_eager():
+    """2 eager steps + capture + 2 replays of the CUDA-graphed step = 5 eager steps, bit for bit: losses, weights, BatchNorm
+    running buffers and batch counters (they advance inside the graph)"""
+    from vsr_b200.metrics import PSNR, SSIM
+    from vsr_b200.optim import FlatAdam
+    from vsr_b200.runner import MISRTrainStep
+    fx = torch.load(CASES[0])
+    res = []
+    for use_graph in (False, True):
+        net = _load(fx).cuda()
+        opt = FlatAdam(net.parameters(), lr=1e-4, eps=1e-4)
+        step = MISRTrainStep(net, [torch.nn.MSELoss()], [1.0], [PSNR().cuda(), SSIM().cuda()], opt, "acdc", use_graph=use_graph)
+        losses = []
+        for _ in range(5):
+            acc = torch.zeros(4, device="cuda")
+            lv, _ = step.train_step([x.cuda() for x in fx["inputs"]], [fx["target"].cuda()], acc)
+            losses.append(torch.cat([lv.reshape(-1), acc]).clone())
+        res.append((torch.stack(losses), {k: v.clone() for k, v in net.state_dict().items()}))
+    assert torch.equal(res[0][0], res[1][0])
+    for k, v in res[0][1].items():
+        assert torch.equal(v, res[1][1][k]), k
+    assert int(res[1][1]["spy_net.blocks.0.block.1.num_batches_tracked"]) == 5 * (fx["kwargs"]["num_frames"] - 1)

@@ -790,7 +790,8 @@ class SplitOps(CudaOps):
         _need_cuda(dw, dz, *srcs)
         # (saved activations feed several weight gradients - the LR / HR feature lists of DRFNet - so their planes are cached
         # like the tap-GEMM sources; a gradient map feeds one weight gradient: split, not kept)
-        pl_s, pl_z = [self._planes(s) for s in srcs], self._planes(dz, cached=False)
+        # (a cached pair may have been made from another 4-D view of the same bytes: take the operand's own shape)
+        pl_s, pl_z = [self._planes(s).view(2, *s.shape) for s in srcs], self._planes(dz, cached=False)
         hi, lo = [p[0] for p in pl_s], [p[1] for p in pl_s]
         period = dz.shape[-1]
         terms = ((hi, pl_z[0]), (lo, pl_z[0]), (hi, pl_z[1]))
