@@ -158,13 +158,15 @@ int vsr_tapgemm_wgrad_finish(const VsrTapGemmDesc* d, float* dw, float* db, int3
  *   vsr_tapgemm(dtype = VSR_BF16X2, epi = 0)    -> raw fp32 accumulators in `out`
  *   vsr_tap_epilogue(out, ...)                  -> the VSR_EPI_* flags of vsr_tapgemm applied in place, in fp32, in the
  *                                                  order listed above ([rows][c] maps, c % 4 == 0; bias[c]; PRELU_BWD
- *                                                  writes one partial per block into slope_partials)
+ *                                                  writes one partial per block into slope_partials); `planes` /
+ *                                                  `planes2` (optional): the bf16 planes of `out` / `out2`, written in
+ *                                                  the same pass (saves the next consumer's vsr_split_planes a read)
  *   vsr_gather_split(src, idx, dst, n)          -> dst[i] = bf16 high part of src[idx[i]], or its low part
  *                                                  bf16(src - high) when bit 30 of idx[i] is set; 0 for idx[i] < 0 */
 int vsr_split_planes(const float* x, void* planes, int64_t numel, void* stream);
 int vsr_tap_epilogue(float* out, int64_t rows, int32_t c, const float* bias, int32_t epi, float out_scale,
                      const float* slope, const float* residual, const float* aux_y, float* out2, const float* res2,
-                     float* slope_partials, void* stream);
+                     float* slope_partials, void* planes, void* planes2, void* stream);
 int vsr_gather_split(const float* src, const int32_t* idx, void* dst, int64_t n, void* stream);
 
 /* colsum: db[c] (+)= sum over pixels x[pix][c]  (bias gradient; fixed order).

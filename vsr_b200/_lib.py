@@ -77,7 +77,7 @@ _SIGS = {
     "vsr_gather_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "vsr_slab_index": (C.c_int64, [C.c_int32, C.c_int32]),
     "vsr_split_planes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
-    "vsr_tap_epilogue": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_float] + [C.c_void_p] * 7),
+    "vsr_tap_epilogue": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_float] + [C.c_void_p] * 9),
     "vsr_gather_split": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "vsr_loss_fwd_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_float,
                                    C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),

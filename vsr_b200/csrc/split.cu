@@ -46,6 +46,8 @@ struct EpiArgs {
   float* out2;
   const float* res2;
   float* slope_partials;
+  uint2* planes;   // optional: the two bf16 planes of `out` ([2][numel], what vsr_split_planes(out) would give), written here
+  uint2* planes2;  // optional: the same for `out2`
   float out_scale;
   int epi;
   int c4;          // channels / 4
@@ -99,11 +101,25 @@ __global__ void __launch_bounds__(256) tap_epilogue_kernel(const EpiArgs a) {
     } else {
       out4[i] = make_float4(v[0], v[1], v[2], v[3]);
     }
+    if (a.planes) {
+      uint2 h, l;
+      split2(v[0], v[1], &h.x, &l.x);
+      split2(v[2], v[3], &h.y, &l.y);
+      a.planes[i] = h;
+      a.planes[a.n4 + i] = l;
+    }
     if (epi & VSR_EPI_OUT2) {
       const float4 r = __ldg(reinterpret_cast<const float4*>(a.res2) + i);
       const float s2 = (epi & VSR_EPI_OUT2_SUB) ? -1.f : 1.f;
-      reinterpret_cast<float4*>(a.out2)[i] =
-          make_float4(fmaf(s2, r.x, v[0]), fmaf(s2, r.y, v[1]), fmaf(s2, r.z, v[2]), fmaf(s2, r.w, v[3]));
+      const float4 o2 = make_float4(fmaf(s2, r.x, v[0]), fmaf(s2, r.y, v[1]), fmaf(s2, r.z, v[2]), fmaf(s2, r.w, v[3]));
+      reinterpret_cast<float4*>(a.out2)[i] = o2;
+      if (a.planes2) {
+        uint2 h, l;
+        split2(o2.x, o2.y, &h.x, &l.x);
+        split2(o2.z, o2.w, &h.y, &l.y);
+        a.planes2[i] = h;
+        a.planes2[a.n4 + i] = l;
+      }
     }
   }
   if (epi & VSR_EPI_PRELU_BWD) {
@@ -146,7 +162,7 @@ extern "C" int vsr_split_planes(const float* x, void* planes, int64_t numel, voi
 
 extern "C" int vsr_tap_epilogue(float* out, int64_t rows, int32_t c, const float* bias, int32_t epi, float out_scale,
                                 const float* slope, const float* residual, const float* aux_y, float* out2, const float* res2,
-                                float* slope_partials, void* stream) {
+                                float* slope_partials, void* planes, void* planes2, void* stream) {
   VSR_CHECK_ARG(out && rows > 0 && c > 0 && c % 4 == 0, "vsr_tap_epilogue: bad arguments (c must be a multiple of 4)");
   if (epi & VSR_EPI_BIAS) VSR_CHECK_ARG(bias, "vsr_tap_epilogue: BIAS without bias");
   if (epi & VSR_EPI_RES_PRE) VSR_CHECK_ARG(residual, "vsr_tap_epilogue: RES_PRE without residual");
@@ -154,8 +170,11 @@ extern "C" int vsr_tap_epilogue(float* out, int64_t rows, int32_t c, const float
   if (epi & (VSR_EPI_PRELU_BWD | VSR_EPI_RELU_BWD)) VSR_CHECK_ARG(aux_y, "vsr_tap_epilogue: *_BWD without aux_y");
   if (epi & VSR_EPI_PRELU_BWD) VSR_CHECK_ARG(slope_partials, "vsr_tap_epilogue: PRELU_BWD without slope_partials");
   if (epi & VSR_EPI_OUT2) VSR_CHECK_ARG(out2 && res2, "vsr_tap_epilogue: OUT2 without out2/res2");
-  if (epi == 0) return VSR_OK;
+  if (epi == 0 && !planes) return VSR_OK;
+  VSR_CHECK_ARG(!planes2 || (epi & VSR_EPI_OUT2), "vsr_tap_epilogue: planes2 without OUT2");
   EpiArgs a;
+  a.planes = static_cast<uint2*>(planes);
+  a.planes2 = static_cast<uint2*>(planes2);
   a.out = out; a.bias = bias; a.slope = slope; a.residual = residual; a.aux_y = aux_y; a.out2 = out2; a.res2 = res2;
   a.slope_partials = slope_partials; a.out_scale = out_scale; a.epi = epi; a.c4 = c / 4; a.n4 = rows * (long)(c / 4);
   int grid = grid_for(a.n4, 256, 6);

@@ -775,8 +775,20 @@ class SplitOps(CudaOps):
             self._meta = ("tapgemm", 2.0 * pix * tab.n_taps_total * tab.nt * tab.kc * tab.useful, sig, nbytes)
         check(self.lib.vsr_tapgemm(C.byref(d), _stream()), "vsr_tapgemm(bf16x2)")
         self._meta = None
+        # the epilogue pass also writes the bf16 planes of what it produces (the next tap-GEMM that reads the map finds them
+        # in the cache instead of re-reading the fp32 map); a launch without an epilogue leaves the raw accumulators as they are
+        pl = pl2 = None
+        if epi:
+            pl = torch.empty((2, *out.shape), dtype=torch.bfloat16, device=out.device)
+            if out2 is not None:
+                pl2 = torch.empty((2, *out2.shape), dtype=torch.bfloat16, device=out.device)
         check(self.lib.vsr_tap_epilogue(_p(out), pix, out.shape[-1], _p(bias), epi, float(out_scale), _p(slope), _p(residual),
-                                        _p(aux_y), _p(out2), _p(res2), _p(slope_partials), _stream()), "vsr_tap_epilogue")
+                                        _p(aux_y), _p(out2), _p(res2), _p(slope_partials), _p(pl), _p(pl2), _stream()),
+              "vsr_tap_epilogue")
+        if pl is not None:
+            self._cache[(out.data_ptr(), out.data_ptr() + out.numel() * 4)] = pl
+        if pl2 is not None:
+            self._cache[(out2.data_ptr(), out2.data_ptr() + out2.numel() * 4)] = pl2
         self.launches += 2 if epi else 1
 
     def tapgemm_wgrad_workspace(self, tab, srcs, dz):
