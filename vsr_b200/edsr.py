@@ -12,7 +12,7 @@ import torch.nn as nn
 
 from ._lib import EPI_BIAS, EPI_RELU, EPI_RELU_BWD, EPI_RES_PRE, EPI_SCALE
 from .drf_plan import DrfPlan, Layer, phase_table
-from .nets import _PRECISIONS, BaseNet
+from .nets import _PRECISIONS, _TC_LAYOUT, BaseNet, pack_weights, packed_weight_state
 from .ops import TapTable
 
 
@@ -138,7 +138,7 @@ class EDSRNet(BaseNet):
             raise NotImplementedError
         self.tail = nn.Sequential(up)
         self.tail.add_module("conv", nn.Conv2d(F, out_channels, 3, padding=1))
-        self._plan = EdsrPlan(in_channels, out_channels, num_resblocks, F, upscale_factor, precision == "bf16")
+        self._plan = EdsrPlan(in_channels, out_channels, num_resblocks, F, upscale_factor, precision in _TC_LAYOUT)
         assert [n for n, _ in self.named_parameters()] == list(self._plan.params), "parameter order differs"
         self._ops = None
         self._dev_state = None
@@ -172,20 +172,18 @@ class EDSRNet(BaseNet):
             return self._ops
         if self.flat.device.type != "cuda":
             raise RuntimeError("vsr_b200 nets run on CUDA only (there is no CPU fallback); call .to('cuda')")
-        from .ops import cuda_ops
-        return cuda_ops()
+        from .ops import cuda_ops, split_ops
+        return split_ops() if self.precision in ("bf16x3", "tf32") else cuda_ops()
 
     def _state(self):
         if self._dev_state is None:
             P, dev = self._plan, self.flat.device
             act = torch.float64 if self.flat.dtype == torch.float64 else _PRECISIONS[self.precision]
             st = {"act": act,
-                  "fwd_w": torch.empty(P.fwd_w_numel, dtype=act, device=dev),
-                  "bwd_w": torch.empty(P.bwd_w_numel, dtype=act, device=dev),
                   "fwd_b": torch.empty(P.fwd_b_numel, dtype=self.flat.dtype, device=dev),
-                  "fwd_w_idx": torch.from_numpy(P.fwd_w_idx).to(dev), "bwd_w_idx": torch.from_numpy(P.bwd_w_idx).to(dev),
                   "fwd_b_idx": torch.from_numpy(P.fwd_b_idx).to(dev),
                   "unpack": [(lo, torch.from_numpy(i).to(dev)) for lo, i in P.unpack_passes], "ws": {}}
+            st.update(packed_weight_state(self, P, dev, act))
             b = P.bias_unpack_idx
             nz = (b >= 0).nonzero()[0]
             st["bias_unpack"] = (int(nz.min()), torch.from_numpy(b[nz.min():nz.max() + 1].copy()).to(dev))
@@ -204,11 +202,7 @@ class EDSRNet(BaseNet):
         return flat[p.offset:p.offset + int(np.prod(p.shape))].view(p.shape)
 
     def _pack(self, need_bwd):
-        st, ops = self._state(), self._backend()
-        ops.gather(self.flat, st["fwd_w_idx"], st["fwd_w"])
-        ops.gather(self.flat, st["fwd_b_idx"], st["fwd_b"])
-        if need_bwd:
-            ops.gather(self.flat, st["bwd_w_idx"], st["bwd_w"])
+        pack_weights(self, self._state(), need_bwd)
 
     def _conv(self, lname, src, out, epi=0, **kw):
         st, L = self._state(), self._plan.fwd[lname]

@@ -24,6 +24,48 @@ _PRECISIONS = {"fp32": torch.float32, "bf16": torch.bfloat16, "bf16x3": torch.fl
 _TC_LAYOUT = ("bf16", "bf16x3", "tf32")      # plans with 64-channel taps and swizzled bf16 weight slabs
 
 
+class TripledSlabs:
+    """A weight buffer of the bf16x3 mode addressed with the plan's own offsets: every layer's slabs are stored three times
+    over ([wh | wh | wl] per group, DrfPlan.split_index), so the plan's [w_off, w_off + w_numel) is [3 w_off, 3 (w_off + w_numel))"""
+
+    def __init__(self, buf):
+        self.buf = buf
+
+    def __getitem__(self, s):
+        return self.buf[3 * s.start:3 * s.stop]
+
+
+def split_mode(net):
+    """True when `net` runs the strict mode on tensor cores (precision 'bf16x3' / 'tf32'; the float64 emulation runs of the
+    tests keep the plain layout)"""
+    return net.precision in ("bf16x3", "tf32") and net.flat.dtype != torch.float64 and getattr(net._backend(), "split", False)
+
+
+def packed_weight_state(net, P, dev, act):
+    """the packed weight / bias buffers and packing maps shared by the nets that keep their own state dict (RBPNet,
+    EDSRNet, ...): plain slabs, or the tripled bf16 slabs of the bf16x3 mode"""
+    if split_mode(net):
+        return {"fwd_w": TripledSlabs(torch.empty(3 * P.fwd_w_numel, dtype=torch.bfloat16, device=dev)),
+                "bwd_w": TripledSlabs(torch.empty(3 * P.bwd_w_numel, dtype=torch.bfloat16, device=dev)),
+                "fwd_w_idx": torch.from_numpy(P.split_index("fwd")).to(dev), "bwd_w_idx": torch.from_numpy(P.split_index("bwd")).to(dev),
+                "split": True}
+    return {"fwd_w": torch.empty(P.fwd_w_numel, dtype=act, device=dev), "bwd_w": torch.empty(P.bwd_w_numel, dtype=act, device=dev),
+            "fwd_w_idx": torch.from_numpy(P.fwd_w_idx).to(dev), "bwd_w_idx": torch.from_numpy(P.bwd_w_idx).to(dev), "split": False}
+
+
+def pack_weights(net, st, need_bwd):
+    ops = net._backend()
+    if st["split"]:
+        ops.gather_split(net.flat, st["fwd_w_idx"], st["fwd_w"].buf)
+        if need_bwd:
+            ops.gather_split(net.flat, st["bwd_w_idx"], st["bwd_w"].buf)
+    else:
+        ops.gather(net.flat, st["fwd_w_idx"], st["fwd_w"])
+        if need_bwd:
+            ops.gather(net.flat, st["bwd_w_idx"], st["bwd_w"])
+    ops.gather(net.flat, st["fwd_b_idx"], st["fwd_b"])
+
+
 class BaseNet(nn.Module):
     """The base class for all nets (reference: base_net.py:5-13)."""
 

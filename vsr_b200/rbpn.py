@@ -27,7 +27,7 @@ import torch.nn as nn
 
 from ._lib import EPI_BIAS, EPI_OUT2, EPI_OUT2_SUB, EPI_PRELU, EPI_RES_PRE
 from .drf_plan import MAX_NT, PROJ, DrfPlan, Layer, _split_nt, phase_table
-from .nets import _PRECISIONS, BaseNet
+from .nets import _PRECISIONS, _TC_LAYOUT, BaseNet, pack_weights, packed_weight_state
 from .ops import TapTable
 
 
@@ -310,7 +310,8 @@ class _RbpFunction(torch.autograd.Function):
 class RBPNet(BaseNet):
     """Recurrent Back-Projection Network (reference: rbp_net.py:8-91).  Args as the reference: in_channels, out_channels,
     base_filter, feat, num_stages (3: DBPNet concatenates three stages), num_resblocks, num_frames, upscale_factor;
-    precision 'fp32' (CUDA-core strict mode) | 'bf16' (tcgen05 mode, base_filter % 64 == 0 and feat % 64 == 0).
+    precision 'fp32' (CUDA-core strict mode) | 'bf16' (tcgen05 mode, base_filter % 64 == 0 and feat % 64 == 0) | 'bf16x3' /
+    'tf32' (strict accuracy on the tensor cores, same channel constraint).
     forward(list of num_frames tensors [N,C,h,w]) -> tensor [N,out_channels,r*h,r*w].  out_channels must be 1 (the last
     convolution runs on the N = 1 kernels)."""
 
@@ -338,7 +339,7 @@ class RBPNet(BaseNet):
         self.res_feat3 = nn.Sequential(*[ResnetBlock(Fe) for _ in range(R)], ConvBlock(Fe, B, k, s, p))
         self.output = ConvBlock((num_frames - 1) * Fe, out_channels, 3, 1, 1, activation=None)
         self._plan = RbpPlan([(n, tuple(q.shape)) for n, q in self.named_parameters()], B, Fe, upscale_factor, R,
-                             precision == "bf16")
+                             precision in _TC_LAYOUT)
         self._ops = None
         self._dev_state = None
         self.flat = self.flat_grad = None
@@ -371,8 +372,8 @@ class RBPNet(BaseNet):
             return self._ops
         if self.flat.device.type != "cuda":
             raise RuntimeError("vsr_b200 nets run on CUDA only (there is no CPU fallback); call .to('cuda')")
-        from .ops import cuda_ops
-        return cuda_ops()
+        from .ops import cuda_ops, split_ops
+        return split_ops() if self.precision in ("bf16x3", "tf32") else cuda_ops()
 
     def enable_sync_bn(self, process_group=None):
         """(MISRTrainStep calls this on every MISR net under data parallelism; RBPNet has no BatchNorm)"""
@@ -382,12 +383,10 @@ class RBPNet(BaseNet):
             P, dev = self._plan, self.flat.device
             act = torch.float64 if self.flat.dtype == torch.float64 else _PRECISIONS[self.precision]
             st = {"act": act,
-                  "fwd_w": torch.empty(P.fwd_w_numel, dtype=act, device=dev),
-                  "bwd_w": torch.empty(P.bwd_w_numel, dtype=act, device=dev),
                   "fwd_b": torch.empty(P.fwd_b_numel, dtype=self.flat.dtype, device=dev),
-                  "fwd_w_idx": torch.from_numpy(P.fwd_w_idx).to(dev), "bwd_w_idx": torch.from_numpy(P.bwd_w_idx).to(dev),
                   "fwd_b_idx": torch.from_numpy(P.fwd_b_idx).to(dev),
                   "unpack": [(lo, torch.from_numpy(i).to(dev)) for lo, i in P.unpack_passes], "ws": {}}
+            st.update(packed_weight_state(self, P, dev, act))
             b = P.bias_unpack_idx
             nz = (b >= 0).nonzero()[0]
             st["bias_unpack"] = (int(nz.min()), torch.from_numpy(b[nz.min():nz.max() + 1].copy()).to(dev))
@@ -406,11 +405,7 @@ class RBPNet(BaseNet):
         return flat[p.offset:p.offset + int(np.prod(p.shape))].view(p.shape)
 
     def _pack(self, need_bwd):
-        st, ops = self._state(), self._backend()
-        ops.gather(self.flat, st["fwd_w_idx"], st["fwd_w"])
-        ops.gather(self.flat, st["fwd_b_idx"], st["fwd_b"])
-        if need_bwd:
-            ops.gather(self.flat, st["bwd_w_idx"], st["bwd_w"])
+        pack_weights(self, self._state(), need_bwd)
 
     # ---- forward: every launch is recorded (when `save`) for the reverse walk of _backward ----
     def _forward(self, frames, save):
