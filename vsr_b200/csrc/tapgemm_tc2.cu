@@ -49,7 +49,7 @@ constexpr int kEpiWarps = 8;                  // two per TMEM lane quarter: even
 constexpr int kTileBytes = 4096;              // epilogue tile: 32 pixels x 64 channels bf16
 constexpr int kMaxSmemGroups = 20;            // group table rows cached in smem (16 B each, ctrl[448..768))
 constexpr int kMaxSmemTaps = 256;             // column entries cached in smem (8 B each)
-constexpr int kMaxParamCols = 64;             // host-built columns travel in the kernel arguments
+constexpr int kMaxParamCols = 96;             // host-built columns travel in the kernel arguments
 constexpr int kMaxTallGroups = 8;
 constexpr int kBiasFloats = 1024;
 constexpr int kCtrlBytes = 1024 + kMaxSmemTaps * 8 + kBiasFloats * 4;   // 7 KiB, keeps 1024-byte alignment
@@ -219,7 +219,9 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
   const uint32_t res_base = epi_base + a.epi_bytes;        // resident weight slabs (resident mode)
   const uint32_t stage_base = res_base + a.res_bytes;
   const bool grp_in_smem = a.n_groups <= kMaxSmemGroups;
-  const bool taps_in_smem = a.n_taps_total <= kMaxSmemTaps;
+  // (shared-load mode: the host-built columns - at most kMaxParamCols - always sit in shared memory, however long the tap
+  //  table is; only the plain mode falls back to the global tap table for tables beyond kMaxSmemTaps)
+  const bool taps_in_smem = a.tall || a.n_taps_total <= kMaxSmemTaps;
   // A "column" is one A load feeding ndy taps (weight slabs slab0 + j*stride) whose row shifts are
   // dy0 + j; plain mode: every tap is a column of its own.
   if (a.tall) {
@@ -775,13 +777,19 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
 
 // Host: fold the taps of a (single-group) table into columns = taps with equal (src, c0, dx), consecutive dy
 // and evenly spaced slab indices.  Returns the longest column (0 if the table does not fit the argument array).
-int build_columns(const int32_t* taps, int n_taps, int idx_base, int max_cols, uint2* cols, int* n_cols) {
-  struct T { int src, dy, dx, c0, idx; };
+// `split` (bf16x3 tables): the group holds its taps three times over - [high plane x wh | low plane x wh | high plane x wl] -
+// so the first and the last third have equal (src, c0, dx, dy); the third a tap belongs to joins the sort key, otherwise the
+// two copies would interleave and no column could form.
+int build_columns(const int32_t* taps, int n_taps, int idx_base, int max_cols, uint2* cols, int* n_cols, bool split) {
+  struct T { int src, dy, dx, c0, idx, cls; };
   std::vector<T> v(n_taps);
-  for (int i = 0; i < n_taps; ++i) v[i] = T{taps[4 * i], taps[4 * i + 1], taps[4 * i + 2], taps[4 * i + 3], idx_base + i};
+  const int third = split && n_taps % 3 == 0 ? n_taps / 3 : n_taps;
+  for (int i = 0; i < n_taps; ++i)
+    v[i] = T{taps[4 * i], taps[4 * i + 1], taps[4 * i + 2], taps[4 * i + 3], idx_base + i, i / third};
   for (const T& t : v)
     if (t.src < 0 || t.src > 15 || t.dy < -8 || t.dy > 7 || t.dx < -8 || t.dx > 7 || (t.c0 & 7)) return 0;
   std::stable_sort(v.begin(), v.end(), [](const T& x, const T& y) {
+    if (x.cls != y.cls) return x.cls < y.cls;
     if (x.src != y.src) return x.src < y.src;
     if (x.c0 != y.c0) return x.c0 < y.c0;
     if (x.dx != y.dx) return x.dx < y.dx;
@@ -792,8 +800,8 @@ int build_columns(const int32_t* taps, int n_taps, int idx_base, int max_cols, u
   while (i < v.size()) {
     size_t j = i + 1;
     int stride = 0;
-    while (j < v.size() && j - i < 3 && v[j].src == v[i].src && v[j].c0 == v[i].c0 && v[j].dx == v[i].dx &&
-           v[j].dy == v[j - 1].dy + 1) {
+    while (j < v.size() && j - i < 3 && v[j].cls == v[i].cls && v[j].src == v[i].src && v[j].c0 == v[i].c0 &&
+           v[j].dx == v[i].dx && v[j].dy == v[j - 1].dy + 1) {
       const int st = v[j].idx - v[j - 1].idx;
       if (j == i + 1) stride = st;
       if (st != stride || st <= 0 || st > 4095) break;
@@ -968,7 +976,9 @@ int tapgemm_tc2_launch(const VsrTapGemmDesc* d, cudaStream_t stream) {
         const int begin = d->n_groups == 1 ? 0 : d->group_tab_host[4 * gi + 1];
         const int count = d->n_groups == 1 ? d->n_taps_total : d->group_tab_host[4 * gi + 2];
         int nc = 0;
-        const int lg = build_columns(d->tap_tab_host + 4 * begin, count, begin, kMaxParamCols - n_cols, a.cols + n_cols, &nc);
+        // (bf16 tables keep the 64-column limit they were tuned with; the tripled tables of the bf16x3 mode may use all 96)
+        const int lg = build_columns(d->tap_tab_host + 4 * begin, count, begin, (split ? kMaxParamCols : 64) - n_cols,
+                                     a.cols + n_cols, &nc, split);
         if (lg == 0 || begin > 0xffff || count > 0x7fff) { ok = false; break; }
         a.tgroups[gi] = make_int4(o0, n_cols, nc, begin | (count << 16));
         n_cols += nc;
