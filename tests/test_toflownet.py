@@ -309,3 +309,68 @@ def test_misr_train_step_with_toflownet_graph_replay_equals_eager():
     for k, v in res[0][1].items():
         assert torch.equal(v, res[1][1][k]), k
     assert int(res[1][1]["spy_net.blocks.0.block.1.num_batches_tracked"]) == 5 * (fx["kwargs"]["num_frames"] - 1)
+
+
+def test_misr_trainer_epoch_on_cpu():
+    """MISRTrainer = AcdcMISRTrainer's epoch loop (base_trainer.py:99-144; the reference trains TOFlowNet with it) over the
+    synthetic MISR dataset through the emulation: the log has the reference's keys, the loss falls, validation runs in eval
+    mode (running buffers) without touching them"""
+    from tests.emu import EmuOps
+    from vsr_b200.data import Dataloader, SyntheticCineDataset
+    from vsr_b200.metrics import PSNR, SSIM
+    from vsr_b200.optim import FlatAdam
+    from vsr_b200.runner import MISRTrainer
+    from vsr_b200.toflow import TOFlowNet
+    ds = SyntheticCineDataset(2, num_frames=3, temporal_order="middle", type="train", num_sequences=1, patch_size=(8, 8),
+                              misr=True)
+    ds.data = ds.data[:4]
+    loader = Dataloader(ds, batch_size=2, pin_memory=False)
+    torch.manual_seed(0)
+    net = TOFlowNet(1, 1, 3, 2)
+    net._ops = EmuOps()
+    tr = MISRTrainer("cpu", loader, loader, net, [torch.nn.L1Loss()], [1.0], [PSNR(), SSIM()],
+                     FlatAdam(net.parameters(), lr=1e-3), None, None, None, 1)
+    logs = [tr._run_epoch("training")[0] for _ in range(3)]
+    assert list(logs[0]) == ["Loss", "L1Loss", "PSNR", "SSIM"]
+    assert logs[2]["Loss"] < logs[0]["Loss"]
+    before = {k: v.clone() for k, v in net.state_dict().items() if "running" in k or "num_batches" in k}
+    vlog, _, out = tr._run_epoch("validation")
+    assert out.shape == (2, 1, 16, 16) and vlog["Loss"] > 0
+    after = net.state_dict()
+    assert all(torch.equal(v, after[k]) for k, v in before.items())
+    assert int(after["spy_net.blocks.0.block.1.num_batches_tracked"]) == 3 * 2 * 2        # epochs x batches x neighbours
+
+
+def test_checkpoint_interchange_with_live_reference(tmp_path):
+    """base_trainer.py:229-237 / base_predictor.py:135-136: a checkpoint written from the drop-in loads (strict) into the
+    reference's TOFlowNet and back; both nets then agree in training mode (outputs, running buffers) and in eval mode"""
+    from oracle import load_reference
+    from tests.emu import EmuOps
+    from vsr_b200.toflow import TOFlowNet
+    if not load_reference.available():
+        pytest.skip("/root/reference not mounted")
+    Ref = load_reference.load().TOFlowNet
+    kw = dict(in_channels=1, out_channels=1, num_frames=3, upscale_factor=2)
+    torch.manual_seed(1)
+    ours = TOFlowNet(**kw)
+    ours._ops = EmuOps()
+    torch.save({"net": ours.state_dict()}, tmp_path / "ck.pth")
+    ref = Ref(**kw)
+    ref.load_state_dict(torch.load(tmp_path / "ck.pth")["net"], strict=True)
+    x = [torch.randn(2, 1, 9, 10) for _ in range(3)]                 # padded to 32 x 32 inside the nets
+    rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
+    ours.train(), ref.train()
+    with torch.no_grad():
+        a, b = ours(x), ref(list(x))
+    assert rel(a, b) <= 2e-5
+    sa, sb = ours.state_dict(), ref.state_dict()
+    assert list(sa) == list(sb)
+    for k in sa:
+        if "running" in k or "num_batches" in k:
+            assert torch.allclose(sa[k].double(), sb[k].double(), rtol=1e-5, atol=1e-6), k
+    ours2 = TOFlowNet(**kw)
+    ours2.load_state_dict(ref.state_dict(), strict=True)
+    ours2._ops = EmuOps()
+    ours2.eval(), ref.eval()
+    with torch.no_grad():
+        assert rel(ours2(x), ref(list(x))) <= 2e-5

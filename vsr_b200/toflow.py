@@ -163,7 +163,8 @@ class TOFlowNet(BaseNet):
         return out
 
     def enable_sync_bn(self, process_group=None):
-        raise NotImplementedError("TOFlowNet: synchronised BatchNorm2d is not implemented (single-device statistics)")
+        """(MISRTrainStep calls this under data parallelism.)  TOFlowNet keeps rank-local BatchNorm2d statistics - what
+        torch's DistributedDataParallel does with plain nn.BatchNorm2d; gradients are all-reduced like every other net's."""
 
     # ---- forward ----
     def _forward(self, frames, save):
