@@ -696,6 +696,7 @@ class SplitOps(CudaOps):
         super().__init__()
         self._wg_ws = None
         self._db_dummy = None
+        self._retired = []
         self._cache = {}
 
     def __getattribute__(self, name):
@@ -809,9 +810,13 @@ class SplitOps(CudaOps):
         terms = ((hi, pl_z[0]), (lo, pl_z[0]), (hi, pl_z[1]))
         descs = [_make_desc(tab, ss, zz) for ss, zz in terms]
         need = 3 * self.lib.vsr_tapgemm_wgrad_workspace(C.byref(descs[0]))
+        # (a workspace that has to grow is replaced, never freed: a captured CUDA graph of another net may still replay
+        #  launches that write into the old one)
         if self._wg_ws is None or self._wg_ws.numel() * 4 < need or self._wg_ws.device != dz.device:
+            self._retired.append(self._wg_ws)
             self._wg_ws = torch.empty((need + 3) // 4, dtype=torch.float32, device=dz.device)
         if self._db_dummy is None or self._db_dummy.numel() < period or self._db_dummy.device != dz.device:
+            self._retired.append(self._db_dummy)
             self._db_dummy = torch.empty(max(period, 1024), dtype=torch.float32, device=dz.device)
         ws, nbytes = self._wg_ws, self._wg_ws.numel() * 4
         if self.timing is not None:
