@@ -169,6 +169,27 @@ int vsr_tap_epilogue(float* out, int64_t rows, int32_t c, const float* bias, int
                      float* slope_partials, void* planes, void* planes2, void* stream);
 int vsr_gather_split(const float* src, const int32_t* idx, void* dst, int64_t n, void* stream);
 
+/* Weight (+ bias) gradients of SEVERAL 1x1 convolutions that read the same list of 64-channel maps, in one pass over
+ * the maps (csrc/wgrad_shared.cu): layer g multiplies its gradient map dzs[g] with the first ntaps[g] sources,
+ *   dw[g][t][j][k] (+)= sum_pix dzs[g][pix][j] * srcs[t][pix][k],  t < ntaps[g];   db[g][j] (+)= sum_pix dzs[g][pix][j]
+ * (dw[g]: fp32 [ntaps[g]][64][64] plain row-major = the packed slab order of the layer; db[g] may be NULL).  Every source
+ * tile is loaded once per launch instead of once per layer: the dense connections of the feedback block
+ * (f_block.{up,down}_blocks[g].conv1 on torch.cat(lr_list / hr_list), drf_net.py:89-105) make the separate weight gradients
+ * read map j once for every g >= j.  All maps: VSR_BF16 [n][h][w][64] on one pixel grid; sum over g of ceil(ntaps[g] / 2)
+ * <= 8 (tensor-memory accumulators), otherwise VSR_ERR_UNSUPPORTED: split the layer set.  Fixed summation order. */
+#define VSR_WS_MAX_SRCS 8
+#define VSR_WS_MAX_DZ 4
+typedef struct VsrWgradSharedDesc {
+  int32_t n_srcs, n_dz;
+  VsrTensor4 srcs[VSR_WS_MAX_SRCS];
+  VsrTensor4 dzs[VSR_WS_MAX_DZ];
+  int32_t ntaps[VSR_WS_MAX_DZ];
+  float* dw[VSR_WS_MAX_DZ];
+  float* db[VSR_WS_MAX_DZ];
+} VsrWgradSharedDesc;
+size_t vsr_wgrad_shared_workspace(const VsrWgradSharedDesc* d);
+int vsr_wgrad_shared(const VsrWgradSharedDesc* d, int accumulate, void* workspace, size_t workspace_bytes, void* stream);
+
 /* colsum: db[c] (+)= sum over pixels x[pix][c]  (bias gradient; fixed order).
  * workspace >= vsr_colsum_workspace(rows, c) bytes. */
 size_t vsr_colsum_workspace(int64_t rows, int32_t c);

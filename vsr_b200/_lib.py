@@ -33,6 +33,15 @@ class VsrTapGemmDesc(C.Structure):
     ]
 
 
+VSR_WS_MAX_SRCS, VSR_WS_MAX_DZ = 8, 4
+
+
+class VsrWgradSharedDesc(C.Structure):
+    _fields_ = [("n_srcs", C.c_int32), ("n_dz", C.c_int32), ("srcs", VsrTensor4 * VSR_WS_MAX_SRCS),
+                ("dzs", VsrTensor4 * VSR_WS_MAX_DZ), ("ntaps", C.c_int32 * VSR_WS_MAX_DZ),
+                ("dw", C.c_void_p * VSR_WS_MAX_DZ), ("db", C.c_void_p * VSR_WS_MAX_DZ)]
+
+
 _SIGS = {
     "vsr_abi_version": (C.c_int, []),
     "vsr_last_error": (C.c_char_p, []),
@@ -49,6 +58,8 @@ _SIGS = {
                                             C.c_size_t, C.c_void_p]),
     "vsr_tapgemm_wgrad_finish": (C.c_int, [C.POINTER(VsrTapGemmDesc), C.c_void_p, C.c_void_p, C.c_int32, C.c_int,
                                            C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "vsr_wgrad_shared_workspace": (C.c_size_t, [C.POINTER(VsrWgradSharedDesc)]),
+    "vsr_wgrad_shared": (C.c_int, [C.POINTER(VsrWgradSharedDesc), C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "vsr_colsum_workspace": (C.c_size_t, [C.c_int64, C.c_int32]),
     "vsr_colsum": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_int,
                              C.c_void_p, C.c_size_t, C.c_void_p]),

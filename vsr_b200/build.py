@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIBPATH = os.path.join(LIBDIR, "libvsr_sm100.so")
-SOURCES = ["core.cu", "tapgemm_simt.cu", "tma_host.cu", "tapgemm_tc2.cu", "wgrad_tc.cu", "layers.cu", "lastconv_mma.cu", "firstconv_mma.cu", "metrics.cu",
+SOURCES = ["core.cu", "tapgemm_simt.cu", "tma_host.cu", "tapgemm_tc2.cu", "wgrad_tc.cu", "wgrad_shared.cu", "layers.cu", "lastconv_mma.cu", "firstconv_mma.cu", "metrics.cu",
            "resample.cu", "resample_int.cu", "dense3d.cu", "downscale.cu", "flow.cu", "split.cu", "toflow.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]

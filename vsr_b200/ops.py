@@ -241,6 +241,40 @@ class CudaOps:
               "vsr_tapgemm_wgrad_finish")
         self.launches += 1
 
+    # ---- weight gradients of several 1x1 convolutions over one feature list, in one pass -----
+    MAX_SHARED_ACC, MAX_SHARED_DZ, MAX_SHARED_SRCS = 8, _lib.VSR_WS_MAX_DZ, _lib.VSR_WS_MAX_SRCS
+
+    def _shared_desc(self, srcs, dzs, ntaps, dws, dbs):
+        d = _lib.VsrWgradSharedDesc()
+        d.n_srcs, d.n_dz = len(srcs), len(dzs)
+        for i, t in enumerate(srcs):
+            d.srcs[i] = _tensor4(t)
+        for g, (z, nt, dw, db) in enumerate(zip(dzs, ntaps, dws, dbs)):
+            d.dzs[g], d.ntaps[g] = _tensor4(z), nt
+            d.dw[g] = dw.data_ptr()
+            d.db[g] = db.data_ptr() if db is not None else None
+        return d
+
+    def wgrad_shared_ok(self, srcs, dzs, ntaps):
+        """can `wgrad_shared` take this layer set in ONE launch?  (bf16 maps of 64 channels, <= 8 accumulators)"""
+        return (all(t.dtype == torch.bfloat16 and t.shape[-1] == 64 for t in (*srcs, *dzs)) and len(srcs) <= self.MAX_SHARED_SRCS and
+                len(dzs) <= self.MAX_SHARED_DZ and sum((n + 1) // 2 for n in ntaps) <= self.MAX_SHARED_ACC)
+
+    def wgrad_shared(self, srcs, dzs, ntaps, dws, dbs, accumulate, workspace_of):
+        """dws[g][t] (+)= dzs[g]^T srcs[t] for t < ntaps[g], dbs[g] (+)= column sums of dzs[g]; every source is read once.
+        `workspace_of(nbytes)` returns a workspace tensor of at least that many bytes."""
+        _need_cuda(*srcs, *dzs, *dws, *[b for b in dbs if b is not None])
+        d = self._shared_desc(srcs, dzs, ntaps, dws, dbs)
+        ws = workspace_of(self.lib.vsr_wgrad_shared_workspace(C.byref(d)))
+        if self.timing is not None:
+            pix = dzs[0].numel() // 64
+            nbytes = 2 * pix * 64 * (len(srcs) + len(dzs))
+            self._meta = ("wgrad", 2.0 * pix * sum(ntaps) * 64 * 64, f"shared_srcs{len(srcs)}_dz{len(dzs)}_taps{sum(ntaps)}_px{pix}", nbytes)
+        check(self.lib.vsr_wgrad_shared(C.byref(d), int(accumulate), _p(ws), ws.numel() * ws.element_size(), _stream()),
+              "vsr_wgrad_shared")
+        self._meta = None
+        self.launches += 2
+
     # ---- small kernels -----------------------------------------------------------------
     def colsum_workspace(self, rows, c):
         return self.lib.vsr_colsum_workspace(rows, c)
