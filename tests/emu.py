@@ -576,6 +576,28 @@ class EmuOps:
         dhr.copy_(F.pixel_shuffle(dout[..., :r * r].permute(0, 3, 1, 2), r))
         self.launches += 1
 
+    # ---- weight gradients of several 1x1 convolutions over one feature list (csrc/wgrad_shared.cu) ----
+    MAX_SHARED_ACC, MAX_SHARED_DZ, MAX_SHARED_SRCS = 8, 4, 8
+
+    def wgrad_shared_ok(self, srcs, dzs, ntaps):
+        c = dzs[0].shape[-1]
+        return (all(t.shape[-1] == c for t in (*srcs, *dzs)) and len(srcs) <= self.MAX_SHARED_SRCS and
+                len(dzs) <= self.MAX_SHARED_DZ and sum((n + 1) // 2 for n in ntaps) <= self.MAX_SHARED_ACC)
+
+    def wgrad_shared(self, srcs, dzs, ntaps, dws, dbs, accumulate, workspace_of):
+        workspace_of(16)
+        for dz, nt, dw, db in zip(dzs, ntaps, dws, dbs):
+            ct = torch.float64 if dz.dtype == torch.float64 else torch.float32
+            c = dz.shape[-1]
+            z = dz.reshape(-1, c).to(ct)
+            g = torch.stack([z.t() @ srcs[t].reshape(-1, c).to(ct) for t in range(nt)]).reshape(-1)        # [nt][j][k]
+            tgt = dw.view(-1)[:g.numel()]
+            tgt.copy_((tgt.to(ct) + g if accumulate else g).to(dw.dtype))
+            if db is not None:
+                cs = z.sum(0)
+                db.copy_((db.to(ct) + cs if accumulate else cs).to(db.dtype))
+        self.launches += 2
+
     # ---- TOFlowNet (csrc/toflow.cu) ----
     def upsample_bicubic(self, x, r, y):
         y.copy_(F.interpolate(x.reshape(-1, 1, *x.shape[-2:]), scale_factor=r, mode="bicubic", align_corners=False).reshape(y.shape))

@@ -317,3 +317,36 @@ def test_tc_bf16_cta_pairs_and_single_ctas_agree_with_the_emulation(pair, monkey
     # more tiles than CTA pairs, two TMEM buffers in flight, PReLU' on a wide output
     _run_case(grouped_table(64, 256, 4, 1), n=40, h=32, w=32, src_c=64, out_c=1024, dtype=torch.bfloat16,
               epi=L.EPI_PRELU_BWD, seed=36)
+
+
+@pytest.mark.parametrize("shape,ntaps", [((3, 16, 24), [2, 3]), ((2, 8, 512), [4, 5, 6]), ((5, 7, 9), [1]), ((1, 32, 32), [2, 3, 4, 5])])
+def test_wgrad_shared_matches_float64(shape, ntaps):
+    """csrc/wgrad_shared.cu: the weight (+ bias) gradients of several 1x1 convolutions over one list of 64-channel maps in
+    one pass (every source tile loaded once) against float64 sums over the same bf16 operands; ragged pixel grids (partial
+    TMA boxes), odd tap counts (the last pair's second half is padding), accumulate on / off"""
+    from vsr_b200.ops import cuda_ops
+    ops = cuda_ops()
+    g = torch.Generator(device="cuda").manual_seed(sum(ntaps))
+    n, h, w = shape
+    srcs = [torch.randn(n, h, w, 64, device="cuda", generator=g).bfloat16() for _ in range(max(ntaps))]
+    dzs = [torch.randn(n, h, w, 64, device="cuda", generator=g).bfloat16() for _ in ntaps]
+    assert ops.wgrad_shared_ok(srcs, dzs, ntaps)
+    dws = [torch.full((nt, 64, 64), 0.5, device="cuda") for nt in ntaps]
+    dbs = [torch.full((64,), -1.0, device="cuda") if i % 2 == 0 else None for i in range(len(ntaps))]
+    ws = {}
+
+    def workspace_of(nbytes):
+        ws["t"] = torch.empty((nbytes + 3) // 4, device="cuda")
+        return ws["t"]
+
+    for accumulate in (False, True):
+        ops.wgrad_shared(srcs, dzs, ntaps, dws, dbs, accumulate, workspace_of)
+        mult = 2.0 if accumulate else 1.0
+        for dz, nt, dw, db in zip(dzs, ntaps, dws, dbs):
+            z = dz.reshape(-1, 64).double()
+            ref = torch.stack([z.t() @ srcs[t].reshape(-1, 64).double() for t in range(nt)])
+            assert (dw.double() - mult * ref).abs().max() <= 2e-5 * mult * ref.abs().max()
+            if db is not None:
+                cs = z.sum(0)
+                assert (db.double() - mult * cs).abs().max() <= 2e-5 * mult * cs.abs().max() + 1e-4
+    assert not ops.wgrad_shared_ok(srcs + srcs, dzs, ntaps) or len(srcs) <= 4

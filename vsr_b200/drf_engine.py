@@ -481,6 +481,63 @@ class DrfEngine:
                 wsb = self._workspace("colsum", ops.colsum_workspace(rows, L.bias_c))
                 ops.colsum(dz, rows, L.bias_c, db, True, wsb)
 
+        # Dense connections (drf_net.py:89-105): the 1x1 convolution of projection group g reads the concatenation of the
+        # feature maps 0..g, so the separate weight gradients read map j once for every g >= j - 20 + 5 high-resolution
+        # maps for the down-projection layers of a 6-group net.  Sets of those layers go through ONE pass over the maps
+        # (ops.wgrad_shared: every source tile loaded once, <= 8 tensor-memory accumulators per launch); the sets are the
+        # contiguous partition of g = 1..G-1 that reads the fewest maps.
+        shared_done = {}
+
+        def shared_sets(members):
+            """members: [(lname, ntaps)] with ntaps ascending -> contiguous groups minimising sum(max ntaps + len)"""
+            n, best = len(members), None
+            for cut in range(1 << max(n - 1, 0)):
+                groups, cur = [], [members[0]]
+                for i in range(1, n):
+                    if cut >> (i - 1) & 1:
+                        groups.append(cur)
+                        cur = []
+                    cur.append(members[i])
+                groups.append(cur)
+                if any(len(g_) > ops.MAX_SHARED_DZ or g_[-1][1] > ops.MAX_SHARED_SRCS or
+                       sum((nt + 1) // 2 for _, nt in g_) > ops.MAX_SHARED_ACC for g_ in groups):
+                    continue
+                cost = sum(g_[-1][1] + len(g_) for g_ in groups)
+                if best is None or cost < best[0]:
+                    best = (cost, groups)
+            return best[1] if best else []
+
+        if stacked and hasattr(ops, "wgrad_shared"):
+            for fam, src_key, dz_fmt, view in ((lambda g: f"dn{g}_c1", "hr", "dz_d{}", True), (lambda g: f"up{g}_c1", "lr", "dz_u{}", False)):
+                members = [(fam(g), g + 1) for g in range(1, G) if fam(g) in deferred]
+                if len(members) < 2:
+                    continue
+                for grp in shared_sets(members):
+                    if len(grp) < 2:
+                        continue
+                    shp = None
+
+                    def flat(b, shp_=None):
+                        b = b.view(b.shape[0] * b.shape[1], *b.shape[2:])
+                        return b.view(b.shape[0], b.shape[1], b.shape[2] * r2, F) if view else b
+
+                    srcs = [flat(bufs[f"{src_key}{j}"]) for j in range(grp[-1][1])]
+                    dzs = [flat(dzb[dz_fmt.format(nt - 1)]) for _, nt in grp]
+                    ntaps = [nt for _, nt in grp]
+                    if not ops.wgrad_shared_ok(srcs, dzs, ntaps):
+                        continue
+                    for lname, _ in grp:
+                        shared_done[lname] = (grp, srcs, dzs, ntaps)
+
+        def shared_wgrad(lname):
+            grp, srcs, dzs, ntaps = shared_done[lname]
+            layers = [P.fwd[n_] for n_, _ in grp]
+            ops.wgrad_shared(srcs, dzs, ntaps, [dw_packed[L.w_off:L.w_off + L.w_numel] for L in layers],
+                             [db_packed[L.b_off:L.b_off + L.bias_c] for L in layers], True,
+                             lambda nbytes: self._workspace("wgshared", nbytes))
+            for n_, _ in grp:
+                shared_done[n_] = None               # the whole set is done
+
         for lname, (srcs, dz, wsl, used) in pending.items():
             L = P.fwd[lname]
             ops.tapgemm_wgrad_finish(L.table, srcs, dz, dw_packed[L.w_off:L.w_off + L.w_numel],
@@ -488,7 +545,10 @@ class DrfEngine:
         # ---- bucket by bucket: deferred weight gradients, un-pack (weights, biases), hand the range over ----
         for blo, bhi, names, wparts, bpart in self.buckets:
             for lname in names:
-                if lname in deferred:
+                if lname in shared_done:
+                    if shared_done[lname] is not None:
+                        shared_wgrad(lname)
+                elif lname in deferred:
                     deferred_wgrad(lname)
             for lo, idx in wparts:
                 ops.gather_add(dw_packed, idx, gflat[lo:lo + idx.numel()])

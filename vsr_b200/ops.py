@@ -724,7 +724,8 @@ class SplitOps(CudaOps):
     # the last convolution of the forward pass.
     _READ_ONLY = ("tapgemm", "tapgemm_wgrad", "tapgemm_wgrad_workspace", "tapgemm_wgrad_partial", "colsum", "colsum_workspace",
                   "reduce_partials", "gather", "gather_add", "conv3x3_first_bwd", "conv3x3_first_bwd_workspace",
-                  "conv3x3_last_bwd_workspace", "metric_workspace", "start_timing", "stop_timing", "gemm_records", "table3")
+                  "conv3x3_last_bwd_workspace", "metric_workspace", "start_timing", "stop_timing", "gemm_records", "table3",
+                  "wgrad_shared", "wgrad_shared_ok")
 
     def __init__(self):
         super().__init__()
@@ -875,6 +876,23 @@ class SplitOps(CudaOps):
             self.launches += 6
         self._meta = None
         return False
+
+    def wgrad_shared_ok(self, srcs, dzs, ntaps):
+        return (all(t.dtype == torch.float32 and t.shape[-1] == 64 for t in (*srcs, *dzs)) and len(srcs) <= self.MAX_SHARED_SRCS and
+                len(dzs) <= self.MAX_SHARED_DZ and sum((n + 1) // 2 for n in ntaps) <= self.MAX_SHARED_ACC)
+
+    def wgrad_shared(self, srcs, dzs, ntaps, dws, dbs, accumulate, workspace_of):
+        """the three bf16 terms of every product through the shared-source kernel: (src_h, dz_h), (src_l, dz_h), (src_h, dz_l);
+        the bias gradients are the column sums of dz_h + dz_l"""
+        pl_s = [self._planes(s).view(2, *s.shape) for s in srcs]
+        pl_z = [self._planes(z, cached=False) for z in dzs]
+        hi, lo = [p[0] for p in pl_s], [p[1] for p in pl_s]
+        zh, zl = [p[0] for p in pl_z], [p[1] for p in pl_z]
+        none = [None] * len(dzs)
+        base = CudaOps.wgrad_shared
+        base(self, hi, zh, ntaps, dws, dbs, accumulate, workspace_of)
+        base(self, lo, zh, ntaps, dws, none, True, workspace_of)
+        base(self, hi, zl, ntaps, dws, dbs, True, workspace_of)
 
     def gather_split(self, src, idx, dst):
         _need_cuda(src, idx, dst)
