@@ -330,15 +330,15 @@ def test_misr_trainer_epoch_on_cpu():
     net._ops = EmuOps()
     tr = MISRTrainer("cpu", loader, loader, net, [torch.nn.L1Loss()], [1.0], [PSNR(), SSIM()],
                      FlatAdam(net.parameters(), lr=1e-3), None, None, None, 1)
-    logs = [tr._run_epoch("training")[0] for _ in range(3)]
+    logs = [tr._run_epoch("training")[0] for _ in range(2)]
     assert list(logs[0]) == ["Loss", "L1Loss", "PSNR", "SSIM"]
-    assert logs[2]["Loss"] < logs[0]["Loss"]
+    assert logs[1]["Loss"] < logs[0]["Loss"]
     before = {k: v.clone() for k, v in net.state_dict().items() if "running" in k or "num_batches" in k}
     vlog, _, out = tr._run_epoch("validation")
     assert out.shape == (2, 1, 16, 16) and vlog["Loss"] > 0
     after = net.state_dict()
     assert all(torch.equal(v, after[k]) for k, v in before.items())
-    assert int(after["spy_net.blocks.0.block.1.num_batches_tracked"]) == 3 * 2 * 2        # epochs x batches x neighbours
+    assert int(after["spy_net.blocks.0.block.1.num_batches_tracked"]) == 2 * 2 * 2        # epochs x batches x neighbours
 
 
 def test_checkpoint_interchange_with_live_reference(tmp_path):
