@@ -261,3 +261,22 @@ def test_prelu_slopes_zero_and_negative(dtype, tol):
         assert (p.grad.double() - sd[k].grad).abs().max() <= tol * gmax, k
     slopes = [k for k in sd if "prelu" in k]
     assert any(float(sd[k].grad.abs()) > 1e-3 * gmax for k in slopes)      # the slope gradients are exercised
+
+
+def test_shared_weight_gradient_sets():
+    """the sets of dense 1x1 layers that go through one wgrad_shared launch: contiguous, within the kernel's limits
+    (<= 4 gradient maps, <= 8 sources, <= 8 tensor-memory accumulators), fewest maps read"""
+    from vsr_b200.drf_engine import shared_wgrad_sets
+    mk = lambda G: [(f"dn{g}_c1", g + 1) for g in range(1, G)]
+    names = lambda sets: [[n for n, _ in s] for s in sets]
+    assert names(shared_wgrad_sets(mk(3), 4, 8, 8)) == [["dn1_c1", "dn2_c1"]]
+    six = shared_wgrad_sets(mk(6), 4, 8, 8)
+    assert names(six) == [["dn1_c1", "dn2_c1"], ["dn3_c1", "dn4_c1", "dn5_c1"]]          # 3 + 2 and 6 + 3 = 14 maps (25 apart)
+    assert sum(s[-1][1] + len(s) for s in six) == 14
+    for G in range(2, 8):
+        sets = shared_wgrad_sets(mk(G), 4, 8, 8)
+        assert [m for s in sets for m in s] == mk(G)
+        for s in sets:
+            assert len(s) <= 4 and s[-1][1] <= 8 and sum((nt + 1) // 2 for _, nt in s) <= 8
+        assert sum(s[-1][1] + len(s) for s in sets) <= sum(nt + 1 for _, nt in mk(G))
+    assert shared_wgrad_sets([], 4, 8, 8) == []

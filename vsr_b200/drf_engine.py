@@ -34,6 +34,30 @@ def _as_stacked(ts):
     return v if v is not None else torch.stack([t.contiguous() for t in ts])
 
 
+def shared_wgrad_sets(members, max_dz, max_srcs, max_acc):
+    """members: [(layer name, ntaps)] of 1x1 convolutions on prefixes of ONE feature list, ntaps ascending (layer g reads the
+    maps 0..ntaps-1).  Returns the contiguous partition into sets that one `wgrad_shared` launch can take (<= max_dz
+    layers, <= max_srcs maps, sum of ceil(ntaps / 2) <= max_acc tensor-memory accumulators) reading the fewest maps:
+    a set costs its largest ntaps (every source once) + one gradient map per layer."""
+    n, best = len(members), None
+    if n == 0:
+        return []
+    for cut in range(1 << (n - 1)):
+        groups, cur = [], [members[0]]
+        for i in range(1, n):
+            if cut >> (i - 1) & 1:
+                groups.append(cur)
+                cur = []
+            cur.append(members[i])
+        groups.append(cur)
+        if any(len(g_) > max_dz or g_[-1][1] > max_srcs or sum((nt + 1) // 2 for _, nt in g_) > max_acc for g_ in groups):
+            continue
+        cost = sum(g_[-1][1] + len(g_) for g_ in groups)
+        if best is None or cost < best[0]:
+            best = (cost, groups)
+    return best[1] if best else []
+
+
 class _Frame:
     __slots__ = ("x", "a1", "inn", "hidden", "lr", "u", "hr", "d", "f", "feat", "s", "y")
 
@@ -488,24 +512,7 @@ class DrfEngine:
         # contiguous partition of g = 1..G-1 that reads the fewest maps.
         shared_done = {}
 
-        def shared_sets(members):
-            """members: [(lname, ntaps)] with ntaps ascending -> contiguous groups minimising sum(max ntaps + len)"""
-            n, best = len(members), None
-            for cut in range(1 << max(n - 1, 0)):
-                groups, cur = [], [members[0]]
-                for i in range(1, n):
-                    if cut >> (i - 1) & 1:
-                        groups.append(cur)
-                        cur = []
-                    cur.append(members[i])
-                groups.append(cur)
-                if any(len(g_) > ops.MAX_SHARED_DZ or g_[-1][1] > ops.MAX_SHARED_SRCS or
-                       sum((nt + 1) // 2 for _, nt in g_) > ops.MAX_SHARED_ACC for g_ in groups):
-                    continue
-                cost = sum(g_[-1][1] + len(g_) for g_ in groups)
-                if best is None or cost < best[0]:
-                    best = (cost, groups)
-            return best[1] if best else []
+        shared_sets = lambda members: shared_wgrad_sets(members, ops.MAX_SHARED_DZ, ops.MAX_SHARED_SRCS, ops.MAX_SHARED_ACC)
 
         if stacked and hasattr(ops, "wgrad_shared"):
             for fam, src_key, dz_fmt, view in ((lambda g: f"dn{g}_c1", "hr", "dz_d{}", True), (lambda g: f"up{g}_c1", "lr", "dz_u{}", False)):
