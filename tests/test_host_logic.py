@@ -280,3 +280,30 @@ def test_shared_weight_gradient_sets():
             assert len(s) <= 4 and s[-1][1] <= 8 and sum((nt + 1) // 2 for _, nt in s) <= 8
         assert sum(s[-1][1] + len(s) for s in sets) <= sum(nt + 1 for _, nt in mk(G))
     assert shared_wgrad_sets([], 4, 8, 8) == []
+
+
+def test_split_ops_plane_cache_invalidation():
+    """ops.SplitOps (precision='bf16x3'): a cached plane pair dies when a tap-GEMM output overlaps its fp32 map and ALL pairs
+    die when any method that may write a map is fetched; methods that cannot write a map leave the cache alone"""
+    from vsr_b200.ops import SplitOps
+    ops = SplitOps()
+    buf = torch.zeros(4, 8, 8, 64)
+    key = lambda t: (t.data_ptr(), t.data_ptr() + t.numel() * 4)
+    ops._cache[key(buf[0])] = "p0"
+    ops._cache[key(buf[1])] = "p1"
+    ops._cache[key(buf[2:4].reshape(-1))] = "p23"
+    ops._invalidate(buf[1])                                   # exact range
+    assert set(ops._cache.values()) == {"p0", "p23"}
+    ops._invalidate(buf[3, 2:3])                              # a slice inside the stacked pair
+    assert set(ops._cache.values()) == {"p0"}
+    ops._invalidate(None)
+    for name in ("tapgemm", "tapgemm_wgrad", "colsum", "wgrad_shared", "gather", "reduce_partials", "conv3x3_first_bwd"):
+        getattr(ops, name)
+        assert ops._cache, name                               # read-only with respect to maps
+    assert ops.split and ops.partials_len > 0 and ops._cache  # plain attributes
+    for name in ("act_bwd", "conv3x3_first", "conv3x3_last_bwd", "gather_split", "add", "upsample_linear", "loss_fwd_bwd_seg"):
+        ops._cache[key(buf[0])] = "p0"
+        getattr(ops, name)
+        assert not ops._cache, name                           # may write a map: everything is re-split
+    t3 = SplitOps.table3(__import__("vsr_b200.ops", fromlist=["TapTable"]).TapTable(64, 64, [(0, [(0, 0, 0, 0), (1, 1, -1, 64)])]))
+    assert t3.groups == [(0, [(0, 0, 0, 0), (1, 1, -1, 64), (8, 0, 0, 0), (9, 1, -1, 64), (0, 0, 0, 0), (1, 1, -1, 64)])]
