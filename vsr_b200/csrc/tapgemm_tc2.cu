@@ -950,7 +950,14 @@ int tapgemm_tc2_launch(const VsrTapGemmDesc* d, cudaStream_t stream) {
   }
   if (!split) { cand[n_cand][0] = 1; cand[n_cand++][1] = 1; }
   int ndy_max = 1;
-  for (int ci = 0; ci < n_cand; ++ci) {
+  // Pass 0 evaluates the smallest epilogue staging alone, to learn whether the shared-load mode engages at all; pass 1 picks
+  // the candidate.  For long tables (>= 64 taps in a group) a candidate whose staging squeezes the shared-load mode out is
+  // skipped: double-buffered operands hide L2 latency in the epilogue, but plain columns double the L2 -> SM operand
+  // stream of every tap (the PReLU' data gradient of the 128-channel strided convolution ran 121 us against its forward
+  // twin's 60 us, profiles/r02b_sweep_config5.json).
+  bool tall_min = false;
+  for (int pass = 0; pass < 2; ++pass)
+  for (int ci = pass == 0 ? n_cand - 1 : 0; ci < n_cand; ++ci) {
     a.epi_obuf = cand[ci][0];
     a.epi_ibuf = cand[ci][1];
     a.epi_bytes = kEpiWarps * (a.epi_obuf + a.epi_ibuf * n_in) * kTileBytes;
@@ -1062,6 +1069,11 @@ int tapgemm_tc2_launch(const VsrTapGemmDesc* d, cudaStream_t stream) {
     if (stages < 1 && ci + 1 < n_cand) continue;
     VSR_CHECK_SUPPORTED(stages >= 1, "tapgemm(bf16, v2): no room for a pipeline stage");
     a.stages = stages;
+    if (pass == 0) {
+      tall_min = a.tall != 0;
+      break;
+    }
+    if (tall_min && !a.tall && d->max_group_taps >= 64 && ci + 1 < n_cand) continue;
     if (stages >= 3 || ci + 1 == n_cand) break;
   }
   const int smem = kCtrlBytes + a.epi_bytes + a.res_bytes + a.stages * a.stage_bytes;
