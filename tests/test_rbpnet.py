@@ -130,3 +130,28 @@ def test_misr_train_step_with_rbpnet_equals_reference_step():
         assert abs(float(lv[0]) - float(loss.detach())) <= 2e-5 * abs(float(loss.detach()))
     for k, p in net.named_parameters():
         assert (p.data - sd[k].data).abs().max() <= 2e-5, k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_gpu_misr_step_graph_replay_equals_eager(precision):
+    """the CUDA-graphed MISR step with RBPNet (2 eager steps + capture + 2 replays) = 5 eager steps bit for bit: the table of
+    PReLU slope-gradient destinations is uploaded by the first eager step (a host -> device copy cannot be captured)"""
+    from vsr_b200.metrics import PSNR, SSIM
+    from vsr_b200.optim import FlatAdam
+    from vsr_b200.runner import MISRTrainStep
+    fx = torch.load(BIG if precision == "bf16" else SMALL[0])
+    res = []
+    for use_graph in (False, True):
+        net = RBPNet(precision=precision, **fx["kwargs"])
+        net.load_state_dict(_state(fx))
+        net = net.cuda()
+        opt = FlatAdam(net.parameters(), lr=1e-4)
+        step = MISRTrainStep(net, [torch.nn.L1Loss()], [1.0], [PSNR().cuda(), SSIM().cuda()], opt, "acdc", use_graph=use_graph)
+        log = []
+        for _ in range(5):
+            acc = torch.zeros(4, device="cuda")
+            lv, _ = step.train_step([x.cuda() for x in fx["inputs"]], [fx["target"].cuda()], acc)
+            log.append(torch.cat([lv.reshape(-1), acc]).clone())
+        res.append((torch.stack(log), net.flat.clone()))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])

@@ -606,7 +606,11 @@ class RBPNet(BaseNet):
         lo, idx = st["bias_unpack"]
         ops.gather_add(db, idx, gflat[lo:lo + idx.numel()])
         if row_dst:
-            rd = torch.tensor(row_dst, dtype=torch.int32, device=dev)
+            # (the launch sequence is a function of the architecture only: the destination table is uploaded by the first,
+            #  eager step and reused - a host -> device copy is not capturable in the step's CUDA graph)
+            rd = st.get("row_dst")
+            if rd is None or rd.numel() != len(row_dst) or rd.device != dev:
+                rd = st["row_dst"] = torch.tensor(row_dst, dtype=torch.int32, device=dev)
             ops.reduce_partials(partials, len(row_dst), rd, gflat)
         return gflat
 

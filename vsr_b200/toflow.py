@@ -10,11 +10,11 @@ Pipeline (csrc/toflow.cu for everything that is not a convolution or a BatchNorm
   frames -> bicubic x r (one launch for all frames) -> padded to multiples of 16 with the batch minimum (device-side
   reduction, no host read-back) -> 2x2 average-pooling pyramid of all frames (three launches) -> per neighbour frame:
   SpyNet = 4 levels of {bilinear x2 of the flow (align_corners=True), warp of the neighbour + concatenation [ref, warped,
-  flow] in ONE kernel, five 7x7 convolutions (49 taps x cin / 16 each) with BatchNorm2d (batch statistics, running buffers
+  flow] in ONE kernel, five 7x7 convolutions (49 taps x cin / 32 each) with BatchNorm2d (batch statistics, running buffers
   updated once per call like the module) + ReLU between them, flow update} -> warp of the full-resolution neighbour straight
   into its channel of the output block's input -> 9x9, 9x9, 1x1, 1x1 convolutions (ReLU in the epilogues) -> + reference
   frame, crop.
-Layout: feature maps pixel-major [N, h, w, c] with the channel counts padded to multiples of 16 by structural zeros; images
+Layout: feature maps pixel-major [N, h, w, c] with the channel counts padded to multiples of 32 by structural zeros; images
 and flows planar.  Backward: the forward pass records one entry per launch and the backward pass walks the record in
 reverse; the up-sampled / padded frames are data (no parameter precedes them), so gradients stop at the warps' flow inputs.
 """
@@ -45,7 +45,7 @@ def _spy_block(cin):
 
 class ToflowPlan(RbpPlan):
     """Tap tables and packing maps of TOFlowNet; reuses the packing machinery of DrfPlan / RbpPlan."""
-    KC = 16
+    KC = 32
 
     def __init__(self, named_shapes, T):
         self.variant, self.T, self.r, self.bf16 = "toflow", T, 1, False
