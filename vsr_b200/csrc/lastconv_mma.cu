@@ -73,7 +73,7 @@ __device__ __forceinline__ Tile decode(const LcGeom& g, long t) {
 // forward.  NH = C / 32 (a lane loads 16 bytes = 8 channels of each 32-channel half of a pixel).
 // ------------------------------------------------------------------------------------------------------------------
 template <int NH>
-__global__ void __launch_bounds__(kThreads) lastconv_fwd_kernel(const __nv_bfloat16* __restrict__ x,
+__global__ void __launch_bounds__(kThreads, 4) lastconv_fwd_kernel(const __nv_bfloat16* __restrict__ x,
                                                                 const __grid_constant__ LcGeom g,
                                                                 const float* __restrict__ wt, const float* __restrict__ bias,
                                                                 float* __restrict__ y) {
