@@ -90,7 +90,9 @@ def _check_net(net, fx, device, out_tol, grad_tol, srnet_floor=None):
     for o, ref in zip(lr, fx["lr_imgs"]):
         assert (o.detach().cpu() - ref).abs().max() <= out_tol * ref.abs().max()
     flow_loss, sr_loss = _losses(sr, lr, fx)
-    assert abs(float(flow_loss) - float(fx["flow_loss"])) <= 1e-5 and abs(float(sr_loss) - float(fx["sr_loss"])) <= 1e-5
+    # (loss bar of DESIGN.md section 1: relative 1e-5; the fixtures' losses are 1.0 .. 1.8)
+    assert abs(float(flow_loss) - float(fx["flow_loss"])) <= 1e-5 * max(1.0, float(fx["flow_loss"]))
+    assert abs(float(sr_loss) - float(fx["sr_loss"])) <= 1e-5 * max(1.0, float(fx["sr_loss"]))
     (flow_loss + sr_loss).backward()
     got = {k: p.grad.detach() for k, p in net.named_parameters()}
     for prefix, floor in (("srnet.", srnet_floor or grad_tol), ("fnet.", 5e-3)):
@@ -262,3 +264,42 @@ def test_frvsr_train_step_gpu_graphed():
     Adam divides by sqrt(v) + eps, so the flow net's ill-conditioned fp32 gradients (_check_net) move elements with small
     gradients by a visible fraction of lr = 1e-3 per step"""
     _frvsr_step_vs_oracle("cuda", 4, True, 1e-3, 1e-4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", CASES, ids=ids)
+def test_gpu_bf16x3_matches_reference_golden(path):
+    """precision='bf16x3': SRNet's 64 -> 64 layers on the tcgen05 tap-GEMM as three bf16 products per product, the flow net
+    and the 17-channel head on the CUDA cores, fp32 maps - the same bars as the strict fp32 mode"""
+    from vsr_b200.frvsr import FRVSRNet
+    from vsr_b200.ops import SplitOps
+    fx = torch.load(path)
+    net = FRVSRNet(precision="bf16x3", **fx["kwargs"])
+    net.load_state_dict(_state(fx))
+    net = net.cuda()
+    assert isinstance(net._backend(), SplitOps) and {"s_b0_1", "s_d1", "s_d2"} <= set(net._planB.fwd) and "f4_2" in net._plan.fwd
+    _check_net(net, fx, "cuda", 1e-4, 1e-4, srnet_floor=5e-3)
+
+
+@pytest.mark.gpu
+def test_frvsr_train_step_gpu_graphed_bf16x3():
+    """the fused, CUDA-graphed FRVSR step in the mixed mode: graph replay = eager launch bit for bit"""
+    from vsr_b200.frvsr import FRVSRNet
+    from vsr_b200.metrics import PSNR, SSIM
+    from vsr_b200.optim import FlatAdam
+    from vsr_b200.runner import FRVSRTrainStep
+    fx = torch.load(CASES[0])
+    res = []
+    for use_graph in (False, True):
+        net = FRVSRNet(precision="bf16x3", **fx["kwargs"])
+        net.load_state_dict(_state(fx))
+        net = net.cuda()
+        step = FRVSRTrainStep(net, [torch.nn.L1Loss(), torch.nn.MSELoss()], [1.0, 0.5], [PSNR().cuda(), SSIM().cuda()],
+                              FlatAdam(net.parameters(), lr=1e-4), "acdc", use_graph=use_graph)
+        log = []
+        for _ in range(5):
+            acc = torch.zeros(5, device="cuda")
+            lv, _ = step.train_step([x.cuda() for x in fx["inputs"]], [y.cuda() for y in fx["targets"]], acc)
+            log.append(torch.cat([lv.reshape(-1), acc]).clone())
+        res.append((torch.stack(log), net.flat.clone()))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])

@@ -55,9 +55,9 @@ def cases():
                 lambda p: RBPNet(1, 1, 64, 64, 3, 5, 7, 4, precision=p), MISRTrainStep, [l1()],
                 lambda n: (frames(n, 7, 7), frames(n, 1, 8, True)),
                 lambda sd, x: [restated.rbpnet_forward(x, sd, 4, 7)], 1, ("bf16", "bf16x3", "fp32")))
-    out.append(("FRVSRNet(10 blocks) x4, 5 frames", 8, lambda p: FRVSRNet(1, 1, 4, num_resblocks=10), FRVSRTrainStep, [l1(), l1()],
-                lambda n: (frames(n, 5, 9), frames(n, 5, 10, True)),
-                lambda sd, x: restated.frvsrnet_forward(x, sd, 4), 5, ("fp32",)))
+    out.append(("FRVSRNet(10 blocks) x4, 5 frames", 8, lambda p: FRVSRNet(1, 1, 4, num_resblocks=10, precision=p), FRVSRTrainStep,
+                [l1(), l1()], lambda n: (frames(n, 5, 9), frames(n, 5, 10, True)),
+                lambda sd, x: restated.frvsrnet_forward(x, sd, 4), 5, ("bf16x3", "fp32")))
     out.append(("TOFlowNet(7 frames) x4", 8, lambda p: TOFlowNet(1, 1, 7, 4), MISRTrainStep, [torch.nn.MSELoss()],
                 lambda n: (frames(n, 7, 11), frames(n, 1, 12, True)),
                 lambda sd, x: [restated.toflownet_forward(x, sd, 4, True, None)], 1, ("fp32",)))

@@ -4,8 +4,10 @@ residual blocks and two stride-2 transposed convolutions").
 
 Same constructor arguments, forward I/O (list of T frames [N,C,h,w] -> (sr_imgs, lr_imgs), or sr_imgs alone with
 `is_prediction`) and state_dict (keys, shapes; Xavier-uniform convolution weights like :33-37) as the reference.  Strict
-fp32 mode only (`precision='fp32'`: the CUDA-core tap-GEMM); FNet's 32-channel levels do not fit the 64-channel tcgen05
-tiles and the net is not on BASELINE's headline path.
+accuracy only: `precision='fp32'` runs every layer on the CUDA-core tap-GEMM; `precision='bf16x3'` (alias 'tf32') runs
+SRNet's 64 -> 64 layers - 0.92 of the MACs - on the tcgen05 tap-GEMM as three bf16 products per product (fp32 maps,
+ops.SplitOps); the flow net and SRNet's 17-channel head stay on the CUDA cores (the warp amplifies a flow error by the image
+gradient times half the frame width: fp32 products are needed there to hold the 1e-4 output bar).
 
 Layout: every feature map is pixel-major [N, h, w, c].  SRNet's two ConvTranspose2d(k=3, s=2, p=1, output_padding=1)
 (:82-85) write the phase-blocked high-resolution layout of the other nets: the first one LR -> four 2x phase
@@ -72,9 +74,12 @@ class FrvsrPlan(RbpPlan):
     FLOW_PAD = 32       # output channels of the flow head (2 real; one K chunk for its data gradient)
     SIN_PAD = 32        # input channels of SRNet's head (r*r + 1 = 17 real)
 
-    def __init__(self, named_shapes, R):
-        self.variant, self.R, self.r, self.bf16 = "frvsr", R, 4, False
-        self.kc = self.KC
+    def __init__(self, named_shapes, R, subset=None, kc=None, bf16=False):
+        """subset: None = every layer (strict fp32 mode); 'wide' = the layers with 64-channel blocks on both sides (the
+        tensor-core tables of precision='bf16x3': kc = 64, bf16 slab layout), 'narrow' = the others (CUDA-core tables)"""
+        self.variant, self.R, self.r, self.bf16 = "frvsr", R, 4, bf16
+        self.subset = subset
+        self.kc = kc or self.KC
         self.F, self.Fe, self.B, self.G = 64, 64, 64, 0
         self.phases = phase_table(4)
         self.slot_of = {yx: i for i, yx in enumerate(self.phases)}
@@ -87,8 +92,10 @@ class FrvsrPlan(RbpPlan):
 
     # 3x3 convolution on a pixel-major map; channels beyond cin / cout (up to cin_pad / cout_pad) are structural zeros
     def _conv3(self, lname, wname, cin, cout, act, cin_pad=None, cout_pad=None, need_dgrad=True):
-        W, kc = self._W(wname), self.kc
         cin_pad, cout_pad = cin_pad or cin, cout_pad or cout
+        if not self._take(lname, cin_pad, cout_pad):
+            return
+        W, kc = self._W(wname), self.kc
         self.act[lname] = act
         groups, slabs = [], []
         for (o0, nt) in _split_nt(cout_pad):
@@ -121,7 +128,15 @@ class FrvsrPlan(RbpPlan):
 
     # ConvTranspose2d(C, C, k=3, s=2, p=1, output_padding=1) from resolution level `lvl` (1 or 2) to 2 * lvl on phase-blocked
     # maps.  Along an axis output 2I + q reads input I with kernel tap 1 (q = 0), or I with tap 2 and I + 1 with tap 0 (q = 1).
+    def _take(self, lname, ci, co):
+        # SRNet only: the flow net keeps fp32 products - a flow error of 1e-5 (the 16 significant bits of a bf16 pair) is
+        # multiplied by the image gradient and half the frame width in the warp and shows as 7e-4 in the next frame's output
+        wide = lname.startswith("s_") and ci % 64 == 0 and co % 64 == 0
+        return self.subset is None or (self.subset == "wide") == wide
+
     def _deconv2(self, lname, wname, C, lvl):
+        if not self._take(lname, C, C):
+            return
         WT, kc = self._W(wname), self.kc                     # [Cin, Cout, 3, 3]
         self.act[lname] = "relu"
         Q = {0: [(0, 1)], 1: [(0, 2), (1, 0)]}               # q -> [(input offset, kernel tap)]
@@ -200,8 +215,9 @@ class FRVSRNet(BaseNet):
 
     def __init__(self, in_channels, out_channels, upscale_factor, is_prediction=False, num_resblocks=10, precision="fp32"):
         super().__init__()
-        if precision != "fp32":
-            raise ValueError("FRVSRNet runs in the strict fp32 mode only (precision='fp32')")
+        if precision not in ("fp32", "bf16x3", "tf32"):
+            raise ValueError("FRVSRNet: precision 'fp32' (CUDA cores) or 'bf16x3' / 'tf32' (the strict bar with the 64-channel "
+                             "layers on the tensor cores)")
         if in_channels != 1 or out_channels != 1:
             raise NotImplementedError("FRVSRNet: in_channels = out_channels = 1 (single-channel cine MRI)")
         if upscale_factor != 4:
@@ -213,7 +229,13 @@ class FRVSRNet(BaseNet):
         for m in self.modules():                                     # frvsr_net.py:33-37
             if m.__class__.__name__.find("Conv") != -1:
                 nn.init.xavier_uniform_(m.weight)
-        self._plan = FrvsrPlan([(n, tuple(q.shape)) for n, q in self.named_parameters()], num_resblocks)
+        shapes = [(n, tuple(q.shape)) for n, q in self.named_parameters()]
+        # precision='bf16x3': SRNet's residual blocks and transposed convolutions (64 -> 64: 0.92 of the MACs) run on the tensor
+        # cores as three bf16 products per product (ops.SplitOps); SRNet's 17-channel head and the whole
+        # flow net stay on the CUDA-core tap-GEMM (FrvsrPlan._take); maps are fp32 throughout
+        self._hybrid = precision != "fp32"
+        self._plan = FrvsrPlan(shapes, num_resblocks, subset="narrow" if self._hybrid else None)
+        self._planB = FrvsrPlan(shapes, num_resblocks, subset="wide", kc=64, bf16=True) if self._hybrid else None
         self._ops = None
         self._dev_state = None
         self.flat = self.flat_grad = None
@@ -221,8 +243,24 @@ class FRVSRNet(BaseNet):
 
     # the flat-bucket plumbing is RBPNet's
     from .rbpn import RBPNet as _R
-    _flatten, _is_flat, _backend, _ws, _pview, _pack = _R._flatten, _R._is_flat, _R._backend, _R._ws, _R._pview, _R._pack
+    _flatten, _is_flat, _backend, _ws, _pview, _make_state = _R._flatten, _R._is_flat, _R._backend, _R._ws, _R._pview, _R._make_state
     del _R
+
+    def _pack(self, need_bwd):
+        from .nets import pack_weights
+        st = self._state()
+        pack_weights(self, st, need_bwd)
+        if self._hybrid:
+            pack_weights(self, st["B"], need_bwd)
+
+    def _of(self, lname):
+        """(plan, state, tap-GEMM, weight gradient, its workspace size) of a layer: the tensor-core tables of the bf16x3 mode
+        or the CUDA-core ones"""
+        ops, st = self._backend(), self._state()
+        if self._hybrid and lname in self._planB.fwd:
+            return self._planB, st["B"], ops.tapgemm, ops.tapgemm_wgrad, ops.tapgemm_wgrad_workspace
+        return (self._plan, st, getattr(ops, "tapgemm_plain", ops.tapgemm), getattr(ops, "tapgemm_wgrad_plain", ops.tapgemm_wgrad),
+                getattr(ops, "tapgemm_wgrad_workspace_plain", ops.tapgemm_wgrad_workspace))
 
     def _apply(self, fn, *a, **kw):
         out = super()._apply(fn, *a, **kw)
@@ -231,9 +269,13 @@ class FRVSRNet(BaseNet):
 
     def _state(self):
         if self._dev_state is None:
-            from .rbpn import RBPNet
-            st = RBPNet._state(self)
+            st = self._make_state(self._plan, False if self._hybrid else None)
+            if self._hybrid:
+                if self.flat.dtype != torch.float32 or not getattr(self._backend(), "split", False):
+                    raise RuntimeError("FRVSRNet(precision='bf16x3') runs on the CUDA backend in fp32 storage only")
+                st["B"] = self._make_state(self._planB, True)
             st["lrelu"] = torch.tensor([_LRELU], dtype=self.flat.dtype, device=self.flat.device)
+            self._dev_state = st
         return self._dev_state
 
     # ---- forward ----
@@ -246,8 +288,9 @@ class FRVSRNet(BaseNet):
         rec = (lambda *e: tape.append(e)) if save else (lambda *e: None)
 
         def conv(lname, src, residual=None):
-            L = P.fwd[lname]
-            a = P.act[lname]
+            P_, st_, tapgemm, _, _ = self._of(lname)
+            L = P_.fwd[lname]
+            a = P_.act[lname]
             out = new(src.shape[1], src.shape[2], L.out_c)
             epi, kw = EPI_BIAS, {}
             if a == "lrelu":
@@ -258,8 +301,8 @@ class FRVSRNet(BaseNet):
             if residual is not None:
                 epi |= EPI_RES_PRE
                 kw["residual"] = residual
-            ops.tapgemm(L.table, [src], out, st["fwd_w"][L.w_off:L.w_off + L.w_numel],
-                        bias=st["fwd_b"][L.b_off:L.b_off + L.out_c], epi=epi, **kw)
+            tapgemm(L.table, [src], out, st_["fwd_w"][L.w_off:L.w_off + L.w_numel],
+                    bias=st_["fwd_b"][L.b_off:L.b_off + L.out_c], epi=epi, **kw)
             rec("conv", lname, src, out, residual)
             return out
 
@@ -337,8 +380,9 @@ class FRVSRNet(BaseNet):
         lr_outs = [e[3] for e in tape if e[0] == "warp"][1::2]         # per frame: the SR warp first, then the LR warp
         dev, pd = sr_outs[0].device, self.flat.dtype
         gflat = torch.zeros(P.n_params, dtype=pd, device=dev)
-        dw = torch.zeros(P.fwd_w_numel, dtype=pd, device=dev)
-        db = torch.zeros(P.fwd_b_numel, dtype=pd, device=dev)
+        plans = [(P, st)] + ([(self._planB, st["B"])] if self._hybrid else [])
+        dwb = {id(p_): (torch.zeros(p_.fwd_w_numel, dtype=pd, device=dev), torch.zeros(p_.fwd_b_numel, dtype=pd, device=dev))
+               for p_, _ in plans}
         scratch = torch.zeros(ops.partials_len, dtype=pd, device=dev)  # slope-gradient partials of the constant LeakyReLU
         G = {}
 
@@ -385,18 +429,20 @@ class FRVSRNet(BaseNet):
                 ent = G.pop(out.data_ptr(), None)
                 if ent is None:
                     continue
-                L = P.fwd[lname]
-                dz = act_bwd(ent[0], out, P.act[lname])
+                P_, st_, tapgemm, wgrad, wgrad_ws = self._of(lname)
+                dw, db = dwb[id(P_)]
+                L = P_.fwd[lname]
+                dz = act_bwd(ent[0], out, P_.act[lname])
                 if residual is not None:
                     acc(residual, dz)
-                ws = self._ws("wgrad", ops.tapgemm_wgrad_workspace(L.table, [src], dz))
+                ws = self._ws("wgrad", wgrad_ws(L.table, [src], dz))
                 dbl = db[L.b_off:L.b_off + L.bias_c]
-                if not ops.tapgemm_wgrad(L.table, [src], dz, dw[L.w_off:L.w_off + L.w_numel], True, ws, db=dbl, db_period=L.bias_c):
+                if not wgrad(L.table, [src], dz, dw[L.w_off:L.w_off + L.w_numel], True, ws, db=dbl, db_period=L.bias_c):
                     rows = dz.numel() // L.bias_c
                     ops.colsum(dz, rows, L.bias_c, dbl, True, self._ws("colsum", ops.colsum_workspace(rows, L.bias_c)))
-                Lb = P.bwd[lname]
+                Lb = P_.bwd[lname]
                 ds = torch.empty_like(src)
-                ops.tapgemm(Lb.table, [dz], ds, st["bwd_w"][Lb.w_off:Lb.w_off + Lb.w_numel], epi=0)
+                tapgemm(Lb.table, [dz], ds, st_["bwd_w"][Lb.w_off:Lb.w_off + Lb.w_numel], epi=0)
                 acc(src, ds)
             elif kind == "first":
                 _, prefix, xin, y = e
@@ -448,10 +494,12 @@ class FRVSRNet(BaseNet):
                     d = torch.empty_like(warped)
                     ops.s2d_cat_bwd(ent[0].view(sin.shape), 4, d)
                     acc(warped, d)
-        for lo, idx in st["unpack"]:
-            ops.gather_add(dw, idx, gflat[lo:lo + idx.numel()])
-        lo, idx = st["bias_unpack"]
-        ops.gather_add(db, idx, gflat[lo:lo + idx.numel()])
+        for p_, st_ in plans:
+            dw, db = dwb[id(p_)]
+            for lo, idx in st_["unpack"]:
+                ops.gather_add(dw, idx, gflat[lo:lo + idx.numel()])
+            lo, idx = st_["bias_unpack"]
+            ops.gather_add(db, idx, gflat[lo:lo + idx.numel()])
         return gflat
 
     def forward(self, inputs):

@@ -41,10 +41,10 @@ def split_mode(net):
     return net.precision in ("bf16x3", "tf32") and net.flat.dtype != torch.float64 and getattr(net._backend(), "split", False)
 
 
-def packed_weight_state(net, P, dev, act):
+def packed_weight_state(net, P, dev, act, split=None):
     """the packed weight / bias buffers and packing maps shared by the nets that keep their own state dict (RBPNet,
-    EDSRNet, ...): plain slabs, or the tripled bf16 slabs of the bf16x3 mode"""
-    if split_mode(net):
+    EDSRNet, ...): plain slabs, or the tripled bf16 slabs of the bf16x3 mode (`split`: None = by the net's precision)"""
+    if split_mode(net) if split is None else split:
         return {"fwd_w": TripledSlabs(torch.empty(3 * P.fwd_w_numel, dtype=torch.bfloat16, device=dev)),
                 "bwd_w": TripledSlabs(torch.empty(3 * P.bwd_w_numel, dtype=torch.bfloat16, device=dev)),
                 "fwd_w_idx": torch.from_numpy(P.split_index("fwd")).to(dev), "bwd_w_idx": torch.from_numpy(P.split_index("bwd")).to(dev),

@@ -189,6 +189,16 @@ class CudaOps:
     def tapgemm_wgrad_workspace(self, tab, srcs, dz):
         return self.lib.vsr_tapgemm_wgrad_workspace(C.byref(_make_desc(tab, srcs, dz)))
 
+    # (the names SplitOps gives to the CUDA-core path of mixed nets; here they are the methods themselves)
+    def tapgemm_plain(self, tab, srcs, out, w, **kw):
+        return self.tapgemm(tab, srcs, out, w, **kw)
+
+    def tapgemm_wgrad_plain(self, tab, srcs, dz, dw, accumulate, workspace, db=None, db_period=0):
+        return self.tapgemm_wgrad(tab, srcs, dz, dw, accumulate, workspace, db=db, db_period=db_period)
+
+    def tapgemm_wgrad_workspace_plain(self, tab, srcs, dz):
+        return self.tapgemm_wgrad_workspace(tab, srcs, dz)
+
     def tapgemm_wgrad(self, tab, srcs, dz, dw, accumulate, workspace, db=None, db_period=0):
         """weight gradient; with db, also tries to fuse the bias gradient — returns True if db was produced."""
         d = _make_desc(tab, srcs, dz)
@@ -725,7 +735,7 @@ class SplitOps(CudaOps):
     _READ_ONLY = ("tapgemm", "tapgemm_wgrad", "tapgemm_wgrad_workspace", "tapgemm_wgrad_partial", "colsum", "colsum_workspace",
                   "reduce_partials", "gather", "gather_add", "conv3x3_first_bwd", "conv3x3_first_bwd_workspace",
                   "conv3x3_last_bwd_workspace", "metric_workspace", "start_timing", "stop_timing", "gemm_records", "table3",
-                  "wgrad_shared", "wgrad_shared_ok")
+                  "wgrad_shared", "wgrad_shared_ok", "tapgemm_plain", "tapgemm_wgrad_plain", "tapgemm_wgrad_workspace_plain")
 
     def __init__(self):
         super().__init__()
@@ -893,6 +903,19 @@ class SplitOps(CudaOps):
         base(self, hi, zh, ntaps, dws, dbs, accumulate, workspace_of)
         base(self, lo, zh, ntaps, dws, none, True, workspace_of)
         base(self, hi, zl, ntaps, dws, dbs, True, workspace_of)
+
+    # the CUDA-core fp32 tap-GEMM through THIS backend (nets that mix narrow CUDA-core layers with 64-channel tensor-core
+    # layers: FRVSRNet): the cache must see the write
+    def tapgemm_plain(self, tab, srcs, out, w, **kw):
+        self._invalidate(out)
+        self._invalidate(kw.get("out2"))
+        return CudaOps.tapgemm(self, tab, srcs, out, w, **kw)
+
+    def tapgemm_wgrad_plain(self, tab, srcs, dz, dw, accumulate, workspace, db=None, db_period=0):
+        return CudaOps.tapgemm_wgrad(self, tab, srcs, dz, dw, accumulate, workspace, db=db, db_period=db_period)
+
+    def tapgemm_wgrad_workspace_plain(self, tab, srcs, dz):
+        return CudaOps.tapgemm_wgrad_workspace(self, tab, srcs, dz)
 
     def gather_split(self, src, idx, dst):
         _need_cuda(src, idx, dst)

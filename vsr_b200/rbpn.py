@@ -380,18 +380,24 @@ class RBPNet(BaseNet):
 
     def _state(self):
         if self._dev_state is None:
-            P, dev = self._plan, self.flat.device
+            self._dev_state = self._make_state(self._plan, None)
+        return self._dev_state
+
+    def _make_state(self, P, split):
+        """packed weight / bias buffers and un-packing maps of plan `P` (split: None = by the precision, True / False =
+        tripled bf16 slabs of the bf16x3 mode / plain slabs - nets that mix both kinds of layers keep one state per plan)"""
+        if True:
+            dev = self.flat.device
             act = torch.float64 if self.flat.dtype == torch.float64 else _PRECISIONS[self.precision]
             st = {"act": act,
                   "fwd_b": torch.empty(P.fwd_b_numel, dtype=self.flat.dtype, device=dev),
                   "fwd_b_idx": torch.from_numpy(P.fwd_b_idx).to(dev),
                   "unpack": [(lo, torch.from_numpy(i).to(dev)) for lo, i in P.unpack_passes], "ws": {}}
-            st.update(packed_weight_state(self, P, dev, act))
+            st.update(packed_weight_state(self, P, dev, act, split))
             b = P.bias_unpack_idx
             nz = (b >= 0).nonzero()[0]
             st["bias_unpack"] = (int(nz.min()), torch.from_numpy(b[nz.min():nz.max() + 1].copy()).to(dev))
-            self._dev_state = st
-        return self._dev_state
+        return st
 
     def _ws(self, key, nbytes):
         st = self._state()["ws"]
