@@ -153,8 +153,8 @@ class TOFlowNet(BaseNet):
 
     # the flat-bucket plumbing is RBPNet's
     from .rbpn import RBPNet as _R
-    _flatten, _is_flat, _backend, _ws, _pview, _pack, _state = (_R._flatten, _R._is_flat, _R._backend, _R._ws, _R._pview,
-                                                                _R._pack, _R._state)
+    _flatten, _is_flat, _backend, _ws, _pview, _pack, _state, _make_state = (_R._flatten, _R._is_flat, _R._backend, _R._ws,
+                                                                             _R._pview, _R._pack, _R._state, _R._make_state)
     del _R
 
     def _apply(self, fn, *a, **kw):
