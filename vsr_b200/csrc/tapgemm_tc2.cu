@@ -156,6 +156,13 @@ __device__ __forceinline__ TileCoord decode_tile(const Tc2Args& a, int tile, int
   return t;
 }
 
+// PReLU' of one element whose stored activation is f (slope > 0 or = 0: the branch is the sign of f): where f <= 0 the
+// slope sum takes g * f and g is scaled by the slope.  Two predicated instructions behind one FSETP.
+__device__ __forceinline__ void prelu_bwd_elem(float& acc, float& g, float f, float slope) {
+  asm("{\n\t.reg .pred pp;\n\tsetp.gt.f32 pp, %2, 0f00000000;\n\t"
+      "@!pp fma.rn.f32 %0, %1, %2, %0;\n\t@!pp mul.f32 %1, %1, %3;\n\t}"
+      : "+f"(acc), "+f"(g) : "f"(f), "f"(slope));
+}
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -514,7 +521,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
     // (slope == 0 and slope < 0: see Prelu in common.cuh)
     const Prelu pr = make_prelu((epi & (VSR_EPI_PRELU | VSR_EPI_PRELU_BWD)) ? __ldg(a.slope) : 1.f);
     const bool slope01 = pr.fwd >= 0.f && pr.fwd <= 1.f;
-    float slope_acc = 0.f;
+    float slope_acc = 0.f, slope_acc1 = 0.f;      // (two chains: even / odd channels)
     long long e_wait = 0, e_in = 0, e_ld = 0, e_math = 0, e_st = 0, e_iss = 0, e_t0 = kAttrib ? clock64() : 0;
 
     // the chunks of this warp in processing order: (tile, sub-tile m, first channel c)
@@ -640,26 +647,51 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
               for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
             }
             if (epi & (VSR_EPI_PRELU_BWD | VSR_EPI_RELU_BWD)) {
+              // The branch of an element is decided once per warp-uniform case OUTSIDE the element loop and the two
+              // updates are predicated on it (unpack, FSETP, @!pos FFMA, @!pos FMUL: ~4 instructions per element).  With
+              // the tag test inside the loop and select-style arithmetic the compiler materialised every predicate as an
+              // integer and re-tested it (~12 instructions per element: the epilogue warps, not the MMAs or the
+              // memory system, bounded the PReLU' data gradients).
+              // out-of-image pixels read f = 0 from the TMA zero fill and contribute exactly 0.
+              // d(slope) = sum over x <= 0 of g * x with x = y / slope: accumulate g * y here and scale by 1 / slope
+              // once per CTA.
+              if ((epi & VSR_EPI_PRELU_BWD) && pr.tag) {         // negative slope: the branch travels in the LSB of y
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const uint4 aq = ld_shared_v4(tile_addr(aux_t, lane, 4 * h + j));
-                const uint32_t w4[4] = {aq.x, aq.y, aq.z, aq.w};
+                for (int j = 0; j < 4; ++j) {
+                  const uint4 aq = ld_shared_v4(tile_addr(aux_t, lane, 4 * h + j));
+                  const uint32_t w4[4] = {aq.x, aq.y, aq.z, aq.w};
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
+                  for (int q = 0; q < 4; ++q) {
 #pragma unroll
-                  for (int p = 0; p < 2; ++p) {
-                    const float f = p ? bf16_hi(w4[q]) : bf16_lo(w4[q]);
-                    const int i = 8 * j + 2 * q + p;
-                    bool pos = f > 0.f;
-                    if (epi & VSR_EPI_PRELU_BWD) {
-                      if (pr.tag) pos = ((w4[q] >> (16 * p)) & 1u) != 0u;
-                      // out-of-image pixels read f = 0 from the TMA zero fill and contribute exactly 0
-                      // d(slope) = sum over x <= 0 of g * x with x = y / slope: accumulate g * y here and
-                      // scale by 1 / slope once per CTA
-                      slope_acc = fmaf(v[i], pos ? 0.f : f, slope_acc);
-                      v[i] *= pos ? 1.f : pr.slope;
-                    } else {
-                      v[i] = pos ? v[i] : 0.f;
+                    for (int p = 0; p < 2; ++p) {
+                      const int i = 8 * j + 2 * q + p;
+                      const float f = p ? bf16_hi(w4[q]) : bf16_lo(w4[q]);
+                      if (!(w4[q] & (1u << (16 * p)))) {
+                        slope_acc = fmaf(v[i], f, slope_acc);
+                        v[i] *= pr.slope;
+                      }
+                    }
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const uint4 aq = ld_shared_v4(tile_addr(aux_t, lane, 4 * h + j));
+                  const uint32_t w4[4] = {aq.x, aq.y, aq.z, aq.w};
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+#pragma unroll
+                    for (int p = 0; p < 2; ++p) {
+                      const int i = 8 * j + 2 * q + p;
+                      const float f = p ? bf16_hi(w4[q]) : bf16_lo(w4[q]);
+                      if (epi & VSR_EPI_PRELU_BWD) {
+                        // (written as predicated PTX: from the C++ form the compiler built FFMA + FSEL, one serial
+                        // 8-cycle link per element in the slope sum)
+                        if (p) prelu_bwd_elem(slope_acc1, v[i], f, pr.slope);
+                        else prelu_bwd_elem(slope_acc, v[i], f, pr.slope);
+                      } else if (!(f > 0.f)) {
+                        v[i] = 0.f;
+                      }
                     }
                   }
                 }
@@ -752,7 +784,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
       printf("tc2-prof epilogue warp %d: total %lld cyc, wait(tfull) %lld, operands %lld, tmem-ld %lld, math %lld, pack+sts %lld, fence+issue %lld\n",
              warp, clock64() - e_t0, e_wait, e_in, e_ld, e_math, e_st, e_iss);
     if (epi & VSR_EPI_PRELU_BWD) {
-      slope_acc = warp_sum(slope_acc) * pr.inv;
+      slope_acc = warp_sum(slope_acc + slope_acc1) * pr.inv;
       if (lane == 0) red[ew] = slope_acc;
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (ew == 0 && lane == 0)
