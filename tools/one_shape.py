@@ -1,6 +1,9 @@
 """Run ONE tap-GEMM shape a few times (for `ncu --set full --import-source on -k regex:tapgemm_tc2 -s 4 -c 1`).
 
-    python tools/one_shape.py hr2 | hr6 | deconv | conv8 | deconv_bwd | duf_c2z | duf_c2 | duf_dgrad
+    python tools/one_shape.py hr2 | hr6 | deconv | conv8 | deconv_bwd | dgrad16 | duf_c2z | duf_c2 | duf_dgrad
+
+`dgrad16`: the data gradient of the strided 8x8 convolution with the PReLU' epilogue (16 taps, nt 256, 4 groups, epi 16:
+saved activation by TMA, slope-gradient partial sums) - the shape whose epilogue was instruction-bound.
 """
 import os
 import sys
@@ -39,6 +42,23 @@ def main():
             kbench.tapgemm_case("duf_dgrad", tab, n, h, w, [288, 288, 288], 128, torch.bfloat16, 3, flush, res)
         return
     N, h, w, F = 32, 32, 32, 64
+    if which == "dgrad16":
+        ops = kbench.cuda_ops()
+        groups = []
+        for g in range(4):
+            gy, gx = g // 2, g % 2
+            groups.append((g * 256, [(0, dy - 1 + gy, dx - 1 + gx, 0) for dy in (0, 1) for dx in (0, 1)]))
+        tab = TapTable(64, 256, groups)
+        dz = torch.randn(N, h, w, F, device="cuda").to(torch.bfloat16)
+        y = torch.randn(N, h, w, 16 * F, device="cuda").to(torch.bfloat16)        # saved activation of the consumer
+        out = torch.empty_like(y)
+        wts = (torch.randn(tab.n_taps_total * tab.nt * tab.kc, device="cuda") * 0.05).to(torch.bfloat16)
+        slope = torch.tensor([0.2], device="cuda")
+        parts = torch.zeros(1024, device="cuda")
+        fn = lambda: ops.tapgemm(tab, [dz], out, wts, epi=16, slope=slope, aux_y=y, slope_partials=parts)
+        ms = kbench.timed(fn, 5, flush)
+        print("dgrad16", ms * 1e3, "us")
+        return
     if which in ("deconv", "deconv_bwd"):
         groups = []
         for g in range(4):

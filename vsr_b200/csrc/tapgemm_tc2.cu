@@ -156,6 +156,12 @@ __device__ __forceinline__ TileCoord decode_tile(const Tc2Args& a, int tile, int
   return t;
 }
 
+// two fp32 additions in one instruction (FADD2: sm_100 packed fp32, same rounding as two FADDs)
+__device__ __forceinline__ void add2(float& x, float& y, float bx, float by) {
+  const float2 r = __fadd2_rn(make_float2(x, y), make_float2(bx, by));
+  x = r.x;
+  y = r.y;
+}
 // PReLU' of one element whose stored activation is f (slope > 0 or = 0: the branch is the sign of f): where f <= 0 the
 // slope sum takes g * f and g is scaled by the slope.  Two predicated instructions behind one FSETP.
 __device__ __forceinline__ void prelu_bwd_elem(float& acc, float& g, float f, float slope) {
@@ -602,14 +608,16 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                   const float4 b = bp[i];
-                  v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+                  add2(v[4 * i], v[4 * i + 1], b.x, b.y);
+                  add2(v[4 * i + 2], v[4 * i + 3], b.z, b.w);
                 }
               } else {
                 const float4* bp = reinterpret_cast<const float4*>(a.bias + grp.x + c + 32 * h);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                   const float4 b = __ldg(bp + i);
-                  v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+                  add2(v[4 * i], v[4 * i + 1], b.x, b.y);
+                  add2(v[4 * i + 2], v[4 * i + 3], b.z, b.w);
                 }
               }
             }
@@ -632,7 +640,11 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
               if (slope01) {
                 // for 0 <= a <= 1: PReLU(v) = max(v, a*v) exactly (two instructions per element instead of three)
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], pr.fwd * v[i]);
+                for (int i = 0; i < 32; i += 2) {
+                  const float2 t = __fmul2_rn(make_float2(v[i], v[i + 1]), make_float2(pr.fwd, pr.fwd));
+                  v[i] = fmaxf(v[i], t.x);
+                  v[i + 1] = fmaxf(v[i + 1], t.y);
+                }
               } else {
                 if (pr.tag) {
 #pragma unroll
