@@ -54,6 +54,14 @@ class VSRTrainStep:
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         self._comm_stream, self._comm_pending = None, False
+        # "overlap": range k is all-reduced on a side stream while the weight gradients of range k + 1 run;
+        # "serial": ONE all-reduce of the whole bucket on the compute stream after backward.  (NCCL's CTAs take SMs
+        # away from the persistent one-CTA-per-SM weight-gradient kernels running beside them, whose displaced CTAs
+        # then run as a second wave - the overlap can cost as much as the exchange it hides.)
+        # Measured equal on 2 GPUs (10.97 ms per step both ways, profiles/r02c_2gpu_{overlap,serial}.json).
+        self.comm_mode = os.environ.get("VSR_COMM_MODE", "overlap")
+        if self.comm_mode not in ("overlap", "serial"):
+            raise ValueError(f"VSR_COMM_MODE must be 'overlap' or 'serial', not {self.comm_mode!r}")
         if isinstance(optimizer, FlatAdam):
             optimizer.bind(net)
             optimizer.grad_scale = 1.0 / self.world
@@ -143,7 +151,10 @@ class VSRTrainStep:
         eng.pack(net.flat, need_bwd=True)
         outs, saved = eng.forward(inputs, save=True)
         lvals, grads = self._loss(outs, targets, True)
-        gflat = eng.backward(saved, grads, on_bucket=self._reduce_bucket if self.world > 1 else None)
+        overlap = self.world > 1 and self.comm_mode == "overlap"
+        gflat = eng.backward(saved, grads, on_bucket=self._reduce_bucket if overlap else None)
+        if self.world > 1 and not overlap:
+            dist.all_reduce(gflat, group=self.pg)
         net.flat_grad = gflat
         return lvals, outs, gflat
 
