@@ -299,15 +299,17 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
   // Everything above reads only launch-time constants (tables uploaded when the layer plan was built,
   // kernel arguments) and this CTA's own shared / tensor memory; tensors written by earlier kernels
   // are touched only below this point.
-  ptx::pdl_wait();
-  if (bias_in_smem)
-    for (int i = threadIdx.x; i < a.Cout; i += blockDim.x) bias_s[i] = __ldg(a.bias + i);
+  // The CTA-wide (pair-wide) synchronisation belongs to the prologue as well: after pdl_wait() the producers issue their
+  // first loads at once.  (The bias - packed by an earlier kernel of the step - used to be staged by all threads between the
+  // wait and this synchronisation: one global-load latency on the critical path of every launch.  Only the epilogue warps
+  // need it; they stage it among themselves below while the first loads and MMAs are in flight.)
   ptx::tc_fence_before();
   if (PAIR) ptx::cluster_sync();       // the peer's barriers are initialised before anything arrives on them
   else __syncthreads();
   ptx::tc_fence_after();
-  ptx::pdl_launch_dependents();
   const uint32_t tmem_base = *tmem_slot_gen;
+  ptx::pdl_wait();
+  ptx::pdl_launch_dependents();
   const uint64_t g_t1 = kAttrib ? ptx::globaltimer_ns() : 0;
 
   if (warp < kProducers) {
@@ -498,6 +500,10 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
     // ===================== epilogue (8 warps: TMEM lane quarter x chunk parity) =====================
     const int ew = warp - kEpiWarp0;
     const int quarter = warp & 3;                 // TMEM lanes [32*quarter, 32*quarter+32) = tile pixels
+    if (bias_in_smem) {
+      for (int i = ew * 32 + lane; i < a.Cout; i += kEpiWarps * 32) bias_s[i] = __ldg(a.bias + i);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
     // nt > 64: the two warps of a lane quarter split every tile by chunk parity (c = 64*chalf mod 128);
     // nt == 64 (one chunk per tile): they alternate tiles instead, i.e. warp set `chalf` owns TMEM
     // buffer `chalf`, which doubles the time each warp has to hide its operand loads
@@ -791,7 +797,9 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
         else ptx::mbar_arrive(tempty_bar + 8 * buf);
       }
     }
-    if (lane == 0) bulk_wait0();                 // all output bytes are written before the CTA retires
+    // all output bytes are written before the CTA retires (waiting only for the TMA unit to have READ the staging tiles -
+    // cp.async.bulk.wait_group.read - measured the same step time on one box, so the stronger wait stays)
+    if (lane == 0) bulk_wait0();
     if (prof && blockIdx.x == 0 && lane == 0 && (ew & 3) == 0)
       printf("tc2-prof epilogue warp %d: total %lld cyc, wait(tfull) %lld, operands %lld, tmem-ld %lld, math %lld, pack+sts %lld, fence+issue %lld\n",
              warp, clock64() - e_t0, e_wait, e_in, e_ld, e_math, e_st, e_iss);
