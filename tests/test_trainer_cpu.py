@@ -89,8 +89,8 @@ def test_flat_adam_state_dict_roundtrip():
     assert torch.equal(net.flat, net2.flat)
 
 
-def _dp_worker(rank, world, port, path, q):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+def _dp_worker(rank, world, port, path, q, comm_mode="overlap"):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), VSR_COMM_MODE=comm_mode)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.set_num_threads(1)
     fx = torch.load(path)
@@ -107,7 +107,9 @@ def _dp_worker(rank, world, port, path, q):
     dist.destroy_process_group()
 
 
-def test_two_rank_data_parallel_equals_single_rank():
+@pytest.mark.parametrize("comm_mode", ["overlap", "serial"])
+def test_two_rank_data_parallel_equals_single_rank(comm_mode):
+    # overlap: bucket-by-bucket all-reduce from the engine's callback; serial: one all-reduce after backward
     path = os.path.join(GOLDEN, "drfnet_f8_g2_x2.pt")   # batch of 2 -> one sample per rank
     fx = torch.load(path)
     net, opt, step = _setup(fx)
@@ -115,8 +117,8 @@ def test_two_rank_data_parallel_equals_single_rank():
         step.train_step(fx["inputs"], fx["targets"])
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + os.getpid() % 2000
-    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, path, q)) for r in range(2)]
+    port = 29500 + os.getpid() % 2000 + (7 if comm_mode == "serial" else 0)
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, path, q, comm_mode)) for r in range(2)]
     for p in procs:
         p.start()
     flat = torch.from_numpy(q.get(timeout=180))
