@@ -500,10 +500,6 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
     // ===================== epilogue (8 warps: TMEM lane quarter x chunk parity) =====================
     const int ew = warp - kEpiWarp0;
     const int quarter = warp & 3;                 // TMEM lanes [32*quarter, 32*quarter+32) = tile pixels
-    if (bias_in_smem) {
-      for (int i = ew * 32 + lane; i < a.Cout; i += kEpiWarps * 32) bias_s[i] = __ldg(a.bias + i);
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-    }
     // nt > 64: the two warps of a lane quarter split every tile by chunk parity (c = 64*chalf mod 128);
     // nt == 64 (one chunk per tile): they alternate tiles instead, i.e. warp set `chalf` owns TMEM
     // buffer `chalf`, which doubles the time each warp has to hide its operand loads
@@ -562,6 +558,11 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_tc2_kernel(const __grid_c
     for (int d = 0; d < ibuf && la_ok; ++d) {
       if (lane == 0) issue_chunk(la, d);
       la_ok = next_chunk(la);
+    }
+    // (after the operand prefetch above: the bias load must not delay it)
+    if (bias_in_smem) {
+      for (int i = ew * 32 + lane; i < a.Cout; i += kEpiWarps * 32) bias_s[i] = __ldg(a.bias + i);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
     }
     uint32_t q = 0;                                // chunks processed by this warp
     int it = 0;
