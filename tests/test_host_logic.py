@@ -307,3 +307,33 @@ def test_split_ops_plane_cache_invalidation():
         assert not ops._cache, name                           # may write a map: everything is re-split
     t3 = SplitOps.table3(__import__("vsr_b200.ops", fromlist=["TapTable"]).TapTable(64, 64, [(0, [(0, 0, 0, 0), (1, 1, -1, 64)])]))
     assert t3.groups == [(0, [(0, 0, 0, 0), (1, 1, -1, 64), (8, 0, 0, 0), (9, 1, -1, 64), (0, 0, 0, 0), (1, 1, -1, 64)])]
+
+
+def test_flat_bucket_check_is_cached_and_invalidated():
+    """`_is_flat` runs twice per training step: the walk over the module tree is repeated only after a parameter was
+    registered somewhere; a re-pointed `.data`, a replaced Parameter object and `load_state_dict(assign=True)` are all
+    detected, in-place loads and dtype moves keep the bucket."""
+    import torch.nn as nn
+    from vsr_b200.nets import DRFNet
+    net = DRFNet(in_channels=1, out_channels=1, num_features=8, num_groups=2, upscale_factor=2)
+    assert net._is_flat() and net._flat_cache is not None
+    cached = net._flat_cache
+    assert net._is_flat() and net._flat_cache is cached           # second call: pointer comparison only
+    p0 = next(net.parameters())
+    p0.data = p0.data.clone()
+    assert not net._is_flat()
+    net._flatten()
+    assert net._is_flat()
+    net.in_block.conv1.weight = nn.Parameter(net.in_block.conv1.weight.detach().clone())
+    assert not net._is_flat()
+    net._flatten()
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    net.load_state_dict(sd)
+    assert net._is_flat()
+    net.load_state_dict(sd, assign=True)
+    assert not net._is_flat()
+    net._flatten()
+    net.double()
+    assert net._is_flat() and net.flat.dtype == torch.float64
+    for p, ref in zip(net.parameters(), net._plan.params.values()):
+        assert p.data_ptr() == net.flat.data_ptr() + ref.offset * net.flat.element_size()

@@ -24,6 +24,19 @@ _PRECISIONS = {"fp32": torch.float32, "bf16": torch.bfloat16, "bf16x3": torch.fl
 _TC_LAYOUT = ("bf16", "bf16x3", "tf32")      # plans with 64-channel taps and swizzled bf16 weight slabs
 
 
+# Bumped whenever ANY module registers a parameter (`module.weight = nn.Parameter(...)`, `load_state_dict(assign=True)`):
+# `_DRFBase._is_flat` repeats its walk over the module tree only then.
+_PARAM_EPOCH = [0]
+
+
+def _on_parameter_registration(module, name, param):
+    _PARAM_EPOCH[0] += 1
+    return None
+
+
+nn.modules.module.register_module_parameter_registration_hook(_on_parameter_registration)
+
+
 class TripledSlabs:
     """A weight buffer of the bf16x3 mode addressed with the plan's own offsets: every layer's slabs are stored three times
     over ([wh | wh | wl] per group, DrfPlan.split_index), so the plan's [w_off, w_off + w_numel) is [3 w_off, 3 (w_off + w_numel))"""
@@ -190,6 +203,7 @@ class _DRFBase(BaseNet):
         self._engine = None
         self._ops = None          # tests may set an emulated backend here; product uses CudaOps
         self.flat = None
+        self._flat_cache = None
         self.flat_grad = None
         self._flatten()
 
@@ -203,15 +217,30 @@ class _DRFBase(BaseNet):
             flat[ref.offset:ref.offset + n].copy_(p.data.reshape(-1))
             p.data = flat[ref.offset:ref.offset + n].view(ref.shape)
         self.flat = flat
+        self._flat_cache = None
         if self._engine is not None and (self._engine.device != dev or self._engine.param_dtype != dt):
             self._engine = None
 
     def _is_flat(self):
+        # Called on every step (twice: the step and FlatAdam).  Walking the module tree costs ~180 us for DRFNet-L - host
+        # time the device idles through when the caller reads the loss back every step - so the walk is repeated only after
+        # some module registered a parameter (the global hook below); otherwise the Parameter objects are the ones seen by
+        # the last walk and only their storage pointers are compared (~15 us).
+        c = self._flat_cache
+        if c is not None and c[0] == _PARAM_EPOCH[0] and c[1] is self.flat:
+            for p, e in zip(c[2], c[3]):
+                if p.data_ptr() != e:
+                    return False
+            return True
         base = self.flat.data_ptr()
         es = self.flat.element_size()
+        params, ptrs = [], []
         for p, ref in zip(self.parameters(), self._plan.params.values()):
             if p.data_ptr() != base + ref.offset * es or p.device != self.flat.device:
                 return False
+            params.append(p)
+            ptrs.append(base + ref.offset * es)
+        self._flat_cache = (_PARAM_EPOCH[0], self.flat, params, ptrs)
         return True
 
     def _apply(self, fn, *a, **kw):

@@ -62,6 +62,7 @@ class FlatAdam(torch.optim.Optimizer):
             self._hyper_ev = [None] * self._RING
             if flat.is_cuda:
                 self._hyper_host = [h.pin_memory() for h in self._hyper_host]
+            self._hyper_np = [h.numpy() for h in self._hyper_host]     # views: filled without building a tensor per step
         # The H2D copy below is asynchronous and the host runs ahead of the device (graph replay, one sync per epoch):
         # a pinned buffer is rewritten only after the copy that last read it has executed (ring + events), otherwise
         # step k could see the step count / lr of step k+1.
@@ -69,7 +70,7 @@ class FlatAdam(torch.optim.Optimizer):
         self._hyper_i = (i + 1) % self._RING
         if self._hyper_ev[i] is not None:
             self._hyper_ev[i].synchronize()
-        self._hyper_host[i].copy_(torch.tensor(vals, dtype=torch.float32))
+        self._hyper_np[i][:] = vals
         self._hyper_dev.copy_(self._hyper_host[i], non_blocking=True)
         if flat.is_cuda:
             ev = self._hyper_ev[i] or torch.cuda.Event()
