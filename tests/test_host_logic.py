@@ -316,9 +316,9 @@ def test_flat_bucket_check_is_cached_and_invalidated():
     import torch.nn as nn
     from vsr_b200.nets import DRFNet
     net = DRFNet(in_channels=1, out_channels=1, num_features=8, num_groups=2, upscale_factor=2)
-    assert net._is_flat() and net._flat_cache is not None
-    cached = net._flat_cache
-    assert net._is_flat() and net._flat_cache is cached           # second call: pointer comparison only
+    assert net._is_flat() and net.__dict__.get("_flat_cache") is not None
+    cached = net.__dict__["_flat_cache"]
+    assert net._is_flat() and net.__dict__["_flat_cache"] is cached           # second call: pointer comparison only
     p0 = next(net.parameters())
     p0.data = p0.data.clone()
     assert not net._is_flat()

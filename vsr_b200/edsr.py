@@ -10,6 +10,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
+from . import _flat
 from ._lib import EPI_BIAS, EPI_RELU, EPI_RELU_BWD, EPI_RES_PRE, EPI_SCALE
 from .drf_plan import DrfPlan, Layer, phase_table
 from .nets import _PRECISIONS, _TC_LAYOUT, BaseNet, pack_weights, packed_weight_state
@@ -158,9 +159,7 @@ class EDSRNet(BaseNet):
         self._dev_state = None
 
     def _is_flat(self):
-        base, es = self.flat.data_ptr(), self.flat.element_size()
-        return all(p.data_ptr() == base + r.offset * es and p.device == self.flat.device
-                   for p, r in zip(self.parameters(), self._plan.params.values()))
+        return _flat.is_flat(self)      # cached: the module tree is walked only after a parameter registration
 
     def _apply(self, fn, *a, **kw):
         out = super()._apply(fn, *a, **kw)

@@ -14,6 +14,7 @@ import math
 import torch
 import torch.nn as nn
 
+from . import _flat
 from .drf_engine import DrfEngine
 from .drf_plan import PROJ, DrfPlan
 
@@ -22,19 +23,6 @@ from .drf_plan import PROJ, DrfPlan
 # mode accuracy (<= 1e-4 of the reference) on tensor cores
 _PRECISIONS = {"fp32": torch.float32, "bf16": torch.bfloat16, "bf16x3": torch.float32, "tf32": torch.float32}
 _TC_LAYOUT = ("bf16", "bf16x3", "tf32")      # plans with 64-channel taps and swizzled bf16 weight slabs
-
-
-# Bumped whenever ANY module registers a parameter (`module.weight = nn.Parameter(...)`, `load_state_dict(assign=True)`):
-# `_DRFBase._is_flat` repeats its walk over the module tree only then.
-_PARAM_EPOCH = [0]
-
-
-def _on_parameter_registration(module, name, param):
-    _PARAM_EPOCH[0] += 1
-    return None
-
-
-nn.modules.module.register_module_parameter_registration_hook(_on_parameter_registration)
 
 
 class TripledSlabs:
@@ -203,7 +191,6 @@ class _DRFBase(BaseNet):
         self._engine = None
         self._ops = None          # tests may set an emulated backend here; product uses CudaOps
         self.flat = None
-        self._flat_cache = None
         self.flat_grad = None
         self._flatten()
 
@@ -217,31 +204,11 @@ class _DRFBase(BaseNet):
             flat[ref.offset:ref.offset + n].copy_(p.data.reshape(-1))
             p.data = flat[ref.offset:ref.offset + n].view(ref.shape)
         self.flat = flat
-        self._flat_cache = None
         if self._engine is not None and (self._engine.device != dev or self._engine.param_dtype != dt):
             self._engine = None
 
     def _is_flat(self):
-        # Called on every step (twice: the step and FlatAdam).  Walking the module tree costs ~180 us for DRFNet-L - host
-        # time the device idles through when the caller reads the loss back every step - so the walk is repeated only after
-        # some module registered a parameter (the global hook below); otherwise the Parameter objects are the ones seen by
-        # the last walk and only their storage pointers are compared (~15 us).
-        c = self._flat_cache
-        if c is not None and c[0] == _PARAM_EPOCH[0] and c[1] is self.flat:
-            for p, e in zip(c[2], c[3]):
-                if p.data_ptr() != e:
-                    return False
-            return True
-        base = self.flat.data_ptr()
-        es = self.flat.element_size()
-        params, ptrs = [], []
-        for p, ref in zip(self.parameters(), self._plan.params.values()):
-            if p.data_ptr() != base + ref.offset * es or p.device != self.flat.device:
-                return False
-            params.append(p)
-            ptrs.append(base + ref.offset * es)
-        self._flat_cache = (_PARAM_EPOCH[0], self.flat, params, ptrs)
-        return True
+        return _flat.is_flat(self)      # cached: the module tree is walked only after a parameter registration
 
     def _apply(self, fn, *a, **kw):
         out = super()._apply(fn, *a, **kw)     # .to(device) / .double(): params moved in place

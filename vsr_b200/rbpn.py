@@ -25,6 +25,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
+from . import _flat
 from ._lib import EPI_BIAS, EPI_OUT2, EPI_OUT2_SUB, EPI_PRELU, EPI_RES_PRE
 from .drf_plan import MAX_NT, PROJ, DrfPlan, Layer, _split_nt, phase_table
 from .nets import _PRECISIONS, _TC_LAYOUT, BaseNet, pack_weights, packed_weight_state
@@ -358,9 +359,7 @@ class RBPNet(BaseNet):
         self._dev_state = None
 
     def _is_flat(self):
-        base, es = self.flat.data_ptr(), self.flat.element_size()
-        return all(p.data_ptr() == base + r.offset * es and p.device == self.flat.device
-                   for p, r in zip(self.parameters(), self._plan.params.values()))
+        return _flat.is_flat(self)      # cached: the module tree is walked only after a parameter registration
 
     def _apply(self, fn, *a, **kw):
         out = super()._apply(fn, *a, **kw)
